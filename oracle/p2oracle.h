@@ -1,0 +1,123 @@
+/* p2oracle.h — CPU oracle for the Plonky2 proving hot path behind City Rollup worker jobs.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (city_rollup_b200/, include/) may
+ * include, link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference leg use it, as the checker / the reported CPU baseline.
+ *
+ * What it restates: the reference (QEDProtocol/city-rollup) reaches this path only through
+ * `circuit_data.prove(pw)` (e.g. city_common_circuit/src/proof_minifier/pm_core.rs:151); the
+ * arithmetic lives in the un-vendored git dependency plonky2 0.2.2 @ QEDProtocol/plonky2-hwa
+ * rev 6a8ca008 (Cargo.toml:101-102, Cargo.lock:4174-4223), which is NOT on disk.  This file
+ * therefore restates the published plonky2 0.2.2 algorithms and is pinned
+ * against every known answer the reference tree itself holds for the path:
+ *   K1/K2 city_crypto/src/hash/cached_zero_hashes.rs:10-1036,1039-2066 (Poseidon permutation, sponge)
+ *   K3    qbench_data/example.bin (10 stored proofs: Merkle leaf/path/cap conventions, FRI folds)
+ *   K4/K5 city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145 (generator 7, FRI params)
+ * PARITY STATUS: Poseidon / sponge / Merkle / FRI-fold conventions are pinned by those vectors;
+ * NTT/LDE values, caps of given polynomials and the transcript are NOT pinned by any reference
+ * test or fixture — for those this oracle is "parity unpinned" beyond exactness
+ * of field arithmetic and the self-consistency checks in tests/.
+ */
+#ifndef P2ORACLE_H
+#define P2ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_P 0xFFFFFFFF00000001ULL
+#define GL_EPS 0xFFFFFFFFULL /* 2^64 mod p */
+
+/* ---- field (plonky2_field GoldilocksField) ---- */
+uint64_t gl_canon(uint64_t a);
+uint64_t gl_add(uint64_t a, uint64_t b);
+uint64_t gl_sub(uint64_t a, uint64_t b);
+uint64_t gl_mul(uint64_t a, uint64_t b);
+uint64_t gl_pow(uint64_t a, uint64_t e);
+uint64_t gl_inv(uint64_t a);
+uint64_t gl_root_of_unity(unsigned log_n); /* primitive 2^log_n-th root, plonky2 convention */
+/* quadratic extension F[X]/(X^2-7); element = {c0,c1} */
+void gl2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+void gl2_inv(const uint64_t a[2], uint64_t out[2]);
+
+/* ---- Poseidon ---- */
+void poseidon_permute(uint64_t state[12]);
+void poseidon_hash_no_pad(const uint64_t *in, size_t len, uint64_t out[4]);
+void poseidon_hash_or_noop(const uint64_t *in, size_t len, uint64_t out[4]);
+void poseidon_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+
+/* ---- Merkle tree (plonky2 hash/merkle_tree.rs) ----
+ * leaves: row-major n_leaves x leaf_len.  digests_out: 2*(n_leaves - 2^cap_height) digests of 4
+ * u64 in plonky2's interleaved layout.  cap_out: 2^cap_height digests. */
+void merkle_tree_new(const uint64_t *leaves, size_t n_leaves, size_t leaf_len, unsigned cap_height,
+                     uint64_t *digests_out, uint64_t *cap_out);
+/* siblings_out: (log2(n_leaves)-cap_height) digests, leaf level first. */
+void merkle_prove(const uint64_t *digests, size_t n_leaves, unsigned cap_height, size_t leaf_index,
+                  uint64_t *siblings_out);
+/* returns 1 if the path leads to cap[leaf_index >> n_siblings] */
+int merkle_verify(const uint64_t *leaf, size_t leaf_len, size_t leaf_index, const uint64_t *siblings,
+                  unsigned n_siblings, const uint64_t *cap);
+
+/* ---- FFT (plonky2_field fft.rs / polynomial/mod.rs) ---- all natural order ---- */
+void gl_fft(uint64_t *a, unsigned log_n);                    /* coeffs -> values, in place */
+void gl_ifft(uint64_t *a, unsigned log_n);                   /* values -> coeffs, in place */
+void gl_coset_fft(uint64_t *a, unsigned log_n, uint64_t shift);
+void gl_coset_ifft(uint64_t *a, unsigned log_n, uint64_t shift);
+void gl2_coset_fft(uint64_t *a /* n ext elems, interleaved */, unsigned log_n, uint64_t shift);
+
+/* ---- PolynomialBatch (plonky2 fri/oracle.rs) ----
+ * cols: n_cols pointers to 2^log_n u64 each.  Outputs (each may be NULL to skip):
+ *   coeffs_out  n_cols x n (column-major, natural order)   [from_values only]
+ *   leaves_out  (n<<rate_bits) x n_cols row-major, row j = LDE row bitrev(j) on coset 7*<w>
+ *   digests_out 2*((n<<rate_bits) - 2^cap_height) x 4, plonky2 layout;  cap_out 2^cap_height x 4
+ * blinding (salted) batches are not used by any worker circuit and not restated. */
+void batch_from_coeffs(const uint64_t *const *cols, size_t n_cols, unsigned log_n, unsigned rate_bits,
+                       unsigned cap_height, uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
+void batch_from_values(const uint64_t *const *cols, size_t n_cols, unsigned log_n, unsigned rate_bits,
+                       unsigned cap_height, uint64_t *coeffs_out, uint64_t *leaves_out,
+                       uint64_t *digests_out, uint64_t *cap_out);
+
+/* ---- Challenger (plonky2 iop/challenger.rs) ---- */
+typedef struct {
+  uint64_t state[12];
+  uint64_t in[8];
+  uint64_t out[8];
+  unsigned n_in, n_out;
+} p2o_challenger;
+void challenger_init(p2o_challenger *c);
+void challenger_observe(p2o_challenger *c, const uint64_t *elems, size_t n);
+uint64_t challenger_get(p2o_challenger *c);
+
+/* ---- FRI commit phase + PoW (plonky2 fri/prover.rs) ----
+ * coeffs/values: len ext elements (interleaved c0,c1), values in natural order on coset 7*<w_len>.
+ * Per layer i (arity 2^arity_bits[i]): the tree is built over bit-reversed values chunked by arity.
+ * Outputs: caps_out  n_layers x 2^cap_height x 4;  layer_leaves_out[i] (may be NULL) receives the
+ * layer's leaves row-major (len_i/arity x 2*arity); layer_digests_out[i] likewise (plonky2 layout).
+ * final_poly_out: (len >> sum(arity_bits) >> rate_bits) ext elements.  The challenger is advanced
+ * exactly as fri_committed_trees does (observe cap, squeeze beta, ..., observe final poly). */
+void fri_committed_trees(const uint64_t *coeffs, const uint64_t *values, size_t len,
+                         const unsigned *arity_bits, size_t n_layers, unsigned rate_bits,
+                         unsigned cap_height, p2o_challenger *ch, uint64_t *caps_out,
+                         uint64_t **layer_leaves_out, uint64_t **layer_digests_out,
+                         uint64_t *final_poly_out, uint64_t *betas_out);
+/* smallest witness w such that Poseidon(duplex state with w appended)[7] has >= pow_bits leading
+ * zero bits (the reference picks any valid w via rayon find_any — SURVEY §0.5; we define the
+ * minimum).  Advances the challenger like fri_proof_of_work (observe w, squeeze response). */
+uint64_t fri_proof_of_work(p2o_challenger *ch, unsigned pow_bits);
+/* check used on stored proofs: does w satisfy the PoW for this challenger state? (does not advance) */
+int fri_pow_check(const p2o_challenger *ch, uint64_t w, unsigned pow_bits);
+
+/* arity-2^arity_bits fold of one coset (verifier's compute_evaluation): evals[arity] ext in the
+ * bit-reversed order they are stored in a layer leaf, x_index_within_coset, returns P(beta). */
+void fri_compute_evaluation(uint64_t x /* base-field point of evals[x_index_within_coset] */,
+                            unsigned x_index_within_coset, unsigned arity_bits, const uint64_t *evals,
+                            const uint64_t beta[2], uint64_t out[2]);
+
+unsigned p2o_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/* from the (read-only) reference checkout.
+
+This script is the ONLY thing in the repo that reads /root/reference, and it is
+never run by tests, smoke() or bench.py (the GPU box has no /root/reference).
+It extracts, verbatim, the known-answer data the reference holds for the
+Plonky2 hot path:
+
+  K1/K2  city_crypto/src/hash/cached_zero_hashes.rs:10-1036, :1039-2066
+         -> zero_hashes.json  {"zero": [[4 u64] x128], "marked": [[4 u64] x128]}
+  K3     qbench_data/example.bin (10 stored plonky2 proofs, bincode)
+         -> example_proofs.bin (concatenated proof blobs) + example_proofs.json (index)
+  K4/K5  city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145
+         -> circuit_params.json (FRI/Plonk parameters + the 80 k_is)
+
+Usage:  python tests/golden/make_golden.py [/root/reference]
+"""
+import json
+import os
+import re
+import struct
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def zero_hash_tables():
+    src = open(os.path.join(REF, "city_crypto/src/hash/cached_zero_hashes.rs")).read()
+    # four consts in the file; the first two are the HashOut tables, the last two are
+    # QHashOut copies.  Split on the const declarations.
+    parts = re.split(r"const CACHED_(?:MARKED_LEAF_)?ZERO_HASHES", src)[1:]
+    tables = []
+    for p in parts:
+        nums = [int(x) for x in re.findall(r"GoldilocksField\((\d+)\)", p)]
+        assert len(nums) == 128 * 4, len(nums)
+        tables.append([nums[i : i + 4] for i in range(0, 512, 4)])
+    assert tables[0] == tables[2] and tables[1] == tables[3]
+    return {"zero": tables[0], "marked": tables[1],
+            "source": "city_crypto/src/hash/cached_zero_hashes.rs:10-1036,1039-2066"}
+
+
+def example_proofs():
+    d = open(os.path.join(REF, "qbench_data/example.bin"), "rb").read()
+    off = 8 + 4 + 48  # checkpoint_id u64, rpc_node_id u32, CityOpJobConfig 6xu64
+    (n,) = struct.unpack_from("<Q", d, off)
+    off += 8
+    blobs, index = [], []
+    pos = 0
+    for _ in range(n):
+        kid = d[off : off + 24]
+        off += 24
+        (l,) = struct.unpack_from("<Q", d, off)
+        off += 8
+        if l > 100000:  # the ten stored ProofWithPublicInputs blobs
+            blobs.append(d[off : off + l])
+            index.append({"job_id": kid.hex(), "circuit_type": kid[9], "offset": pos, "len": l})
+            pos += l
+        off += l
+    assert len(blobs) == 10
+    return b"".join(blobs), {"proofs": index, "source": "qbench_data/example.bin"}
+
+
+def circuit_params():
+    src = open(os.path.join(REF, "city_common_circuit/src/circuits/zk_signature2/mod.rs")).read()
+    body = src[src.index("pub fn get_verifier_template_zk_signature") :]
+    body = body[: body.index("\n}\n")]
+    kis = [int(x) for x in re.findall(r"^\s+(\d+),\s*$", body[body.index("k_is") :], re.M)]
+    assert len(kis) == 80, len(kis)
+
+    def field(name):
+        return int(re.search(name + r":\s*(\d+)", body).group(1))
+
+    arity = re.search(r"ConstantArityBits\((\d+),\s*(\d+)\)", body)
+    return {
+        "source": "city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145",
+        "rate_bits": field("rate_bits"),
+        "cap_height": field("cap_height"),
+        "proof_of_work_bits": field("proof_of_work_bits"),
+        "constant_arity_bits": [int(arity.group(1)), int(arity.group(2))],
+        "num_query_rounds": field("num_query_rounds"),
+        "degree_bits": field("degree_bits"),
+        "reduction_arity_bits": [int(x) for x in re.search(r"reduction_arity_bits:\s*vec!\[([^\]]*)\]", body).group(1).split(",")],
+        "num_leaves_per_oracle": [int(x) for x in re.search(r"num_leaves_per_oracle:\s*vec!\[([^\]]*)\]", body).group(1).split(",")],
+        "num_challenges": field("num_challenges"),
+        "num_constants": field("num_constants"),
+        "num_routed_wires": field("num_routed_wires"),
+        "num_wires": field("num_wires"),
+        "num_quotient_polys": field("num_quotient_polys"),
+        "quotient_degree_factor": field("quotient_degree_factor"),
+        "num_gate_constraints": field("num_gate_constraints"),
+        "num_partial_products": field("num_partial_products"),
+        "total_partial_products": field("total_partial_products"),
+        "k_is": kis,
+    }
+
+
+if __name__ == "__main__":
+    json.dump(zero_hash_tables(), open(os.path.join(OUT, "zero_hashes.json"), "w"))
+    blob, idx = example_proofs()
+    open(os.path.join(OUT, "example_proofs.bin"), "wb").write(blob)
+    json.dump(idx, open(os.path.join(OUT, "example_proofs.json"), "w"), indent=1)
+    json.dump(circuit_params(), open(os.path.join(OUT, "circuit_params.json"), "w"), indent=1)
+    print("golden fixtures written to", OUT)
