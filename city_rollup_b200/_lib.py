@@ -1,0 +1,93 @@
+"""ctypes binding of libp2b.so (include/p2b.h).  Loading fails loudly when the CUDA library has not
+been built; there is no CPU fallback (the oracle under oracle/ is test infrastructure only)."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libp2b.so")
+
+u64 = C.c_uint64
+u64p = C.POINTER(C.c_uint64)
+u32 = C.c_uint32
+vp = C.c_void_p
+sz = C.c_size_t
+
+# name -> (restype, argtypes).  Every symbol include/p2b.h declares is listed here
+# (tests/test_abi.py checks the header against this table and against the built library).
+SIGNATURES = {
+    "p2b_version": (C.c_int, []),
+    "p2b_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "p2b_init_on_stream": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+    "p2b_destroy": (None, [vp]),
+    "p2b_last_error": (C.c_char_p, [vp]),
+    "p2b_synchronize": (C.c_int, [vp]),
+    "p2b_host_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
+    "p2b_host_free": (C.c_int, [vp, vp]),
+    "p2b_launch_count": (u64, [vp]),
+    "p2b_timer_start": (C.c_int, [vp]),
+    "p2b_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "p2b_batch_from_values": (C.c_int, [vp, C.POINTER(u64p), sz, u32, u32, u32, u32, C.POINTER(vp)]),
+    "p2b_batch_from_coeffs": (C.c_int, [vp, C.POINTER(u64p), sz, u32, u32, u32, u32, C.POINTER(vp)]),
+    "p2b_batch_from_values_dev": (C.c_int, [vp, vp, sz, u32, u32, u32, u32, C.POINTER(vp)]),
+    "p2b_batch_from_coeffs_dev": (C.c_int, [vp, vp, sz, u32, u32, u32, u32, C.POINTER(vp)]),
+    "p2b_batch_free": (None, [vp]),
+    "p2b_batch_n_cols": (sz, [vp]),
+    "p2b_batch_degree_log": (u32, [vp]),
+    "p2b_batch_rate_bits": (u32, [vp]),
+    "p2b_batch_tree": (vp, [vp]),
+    "p2b_batch_cap": (C.c_int, [vp, u64p]),
+    "p2b_batch_coeffs": (C.c_int, [vp, sz, u64p]),
+    "p2b_batch_leaf": (C.c_int, [vp, sz, u64p]),
+    "p2b_batch_lde_values": (C.c_int, [vp, sz, sz, u64p]),
+    "p2b_batch_leaves": (C.c_int, [vp, u64p]),
+    "p2b_batch_dev_lde": (vp, [vp]),
+    "p2b_batch_dev_coeffs": (vp, [vp]),
+    "p2b_merkle_new": (C.c_int, [vp, u64p, sz, sz, u32, C.POINTER(vp)]),
+    "p2b_tree_free": (None, [vp]),
+    "p2b_tree_n_leaves": (sz, [vp]),
+    "p2b_tree_cap_height": (u32, [vp]),
+    "p2b_tree_cap": (C.c_int, [vp, u64p]),
+    "p2b_tree_prove": (C.c_int, [vp, sz, u64p]),
+    "p2b_tree_digests": (C.c_int, [vp, u64p]),
+    "p2b_tree_leaf": (C.c_int, [vp, sz, u64p]),
+    "p2b_poseidon_permute": (C.c_int, [vp, u64p, sz]),
+    "p2b_hash_no_pad": (C.c_int, [vp, u64p, sz, u64p]),
+    "p2b_two_to_one": (C.c_int, [vp, u64p, u64p, sz, u64p]),
+    "p2b_challenger_new": (C.c_int, [vp, C.POINTER(vp)]),
+    "p2b_challenger_free": (None, [vp]),
+    "p2b_challenger_observe": (C.c_int, [vp, u64p, sz]),
+    "p2b_challenger_observe_cap": (C.c_int, [vp, vp]),
+    "p2b_challenger_get": (C.c_int, [vp, sz, u64p]),
+    "p2b_challenger_export": (C.c_int, [vp, u64p]),
+    "p2b_challenger_import": (C.c_int, [vp, u64p]),
+    "p2b_fri_commit": (C.c_int, [vp, u64p, u64p, sz, C.POINTER(u32), sz, u32, u32, vp, C.POINTER(vp), u64p]),
+    "p2b_fri_pow": (C.c_int, [vp, vp, u32, u64p]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a into city_rollup_b200/libp2b.so (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc")]
+    if not verbose:
+        args.append("-s")
+    subprocess.check_call(args)
+    return SO_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the CUDA path)")
+        lib = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

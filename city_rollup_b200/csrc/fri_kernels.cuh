@@ -1,0 +1,120 @@
+// fri_kernels.cuh — device-resident Challenger, FRI arity folding, proof-of-work grinding.
+//
+// Replaces plonky2 0.2.2 iop/challenger.rs (Challenger<F, PoseidonHash>), fri/prover.rs
+// (fri_committed_trees' fold `reduce_with_powers(chunk, beta)`, fri_proof_of_work) — SURVEY.md A.7/A.9;
+// FRI parameters as dumped at city_common_circuit/src/circuits/zk_signature2/mod.rs:38-50.
+// The transcript state lives in HBM and is advanced by single-thread kernels, so the commit loop
+// (tree -> observe cap -> beta -> fold -> coset NTT) never synchronises with the host.
+#pragma once
+#include "poseidon.cuh"
+
+namespace frik {
+
+// Challenger state: sponge_state[12] | n_in | input_buffer[8] | n_out | output_buffer[8]
+constexpr int CH_WORDS = 30;
+constexpr int CH_NIN = 12, CH_IN = 13, CH_NOUT = 21, CH_OUT = 22;
+
+__device__ __forceinline__ void duplexing(uint64_t* st) {
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = st[i];
+  uint32_t n_in = (uint32_t)st[CH_NIN];
+  for (uint32_t i = 0; i < n_in; i++) s[i] = st[CH_IN + i];  // overwrite mode
+  poseidon::permute(s);
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = s[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) st[CH_OUT + i] = s[i];
+  st[CH_NIN] = 0;
+  st[CH_NOUT] = 8;
+}
+
+// Challenger::observe_elements
+__global__ void k_challenger_observe(uint64_t* __restrict__ st, const uint64_t* __restrict__ elems, size_t n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (size_t i = 0; i < n; i++) {
+    st[CH_NOUT] = 0;
+    uint32_t k = (uint32_t)st[CH_NIN];
+    st[CH_IN + k] = gl::canon(elems[i]);
+    st[CH_NIN] = k + 1;
+    if (k + 1 == 8) duplexing(st);
+  }
+}
+
+// Challenger::get_n_challenges
+__global__ void k_challenger_get(uint64_t* __restrict__ st, size_t n, uint64_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (size_t i = 0; i < n; i++) {
+    if (st[CH_NIN] != 0 || st[CH_NOUT] == 0) duplexing(st);
+    uint32_t k = (uint32_t)st[CH_NOUT] - 1;
+    out[i] = st[CH_OUT + k];
+    st[CH_NOUT] = k;
+  }
+}
+
+__global__ void k_deinterleave(const uint64_t* __restrict__ in, size_t len, uint64_t* __restrict__ c0,
+                               uint64_t* __restrict__ c1) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  ulonglong2 v = reinterpret_cast<const ulonglong2*>(in)[i];
+  c0[i] = gl::canon(v.x);
+  c1[i] = gl::canon(v.y);
+}
+__global__ void k_interleave(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1, size_t len,
+                             uint64_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  reinterpret_cast<ulonglong2*>(out)[i] = make_ulonglong2(c0[i], c1[i]);
+}
+// out[j] = in[bitrev(j)] for interleaved extension elements (reverse_index_bits_in_place)
+__global__ void k_bitrev_ext(const uint64_t* __restrict__ in, uint32_t log_len, uint64_t* __restrict__ out) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >> log_len) return;
+  size_t r = log_len ? (size_t)(__brevll((unsigned long long)j) >> (64 - log_len)) : 0;
+  ulonglong2 v = reinterpret_cast<const ulonglong2*>(in)[r];
+  reinterpret_cast<ulonglong2*>(out)[j] = make_ulonglong2(gl::canon(v.x), gl::canon(v.y));
+}
+
+// coeffs'[i] = sum_{j < arity} coeffs[i*arity + j] * beta^j   (Horner from the top coefficient)
+__global__ void __launch_bounds__(256)
+k_fold_coeffs(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1, size_t len, uint32_t arity_bits,
+              const uint64_t* __restrict__ beta, uint64_t* __restrict__ o0, uint64_t* __restrict__ o1) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (len >> arity_bits)) return;
+  const uint32_t arity = 1u << arity_bits;
+  gl::ext2 b{beta[0], beta[1]};
+  gl::ext2 acc{0, 0};
+  for (uint32_t j = arity; j-- > 0;) {
+    acc = gl::ext_mul(acc, b);
+    size_t k = (i << arity_bits) + j;
+    acc = gl::ext_add(acc, gl::ext2{c0[k], c1[k]});
+  }
+  o0[i] = acc.c0;
+  o1[i] = acc.c1;
+}
+
+// fri_proof_of_work: candidate w = base + thread; the duplex state is the sponge state with the pending
+// inputs written over its head and w at position n_in; response = state[7] after one permutation.
+__global__ void __launch_bounds__(256)
+k_pow_search(const uint64_t* __restrict__ st, uint64_t base, uint64_t count, uint32_t pow_bits,
+             unsigned long long* __restrict__ best) {
+  uint64_t off = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (off >= count) return;
+  uint64_t w = base + off;
+  if (w >= GL_P) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = st[i];
+  uint32_t n_in = (uint32_t)st[CH_NIN];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if ((uint32_t)i < n_in) s[i] = st[CH_IN + i];
+    if ((uint32_t)i == n_in) s[i] = w;
+  }
+  poseidon::permute_nc(s);
+  uint64_t resp = gl::canon(s[7]);
+  bool ok = pow_bits == 0 || (resp >> (64 - pow_bits)) == 0;
+  if (ok) atomicMin(best, (unsigned long long)w);
+}
+
+}  // namespace frik

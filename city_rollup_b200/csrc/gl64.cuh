@@ -1,0 +1,127 @@
+// gl64.cuh — Goldilocks field (p = 2^64 - 2^32 + 1) on the sm_100a integer pipes.
+//
+// Replaces plonky2_field 0.2.2 GoldilocksField (the type every reference call site instantiates:
+// `type F = GoldilocksField`, city_rollup_core_worker/src/lib.rs:25-26).  Elements are raw u64,
+// inputs may be non-canonical (>= p), stored outputs are canonical.
+//
+// Design: a 64x64 product is 4 32x32 IMAD(.WIDE/.HI) with the carries kept in predicate chains
+// (mad.lo.cc/madc.hi.cc), and the 128->64 reduction uses 2^64 = 2^32-1, 2^96 = -1 (mod p) with both
+// conditional corrections done branch-free through the carry flag (subc/addc masks).  ptxas emits
+// 18 integer instructions per multiplication (7 on the FMA pipe, 11 on the ALU pipe).
+// The sub.cc -> subc mask idiom is used only after subtract chains (where it is well defined).
+#pragma once
+#include <cstdint>
+
+#define GL_P 0xFFFFFFFF00000001ull
+#define GL_EPS 0xFFFFFFFFull
+
+namespace gl {
+
+__device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// any u64 -> canonical
+__device__ __forceinline__ uint64_t canon(uint64_t a) { return a >= GL_P ? a - GL_P : a; }
+
+// (a*b) mod p, any u64 inputs; result is a u64 congruent to the product, NOT necessarily < p.
+__device__ __forceinline__ uint64_t mul_nc(uint64_t a, uint64_t b) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,m,tl,th;\n\t"
+      // 128-bit product x3:x2:x1:x0
+      "mul.lo.u32 x0, %2, %4;\n\t"
+      "mul.hi.u32 x1, %2, %4;\n\t"
+      "mul.lo.u32 x2, %3, %5;\n\t"
+      "mul.hi.u32 x3, %3, %5;\n\t"
+      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+      "madc.hi.cc.u32 x2, %2, %5, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      // t = (x1:x0) - x3; on borrow subtract EPS (2^64 = EPS mod p)
+      "sub.cc.u32 tl, x0, x3;\n\t"
+      "subc.cc.u32 th, x1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 tl, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      // r = t + x2*EPS; on carry add EPS = (c<<32) - c.  NOTE: the carry of an add chain must not be
+      // turned into a mask with `subc` — ptxas keeps the raw adder carry in CC.CF, so add.cc -> subc
+      // yields the complemented mask.  addc materialises c unambiguously and ptxas fuses the three
+      // trailing ops into SEL + IADD3 + IADD3.X.
+      "mad.lo.cc.u32 tl, x2, 0xFFFFFFFF, tl;\n\t"
+      "madc.hi.cc.u32 th, x2, 0xFFFFFFFF, th;\n\t"
+      "addc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      "add.u32 %1, th, m;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack(r0, r1);
+}
+
+__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return canon(mul_nc(a, b)); }
+
+// a + b mod p; requires a + b < 2^65 - 2^32 (true when at least one operand is canonical).
+// Result is a u64 congruent to the sum, not necessarily canonical.
+__device__ __forceinline__ uint64_t add_nc(uint64_t a, uint64_t b) {
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\t"
+      "addc.cc.u32 %1, %3, %5;\n\t"
+      "addc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "add.u32 %1, %1, m;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+  return pack(r0, r1);
+}
+// a - b mod p; requires b canonical (b - a <= p - 1).  Result congruent, not necessarily canonical.
+__device__ __forceinline__ uint64_t sub_nc(uint64_t a, uint64_t b) {
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.cc.u32 %1, %3, %5;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+  return pack(r0, r1);
+}
+// canonical in (both), canonical out
+__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return canon(add_nc(a, b)); }
+__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return canon(sub_nc(a, b)); }
+__device__ __forceinline__ uint64_t neg(uint64_t a) { return a ? GL_P - a : 0; }  // a canonical
+
+__device__ __forceinline__ uint64_t pow(uint64_t a, uint64_t e) {
+  uint64_t r = 1;
+  while (e) {
+    if (e & 1) r = mul(r, a);
+    a = mul(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+__device__ __forceinline__ uint64_t inv(uint64_t a) { return pow(a, GL_P - 2); }
+
+// ---- quadratic extension F[X]/(X^2 - 7) (plonky2 QuadraticExtension<GoldilocksField>, W = 7) ----
+struct ext2 {
+  uint64_t c0, c1;
+};
+__device__ __forceinline__ ext2 ext_add(ext2 a, ext2 b) { return {add(a.c0, b.c0), add(a.c1, b.c1)}; }
+__device__ __forceinline__ ext2 ext_sub(ext2 a, ext2 b) { return {sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+__device__ __forceinline__ ext2 ext_mul(ext2 a, ext2 b) {
+  uint64_t c0 = add(mul(a.c0, b.c0), mul(7, mul(a.c1, b.c1)));
+  uint64_t c1 = add(mul(a.c0, b.c1), mul(a.c1, b.c0));
+  return {c0, c1};
+}
+__device__ __forceinline__ ext2 ext_scale(ext2 a, uint64_t s) { return {mul(a.c0, s), mul(a.c1, s)}; }
+
+}  // namespace gl

@@ -1,0 +1,208 @@
+// hash_kernels.cuh — Poseidon leaf hashing and Merkle tree levels (one permutation per thread).
+//
+// Replaces plonky2 0.2.2 hash/merkle_tree.rs MerkleTree::new (fill_digests_buf / fill_subtree) for
+// H = PoseidonHash.  Device layout of a tree: `levels` holds the digests level by level, leaf level
+// first: level l (0 = leaf digests) has n_leaves >> l digests of 4 u64, down to the cap level
+// (2^cap_height digests).  plonky2's interleaved `digests` vector is produced on demand by
+// k_export_plonky2_digests (bit-exact with fill_subtree's layout).
+#pragma once
+#include "poseidon.cuh"
+
+namespace hashk {
+
+__device__ __forceinline__ void store_digest(uint64_t* __restrict__ dst, const uint64_t d[4]) {
+  ulonglong2* p = reinterpret_cast<ulonglong2*>(dst);
+  p[0] = make_ulonglong2(d[0], d[1]);
+  p[1] = make_ulonglong2(d[2], d[3]);
+}
+__device__ __forceinline__ void load_digest(const uint64_t* __restrict__ src, uint64_t d[4]) {
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src);
+  ulonglong2 a = p[0], b = p[1];
+  d[0] = a.x;
+  d[1] = a.y;
+  d[2] = b.x;
+  d[3] = b.y;
+}
+
+// Leaf digests of a column-major matrix: leaf j = (data[c * col_stride + j])_{c < n_cols}.
+// hash_or_noop: n_cols <= 4 -> zero-padded copy, else overwrite-mode sponge, 8 columns per permutation.
+// Consecutive threads read consecutive j of the same column: every load is a full 256 B per warp.
+__global__ void __launch_bounds__(256, 2)
+k_leaf_hash_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t n_cols, size_t n_leaves,
+                     uint64_t* __restrict__ digests) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_leaves) return;
+  uint64_t out[4];
+  if (n_cols <= 4) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = (uint32_t)i < n_cols ? gl::canon(data[(size_t)i * col_stride + j]) : 0;
+  } else {
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    uint64_t nxt[8];
+    const uint64_t* p = data + j;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nxt[i] = (uint32_t)i < n_cols ? p[(size_t)i * col_stride] : 0;
+    for (uint32_t c0 = 0; c0 < n_cols; c0 += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (c0 + i < n_cols) s[i] = nxt[i];
+      // prefetch the next 8 columns before the ~20k-instruction permutation
+      if (c0 + 8 < n_cols) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (c0 + 8 + i < n_cols) nxt[i] = p[(size_t)(c0 + 8 + i) * col_stride];
+      }
+      poseidon::permute_nc(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+  }
+  store_digest(digests + 4 * j, out);
+}
+
+// Leaf digests of row-major leaves (MerkleTree::new's own input layout; FRI layer leaves).
+__global__ void __launch_bounds__(256)
+k_leaf_hash_rowmajor(const uint64_t* __restrict__ leaves, size_t leaf_len, size_t n_leaves,
+                     uint64_t* __restrict__ digests) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_leaves) return;
+  const uint64_t* p = leaves + j * leaf_len;
+  uint64_t out[4];
+  if (leaf_len <= 4) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = (size_t)i < leaf_len ? gl::canon(p[i]) : 0;
+  } else {
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (size_t c0 = 0; c0 < leaf_len; c0 += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (c0 + i < leaf_len) s[i] = p[c0 + i];
+      poseidon::permute_nc(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+  }
+  store_digest(digests + 4 * j, out);
+}
+
+// One tree level: parent[i] = two_to_one(child[2i], child[2i+1]).
+__global__ void __launch_bounds__(256)
+k_tree_level(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, size_t n_parents) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_parents) return;
+  uint64_t l[4], r[4], o[4];
+  load_digest(child + 8 * i, l);
+  load_digest(child + 8 * i + 4, r);
+  poseidon::two_to_one(l, r, o);
+  store_digest(parent + 4 * i, o);
+}
+
+// n independent pairs (p2b_two_to_one)
+__global__ void __launch_bounds__(256)
+k_two_to_one_pairs(const uint64_t* __restrict__ left, const uint64_t* __restrict__ right, size_t n,
+                   uint64_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t l[4], r[4], o[4];
+  load_digest(left + 4 * i, l);
+  load_digest(right + 4 * i, r);
+  poseidon::two_to_one(l, r, o);
+  store_digest(out + 4 * i, o);
+}
+
+// n independent permutations, states row-major n x 12
+__global__ void __launch_bounds__(256) k_permute_states(uint64_t* __restrict__ states, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) s[k] = states[12 * i + k];
+  poseidon::permute(s);
+#pragma unroll
+  for (int k = 0; k < 12; k++) states[12 * i + k] = s[k];
+}
+
+// levels (leaf level first) -> plonky2's `digests` layout.  L = log2(n_leaves) - cap_height layers are
+// stored (the roots live in the cap only).  For the node q of layer i inside cap-subtree t:
+//   dst = t * (2^(L+1) - 2) + 2 * (((q >> 1) << (i + 1)) + 2^i - 1) + (q & 1)
+__global__ void __launch_bounds__(256)
+k_export_plonky2_digests(const uint64_t* __restrict__ levels, size_t n_leaves, uint32_t L,
+                         uint64_t* __restrict__ out) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index over all stored nodes
+  size_t total = 2 * n_leaves - (2 * (n_leaves >> L));         // sum_{i<L} n_leaves >> i
+  if (g >= total) return;
+  // find layer i: nodes of layer i start at offset 2*n_leaves - 2*(n_leaves >> i)
+  uint32_t i = 0;
+  size_t off = 0;
+  while (g >= off + (n_leaves >> i)) {
+    off += n_leaves >> i;
+    i++;
+  }
+  size_t node = g - off;              // index inside layer i (whole tree)
+  size_t t = node >> (L - i);         // cap subtree
+  size_t q = node & ((((size_t)1) << (L - i)) - 1);
+  size_t dst = t * ((((size_t)1) << (L + 1)) - 2) + 2 * (((q >> 1) << (i + 1)) + (((size_t)1) << i) - 1) + (q & 1);
+  uint64_t d[4];
+  load_digest(levels + 4 * g, d);
+  store_digest(out + 4 * dst, d);
+}
+
+// siblings of `leaf_index` for layers 0..L-1 -> out[L][4]
+__global__ void k_gather_proof(const uint64_t* __restrict__ levels, size_t n_leaves, uint32_t L, size_t leaf_index,
+                               uint64_t* __restrict__ out) {
+  uint32_t i = threadIdx.x >> 2, w = threadIdx.x & 3;
+  if (i >= L) return;
+  size_t off = 2 * n_leaves - 2 * (n_leaves >> i);
+  size_t sib = (leaf_index >> i) ^ 1;
+  out[4 * i + w] = levels[4 * (off + sib) + w];
+}
+
+// row `j` of a column-major matrix -> out[n_cols]
+__global__ void k_gather_row_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t n_cols, size_t j,
+                                      uint64_t* __restrict__ out) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_cols) out[c] = data[(size_t)c * col_stride + j];
+}
+
+// column-major (n_cols x n_rows) -> row-major (n_rows x n_cols) through a 32x32 shared tile
+__global__ void __launch_bounds__(256)
+k_transpose_to_rowmajor(const uint64_t* __restrict__ in, size_t col_stride, uint32_t n_cols, size_t n_rows,
+                        uint64_t* __restrict__ out) {
+  __shared__ uint64_t tile[32][33];
+  size_t r0 = (size_t)blockIdx.x * 32;
+  uint32_t c0 = blockIdx.y * 32;
+  uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (uint32_t k = ty; k < 32; k += 8) {
+    uint32_t c = c0 + k;
+    size_t r = r0 + tx;
+    if (c < n_cols && r < n_rows) tile[k][tx] = in[(size_t)c * col_stride + r];
+  }
+  __syncthreads();
+  for (uint32_t k = ty; k < 32; k += 8) {
+    size_t r = r0 + k;
+    uint32_t c = c0 + tx;
+    if (c < n_cols && r < n_rows) out[r * n_cols + c] = tile[tx][k];
+  }
+}
+
+// hash_no_pad of one host-provided vector (utility / known-answer tests): a single thread
+__global__ void k_hash_no_pad_single(const uint64_t* __restrict__ in, size_t len, uint64_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  for (size_t c0 = 0; c0 < len; c0 += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (c0 + i < len) s[i] = in[c0 + i];
+    poseidon::permute_nc(s);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+}
+
+}  // namespace hashk

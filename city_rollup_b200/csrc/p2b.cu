@@ -1,0 +1,1069 @@
+// p2b.cu — C ABI (include/p2b.h) over the sm_100a kernels: contexts, device-resident handles,
+// PolynomialBatch::{from_values,from_coeffs}, MerkleTree::new, Poseidon utilities, Challenger, FRI.
+// No CPU fallback: every entry point fails with P2B_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/p2b.h"
+#include "fri_kernels.cuh"
+#include "hash_kernels.cuh"
+#include "ntt_kernels.cuh"
+
+#define P2B_VERSION 100
+
+static thread_local std::string g_init_error;
+
+struct p2b_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool poisoned = false;
+  std::string err;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // twiddle tables (device)
+  uint64_t* d_w12 = nullptr;
+  uint64_t* d_rlo = nullptr;
+  uint64_t* d_rhi = nullptr;
+  // small pinned staging buffer for accessor results
+  uint64_t* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  nttk::Tables tables() const { return nttk::Tables{d_w12, d_rlo, d_rhi}; }
+};
+
+struct p2b_tree {
+  p2b_ctx* ctx = nullptr;
+  size_t n_leaves = 0;
+  uint32_t log_leaves = 0;
+  uint32_t cap_height = 0;
+  size_t leaf_len = 0;
+  uint64_t* d_levels = nullptr;  // 2*n_leaves - 2^cap_height digests, leaf level first
+  // leaves: either column-major (owned by a batch; col stride = n_leaves) or row-major (owned here)
+  const uint64_t* d_leaves_cm = nullptr;
+  uint64_t* d_leaves_rm = nullptr;
+  bool owned_by_batch = false;
+};
+
+struct p2b_batch {
+  p2b_ctx* ctx = nullptr;
+  size_t n_cols = 0;
+  uint32_t log_n = 0, rate_bits = 0, cap_height = 0;
+  uint64_t* d_coeffs = nullptr;  // n_cols x n
+  uint64_t* d_lde = nullptr;     // n_cols x (n << rate_bits), leaf order
+  p2b_tree tree;
+};
+
+struct p2b_challenger {
+  p2b_ctx* ctx = nullptr;
+  uint64_t* d_state = nullptr;  // frik::ChallengerState (30 u64)
+};
+
+// ------------------------------------------------------------------------------------------------
+static int fail(p2b_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) {
+    ctx->err = buf;
+    if (code == P2B_ERR_CUDA) ctx->poisoned = true;
+  } else {
+    g_init_error = buf;
+  }
+  return code;
+}
+
+#define CU(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? P2B_ERR_OOM : P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
+  } while (0)
+
+#define CHECK_CTX(ctx)                                                        \
+  do {                                                                        \
+    if (!(ctx)) return P2B_ERR_INVALID;                                       \
+    if ((ctx)->poisoned) return fail(ctx, P2B_ERR_CUDA, "context poisoned by an earlier CUDA error: %s", (ctx)->err.c_str()); \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                           \
+    if (e__ != cudaSuccess) return fail(ctx, P2B_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(ctx, P2B_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static int dmalloc(p2b_ctx* ctx, uint64_t** p, size_t n_u64) {
+  *p = nullptr;
+  if (n_u64 == 0) n_u64 = 1;
+  CU(ctx, cudaMallocAsync((void**)p, n_u64 * sizeof(uint64_t), ctx->stream));
+  return P2B_OK;
+}
+static void dfree(p2b_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int p2b_version(void) { return P2B_VERSION; }
+
+static int ctx_setup(p2b_ctx* ctx) {
+  CU(ctx, cudaEventCreate(&ctx->ev0));
+  CU(ctx, cudaEventCreate(&ctx->ev1));
+  // keep freed blocks cached in the stream-ordered pool (no trimming at sync points)
+  cudaMemPool_t pool;
+  CU(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  uint64_t thresh = UINT64_MAX;
+  CU(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  int rc;
+  if ((rc = dmalloc(ctx, &ctx->d_w12, 2048))) return rc;
+  if ((rc = dmalloc(ctx, &ctx->d_rlo, 65536))) return rc;
+  if ((rc = dmalloc(ctx, &ctx->d_rhi, 65536))) return rc;
+  // G = 7^((p-1)/2^32): primitive 2^32-th root (plonky2 POWER_OF_TWO_GENERATOR); w_4096 = G^(2^20)
+  const uint64_t G = 1753635133440165772ull;
+  uint64_t g16 = G, w4096 = G;
+  auto mulmod = [](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); };
+  for (int i = 0; i < 16; i++) g16 = mulmod(g16, g16);
+  for (int i = 0; i < 20; i++) w4096 = mulmod(w4096, w4096);
+  nttk::k_pow_table<<<cdiv(65536, 256), 256, 0, ctx->stream>>>(G, 65536, ctx->d_rlo);
+  LAUNCH_CHECK(ctx);
+  nttk::k_pow_table<<<cdiv(65536, 256), 256, 0, ctx->stream>>>(g16, 65536, ctx->d_rhi);
+  LAUNCH_CHECK(ctx);
+  nttk::k_pow_table<<<cdiv(2048, 256), 256, 0, ctx->stream>>>(w4096, 2048, ctx->d_w12);
+  LAUNCH_CHECK(ctx);
+  ctx->h_stage_bytes = 1 << 20;
+  CU(ctx, cudaMallocHost((void**)&ctx->h_stage, ctx->h_stage_bytes));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->launches = 0;
+  return P2B_OK;
+}
+
+static int init_common(int device, void* stream, bool borrow, p2b_ctx** out) {
+  if (!out) return P2B_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, P2B_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, P2B_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, P2B_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  p2b_ctx* ctx = new (std::nothrow) p2b_ctx();
+  if (!ctx) return fail(nullptr, P2B_ERR_OOM, "host allocation failed");
+  ctx->device = device;
+  if (borrow) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(nullptr, P2B_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+  }
+  int rc = ctx_setup(ctx);
+  if (rc != P2B_OK) {
+    g_init_error = ctx->err;
+    p2b_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return P2B_OK;
+}
+
+extern "C" int p2b_init(int device, p2b_ctx** out) { return init_common(device, nullptr, false, out); }
+extern "C" int p2b_init_on_stream(int device, void* cuda_stream, p2b_ctx** out) {
+  return init_common(device, cuda_stream, true, out);
+}
+
+extern "C" void p2b_destroy(p2b_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  dfree(ctx, ctx->d_w12);
+  dfree(ctx, ctx->d_rlo);
+  dfree(ctx, ctx->d_rhi);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* p2b_last_error(const p2b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+extern "C" int p2b_synchronize(p2b_ctx* ctx) {
+  CHECK_CTX(ctx);
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2B_OK;
+}
+
+extern "C" int p2b_host_alloc(p2b_ctx* ctx, size_t bytes, void** out) {
+  CHECK_CTX(ctx);
+  if (!out) return P2B_ERR_INVALID;
+  CU(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+  return P2B_OK;
+}
+extern "C" int p2b_host_free(p2b_ctx* ctx, void* p) {
+  CHECK_CTX(ctx);
+  if (p) CU(ctx, cudaFreeHost(p));
+  return P2B_OK;
+}
+extern "C" uint64_t p2b_launch_count(const p2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int p2b_timer_start(p2b_ctx* ctx) {
+  CHECK_CTX(ctx);
+  CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return P2B_OK;
+}
+extern "C" int p2b_timer_stop_ms(p2b_ctx* ctx, float* ms_out) {
+  CHECK_CTX(ctx);
+  if (!ms_out) return P2B_ERR_INVALID;
+  CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(ctx, cudaEventSynchronize(ctx->ev1));
+  CU(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+  return P2B_OK;
+}
+
+// copy `n` u64 from device to a caller (pageable or pinned) buffer, synchronously
+static int d2h(p2b_ctx* ctx, uint64_t* dst, const uint64_t* d_src, size_t n) {
+  CU(ctx, cudaMemcpyAsync(dst, d_src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NTT driver
+struct NttPlan {
+  uint32_t lr, ls;
+};
+static NttPlan plan_for(uint32_t log_n) {
+  NttPlan p;
+  if (log_n <= 12) {
+    p.lr = 0;
+    p.ls = log_n;
+  } else {
+    p.ls = (log_n + 1) / 2;
+    p.lr = log_n - p.ls;
+  }
+  return p;
+}
+static inline uint32_t u32min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// values (n_cols x n, natural) -> coefficients (n_cols x n, natural).  d_tmp: n_cols x n scratch
+// (only used when n > 2^12); may alias neither input nor output.
+static int run_intt(p2b_ctx* ctx, const uint64_t* d_vals, uint64_t* d_coeffs, uint64_t* d_tmp, size_t n_cols,
+                    uint32_t log_n, size_t tmp_poly_stride) {
+  const size_t n = (size_t)1 << log_n;
+  NttPlan pl = plan_for(log_n);
+  // 1/n mod p = p - (p-1)/n
+  const uint64_t ninv = GL_P - ((GL_P - 1) >> log_n);
+  const uint64_t scale = log_n == 0 ? 1 : ninv;
+  nttk::RowsParams rp{};
+  rp.log_n = log_n;
+  rp.lr = pl.lr;
+  rp.ls = pl.ls;
+  rp.log_cosets = 0;
+  rp.mode = 2;
+  rp.prescale = 0;
+  rp.scale = scale;
+  rp.tb = ctx->tables();
+  rp.out = d_coeffs;
+  rp.out_poly_stride = n;
+  rp.out_coset_stride = 0;
+  if (pl.lr == 0) {
+    rp.in = d_vals;
+    rp.in_poly_stride = n;
+    rp.log_TR = 0;
+    size_t smem = n * 8;
+    nttk::k_ntt_rows<<<dim3(1, (unsigned)n_cols, 1), 256, smem, ctx->stream>>>(rp);
+    LAUNCH_CHECK(ctx);
+    return P2B_OK;
+  }
+  nttk::ColsParams cp{};
+  cp.in = d_vals;
+  cp.in_poly_stride = n;
+  cp.out = d_tmp;
+  cp.out_poly_stride = tmp_poly_stride;
+  cp.out_coset_stride = 0;
+  cp.log_n = log_n;
+  cp.lr = pl.lr;
+  cp.ls = pl.ls;
+  cp.log_T = u32min(pl.ls, (pl.lr >= 9 ? 13 : 12) - pl.lr);
+  cp.log_cosets = 0;
+  cp.natural_rows = 1;
+  cp.prescale = 0;
+  cp.tb = ctx->tables();
+  {
+    size_t smem = ((size_t)8 << pl.lr) << cp.log_T;
+    dim3 grid((unsigned)(((size_t)1 << pl.ls) >> cp.log_T), (unsigned)n_cols, 1);
+    nttk::k_ntt_cols<<<grid, 256, smem, ctx->stream>>>(cp);
+    LAUNCH_CHECK(ctx);
+  }
+  rp.in = d_tmp;
+  rp.in_poly_stride = tmp_poly_stride;
+  rp.log_TR = u32min(pl.lr, (pl.ls >= 10 ? 13 : 12) - pl.ls);
+  {
+    size_t S = (size_t)1 << pl.ls, TR = (size_t)1 << rp.log_TR;
+    size_t smem = TR * (S + (TR > 1 ? 1 : 0)) * 8;
+    dim3 grid((unsigned)(((size_t)1 << pl.lr) >> rp.log_TR), (unsigned)n_cols, 1);
+    nttk::k_ntt_rows<<<grid, 256, smem, ctx->stream>>>(rp);
+    LAUNCH_CHECK(ctx);
+  }
+  return P2B_OK;
+}
+
+// coefficients (n_cols x n, natural, stride in_stride) -> coset evaluations on shift * w_{n<<rate_bits}^t * <w_n>,
+// all 2^rate_bits cosets, written in leaf (bit-reversed) order: d_lde is n_cols x (n << rate_bits).
+// `shift` is the coset shift of the whole domain (7 for PolynomialBatch; 7^(arity^l) for FRI layers).
+static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uint64_t* d_lde, size_t n_cols,
+                   uint32_t log_n, uint32_t rate_bits, uint64_t shift) {
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  const uint32_t n_cosets = 1u << rate_bits;
+  NttPlan pl = plan_for(log_n);
+  // power tables of s_t = shift * w_N^t
+  nttk::CosetPow cpw{};
+  uint64_t *d_lo = nullptr, *d_hi = nullptr;
+  uint32_t hi_count = (uint32_t)(n > 4096 ? n >> 12 : 1);
+  int rc;
+  if ((rc = dmalloc(ctx, &d_lo, (size_t)n_cosets * 4096))) return rc;
+  if ((rc = dmalloc(ctx, &d_hi, (size_t)n_cosets * hi_count))) return rc;
+  auto mulmod = [](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); };
+  auto powmod = [&](uint64_t a, uint64_t e) {
+    uint64_t r = 1;
+    a %= GL_P;
+    while (e) {
+      if (e & 1) r = mulmod(r, a);
+      a = mulmod(a, a);
+      e >>= 1;
+    }
+    return r;
+  };
+  const uint64_t G = 1753635133440165772ull;
+  const uint32_t log_N = log_n + rate_bits;
+  uint64_t wN = powmod(G, (uint64_t)1 << (32 - log_N));
+  for (uint32_t t = 0; t < n_cosets; t++) {
+    uint64_t st = mulmod(shift % GL_P, powmod(wN, t));
+    nttk::k_pow_table<<<cdiv(4096, 256), 256, 0, ctx->stream>>>(st, 4096, d_lo + (size_t)t * 4096);
+    LAUNCH_CHECK(ctx);
+    nttk::k_pow_table<<<cdiv(hi_count, 256), 256, 0, ctx->stream>>>(powmod(st, 4096), hi_count,
+                                                                    d_hi + (size_t)t * hi_count);
+    LAUNCH_CHECK(ctx);
+  }
+  cpw.lo = d_lo;
+  cpw.hi = d_hi;
+  cpw.hi_count = hi_count;
+
+  if (pl.lr == 0) {
+    nttk::RowsParams rp{};
+    rp.in = d_coeffs;
+    rp.in_poly_stride = in_stride;
+    rp.out = d_lde;
+    rp.out_poly_stride = N;
+    rp.out_coset_stride = n;
+    rp.log_n = log_n;
+    rp.lr = 0;
+    rp.ls = log_n;
+    rp.log_TR = 0;
+    rp.log_cosets = rate_bits;
+    rp.mode = 0;
+    rp.prescale = 1;
+    rp.scale = 1;
+    rp.cp = cpw;
+    rp.tb = ctx->tables();
+    nttk::k_ntt_rows<<<dim3(1, (unsigned)n_cols, n_cosets), 256, n * 8, ctx->stream>>>(rp);
+    LAUNCH_CHECK(ctx);
+  } else {
+    nttk::ColsParams cp{};
+    cp.in = d_coeffs;
+    cp.in_poly_stride = in_stride;
+    cp.out = d_lde;
+    cp.out_poly_stride = N;
+    cp.out_coset_stride = n;
+    cp.log_n = log_n;
+    cp.lr = pl.lr;
+    cp.ls = pl.ls;
+    cp.log_T = u32min(pl.ls, (pl.lr >= 9 ? 13 : 12) - pl.lr);
+    cp.log_cosets = rate_bits;
+    cp.natural_rows = 0;
+    cp.prescale = 1;
+    cp.cp = cpw;
+    cp.tb = ctx->tables();
+    {
+      size_t smem = ((size_t)8 << pl.lr) << cp.log_T;
+      dim3 grid((unsigned)(((size_t)1 << pl.ls) >> cp.log_T), (unsigned)n_cols, n_cosets);
+      nttk::k_ntt_cols<<<grid, 256, smem, ctx->stream>>>(cp);
+      LAUNCH_CHECK(ctx);
+    }
+    // pass B in place over all N/S rows of every column
+    nttk::RowsParams rp{};
+    rp.in = d_lde;
+    rp.in_poly_stride = N;
+    rp.out = d_lde;
+    rp.out_poly_stride = N;
+    rp.out_coset_stride = 0;
+    rp.log_n = log_n;
+    rp.lr = pl.lr;
+    rp.ls = pl.ls;
+    uint32_t log_rows = pl.lr + rate_bits;
+    rp.log_TR = u32min(log_rows, 12 - pl.ls);
+    rp.log_cosets = 0;
+    rp.mode = 0;
+    rp.prescale = 0;
+    rp.scale = 1;
+    rp.tb = ctx->tables();
+    size_t S = (size_t)1 << pl.ls, TR = (size_t)1 << rp.log_TR;
+    size_t smem = TR * (S + (TR > 1 ? 1 : 0)) * 8;
+    dim3 grid((unsigned)(((size_t)1 << log_rows) >> rp.log_TR), (unsigned)n_cols, 1);
+    nttk::k_ntt_rows<<<grid, 256, smem, ctx->stream>>>(rp);
+    LAUNCH_CHECK(ctx);
+  }
+  dfree(ctx, d_lo);
+  dfree(ctx, d_hi);
+  return P2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Merkle
+static size_t levels_len(size_t n_leaves, uint32_t cap_height) { return 2 * n_leaves - ((size_t)1 << cap_height); }
+static size_t level_off(size_t n_leaves, uint32_t i) { return 2 * n_leaves - 2 * (n_leaves >> i); }
+
+// leaf digests must already be in t->d_levels[0 .. n_leaves)
+static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
+  uint32_t L = t->log_leaves - t->cap_height;
+  for (uint32_t i = 0; i < L; i++) {
+    size_t n_par = t->n_leaves >> (i + 1);
+    hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
+                                                                  t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);
+    LAUNCH_CHECK(ctx);
+  }
+  return P2B_OK;
+}
+
+static int tree_from_colmajor(p2b_ctx* ctx, p2b_tree* t, const uint64_t* d_data, size_t n_leaves, uint32_t log_leaves,
+                              size_t n_cols, uint32_t cap_height) {
+  t->ctx = ctx;
+  t->n_leaves = n_leaves;
+  t->log_leaves = log_leaves;
+  t->cap_height = cap_height;
+  t->leaf_len = n_cols;
+  t->d_leaves_cm = d_data;
+  int rc;
+  if ((rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height)))) return rc;
+  hashk::k_leaf_hash_colmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_data, n_leaves, (uint32_t)n_cols, n_leaves,
+                                                                          t->d_levels);
+  LAUNCH_CHECK(ctx);
+  return build_levels(ctx, t);
+}
+
+// ------------------------------------------------------------------------------------------------ PolynomialBatch
+static int check_batch_args(p2b_ctx* ctx, const void* cols, size_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                            uint32_t cap_height, uint32_t flags, p2b_batch** out) {
+  if (!cols || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (n_cols == 0 || n_cols > 65535) return fail(ctx, P2B_ERR_INVALID, "n_cols must be in 1..65535 (got %zu)", n_cols);
+  if (log_n > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "log_n %u > 24", log_n);
+  if (rate_bits > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "rate_bits %u > 6", rate_bits);
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds log2(#leaves) = %u", cap_height, log_n + rate_bits);
+  if (flags != 0) return fail(ctx, P2B_ERR_UNSUPPORTED, "blinding (salted) batches are not supported (flags=%u)", flags);
+  return P2B_OK;
+}
+
+static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, bool is_values, size_t n_cols,
+                       uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  p2b_batch* b = new (std::nothrow) p2b_batch();
+  if (!b) {
+    dfree(ctx, d_in);
+    return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  }
+  b->ctx = ctx;
+  b->n_cols = n_cols;
+  b->log_n = log_n;
+  b->rate_bits = rate_bits;
+  b->cap_height = cap_height;
+  b->tree.owned_by_batch = true;
+  int rc = dmalloc(ctx, &b->d_lde, n_cols * N);
+  if (rc == P2B_OK) {
+    if (is_values) {
+      rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
+      // scratch for the two-pass inverse transform: the first n words of every LDE column
+      if (rc == P2B_OK) rc = run_intt(ctx, d_in, b->d_coeffs, b->d_lde, n_cols, log_n, N);
+      dfree(ctx, d_in);
+    } else {
+      b->d_coeffs = d_in;
+    }
+  } else {
+    dfree(ctx, d_in);
+  }
+  if (rc == P2B_OK) rc = run_lde(ctx, b->d_coeffs, n, b->d_lde, n_cols, log_n, rate_bits, 7);
+  if (rc == P2B_OK) rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
+  if (rc != P2B_OK) {
+    p2b_batch_free(b);
+    return rc;
+  }
+  *out = b;
+  return P2B_OK;
+}
+
+static int upload_cols(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, size_t n, uint64_t** d_out) {
+  int rc = dmalloc(ctx, d_out, n_cols * n);
+  if (rc) return rc;
+  // one DMA per run of columns that are contiguous in host memory (a single copy when the caller
+  // keeps the matrix in one allocation; one per column for plonky2's Vec<PolynomialValues>)
+  size_t c = 0;
+  while (c < n_cols) {
+    size_t e = c + 1;
+    while (e < n_cols && cols[e] == cols[e - 1] + n) e++;
+    if (!cols[c]) return fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c);
+    CU(ctx, cudaMemcpyAsync(*d_out + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    c = e;
+  }
+  return P2B_OK;
+}
+
+static int batch_from_host(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                           uint32_t cap_height, uint32_t flags, bool is_values, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  int rc = check_batch_args(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, out);
+  if (rc) return rc;
+  uint64_t* d_in = nullptr;
+  rc = upload_cols(ctx, cols, n_cols, (size_t)1 << log_n, &d_in);
+  if (rc) {
+    dfree(ctx, d_in);
+    return rc;
+  }
+  return batch_build(ctx, d_in, is_values, n_cols, log_n, rate_bits, cap_height, out);
+}
+
+static int batch_from_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                          uint32_t cap_height, uint32_t flags, bool is_values, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  int rc = check_batch_args(ctx, d_cols, n_cols, log_n, rate_bits, cap_height, flags, out);
+  if (rc) return rc;
+  const size_t n = (size_t)1 << log_n;
+  uint64_t* d_in = nullptr;
+  if (is_values) {
+    // the inverse transform reads the caller's buffer directly; nothing to copy
+    p2b_batch* b = nullptr;
+    const size_t N = n << rate_bits;
+    b = new (std::nothrow) p2b_batch();
+    if (!b) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+    b->ctx = ctx;
+    b->n_cols = n_cols;
+    b->log_n = log_n;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    b->tree.owned_by_batch = true;
+    rc = dmalloc(ctx, &b->d_lde, n_cols * N);
+    if (rc == P2B_OK) rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
+    if (rc == P2B_OK) rc = run_intt(ctx, d_cols, b->d_coeffs, b->d_lde, n_cols, log_n, N);
+    if (rc == P2B_OK) rc = run_lde(ctx, b->d_coeffs, n, b->d_lde, n_cols, log_n, rate_bits, 7);
+    if (rc == P2B_OK) rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
+    if (rc != P2B_OK) {
+      p2b_batch_free(b);
+      return rc;
+    }
+    *out = b;
+    return P2B_OK;
+  }
+  rc = dmalloc(ctx, &d_in, n_cols * n);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(d_in, d_cols, n_cols * n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return batch_build(ctx, d_in, false, n_cols, log_n, rate_bits, cap_height, out);
+}
+
+extern "C" int p2b_batch_from_values(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n,
+                                     uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
+  return batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, true, out);
+}
+extern "C" int p2b_batch_from_coeffs(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n,
+                                     uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
+  return batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, false, out);
+}
+extern "C" int p2b_batch_from_values_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, uint32_t log_n,
+                                         uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
+  return batch_from_dev(ctx, d_cols, n_cols, log_n, rate_bits, cap_height, flags, true, out);
+}
+extern "C" int p2b_batch_from_coeffs_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, uint32_t log_n,
+                                         uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
+  return batch_from_dev(ctx, d_cols, n_cols, log_n, rate_bits, cap_height, flags, false, out);
+}
+
+extern "C" void p2b_batch_free(p2b_batch* b) {
+  if (!b) return;
+  p2b_ctx* ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  dfree(ctx, b->d_coeffs);
+  dfree(ctx, b->d_lde);
+  dfree(ctx, b->tree.d_levels);
+  delete b;
+}
+
+extern "C" size_t p2b_batch_n_cols(const p2b_batch* b) { return b ? b->n_cols : 0; }
+extern "C" uint32_t p2b_batch_degree_log(const p2b_batch* b) { return b ? b->log_n : 0; }
+extern "C" uint32_t p2b_batch_rate_bits(const p2b_batch* b) { return b ? b->rate_bits : 0; }
+extern "C" p2b_tree* p2b_batch_tree(p2b_batch* b) { return b ? &b->tree : nullptr; }
+extern "C" const uint64_t* p2b_batch_dev_lde(const p2b_batch* b) { return b ? b->d_lde : nullptr; }
+extern "C" const uint64_t* p2b_batch_dev_coeffs(const p2b_batch* b) { return b ? b->d_coeffs : nullptr; }
+
+extern "C" int p2b_batch_cap(p2b_batch* b, uint64_t* out) {
+  if (!b) return P2B_ERR_INVALID;
+  return p2b_tree_cap(&b->tree, out);
+}
+extern "C" int p2b_batch_coeffs(p2b_batch* b, size_t col, uint64_t* out) {
+  if (!b || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  if (col >= b->n_cols) return fail(ctx, P2B_ERR_INVALID, "column %zu out of range", col);
+  size_t n = (size_t)1 << b->log_n;
+  return d2h(ctx, out, b->d_coeffs + col * n, n);
+}
+extern "C" int p2b_batch_leaf(p2b_batch* b, size_t leaf_index, uint64_t* out) {
+  if (!b) return P2B_ERR_INVALID;
+  return p2b_tree_leaf(&b->tree, leaf_index, out);
+}
+extern "C" int p2b_batch_lde_values(p2b_batch* b, size_t index, size_t step, uint64_t* out) {
+  if (!b) return P2B_ERR_INVALID;
+  uint32_t bits = b->log_n + b->rate_bits;
+  size_t i = index * step;
+  if (i >> bits) return fail(b->ctx, P2B_ERR_INVALID, "index*step %zu out of range", i);
+  size_t r = 0;
+  for (uint32_t k = 0; k < bits; k++) r |= ((i >> k) & 1) << (bits - 1 - k);
+  return p2b_tree_leaf(&b->tree, r, out);
+}
+extern "C" int p2b_batch_leaves(p2b_batch* b, uint64_t* out) {
+  if (!b || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  size_t N = (size_t)1 << (b->log_n + b->rate_bits);
+  uint64_t* d_rm = nullptr;
+  int rc = dmalloc(ctx, &d_rm, N * b->n_cols);
+  if (rc) return rc;
+  dim3 grid(cdiv(N, 32), cdiv(b->n_cols, 32));
+  hashk::k_transpose_to_rowmajor<<<grid, 256, 0, ctx->stream>>>(b->d_lde, N, (uint32_t)b->n_cols, N, d_rm);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d_rm, N * b->n_cols);
+  dfree(ctx, d_rm);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ MerkleTree
+extern "C" int p2b_merkle_new(p2b_ctx* ctx, const uint64_t* leaves, size_t n_leaves, size_t leaf_len,
+                              uint32_t cap_height, p2b_tree** out) {
+  CHECK_CTX(ctx);
+  if (!leaves || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return fail(ctx, P2B_ERR_INVALID, "n_leaves must be a power of two");
+  uint32_t log_leaves = 0;
+  while (((size_t)1 << log_leaves) < n_leaves) log_leaves++;
+  if (cap_height > log_leaves)
+    return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds log2(#leaves) = %u", cap_height, log_leaves);
+  p2b_tree* t = new (std::nothrow) p2b_tree();
+  if (!t) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  t->ctx = ctx;
+  t->n_leaves = n_leaves;
+  t->log_leaves = log_leaves;
+  t->cap_height = cap_height;
+  t->leaf_len = leaf_len;
+  int rc = dmalloc(ctx, &t->d_leaves_rm, n_leaves * leaf_len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height));
+  if (rc == P2B_OK && leaf_len) {
+    cudaError_t e = cudaMemcpyAsync(t->d_leaves_rm, leaves, n_leaves * leaf_len * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  }
+  if (rc == P2B_OK) {
+    hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves,
+                                                                            t->d_levels);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  }
+  if (rc == P2B_OK) rc = build_levels(ctx, t);
+  if (rc != P2B_OK) {
+    p2b_tree_free(t);
+    return rc;
+  }
+  *out = t;
+  return P2B_OK;
+}
+
+extern "C" void p2b_tree_free(p2b_tree* t) {
+  if (!t || t->owned_by_batch) return;
+  p2b_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
+  dfree(ctx, t->d_levels);
+  dfree(ctx, t->d_leaves_rm);
+  delete t;
+}
+extern "C" size_t p2b_tree_n_leaves(const p2b_tree* t) { return t ? t->n_leaves : 0; }
+extern "C" uint32_t p2b_tree_cap_height(const p2b_tree* t) { return t ? t->cap_height : 0; }
+
+extern "C" int p2b_tree_cap(p2b_tree* t, uint64_t* out) {
+  if (!t || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = t->ctx;
+  CHECK_CTX(ctx);
+  uint32_t L = t->log_leaves - t->cap_height;
+  return d2h(ctx, out, t->d_levels + 4 * level_off(t->n_leaves, L), (size_t)4 << t->cap_height);
+}
+
+extern "C" int p2b_tree_prove(p2b_tree* t, size_t leaf_index, uint64_t* out) {
+  if (!t || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = t->ctx;
+  CHECK_CTX(ctx);
+  if (leaf_index >= t->n_leaves) return fail(ctx, P2B_ERR_INVALID, "leaf index %zu out of range", leaf_index);
+  uint32_t L = t->log_leaves - t->cap_height;
+  if (L == 0) return P2B_OK;
+  uint64_t* d_tmp = nullptr;
+  int rc = dmalloc(ctx, &d_tmp, 4 * (size_t)L);
+  if (rc) return rc;
+  hashk::k_gather_proof<<<1, 4 * L <= 32 ? 32 : 4 * ((L + 7) / 8) * 8, 0, ctx->stream>>>(t->d_levels, t->n_leaves, L,
+                                                                                         leaf_index, d_tmp);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d_tmp, 4 * (size_t)L);
+  dfree(ctx, d_tmp);
+  return rc;
+}
+
+extern "C" int p2b_tree_digests(p2b_tree* t, uint64_t* out) {
+  if (!t || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = t->ctx;
+  CHECK_CTX(ctx);
+  uint32_t L = t->log_leaves - t->cap_height;
+  size_t total = 2 * (t->n_leaves - ((size_t)1 << t->cap_height));
+  if (total == 0) return P2B_OK;
+  uint64_t* d_tmp = nullptr;
+  int rc = dmalloc(ctx, &d_tmp, 4 * total);
+  if (rc) return rc;
+  hashk::k_export_plonky2_digests<<<cdiv(total, 256), 256, 0, ctx->stream>>>(t->d_levels, t->n_leaves, L, d_tmp);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d_tmp, 4 * total);
+  dfree(ctx, d_tmp);
+  return rc;
+}
+
+extern "C" int p2b_tree_leaf(p2b_tree* t, size_t leaf_index, uint64_t* out) {
+  if (!t || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = t->ctx;
+  CHECK_CTX(ctx);
+  if (leaf_index >= t->n_leaves) return fail(ctx, P2B_ERR_INVALID, "leaf index %zu out of range", leaf_index);
+  if (t->leaf_len == 0) return P2B_OK;
+  if (t->d_leaves_rm) return d2h(ctx, out, t->d_leaves_rm + leaf_index * t->leaf_len, t->leaf_len);
+  uint64_t* d_tmp = nullptr;
+  int rc = dmalloc(ctx, &d_tmp, t->leaf_len);
+  if (rc) return rc;
+  hashk::k_gather_row_colmajor<<<cdiv(t->leaf_len, 128), 128, 0, ctx->stream>>>(t->d_leaves_cm, t->n_leaves,
+                                                                               (uint32_t)t->leaf_len, leaf_index, d_tmp);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d_tmp, t->leaf_len);
+  dfree(ctx, d_tmp);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ Poseidon
+extern "C" int p2b_poseidon_permute(p2b_ctx* ctx, uint64_t* states, size_t n) {
+  CHECK_CTX(ctx);
+  if (!states) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (n == 0) return P2B_OK;
+  uint64_t* d = nullptr;
+  int rc = dmalloc(ctx, &d, 12 * n);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(d, states, 12 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  hashk::k_permute_states<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d, n);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, states, d, 12 * n);
+  dfree(ctx, d);
+  return rc;
+}
+
+extern "C" int p2b_hash_no_pad(p2b_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out) {
+  CHECK_CTX(ctx);
+  if ((!in && len) || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  uint64_t* d = nullptr;
+  int rc = dmalloc(ctx, &d, len + 4);
+  if (rc) return rc;
+  if (len) CU(ctx, cudaMemcpyAsync(d + 4, in, len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  hashk::k_hash_no_pad_single<<<1, 32, 0, ctx->stream>>>(d + 4, len, d);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d, 4);
+  dfree(ctx, d);
+  return rc;
+}
+
+extern "C" int p2b_two_to_one(p2b_ctx* ctx, const uint64_t* left, const uint64_t* right, size_t n, uint64_t* out) {
+  CHECK_CTX(ctx);
+  if (!left || !right || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (n == 0) return P2B_OK;
+  uint64_t* d = nullptr;
+  int rc = dmalloc(ctx, &d, 12 * n);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(d, left, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d + 4 * n, right, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  hashk::k_two_to_one_pairs<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d, d + 4 * n, n, d + 8 * n);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d + 8 * n, 4 * n);
+  dfree(ctx, d);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ Challenger
+extern "C" int p2b_challenger_new(p2b_ctx* ctx, p2b_challenger** out) {
+  CHECK_CTX(ctx);
+  if (!out) return P2B_ERR_INVALID;
+  *out = nullptr;
+  p2b_challenger* c = new (std::nothrow) p2b_challenger();
+  if (!c) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  c->ctx = ctx;
+  int rc = dmalloc(ctx, &c->d_state, frik::CH_WORDS);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  CU(ctx, cudaMemsetAsync(c->d_state, 0, frik::CH_WORDS * sizeof(uint64_t), ctx->stream));
+  *out = c;
+  return P2B_OK;
+}
+extern "C" void p2b_challenger_free(p2b_challenger* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  dfree(c->ctx, c->d_state);
+  delete c;
+}
+
+// observe n elements that already live on the device
+static int challenger_observe_dev(p2b_challenger* c, const uint64_t* d_elems, size_t n) {
+  p2b_ctx* ctx = c->ctx;
+  if (n == 0) return P2B_OK;
+  frik::k_challenger_observe<<<1, 32, 0, ctx->stream>>>(c->d_state, d_elems, n);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
+extern "C" int p2b_challenger_observe(p2b_challenger* c, const uint64_t* elems, size_t n) {
+  if (!c) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = c->ctx;
+  CHECK_CTX(ctx);
+  if (n == 0) return P2B_OK;
+  if (!elems) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  uint64_t* d = nullptr;
+  int rc = dmalloc(ctx, &d, n);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(d, elems, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  rc = challenger_observe_dev(c, d, n);
+  // the H2D source may be pageable and reused by the caller right after we return
+  if (rc == P2B_OK) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, d);
+  return rc;
+}
+
+extern "C" int p2b_challenger_observe_cap(p2b_challenger* c, p2b_tree* t) {
+  if (!c || !t) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = c->ctx;
+  CHECK_CTX(ctx);
+  if (t->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "tree belongs to a different context");
+  uint32_t L = t->log_leaves - t->cap_height;
+  return challenger_observe_dev(c, t->d_levels + 4 * level_off(t->n_leaves, L), (size_t)4 << t->cap_height);
+}
+
+extern "C" int p2b_challenger_get(p2b_challenger* c, size_t n, uint64_t* out) {
+  if (!c || (!out && n)) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = c->ctx;
+  CHECK_CTX(ctx);
+  if (n == 0) return P2B_OK;
+  uint64_t* d = nullptr;
+  int rc = dmalloc(ctx, &d, n);
+  if (rc) return rc;
+  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(c->d_state, n, d);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d, n);
+  dfree(ctx, d);
+  return rc;
+}
+
+extern "C" int p2b_challenger_export(p2b_challenger* c, uint64_t* out30) {
+  if (!c || !out30) return P2B_ERR_INVALID;
+  CHECK_CTX(c->ctx);
+  return d2h(c->ctx, out30, c->d_state, frik::CH_WORDS);
+}
+extern "C" int p2b_challenger_import(p2b_challenger* c, const uint64_t* in30) {
+  if (!c || !in30) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = c->ctx;
+  CHECK_CTX(ctx);
+  if (in30[12] > 8 || in30[21] > 8) return fail(ctx, P2B_ERR_INVALID, "buffer length > 8");
+  CU(ctx, cudaMemcpyAsync(c->d_state, in30, frik::CH_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ FRI
+extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, size_t len,
+                              const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits, uint32_t cap_height,
+                              p2b_challenger* ch, p2b_tree** layers_out, uint64_t* final_poly_out) {
+  CHECK_CTX(ctx);
+  if (!coeffs_ext || !values_ext || !ch || !final_poly_out || (n_layers && (!arity_bits || !layers_out)))
+    return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
+  if (len == 0 || (len & (len - 1))) return fail(ctx, P2B_ERR_INVALID, "len must be a power of two");
+  uint32_t log_len = 0;
+  while (((size_t)1 << log_len) < len) log_len++;
+  uint32_t sum = 0;
+  for (size_t l = 0; l < n_layers; l++) {
+    if (arity_bits[l] == 0 || arity_bits[l] > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "arity_bits must be in 1..6");
+    sum += arity_bits[l];
+    layers_out[l] = nullptr;
+  }
+  if (sum + rate_bits > log_len) return fail(ctx, P2B_ERR_INVALID, "reduction exceeds the polynomial length");
+  if (log_len > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "len > 2^24");
+
+  // device buffers: coefficients as two planes (c0 | c1), each `len`; values interleaved in leaf order
+  uint64_t *d_in = nullptr, *d_coef = nullptr, *d_vals = nullptr, *d_beta = nullptr, *d_planes = nullptr;
+  int rc = dmalloc(ctx, &d_in, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_coef, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_beta, 2);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_planes, 2 * len);
+  std::vector<p2b_tree*> trees;
+  auto cleanup = [&](int code) {
+    dfree(ctx, d_in);
+    dfree(ctx, d_coef);
+    dfree(ctx, d_vals);
+    dfree(ctx, d_beta);
+    dfree(ctx, d_planes);
+    if (code != P2B_OK) {
+      for (p2b_tree* t : trees) p2b_tree_free(t);
+      for (size_t l = 0; l < n_layers; l++) layers_out[l] = nullptr;
+    }
+    return code;
+  };
+  if (rc) return cleanup(rc);
+#define CUF(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+#define LAUNCHF()                                                                                  \
+  do {                                                                                             \
+    ctx->launches++;                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+
+  // coefficients -> planes
+  CUF(cudaMemcpyAsync(d_in, coeffs_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  frik::k_deinterleave<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d_in, len, d_coef, d_coef + len);
+  LAUNCHF();
+  // layer-0 values: natural order interleaved -> leaf order (bit-reversed), row-major leaves
+  CUF(cudaMemcpyAsync(d_in, values_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  size_t cur = len;
+  uint32_t log_cur = log_len;
+  uint64_t shift = 7;
+  auto mulmod = [](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); };
+  for (size_t l = 0; l < n_layers; l++) {
+    const uint32_t ab = arity_bits[l];
+    const size_t n_leaves = cur >> ab, leaf_len = (size_t)2 << ab;
+    if (cap_height > log_cur - ab)
+      return cleanup(fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds layer %zu height %u", cap_height, l, log_cur - ab));
+    p2b_tree* t = new (std::nothrow) p2b_tree();
+    if (!t) return cleanup(fail(ctx, P2B_ERR_OOM, "host allocation failed"));
+    trees.push_back(t);
+    t->ctx = ctx;
+    t->n_leaves = n_leaves;
+    t->log_leaves = log_cur - ab;
+    t->cap_height = cap_height;
+    t->leaf_len = leaf_len;
+    if ((rc = dmalloc(ctx, &t->d_leaves_rm, 2 * cur))) return cleanup(rc);
+    if ((rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height)))) return cleanup(rc);
+    if (l == 0) {
+      frik::k_bitrev_ext<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_in, log_cur, t->d_leaves_rm);
+      LAUNCHF();
+    } else {
+      // d_planes holds the coset NTT of the folded coefficients in leaf order, as planes
+      frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_planes, d_planes + cur, cur, t->d_leaves_rm);
+      LAUNCHF();
+    }
+    hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+    LAUNCHF();
+    if ((rc = build_levels(ctx, t))) return cleanup(rc);
+    // observe_cap, beta = get_extension_challenge (device resident)
+    if ((rc = p2b_challenger_observe_cap(ch, t))) return cleanup(rc);
+    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_beta);
+    LAUNCHF();
+    // fold: coeffs[i] = sum_j coeffs[i*arity + j] * beta^j
+    frik::k_fold_coeffs<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, cur, ab, d_beta, d_in, d_in + n_leaves);
+    LAUNCHF();
+    // (folded planes now in d_in[0..n_leaves), d_in[n_leaves..2 n_leaves)); move back to d_coef
+    CUF(cudaMemcpyAsync(d_coef, d_in, 2 * n_leaves * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    cur = n_leaves;
+    log_cur -= ab;
+    for (uint32_t k = 0; k < ab; k++) shift = mulmod(shift, shift);
+    if (l + 1 < n_layers) {
+      // values of the next layer = coset NTT (shift) of the folded coefficients, leaf order, 2 planes
+      if ((rc = run_lde(ctx, d_coef, cur, d_planes, 2, log_cur, 0, shift))) return cleanup(rc);
+    }
+  }
+  // final polynomial: first cur >> rate_bits coefficients (the rest are zero for a valid codeword)
+  size_t n_final = cur >> rate_bits;
+  uint64_t* d_final = d_in;  // reuse
+  frik::k_interleave<<<cdiv(n_final, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, n_final, d_final);
+  LAUNCHF();
+  if ((rc = challenger_observe_dev(ch, d_final, 2 * n_final))) return cleanup(rc);
+  CUF(cudaMemcpyAsync(final_poly_out, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUF(cudaStreamSynchronize(ctx->stream));
+  for (size_t l = 0; l < n_layers; l++) layers_out[l] = trees[l];
+  return cleanup(P2B_OK);
+#undef CUF
+#undef LAUNCHF
+}
+
+extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint64_t* witness_out) {
+  CHECK_CTX(ctx);
+  if (!ch || !witness_out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
+  if (pow_bits > 40) return fail(ctx, P2B_ERR_UNSUPPORTED, "pow_bits > 40");
+  uint64_t* d_best = nullptr;
+  int rc = dmalloc(ctx, &d_best, 1);
+  if (rc) return rc;
+  const uint64_t chunk = (uint64_t)1 << 20;
+  uint64_t found = ~0ull;
+  for (uint64_t base = 0; found == ~0ull; base += chunk) {
+    CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
+    frik::k_pow_search<<<cdiv(chunk, 256), 256, 0, ctx->stream>>>(ch->d_state, base, chunk, pow_bits, (unsigned long long*)d_best);
+    LAUNCH_CHECK(ctx);
+    rc = d2h(ctx, &found, d_best, 1);
+    if (rc) break;
+    if (base + chunk < base) break;
+  }
+  dfree(ctx, d_best);
+  if (rc) return rc;
+  if (found == ~0ull) return fail(ctx, P2B_ERR_INVALID, "no proof-of-work witness found");
+  // challenger.observe_element(w); pow_response = challenger.get_challenge()
+  uint64_t* d_w = nullptr;
+  if ((rc = dmalloc(ctx, &d_w, 2))) return rc;
+  CU(ctx, cudaMemcpyAsync(d_w, &found, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  rc = challenger_observe_dev(ch, d_w, 1);
+  if (rc == P2B_OK) {
+    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 1, d_w + 1);
+    ctx->launches++;
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, d_w);
+  *witness_out = found;
+  return rc;
+}

@@ -1,0 +1,359 @@
+"""Host-side mirror of the plonky2 prover surface City Rollup's workers call, backed by the CUDA
+library (libp2b.so) through its C ABI.
+
+The reference is Rust and no Rust toolchain exists in this image, so this Python layer plays the part of
+the patched `plonky2` crate (INTEGRATION.md shows the Rust binding): same names, argument meaning and
+error behaviour as plonky2 0.2.2 —
+
+    PolynomialBatch.from_values / from_coeffs / get_lde_values   (fri/oracle.rs)
+    MerkleTree.new / prove / cap / digests / get                 (hash/merkle_tree.rs)
+    Challenger.observe_* / get_*                                  (iop/challenger.rs)
+    fri_committed_trees / fri_proof_of_work                      (fri/prover.rs)
+
+reached in the reference only via `circuit_data.prove(pw)` (e.g.
+city_common_circuit/src/proof_minifier/pm_core.rs:151).  Field elements are numpy uint64.
+Errors surface as P2BError (the analogue of the `anyhow::Error` the worker loop propagates,
+city_rollup_core_worker/src/actors/simple.rs:83); nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+u64p = _lib.u64p
+
+
+class P2BError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"p2b error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "expected a contiguous uint64 array"
+    return a.ctypes.data_as(u64p)
+
+
+class Context:
+    """One CUDA device + stream (p2b_ctx).  Not thread-safe; create one per worker thread."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        if stream is None:
+            rc = self.lib.p2b_init(device, C.byref(h))
+        else:
+            rc = self.lib.p2b_init_on_stream(device, C.c_void_p(stream), C.byref(h))
+        if rc != 0:
+            raise P2BError(rc, self.lib.p2b_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise P2BError(rc, self.lib.p2b_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(self.lib.p2b_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.p2b_launch_count(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.p2b_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self.check(self.lib.p2b_timer_stop_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def pinned_empty(self, shape):
+        """uint64 array backed by pinned host memory (freed with the context)."""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self.check(self.lib.p2b_host_alloc(self.h, n * 8, C.byref(p)))
+        buf = (C.c_uint64 * n).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint64).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return a
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.p2b_host_free(self.h, p)
+            self._pinned = []
+            self.lib.p2b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Poseidon utilities (PoseidonHash) ----
+    def poseidon_permute(self, states):
+        s = np.ascontiguousarray(np.array(states, dtype=np.uint64)).reshape(-1, 12).copy()
+        self.check(self.lib.p2b_poseidon_permute(self.h, _ptr(s), s.shape[0]))
+        return s
+
+    def hash_no_pad(self, x):
+        x = np.ascontiguousarray(np.array(x, dtype=np.uint64)).reshape(-1)
+        o = np.zeros(4, np.uint64)
+        xp = _ptr(x) if x.size else None
+        self.check(self.lib.p2b_hash_no_pad(self.h, xp, x.size, _ptr(o)))
+        return o
+
+    def two_to_one(self, left, right):
+        l = np.ascontiguousarray(np.array(left, dtype=np.uint64)).reshape(-1, 4)
+        r = np.ascontiguousarray(np.array(right, dtype=np.uint64)).reshape(-1, 4)
+        o = np.zeros_like(l)
+        self.check(self.lib.p2b_two_to_one(self.h, _ptr(l), _ptr(r), l.shape[0], _ptr(o)))
+        return o
+
+
+class MerkleTree:
+    """plonky2::hash::merkle_tree::MerkleTree<GoldilocksField, PoseidonHash> (device resident)."""
+
+    def __init__(self, ctx, handle, owner=None):
+        self.ctx, self.h, self._owner = ctx, handle, owner
+        lib = ctx.lib
+        self.n_leaves = int(lib.p2b_tree_n_leaves(handle))
+        self.cap_height = int(lib.p2b_tree_cap_height(handle))
+
+    @classmethod
+    def new(cls, ctx, leaves, cap_height):
+        """MerkleTree::new(leaves: Vec<Vec<F>>, cap_height)"""
+        leaves = np.ascontiguousarray(np.array(leaves, dtype=np.uint64))
+        if leaves.ndim != 2:
+            raise ValueError("leaves must be (n_leaves, leaf_len)")
+        h = C.c_void_p()
+        lp = _ptr(leaves) if leaves.size else _ptr(np.zeros(1, np.uint64))
+        ctx.check(ctx.lib.p2b_merkle_new(ctx.h, lp, leaves.shape[0], leaves.shape[1], cap_height, C.byref(h)))
+        t = cls(ctx, h)
+        t.leaf_len = leaves.shape[1]
+        return t
+
+    @property
+    def cap(self):
+        o = np.zeros((1 << self.cap_height, 4), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_tree_cap(self.h, _ptr(o)))
+        return o
+
+    @property
+    def digests(self):
+        """tree.digests in plonky2's interleaved layout"""
+        n = 2 * (self.n_leaves - (1 << self.cap_height))
+        o = np.zeros((max(n, 1), 4), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_tree_digests(self.h, _ptr(o)))
+        return o[:n]
+
+    def prove(self, leaf_index):
+        """MerkleTree::prove(leaf_index).siblings"""
+        L = self.n_leaves.bit_length() - 1 - self.cap_height
+        o = np.zeros((max(L, 1), 4), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_tree_prove(self.h, leaf_index, _ptr(o)))
+        return o[:L]
+
+    def get(self, leaf_index, leaf_len=None):
+        """MerkleTree::get(leaf_index)"""
+        n = leaf_len if leaf_len is not None else self.leaf_len
+        o = np.zeros(max(n, 1), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_tree_leaf(self.h, leaf_index, _ptr(o)))
+        return o[:n]
+
+    def free(self):
+        if self.h and self._owner is None:
+            self.ctx.lib.p2b_tree_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+class PolynomialBatch:
+    """plonky2::fri::oracle::PolynomialBatch<GoldilocksField, PoseidonGoldilocksConfig, 2>"""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        lib = ctx.lib
+        self.n_cols = int(lib.p2b_batch_n_cols(handle))
+        self.degree_log = int(lib.p2b_batch_degree_log(handle))
+        self.rate_bits = int(lib.p2b_batch_rate_bits(handle))
+        self.merkle_tree = MerkleTree(ctx, C.c_void_p(lib.p2b_batch_tree(handle)), owner=self)
+        self.merkle_tree.leaf_len = self.n_cols
+
+    @staticmethod
+    def _cols(values):
+        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.uint64)) for c in values]
+        if not cols:
+            raise ValueError("empty batch")
+        n = cols[0].size
+        if n == 0 or n & (n - 1) or any(c.size != n for c in cols):
+            raise ValueError("all columns must have the same power-of-two length")
+        ptrs = (u64p * len(cols))(*[_ptr(c) for c in cols])
+        return cols, ptrs, n.bit_length() - 1
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None):
+        """PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)"""
+        cols, ptrs, log_n = cls._cols(values)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_from_values(ctx.h, ptrs, len(cols), log_n, rate_bits, cap_height,
+                                                1 if blinding else 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_coeffs(cls, ctx, polynomials, rate_bits, blinding, cap_height, timing=None, fft_root_table=None):
+        """PolynomialBatch::from_coeffs(polynomials, rate_bits, blinding, cap_height, timing, fft_root_table)"""
+        cols, ptrs, log_n = cls._cols(polynomials)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_from_coeffs(ctx.h, ptrs, len(cols), log_n, rate_bits, cap_height,
+                                                1 if blinding else 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_values_device(cls, ctx, dev_ptr, n_cols, log_n, rate_bits, cap_height):
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_from_values_dev(ctx.h, C.c_void_p(dev_ptr), n_cols, log_n, rate_bits,
+                                                    cap_height, 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_coeffs_device(cls, ctx, dev_ptr, n_cols, log_n, rate_bits, cap_height):
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_from_coeffs_dev(ctx.h, C.c_void_p(dev_ptr), n_cols, log_n, rate_bits,
+                                                    cap_height, 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def cap(self):
+        return self.merkle_tree.cap
+
+    def coeffs(self, col):
+        """batch.polynomials[col].coeffs"""
+        o = np.zeros(1 << self.degree_log, np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_coeffs(self.h, col, _ptr(o)))
+        return o
+
+    def get_lde_values(self, index, step=1):
+        """PolynomialBatch::get_lde_values(index, step)"""
+        o = np.zeros(self.n_cols, np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_lde_values(self.h, index, step, _ptr(o)))
+        return o
+
+    def leaf(self, leaf_index):
+        o = np.zeros(self.n_cols, np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_leaf(self.h, leaf_index, _ptr(o)))
+        return o
+
+    def leaves(self):
+        """batch.merkle_tree.leaves as an (n_leaves, n_cols) array"""
+        N = 1 << (self.degree_log + self.rate_bits)
+        o = np.zeros((N, self.n_cols), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_leaves(self.h, _ptr(o)))
+        return o
+
+    def free(self):
+        if self.h:
+            self.merkle_tree.h = None
+            self.ctx.lib.p2b_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+class Challenger:
+    """plonky2::iop::challenger::Challenger<GoldilocksField, PoseidonHash>, state resident in HBM"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_challenger_new(ctx.h, C.byref(h)))
+        self.h = h
+
+    def observe_elements(self, elems):
+        e = np.ascontiguousarray(np.array(elems, dtype=np.uint64)).reshape(-1)
+        if e.size:
+            self.ctx.check(self.ctx.lib.p2b_challenger_observe(self.h, _ptr(e), e.size))
+
+    observe_element = lambda self, e: self.observe_elements([e])
+    observe_hash = observe_elements
+    observe_extension_elements = observe_elements
+
+    def observe_cap(self, tree_or_batch):
+        t = tree_or_batch.merkle_tree if isinstance(tree_or_batch, PolynomialBatch) else tree_or_batch
+        self.ctx.check(self.ctx.lib.p2b_challenger_observe_cap(self.h, t.h))
+
+    def get_n_challenges(self, n):
+        o = np.zeros(max(n, 1), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_challenger_get(self.h, n, _ptr(o)))
+        return [int(x) for x in o[:n]]
+
+    def get_challenge(self):
+        return self.get_n_challenges(1)[0]
+
+    def get_extension_challenge(self):
+        return self.get_n_challenges(2)
+
+    def export_state(self):
+        o = np.zeros(30, np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_challenger_export(self.h, _ptr(o)))
+        return o
+
+    def import_state(self, s):
+        s = np.ascontiguousarray(np.array(s, dtype=np.uint64))
+        self.ctx.check(self.ctx.lib.p2b_challenger_import(self.h, _ptr(s)))
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.p2b_challenger_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+def fri_committed_trees(ctx, coeffs, values, challenger, reduction_arity_bits, rate_bits=3, cap_height=4):
+    """fri::prover::fri_committed_trees(coeffs, values, challenger, fri_params)
+    -> (trees: list[MerkleTree], final_poly_coeffs (n,2))"""
+    coeffs = np.ascontiguousarray(np.array(coeffs, dtype=np.uint64)).reshape(-1, 2)
+    values = np.ascontiguousarray(np.array(values, dtype=np.uint64)).reshape(-1, 2)
+    n = coeffs.shape[0]
+    nl = len(reduction_arity_bits)
+    ab = (C.c_uint32 * max(nl, 1))(*reduction_arity_bits)
+    handles = (C.c_void_p * max(nl, 1))()
+    n_final = (n >> sum(reduction_arity_bits)) >> rate_bits
+    final = np.zeros((max(n_final, 1), 2), np.uint64)
+    ctx.check(ctx.lib.p2b_fri_commit(ctx.h, _ptr(coeffs), _ptr(values), n, ab, nl, rate_bits, cap_height,
+                                     challenger.h, handles, _ptr(final)))
+    trees = []
+    ln = n
+    for i, a in enumerate(reduction_arity_bits):
+        t = MerkleTree(ctx, C.c_void_p(handles[i]))
+        t.leaf_len = 2 << a
+        trees.append(t)
+        ln >>= a
+    return trees, final[:n_final]
+
+
+def fri_proof_of_work(ctx, challenger, proof_of_work_bits):
+    """fri::prover::fri_proof_of_work(challenger, config) -> pow_witness (the minimal one)"""
+    w = C.c_uint64()
+    ctx.check(ctx.lib.p2b_fri_pow(ctx.h, challenger.h, proof_of_work_bits, C.byref(w)))
+    return int(w.value)

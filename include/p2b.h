@@ -1,0 +1,171 @@
+/* p2b.h — C ABI of the B200-native Plonky2 proving hot path behind City Rollup worker jobs.
+ *
+ * This is the drop-in boundary.  The reference reaches the path only through
+ * `circuit_data.prove(pw)` (e.g. city_common_circuit/src/proof_minifier/pm_core.rs:151,
+ * city_rollup_circuit/src/block_circuits/ops/l2_transfer/circuit.rs:234,
+ * city_common_circuit/src/treeprover/aggregation/state_transition/mod.rs:298); the functions replaced
+ * live in the plonky2 0.2.2 dependency it patches in at Cargo.toml:101-102,128-129.  A patched
+ * `plonky2` crate binds these entry points from a thin FFI crate (rust/plonky2_b200_sys, see
+ * INTEGRATION.md); each declaration below names the Rust item it stands in for.
+ *
+ * Conventions
+ *  - Field elements are raw little-endian u64 (GoldilocksField is a transparent u64).  Inputs may be
+ *    non-canonical (>= p = 2^64-2^32+1, cf. city_crypto/src/hash/qhashout.rs:149-152); every output
+ *    is canonical.  A digest (HashOut) is 4 u64; a cap of height h is 2^h digests; an extension
+ *    element (QuadraticExtension, X^2 = 7) is 2 u64 {c0, c1}.
+ *  - Every function returns P2B_OK (0) or a negative p2b_status and never throws / aborts / unwinds;
+ *    the message is available from p2b_last_error().  CUDA errors are sticky: after
+ *    P2B_ERR_CUDA the context is poisoned and must be destroyed (the worker loop maps this to
+ *    anyhow::Error, city_rollup_core_worker/src/actors/simple.rs:83).
+ *  - The caller owns every pointer it passes and every plain output buffer.  The library owns the
+ *    opaque handles until the matching *_free; no handle may outlive its context.
+ *  - A p2b_ctx is bound to one device and one CUDA stream and is NOT thread-safe; use one context per
+ *    OS thread (several per GPU are fine and let small proofs overlap).
+ *  - Host inputs may be pageable or pinned; pinned (p2b_host_alloc) buffers are copied with one
+ *    asynchronous DMA per column group and are what bench.py uses.
+ *  - There is no CPU fallback: if no CUDA device is usable p2b_init fails.
+ */
+#ifndef P2B_H
+#define P2B_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  P2B_OK = 0,
+  P2B_ERR_INVALID = -1, /* bad argument */
+  P2B_ERR_CUDA = -2,    /* CUDA runtime error (context poisoned) */
+  P2B_ERR_OOM = -3,     /* device or host allocation failed */
+  P2B_ERR_UNSUPPORTED = -4
+} p2b_status;
+
+typedef struct p2b_ctx p2b_ctx;
+typedef struct p2b_batch p2b_batch;           /* plonky2::fri::oracle::PolynomialBatch */
+typedef struct p2b_tree p2b_tree;             /* plonky2::hash::merkle_tree::MerkleTree<F, PoseidonHash> */
+typedef struct p2b_challenger p2b_challenger; /* plonky2::iop::challenger::Challenger<F, PoseidonHash> */
+
+/* ---------------------------------------------------------------- context ---------------- */
+int p2b_version(void);
+/* Creates a context on `device` with its own non-blocking stream. */
+int p2b_init(int device, p2b_ctx **out);
+/* Same, but all work is enqueued on the caller's cudaStream_t (e.g. a framework's current stream);
+ * the stream is borrowed, not destroyed. */
+int p2b_init_on_stream(int device, void *cuda_stream, p2b_ctx **out);
+void p2b_destroy(p2b_ctx *ctx);
+/* Message of the last failure on this context ("" if none).  ctx may be NULL (global init error). */
+const char *p2b_last_error(const p2b_ctx *ctx);
+/* Blocks until all work enqueued on the context's stream has finished. */
+int p2b_synchronize(p2b_ctx *ctx);
+/* Pinned host memory for inputs/outputs that should move by DMA without staging. */
+int p2b_host_alloc(p2b_ctx *ctx, size_t bytes, void **out);
+int p2b_host_free(p2b_ctx *ctx, void *p);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t p2b_launch_count(const p2b_ctx *ctx);
+/* CUDA-event timing on the context's stream (bench.py times kernels on the launching stream). */
+int p2b_timer_start(p2b_ctx *ctx);
+int p2b_timer_stop_ms(p2b_ctx *ctx, float *ms_out); /* synchronises on the stop event */
+
+/* ---------------------------------------------------------------- PolynomialBatch -------- */
+/* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height, timing, fft_root_table)
+ * cols[c] points to 2^log_n values of column c (plonky2's Vec<PolynomialValues<F>>: one allocation
+ * per column).  Computes per column ifft -> lde(rate_bits) -> coset_fft(shift 7), the bit-reversed
+ * leaf order and the Poseidon Merkle tree with 2^cap_height roots.  Everything stays in HBM.
+ * flags: must be 0 (blinding/salting is used by no worker circuit). */
+int p2b_batch_from_values(p2b_ctx *ctx, const uint64_t *const *cols, size_t n_cols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch **out);
+/* PolynomialBatch::from_coeffs(polynomials, ...): cols[c] = 2^log_n coefficients of column c. */
+int p2b_batch_from_coeffs(p2b_ctx *ctx, const uint64_t *const *cols, size_t n_cols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch **out);
+/* Device-resident inputs: d_cols is a device pointer to n_cols x 2^log_n u64, column-major
+ * (column c at d_cols + c * 2^log_n).  Used when the previous prover stage already left its output
+ * in HBM (witness upload once, Z/partial products, quotient chunks). */
+int p2b_batch_from_values_dev(p2b_ctx *ctx, const uint64_t *d_cols, size_t n_cols, uint32_t log_n,
+                              uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch **out);
+int p2b_batch_from_coeffs_dev(p2b_ctx *ctx, const uint64_t *d_cols, size_t n_cols, uint32_t log_n,
+                              uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch **out);
+void p2b_batch_free(p2b_batch *b);
+
+size_t p2b_batch_n_cols(const p2b_batch *b);
+uint32_t p2b_batch_degree_log(const p2b_batch *b);
+uint32_t p2b_batch_rate_bits(const p2b_batch *b);
+/* batch.merkle_tree (borrowed; freed with the batch) */
+p2b_tree *p2b_batch_tree(p2b_batch *b);
+/* batch.merkle_tree.cap -> out[4 << cap_height] */
+int p2b_batch_cap(p2b_batch *b, uint64_t *out);
+/* batch.polynomials[col].coeffs -> out[2^log_n] (natural order) */
+int p2b_batch_coeffs(p2b_batch *b, size_t col, uint64_t *out);
+/* batch.merkle_tree.leaves[leaf_index] (= MerkleTree::get) -> out[n_cols] */
+int p2b_batch_leaf(p2b_batch *b, size_t leaf_index, uint64_t *out);
+/* PolynomialBatch::get_lde_values(index, step) -> out[n_cols] (row bitrev(index*step)) */
+int p2b_batch_lde_values(p2b_batch *b, size_t index, size_t step, uint64_t *out);
+/* all leaves, row-major (2^(log_n+rate_bits) x n_cols), i.e. batch.merkle_tree.leaves flattened */
+int p2b_batch_leaves(p2b_batch *b, uint64_t *out);
+/* Device views (valid until p2b_batch_free): LDE values column-major in leaf order
+ * (column c, leaf j at d_lde[c * 2^(log_n+rate_bits) + j]) and coefficients column-major. */
+const uint64_t *p2b_batch_dev_lde(const p2b_batch *b);
+const uint64_t *p2b_batch_dev_coeffs(const p2b_batch *b);
+
+/* ---------------------------------------------------------------- MerkleTree ------------- */
+/* MerkleTree::<F, PoseidonHash>::new(leaves, cap_height); leaves row-major n_leaves x leaf_len
+ * (n_leaves a power of two, cap_height <= log2(n_leaves)). */
+int p2b_merkle_new(p2b_ctx *ctx, const uint64_t *leaves, size_t n_leaves, size_t leaf_len,
+                   uint32_t cap_height, p2b_tree **out);
+void p2b_tree_free(p2b_tree *t);
+size_t p2b_tree_n_leaves(const p2b_tree *t);
+uint32_t p2b_tree_cap_height(const p2b_tree *t);
+/* tree.cap -> out[4 << cap_height] */
+int p2b_tree_cap(p2b_tree *t, uint64_t *out);
+/* MerkleTree::prove(leaf_index).siblings -> out[4 * (log2(n_leaves) - cap_height)], leaf level first */
+int p2b_tree_prove(p2b_tree *t, size_t leaf_index, uint64_t *out);
+/* tree.digests in plonky2's interleaved layout -> out[4 * 2 * (n_leaves - 2^cap_height)] */
+int p2b_tree_digests(p2b_tree *t, uint64_t *out);
+/* tree.leaves[leaf_index] -> out[leaf_len] (trees built by p2b_merkle_new / p2b_fri_commit) */
+int p2b_tree_leaf(p2b_tree *t, size_t leaf_index, uint64_t *out);
+
+/* ---------------------------------------------------------------- Poseidon --------------- */
+/* n independent permutations; states is n x 12 (row-major), permuted in place.
+ * (plonky2::hash::poseidon::Poseidon::poseidon) */
+int p2b_poseidon_permute(p2b_ctx *ctx, uint64_t *states, size_t n);
+/* PoseidonHash::hash_no_pad(in[0..len]) -> out[4] */
+int p2b_hash_no_pad(p2b_ctx *ctx, const uint64_t *in, size_t len, uint64_t *out);
+/* PoseidonHash::two_to_one for n pairs: left/right are n x 4, out n x 4 */
+int p2b_two_to_one(p2b_ctx *ctx, const uint64_t *left, const uint64_t *right, size_t n, uint64_t *out);
+
+/* ---------------------------------------------------------------- Challenger ------------- */
+/* The transcript lives in HBM so that the FRI commit loop (tree -> observe cap -> beta -> fold) runs
+ * without a host round trip per layer. */
+int p2b_challenger_new(p2b_ctx *ctx, p2b_challenger **out);
+void p2b_challenger_free(p2b_challenger *c);
+/* Challenger::observe_elements */
+int p2b_challenger_observe(p2b_challenger *c, const uint64_t *elems, size_t n);
+/* Challenger::observe_cap(&tree.cap) without leaving the device */
+int p2b_challenger_observe_cap(p2b_challenger *c, p2b_tree *t);
+/* Challenger::get_n_challenges(n) -> out[n] (synchronises) */
+int p2b_challenger_get(p2b_challenger *c, size_t n, uint64_t *out);
+/* raw state for seeding / cross-checking: out = sponge_state[12] || input_len || input_buffer[8] ||
+ * output_len || output_buffer[8]  (30 u64) */
+int p2b_challenger_export(p2b_challenger *c, uint64_t *out30);
+int p2b_challenger_import(p2b_challenger *c, const uint64_t *in30);
+
+/* ---------------------------------------------------------------- FRI -------------------- */
+/* fri::prover::fri_committed_trees(coeffs, values, challenger, fri_params):
+ * coeffs / values: `len` extension elements (interleaved c0,c1), values in natural order on the coset
+ * 7*<w_len>.  For each layer i (arity 2^arity_bits[i]): Merkle tree over the bit-reversed values
+ * chunked by arity, observe its cap, squeeze beta, fold the coefficients, coset-NTT the next layer.
+ * layers_out[i] receives the layer tree (caller frees with p2b_tree_free).  final_poly_out receives
+ * (len >> sum(arity_bits) >> rate_bits) extension elements, which are also observed. */
+int p2b_fri_commit(p2b_ctx *ctx, const uint64_t *coeffs_ext, const uint64_t *values_ext, size_t len,
+                   const uint32_t *arity_bits, size_t n_layers, uint32_t rate_bits, uint32_t cap_height,
+                   p2b_challenger *challenger, p2b_tree **layers_out, uint64_t *final_poly_out);
+/* fri::prover::fri_proof_of_work: the SMALLEST witness w with >= pow_bits leading zero bits in the
+ * response (the reference accepts any valid w, found by rayon find_any — SURVEY §0.5).  Observes w and
+ * squeezes the response like the reference. */
+int p2b_fri_pow(p2b_ctx *ctx, p2b_challenger *challenger, uint32_t pow_bits, uint64_t *witness_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2B_H */

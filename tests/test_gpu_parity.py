@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path, driven through the C ABI (libp2b.so), against the CPU oracle on the
+same seeded inputs, against the reference's golden fixtures, and — at BASELINE.json's full sizes —
+through size-independent properties.  Bit-exact everywhere (integer arithmetic mod p)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import p2oracle as O
+from proof_parser import parse_proof
+from util import P, bitrev, rand_felts, splitmix64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import city_rollup_b200 as m
+
+    c = m.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def m():
+    import city_rollup_b200 as mod
+
+    return mod
+
+
+# ----------------------------------------------------------------------------- Poseidon
+def test_poseidon_permutation_random_and_noncanonical(ctx):
+    states = rand_felts(11, (300, 12), canonical=False)
+    states[0] = 0
+    states[1] = np.uint64(P - 1)
+    states[2] = np.uint64(2**64 - 1)
+    states[3] = np.uint64(P)
+    got = ctx.poseidon_permute(states)
+    for i in range(states.shape[0]):
+        assert (got[i] == O.permute(states[i])).all(), i
+    assert (got < np.uint64(P)).all()
+
+
+def test_k1_k2_zero_hash_chains_on_gpu(ctx, golden_dir):
+    """city_crypto/src/hash/cached_zero_hashes.rs:10-1036 and :1039-2066, computed by the CUDA kernels"""
+    z = json.load(open(os.path.join(golden_dir, "zero_hashes.json")))
+    cur = np.zeros((1, 4), np.uint64)
+    for i in range(1, 128):
+        cur = ctx.two_to_one(cur, cur)
+        assert cur[0].tolist() == z["zero"][i], i
+    cur = ctx.hash_no_pad([0] * 8 + [1]).reshape(1, 4)
+    assert cur[0].tolist() == z["marked"][1]
+    for i in range(2, 128):
+        cur = ctx.two_to_one(cur, cur)
+        assert cur[0].tolist() == z["marked"][i], i
+
+
+def test_hash_no_pad_lengths(ctx):
+    for n in (0, 1, 4, 5, 7, 8, 9, 16, 17, 135):
+        x = rand_felts(n + 1, n, canonical=False)
+        assert (ctx.hash_no_pad(x) == O.hash_no_pad(x)).all(), n
+
+
+def test_k3_stored_proof_paths_on_gpu(ctx, m, golden_dir):
+    """qbench_data/example.bin: leaf hashing (135/20/16/32-wide) and path climbing on the GPU must reach the
+    caps stored in the proofs."""
+    idx = json.load(open(os.path.join(golden_dir, "example_proofs.json")))["proofs"]
+    blob = open(os.path.join(golden_dir, "example_proofs.bin"), "rb").read()
+    p = parse_proof(blob[idx[0]["offset"] : idx[0]["offset"] + idx[0]["len"]])
+    caps = [None, p["wires_cap"], p["zs_pp_cap"], p["quotient_cap"]]
+    rounds = p["query_rounds"]
+    x_indices = [O.merkle_find_index(r["initial"][3][0], r["initial"][3][1], caps[3]) for r in rounds]
+    for t in (1, 2, 3):
+        leaves = np.stack([r["initial"][t][0] for r in rounds] + [rounds[0]["initial"][t][0]] * 4)  # pad 28 -> 32
+        tree = m.MerkleTree.new(ctx, leaves, 5)  # cap_height = log2(32): the cap is the leaf digests
+        cur = tree.cap[:28].copy()
+        idxs = np.array(x_indices)
+        for lvl in range(11):
+            sib = np.stack([r["initial"][t][1][lvl] for r in rounds])
+            bit = (idxs >> lvl) & 1
+            left = np.where(bit[:, None] == 1, sib, cur)
+            right = np.where(bit[:, None] == 1, cur, sib)
+            cur = ctx.two_to_one(left, right)
+        for k in range(28):
+            assert (cur[k] == caps[t][x_indices[k] >> 11]).all()
+    # FRI layer 0 leaves: 16 extension evaluations = 32 felts
+    leaves = np.stack([r["steps"][0][0].reshape(-1) for r in rounds] + [rounds[0]["steps"][0][0].reshape(-1)] * 4)
+    tree = m.MerkleTree.new(ctx, leaves, 5)
+    cur = tree.cap[:28].copy()
+    idxs = np.array(x_indices) >> 4
+    for lvl in range(7):
+        sib = np.stack([r["steps"][0][1][lvl] for r in rounds])
+        bit = (idxs >> lvl) & 1
+        cur = ctx.two_to_one(np.where(bit[:, None] == 1, sib, cur), np.where(bit[:, None] == 1, cur, sib))
+    for k in range(28):
+        assert (cur[k] == p["commit_phase_merkle_caps"][0][idxs[k] >> 7]).all()
+
+
+# ----------------------------------------------------------------------------- MerkleTree::new
+@pytest.mark.parametrize("n_leaves,leaf_len,cap_height", [
+    (1, 5, 0), (2, 3, 0), (2, 3, 1), (16, 4, 2), (16, 5, 0), (64, 7, 3), (64, 8, 6), (128, 9, 4),
+    (256, 32, 4), (512, 135, 4), (1024, 20, 0), (2048, 1, 4), (4096, 16, 4)])
+def test_merkle_tree_new(ctx, m, n_leaves, leaf_len, cap_height):
+    leaves = rand_felts(n_leaves * 131 + leaf_len, (n_leaves, leaf_len), canonical=False)
+    dg, cap = O.merkle_tree_new(leaves, cap_height)
+    t = m.MerkleTree.new(ctx, leaves, cap_height)
+    assert (t.cap == cap).all()
+    assert (t.digests == dg).all()  # plonky2's interleaved layout
+    for i in sorted({0, n_leaves - 1, n_leaves // 2, (n_leaves * 5) // 7}):
+        sib = t.prove(i)
+        assert (sib == O.merkle_prove(dg, n_leaves, cap_height, i)).all()
+        assert O.merkle_verify(leaves[i], i, sib, cap)
+        assert (t.get(i) == leaves[i]).all()
+
+
+def test_merkle_errors(ctx, m):
+    with pytest.raises(m.P2BError):
+        m.MerkleTree.new(ctx, np.zeros((3, 4), np.uint64), 0)  # not a power of two
+    with pytest.raises(m.P2BError):
+        m.MerkleTree.new(ctx, np.zeros((4, 4), np.uint64), 3)  # cap above the leaves
+    t = m.MerkleTree.new(ctx, np.zeros((4, 4), np.uint64), 1)
+    with pytest.raises(m.P2BError):
+        t.prove(4)
+
+
+# ----------------------------------------------------------------------------- PolynomialBatch
+def _check_batch(ctx, m, cols, rate_bits, cap_height, from_values, sample_only=False):
+    n = cols[0].size
+    log_n = n.bit_length() - 1
+    N = n << rate_bits
+    ref = (O.batch_from_values if from_values else O.batch_from_coeffs)(cols, rate_bits, cap_height)
+    mk = m.PolynomialBatch.from_values if from_values else m.PolynomialBatch.from_coeffs
+    b = mk(ctx, cols, rate_bits, False, cap_height)
+    assert (b.cap == ref["cap"]).all()
+    if from_values:
+        for c in sorted({0, len(cols) - 1, len(cols) // 2}):
+            assert (b.coeffs(c) == ref["coeffs"][c]).all(), c
+    else:
+        assert (b.coeffs(0) == (cols[0] % np.uint64(P))).all()
+    if not sample_only:
+        assert (b.leaves() == ref["leaves"]).all()
+        assert (b.merkle_tree.digests == ref["digests"]).all()
+    for j in sorted({0, 1 % N, N - 1, N // 3, (N * 5) // 7}):
+        assert (b.leaf(j) == ref["leaves"][j]).all(), j
+        assert (b.get_lde_values(bitrev(j, log_n + rate_bits), 1) == ref["leaves"][j]).all()
+        sib = b.merkle_tree.prove(j)
+        assert (sib == O.merkle_prove(ref["digests"], N, cap_height, j)).all()
+        assert O.merkle_verify(ref["leaves"][j], j, sib, ref["cap"])
+    b.free()
+
+
+@pytest.mark.parametrize("log_n,n_cols,rate_bits,cap_height", [
+    (0, 3, 3, 0), (1, 2, 3, 1), (2, 5, 3, 4), (3, 9, 1, 0), (5, 20, 3, 4), (8, 16, 3, 4), (10, 135, 3, 4),
+    (12, 135, 3, 4), (12, 20, 3, 4), (12, 16, 3, 4), (12, 85, 3, 4), (12, 1, 0, 0), (13, 17, 3, 4),
+    (14, 20, 3, 4), (15, 8, 2, 4), (16, 4, 3, 4)])
+def test_batch_from_values(ctx, m, log_n, n_cols, rate_bits, cap_height):
+    cols = [rand_felts(0x5EED0001 + c, 1 << log_n, canonical=(c % 3 != 0)) for c in range(n_cols)]
+    _check_batch(ctx, m, cols, rate_bits, cap_height, True)
+
+
+@pytest.mark.parametrize("log_n,n_cols,rate_bits,cap_height", [
+    (4, 16, 3, 4), (12, 16, 3, 4), (13, 16, 3, 4), (16, 2, 3, 4)])
+def test_batch_from_coeffs(ctx, m, log_n, n_cols, rate_bits, cap_height):
+    cols = [rand_felts(0xC0EFF + c, 1 << log_n, canonical=(c % 2 == 0)) for c in range(n_cols)]
+    _check_batch(ctx, m, cols, rate_bits, cap_height, False)
+
+
+def test_batch_config1_shape_bit_exact(ctx, m):
+    """BASELINE.json configs[1]: 2^16 rows x 135 wire columns, rate_bits 3, cap_height 4 — the full commit
+    against the oracle (coefficients, sampled leaves, paths, cap)."""
+    cols = [rand_felts(0x5EED0001 + c, 1 << 16) for c in range(135)]
+    _check_batch(ctx, m, cols, 3, 4, True, sample_only=True)
+
+
+def test_batch_errors(ctx, m):
+    with pytest.raises(m.P2BError):
+        m.PolynomialBatch.from_values(ctx, [np.zeros(8, np.uint64)], 3, True, 4)  # blinding unsupported
+    with pytest.raises(m.P2BError):
+        m.PolynomialBatch.from_values(ctx, [np.zeros(2, np.uint64)], 1, False, 4)  # cap above the leaves
+    with pytest.raises(ValueError):
+        m.PolynomialBatch.from_values(ctx, [np.zeros(6, np.uint64)], 3, False, 1)
+    with pytest.raises(ValueError):
+        m.PolynomialBatch.from_values(ctx, [], 3, False, 1)
+    # the context stays usable after argument errors
+    assert (ctx.hash_no_pad([1, 2, 3, 4, 5]) == O.hash_no_pad([1, 2, 3, 4, 5])).all()
+
+
+def _horner(coeffs, x):
+    acc = 0
+    for c in reversed([int(c) for c in coeffs]):
+        acc = (acc * x + c) % P
+    return acc
+
+
+def test_large_batch_properties_2p20(ctx, m):
+    """2^20 rows (the M2 shape's row count) x 6 columns: too big for a full oracle run in seconds, so use
+    size-independent properties: ifft/fft round trip at sampled points, linearity, Merkle paths."""
+    log_n, rate = 20, 3
+    n = 1 << log_n
+    a = [rand_felts(1 + c, n) for c in range(3)]
+    bcols = [rand_felts(77 + c, n) for c in range(3)]
+    s = [((x.astype(object) + y.astype(object)) % P).astype(np.uint64) for x, y in zip(a, bcols)]
+    batch = m.PolynomialBatch.from_values(ctx, a + bcols, rate, False, 4)
+    bsum = m.PolynomialBatch.from_values(ctx, s, rate, False, 4)
+    log_N = log_n + rate
+    w = O.root_of_unity(log_N)
+    cap = batch.cap
+    for j in (0, 12345, (1 << log_N) - 1, 5 << 19):
+        leaf = batch.leaf(j)
+        lsum = bsum.leaf(j)
+        for c in range(3):  # linearity of the whole pipeline
+            assert int(lsum[c]) == (int(leaf[c]) + int(leaf[3 + c])) % P
+        assert O.merkle_verify(leaf, j, batch.merkle_tree.prove(j), cap)
+    # LDE restricted to the subgroup coset: evaluate the coefficients directly at one point
+    coeffs0 = batch.coeffs(0)
+    j = 987654
+    x = 7 * pow(w, bitrev(j, log_N), P) % P
+    assert int(batch.leaf(j)[0]) == _horner(coeffs0, x)
+    # ifft really inverts: coefficients evaluated at w_n^i give back value i
+    wn = O.root_of_unity(log_n)
+    for i in (0, 1, 54321):
+        assert _horner(coeffs0, pow(wn, i, P)) == int(a[0][i])
+    batch.free()
+    bsum.free()
+
+
+# ----------------------------------------------------------------------------- Challenger / FRI
+def test_challenger_matches_oracle(ctx, m):
+    rng = np.random.default_rng(3)
+    g, o = m.Challenger(ctx), O.Challenger()
+    for step in range(40):
+        k = int(rng.integers(0, 20))
+        e = rand_felts(1000 + step, k, canonical=(step % 2 == 0))
+        g.observe_elements(e)
+        o.observe(e)
+        if step % 3 != 1:
+            q = int(rng.integers(1, 12))
+            assert g.get_n_challenges(q) == o.get_n(q)
+    st, inb = o.state_words()
+    ex = g.export_state()
+    assert ex[:12].tolist() == st and int(ex[12]) == len(inb) and ex[13:13 + len(inb)].tolist() == inb
+    g2 = m.Challenger(ctx)
+    g2.import_state(ex)
+    assert g2.get_n_challenges(9) == g.get_n_challenges(9)
+
+
+@pytest.mark.parametrize("log_n,arity_bits,rate_bits,cap_height", [
+    (5, [4], 3, 0), (7, [4, 3], 3, 1), (9, [4, 4], 3, 4), (12, [4, 4], 3, 4), (12, [1, 2, 3, 4], 3, 2),
+    (13, [4, 4], 3, 4), (14, [4, 4, 4], 2, 4), (16, [4, 4, 4], 3, 4)])
+def test_fri_committed_trees(ctx, m, log_n, arity_bits, rate_bits, cap_height):
+    n = 1 << log_n
+    N = n << rate_bits
+    coeffs = np.zeros((N, 2), np.uint64)
+    coeffs[:n] = rand_felts(900 + log_n, (n, 2))
+    values = O.ext_coset_fft(coeffs, 7)
+    seed = rand_felts(4, 5)
+    oc = O.Challenger()
+    oc.observe(seed)
+    ref = O.fri_committed_trees(coeffs, values, arity_bits, oc, rate_bits, cap_height)
+    gc = m.Challenger(ctx)
+    gc.observe_elements(seed)
+    trees, final = m.fri_committed_trees(ctx, coeffs, values, gc, arity_bits, rate_bits, cap_height)
+    assert (final == ref["final_poly"]).all()
+    for l, t in enumerate(trees):
+        assert (t.cap == ref["caps"][l]).all(), l
+        assert (t.digests == ref["digests"][l][: t.digests.shape[0]]).all(), l
+        nl = t.n_leaves
+        for j in sorted({0, nl - 1, nl // 3}):
+            assert (t.get(j) == ref["leaves"][l][j]).all()
+            assert (t.prove(j) == O.merkle_prove(ref["digests"][l], nl, cap_height, j)).all()
+    # transcripts agree after the commit phase, and so does the proof of work (minimal witness)
+    assert gc.export_state()[:12].tolist() == oc.state_words()[0]
+    wg = m.fri_proof_of_work(ctx, gc, 12)
+    wo = O.fri_proof_of_work(oc, 12)
+    assert wg == wo
+    assert gc.get_n_challenges(4) == oc.get_n(4)
+
+
+def test_pow_16_bits_is_minimal(ctx, m):
+    gc, oc = m.Challenger(ctx), O.Challenger()
+    gc.observe_elements([5, 6, 7, 8, 9])
+    oc.observe([5, 6, 7, 8, 9])
+    base = oc.clone()
+    w = m.fri_proof_of_work(ctx, gc, 16)
+    assert O.fri_pow_check(base, w, 16) == 1
+    assert w == O.fri_proof_of_work(oc, 16)

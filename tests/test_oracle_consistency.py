@@ -1,0 +1,113 @@
+"""CPU-only self-consistency of the oracle's unpinned parts (NTT/LDE/FRI/challenger): the reference holds
+no golden vector for these, so they are checked against independent definitions."""
+import numpy as np
+
+import p2oracle as O
+from util import P, bitrev, rand_felts
+
+
+def horner(coeffs, x):
+    acc = 0
+    for c in reversed([int(c) for c in coeffs]):
+        acc = (acc * x + c) % P
+    return acc
+
+
+def test_fft_matches_direct_evaluation():
+    for log_n in (0, 1, 2, 5, 8):
+        n = 1 << log_n
+        c = rand_felts(100 + log_n, n)
+        v = O.fft(c)
+        w = O.root_of_unity(log_n)
+        for r in {0, 1 % n, n // 2, n - 1, (3 * n) // 7}:
+            assert int(v[r]) == horner(c, pow(w, r, P))
+        assert (O.ifft(v) == c).all()
+
+
+def test_coset_fft_and_lde_rows():
+    log_n, rate = 6, 3
+    n, N = 1 << log_n, 1 << (log_n + rate)
+    cols = [rand_felts(7 + i, n) for i in range(5)]
+    out = O.batch_from_coeffs(cols, rate, 2)
+    w = O.root_of_unity(log_n + rate)
+    for j in (0, 1, 17, N - 1):
+        x = 7 * pow(w, bitrev(j, log_n + rate), P) % P
+        for c in range(5):
+            assert int(out["leaves"][j, c]) == horner(cols[c], x)
+    vals = [O.fft(c) for c in cols]
+    out2 = O.batch_from_values(vals, rate, 2)
+    assert (out2["coeffs"] == np.array(cols)).all()
+    assert (out2["leaves"] == out["leaves"]).all() and (out2["cap"] == out["cap"]).all()
+
+
+def test_merkle_prove_verify_and_layout():
+    for (n, w, ch) in ((16, 7, 2), (8, 3, 0), (32, 20, 5), (4, 9, 1), (64, 135, 4)):
+        leaves = rand_felts(n * 1000 + w, (n, w))
+        dg, cap = O.merkle_tree_new(leaves, ch)
+        assert dg.shape[0] == 2 * (n - (1 << ch))
+        for i in range(n):
+            sib = O.merkle_prove(dg, n, ch, i)
+            assert O.merkle_verify(leaves[i], i, sib, cap)
+        # cap_height == log2(n): cap = leaf digests
+        if (1 << ch) == n:
+            for i in range(n):
+                assert (cap[i] == O.hash_or_noop(leaves[i])).all()
+
+
+def test_challenger_is_a_duplex_sponge():
+    ch = O.Challenger()
+    ch.observe([1, 2, 3])
+    a = ch.get()
+    s = O.permute([1, 2, 3] + [0] * 9)
+    assert a == int(s[7])  # pops from the end of the squeezed rate
+    assert ch.get() == int(s[6])
+    ch.observe(list(range(10, 19)))  # 9 elements: one automatic duplex at 8, one pending
+    s2 = s.copy()
+    s2[:8] = np.arange(10, 18, dtype=np.uint64)
+    s2 = O.permute(s2)
+    s3 = s2.copy()
+    s3[0] = 18
+    s3 = O.permute(s3)
+    assert ch.get() == int(s3[7])
+
+
+def test_fri_fold_matches_verifier_interpolation():
+    """prover-side fold of coefficients == verifier-side compute_evaluation on the committed leaves"""
+    log_n, rate = 7, 3
+    n = 1 << log_n
+    N = n << rate
+    coeffs = np.zeros((N, 2), np.uint64)
+    coeffs[:n] = rand_felts(5, (n, 2))
+    values = O.ext_coset_fft(coeffs, 7)
+    ch = O.Challenger()
+    ch.observe([42])
+    arity_bits = [4, 3]
+    out = O.fri_committed_trees(coeffs, values, arity_bits, ch, rate, 1)
+    log_N = log_n + rate
+    w = O.root_of_unity(log_N)
+    for x_index in (0, 5, 321, N - 1):
+        xi = x_index
+        x = 7 * pow(w, bitrev(xi, log_N), P) % P
+        leaf = out["leaves"][0][xi >> 4].reshape(16, 2)
+        ev = O.fri_compute_evaluation(x, xi & 15, 4, leaf, out["betas"][0])
+        xi >>= 4
+        x = pow(x, 16, P)
+        leaf1 = out["leaves"][1][xi >> 3].reshape(8, 2)
+        assert [int(v) for v in leaf1[xi & 7]] == ev
+        ev2 = O.fri_compute_evaluation(x, xi & 7, 3, leaf1, out["betas"][1])
+        x = pow(x, 8, P)
+        # final poly evaluated at x (extension coefficients, base point)
+        acc = [0, 0]
+        for c in reversed(out["final_poly"].tolist()):
+            acc = [(acc[0] * x + c[0]) % P, (acc[1] * x + c[1]) % P]
+        assert acc == ev2
+    assert out["final_poly"].shape[0] == (N >> 7) >> rate
+
+
+def test_pow_is_minimal_and_valid():
+    ch = O.Challenger()
+    ch.observe([9, 8, 7])
+    base = ch.clone()
+    w = O.fri_proof_of_work(ch, 10)
+    assert O.fri_pow_check(base, w, 10) == 1
+    assert all(O.fri_pow_check(base, v, 10) == 0 for v in range(w))
