@@ -27,6 +27,8 @@ SIGNATURES = {
     "p2b_launch_count": (u64, [vp]),
     "p2b_timer_start": (C.c_int, [vp]),
     "p2b_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "p2b_profile_enable": (C.c_int, [vp, C.c_int]),
+    "p2b_profile_read": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
     "p2b_batch_from_values": (C.c_int, [vp, C.POINTER(u64p), sz, u32, u32, u32, u32, C.POINTER(vp)]),
     "p2b_batch_from_coeffs": (C.c_int, [vp, C.POINTER(u64p), sz, u32, u32, u32, u32, C.POINTER(vp)]),
     "p2b_batch_from_values_dev": (C.c_int, [vp, vp, sz, u32, u32, u32, u32, C.POINTER(vp)]),

@@ -31,6 +31,18 @@ struct p2b_ctx {
   uint64_t* d_w12 = nullptr;
   uint64_t* d_rlo = nullptr;
   uint64_t* d_rhi = nullptr;
+  // optional per-stage timing
+  bool profiling = false;
+  struct StageRec {
+    int stage;
+    cudaEvent_t a, b;
+    uint64_t launches;
+  };
+  std::vector<StageRec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  int cur_stage = -1;
+  cudaEvent_t cur_ev = nullptr;
+  uint64_t cur_launch0 = 0;
   // small pinned staging buffer for accessor results
   uint64_t* h_stage = nullptr;
   size_t h_stage_bytes = 0;
@@ -114,6 +126,58 @@ static int dmalloc(p2b_ctx* ctx, uint64_t** p, size_t n_u64) {
 }
 static void dfree(p2b_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ---- stage timing -----------------------------------------------------------------------------
+enum { ST_H2D = 0, ST_INTT, ST_LDE, ST_LEAF, ST_TREE, ST_FRI, ST_TRANSCRIPT, ST_OTHER };
+static cudaEvent_t prof_event(p2b_ctx* ctx) {
+  if (!ctx->ev_pool.empty()) {
+    cudaEvent_t e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+static void stage_end(p2b_ctx* ctx) {
+  if (!ctx->profiling || ctx->cur_stage < 0) return;
+  cudaEvent_t b = prof_event(ctx);
+  cudaEventRecord(b, ctx->stream);
+  ctx->recs.push_back({ctx->cur_stage, ctx->cur_ev, b, ctx->launches - ctx->cur_launch0});
+  ctx->cur_stage = -1;
+  ctx->cur_ev = nullptr;
+}
+static void stage_begin(p2b_ctx* ctx, int stage) {
+  if (!ctx->profiling) return;
+  stage_end(ctx);
+  ctx->cur_stage = stage;
+  ctx->cur_ev = prof_event(ctx);
+  ctx->cur_launch0 = ctx->launches;
+  cudaEventRecord(ctx->cur_ev, ctx->stream);
+}
+
+extern "C" int p2b_profile_enable(p2b_ctx* ctx, int on) {
+  CHECK_CTX(ctx);
+  stage_end(ctx);
+  ctx->profiling = on != 0;
+  return P2B_OK;
+}
+extern "C" int p2b_profile_read(p2b_ctx* ctx, float* ms_out, uint64_t* count_out) {
+  CHECK_CTX(ctx);
+  if (!ms_out) return P2B_ERR_INVALID;
+  stage_end(ctx);
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->recs) {
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_out[r.stage] += ms;
+    if (count_out) count_out[r.stage] += r.launches;
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->recs.clear();
+  return P2B_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -200,6 +264,12 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   dfree(ctx, ctx->d_rhi);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->cur_ev) cudaEventDestroy(ctx->cur_ev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -464,10 +534,14 @@ static int tree_from_colmajor(p2b_ctx* ctx, p2b_tree* t, const uint64_t* d_data,
   t->d_leaves_cm = d_data;
   int rc;
   if ((rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height)))) return rc;
+  stage_begin(ctx, ST_LEAF);
   hashk::k_leaf_hash_colmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_data, n_leaves, (uint32_t)n_cols, n_leaves,
                                                                           t->d_levels);
   LAUNCH_CHECK(ctx);
-  return build_levels(ctx, t);
+  stage_begin(ctx, ST_TREE);
+  rc = build_levels(ctx, t);
+  stage_end(ctx);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ PolynomialBatch
@@ -503,7 +577,9 @@ static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, boo
     if (is_values) {
       rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
       // scratch for the two-pass inverse transform: the first n words of every LDE column
+      stage_begin(ctx, ST_INTT);
       if (rc == P2B_OK) rc = run_intt(ctx, d_in, b->d_coeffs, b->d_lde, n_cols, log_n, N);
+      stage_end(ctx);
       dfree(ctx, d_in);
     } else {
       b->d_coeffs = d_in;
@@ -511,7 +587,9 @@ static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, boo
   } else {
     dfree(ctx, d_in);
   }
+  stage_begin(ctx, ST_LDE);
   if (rc == P2B_OK) rc = run_lde(ctx, b->d_coeffs, n, b->d_lde, n_cols, log_n, rate_bits, 7);
+  stage_end(ctx);
   if (rc == P2B_OK) rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
   if (rc != P2B_OK) {
     p2b_batch_free(b);
@@ -543,7 +621,9 @@ static int batch_from_host(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_c
   int rc = check_batch_args(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, out);
   if (rc) return rc;
   uint64_t* d_in = nullptr;
+  stage_begin(ctx, ST_H2D);
   rc = upload_cols(ctx, cols, n_cols, (size_t)1 << log_n, &d_in);
+  stage_end(ctx);
   if (rc) {
     dfree(ctx, d_in);
     return rc;
@@ -572,8 +652,11 @@ static int batch_from_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, u
     b->tree.owned_by_batch = true;
     rc = dmalloc(ctx, &b->d_lde, n_cols * N);
     if (rc == P2B_OK) rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
+    stage_begin(ctx, ST_INTT);
     if (rc == P2B_OK) rc = run_intt(ctx, d_cols, b->d_coeffs, b->d_lde, n_cols, log_n, N);
+    stage_begin(ctx, ST_LDE);
     if (rc == P2B_OK) rc = run_lde(ctx, b->d_coeffs, n, b->d_lde, n_cols, log_n, rate_bits, 7);
+    stage_end(ctx);
     if (rc == P2B_OK) rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
     if (rc != P2B_OK) {
       p2b_batch_free(b);

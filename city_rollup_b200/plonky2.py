@@ -68,6 +68,19 @@ class Context:
         self.check(self.lib.p2b_timer_stop_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
+    STAGES = ("h2d", "intt", "lde", "leaf_hash", "tree_levels", "fri_fold_ntt", "transcript", "other")
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.p2b_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> ({stage: ms}, {stage: launches}) accumulated since the previous read"""
+        ms = (C.c_float * 8)()
+        cnt = (C.c_uint64 * 8)()
+        self.check(self.lib.p2b_profile_read(self.h, ms, cnt))
+        return ({s: float(ms[i]) for i, s in enumerate(self.STAGES)},
+                {s: int(cnt[i]) for i, s in enumerate(self.STAGES)})
+
     def pinned_empty(self, shape):
         """uint64 array backed by pinned host memory (freed with the context)."""
         n = int(np.prod(shape))

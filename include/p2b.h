@@ -68,6 +68,15 @@ uint64_t p2b_launch_count(const p2b_ctx *ctx);
 int p2b_timer_start(p2b_ctx *ctx);
 int p2b_timer_stop_ms(p2b_ctx *ctx, float *ms_out); /* synchronises on the stop event */
 
+/* Per-stage device timing (CUDA events recorded on the context's stream around each stage of the
+ * batch / FRI pipelines).  Stages: 0 h2d, 1 intt, 2 lde, 3 leaf_hash, 4 tree_levels, 5 fri_fold_ntt,
+ * 6 transcript, 7 other.  p2b_profile_read synchronises, ADDS the elapsed ms of every recorded stage
+ * interval since the last read to ms_out[8] and to count_out[8] (kernel launches per stage; may be NULL),
+ * and clears the record. */
+#define P2B_N_STAGES 8
+int p2b_profile_enable(p2b_ctx *ctx, int on);
+int p2b_profile_read(p2b_ctx *ctx, float *ms_out, uint64_t *count_out);
+
 /* ---------------------------------------------------------------- PolynomialBatch -------- */
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height, timing, fft_root_table)
  * cols[c] points to 2^log_n values of column c (plonky2's Vec<PolynomialValues<F>>: one allocation

@@ -19,19 +19,38 @@ static inline uint64_t sbox7(uint64_t x) {
   return gli_mul(x3, x4);
 }
 
+/* MDS layer on the two 32-bit halves of every lane: the circulant entries are < 2^6, so the 12-term sums
+ * of 32-bit halves stay below 2^42 in plain u64 accumulators (the same restructuring plonky2's optimised
+ * Goldilocks MDS uses; the result equals the u128 row sums of the naive schedule). */
 static inline void mds_layer(uint64_t s[12]) {
-  uint64_t o[12];
-  for (int r = 0; r < 12; r++) {
-    u128 acc = 0;
-    for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_CIRC[i];
-    if (r == 0) acc += (u128)s[0] * MDS_DIAG0;
-    o[r] = gli_reduce128(acc);
+  uint32_t lo[24], hi[24];
+  uint64_t al[12], ah[12];
+  static const uint32_t C32[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  for (int i = 0; i < 12; i++) {
+    lo[i] = lo[i + 12] = (uint32_t)s[i];
+    hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32);
   }
-  for (int r = 0; r < 12; r++) s[r] = o[r];
+  for (int r = 0; r < 12; r++) {
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 12; i++) {
+      a += (uint64_t)lo[i + r] * C32[i];
+      b += (uint64_t)hi[i + r] * C32[i];
+    }
+    al[r] = a;
+    ah[r] = b;
+  }
+  al[0] += (uint64_t)lo[0] * MDS_DIAG0;
+  ah[0] += (uint64_t)hi[0] * MDS_DIAG0;
+  for (int r = 0; r < 12; r++) {
+    /* al + 2^32 ah, ah = ah1:ah0 :  al + ah1*(2^32-1) + (ah0 << 32)  with one carry fold */
+    uint64_t m = al[r] + (ah[r] >> 32) * GL_EPS, t;
+    if (__builtin_add_overflow(m, ah[r] << 32, &t)) t += GL_EPS;
+    s[r] = t >= GL_P ? t - GL_P : t;
+  }
 }
 
 void poseidon_permute(uint64_t s[12]) {
-  for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+  for (int i = 0; i < 12; i++) s[i] = s[i] >= GL_P ? s[i] - GL_P : s[i];
   for (int r = 0; r < 30; r++) {
     for (int i = 0; i < 12; i++) s[i] = gli_add(s[i], RC[12 * r + i]);  /* constants on ALL lanes */
     if (r < 4 || r >= 26) {
