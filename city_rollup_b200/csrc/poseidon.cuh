@@ -9,9 +9,11 @@
 // Schedule (one permutation per thread, state in registers):
 //   * the round-constant layer of round r+1 is folded into the MDS accumulators of round r;
 //   * S-box x^7 = 4 Goldilocks multiplications with non-canonical (u64) intermediates;
-//   * the MDS layer (circulant [17,15,41,16,2,28,13,13,39,18,34,20] + diag(8,0,..)) runs on the two
-//     32-bit halves of every lane: 2 x 144 IMAD.WIDE.U32 by a small immediate into 64-bit accumulators
-//     (< 2^41, no overflow), then one 96-bit -> 64-bit fold per lane using 2^64 = 2^32 - 1;
+//   * the MDS layer (circulant [17,15,41,16,2,28,13,13,39,18,34,20] + diag(8,0,..)) runs on three
+//     22/21/21-bit limbs of every lane: 3 x 144 full-rate 32-bit IMADs into 32-bit accumulators (< 2^31,
+//     no carries), then one fold per lane using 2^64 = 2^32 - 1.  (Measured on B200: IMAD.WIDE.U32 and
+//     IMAD.HI issue at half the IMAD rate, and the first version of this kernel ran the FMA-heavy pipe at
+//     92% — profiles/r01_leaf_hash_v1.md.)
 //   * nothing is canonicalised until the digest is written.
 #pragma once
 #include "gl64.cuh"
@@ -35,55 +37,80 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
   return gl::mul_nc(x3, x4);
 }
 
-// acc_lo + 2^32 * acc_hi (both < 2^42) -> u64 congruent mod p
-__device__ __forceinline__ uint64_t fold96(uint64_t al, uint64_t ah) {
-  uint32_t ah0 = (uint32_t)ah, ah1 = (uint32_t)(ah >> 32);
+// Round constants pre-split into the three MDS limbs (bits [0,22), [22,43), [43,64)).
+__constant__ uint4 RCL[372] = {
+#include "poseidon_rc_limbs.inc"
+};
+
+// (x << K) + a in one ALU-pipe instruction (LEA); written in PTX so that the front end cannot fold the
+// shift-adds back into multiplications by 17/18
+template <int K>
+__device__ __forceinline__ uint32_t shl_add(uint32_t x, uint32_t a) {
+  uint32_t t;
+  asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(x), "n"(K));
+  return t + a;
+}
+
+// a0 + 2^22 a1 + 2^43 a2 (a_k < 2^31) -> u64 congruent mod p, using 2^64 = 2^32 - 1
+__device__ __forceinline__ uint64_t fold_limbs(uint32_t a0, uint32_t a1, uint32_t a2) {
+  uint32_t u_hi = a2 >> 21;  // bits >= 64 of a2 * 2^43
+  uint32_t u_lo = a2 << 11;  // bits 32..63 (as the high word)
+  // m = a0 + (a1 << 22) + u_hi * (2^32 - 1)  < 2^53: no overflow
+  uint64_t m = ((uint64_t)a1 << 22) + a0 + ((uint64_t)u_hi << 32) - u_hi;
   uint32_t r0, r1;
   asm("{\n\t"
-      ".reg .u64 m;\n\t"
       ".reg .u32 ml,mh,c;\n\t"
-      "mad.wide.u32 m, %4, 0xFFFFFFFF, %2;\n\t"  // al + ah1*(2^32-1)  (2^64 = 2^32-1), < 2^43
-      "mov.b64 {ml,mh}, m;\n\t"
-      "add.cc.u32 mh, mh, %3;\n\t"               // + ah0 * 2^32
+      "mov.b64 {ml,mh}, %2;\n\t"
+      "add.cc.u32 mh, mh, %3;\n\t"  // + u_lo * 2^32
       "addc.u32 c, 0, 0;\n\t"
-      "sub.cc.u32 %0, ml, c;\n\t"                // + c*(2^32-1)
+      "sub.cc.u32 %0, ml, c;\n\t"   // + c * (2^32 - 1)
       "subc.u32 mh, mh, 0;\n\t"
       "add.u32 %1, mh, c;\n\t"
       "}"
       : "=r"(r0), "=r"(r1)
-      : "l"(al), "r"(ah0), "r"(ah1));
+      : "l"(m), "r"(u_lo));
   return gl::pack(r0, r1);
 }
 
-// s <- MDS * s + rc  (rc = next round's constants, or nullptr-equivalent zero when last)
-template <bool WITH_RC>
-__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint64_t* __restrict__ rc) {
-  uint32_t lo[12], hi[12];
+// s <- MDS * s + rc (rc = limbs of the next round's constants).
+// Every lane is cut into limbs of 22/21/21 bits so that the 12-term row sums with the 6-bit circulant
+// entries (sum 256, +8 on the diagonal) plus the constant limb stay below 2^31: 3 x 144 plain 32-bit
+// IMADs (full rate on the FMA-heavy pipe) instead of 2 x 144 half-rate IMAD.WIDE, no carries at all.
+__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint4* __restrict__ rc) {
+  uint32_t l0[12], l1[12], l2[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
-    lo[i] = (uint32_t)s[i];
-    hi[i] = (uint32_t)(s[i] >> 32);
+    uint32_t lo = (uint32_t)s[i], hi = (uint32_t)(s[i] >> 32);
+    l0[i] = lo & 0x3FFFFFu;
+    l1[i] = __funnelshift_r(lo, hi, 22) & 0x1FFFFFu;
+    l2[i] = hi >> 11;
   }
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    uint64_t al, ah;
-    if (WITH_RC) {
-      uint64_t k = rc[r];
-      al = (uint32_t)k;
-      ah = k >> 32;
-    } else {
-      al = 0;
-      ah = 0;
-    }
+    uint4 k = rc[r];
+    uint32_t a0 = k.x, a1 = k.y, a2 = k.z;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      uint32_t c = MDSC[(r == 0 && i == 0) ? 12 : i];  // diag(8,0,...,0) folded into [12]
-      // explicit mad.wide.u32: nvcc otherwise strength-reduces x16/x2 into shift+mask sequences and
-      // carries a dead "hi*c" term through every accumulation
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(al) : "r"(lo[(i + r) % 12]), "r"(c));
-      asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(ah) : "r"(hi[(i + r) % 12]), "r"(c));
+      const uint32_t x0 = l0[(i + r) % 12], x1 = l1[(i + r) % 12], x2 = l2[(i + r) % 12];
+      // Pipe balancing: the S-boxes keep the FMA-heavy pipe busier than the ALU pipe, so the terms whose
+      // multiplier is 2^a (16, 2) or 2^a + 2^b (17, 18) are done as shift-adds on the ALU pipe.
+      if (i == 3) {  // x16
+        a0 = shl_add<4>(x0, a0), a1 = shl_add<4>(x1, a1), a2 = shl_add<4>(x2, a2);
+      } else if (i == 4) {  // x2
+        a0 = shl_add<1>(x0, a0), a1 = shl_add<1>(x1, a1), a2 = shl_add<1>(x2, a2);
+      } else if (i == 0 && r != 0) {  // x17
+        a0 = shl_add<4>(x0, a0 + x0), a1 = shl_add<4>(x1, a1 + x1), a2 = shl_add<4>(x2, a2 + x2);
+      } else if (i == 9) {  // x18
+        a0 = shl_add<4>(x0, shl_add<1>(x0, a0)), a1 = shl_add<4>(x1, shl_add<1>(x1, a1)),
+        a2 = shl_add<4>(x2, shl_add<1>(x2, a2));
+      } else {
+        uint32_t c = MDSC[(r == 0 && i == 0) ? 12 : i];  // diag(8,0,...,0) folded into [12]
+        a0 += x0 * c;
+        a1 += x1 * c;
+        a2 += x2 * c;
+      }
     }
-    s[r] = fold96(al, ah);
+    s[r] = fold_limbs(a0, a1, a2);
   }
 }
 
@@ -99,7 +126,7 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
     } else {
       s[0] = sbox7(s[0]);
     }
-    mds_layer<true>(s, RC + 12 * (r + 1));
+    mds_layer(s, RCL + 12 * (r + 1));
   }
 }
 

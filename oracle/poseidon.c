@@ -11,7 +11,6 @@
 static const uint64_t RC[360] = {
 #include "poseidon_rc.inc"
 };
-static const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 static const uint64_t MDS_DIAG0 = 8;
 
 static inline uint64_t sbox7(uint64_t x) {

@@ -1,0 +1,63 @@
+// poseidon_bench.cu — pure permutation throughput of city_rollup_b200/csrc/poseidon.cuh for different
+// launch bounds (occupancy vs registers).  Development tool; prints clk/perm/SM at the max clock.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../city_rollup_b200/csrc -o poseidon_bench poseidon_bench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "poseidon.cuh"
+
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k(uint64_t* io, int iters) {
+  size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = io[t] + i;
+  for (int it = 0; it < iters; it++) poseidon::permute_nc(s);
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= s[i];
+  io[t] = r;
+}
+
+template <int BLOCK, int MINB>
+void run(uint64_t* d, int sms) {
+  int blocks = sms * MINB * 4, iters = 16;
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k<BLOCK, MINB>);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<BLOCK, MINB>, BLOCK, 0);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k<BLOCK, MINB><<<blocks, BLOCK>>>(d, iters);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k<BLOCK, MINB><<<blocks, BLOCK>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  double perms = (double)blocks * BLOCK * iters;
+  printf("block=%d minb=%d regs=%d occ_blocks=%d warps/SM=%d : %.3f ms, %.3f Gperm/s, %.1f clk/perm/SM @1965MHz\n", BLOCK, MINB,
+         a.numRegs, occ, occ * BLOCK / 32, best, perms / best / 1e6, 1.965e9 * sms / (perms / (best * 1e-3)));
+}
+
+int main() {
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, 0);
+  uint64_t* d;
+  cudaMalloc(&d, (size_t)p.multiProcessorCount * 8 * 4 * 256 * 8);
+  cudaMemset(d, 1, (size_t)p.multiProcessorCount * 8 * 4 * 256 * 8);
+  run<256, 1>(d, p.multiProcessorCount);
+  run<256, 2>(d, p.multiProcessorCount);
+  run<256, 3>(d, p.multiProcessorCount);
+  run<128, 4>(d, p.multiProcessorCount);
+  run<128, 5>(d, p.multiProcessorCount);
+  run<128, 6>(d, p.multiProcessorCount);
+  run<128, 8>(d, p.multiProcessorCount);
+  run<64, 8>(d, p.multiProcessorCount);
+  return 0;
+}
