@@ -1,0 +1,181 @@
+// plonky2_b200.hpp — header-only C++17 host mirror of the plonky2 prover surface City Rollup's workers
+// call (PolynomialBatch::from_values / from_coeffs, MerkleTree::new / prove, Challenger,
+// fri_committed_trees, fri_proof_of_work), over the C ABI of include/p2b.h.  RAII handles, errors as
+// exceptions (the analogue of the anyhow::Result the reference propagates,
+// city_rollup_core_worker/src/actors/simple.rs:83).  No computation happens on the host.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/p2b.h"
+
+namespace plonky2_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error("p2b error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+using F = uint64_t;                 // GoldilocksField (raw u64)
+using HashOut = std::array<F, 4>;   // plonky2::hash::hash_types::HashOut
+using Ext = std::array<F, 2>;       // QuadraticExtension<GoldilocksField>
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int rc = p2b_init(device, &h_);
+    if (rc != P2B_OK) throw Error(rc, p2b_last_error(nullptr));
+  }
+  ~Context() { p2b_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  void check(int rc) const {
+    if (rc != P2B_OK) throw Error(rc, p2b_last_error(h_));
+  }
+  p2b_ctx* get() const { return h_; }
+
+ private:
+  p2b_ctx* h_ = nullptr;
+};
+
+// plonky2::hash::merkle_tree::MerkleTree<F, PoseidonHash>
+class MerkleTree {
+ public:
+  // MerkleTree::new(leaves, cap_height); leaves row-major n_leaves x leaf_len
+  static MerkleTree create(const Context& ctx, const std::vector<F>& leaves, size_t n_leaves, size_t leaf_len, uint32_t cap_height) {
+    p2b_tree* t = nullptr;
+    ctx.check(p2b_merkle_new(ctx.get(), leaves.data(), n_leaves, leaf_len, cap_height, &t));
+    return MerkleTree(&ctx, t, true);
+  }
+  MerkleTree(const Context* ctx, p2b_tree* t, bool owned) : ctx_(ctx), t_(t), owned_(owned) {}
+  MerkleTree(MerkleTree&& o) noexcept : ctx_(o.ctx_), t_(std::exchange(o.t_, nullptr)), owned_(o.owned_) {}
+  ~MerkleTree() { if (owned_ && t_) p2b_tree_free(t_); }
+  std::vector<HashOut> cap() const {
+    std::vector<HashOut> out(size_t(1) << p2b_tree_cap_height(t_));
+    ctx_->check(p2b_tree_cap(t_, out[0].data()));
+    return out;
+  }
+  // MerkleTree::prove(leaf_index).siblings
+  std::vector<HashOut> prove(size_t leaf_index) const {
+    size_t n = p2b_tree_n_leaves(t_), L = 0;
+    while ((size_t(1) << L) < n) L++;
+    L -= p2b_tree_cap_height(t_);
+    std::vector<HashOut> out(L ? L : 1);
+    ctx_->check(p2b_tree_prove(t_, leaf_index, out[0].data()));
+    out.resize(L);
+    return out;
+  }
+  p2b_tree* get() const { return t_; }
+
+ private:
+  const Context* ctx_;
+  p2b_tree* t_;
+  bool owned_;
+};
+
+// plonky2::fri::oracle::PolynomialBatch<F, PoseidonGoldilocksConfig, 2>
+class PolynomialBatch {
+ public:
+  // from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)
+  static PolynomialBatch from_values(const Context& ctx, const std::vector<std::vector<F>>& values, size_t rate_bits,
+                                     bool blinding, size_t cap_height) {
+    return build(ctx, values, rate_bits, blinding, cap_height, true);
+  }
+  // from_coeffs(polynomials, rate_bits, blinding, cap_height, timing, fft_root_table)
+  static PolynomialBatch from_coeffs(const Context& ctx, const std::vector<std::vector<F>>& polys, size_t rate_bits,
+                                     bool blinding, size_t cap_height) {
+    return build(ctx, polys, rate_bits, blinding, cap_height, false);
+  }
+  PolynomialBatch(PolynomialBatch&& o) noexcept : ctx_(o.ctx_), b_(std::exchange(o.b_, nullptr)) {}
+  ~PolynomialBatch() { if (b_) p2b_batch_free(b_); }
+  MerkleTree merkle_tree() const { return MerkleTree(ctx_, p2b_batch_tree(b_), false); }
+  // get_lde_values(index, step)
+  std::vector<F> get_lde_values(size_t index, size_t step) const {
+    std::vector<F> out(p2b_batch_n_cols(b_));
+    ctx_->check(p2b_batch_lde_values(b_, index, step, out.data()));
+    return out;
+  }
+  std::vector<F> coeffs(size_t col) const {
+    std::vector<F> out(size_t(1) << p2b_batch_degree_log(b_));
+    ctx_->check(p2b_batch_coeffs(b_, col, out.data()));
+    return out;
+  }
+  p2b_batch* get() const { return b_; }
+
+ private:
+  PolynomialBatch(const Context* c, p2b_batch* b) : ctx_(c), b_(b) {}
+  static PolynomialBatch build(const Context& ctx, const std::vector<std::vector<F>>& cols, size_t rate_bits, bool blinding,
+                               size_t cap_height, bool values) {
+    if (cols.empty()) throw Error(P2B_ERR_INVALID, "empty batch");
+    size_t n = cols[0].size();
+    uint32_t log_n = 0;
+    while ((size_t(1) << log_n) < n) log_n++;
+    if ((size_t(1) << log_n) != n) throw Error(P2B_ERR_INVALID, "length must be a power of two");
+    std::vector<const F*> ptrs;
+    for (auto& c : cols) {
+      if (c.size() != n) throw Error(P2B_ERR_INVALID, "ragged columns");
+      ptrs.push_back(c.data());
+    }
+    p2b_batch* b = nullptr;
+    auto fn = values ? p2b_batch_from_values : p2b_batch_from_coeffs;
+    ctx.check(fn(ctx.get(), ptrs.data(), ptrs.size(), log_n, (uint32_t)rate_bits, (uint32_t)cap_height, blinding ? 1u : 0u, &b));
+    return PolynomialBatch(&ctx, b);
+  }
+  const Context* ctx_;
+  p2b_batch* b_;
+};
+
+// plonky2::iop::challenger::Challenger<F, PoseidonHash>
+class Challenger {
+ public:
+  explicit Challenger(const Context& ctx) : ctx_(&ctx) { ctx.check(p2b_challenger_new(ctx.get(), &c_)); }
+  ~Challenger() { p2b_challenger_free(c_); }
+  Challenger(const Challenger&) = delete;
+  void observe_elements(const std::vector<F>& e) { ctx_->check(p2b_challenger_observe(c_, e.data(), e.size())); }
+  void observe_cap(const MerkleTree& t) { ctx_->check(p2b_challenger_observe_cap(c_, t.get())); }
+  std::vector<F> get_n_challenges(size_t n) {
+    std::vector<F> out(n ? n : 1);
+    ctx_->check(p2b_challenger_get(c_, n, out.data()));
+    out.resize(n);
+    return out;
+  }
+  Ext get_extension_challenge() {
+    auto v = get_n_challenges(2);
+    return {v[0], v[1]};
+  }
+  p2b_challenger* get() const { return c_; }
+
+ private:
+  const Context* ctx_;
+  p2b_challenger* c_ = nullptr;
+};
+
+// fri::prover::fri_committed_trees(coeffs, values, challenger, fri_params)
+inline std::pair<std::vector<MerkleTree>, std::vector<Ext>> fri_committed_trees(
+    const Context& ctx, const std::vector<Ext>& coeffs, const std::vector<Ext>& values, Challenger& challenger,
+    const std::vector<uint32_t>& reduction_arity_bits, uint32_t rate_bits, uint32_t cap_height) {
+  size_t len = coeffs.size(), n_final = len >> rate_bits;
+  for (uint32_t a : reduction_arity_bits) n_final >>= a;
+  std::vector<p2b_tree*> raw(reduction_arity_bits.size() ? reduction_arity_bits.size() : 1, nullptr);
+  std::vector<Ext> final_poly(n_final ? n_final : 1);
+  ctx.check(p2b_fri_commit(ctx.get(), coeffs[0].data(), values[0].data(), len, reduction_arity_bits.data(),
+                           reduction_arity_bits.size(), rate_bits, cap_height, challenger.get(), raw.data(),
+                           final_poly[0].data()));
+  std::vector<MerkleTree> trees;
+  for (size_t i = 0; i < reduction_arity_bits.size(); i++) trees.emplace_back(&ctx, raw[i], true);
+  final_poly.resize(n_final);
+  return {std::move(trees), std::move(final_poly)};
+}
+
+// fri::prover::fri_proof_of_work(challenger, config) — returns the minimal witness
+inline F fri_proof_of_work(const Context& ctx, Challenger& challenger, uint32_t proof_of_work_bits) {
+  F w = 0;
+  ctx.check(p2b_fri_pow(ctx.get(), challenger.get(), proof_of_work_bits, &w));
+  return w;
+}
+
+}  // namespace plonky2_b200

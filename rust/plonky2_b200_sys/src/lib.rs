@@ -1,0 +1,121 @@
+//! Raw bindings of include/p2b.h plus the minimal safe wrappers the patched `plonky2` crate uses.
+//! Every `extern "C"` item mirrors one declaration of the header; see INTEGRATION.md for the call
+//! sites inside plonky2 (fri/oracle.rs, hash/merkle_tree.rs, fri/prover.rs, iop/challenger.rs).
+#![allow(non_camel_case_types)]
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] pub struct p2b_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct p2b_batch { _p: [u8; 0] }
+#[repr(C)] pub struct p2b_tree { _p: [u8; 0] }
+#[repr(C)] pub struct p2b_challenger { _p: [u8; 0] }
+
+extern "C" {
+    pub fn p2b_version() -> c_int;
+    pub fn p2b_init(device: c_int, out: *mut *mut p2b_ctx) -> c_int;
+    pub fn p2b_init_on_stream(device: c_int, stream: *mut c_void, out: *mut *mut p2b_ctx) -> c_int;
+    pub fn p2b_destroy(ctx: *mut p2b_ctx);
+    pub fn p2b_last_error(ctx: *const p2b_ctx) -> *const c_char;
+    pub fn p2b_synchronize(ctx: *mut p2b_ctx) -> c_int;
+    pub fn p2b_host_alloc(ctx: *mut p2b_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn p2b_host_free(ctx: *mut p2b_ctx, p: *mut c_void) -> c_int;
+    pub fn p2b_launch_count(ctx: *const p2b_ctx) -> u64;
+    pub fn p2b_timer_start(ctx: *mut p2b_ctx) -> c_int;
+    pub fn p2b_timer_stop_ms(ctx: *mut p2b_ctx, ms: *mut f32) -> c_int;
+    pub fn p2b_profile_enable(ctx: *mut p2b_ctx, on: c_int) -> c_int;
+    pub fn p2b_profile_read(ctx: *mut p2b_ctx, ms: *mut f32, count: *mut u64) -> c_int;
+
+    pub fn p2b_batch_from_values(ctx: *mut p2b_ctx, cols: *const *const u64, n_cols: usize, log_n: u32,
+        rate_bits: u32, cap_height: u32, flags: u32, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_from_coeffs(ctx: *mut p2b_ctx, cols: *const *const u64, n_cols: usize, log_n: u32,
+        rate_bits: u32, cap_height: u32, flags: u32, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_from_values_dev(ctx: *mut p2b_ctx, d_cols: *const u64, n_cols: usize, log_n: u32,
+        rate_bits: u32, cap_height: u32, flags: u32, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_from_coeffs_dev(ctx: *mut p2b_ctx, d_cols: *const u64, n_cols: usize, log_n: u32,
+        rate_bits: u32, cap_height: u32, flags: u32, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_free(b: *mut p2b_batch);
+    pub fn p2b_batch_n_cols(b: *const p2b_batch) -> usize;
+    pub fn p2b_batch_degree_log(b: *const p2b_batch) -> u32;
+    pub fn p2b_batch_rate_bits(b: *const p2b_batch) -> u32;
+    pub fn p2b_batch_tree(b: *mut p2b_batch) -> *mut p2b_tree;
+    pub fn p2b_batch_cap(b: *mut p2b_batch, out: *mut u64) -> c_int;
+    pub fn p2b_batch_coeffs(b: *mut p2b_batch, col: usize, out: *mut u64) -> c_int;
+    pub fn p2b_batch_leaf(b: *mut p2b_batch, leaf_index: usize, out: *mut u64) -> c_int;
+    pub fn p2b_batch_lde_values(b: *mut p2b_batch, index: usize, step: usize, out: *mut u64) -> c_int;
+    pub fn p2b_batch_leaves(b: *mut p2b_batch, out: *mut u64) -> c_int;
+    pub fn p2b_batch_dev_lde(b: *const p2b_batch) -> *const u64;
+    pub fn p2b_batch_dev_coeffs(b: *const p2b_batch) -> *const u64;
+
+    pub fn p2b_merkle_new(ctx: *mut p2b_ctx, leaves: *const u64, n_leaves: usize, leaf_len: usize,
+        cap_height: u32, out: *mut *mut p2b_tree) -> c_int;
+    pub fn p2b_tree_free(t: *mut p2b_tree);
+    pub fn p2b_tree_n_leaves(t: *const p2b_tree) -> usize;
+    pub fn p2b_tree_cap_height(t: *const p2b_tree) -> u32;
+    pub fn p2b_tree_cap(t: *mut p2b_tree, out: *mut u64) -> c_int;
+    pub fn p2b_tree_prove(t: *mut p2b_tree, leaf_index: usize, out: *mut u64) -> c_int;
+    pub fn p2b_tree_digests(t: *mut p2b_tree, out: *mut u64) -> c_int;
+    pub fn p2b_tree_leaf(t: *mut p2b_tree, leaf_index: usize, out: *mut u64) -> c_int;
+
+    pub fn p2b_poseidon_permute(ctx: *mut p2b_ctx, states: *mut u64, n: usize) -> c_int;
+    pub fn p2b_hash_no_pad(ctx: *mut p2b_ctx, input: *const u64, len: usize, out: *mut u64) -> c_int;
+    pub fn p2b_two_to_one(ctx: *mut p2b_ctx, left: *const u64, right: *const u64, n: usize, out: *mut u64) -> c_int;
+
+    pub fn p2b_challenger_new(ctx: *mut p2b_ctx, out: *mut *mut p2b_challenger) -> c_int;
+    pub fn p2b_challenger_free(c: *mut p2b_challenger);
+    pub fn p2b_challenger_observe(c: *mut p2b_challenger, elems: *const u64, n: usize) -> c_int;
+    pub fn p2b_challenger_observe_cap(c: *mut p2b_challenger, t: *mut p2b_tree) -> c_int;
+    pub fn p2b_challenger_get(c: *mut p2b_challenger, n: usize, out: *mut u64) -> c_int;
+    pub fn p2b_challenger_export(c: *mut p2b_challenger, out30: *mut u64) -> c_int;
+    pub fn p2b_challenger_import(c: *mut p2b_challenger, in30: *const u64) -> c_int;
+
+    pub fn p2b_fri_commit(ctx: *mut p2b_ctx, coeffs_ext: *const u64, values_ext: *const u64, len: usize,
+        arity_bits: *const u32, n_layers: usize, rate_bits: u32, cap_height: u32,
+        challenger: *mut p2b_challenger, layers_out: *mut *mut p2b_tree, final_poly_out: *mut u64) -> c_int;
+    pub fn p2b_fri_pow(ctx: *mut p2b_ctx, challenger: *mut p2b_challenger, pow_bits: u32, witness_out: *mut u64) -> c_int;
+}
+
+/// Error type the patched plonky2 converts into `anyhow::Error` (the reference propagates it with `?`
+/// up to `SimpleActorWorker::process_job`, city_rollup_core_worker/src/actors/simple.rs:83).
+#[derive(Debug)]
+pub struct P2bError { pub code: i32, pub message: String }
+impl std::fmt::Display for P2bError {
+    fn fmt(&self, f: &mut std::fmt::Formatter<'_>) -> std::fmt::Result { write!(f, "p2b error {}: {}", self.code, self.message) }
+}
+impl std::error::Error for P2bError {}
+
+/// One context per worker thread (a p2b_ctx is not thread-safe).
+pub struct Context(pub *mut p2b_ctx);
+unsafe impl Send for Context {}
+impl Context {
+    pub fn new(device: i32) -> Result<Self, P2bError> {
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { p2b_init(device, &mut h) };
+        if rc != 0 { return Err(P2bError { code: rc, message: last_error(std::ptr::null()) }); }
+        Ok(Context(h))
+    }
+    pub fn check(&self, rc: c_int) -> Result<(), P2bError> {
+        if rc == 0 { Ok(()) } else { Err(P2bError { code: rc, message: last_error(self.0) }) }
+    }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { p2b_destroy(self.0) } } }
+
+pub fn last_error(ctx: *const p2b_ctx) -> String {
+    unsafe { CStr::from_ptr(p2b_last_error(ctx)).to_string_lossy().into_owned() }
+}
+
+/// Owning handle of a device-resident PolynomialBatch.
+pub struct Batch(pub *mut p2b_batch);
+unsafe impl Send for Batch {}
+impl Drop for Batch { fn drop(&mut self) { unsafe { p2b_batch_free(self.0) } } }
+
+/// `PolynomialBatch::from_values` for `F = GoldilocksField` (a transparent u64): one pointer per column.
+pub fn batch_from_values(ctx: &Context, cols: &[&[u64]], rate_bits: usize, cap_height: usize) -> Result<Batch, P2bError> {
+    let n = cols[0].len();
+    assert!(n.is_power_of_two() && cols.iter().all(|c| c.len() == n));
+    let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
+    let mut h = std::ptr::null_mut();
+    ctx.check(unsafe {
+        p2b_batch_from_values(ctx.0, ptrs.as_ptr(), ptrs.len(), n.trailing_zeros(), rate_bits as u32, cap_height as u32, 0, &mut h)
+    })?;
+    Ok(Batch(h))
+}
