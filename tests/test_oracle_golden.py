@@ -122,3 +122,135 @@ def test_field_mul_against_slow_mod():
     for a in vals:
         if a % P:
             assert L.gl_mul(a, L.gl_inv(a)) == 1
+
+
+# --------------------------------------------------------------------------------------------------
+# K3, FRI part: the fold convention (point order inside a layer leaf, coset shift, arity fold) pinned on
+# the stored proofs.  The FRI betas depend on the transcript (circuit digest not in the dump), so they are
+# SOLVED: in every query round the degree-15 interpolant P_q of the 16 opened layer-0 evaluations satisfies
+# P_q(beta_0) = (opened layer-1 evaluation); two rounds give beta_0 as the common root (polynomial gcd over
+# GF(p^2)), and the remaining 26 rounds — and the oracle's fri_compute_evaluation — must agree with it.
+# The same is done for beta_1 against final_poly.
+def _emul(a, b):
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def _esub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def _einv(a):
+    n = pow((a[0] * a[0] - 7 * a[1] * a[1]) % P, P - 2, P)
+    return (a[0] * n % P, (-a[1]) * n % P)
+
+
+def _interp_coeffs(xs, ys):
+    """coefficients (ext) of the polynomial through (xs[i] base, ys[i] ext)"""
+    n = len(xs)
+    master = [1]
+    for x in xs:  # master(X) *= (X - x)
+        master = [(-x * master[0]) % P] + [(master[i - 1] - x * master[i]) % P for i in range(1, len(master))] + [master[-1]]
+    out = [(0, 0)] * n
+    for i in range(n):
+        q = [0] * n  # master / (X - xs[i]) by synthetic division
+        q[n - 1] = master[n]
+        for k in range(n - 1, 0, -1):
+            q[k - 1] = (master[k] + xs[i] * q[k]) % P
+        d = 1
+        for j in range(n):
+            if j != i:
+                d = d * (xs[i] - xs[j]) % P
+        s = pow(d, P - 2, P)
+        out = [((o[0] + ys[i][0] * q[k] % P * s) % P, (o[1] + ys[i][1] * q[k] % P * s) % P) for k, o in enumerate(out)]
+    return out
+
+
+def _poly_trim(a):
+    while a and a[-1] == (0, 0):
+        a = a[:-1]
+    return a
+
+
+def _poly_mod(a, b):
+    a = _poly_trim(list(a))
+    b = _poly_trim(list(b))
+    inv = _einv(b[-1])
+    while len(a) >= len(b):
+        f = _emul(a[-1], inv)
+        sh = len(a) - len(b)
+        for i, c in enumerate(b):
+            a[sh + i] = _esub(a[sh + i], _emul(f, c))
+        a = _poly_trim(a)
+    return a
+
+
+def _poly_gcd(a, b):
+    while _poly_trim(list(b)):
+        a, b = b, _poly_mod(a, b)
+    return _poly_trim(list(a))
+
+
+def _coset_points(x, within, arity_bits):
+    arity = 1 << arity_bits
+    g = O.root_of_unity(arity_bits)
+    rev = int(format(within, f"0{arity_bits}b")[::-1], 2)
+    start = x * pow(g, arity - rev, P) % P
+    return [start * pow(g, i, P) % P for i in range(arity)]
+
+
+def _bitrev_list(v, bits):
+    return [v[int(format(i, f"0{bits}b")[::-1], 2)] for i in range(len(v))]
+
+
+def test_k3_fri_fold_convention_on_stored_proofs(params, proofs):
+    log_N = params["degree_bits"] + params["rate_bits"]
+    w = O.root_of_unity(log_N)
+    for p in proofs[:3]:
+        rounds = p["query_rounds"]
+        data = []
+        for rnd in rounds:
+            x_index = O.merkle_find_index(rnd["initial"][3][0], rnd["initial"][3][1], p["quotient_cap"])
+            x0 = 7 * pow(w, int(format(x_index, f"0{log_N}b")[::-1], 2), P) % P
+            data.append((x_index, x0))
+
+        def layer_poly(rnd, x, within, layer):
+            ev = [tuple(int(c) for c in e) for e in rnd["steps"][layer][0]]
+            return _interp_coeffs(_coset_points(x, within, 4), _bitrev_list(ev, 4))
+
+        # ---- beta_0 from rounds 0 and 1
+        polys = []
+        for q in (0, 1):
+            xi, x0 = data[q]
+            pol = layer_poly(rounds[q], x0, xi & 15, 0)
+            target = tuple(int(c) for c in rounds[q]["steps"][1][0][(xi >> 4) & 15])
+            pol[0] = _esub(pol[0], target)
+            polys.append(pol)
+        g = _poly_gcd(polys[0], polys[1])
+        assert len(g) == 2, "expected a unique common root"
+        beta0 = _emul(((-g[0][0]) % P, (-g[0][1]) % P), _einv(g[1]))
+        # ---- beta_1 from final_poly
+        fin = [tuple(int(c) for c in e) for e in p["final_poly"]]
+
+        def final_eval(x):
+            acc = (0, 0)
+            for c in reversed(fin):
+                acc = ((acc[0] * x + c[0]) % P, (acc[1] * x + c[1]) % P)
+            return acc
+
+        polys = []
+        for q in (0, 1):
+            xi, x0 = data[q]
+            x1 = pow(x0, 16, P)
+            pol = layer_poly(rounds[q], x1, (xi >> 4) & 15, 1)
+            pol[0] = _esub(pol[0], final_eval(pow(x1, 16, P)))
+            polys.append(pol)
+        g = _poly_gcd(polys[0], polys[1])
+        assert len(g) == 2
+        beta1 = _emul(((-g[0][0]) % P, (-g[0][1]) % P), _einv(g[1]))
+        # ---- every round, through the oracle's verifier-side fold
+        for rnd, (xi, x0) in zip(rounds, data):
+            e0 = O.fri_compute_evaluation(x0, xi & 15, 4, rnd["steps"][0][0], list(beta0))
+            assert e0 == [int(c) for c in rnd["steps"][1][0][(xi >> 4) & 15]]
+            x1 = pow(x0, 16, P)
+            e1 = O.fri_compute_evaluation(x1, (xi >> 4) & 15, 4, rnd["steps"][1][0], list(beta1))
+            assert tuple(e1) == final_eval(pow(x1, 16, P))
