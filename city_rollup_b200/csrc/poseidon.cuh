@@ -9,11 +9,10 @@
 // Schedule (one permutation per thread, state in registers):
 //   * the round-constant layer of round r+1 is folded into the MDS accumulators of round r;
 //   * S-box x^7 = 4 Goldilocks multiplications with non-canonical (u64) intermediates;
-//   * the MDS layer (circulant [17,15,41,16,2,28,13,13,39,18,34,20] + diag(8,0,..)) runs on three
-//     22/21/21-bit limbs of every lane: 3 x 144 full-rate 32-bit IMADs into 32-bit accumulators (< 2^31,
-//     no carries), then one fold per lane using 2^64 = 2^32 - 1.  (Measured on B200: IMAD.WIDE.U32 and
-//     IMAD.HI issue at half the IMAD rate, and the first version of this kernel ran the FMA-heavy pipe at
-//     92% — profiles/r01_leaf_hash_v1.md.)
+//   * the MDS layer (circulant [17,15,41,16,2,28,13,13,39,18,34,20] + diag(8,0,..)) runs on the FP64 pipe
+//     as exact integer arithmetic on the two 32-bit limbs of every lane (see mds_layer below), then one
+//     integer fold per lane using 2^64 = 2^32 - 1.  (History, profiles/r01_summary.md: v1 IMAD.WIDE MDS
+//     saturated the FMA-heavy pipe; v2 22/21/21-bit limbs on plain IMAD; v3 = this.)
 //   * nothing is canonicalised until the digest is written.
 #pragma once
 #include "gl64.cuh"
@@ -25,11 +24,6 @@ __constant__ uint64_t RC[372] = {
 #include "poseidon_rc.inc"
 };
 
-// MDS multipliers live in the constant bank (used as c[bank][off] operands of IMAD.WIDE.U32): as
-// immediates ptxas strength-reduces x2/x16/... into 4-instruction shift+add sequences.
-// [0..11] circulant first row, [12] = circ[0] + diag[0].
-__constant__ uint32_t MDSC[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20, 25};
-
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
   uint64_t x2 = gl::mul_nc(x, x);
   uint64_t x4 = gl::mul_nc(x2, x2);
@@ -37,81 +31,95 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
   return gl::mul_nc(x3, x4);
 }
 
-// Round constants pre-split into the three MDS limbs (bits [0,22), [22,43), [43,64)).
-__constant__ uint4 RCL[372] = {
-#include "poseidon_rc_limbs.inc"
+// ---- MDS layer on the FP64 pipe -----------------------------------------------------------------------
+// B200 keeps a full-rate FP64 pipe (measured 56-63 DFMA/clk/SM, dual-issuing with the integer pipes:
+// profiles/int32_peak.json), and a DFMA multiplies a 32-bit limb by a small MDS entry and accumulates it
+// exactly (every partial sum < 2^53).  Per 32-bit limb set the 12x12 circulant is split by
+// x^12 - 1 = (x^6 - 1)(x^6 + 1): with p_k = s_k + s_{k+6}, m_k = s_k - s_{k+6},
+//     out[r] = P[r] + M[r],  out[r+6] = P[r] - M[r],
+//     P[r] = sum_k Dh[(k-r) mod 6] p_k            Dh = (C[j] + C[j+6]) / 2 = [15,14,40,17,18,24]
+//     M[r] = sum_k +-Eh[(k-r) mod 6] m_k          Eh = (C[j] - C[j+6]) / 2 = [2,1,1,-1,-16,4]  (sign - on wrap)
+// (all entries of C[j] +- C[j+6] are even), 72 instead of 144 multiply-adds; diag(8,0,..,0) adds 4 s_0 to P[0]
+// and M[0].  Integer <-> double conversion is free of I2F/F2I: a limb x becomes the double 2^52 + x by
+// pairing it with the high word 0x43300000, the biases cancel in m_k and are removed from p_k by one DADD,
+// and the chain initialisers (poseidon_rc_f64.inc) carry 2^52 + the next round's constant, so that the low
+// 42 mantissa bits of every result ARE the integer row sum.  208 FP64 instructions per layer replace
+// 3 x 144 IMAD + limb splitting; the FMA-heavy pipe is left to the S-boxes.
+__constant__ unsigned long long RCF[720] = {
+#include "poseidon_rc_f64.inc"
 };
 
-// (x << K) + a in one ALU-pipe instruction (LEA); written in PTX so that the front end cannot fold the
-// shift-adds back into multiplications by 17/18
-template <int K>
-__device__ __forceinline__ uint32_t shl_add(uint32_t x, uint32_t a) {
-  uint32_t t;
-  asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(x), "n"(K));
-  return t + a;
-}
+#define P2B_TWO52_HI 0x43300000u
 
-// a0 + 2^22 a1 + 2^43 a2 (a_k < 2^31) -> u64 congruent mod p, using 2^64 = 2^32 - 1
-__device__ __forceinline__ uint64_t fold_limbs(uint32_t a0, uint32_t a1, uint32_t a2) {
-  uint32_t u_hi = a2 >> 21;  // bits >= 64 of a2 * 2^43
-  uint32_t u_lo = a2 << 11;  // bits 32..63 (as the high word)
-  // m = a0 + (a1 << 22) + u_hi * (2^32 - 1)  < 2^53: no overflow
-  uint64_t m = ((uint64_t)a1 << 22) + a0 + ((uint64_t)u_hi << 32) - u_hi;
+// a + 2^32 b (mod p) for a, b < 2^42 given as the bit patterns of 2^52 + a and 2^52 + b
+__device__ __forceinline__ uint64_t fold_f64(double ya, double yb) {
+  uint32_t a_lo = (uint32_t)__double2loint(ya), a_hw = (uint32_t)__double2hiint(ya);
+  uint32_t b_lo = (uint32_t)__double2loint(yb), b_hw = (uint32_t)__double2hiint(yb);
+  uint32_t b_hi = b_hw - P2B_TWO52_HI;                   // bits >= 32 of b: weight 2^64 = 2^32 - 1
+  uint32_t m = a_hw + b_hw - 2u * P2B_TWO52_HI;          // a_hi + b_hi (< 2^11)
   uint32_t r0, r1;
   asm("{\n\t"
-      ".reg .u32 ml,mh,c;\n\t"
-      "mov.b64 {ml,mh}, %2;\n\t"
-      "add.cc.u32 mh, mh, %3;\n\t"  // + u_lo * 2^32
+      ".reg .u32 yl,yh,c;\n\t"
+      "sub.cc.u32 yl, 0, %4;\n\t"     // Y = (m << 32) - b_hi  (>= 0)
+      "subc.u32 yh, %5, 0;\n\t"
+      "add.cc.u32 yl, yl, %2;\n\t"    // X + Y, X = a_lo + 2^32 b_lo
+      "addc.cc.u32 yh, yh, %3;\n\t"
       "addc.u32 c, 0, 0;\n\t"
-      "sub.cc.u32 %0, ml, c;\n\t"   // + c * (2^32 - 1)
-      "subc.u32 mh, mh, 0;\n\t"
-      "add.u32 %1, mh, c;\n\t"
+      "sub.cc.u32 %0, yl, c;\n\t"     // + c * (2^32 - 1)
+      "subc.u32 yh, yh, 0;\n\t"
+      "add.u32 %1, yh, c;\n\t"
       "}"
       : "=r"(r0), "=r"(r1)
-      : "l"(m), "r"(u_lo));
+      : "r"(a_lo), "r"(b_lo), "r"(b_hi), "r"(m));
   return gl::pack(r0, r1);
 }
 
-// s <- MDS * s + rc (rc = limbs of the next round's constants).
-// Every lane is cut into limbs of 22/21/21 bits so that the 12-term row sums with the 6-bit circulant
-// entries (sum 256, +8 on the diagonal) plus the constant limb stay below 2^31: 3 x 144 plain 32-bit
-// IMADs (full rate on the FMA-heavy pipe) instead of 2 x 144 half-rate IMAD.WIDE, no carries at all.
-__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const uint4* __restrict__ rc) {
-  uint32_t l0[12], l1[12], l2[12];
+// one limb set: x[k] = limb k (any u32) -> y[r] = 2^52 + (MDS x)[r] + K[r]
+__device__ __forceinline__ void mds_limbs_f64(const uint32_t (&x)[12], const unsigned long long* __restrict__ init,
+                                              double (&y)[12]) {
+  constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
+  constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
+  double p[6], m[6];
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint32_t lo = (uint32_t)s[i], hi = (uint32_t)(s[i] >> 32);
-    l0[i] = lo & 0x3FFFFFu;
-    l1[i] = __funnelshift_r(lo, hi, 22) & 0x1FFFFFu;
-    l2[i] = hi >> 11;
+  for (int k = 0; k < 6; k++) {
+    double a = __hiloint2double((int)P2B_TWO52_HI, (int)x[k]);      // 2^52 + x_k
+    double b = __hiloint2double((int)P2B_TWO52_HI, (int)x[k + 6]);  // 2^52 + x_{k+6}
+    m[k] = a - b;
+    p[k] = a + (b - 9007199254740992.0);  // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
   }
 #pragma unroll
-  for (int r = 0; r < 12; r++) {
-    uint4 k = rc[r];
-    uint32_t a0 = k.x, a1 = k.y, a2 = k.z;
+  for (int r = 0; r < 6; r++) {
+    double P = __longlong_as_double((long long)init[2 * r]);
+    double M = __longlong_as_double((long long)init[2 * r + 1]);
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const uint32_t x0 = l0[(i + r) % 12], x1 = l1[(i + r) % 12], x2 = l2[(i + r) % 12];
-      // Pipe balancing: the S-boxes keep the FMA-heavy pipe busier than the ALU pipe, so the terms whose
-      // multiplier is 2^a (16, 2) or 2^a + 2^b (17, 18) are done as shift-adds on the ALU pipe.
-      if (i == 3) {  // x16
-        a0 = shl_add<4>(x0, a0), a1 = shl_add<4>(x1, a1), a2 = shl_add<4>(x2, a2);
-      } else if (i == 4) {  // x2
-        a0 = shl_add<1>(x0, a0), a1 = shl_add<1>(x1, a1), a2 = shl_add<1>(x2, a2);
-      } else if (i == 0 && r != 0) {  // x17
-        a0 = shl_add<4>(x0, a0 + x0), a1 = shl_add<4>(x1, a1 + x1), a2 = shl_add<4>(x2, a2 + x2);
-      } else if (i == 9) {  // x18
-        a0 = shl_add<4>(x0, shl_add<1>(x0, a0)), a1 = shl_add<4>(x1, shl_add<1>(x1, a1)),
-        a2 = shl_add<4>(x2, shl_add<1>(x2, a2));
-      } else {
-        uint32_t c = MDSC[(r == 0 && i == 0) ? 12 : i];  // diag(8,0,...,0) folded into [12]
-        a0 += x0 * c;
-        a1 += x1 * c;
-        a2 += x2 * c;
-      }
+    for (int k = 0; k < 6; k++) {
+      const int j = (k - r + 12) % 12;  // circulant index of s_k in row r
+      double d = Dh[j % 6], e = j < 6 ? Eh[j] : -Eh[j - 6];
+      if (r == 0 && k == 0) d += 2., e += 2.;  // diag: + 4 x_0 = 2 p_0 + 2 m_0 on both chains
+      P = fma(d, p[k], P);
+      M = fma(e, m[k], M);
     }
-    s[r] = fold_limbs(a0, a1, a2);
+    if (r == 0) {
+      P = fma(2., m[0], P);
+      M = fma(2., p[0], M);
+    }
+    y[r] = P + M;
+    y[r + 6] = P - M;
   }
+}
+
+// s <- MDS * s + rc(next round); `init` = the 24 chain initialisers of that round
+__device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const unsigned long long* __restrict__ init) {
+  uint32_t x[12];
+  double ylo[12], yhi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) x[i] = (uint32_t)s[i];
+  mds_limbs_f64(x, init, ylo);
+#pragma unroll
+  for (int i = 0; i < 12; i++) x[i] = (uint32_t)(s[i] >> 32);
+  mds_limbs_f64(x, init + 12, yhi);
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = fold_f64(ylo[i], yhi[i]);
 }
 
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).
@@ -126,7 +134,7 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
     } else {
       s[0] = sbox7(s[0]);
     }
-    mds_layer(s, RCL + 12 * (r + 1));
+    mds_layer(s, RCF + 24 * r);
   }
 }
 

@@ -14,11 +14,14 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k(uint64_t* out, uint32_t a, uint32_t b) {
   uint64_t acc[CHAINS];
   uint32_t x[CHAINS], y[CHAINS];
+  double dd[CHAINS];
+  double dm = 1.0 + 1e-9 * a, da = 1e-7 * b;
 #pragma unroll
   for (int i = 0; i < CHAINS; i++) {
     acc[i] = threadIdx.x + i;
     x[i] = a + threadIdx.x * 3 + i;
-    y[i] = b + i;
+    y[i] = b + i + threadIdx.x * 5;
+    dd[i] = (double)(threadIdx.x + i) * 1e-3;
   }
 #pragma unroll 1
   for (int it = 0; it < ITERS; it++) {
@@ -50,13 +53,38 @@ __global__ void __launch_bounds__(256) k(uint64_t* out, uint32_t a, uint32_t b) 
           asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(a));
         } else if (KIND == 9) {  // SHF (funnel shift)
           asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(a));
+        } else if (KIND == 10) {  // DFMA (FP64 pipe)
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+        } else if (KIND == 11) {  // DFMA + IMAD 1:1
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+        } else if (KIND == 12) {  // DFMA + IADD3 1:1
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        } else if (KIND == 13) {  // DFMA + IMAD + IADD3 1:1:1
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        } else if (KIND == 14) {  // DADD
+          asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(dd[i]) : "d"(da));
+        } else if (KIND == 15) {  // DFMA + IMAD.WIDE 1:1
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[i]), "r"(b));
+        } else if (KIND == 16) {  // 2 DFMA + IMAD + IADD3
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+          asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        } else if (KIND == 17) {  // I2F.F64.U32 conversion
+          asm volatile("cvt.rn.f64.u32 %0, %1;" : "=d"(dd[i]) : "r"(x[i]));
+          asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(x[i]), "=r"(y[i]) : "d"(dd[i]));
         }
       }
     }
   }
   uint64_t r = 0;
 #pragma unroll
-  for (int i = 0; i < CHAINS; i++) r += acc[i] + x[i] + y[i];
+  for (int i = 0; i < CHAINS; i++) r += acc[i] + x[i] + y[i] + (uint64_t)__double_as_longlong(dd[i]);
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;  // keep results live
 }
 
@@ -102,6 +130,14 @@ int main() {
   run<7>("imadwide_rz_plus_add64", 3, d, sms);
   run<8>("lop3", 1, d, sms);
   run<9>("shf", 1, d, sms);
+  run<10>("dfma", 1, d, sms);
+  run<11>("mix_dfma_imad", 2, d, sms);
+  run<12>("mix_dfma_iadd3", 2, d, sms);
+  run<13>("mix_dfma_imad_iadd3", 3, d, sms);
+  run<14>("dadd", 1, d, sms);
+  run<15>("mix_dfma_imadwide", 2, d, sms);
+  run<16>("mix_2dfma_imad_iadd3", 4, d, sms);
+  run<17>("cvt_f64_u32_plus_mov", 1, d, sms);
   printf("  \"note\": \"thread-level instructions per second; per_sm_per_clk normalised to 1965 MHz max clock\"\n}\n");
   return 0;
 }
