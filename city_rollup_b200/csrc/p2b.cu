@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "../../include/p2b.h"
 #include "fri_kernels.cuh"
 #include "hash_kernels.cuh"
+#include "ntt2_kernels.cuh"
 #include "ntt_kernels.cuh"
 
 #define P2B_VERSION 100
@@ -31,6 +33,21 @@ struct p2b_ctx {
   uint64_t* d_w12 = nullptr;
   uint64_t* d_rlo = nullptr;
   uint64_t* d_rhi = nullptr;
+  // radix-16 path (ntt2_kernels.cuh): row-stage tables, and lazily built per-size tables kept for the
+  // life of the context (plonky2's FftRootTable analogue): strided-step twiddles keyed by (log_m, d),
+  // coset power tables keyed by (shift, log_n, rate_bits)
+  uint64_t* d_t1 = nullptr;
+  uint64_t* d_t2 = nullptr;
+  std::map<uint64_t, uint64_t*> tw_cache;
+  struct CpKey {
+    uint64_t shift;
+    uint32_t log_n, rate_bits;
+    bool operator<(const CpKey& o) const {
+      return shift != o.shift ? shift < o.shift : log_n != o.log_n ? log_n < o.log_n : rate_bits < o.rate_bits;
+    }
+  };
+  std::map<CpKey, uint64_t*> cp_cache;
+  size_t cp_cache_bytes = 0;
   // optional per-stage timing
   bool profiling = false;
   struct StageRec {
@@ -47,6 +64,7 @@ struct p2b_ctx {
   uint64_t* h_stage = nullptr;
   size_t h_stage_bytes = 0;
   nttk::Tables tables() const { return nttk::Tables{d_w12, d_rlo, d_rhi}; }
+  ntt2::RootTables roots() const { return ntt2::RootTables{d_rlo, d_rhi}; }
 };
 
 struct p2b_tree {
@@ -209,6 +227,10 @@ static int ctx_setup(p2b_ctx* ctx) {
   LAUNCH_CHECK(ctx);
   nttk::k_pow_table<<<cdiv(2048, 256), 256, 0, ctx->stream>>>(w4096, 2048, ctx->d_w12);
   LAUNCH_CHECK(ctx);
+  if ((rc = dmalloc(ctx, &ctx->d_t1, 4096))) return rc;
+  if ((rc = dmalloc(ctx, &ctx->d_t2, 256))) return rc;
+  ntt2::k_build_row_tables<<<16, 256, 0, ctx->stream>>>(ctx->roots(), ctx->d_t1, ctx->d_t2);
+  LAUNCH_CHECK(ctx);
   ctx->h_stage_bytes = 1 << 20;
   CU(ctx, cudaMallocHost((void**)&ctx->h_stage, ctx->h_stage_bytes));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -262,6 +284,10 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   dfree(ctx, ctx->d_w12);
   dfree(ctx, ctx->d_rlo);
   dfree(ctx, ctx->d_rhi);
+  dfree(ctx, ctx->d_t1);
+  dfree(ctx, ctx->d_t2);
+  for (auto& kv : ctx->tw_cache) dfree(ctx, kv.second);
+  for (auto& kv : ctx->cp_cache) dfree(ctx, kv.second);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) {
@@ -335,10 +361,170 @@ static NttPlan plan_for(uint32_t log_n) {
 }
 static inline uint32_t u32min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
+
+// ---- radix-16 path: 2^12 <= n <= 2^20 ------------------------------------------------------------
+static bool ntt2_supported(uint32_t log_n) { return log_n >= 12 && log_n <= 20; }
+
+static int ntt2_get_tw(p2b_ctx* ctx, uint32_t log_m, uint32_t d, const uint64_t** out) {
+  uint64_t key = ((uint64_t)log_m << 8) | d;
+  auto it = ctx->tw_cache.find(key);
+  if (it == ctx->tw_cache.end()) {
+    uint64_t* p = nullptr;
+    int rc;
+    if ((rc = dmalloc(ctx, &p, (size_t)1 << log_m))) return rc;
+    ntt2::k_build_tw<<<cdiv((size_t)1 << log_m, 256), 256, 0, ctx->stream>>>(ctx->roots(), log_m, d, p);
+    LAUNCH_CHECK(ctx);
+    it = ctx->tw_cache.emplace(key, p).first;
+  }
+  *out = it->second;
+  return P2B_OK;
+}
+
+static uint64_t h_mulmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); }
+static uint64_t h_powmod(uint64_t a, uint64_t e) {
+  uint64_t r = 1;
+  a %= GL_P;
+  while (e) {
+    if (e & 1) r = h_mulmod(r, a);
+    a = h_mulmod(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+
+// [2^rate_bits][n] powers of s_t = shift * w_{n << rate_bits}^t
+static int ntt2_get_cp(p2b_ctx* ctx, uint64_t shift, uint32_t log_n, uint32_t rate_bits, const uint64_t** out) {
+  p2b_ctx::CpKey key{shift % GL_P, log_n, rate_bits};
+  auto it = ctx->cp_cache.find(key);
+  if (it == ctx->cp_cache.end()) {
+    const size_t n = (size_t)1 << log_n, bytes = (n << rate_bits) * 8;
+    // bounded cache: FRI layers of different proofs reuse the same few shifts; drop everything if a caller
+    // cycles through many distinct domains
+    if (ctx->cp_cache_bytes + bytes > ((size_t)4 << 30)) {
+      for (auto& kv : ctx->cp_cache) dfree(ctx, kv.second);
+      ctx->cp_cache.clear();
+      ctx->cp_cache_bytes = 0;
+    }
+    uint64_t* p = nullptr;
+    int rc;
+    if ((rc = dmalloc(ctx, &p, n << rate_bits))) return rc;
+    const uint64_t G = 1753635133440165772ull;
+    uint64_t wN = h_powmod(G, (uint64_t)1 << (32 - (log_n + rate_bits)));
+    for (uint32_t t = 0; t < (1u << rate_bits); t++) {
+      uint64_t st = h_mulmod(key.shift, h_powmod(wN, t));
+      nttk::k_pow_table<<<cdiv(n, 256), 256, 0, ctx->stream>>>(st, n, p + (size_t)t * n);
+      LAUNCH_CHECK(ctx);
+    }
+    it = ctx->cp_cache.emplace(key, p).first;
+    ctx->cp_cache_bytes += bytes;
+  }
+  *out = it->second;
+  return P2B_OK;
+}
+
+template <bool PRESCALE>
+static int ntt2_launch_strided(p2b_ctx* ctx, uint32_t d, const ntt2::StridedParams& sp, size_t items, size_t n_cols) {
+  dim3 grid(cdiv(items, 256), (unsigned)n_cols, 1);
+  switch (d) {
+    case 1: ntt2::k_strided<1, PRESCALE><<<grid, 256, 0, ctx->stream>>>(sp); break;
+    case 2: ntt2::k_strided<2, PRESCALE><<<grid, 256, 0, ctx->stream>>>(sp); break;
+    case 3: ntt2::k_strided<3, PRESCALE><<<grid, 256, 0, ctx->stream>>>(sp); break;
+    default: ntt2::k_strided<4, PRESCALE><<<grid, 256, 0, ctx->stream>>>(sp); break;
+  }
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
+// Strided radix steps that bring every size-n transform of `buf` (n_cols columns of `total` contiguous
+// elements, total a multiple of n) down to independent 4096-point rows.  The first step reads `src`.
+// With cp != nullptr the first step is the LDE prescale step (src = coefficients, total = n << log_cosets).
+static int ntt2_strided_steps(p2b_ctx* ctx, const uint64_t* src, size_t src_stride, uint64_t* buf, size_t buf_stride,
+                              size_t n_cols, uint32_t log_n, size_t total, const uint64_t* cp, uint32_t log_cosets) {
+  uint32_t log_m = log_n;
+  bool first = true;
+  int rc;
+  while (log_m > 12) {
+    uint32_t d = log_m - 12 >= 4 ? 4 : log_m - 12;
+    ntt2::StridedParams sp{};
+    if ((rc = ntt2_get_tw(ctx, log_m, d, &sp.tw))) return rc;
+    sp.in = first ? src : buf;
+    sp.in_col_stride = first ? src_stride : buf_stride;
+    sp.out = buf;
+    sp.out_col_stride = buf_stride;
+    sp.out_coset_stride = (size_t)1 << log_n;
+    sp.log_m = log_m;
+    sp.log_n = log_n;
+    sp.log_cosets = log_cosets;
+    sp.cp = cp;
+    if (first && cp) {
+      if ((rc = ntt2_launch_strided<true>(ctx, d, sp, ((size_t)1 << log_n) >> d, n_cols))) return rc;
+    } else {
+      if ((rc = ntt2_launch_strided<false>(ctx, d, sp, (first ? (size_t)1 << log_n : total) >> d, n_cols))) return rc;
+    }
+    first = false;
+    log_m -= d;
+  }
+  return P2B_OK;
+}
+
+static int run_intt2(p2b_ctx* ctx, const uint64_t* d_vals, uint64_t* d_coeffs, uint64_t* d_tmp, size_t n_cols,
+                     uint32_t log_n, size_t tmp_poly_stride) {
+  const size_t n = (size_t)1 << log_n;
+  int rc;
+  ntt2::RowParams rp{};
+  rp.t1 = ctx->d_t1;
+  rp.t2 = ctx->d_t2;
+  rp.log_R = log_n - 12;
+  rp.scale = GL_P - ((GL_P - 1) >> log_n);  // 1/n mod p
+  rp.out = d_coeffs;
+  rp.out_col_stride = n;
+  if (log_n == 12) {
+    rp.in = d_vals;
+    rp.in_col_stride = n;
+  } else {
+    if ((rc = ntt2_strided_steps(ctx, d_vals, n, d_tmp, tmp_poly_stride, n_cols, log_n, n, nullptr, 0))) return rc;
+    rp.in = d_tmp;
+    rp.in_col_stride = tmp_poly_stride;
+  }
+  ntt2::k_row4096<2, false><<<dim3((unsigned)(n >> 12), (unsigned)n_cols, 1), 256, 0, ctx->stream>>>(rp);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
+static int run_lde2(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uint64_t* d_lde, size_t n_cols,
+                    uint32_t log_n, uint32_t rate_bits, uint64_t shift) {
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  int rc;
+  const uint64_t* cp = nullptr;
+  if ((rc = ntt2_get_cp(ctx, shift, log_n, rate_bits, &cp))) return rc;
+  ntt2::RowParams rp{};
+  rp.t1 = ctx->d_t1;
+  rp.t2 = ctx->d_t2;
+  rp.out = d_lde;
+  rp.out_col_stride = N;
+  rp.out_coset_stride = n;
+  if (log_n == 12) {
+    rp.in = d_coeffs;
+    rp.in_col_stride = in_stride;
+    rp.cp = cp;
+    rp.log_cosets = rate_bits;
+    ntt2::k_row4096<0, true><<<dim3(1, (unsigned)n_cols, 1), 256, 0, ctx->stream>>>(rp);
+    LAUNCH_CHECK(ctx);
+    return P2B_OK;
+  }
+  if ((rc = ntt2_strided_steps(ctx, d_coeffs, in_stride, d_lde, N, n_cols, log_n, N, cp, rate_bits))) return rc;
+  rp.in = d_lde;
+  rp.in_col_stride = N;
+  ntt2::k_row4096<0, false><<<dim3((unsigned)(N >> 12), (unsigned)n_cols, 1), 256, 0, ctx->stream>>>(rp);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
 // values (n_cols x n, natural) -> coefficients (n_cols x n, natural).  d_tmp: n_cols x n scratch
 // (only used when n > 2^12); may alias neither input nor output.
 static int run_intt(p2b_ctx* ctx, const uint64_t* d_vals, uint64_t* d_coeffs, uint64_t* d_tmp, size_t n_cols,
                     uint32_t log_n, size_t tmp_poly_stride) {
+  if (ntt2_supported(log_n)) return run_intt2(ctx, d_vals, d_coeffs, d_tmp, n_cols, log_n, tmp_poly_stride);
   const size_t n = (size_t)1 << log_n;
   NttPlan pl = plan_for(log_n);
   // 1/n mod p = p - (p-1)/n
@@ -403,6 +589,7 @@ static int run_intt(p2b_ctx* ctx, const uint64_t* d_vals, uint64_t* d_coeffs, ui
 // `shift` is the coset shift of the whole domain (7 for PolynomialBatch; 7^(arity^l) for FRI layers).
 static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uint64_t* d_lde, size_t n_cols,
                    uint32_t log_n, uint32_t rate_bits, uint64_t shift) {
+  if (ntt2_supported(log_n)) return run_lde2(ctx, d_coeffs, in_stride, d_lde, n_cols, log_n, rate_bits, shift);
   const size_t n = (size_t)1 << log_n, N = n << rate_bits;
   const uint32_t n_cosets = 1u << rate_bits;
   NttPlan pl = plan_for(log_n);
