@@ -115,6 +115,44 @@ void fri_compute_evaluation(uint64_t x /* base-field point of evals[x_index_with
                             unsigned x_index_within_coset, unsigned arity_bits, const uint64_t *evals,
                             const uint64_t beta[2], uint64_t out[2]);
 
+/* ---- PLONK stages between the commitments (plonk.c) ---- */
+enum {
+  P2O_GATE_NOOP = 0,
+  P2O_GATE_CONSTANT = 1,        /* p0 = num_consts */
+  P2O_GATE_PUBLIC_INPUT = 2,
+  P2O_GATE_ARITHMETIC = 3,      /* p0 = num_ops */
+  P2O_GATE_POSEIDON = 4,
+  P2O_GATE_BASE_SUM = 5,        /* BaseSumGate<2>, p0 = num_limbs */
+  P2O_GATE_U32_ARITHMETIC = 6,  /* p0 = num_ops */
+  P2O_GATE_U32_ADD_MANY = 7,    /* p0 = num_addends, p1 = num_ops */
+  P2O_GATE_U32_SUBTRACTION = 8, /* p0 = num_ops */
+  P2O_GATE_U32_RANGE_CHECK = 9  /* p0 = num_input_limbs */
+};
+typedef struct {
+  uint32_t kind, p0, p1;
+  uint32_t selector_index;         /* selectors_info.selector_indices[row] */
+  uint32_t group_start, group_end; /* selectors_info.groups[selector_index] */
+  uint32_t row;                    /* index of the gate in common_data.gates */
+} p2o_gate;
+typedef struct {
+  uint32_t degree_bits, num_wires, num_routed_wires;
+  uint32_t num_constants; /* constant columns, selectors first */
+  uint32_t num_selectors, num_challenges, quotient_degree_factor, num_partial_products, num_gate_constraints;
+  uint32_t n_gates;
+  const p2o_gate *gates;
+  const uint64_t *k_is; /* num_routed_wires */
+} p2o_circuit;
+/* wires: num_wires x n, sigmas: num_routed_wires x n (values on H, column-major).
+ * out: num_challenges * (1 + num_partial_products) columns x n: [Z_0.., partial products of challenge 0, ...] */
+void plonk_partial_products_and_zs(const p2o_circuit *c, const uint64_t *wires, const uint64_t *sigmas,
+                                   const uint64_t *betas, const uint64_t *gammas, uint64_t *out);
+/* *_leaves: the three batches' LDE leaves, row-major in leaf order (as batch_from_* write them).
+ * out_chunks: num_challenges x (quotient_degree_factor * n) coefficients = the quotient chunks in commit order */
+void plonk_compute_quotient_polys(const p2o_circuit *c, unsigned rate_bits, const uint64_t *cs_leaves,
+                                  const uint64_t *wires_leaves, const uint64_t *zs_leaves, const uint64_t *pi_hash,
+                                  const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
+                                  uint64_t *out_chunks);
+
 unsigned p2o_num_threads(void);
 
 #ifdef __cplusplus

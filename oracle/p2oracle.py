@@ -310,3 +310,56 @@ def merkle_find_index(leaf, siblings, cap):
     lib().merkle_find_index.restype = C.c_long
     return int(lib().merkle_find_index(_p(leaf), C.c_size_t(leaf.size), _p(sib), C.c_uint(sib.shape[0]), _p(cap),
                                        C.c_size_t(cap.shape[0])))
+
+
+# ---- PLONK stages between the commitments (plonk.c) ----
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM = range(6)
+GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK = 6, 7, 8, 9
+
+
+class GateStruct(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("p0", C.c_uint32), ("p1", C.c_uint32), ("selector_index", C.c_uint32),
+                ("group_start", C.c_uint32), ("group_end", C.c_uint32), ("row", C.c_uint32)]
+
+
+class CircuitStruct(C.Structure):
+    _fields_ = [("degree_bits", C.c_uint32), ("num_wires", C.c_uint32), ("num_routed_wires", C.c_uint32),
+                ("num_constants", C.c_uint32), ("num_selectors", C.c_uint32), ("num_challenges", C.c_uint32),
+                ("quotient_degree_factor", C.c_uint32), ("num_partial_products", C.c_uint32),
+                ("num_gate_constraints", C.c_uint32), ("n_gates", C.c_uint32),
+                ("gates", C.POINTER(GateStruct)), ("k_is", u64p)]
+
+
+def circuit_struct(desc):
+    """desc: dict with the CircuitStruct scalar fields, 'gates' = list of dicts (GateStruct fields), 'k_is'."""
+    gates = (GateStruct * len(desc["gates"]))(*[
+        GateStruct(g["kind"], g.get("p0", 0), g.get("p1", 0), g["selector_index"], g["group_start"], g["group_end"],
+                   g["row"]) for g in desc["gates"]])
+    k_is = arr(desc["k_is"])
+    cs = CircuitStruct(desc["degree_bits"], desc["num_wires"], desc["num_routed_wires"], desc["num_constants"],
+                       desc["num_selectors"], desc["num_challenges"], desc["quotient_degree_factor"],
+                       desc["num_partial_products"], desc["num_gate_constraints"], len(desc["gates"]),
+                       gates, _p(k_is))
+    cs._keep = (gates, k_is)
+    return cs
+
+
+def partial_products_and_zs(desc, wires, sigmas, betas, gammas):
+    """wires (num_wires, n), sigmas (num_routed, n) values on H -> (num_chal * (1 + num_pp), n)"""
+    cs = circuit_struct(desc)
+    wires, sigmas = arr(wires), arr(sigmas)
+    n = 1 << desc["degree_bits"]
+    out = np.zeros((desc["num_challenges"] * (1 + desc["num_partial_products"]), n), np.uint64)
+    lib().plonk_partial_products_and_zs(C.byref(cs), _p(wires), _p(sigmas), _p(arr(betas)), _p(arr(gammas)), _p(out))
+    return out
+
+
+def compute_quotient_polys(desc, rate_bits, cs_leaves, wires_leaves, zs_leaves, pi_hash, betas, gammas, alphas):
+    """*_leaves: (n << rate_bits, width) leaf-ordered LDE rows -> (num_chal * quotient_degree_factor, n) chunks"""
+    cs = circuit_struct(desc)
+    n = 1 << desc["degree_bits"]
+    out = np.zeros((desc["num_challenges"] * desc["quotient_degree_factor"], n), np.uint64)
+    lib().plonk_compute_quotient_polys(C.byref(cs), C.c_uint(rate_bits), _p(arr(cs_leaves)), _p(arr(wires_leaves)),
+                                       _p(arr(zs_leaves)), _p(arr(pi_hash)), _p(arr(betas)), _p(arr(gammas)),
+                                       _p(arr(alphas)), _p(out))
+    return out

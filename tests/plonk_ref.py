@@ -1,0 +1,519 @@
+"""Test-side helpers for the PLONK stages: a synthetic circuit builder with a witness
+generator, and an INDEPENDENT pure-Python restatement of plonky2 0.2.2's verifier-side `eval_vanishing_poly`
+(plonk/vanishing_poly.rs) over the quadratic extension, written against the scalar `eval_unfiltered` of every
+gate (upstream gates/*.rs; in-tree city_common_circuit/src/u32/gates/*.rs).  It is used to check the verifier
+identity  sum_k alpha^k term_k(zeta) = Z_H(zeta) * sum_i zeta^(n i) t_i(zeta)  on the quotient chunks produced by
+the oracle / the CUDA path, which pins both against a definition that shares no code with either.
+
+No real City Rollup circuit can be built here (the Rust CircuitBuilder is not available), so circuits are
+synthetic: random rows of the closed gate set with random copy constraints.
+"""
+import importlib.util
+import os
+import random
+
+import numpy as np
+
+P = 2**64 - 2**32 + 1
+W = 7  # X^2 = 7
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location(
+    "gen_poseidon_fast_tables", os.path.join(_HERE, "..", "tools", "gen_poseidon_fast_tables.py"))
+PF = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(PF)  # derives FIRST / POST / INIT / W_HATS / VS from MDS + round constants, self-checks
+
+(GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM, GATE_U32_ARITHMETIC,
+ GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK) = range(10)
+UNUSED_SELECTOR = 2**32 - 1
+
+
+class Ext:
+    """F_p[X]/(X^2 - 7)"""
+    __slots__ = ("a", "b")
+
+    def __init__(self, a, b=0):
+        self.a, self.b = a % P, b % P
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Ext) else Ext(x)
+
+    def __add__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a + o.a, self.b + o.b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a - o.a, self.b - o.b)
+
+    def __rsub__(self, o):
+        return Ext.of(o) - self
+
+    def __mul__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a * o.a + W * self.b * o.b, self.a * o.b + self.b * o.a)
+
+    __rmul__ = __mul__
+
+    def inv(self):
+        nrm = pow((self.a * self.a - W * self.b * self.b) % P, P - 2, P)
+        return Ext(self.a * nrm, -self.b * nrm)
+
+    def __pow__(self, e):
+        r, b = Ext(1), self
+        while e:
+            if e & 1:
+                r = r * b
+            b = b * b
+            e >>= 1
+        return r
+
+    def __eq__(self, o):
+        o = Ext.of(o)
+        return self.a == o.a and self.b == o.b
+
+    def __repr__(self):
+        return f"Ext({self.a}, {self.b})"
+
+
+class Fp:
+    """base field with the same operator surface as Ext (used to check a witness row by row)"""
+    __slots__ = ("a",)
+
+    def __init__(self, a):
+        self.a = a % P
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Fp) else Fp(x)
+
+    def __add__(self, o):
+        return Fp(self.a + Fp.of(o).a)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return Fp(self.a - Fp.of(o).a)
+
+    def __rsub__(self, o):
+        return Fp.of(o) - self
+
+    def __mul__(self, o):
+        return Fp(self.a * Fp.of(o).a)
+
+    __rmul__ = __mul__
+
+    def __eq__(self, o):
+        return self.a == Fp.of(o).a
+
+
+# ------------------------------------------------------------------------------------------ gates (scalar form)
+def _mds(s):
+    out = []
+    for r in range(12):
+        acc = s[r] * 0
+        for i in range(12):
+            acc = acc + s[(i + r) % 12] * PF.CIRC[i]
+        if r == 0:
+            acc = acc + s[0] * 8
+        out.append(acc)
+    return out
+
+
+def _sbox(x):
+    x2 = x * x
+    x4 = x2 * x2
+    return x * x2 * x4
+
+
+def eval_gate(kind, p0, p1, w, consts, pi_hash):
+    """constraints of one gate at one point; w / consts / pi_hash are sequences of field-like values"""
+    c = []
+    if kind == GATE_NOOP:
+        pass
+    elif kind == GATE_CONSTANT:
+        for i in range(p0):
+            c.append(consts[i] - w[i])
+    elif kind == GATE_PUBLIC_INPUT:
+        for i in range(4):
+            c.append(w[i] - pi_hash[i])
+    elif kind == GATE_ARITHMETIC:
+        for i in range(p0):
+            c.append(w[4 * i + 3] - (w[4 * i] * w[4 * i + 1] * consts[0] + w[4 * i + 2] * consts[1]))
+    elif kind == GATE_BASE_SUM:
+        acc = w[0] * 0
+        for i in reversed(range(p0)):
+            acc = acc * 2 + w[1 + i]
+        c.append(acc - w[0])
+        for i in range(p0):
+            c.append(w[1 + i] * (w[1 + i] - 1))
+    elif kind == GATE_POSEIDON:
+        SWAP, DELTA, FULL0, PARTIAL, FULL1 = 24, 25, 29, 65, 87
+        swap = w[SWAP]
+        c.append(swap * (swap - 1))
+        for i in range(4):
+            c.append(swap * (w[i + 4] - w[i]) - w[DELTA + i])
+        s = [None] * 12
+        for i in range(4):
+            s[i] = w[i] + w[DELTA + i]
+            s[i + 4] = w[i + 4] - w[DELTA + i]
+        for i in range(8, 12):
+            s[i] = w[i]
+        rnd = 0
+        for r in range(4):
+            s = [s[i] + PF.RC[12 * rnd + i] for i in range(12)]
+            if r != 0:
+                for i in range(12):
+                    sin = w[FULL0 + 12 * (r - 1) + i]
+                    c.append(s[i] - sin)
+                    s[i] = sin
+            s = _mds([_sbox(x) for x in s])
+            rnd += 1
+        s = [s[i] + PF.first_const[i] for i in range(12)]
+        t = [s[0]]
+        for i in range(11):
+            acc = s[0] * 0
+            for j in range(11):
+                acc = acc + s[1 + j] * PF.INIT[i][j]
+            t.append(acc)
+        s = t
+        for r in range(22):
+            sin = w[PARTIAL + r]
+            c.append(s[0] - sin)
+            s[0] = _sbox(sin)
+            if r < 21:
+                s[0] = s[0] + PF.post[r]
+            d = s[0] * PF.M[0][0]
+            for i in range(1, 12):
+                d = d + s[i] * PF.W_HATS[r][i - 1]
+            s = [d] + [s[i] + s[0] * PF.VS[r][i - 1] for i in range(1, 12)]
+        rnd += 22
+        for r in range(4):
+            s = [s[i] + PF.RC[12 * rnd + i] for i in range(12)]
+            for i in range(12):
+                sin = w[FULL1 + 12 * r + i]
+                c.append(s[i] - sin)
+                s[i] = sin
+            s = _mds([_sbox(x) for x in s])
+            rnd += 1
+        for i in range(12):
+            c.append(s[i] - w[12 + i])
+    elif kind == GATE_U32_ARITHMETIC:  # arithmetic_u32.rs:88-150
+        ops = p0
+        for i in range(ops):
+            m0, m1, ad, lo, hi, inv = (w[6 * i + k] for k in range(6))
+            computed = m0 * m1 + ad
+            c.append((inv * (0xFFFFFFFF - hi) - 1) * lo)
+            c.append(hi * (1 << 32) + lo - computed)
+            clo, chi = w[0] * 0, w[0] * 0
+            for j in reversed(range(32)):
+                limb = w[6 * ops + 32 * i + j]
+                c.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+                if j < 16:
+                    clo = clo * 4 + limb
+                else:
+                    chi = chi * 4 + limb
+            c.append(clo - lo)
+            c.append(chi - hi)
+    elif kind == GATE_U32_ADD_MANY:  # add_many_u32.rs:87-135
+        na, ops, per = p0, p1, p0 + 3
+        for i in range(ops):
+            computed = w[0] * 0
+            for j in range(na):
+                computed = computed + w[per * i + j]
+            computed = computed + w[per * i + na]
+            res, carry = w[per * i + na + 1], w[per * i + na + 2]
+            c.append(carry * (1 << 32) + res - computed)
+            cres, ccar = w[0] * 0, w[0] * 0
+            for j in reversed(range(18)):
+                limb = w[per * ops + 18 * i + j]
+                c.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+                if j < 16:
+                    cres = cres * 4 + limb
+                else:
+                    ccar = ccar * 4 + limb
+            c.append(cres - res)
+            c.append(ccar - carry)
+    elif kind == GATE_U32_SUBTRACTION:  # subtraction_u32.rs:82-125
+        ops = p0
+        for i in range(ops):
+            x, y, bin_, res, bout = (w[5 * i + k] for k in range(5))
+            c.append(res - (x - y - bin_ + bout * (1 << 32)))
+            comb = w[0] * 0
+            for j in reversed(range(16)):
+                limb = w[5 * ops + 16 * i + j]
+                c.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+                comb = comb * 4 + limb
+            c.append(comb - res)
+            c.append(bout * (1 - bout))
+    elif kind == GATE_U32_RANGE_CHECK:  # range_check_u32.rs:51-75
+        nl = p0
+        for i in range(nl):
+            comb = w[0] * 0
+            for j in reversed(range(16)):
+                comb = comb * 4 + w[nl + 16 * i + j]
+            c.append(comb - w[i])
+            for j in range(16):
+                limb = w[nl + 16 * i + j]
+                c.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+    else:
+        raise ValueError(kind)
+    return c
+
+
+def gate_degree(kind):
+    return {GATE_NOOP: 0, GATE_CONSTANT: 1, GATE_PUBLIC_INPUT: 1, GATE_ARITHMETIC: 3, GATE_POSEIDON: 7,
+            GATE_BASE_SUM: 2, GATE_U32_ARITHMETIC: 4, GATE_U32_ADD_MANY: 4, GATE_U32_SUBTRACTION: 4,
+            GATE_U32_RANGE_CHECK: 4}[kind]
+
+
+def gate_num_constraints(kind, p0, p1):
+    return {GATE_NOOP: 0, GATE_CONSTANT: p0, GATE_PUBLIC_INPUT: 4, GATE_ARITHMETIC: p0, GATE_POSEIDON: 123,
+            GATE_BASE_SUM: 1 + p0, GATE_U32_ARITHMETIC: p0 * 36, GATE_U32_ADD_MANY: p1 * 21,
+            GATE_U32_SUBTRACTION: p0 * 19, GATE_U32_RANGE_CHECK: p0 * 17}[kind]
+
+
+# ------------------------------------------------------------------------------------------ witness generation
+def poseidon_gate_wires(inputs, swap, rng):
+    """wire values of one PoseidonGate row (plonky2 gates/poseidon.rs PoseidonGenerator, fast partial rounds)"""
+    w = [rng.randrange(P) for _ in range(135)]
+    w[0:12] = inputs
+    w[24] = swap
+    for i in range(4):
+        w[25 + i] = swap * (inputs[i + 4] - inputs[i]) % P
+    s = list(inputs)
+    if swap:
+        s[0:4], s[4:8] = inputs[4:8], inputs[0:4]
+    rnd = 0
+    for r in range(4):
+        s = [(x + PF.RC[12 * rnd + i]) % P for i, x in enumerate(s)]
+        if r != 0:
+            w[29 + 12 * (r - 1):29 + 12 * r] = s
+        s = PF.matvec(PF.M, [pow(x, 7, P) for x in s])
+        rnd += 1
+    s = [(x + k) % P for x, k in zip(s, PF.first_const)]
+    s = [s[0]] + PF.matvec(PF.INIT, s[1:])
+    for r in range(22):
+        w[65 + r] = s[0]
+        s[0] = pow(s[0], 7, P)
+        if r < 21:
+            s[0] = (s[0] + PF.post[r]) % P
+        d = (s[0] * PF.M[0][0] + sum(a * b for a, b in zip(PF.W_HATS[r], s[1:]))) % P
+        s = [d] + [(s[i] + s[0] * PF.VS[r][i - 1]) % P for i in range(1, 12)]
+    rnd += 22
+    for r in range(4):
+        s = [(x + PF.RC[12 * rnd + i]) % P for i, x in enumerate(s)]
+        w[87 + 12 * r:87 + 12 * (r + 1)] = s
+        s = PF.matvec(PF.M, [pow(x, 7, P) for x in s])
+        rnd += 1
+    w[12:24] = s
+    return w
+
+
+def _limbs2(v, count):
+    return [(v >> (2 * j)) & 3 for j in range(count)]
+
+
+class SyntheticCircuit:
+    """Random satisfiable circuit over a list of gates [(kind, p0, p1)], split into selector groups."""
+
+    def __init__(self, degree_bits, gates, groups, seed, num_wires=135, num_routed=80, num_gate_consts=2,
+                 num_challenges=2, quotient_degree_factor=8, link_prob=0.3):
+        rng = random.Random(seed)
+        self.degree_bits, self.n = degree_bits, 1 << degree_bits
+        n = self.n
+        self.gates, self.groups = gates, groups
+        self.num_wires, self.num_routed = num_wires, num_routed
+        self.num_selectors = len(groups)
+        self.num_constants = self.num_selectors + num_gate_consts
+        self.num_challenges, self.qdf = num_challenges, quotient_degree_factor
+        self.num_pp = -(-num_routed // quotient_degree_factor) - 1
+        self.k_is = [pow(7, j, P) for j in range(num_routed)]
+        self.pi_hash = [rng.randrange(P) for _ in range(4)]
+        sel_of = {}
+        for gi, (a, b) in enumerate(groups):
+            for g in range(a, b):
+                sel_of[g] = gi
+        self.sel_of = sel_of
+        # plonky2 groups gates so that selector filter + gate stay within the quotient degree bound
+        for a, b in groups:
+            filt = (b - a - 1) + (1 if len(groups) > 1 else 0)
+            assert all(filt + gate_degree(gates[g][0]) <= quotient_degree_factor for g in range(a, b)), "degree bound"
+        # every gate at least once (public input first, as plonky2 places it), then random
+        order = list(range(len(gates)))
+        row_gate = order + [rng.randrange(len(gates)) for _ in range(n - len(order))]
+        assert len(row_gate) == n
+        self.row_gate = row_gate
+        consts = [[0] * n for _ in range(self.num_constants)]
+        wires = [[0] * n for _ in range(num_wires)]
+        parent = {}
+
+        def find(x):
+            while parent.get(x, x) != x:
+                parent[x] = parent.get(parent[x], parent[x])
+                x = parent[x]
+            return x
+
+        def pick(row, col):
+            """value for a free felt-typed routed input: maybe copied from an earlier routed slot"""
+            if row > 0 and col < num_routed and rng.random() < link_prob:
+                r2, c2 = rng.randrange(row), rng.randrange(num_routed)
+                parent[find((row, col))] = find((r2, c2))
+                return wires[c2][r2]
+            return rng.randrange(P)
+
+        for i, g in enumerate(row_gate):
+            kind, p0, p1 = gates[g]
+            for s in range(self.num_selectors):
+                consts[s][i] = g if s == sel_of[g] else UNUSED_SELECTOR
+            gc = [rng.randrange(P) for _ in range(num_gate_consts)]
+            row = [None] * num_wires
+            if kind == GATE_NOOP:
+                row = [pick(i, c) for c in range(num_wires)]
+            elif kind == GATE_CONSTANT:
+                row = [gc[c] if c < p0 else pick(i, c) for c in range(num_wires)]
+            elif kind == GATE_PUBLIC_INPUT:
+                row = [self.pi_hash[c] if c < 4 else pick(i, c) for c in range(num_wires)]
+            elif kind == GATE_ARITHMETIC:
+                row = [0 if (c < 4 * p0 and c % 4 == 3) else pick(i, c) for c in range(num_wires)]
+                for o in range(p0):
+                    row[4 * o + 3] = (row[4 * o] * row[4 * o + 1] * gc[0] + row[4 * o + 2] * gc[1]) % P
+            elif kind == GATE_POSEIDON:
+                inputs = [pick(i, c) for c in range(12)]
+                row = poseidon_gate_wires(inputs, rng.randrange(2), rng)
+            elif kind == GATE_BASE_SUM:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                bits = [rng.randrange(2) for _ in range(p0)]
+                row[1:1 + p0] = bits
+                row[0] = sum(b << k for k, b in enumerate(bits))
+            elif kind == GATE_U32_ARITHMETIC:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                for o in range(p0):
+                    m0, m1, ad = (rng.randrange(2**32) for _ in range(3))
+                    if o == 0:
+                        m0 = m1 = ad = 2**32 - 1  # high limb = u32::MAX - 1, edge of the canonicity check
+                    out = m0 * m1 + ad
+                    lo, hi = out & 0xFFFFFFFF, out >> 32
+                    inv = pow((0xFFFFFFFF - hi) % P, P - 2, P)
+                    row[6 * o:6 * o + 6] = [m0, m1, ad, lo, hi, inv]
+                    row[6 * p0 + 32 * o:6 * p0 + 32 * (o + 1)] = _limbs2(lo, 16) + _limbs2(hi, 16)
+            elif kind == GATE_U32_ADD_MANY:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                na, ops, per = p0, p1, p0 + 3
+                for o in range(ops):
+                    add = [rng.randrange(2**32) for _ in range(na)]
+                    carry = rng.randrange(2**32)
+                    tot = sum(add) + carry
+                    res, oc = tot & 0xFFFFFFFF, tot >> 32
+                    row[per * o:per * (o + 1)] = add + [carry, res, oc]
+                    row[per * ops + 18 * o:per * ops + 18 * (o + 1)] = _limbs2(res, 16) + _limbs2(oc, 2)
+            elif kind == GATE_U32_SUBTRACTION:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                for o in range(p0):
+                    x, y, bi = rng.randrange(2**32), rng.randrange(2**32), rng.randrange(2)
+                    d = x - y - bi
+                    bo = 1 if d < 0 else 0
+                    res = d + (bo << 32)
+                    row[5 * o:5 * o + 5] = [x, y, bi, res, bo]
+                    row[5 * p0 + 16 * o:5 * p0 + 16 * (o + 1)] = _limbs2(res, 16)
+            elif kind == GATE_U32_RANGE_CHECK:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                for o in range(p0):
+                    v = rng.randrange(2**32)
+                    row[o] = v
+                    row[p0 + 16 * o:p0 + 16 * (o + 1)] = _limbs2(v, 16)
+            for c in range(num_gate_consts):
+                consts[self.num_selectors + c][i] = gc[c]
+            for c in range(num_wires):
+                wires[c][i] = row[c]
+            # the gate's own constraints hold on this row
+            cons = eval_gate(kind, p0, p1, [Fp(x) for x in row], [Fp(x) for x in gc], [Fp(x) for x in self.pi_hash])
+            assert all(x == 0 for x in cons), (kind, [k for k, x in enumerate(cons) if not x == 0][:5])
+        self.wires, self.consts = wires, consts
+        # sigma: every class of linked slots becomes one cycle
+        classes = {}
+        for r in range(n):
+            for c in range(num_routed):
+                classes.setdefault(find((r, c)), []).append((r, c))
+        omega = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - degree_bits), P)
+        self.subgroup = [pow(omega, i, P) for i in range(n)]
+        sigmas = [[0] * n for _ in range(num_routed)]
+        for members in classes.values():
+            assert len({wires[c][r] for r, c in members}) == 1
+            for idx, (r, c) in enumerate(members):
+                r2, c2 = members[(idx + 1) % len(members)]
+                sigmas[c][r] = self.k_is[c2] * self.subgroup[r2] % P
+        self.sigmas = sigmas
+        self.num_gate_constraints = max(gate_num_constraints(*g) for g in gates)
+
+    def desc(self):
+        gates = []
+        for g, (kind, p0, p1) in enumerate(self.gates):
+            s = self.sel_of[g]
+            gates.append(dict(kind=kind, p0=p0, p1=p1, selector_index=s, group_start=self.groups[s][0],
+                              group_end=self.groups[s][1], row=g))
+        return dict(degree_bits=self.degree_bits, num_wires=self.num_wires, num_routed_wires=self.num_routed,
+                    num_constants=self.num_constants, num_selectors=self.num_selectors,
+                    num_challenges=self.num_challenges, quotient_degree_factor=self.qdf,
+                    num_partial_products=self.num_pp, num_gate_constraints=self.num_gate_constraints,
+                    gates=gates, k_is=self.k_is)
+
+    def constants_sigmas_values(self):
+        return [np.array(c, dtype=np.uint64) for c in self.consts + self.sigmas]
+
+    def wire_values(self):
+        return [np.array(c, dtype=np.uint64) for c in self.wires]
+
+
+# ------------------------------------------------------------------------------------------ verifier identity
+def horner_ext(coeffs, x):
+    acc = Ext(0)
+    for c in reversed(coeffs):
+        acc = acc * x + int(c)
+    return acc
+
+
+def eval_vanishing_poly_ext(circ, zeta, consts_z, sigmas_z, wires_z, zs_z, zs_next_z, pps_z, betas, gammas, alphas):
+    """plonky2 plonk/vanishing_poly.rs::eval_vanishing_poly at zeta (no lookups); returns one Ext per challenge.
+    pps_z[i] = the num_pp partial-product openings of challenge i."""
+    n = circ.n
+    zeta_n = zeta ** n
+    z_h = zeta_n - 1
+    l0 = z_h * (Ext(n) * (zeta - 1)).inv()
+    terms_z1, terms_pp = [], []
+    deg = circ.qdf
+    for i in range(circ.num_challenges):
+        terms_z1.append(l0 * (zs_z[i] - 1))
+        num = [wires_z[j] + zeta * (betas[i] * circ.k_is[j] % P) + gammas[i] for j in range(circ.num_routed)]
+        den = [wires_z[j] + sigmas_z[j] * betas[i] + gammas[i] for j in range(circ.num_routed)]
+        accs = [zs_z[i]] + list(pps_z[i]) + [zs_next_z[i]]
+        for k in range(circ.num_pp + 1):
+            np_, dp = Ext(1), Ext(1)
+            for j in range(k * deg, min((k + 1) * deg, circ.num_routed)):
+                np_, dp = np_ * num[j], dp * den[j]
+            terms_pp.append(accs[k] * np_ - accs[k + 1] * dp)
+    gate_terms = [Ext(0)] * circ.num_gate_constraints
+    pi = [Ext(x) for x in circ.pi_hash]
+    for g, (kind, p0, p1) in enumerate(circ.gates):
+        s = consts_z[circ.sel_of[g]]
+        a, b = circ.groups[circ.sel_of[g]]
+        filt = Ext(1)
+        for i in range(a, b):
+            if i != g:
+                filt = filt * (Ext(i) - s)
+        if circ.num_selectors > 1:
+            filt = filt * (Ext(UNUSED_SELECTOR) - s)
+        cons = eval_gate(kind, p0, p1, wires_z, consts_z[circ.num_selectors:], pi)
+        for k, cv in enumerate(cons):
+            gate_terms[k] = gate_terms[k] + cv * filt
+    terms = terms_z1 + terms_pp + gate_terms
+    out = []
+    for i in range(circ.num_challenges):
+        acc = Ext(0)
+        for tv in reversed(terms):
+            acc = acc * alphas[i] + tv
+        out.append(acc)
+    return out, z_h, zeta_n

@@ -1,0 +1,77 @@
+"""CPU: the oracle's PLONK stages (oracle/plonk.c: partial products / Z, compute_quotient_polys, gate evaluators)
+against the independent extension-field restatement of the verifier identity in tests/plonk_ref.py."""
+import random
+
+import numpy as np
+import pytest
+
+import p2oracle as O
+import plonk_ref as R
+
+P = R.P
+
+ALL_GATES = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0),
+             (R.GATE_POSEIDON, 0, 0), (R.GATE_BASE_SUM, 63, 0), (R.GATE_U32_ARITHMETIC, 3, 0),
+             (R.GATE_U32_ADD_MANY, 3, 5), (R.GATE_U32_SUBTRACTION, 6, 0), (R.GATE_U32_RANGE_CHECK, 7, 0)]
+
+
+def prove_plonk_part(circ, seed, rate_bits=3, cap_height=1):
+    """wires commit -> Z / partial products -> quotient chunks, all through the oracle"""
+    rng = random.Random(seed)
+    d = circ.desc()
+    betas = [rng.randrange(P) for _ in range(circ.num_challenges)]
+    gammas = [rng.randrange(P) for _ in range(circ.num_challenges)]
+    alphas = [rng.randrange(P) for _ in range(circ.num_challenges)]
+    cs = O.batch_from_values(circ.constants_sigmas_values(), rate_bits, cap_height, want_digests=False)
+    wi = O.batch_from_values(circ.wire_values(), rate_bits, cap_height, want_digests=False)
+    zs_vals = O.partial_products_and_zs(d, np.array(circ.wires, dtype=np.uint64), np.array(circ.sigmas, dtype=np.uint64),
+                                        betas, gammas)
+    zs = O.batch_from_values(list(zs_vals), rate_bits, cap_height, want_digests=False)
+    chunks = O.compute_quotient_polys(d, rate_bits, cs["leaves"], wi["leaves"], zs["leaves"], circ.pi_hash, betas,
+                                      gammas, alphas)
+    return dict(betas=betas, gammas=gammas, alphas=alphas, cs=cs, wires=wi, zs=zs, zs_vals=zs_vals, chunks=chunks)
+
+
+def check_verifier_identity(circ, pr, seed):
+    rng = random.Random(seed)
+    zeta = R.Ext(rng.randrange(P), rng.randrange(P))
+    g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - circ.degree_bits), P)
+    ev = lambda coeffs, x: [R.horner_ext(c, x) for c in coeffs]
+    cs_z = ev(pr["cs"]["coeffs"], zeta)
+    wires_z = ev(pr["wires"]["coeffs"], zeta)
+    zs_all_z = ev(pr["zs"]["coeffs"], zeta)
+    zs_next = ev(pr["zs"]["coeffs"][:circ.num_challenges], zeta * g)
+    nch, npp = circ.num_challenges, circ.num_pp
+    pps = [zs_all_z[nch + i * npp:nch + (i + 1) * npp] for i in range(nch)]
+    van, z_h, zeta_n = R.eval_vanishing_poly_ext(circ, zeta, cs_z[:circ.num_constants], cs_z[circ.num_constants:],
+                                                 wires_z, zs_all_z[:nch], zs_next, pps, pr["betas"], pr["gammas"],
+                                                 pr["alphas"])
+    for i in range(nch):
+        t = R.Ext(0)
+        for k in reversed(range(circ.qdf)):
+            t = t * zeta_n + R.horner_ext(pr["chunks"][i * circ.qdf + k], zeta)
+        assert van[i] == z_h * t, f"verifier identity fails for challenge {i}"
+
+
+@pytest.mark.parametrize("degree_bits,gates,groups,seed", [
+    (4, ALL_GATES[:4], [(0, 4)], 1),
+    (5, ALL_GATES[:5], [(0, 4), (4, 5)], 2),
+    (6, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 3),
+])
+def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
+    circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)
+    pr = prove_plonk_part(circ, seed + 100)
+    # Z starts at 1 and the grand product closes: Z(w^(n-1)) * (last row's quotient) = 1 is implied by the
+    # identity below; the first is checked directly
+    assert all(int(pr["zs_vals"][i][0]) == 1 for i in range(circ.num_challenges))
+    check_verifier_identity(circ, pr, seed + 200)
+    check_verifier_identity(circ, pr, seed + 201)
+
+
+def test_broken_witness_is_detected():
+    """the identity check has teeth: one flipped wire breaks it"""
+    circ = R.SyntheticCircuit(4, ALL_GATES[:4], [(0, 4)], 9)
+    circ.wires[3][5] = (circ.wires[3][5] + 1) % P
+    pr = prove_plonk_part(circ, 11)
+    with pytest.raises(AssertionError):
+        check_verifier_identity(circ, pr, 12)
