@@ -45,6 +45,11 @@ SIGNATURES = {
     "p2b_batch_leaves": (C.c_int, [vp, u64p]),
     "p2b_batch_dev_lde": (vp, [vp]),
     "p2b_batch_dev_coeffs": (vp, [vp]),
+    "p2b_batch_values": (C.c_int, [vp, sz, u64p]),
+    "p2b_circuit_new": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "p2b_circuit_free": (None, [vp]),
+    "p2b_zs_partial_products_commit": (C.c_int, [vp, vp, vp, vp, u64p, u64p, u32, u32, C.POINTER(vp)]),
+    "p2b_quotient_commit": (C.c_int, [vp, vp, vp, vp, vp, u64p, u64p, u64p, u64p, u32, u32, C.POINTER(vp)]),
     "p2b_merkle_new": (C.c_int, [vp, u64p, sz, sz, u32, C.POINTER(vp)]),
     "p2b_tree_free": (None, [vp]),
     "p2b_tree_n_leaves": (sz, [vp]),
@@ -66,6 +71,20 @@ SIGNATURES = {
     "p2b_fri_commit": (C.c_int, [vp, u64p, u64p, sz, C.POINTER(u32), sz, u32, u32, vp, C.POINTER(vp), u64p]),
     "p2b_fri_pow": (C.c_int, [vp, vp, u32, u64p]),
 }
+
+
+
+class GateStruct(C.Structure):  # p2b_gate
+    _fields_ = [("kind", u32), ("p0", u32), ("p1", u32), ("selector_index", u32), ("group_start", u32),
+                ("group_end", u32), ("row", u32)]
+
+
+class CircuitDescStruct(C.Structure):  # p2b_circuit_desc
+    _fields_ = [("degree_bits", u32), ("num_wires", u32), ("num_routed_wires", u32), ("num_constants", u32),
+                ("num_selectors", u32), ("num_challenges", u32), ("quotient_degree_factor", u32),
+                ("num_partial_products", u32), ("num_gate_constraints", u32), ("n_gates", u32),
+                ("gates", C.POINTER(GateStruct)), ("k_is", u64p)]
+
 
 _lib = None
 

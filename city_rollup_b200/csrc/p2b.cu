@@ -16,6 +16,7 @@
 #include "hash_kernels.cuh"
 #include "ntt2_kernels.cuh"
 #include "ntt_kernels.cuh"
+#include "plonk_kernels.cuh"
 
 #define P2B_VERSION 100
 
@@ -86,7 +87,15 @@ struct p2b_batch {
   uint32_t log_n = 0, rate_bits = 0, cap_height = 0;
   uint64_t* d_coeffs = nullptr;  // n_cols x n
   uint64_t* d_lde = nullptr;     // n_cols x (n << rate_bits), leaf order
+  uint64_t* d_values = nullptr;  // n_cols x n values on H (P2B_KEEP_VALUES)
   p2b_tree tree;
+};
+
+struct p2b_circuit {
+  p2b_ctx* ctx = nullptr;
+  p2b_circuit_desc d{};
+  plonk::Gate* d_gates = nullptr;
+  uint64_t* d_k_is = nullptr;
 };
 
 struct p2b_challenger {
@@ -741,12 +750,14 @@ static int check_batch_args(p2b_ctx* ctx, const void* cols, size_t n_cols, uint3
   if (rate_bits > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "rate_bits %u > 6", rate_bits);
   if (cap_height > log_n + rate_bits)
     return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds log2(#leaves) = %u", cap_height, log_n + rate_bits);
-  if (flags != 0) return fail(ctx, P2B_ERR_UNSUPPORTED, "blinding (salted) batches are not supported (flags=%u)", flags);
+  if (flags & ~P2B_KEEP_VALUES)
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "blinding (salted) batches are not supported (flags=%u)", flags);
   return P2B_OK;
 }
 
 static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, bool is_values, size_t n_cols,
-                       uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
+                       uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out,
+                       bool keep_values = false) {
   const size_t n = (size_t)1 << log_n, N = n << rate_bits;
   p2b_batch* b = new (std::nothrow) p2b_batch();
   if (!b) {
@@ -767,7 +778,10 @@ static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, boo
       stage_begin(ctx, ST_INTT);
       if (rc == P2B_OK) rc = run_intt(ctx, d_in, b->d_coeffs, b->d_lde, n_cols, log_n, N);
       stage_end(ctx);
-      dfree(ctx, d_in);
+      if (keep_values)
+        b->d_values = d_in;
+      else
+        dfree(ctx, d_in);
     } else {
       b->d_coeffs = d_in;
     }
@@ -815,7 +829,8 @@ static int batch_from_host(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_c
     dfree(ctx, d_in);
     return rc;
   }
-  return batch_build(ctx, d_in, is_values, n_cols, log_n, rate_bits, cap_height, out);
+  return batch_build(ctx, d_in, is_values, n_cols, log_n, rate_bits, cap_height, out,
+                     is_values && (flags & P2B_KEEP_VALUES));
 }
 
 static int batch_from_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, uint32_t log_n, uint32_t rate_bits,
@@ -839,6 +854,13 @@ static int batch_from_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, u
     b->tree.owned_by_batch = true;
     rc = dmalloc(ctx, &b->d_lde, n_cols * N);
     if (rc == P2B_OK) rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
+    if (rc == P2B_OK && (flags & P2B_KEEP_VALUES)) {
+      rc = dmalloc(ctx, &b->d_values, n_cols * n);
+      if (rc == P2B_OK) {
+        cudaError_t e = cudaMemcpyAsync(b->d_values, d_cols, n_cols * n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+      }
+    }
     stage_begin(ctx, ST_INTT);
     if (rc == P2B_OK) rc = run_intt(ctx, d_cols, b->d_coeffs, b->d_lde, n_cols, log_n, N);
     stage_begin(ctx, ST_LDE);
@@ -881,6 +903,7 @@ extern "C" void p2b_batch_free(p2b_batch* b) {
   cudaSetDevice(ctx->device);
   dfree(ctx, b->d_coeffs);
   dfree(ctx, b->d_lde);
+  dfree(ctx, b->d_values);
   dfree(ctx, b->tree.d_levels);
   delete b;
 }
@@ -904,6 +927,259 @@ extern "C" int p2b_batch_coeffs(p2b_batch* b, size_t col, uint64_t* out) {
   size_t n = (size_t)1 << b->log_n;
   return d2h(ctx, out, b->d_coeffs + col * n, n);
 }
+extern "C" int p2b_batch_values(p2b_batch* b, size_t col, uint64_t* out) {
+  if (!b || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  if (!b->d_values) return fail(ctx, P2B_ERR_INVALID, "batch was not built from values with P2B_KEEP_VALUES");
+  if (col >= b->n_cols) return fail(ctx, P2B_ERR_INVALID, "column %zu out of range", col);
+  size_t n = (size_t)1 << b->log_n;
+  return d2h(ctx, out, b->d_values + col * n, n);
+}
+
+// ------------------------------------------------------------------------------------------------ PLONK stages
+extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_circuit** out) {
+  CHECK_CTX(ctx);
+  if (!desc || !out || !desc->gates || !desc->k_is) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const p2b_circuit_desc& d = *desc;
+  if (d.degree_bits > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "degree_bits %u > 24", d.degree_bits);
+  if (d.num_challenges == 0 || d.num_challenges > (uint32_t)plonk::MAX_CHALLENGES)
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "num_challenges must be in 1..%d", plonk::MAX_CHALLENGES);
+  if (d.num_routed_wires == 0 || d.num_routed_wires > d.num_wires) return fail(ctx, P2B_ERR_INVALID, "num_routed_wires");
+  if (d.quotient_degree_factor == 0 || (d.quotient_degree_factor & (d.quotient_degree_factor - 1)))
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "quotient_degree_factor %u is not a power of two", d.quotient_degree_factor);
+  if (d.num_partial_products + 1 != (d.num_routed_wires + d.quotient_degree_factor - 1) / d.quotient_degree_factor)
+    return fail(ctx, P2B_ERR_INVALID, "num_partial_products %u does not match ceil(%u / %u) - 1", d.num_partial_products,
+                d.num_routed_wires, d.quotient_degree_factor);
+  if (d.num_selectors > d.num_constants) return fail(ctx, P2B_ERR_INVALID, "num_selectors > num_constants");
+  if (d.n_gates == 0) return fail(ctx, P2B_ERR_INVALID, "no gates");
+  for (uint32_t g = 0; g < d.n_gates; g++) {
+    const p2b_gate& gt = d.gates[g];
+    if (gt.kind >= plonk::GATE_KIND_COUNT) return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: unknown kind %u", g, gt.kind);
+    if (gt.selector_index >= d.num_selectors || gt.group_start > gt.row || gt.row >= gt.group_end)
+      return fail(ctx, P2B_ERR_INVALID, "gate %u: bad selector layout", g);
+    // wires / constants / constraints the gate touches must exist
+    uint32_t wires = 0, consts = 0, cons = 0;
+    switch (gt.kind) {
+      case plonk::GATE_CONSTANT: wires = gt.p0, consts = gt.p0, cons = gt.p0; break;
+      case plonk::GATE_PUBLIC_INPUT: wires = 4, cons = 4; break;
+      case plonk::GATE_ARITHMETIC: wires = 4 * gt.p0, consts = 2, cons = gt.p0; break;
+      case plonk::GATE_POSEIDON: wires = 135, cons = 123; break;
+      case plonk::GATE_BASE_SUM: wires = 1 + gt.p0, cons = 1 + gt.p0; break;
+      case plonk::GATE_U32_ARITHMETIC: wires = 38 * gt.p0, cons = 36 * gt.p0; break;
+      case plonk::GATE_U32_ADD_MANY: wires = (gt.p0 + 3 + 18) * gt.p1, cons = 21 * gt.p1; break;
+      case plonk::GATE_U32_SUBTRACTION: wires = 21 * gt.p0, cons = 19 * gt.p0; break;
+      case plonk::GATE_U32_RANGE_CHECK: wires = 17 * gt.p0, cons = 17 * gt.p0; break;
+      default: break;
+    }
+    if (wires > d.num_wires || consts > d.num_constants - d.num_selectors || cons > d.num_gate_constraints)
+      return fail(ctx, P2B_ERR_INVALID, "gate %u (kind %u) needs %u wires / %u constants / %u constraints", g, gt.kind,
+                  wires, consts, cons);
+  }
+  p2b_circuit* c = new (std::nothrow) p2b_circuit();
+  if (!c) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  c->ctx = ctx;
+  c->d = d;
+  c->d.gates = nullptr;
+  c->d.k_is = nullptr;
+  static_assert(sizeof(plonk::Gate) == sizeof(p2b_gate), "gate layout");
+  int rc = dmalloc(ctx, (uint64_t**)&c->d_gates, (d.n_gates * sizeof(p2b_gate) + 7) / 8);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &c->d_k_is, d.num_routed_wires);
+  if (rc == P2B_OK) {
+    // pageable sources: the copies are complete (staged) when cudaMemcpyAsync returns
+    cudaError_t e = cudaMemcpyAsync(c->d_gates, d.gates, d.n_gates * sizeof(p2b_gate), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(c->d_k_is, d.k_is, d.num_routed_wires * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "circuit upload: %s", cudaGetErrorString(e));
+  }
+  if (rc != P2B_OK) {
+    p2b_circuit_free(c);
+    return rc;
+  }
+  *out = c;
+  return P2B_OK;
+}
+
+extern "C" void p2b_circuit_free(p2b_circuit* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  dfree(c->ctx, c->d_gates);
+  dfree(c->ctx, c->d_k_is);
+  delete c;
+}
+
+static int check_plonk_batches(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires) {
+  if (!c || !cs || !wires) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (c->ctx != ctx || cs->ctx != ctx || wires->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "handle of another context");
+  if (cs->log_n != c->d.degree_bits || wires->log_n != c->d.degree_bits)
+    return fail(ctx, P2B_ERR_INVALID, "batch degree does not match the circuit");
+  if (cs->n_cols != (size_t)c->d.num_constants + c->d.num_routed_wires)
+    return fail(ctx, P2B_ERR_INVALID, "constants_sigmas has %zu columns, expected %u", cs->n_cols,
+                c->d.num_constants + c->d.num_routed_wires);
+  if (wires->n_cols != c->d.num_wires)
+    return fail(ctx, P2B_ERR_INVALID, "wires has %zu columns, expected %u", wires->n_cols, c->d.num_wires);
+  if (cs->rate_bits != wires->rate_bits) return fail(ctx, P2B_ERR_INVALID, "rate_bits differ");
+  return P2B_OK;
+}
+
+extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs,
+                                              const p2b_batch* wires, const uint64_t* betas, const uint64_t* gammas,
+                                              uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  if (!out || !betas || !gammas) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_plonk_batches(ctx, c, cs, wires);
+  if (rc) return rc;
+  if (!cs->d_values || !wires->d_values)
+    return fail(ctx, P2B_ERR_INVALID, "constants_sigmas and wires must be built with P2B_KEEP_VALUES");
+  const p2b_circuit_desc& d = c->d;
+  const size_t n = (size_t)1 << d.degree_bits;
+  const uint32_t nch = d.num_challenges, n_chunks = d.num_partial_products + 1;
+  const size_t n_cols = (size_t)nch * (1 + d.num_partial_products);
+  if (cap_height > d.degree_bits + rate_bits) return fail(ctx, P2B_ERR_INVALID, "cap_height too large");
+  uint64_t *d_local = nullptr, *d_z = nullptr, *d_out = nullptr;
+  if ((rc = dmalloc(ctx, &d_local, (size_t)nch * n_chunks * n))) return rc;
+  if ((rc = dmalloc(ctx, &d_z, (size_t)nch * n))) {
+    dfree(ctx, d_local);
+    return rc;
+  }
+  if ((rc = dmalloc(ctx, &d_out, n_cols * n))) {
+    dfree(ctx, d_local);
+    dfree(ctx, d_z);
+    return rc;
+  }
+  stage_begin(ctx, ST_OTHER);
+  plonk::PpParams pp{};
+  pp.wires = wires->d_values;
+  pp.sigmas = cs->d_values + (size_t)d.num_constants * n;
+  pp.k_is = c->d_k_is;
+  pp.local = d_local;
+  for (uint32_t i = 0; i < nch; i++) {
+    pp.betas[i] = betas[i] % GL_P;
+    pp.gammas[i] = gammas[i] % GL_P;
+  }
+  pp.log_n = d.degree_bits;
+  pp.num_routed = d.num_routed_wires;
+  pp.chunk = d.quotient_degree_factor;
+  pp.n_chunks = n_chunks;
+  pp.roots = ctx->roots();
+  plonk::k_pp_rows<<<dim3(cdiv(n, 256), nch), 256, 0, ctx->stream>>>(pp);
+  LAUNCH_CHECK(ctx);
+  plonk::k_pp_scan<<<nch, 1024, 0, ctx->stream>>>(d_local, d.degree_bits, n_chunks, d_z);
+  LAUNCH_CHECK(ctx);
+  plonk::k_pp_finish<<<dim3(cdiv(n, 256), nch), 256, 0, ctx->stream>>>(d_local, d_z, d.degree_bits, n_chunks, nch, d_out);
+  LAUNCH_CHECK(ctx);
+  stage_end(ctx);
+  dfree(ctx, d_local);
+  dfree(ctx, d_z);
+  return batch_build(ctx, d_out, true, n_cols, d.degree_bits, rate_bits, cap_height, out, true);
+}
+
+extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
+                                   const p2b_batch* zs, const uint64_t* pi_hash, const uint64_t* betas,
+                                   const uint64_t* gammas, const uint64_t* alphas, uint32_t rate_bits,
+                                   uint32_t cap_height, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  if (!out || !betas || !gammas || !alphas || !pi_hash || !zs) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_plonk_batches(ctx, c, cs, wires);
+  if (rc) return rc;
+  const p2b_circuit_desc& d = c->d;
+  const uint32_t nch = d.num_challenges, npp = d.num_partial_products;
+  if (zs->ctx != ctx || zs->log_n != d.degree_bits || zs->n_cols != (size_t)nch * (1 + npp) || zs->rate_bits != cs->rate_bits)
+    return fail(ctx, P2B_ERR_INVALID, "zs_partial_products batch does not match the circuit");
+  uint32_t mdb = 0;
+  while ((1u << mdb) < d.quotient_degree_factor) mdb++;
+  if (mdb > cs->rate_bits)
+    return fail(ctx, P2B_ERR_INVALID, "quotient_degree_factor %u exceeds the LDE rate 2^%u", d.quotient_degree_factor, cs->rate_bits);
+  const uint32_t log_lde = d.degree_bits + mdb;
+  if (log_lde > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "quotient LDE of 2^%u points", log_lde);
+  const size_t n = (size_t)1 << d.degree_bits, lde_size = (size_t)1 << log_lde;
+  const uint32_t n_terms = nch * (npp + 2) + d.num_gate_constraints;
+  // host-side small tables: powers of alpha, Z_H on the coset and its inverses (ZeroPolyOnCoset)
+  std::vector<uint64_t> h_tab((size_t)nch * n_terms + ((size_t)2 << mdb));
+  for (uint32_t i = 0; i < nch; i++) {
+    uint64_t a = alphas[i] % GL_P, p = 1;
+    for (uint32_t k = 0; k < n_terms; k++) {
+      h_tab[(size_t)i * n_terms + k] = p;
+      p = h_mulmod(p, a);
+    }
+  }
+  {
+    const uint64_t G = 1753635133440165772ull;
+    uint64_t g_pow_n = h_powmod(7, n), wr = mdb ? h_powmod(G, (uint64_t)1 << (32 - mdb)) : 1, xr = 1;
+    uint64_t* zh = h_tab.data() + (size_t)nch * n_terms;
+    for (size_t i = 0; i < ((size_t)1 << mdb); i++) {
+      const uint64_t v = h_mulmod(g_pow_n, xr);
+      zh[i] = v ? v - 1 : GL_P - 1;
+      if (zh[i] == 0) return fail(ctx, P2B_ERR_INVALID, "Z_H vanishes on the quotient coset");
+      zh[((size_t)1 << mdb) + i] = h_powmod(zh[i], GL_P - 2);
+      xr = h_mulmod(xr, wr);
+    }
+  }
+  uint64_t *d_tab = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr;
+  if ((rc = dmalloc(ctx, &d_tab, h_tab.size()))) return rc;
+  if ((rc = dmalloc(ctx, &d_q, (size_t)nch * lde_size)) == P2B_OK) rc = dmalloc(ctx, &d_coeffs, (size_t)nch * lde_size);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_tmp, (size_t)nch * lde_size);
+  if (rc == P2B_OK) {
+    // pageable host vector: the runtime stages the copy before returning
+    cudaError_t e = cudaMemcpyAsync(d_tab, h_tab.data(), h_tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  }
+  if (rc == P2B_OK) {
+    stage_begin(ctx, ST_OTHER);
+    plonk::QuotientParams qp{};
+    qp.cs_lde = cs->d_lde;
+    qp.wires_lde = wires->d_lde;
+    qp.zs_lde = zs->d_lde;
+    qp.N = n << cs->rate_bits;
+    qp.gates = c->d_gates;
+    qp.k_is = c->d_k_is;
+    qp.apow = d_tab;
+    qp.zh = d_tab + (size_t)nch * n_terms;
+    qp.out = d_q;
+    for (uint32_t i = 0; i < nch; i++) {
+      qp.betas[i] = betas[i] % GL_P;
+      qp.gammas[i] = gammas[i] % GL_P;
+    }
+    for (int i = 0; i < 4; i++) qp.pi_hash[i] = pi_hash[i] % GL_P;
+    qp.degree_bits = d.degree_bits;
+    qp.mdb = mdb;
+    qp.num_routed = d.num_routed_wires;
+    qp.num_constants = d.num_constants;
+    qp.num_selectors = d.num_selectors;
+    qp.n_chal = nch;
+    qp.chunk = d.quotient_degree_factor;
+    qp.num_pp = npp;
+    qp.n_gates = d.n_gates;
+    qp.n_terms = n_terms;
+    qp.roots = ctx->roots();
+    plonk::k_quotient<<<cdiv(lde_size, 128), 128, 0, ctx->stream>>>(qp);
+    LAUNCH_CHECK(ctx);
+    stage_end(ctx);
+    // values.coset_ifft(7): ifft, then coefficient k / 7^k
+    stage_begin(ctx, ST_INTT);
+    rc = run_intt(ctx, d_q, d_coeffs, d_tmp, nch, log_lde, lde_size);
+    if (rc == P2B_OK) {
+      plonk::k_scale_by_powers<<<dim3(cdiv(lde_size, 256 * 16), nch), 256, 0, ctx->stream>>>(d_coeffs, lde_size,
+                                                                                            h_powmod(7, GL_P - 2));
+      LAUNCH_CHECK(ctx);
+    }
+    stage_end(ctx);
+  }
+  dfree(ctx, d_tab);
+  dfree(ctx, d_q);
+  dfree(ctx, d_tmp);
+  if (rc != P2B_OK) {
+    dfree(ctx, d_coeffs);
+    return rc;
+  }
+  // [challenge][chunk][n] coefficients = num_challenges * quotient_degree_factor polynomials of degree < n
+  return batch_build(ctx, d_coeffs, false, (size_t)nch * d.quotient_degree_factor, d.degree_bits, rate_bits, cap_height, out);
+}
+
 extern "C" int p2b_batch_leaf(p2b_batch* b, size_t leaf_index, uint64_t* out) {
   if (!b) return P2B_ERR_INVALID;
   return p2b_tree_leaf(&b->tree, leaf_index, out);

@@ -1,0 +1,445 @@
+// plonk_kernels.cuh — the PLONK-side prover stages between the three commitments, on device-resident batches.
+//
+// Replaces, for F = Goldilocks / D = 2 / no lookups / no blinding (every City Rollup worker circuit,
+// SURVEY.md §8(c)), plonky2 0.2.2:
+//   plonk/prover.rs          wires_permutation_partial_products_and_zs  (k_pp_*)
+//   plonk/prover.rs          compute_quotient_polys                     (k_quotient + coset iNTT in p2b.cu)
+//   plonk/vanishing_poly.rs  eval_vanishing_poly_base_batch, evaluate_gate_constraints_base_batch
+//   plonk/plonk_common.rs    ZeroPolyOnCoset::{eval, eval_inverse, eval_l_0}, reduce_with_powers_multi
+//   gates/gate.rs            eval_filtered_base_batch / compute_filter
+//   gates/{noop,constant,public_input,arithmetic_base,base_sum,poseidon}.rs  eval_unfiltered_base_*
+// and the in-tree gates of the reference (scalar eval_unfiltered is the specification):
+//   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150, add_many_u32.rs:87-135,
+//   subtraction_u32.rs:82-125, range_check_u32.rs:51-75.
+//
+// Design.  One thread = one point of the quotient LDE coset.  plonky2 materialises every constraint of
+// every gate for a batch of 32 points and then reduces them with the powers of alpha; here every constraint
+// is multiplied by its power of alpha and accumulated the moment it is produced (exact arithmetic, so the
+// result is identical), which needs no per-point constraint storage at all.  Threads walk the points in
+// LEAF order, so that all loads from the three column-major leaf-ordered LDE matrices are coalesced;
+// only the two "next row" Z values and the quotient store are scattered.
+#pragma once
+#include "gl64.cuh"
+#include "ntt2_kernels.cuh"
+#include "poseidon.cuh"
+
+namespace plonk {
+
+#define PFAST_QUAL __device__
+#include "poseidon_fast.inc"
+#undef PFAST_QUAL
+
+enum GateKind : uint32_t {
+  GATE_NOOP = 0,
+  GATE_CONSTANT = 1,
+  GATE_PUBLIC_INPUT = 2,
+  GATE_ARITHMETIC = 3,
+  GATE_POSEIDON = 4,
+  GATE_BASE_SUM = 5,
+  GATE_U32_ARITHMETIC = 6,
+  GATE_U32_ADD_MANY = 7,
+  GATE_U32_SUBTRACTION = 8,
+  GATE_U32_RANGE_CHECK = 9,
+  GATE_KIND_COUNT = 10
+};
+
+struct Gate {  // mirrors p2b_gate (include/p2b.h)
+  uint32_t kind, p0, p1, selector_index, group_start, group_end, row;
+};
+
+constexpr int MAX_CHALLENGES = 4;
+#define P2B_UNUSED_SELECTOR 0xFFFFFFFFull
+
+__device__ __forceinline__ uint64_t fadd(uint64_t a, uint64_t b) { return gl::add(a, b); }
+__device__ __forceinline__ uint64_t fsub(uint64_t a, uint64_t b) { return gl::sub(a, b); }
+__device__ __forceinline__ uint64_t fmul(uint64_t a, uint64_t b) { return gl::mul(a, b); }
+
+// ------------------------------------------------------------------------------------------ partial products / Z
+struct PpParams {
+  const uint64_t* wires;   // num_wires x n values on H (column-major)
+  const uint64_t* sigmas;  // num_routed x n values on H
+  const uint64_t* k_is;
+  uint64_t* local;         // [challenge][chunk][n]: prefix products of the row's chunk quotients
+  uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
+  uint32_t log_n, num_routed, chunk, n_chunks;
+  ntt2::RootTables roots;
+};
+
+// grid (n / 256, num_challenges): per row, the quotient of every chunk of `chunk` routed wires
+// prod(w + beta k_j x + gamma) / prod(w + beta sigma_j + gamma), as running products over the chunks
+__global__ void __launch_bounds__(256) k_pp_rows(PpParams P) {
+  const size_t n = (size_t)1 << P.log_n;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ch = blockIdx.y;
+  const uint64_t beta = P.betas[ch], gamma = P.gammas[ch];
+  const uint64_t bx = fmul(beta, ntt2::root_pow(P.roots, P.log_n, i));  // beta * w^i
+  uint64_t acc = 1;
+  uint64_t* out = P.local + (size_t)ch * P.n_chunks * n + i;
+  for (uint32_t k = 0; k < P.n_chunks; k++) {
+    uint64_t np = 1, dp = 1;
+    for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
+      uint64_t wv = gl::canon(P.wires[(size_t)j * n + i]);
+      uint64_t num = fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma);
+      uint64_t den = fadd(fadd(wv, fmul(beta, gl::canon(P.sigmas[(size_t)j * n + i]))), gamma);
+      np = fmul(np, num);
+      dp = fmul(dp, den);
+    }
+    acc = fmul(acc, fmul(np, gl::inv(dp)));
+    out[(size_t)k * n] = acc;
+  }
+}
+
+// one CTA per challenge: exclusive prefix product of the row totals (last chunk column) -> z[ch][i]
+__global__ void __launch_bounds__(1024) k_pp_scan(const uint64_t* __restrict__ local, uint32_t log_n, uint32_t n_chunks,
+                                                   uint64_t* __restrict__ z) {
+  __shared__ uint64_t part[1024];
+  const size_t n = (size_t)1 << log_n;
+  const uint32_t ch = blockIdx.x, tid = threadIdx.x;
+  const uint64_t* q = local + ((size_t)ch * n_chunks + (n_chunks - 1)) * n;
+  uint64_t* zo = z + (size_t)ch * n;
+  const size_t per = (n + 1023) / 1024, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
+  uint64_t p = 1;
+  for (size_t i = lo; i < hi; i++) p = fmul(p, q[i]);
+  part[tid] = p;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {  // inclusive scan of the partial products
+    uint64_t v = tid >= off ? part[tid - off] : 1;
+    __syncthreads();
+    part[tid] = fmul(part[tid], v);
+    __syncthreads();
+  }
+  uint64_t acc = tid ? part[tid - 1] : 1;
+  for (size_t i = lo; i < hi; i++) {
+    zo[i] = acc;
+    acc = fmul(acc, q[i]);
+  }
+}
+
+// out columns: [Z_0 .. Z_{c-1}, partial products of challenge 0 (n_chunks - 1), challenge 1, ...] x n
+__global__ void __launch_bounds__(256) k_pp_finish(const uint64_t* __restrict__ local, const uint64_t* __restrict__ z,
+                                                    uint32_t log_n, uint32_t n_chunks, uint32_t n_chal,
+                                                    uint64_t* __restrict__ out) {
+  const size_t n = (size_t)1 << log_n;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ch = blockIdx.y, npp = n_chunks - 1;
+  const uint64_t zi = z[(size_t)ch * n + i];
+  out[(size_t)ch * n + i] = zi;
+  for (uint32_t k = 0; k < npp; k++)
+    out[((size_t)n_chal + (size_t)ch * npp + k) * n + i] = fmul(zi, local[((size_t)ch * n_chunks + k) * n + i]);
+}
+
+// ------------------------------------------------------------------------------------------ gate evaluators
+// Accumulates filter-free sum_q alpha^q c_q for every challenge
+struct Acc {
+  uint64_t a[MAX_CHALLENGES];
+  const uint64_t* apow;  // [challenge][stride] powers of alpha, already offset to the first gate term
+  uint32_t stride, n_chal, q;
+  __device__ __forceinline__ void push(uint64_t c) {
+#pragma unroll
+    for (int ch = 0; ch < MAX_CHALLENGES; ch++)
+      if (ch < (int)n_chal) a[ch] = fadd(a[ch], fmul(c, apow[ch * stride + q]));
+    q++;
+  }
+};
+
+struct Vars {
+  const uint64_t* wires;  // column-major leaf-ordered LDE; element j of this point at wires[j * N]
+  size_t N;
+  const uint64_t* consts;  // ditto, already past the selector columns
+  const uint64_t* pi_hash;
+  __device__ __forceinline__ uint64_t w(uint32_t j) const { return wires[(size_t)j * N]; }
+  __device__ __forceinline__ uint64_t c(uint32_t j) const { return consts[(size_t)j * N]; }
+};
+
+__device__ __forceinline__ uint64_t limb4_product(uint64_t limb) {  // prod_{x<4} (limb - x)
+  return fmul(fmul(limb, fsub(limb, 1)), fmul(fsub(limb, 2), fsub(limb, 3)));
+}
+
+__device__ __forceinline__ void mds_plain(uint64_t (&s)[12]) {
+  poseidon::mds_layer(s, poseidon::RCF + 24 * 29);  // round-30 "constants" are zero: pure MDS
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
+}
+__device__ __forceinline__ uint64_t sbox7c(uint64_t x) { return gl::canon(poseidon::sbox7(x)); }
+
+__device__ void eval_poseidon_gate(const Vars& v, Acc& acc) {
+  constexpr int SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 65, FULL1 = 87;
+  const uint64_t swap = v.w(SWAP);
+  acc.push(fmul(swap, fsub(swap, 1)));
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint64_t l = v.w(i), r = v.w(i + 4), d = v.w(DELTA + i);
+    acc.push(fsub(fmul(swap, fsub(r, l)), d));
+    s[i] = fadd(l, d);
+    s[i + 4] = fsub(r, d);
+  }
+#pragma unroll
+  for (int i = 8; i < 12; i++) s[i] = v.w(i);
+  uint32_t round = 0;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = fadd(s[i], poseidon::RC[12 * round + i]);
+    if (r != 0) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        uint64_t in = v.w(FULL0 + 12 * (r - 1) + i);
+        acc.push(fsub(s[i], in));
+        s[i] = in;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = sbox7c(s[i]);
+    mds_plain(s);
+    round++;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = fadd(s[i], PFAST_FIRST[i]);
+  {  // mds_partial_layer_init
+    uint64_t o[12];
+    o[0] = s[0];
+#pragma unroll 1
+    for (int i = 0; i < 11; i++) {
+      uint64_t a = 0;
+#pragma unroll
+      for (int j = 0; j < 11; j++) a = fadd(a, fmul(PFAST_INIT[i * 11 + j], s[1 + j]));
+      o[1 + i] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = o[i];
+  }
+#pragma unroll 1
+  for (int r = 0; r < 22; r++) {
+    uint64_t in = v.w(PARTIAL + r);
+    acc.push(fsub(s[0], in));
+    s[0] = sbox7c(in);
+    if (r < 21) s[0] = fadd(s[0], PFAST_POST[r]);
+    uint64_t d = fmul(s[0], 25);
+#pragma unroll
+    for (int i = 1; i < 12; i++) d = fadd(d, fmul(s[i], PFAST_W_HATS[r * 11 + i - 1]));
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = fadd(s[i], fmul(s[0], PFAST_VS[r * 11 + i - 1]));
+    s[0] = d;
+  }
+  round += 22;
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      s[i] = fadd(s[i], poseidon::RC[12 * round + i]);
+      uint64_t in = v.w(FULL1 + 12 * r + i);
+      acc.push(fsub(s[i], in));
+      s[i] = sbox7c(in);
+    }
+    mds_plain(s);
+    round++;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc.push(fsub(s[i], v.w(12 + i)));
+}
+
+__device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
+  switch (g.kind) {
+    case GATE_NOOP:
+      break;
+    case GATE_CONSTANT:
+      for (uint32_t i = 0; i < g.p0; i++) acc.push(fsub(v.c(i), v.w(i)));
+      break;
+    case GATE_PUBLIC_INPUT:
+      for (uint32_t i = 0; i < 4; i++) acc.push(fsub(v.w(i), v.pi_hash[i]));
+      break;
+    case GATE_ARITHMETIC: {
+      const uint64_t c0 = v.c(0), c1 = v.c(1);
+      for (uint32_t i = 0; i < g.p0; i++) {
+        uint64_t computed = fadd(fmul(fmul(v.w(4 * i), v.w(4 * i + 1)), c0), fmul(v.w(4 * i + 2), c1));
+        acc.push(fsub(v.w(4 * i + 3), computed));
+      }
+      break;
+    }
+    case GATE_BASE_SUM: {
+      uint64_t sum = 0;
+      for (uint32_t i = g.p0; i-- > 0;) sum = fadd(fadd(sum, sum), v.w(1 + i));
+      acc.push(fsub(sum, v.w(0)));
+      for (uint32_t i = 0; i < g.p0; i++) {
+        uint64_t l = v.w(1 + i);
+        acc.push(fmul(l, fsub(l, 1)));
+      }
+      break;
+    }
+    case GATE_POSEIDON:
+      eval_poseidon_gate(v, acc);
+      break;
+    case GATE_U32_ARITHMETIC: {
+      const uint32_t ops = g.p0;
+      for (uint32_t i = 0; i < ops; i++) {
+        uint64_t lo = v.w(6 * i + 3), hi = v.w(6 * i + 4), inv = v.w(6 * i + 5);
+        uint64_t computed = fadd(fmul(v.w(6 * i), v.w(6 * i + 1)), v.w(6 * i + 2));
+        acc.push(fmul(fsub(fmul(inv, fsub(0xFFFFFFFFull, hi)), 1), lo));
+        acc.push(fsub(fadd(fmul(hi, 1ull << 32), lo), computed));
+        uint64_t clo = 0, chi = 0;
+        for (int j = 31; j >= 0; j--) {
+          uint64_t limb = v.w(6 * ops + 32 * i + j);
+          acc.push(limb4_product(limb));
+          if (j < 16)
+            clo = fadd(fmul(clo, 4), limb);
+          else
+            chi = fadd(fmul(chi, 4), limb);
+        }
+        acc.push(fsub(clo, lo));
+        acc.push(fsub(chi, hi));
+      }
+      break;
+    }
+    case GATE_U32_ADD_MANY: {
+      const uint32_t na = g.p0, ops = g.p1, per = na + 3;
+      for (uint32_t i = 0; i < ops; i++) {
+        uint64_t computed = 0;
+        for (uint32_t j = 0; j <= na; j++) computed = fadd(computed, v.w(per * i + j));  // addends + carry
+        uint64_t res = v.w(per * i + na + 1), carry = v.w(per * i + na + 2);
+        acc.push(fsub(fadd(fmul(carry, 1ull << 32), res), computed));
+        uint64_t cres = 0, ccar = 0;
+        for (int j = 17; j >= 0; j--) {
+          uint64_t limb = v.w(per * ops + 18 * i + j);
+          acc.push(limb4_product(limb));
+          if (j < 16)
+            cres = fadd(fmul(cres, 4), limb);
+          else
+            ccar = fadd(fmul(ccar, 4), limb);
+        }
+        acc.push(fsub(cres, res));
+        acc.push(fsub(ccar, carry));
+      }
+      break;
+    }
+    case GATE_U32_SUBTRACTION: {
+      const uint32_t ops = g.p0;
+      for (uint32_t i = 0; i < ops; i++) {
+        uint64_t res = v.w(5 * i + 3), bout = v.w(5 * i + 4);
+        uint64_t initial = fsub(fsub(v.w(5 * i), v.w(5 * i + 1)), v.w(5 * i + 2));
+        acc.push(fsub(res, fadd(initial, fmul(bout, 1ull << 32))));
+        uint64_t comb = 0;
+        for (int j = 15; j >= 0; j--) {
+          uint64_t limb = v.w(5 * ops + 16 * i + j);
+          acc.push(limb4_product(limb));
+          comb = fadd(fmul(comb, 4), limb);
+        }
+        acc.push(fsub(comb, res));
+        acc.push(fmul(bout, fsub(1, bout)));
+      }
+      break;
+    }
+    case GATE_U32_RANGE_CHECK: {
+      const uint32_t nl = g.p0;
+      for (uint32_t i = 0; i < nl; i++) {
+        uint64_t comb = 0;
+        for (int j = 15; j >= 0; j--) comb = fadd(fmul(comb, 4), v.w(nl + 16 * i + j));
+        acc.push(fsub(comb, v.w(i)));
+        for (int j = 0; j < 16; j++) acc.push(limb4_product(v.w(nl + 16 * i + j)));
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ quotient values
+struct QuotientParams {
+  const uint64_t* cs_lde;     // constants || sigmas, column-major, leaf order, column stride N
+  const uint64_t* wires_lde;
+  const uint64_t* zs_lde;     // Zs || partial products
+  size_t N;                   // n << rate_bits
+  const Gate* gates;
+  const uint64_t* k_is;
+  const uint64_t* apow;       // [challenge][n_terms] powers of alpha
+  const uint64_t* zh;         // [2^mdb] Z_H on the coset, then [2^mdb] inverses
+  uint64_t* out;              // [challenge][lde_size], natural order
+  uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
+  uint64_t pi_hash[4];
+  uint32_t degree_bits, mdb;  // lde_size = 2^(degree_bits + mdb)
+  uint32_t num_routed, num_constants, num_selectors, n_chal, chunk, num_pp, n_gates, n_terms;
+  ntt2::RootTables roots;
+};
+
+__global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
+  const uint32_t log_lde = P.degree_bits + P.mdb;
+  const size_t lde_size = (size_t)1 << log_lde;
+  const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= lde_size) return;
+  const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
+  const size_t i_next = (i + ((size_t)1 << P.mdb)) & (lde_size - 1);
+  const size_t leaf_next = ntt2::brev((uint32_t)i_next, log_lde);
+  const uint32_t zi = (uint32_t)(i & (((size_t)1 << P.mdb) - 1));
+  const uint64_t x = fmul(7, ntt2::root_pow(P.roots, log_lde, i));
+  const uint64_t z_h = P.zh[zi], z_h_inv = P.zh[((size_t)1 << P.mdb) + zi];
+  const uint64_t l0 = fmul(z_h, gl::inv(fmul((uint64_t)1 << P.degree_bits, fsub(x, 1))));
+  const uint32_t nch = P.n_chal, npp = P.num_pp;
+  const uint64_t* cs = P.cs_lde + leaf;
+  const uint64_t* wr = P.wires_lde + leaf;
+  const uint64_t* zs = P.zs_lde + leaf;
+  const size_t N = P.N;
+  uint64_t res[MAX_CHALLENGES];
+  // vanishing_z_1_terms (terms 0 .. nch-1), then the partial-product checks of every challenge
+  // (terms nch + cc * (npp + 1) + k); each term is weighted by every challenge's own power of alpha
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++) res[c] = 0;
+  for (uint32_t k = 0; k < nch; k++) {
+    const uint64_t term = fmul(l0, fsub(gl::canon(zs[(size_t)k * N]), 1));
+    for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + k], term));
+  }
+  for (uint32_t cc = 0; cc < nch; cc++) {
+    const uint64_t beta = P.betas[cc], gamma = P.gammas[cc];
+    const uint64_t bx = fmul(beta, x);
+    for (uint32_t k = 0; k <= npp; k++) {
+      uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
+      uint64_t next = k == npp ? P.zs_lde[(size_t)cc * N + leaf_next] : zs[(size_t)(nch + cc * npp + k) * N];
+      uint64_t np = 1, dp = 1;
+      for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
+        uint64_t wv = gl::canon(wr[(size_t)j * N]);
+        np = fmul(np, fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma));
+        dp = fmul(dp, fadd(fadd(wv, fmul(beta, gl::canon(cs[(size_t)(P.num_constants + j) * N]))), gamma));
+      }
+      const uint64_t term = fsub(fmul(gl::canon(prev), np), fmul(gl::canon(next), dp));
+      const uint32_t idx = nch + cc * (npp + 1) + k;
+      for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + idx], term));
+    }
+  }
+  // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
+  Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash};
+  const uint32_t gate_base = nch * (npp + 2);
+  for (uint32_t g = 0; g < P.n_gates; g++) {
+    const Gate gate = P.gates[g];
+    const uint64_t s = gl::canon(cs[(size_t)gate.selector_index * N]);
+    uint64_t filter = 1;
+    for (uint32_t q = gate.group_start; q < gate.group_end; q++)
+      if (q != gate.row) filter = fmul(filter, fsub(q, s));
+    if (P.num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
+    Acc acc;
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++) acc.a[c] = 0;
+    acc.apow = P.apow + gate_base;
+    acc.stride = P.n_terms;
+    acc.n_chal = nch;
+    acc.q = 0;
+    eval_gate(gate, v, acc);
+    for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(filter, acc.a[c]));
+  }
+  for (uint32_t c = 0; c < nch; c++) P.out[(size_t)c * lde_size + i] = fmul(res[c], z_h_inv);
+}
+
+// coefficient k of every column *= base^k  (the second half of coset_ifft: divide by shift^k)
+__global__ void __launch_bounds__(256) k_scale_by_powers(uint64_t* __restrict__ data, size_t len, uint64_t base) {
+  const size_t k0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (k0 >= len) return;
+  uint64_t* col = data + (size_t)blockIdx.y * len;
+  uint64_t p = gl::pow(base, k0);
+  for (size_t k = k0; k < k0 + 16 && k < len; k++) {
+    col[k] = fmul(col[k], p);
+    p = fmul(p, base);
+  }
+}
+
+}  // namespace plonk

@@ -9,6 +9,8 @@ error behaviour as plonky2 0.2.2 —
     MerkleTree.new / prove / cap / digests / get                 (hash/merkle_tree.rs)
     Challenger.observe_* / get_*                                  (iop/challenger.rs)
     fri_committed_trees / fri_proof_of_work                      (fri/prover.rs)
+    all_wires_permutation_partial_products / compute_quotient_polys  (plonk/prover.rs), on a
+    CommonCircuitData-shaped circuit description (CircuitData below)
 
 reached in the reference only via `circuit_data.prove(pw)` (e.g.
 city_common_circuit/src/proof_minifier/pm_core.rs:151).  Field elements are numpy uint64.
@@ -213,13 +215,19 @@ class PolynomialBatch:
         ptrs = (u64p * len(cols))(*[_ptr(c) for c in cols])
         return cols, ptrs, n.bit_length() - 1
 
+    KEEP_VALUES = 1  # P2B_KEEP_VALUES
+    BLINDING = 2     # rejected by the library: no worker circuit is zero-knowledge
+
     @classmethod
-    def from_values(cls, ctx, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None):
-        """PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)"""
+    def from_values(cls, ctx, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None,
+                    keep_values=False):
+        """PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table);
+        keep_values keeps the values on H in HBM (the witness columns / sigmas the Z stage reads again)"""
         cols, ptrs, log_n = cls._cols(values)
         h = C.c_void_p()
-        ctx.check(ctx.lib.p2b_batch_from_values(ctx.h, ptrs, len(cols), log_n, rate_bits, cap_height,
-                                                1 if blinding else 0, C.byref(h)))
+        flags = (cls.BLINDING if blinding else 0) | (cls.KEEP_VALUES if keep_values else 0)
+        ctx.check(ctx.lib.p2b_batch_from_values(ctx.h, ptrs, len(cols), log_n, rate_bits, cap_height, flags,
+                                                C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
@@ -228,7 +236,7 @@ class PolynomialBatch:
         cols, ptrs, log_n = cls._cols(polynomials)
         h = C.c_void_p()
         ctx.check(ctx.lib.p2b_batch_from_coeffs(ctx.h, ptrs, len(cols), log_n, rate_bits, cap_height,
-                                                1 if blinding else 0, C.byref(h)))
+                                                cls.BLINDING if blinding else 0, C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
@@ -253,6 +261,12 @@ class PolynomialBatch:
         """batch.polynomials[col].coeffs"""
         o = np.zeros(1 << self.degree_log, np.uint64)
         self.ctx.check(self.ctx.lib.p2b_batch_coeffs(self.h, col, _ptr(o)))
+        return o
+
+    def values(self, col):
+        """the values on H this batch was built from (keep_values=True)"""
+        o = np.zeros(1 << self.degree_log, np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_values(self.h, col, _ptr(o)))
         return o
 
     def get_lde_values(self, index, step=1):
@@ -370,3 +384,66 @@ def fri_proof_of_work(ctx, challenger, proof_of_work_bits):
     w = C.c_uint64()
     ctx.check(ctx.lib.p2b_fri_pow(ctx.h, challenger.h, proof_of_work_bits, C.byref(w)))
     return int(w.value)
+
+
+class CircuitData:
+    """The slice of plonky2's CommonCircuitData the prover stages between the commitments read (gates +
+    selectors_info, wire/constant counts, num_challenges, quotient_degree_factor, num_partial_products, k_is;
+    cf. the dump at city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145), uploaded once per circuit.
+
+    desc: dict(degree_bits, num_wires, num_routed_wires, num_constants, num_selectors, num_challenges,
+    quotient_degree_factor, num_partial_products, num_gate_constraints, k_is, gates=[dict(kind, p0, p1,
+    selector_index, group_start, group_end, row)])."""
+
+    def __init__(self, ctx, desc):
+        self.ctx, self.desc = ctx, dict(desc)
+        gates = (_lib.GateStruct * len(desc["gates"]))(*[
+            _lib.GateStruct(g["kind"], g.get("p0", 0), g.get("p1", 0), g["selector_index"], g["group_start"],
+                            g["group_end"], g["row"]) for g in desc["gates"]])
+        k_is = np.ascontiguousarray(np.array(desc["k_is"], dtype=np.uint64))
+        d = _lib.CircuitDescStruct(desc["degree_bits"], desc["num_wires"], desc["num_routed_wires"],
+                                   desc["num_constants"], desc["num_selectors"], desc["num_challenges"],
+                                   desc["quotient_degree_factor"], desc["num_partial_products"],
+                                   desc["num_gate_constraints"], len(desc["gates"]), gates, _ptr(k_is))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_circuit_new(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.p2b_circuit_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+def _felts(x):
+    return np.ascontiguousarray(np.array([int(v) for v in x], dtype=np.uint64))
+
+
+def all_wires_permutation_partial_products(ctx, circuit, constants_sigmas_commitment, wires_commitment, betas,
+                                           gammas, rate_bits, cap_height):
+    """plonk::prover::all_wires_permutation_partial_products + the from_values commit of
+    [Zs, partial products] that prove_with_partition_witness performs next -> PolynomialBatch"""
+    h = C.c_void_p()
+    ctx.check(ctx.lib.p2b_zs_partial_products_commit(ctx.h, circuit.h, constants_sigmas_commitment.h,
+                                                     wires_commitment.h, _ptr(_felts(betas)), _ptr(_felts(gammas)),
+                                                     rate_bits, cap_height, C.byref(h)))
+    return PolynomialBatch(ctx, h)
+
+
+def compute_quotient_polys(ctx, circuit, constants_sigmas_commitment, public_inputs_hash, wires_commitment,
+                           zs_partial_products_commitment, betas, gammas, alphas, rate_bits, cap_height):
+    """plonk::prover::compute_quotient_polys + chunking + from_coeffs -> quotient_polys_commitment
+    (PolynomialBatch of num_challenges * quotient_degree_factor polynomials)"""
+    h = C.c_void_p()
+    ctx.check(ctx.lib.p2b_quotient_commit(ctx.h, circuit.h, constants_sigmas_commitment.h, wires_commitment.h,
+                                          zs_partial_products_commitment.h, _ptr(_felts(public_inputs_hash)),
+                                          _ptr(_felts(betas)), _ptr(_felts(gammas)), _ptr(_felts(alphas)), rate_bits,
+                                          cap_height, C.byref(h)))
+    return PolynomialBatch(ctx, h)

@@ -82,7 +82,10 @@ int p2b_profile_read(p2b_ctx *ctx, float *ms_out, uint64_t *count_out);
  * cols[c] points to 2^log_n values of column c (plonky2's Vec<PolynomialValues<F>>: one allocation
  * per column).  Computes per column ifft -> lde(rate_bits) -> coset_fft(shift 7), the bit-reversed
  * leaf order and the Poseidon Merkle tree with 2^cap_height roots.  Everything stays in HBM.
- * flags: must be 0 (blinding/salting is used by no worker circuit). */
+ * flags: 0 or P2B_KEEP_VALUES (blinding/salting is used by no worker circuit, SURVEY §8(c), and is
+ * rejected).  P2B_KEEP_VALUES keeps the input values on H in HBM next to the coefficients — the prover
+ * needs witness.wire_values and prover_data.sigmas again for the partial products (p2b_zs_partial_products_commit). */
+#define P2B_KEEP_VALUES 1u
 int p2b_batch_from_values(p2b_ctx *ctx, const uint64_t *const *cols, size_t n_cols, uint32_t log_n,
                           uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch **out);
 /* PolynomialBatch::from_coeffs(polynomials, ...): cols[c] = 2^log_n coefficients of column c. */
@@ -116,6 +119,61 @@ int p2b_batch_leaves(p2b_batch *b, uint64_t *out);
  * (column c, leaf j at d_lde[c * 2^(log_n+rate_bits) + j]) and coefficients column-major. */
 const uint64_t *p2b_batch_dev_lde(const p2b_batch *b);
 const uint64_t *p2b_batch_dev_coeffs(const p2b_batch *b);
+
+/* values on H of column `col` (batches built from values with P2B_KEEP_VALUES) -> out[2^log_n] */
+int p2b_batch_values(p2b_batch *b, size_t col, uint64_t *out);
+
+/* ---------------------------------------------------------------- PLONK stages ----------- */
+/* What the prover stages between the commitments need of plonky2's CommonCircuitData
+ * (the reference dumps one at city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145):
+ * the gate list with its selector layout (common_data.gates / selectors_info), the wire and constant
+ * counts, num_challenges, quotient_degree_factor, num_partial_products, k_is.  Lookups and blinding are
+ * not supported (no worker circuit uses them: num_lookup_polys 0, zero_knowledge false). */
+typedef enum {
+  P2B_GATE_NOOP = 0,            /* plonky2 NoopGate */
+  P2B_GATE_CONSTANT = 1,        /* ConstantGate { num_consts = p0 } */
+  P2B_GATE_PUBLIC_INPUT = 2,    /* PublicInputGate */
+  P2B_GATE_ARITHMETIC = 3,      /* ArithmeticGate { num_ops = p0 } */
+  P2B_GATE_POSEIDON = 4,        /* PoseidonGate */
+  P2B_GATE_BASE_SUM = 5,        /* BaseSumGate<2> { num_limbs = p0 } */
+  P2B_GATE_U32_ARITHMETIC = 6,  /* city_common_circuit/src/u32/gates/arithmetic_u32.rs  { num_ops = p0 } */
+  P2B_GATE_U32_ADD_MANY = 7,    /* .../add_many_u32.rs { num_addends = p0, num_ops = p1 } */
+  P2B_GATE_U32_SUBTRACTION = 8, /* .../subtraction_u32.rs { num_ops = p0 } */
+  P2B_GATE_U32_RANGE_CHECK = 9  /* .../range_check_u32.rs { num_input_limbs = p0 } */
+} p2b_gate_kind;
+typedef struct {
+  uint32_t kind, p0, p1;
+  uint32_t selector_index;         /* selectors_info.selector_indices[row]: constants column of its selector */
+  uint32_t group_start, group_end; /* selectors_info.groups[selector_index] */
+  uint32_t row;                    /* index of the gate in common_data.gates */
+} p2b_gate;
+typedef struct {
+  uint32_t degree_bits, num_wires, num_routed_wires;
+  uint32_t num_constants; /* constant columns of constants_sigmas, selectors first */
+  uint32_t num_selectors, num_challenges, quotient_degree_factor, num_partial_products, num_gate_constraints;
+  uint32_t n_gates;
+  const p2b_gate *gates;
+  const uint64_t *k_is; /* num_routed_wires */
+} p2b_circuit_desc;
+typedef struct p2b_circuit p2b_circuit;
+int p2b_circuit_new(p2b_ctx *ctx, const p2b_circuit_desc *desc, p2b_circuit **out);
+void p2b_circuit_free(p2b_circuit *c);
+
+/* plonk::prover::all_wires_permutation_partial_products (wires_permutation_partial_products_and_zs for every
+ * challenge) followed by the PolynomialBatch::from_values of [Z_0.., partial products of challenge 0, ...]
+ * exactly as prove_with_partition_witness orders them.  constants_sigmas and wires must have been built
+ * from values with P2B_KEEP_VALUES.  betas / gammas: num_challenges elements each.  The result keeps its
+ * values too (p2b_batch_values). */
+int p2b_zs_partial_products_commit(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+                                   const p2b_batch *wires, const uint64_t *betas, const uint64_t *gammas,
+                                   uint32_t rate_bits, uint32_t cap_height, p2b_batch **out);
+/* plonk::prover::compute_quotient_polys + the chunking + PolynomialBatch::from_coeffs of the
+ * num_challenges * quotient_degree_factor quotient chunks.  quotient_degree_factor must be a power of two
+ * <= 2^rate_bits.  pi_hash = public_inputs_hash (4 elements). */
+int p2b_quotient_commit(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+                        const p2b_batch *wires, const p2b_batch *zs_partial_products, const uint64_t *pi_hash,
+                        const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas, uint32_t rate_bits,
+                        uint32_t cap_height, p2b_batch **out);
 
 /* ---------------------------------------------------------------- MerkleTree ------------- */
 /* MerkleTree::<F, PoseidonHash>::new(leaves, cap_height); leaves row-major n_leaves x leaf_len
