@@ -70,6 +70,9 @@ SIGNATURES = {
     "p2b_challenger_import": (C.c_int, [vp, u64p]),
     "p2b_fri_commit": (C.c_int, [vp, u64p, u64p, sz, C.POINTER(u32), sz, u32, u32, vp, C.POINTER(vp), u64p]),
     "p2b_fri_pow": (C.c_int, [vp, vp, u32, u64p]),
+    "p2b_batch_eval_ext": (C.c_int, [vp, u64p, sz, sz, u64p]),
+    "p2b_fri_proof_len": (sz, [C.POINTER(vp), sz, vp]),
+    "p2b_prove_openings": (C.c_int, [vp, C.POINTER(vp), sz, vp, sz, vp, vp, u64p, sz]),
 }
 
 
@@ -84,6 +87,19 @@ class CircuitDescStruct(C.Structure):  # p2b_circuit_desc
                 ("num_selectors", u32), ("num_challenges", u32), ("quotient_degree_factor", u32),
                 ("num_partial_products", u32), ("num_gate_constraints", u32), ("n_gates", u32),
                 ("gates", C.POINTER(GateStruct)), ("k_is", u64p)]
+
+
+class FriRange(C.Structure):
+    _fields_ = [("oracle", u32), ("first", u32), ("count", u32)]
+
+
+class FriBatchStruct(C.Structure):  # p2b_fri_batch
+    _fields_ = [("point", u64 * 2), ("n_ranges", u32), ("ranges", FriRange * 8)]
+
+
+class FriParamsStruct(C.Structure):  # p2b_fri_params
+    _fields_ = [("rate_bits", u32), ("cap_height", u32), ("proof_of_work_bits", u32), ("num_query_rounds", u32),
+                ("n_layers", u32), ("reduction_arity_bits", u32 * 16)]
 
 
 _lib = None

@@ -17,6 +17,7 @@
 #include "ntt2_kernels.cuh"
 #include "ntt_kernels.cuh"
 #include "plonk_kernels.cuh"
+#include "prover_kernels.cuh"
 
 #define P2B_VERSION 100
 
@@ -1458,41 +1459,26 @@ extern "C" int p2b_challenger_import(p2b_challenger* c, const uint64_t* in30) {
 }
 
 // ------------------------------------------------------------------------------------------------ FRI
-extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, size_t len,
-                              const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits, uint32_t cap_height,
-                              p2b_challenger* ch, p2b_tree** layers_out, uint64_t* final_poly_out) {
-  CHECK_CTX(ctx);
-  if (!coeffs_ext || !values_ext || !ch || !final_poly_out || (n_layers && (!arity_bits || !layers_out)))
-    return fail(ctx, P2B_ERR_INVALID, "null argument");
-  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
-  if (len == 0 || (len & (len - 1))) return fail(ctx, P2B_ERR_INVALID, "len must be a power of two");
-  uint32_t log_len = 0;
-  while (((size_t)1 << log_len) < len) log_len++;
-  uint32_t sum = 0;
-  for (size_t l = 0; l < n_layers; l++) {
-    if (arity_bits[l] == 0 || arity_bits[l] > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "arity_bits must be in 1..6");
-    sum += arity_bits[l];
-    layers_out[l] = nullptr;
-  }
-  if (sum + rate_bits > log_len) return fail(ctx, P2B_ERR_INVALID, "reduction exceeds the polynomial length");
-  if (log_len > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "len > 2^24");
-
-  // device buffers: coefficients as two planes (c0 | c1), each `len`; values interleaved in leaf order
-  uint64_t *d_in = nullptr, *d_coef = nullptr, *d_vals = nullptr, *d_beta = nullptr, *d_planes = nullptr;
-  int rc = dmalloc(ctx, &d_in, 2 * len);
-  if (rc == P2B_OK) rc = dmalloc(ctx, &d_coef, 2 * len);
+// fri_committed_trees on device-resident inputs.
+//   d_coef      coefficients as two planes (c0 | c1) of `len` each; overwritten by the folds
+//   d_vals_nat  layer-0 values, interleaved, natural order (bit-reversed here), or nullptr
+//   d_vals_leaf layer-0 values as two planes of `len` in leaf (bit-reversed) order, or nullptr
+//   d_final     receives the final polynomial, interleaved, 2 * (len >> sum(arity) >> rate_bits) words
+// On success `trees` owns the layer trees; on failure they are freed.
+static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_vals_nat, const uint64_t* d_vals_leaf,
+                           size_t len, uint32_t log_len, const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits,
+                           uint32_t cap_height, p2b_challenger* ch, std::vector<p2b_tree*>& trees, uint64_t* d_final) {
+  uint64_t *d_tmp = nullptr, *d_beta = nullptr, *d_planes = nullptr;
+  int rc = dmalloc(ctx, &d_tmp, 2 * len);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_beta, 2);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_planes, 2 * len);
-  std::vector<p2b_tree*> trees;
   auto cleanup = [&](int code) {
-    dfree(ctx, d_in);
-    dfree(ctx, d_coef);
-    dfree(ctx, d_vals);
+    dfree(ctx, d_tmp);
     dfree(ctx, d_beta);
     dfree(ctx, d_planes);
     if (code != P2B_OK) {
       for (p2b_tree* t : trees) p2b_tree_free(t);
-      for (size_t l = 0; l < n_layers; l++) layers_out[l] = nullptr;
+      trees.clear();
     }
     return code;
   };
@@ -1510,17 +1496,9 @@ extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const ui
     if (e__ != cudaSuccess)                                                                        \
       return cleanup(fail(ctx, P2B_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__)); \
   } while (0)
-
-  // coefficients -> planes
-  CUF(cudaMemcpyAsync(d_in, coeffs_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  frik::k_deinterleave<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d_in, len, d_coef, d_coef + len);
-  LAUNCHF();
-  // layer-0 values: natural order interleaved -> leaf order (bit-reversed), row-major leaves
-  CUF(cudaMemcpyAsync(d_in, values_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   size_t cur = len;
   uint32_t log_cur = log_len;
   uint64_t shift = 7;
-  auto mulmod = [](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); };
   for (size_t l = 0; l < n_layers; l++) {
     const uint32_t ab = arity_bits[l];
     const size_t n_leaves = cur >> ab, leaf_len = (size_t)2 << ab;
@@ -1536,12 +1514,15 @@ extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const ui
     t->leaf_len = leaf_len;
     if ((rc = dmalloc(ctx, &t->d_leaves_rm, 2 * cur))) return cleanup(rc);
     if ((rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height)))) return cleanup(rc);
-    if (l == 0) {
-      frik::k_bitrev_ext<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_in, log_cur, t->d_leaves_rm);
+    stage_begin(ctx, ST_FRI);
+    if (l == 0 && d_vals_nat) {
+      // natural order interleaved -> leaf order (bit-reversed), row-major leaves
+      frik::k_bitrev_ext<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_vals_nat, log_cur, t->d_leaves_rm);
       LAUNCHF();
     } else {
-      // d_planes holds the coset NTT of the folded coefficients in leaf order, as planes
-      frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_planes, d_planes + cur, cur, t->d_leaves_rm);
+      // planes in leaf order: the caller's LDE (layer 0) or the coset NTT of the folded coefficients
+      const uint64_t* pl = l == 0 ? d_vals_leaf : d_planes;
+      frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(pl, pl + cur, cur, t->d_leaves_rm);
       LAUNCHF();
     }
     hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
@@ -1552,30 +1533,94 @@ extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const ui
     frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_beta);
     LAUNCHF();
     // fold: coeffs[i] = sum_j coeffs[i*arity + j] * beta^j
-    frik::k_fold_coeffs<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, cur, ab, d_beta, d_in, d_in + n_leaves);
+    frik::k_fold_coeffs<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, cur, ab, d_beta, d_tmp, d_tmp + n_leaves);
     LAUNCHF();
-    // (folded planes now in d_in[0..n_leaves), d_in[n_leaves..2 n_leaves)); move back to d_coef
-    CUF(cudaMemcpyAsync(d_coef, d_in, 2 * n_leaves * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CUF(cudaMemcpyAsync(d_coef, d_tmp, 2 * n_leaves * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     cur = n_leaves;
     log_cur -= ab;
-    for (uint32_t k = 0; k < ab; k++) shift = mulmod(shift, shift);
+    for (uint32_t k = 0; k < ab; k++) shift = h_mulmod(shift, shift);
     if (l + 1 < n_layers) {
       // values of the next layer = coset NTT (shift) of the folded coefficients, leaf order, 2 planes
       if ((rc = run_lde(ctx, d_coef, cur, d_planes, 2, log_cur, 0, shift))) return cleanup(rc);
     }
+    stage_end(ctx);
   }
   // final polynomial: first cur >> rate_bits coefficients (the rest are zero for a valid codeword)
   size_t n_final = cur >> rate_bits;
-  uint64_t* d_final = d_in;  // reuse
   frik::k_interleave<<<cdiv(n_final, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, n_final, d_final);
   LAUNCHF();
   if ((rc = challenger_observe_dev(ch, d_final, 2 * n_final))) return cleanup(rc);
-  CUF(cudaMemcpyAsync(final_poly_out, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUF(cudaStreamSynchronize(ctx->stream));
-  for (size_t l = 0; l < n_layers; l++) layers_out[l] = trees[l];
   return cleanup(P2B_OK);
 #undef CUF
 #undef LAUNCHF
+}
+
+static int check_fri_args(p2b_ctx* ctx, size_t len, const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits,
+                          uint32_t* log_len_out) {
+  if (len == 0 || (len & (len - 1))) return fail(ctx, P2B_ERR_INVALID, "len must be a power of two");
+  uint32_t log_len = 0;
+  while (((size_t)1 << log_len) < len) log_len++;
+  uint32_t sum = 0;
+  for (size_t l = 0; l < n_layers; l++) {
+    if (arity_bits[l] == 0 || arity_bits[l] > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "arity_bits must be in 1..6");
+    sum += arity_bits[l];
+  }
+  if (sum + rate_bits > log_len) return fail(ctx, P2B_ERR_INVALID, "reduction exceeds the polynomial length");
+  if (log_len > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "len > 2^24");
+  *log_len_out = log_len;
+  return P2B_OK;
+}
+
+extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, size_t len,
+                              const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits, uint32_t cap_height,
+                              p2b_challenger* ch, p2b_tree** layers_out, uint64_t* final_poly_out) {
+  CHECK_CTX(ctx);
+  if (!coeffs_ext || !values_ext || !ch || !final_poly_out || (n_layers && (!arity_bits || !layers_out)))
+    return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
+  uint32_t log_len = 0;
+  int rc = check_fri_args(ctx, len, arity_bits, n_layers, rate_bits, &log_len);
+  if (rc) return rc;
+  uint32_t sum = 0;
+  for (size_t l = 0; l < n_layers; l++) {
+    sum += arity_bits[l];
+    layers_out[l] = nullptr;
+  }
+  const size_t n_final = (len >> sum) >> rate_bits;
+  uint64_t *d_in = nullptr, *d_coef = nullptr, *d_vals = nullptr, *d_final = nullptr;
+  rc = dmalloc(ctx, &d_in, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_coef, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_vals, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_final, 2 * n_final);
+  std::vector<p2b_tree*> trees;
+  if (rc == P2B_OK) {
+    cudaError_t e = cudaMemcpyAsync(d_in, coeffs_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      frik::k_deinterleave<<<cdiv(len, 256), 256, 0, ctx->stream>>>(d_in, len, d_coef, d_coef + len);
+      ctx->launches++;
+      e = cudaMemcpyAsync(d_vals, values_ext, 2 * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  if (rc == P2B_OK)
+    rc = fri_commit_core(ctx, d_coef, d_vals, nullptr, len, log_len, arity_bits, n_layers, rate_bits, cap_height, ch, trees,
+                         d_final);
+  if (rc == P2B_OK) {
+    cudaError_t e = cudaMemcpyAsync(final_poly_out, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      rc = fail(ctx, P2B_ERR_CUDA, "download: %s", cudaGetErrorString(e));
+      for (p2b_tree* t : trees) p2b_tree_free(t);
+      trees.clear();
+    }
+  }
+  dfree(ctx, d_in);
+  dfree(ctx, d_coef);
+  dfree(ctx, d_vals);
+  dfree(ctx, d_final);
+  if (rc == P2B_OK)
+    for (size_t l = 0; l < n_layers; l++) layers_out[l] = trees[l];
+  return rc;
 }
 
 extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint64_t* witness_out) {
@@ -1612,4 +1657,220 @@ extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, 
   dfree(ctx, d_w);
   *witness_out = found;
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ openings + FRI proof
+extern "C" int p2b_batch_eval_ext(p2b_batch* b, const uint64_t* point, size_t first, size_t count, uint64_t* out) {
+  if (!b || !point || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  if (first + count > b->n_cols || first + count < first) return fail(ctx, P2B_ERR_INVALID, "polynomial range out of bounds");
+  if (count == 0) return P2B_OK;
+  const size_t n = (size_t)1 << b->log_n;
+  uint64_t* d_out = nullptr;
+  int rc = dmalloc(ctx, &d_out, 2 * count);
+  if (rc) return rc;
+  provk::k_eval_polys_ext<<<(unsigned)count, 256, 0, ctx->stream>>>(b->d_coeffs + first * n, n, point[0] % GL_P,
+                                                                    point[1] % GL_P, d_out);
+  LAUNCH_CHECK(ctx);
+  rc = d2h(ctx, out, d_out, 2 * count);
+  dfree(ctx, d_out);
+  return rc;
+}
+
+static int check_fri_params(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles, const p2b_fri_params* fp) {
+  if (!oracles || !fp || n_oracles == 0 || n_oracles > 16) return fail(ctx, P2B_ERR_INVALID, "bad oracle list");
+  if (fp->n_layers > P2B_MAX_FRI_LAYERS) return fail(ctx, P2B_ERR_INVALID, "too many FRI layers");
+  for (size_t o = 0; o < n_oracles; o++) {
+    if (!oracles[o]) return fail(ctx, P2B_ERR_INVALID, "null oracle");
+    if (oracles[o]->log_n != oracles[0]->log_n || oracles[o]->rate_bits != fp->rate_bits)
+      return fail(ctx, P2B_ERR_INVALID, "oracle %zu: degree / rate_bits mismatch", o);
+  }
+  return P2B_OK;
+}
+
+static size_t fri_proof_len_impl(const p2b_batch* const* oracles, size_t n_oracles, const p2b_fri_params* fp) {
+  const uint32_t log_N = oracles[0]->log_n + fp->rate_bits;
+  size_t per_query = 0;
+  for (size_t o = 0; o < n_oracles; o++)
+    per_query += oracles[o]->n_cols + 4 * (size_t)(log_N - oracles[o]->cap_height);
+  uint32_t log_cur = log_N;
+  for (uint32_t l = 0; l < fp->n_layers; l++) {
+    const uint32_t ab = fp->reduction_arity_bits[l];
+    log_cur -= ab;
+    per_query += ((size_t)2 << ab) + 4 * (size_t)(log_cur - fp->cap_height);
+  }
+  const size_t n_final = ((size_t)1 << log_cur) >> fp->rate_bits;
+  return (size_t)fp->n_layers * ((size_t)4 << fp->cap_height) + (size_t)fp->num_query_rounds * per_query + 2 * n_final + 1;
+}
+
+extern "C" size_t p2b_fri_proof_len(const p2b_batch* const* oracles, size_t n_oracles, const p2b_fri_params* fp) {
+  if (!oracles || !fp || n_oracles == 0) return 0;
+  uint32_t sum = 0;
+  for (uint32_t l = 0; l < fp->n_layers && l < P2B_MAX_FRI_LAYERS; l++) sum += fp->reduction_arity_bits[l];
+  if (fp->n_layers > P2B_MAX_FRI_LAYERS || sum + fp->rate_bits > oracles[0]->log_n + fp->rate_bits) return 0;
+  return fri_proof_len_impl(oracles, n_oracles, fp);
+}
+
+extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
+                                  const p2b_fri_batch* batches, size_t n_batches, p2b_challenger* ch,
+                                  const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+  CHECK_CTX(ctx);
+  if (!batches || !ch || !proof_out || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
+  int rc = check_fri_params(ctx, oracles, n_oracles, fp);
+  if (rc) return rc;
+  const uint32_t log_n = oracles[0]->log_n, rate_bits = fp->rate_bits, log_N = log_n + rate_bits;
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  uint32_t log_len = 0;
+  if ((rc = check_fri_args(ctx, N, fp->reduction_arity_bits, fp->n_layers, rate_bits, &log_len))) return rc;
+  for (size_t o = 0; o < n_oracles; o++)
+    if (oracles[o]->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "oracle of another context");
+  const size_t proof_len = fri_proof_len_impl(oracles, n_oracles, fp);
+  if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
+  // polynomial pointer tables of every batch
+  std::vector<std::vector<const uint64_t*>> tabs(n_batches);
+  size_t max_m = 0;
+  for (size_t bi = 0; bi < n_batches; bi++) {
+    const p2b_fri_batch& fb = batches[bi];
+    if (fb.n_ranges == 0 || fb.n_ranges > P2B_MAX_FRI_RANGES) return fail(ctx, P2B_ERR_INVALID, "batch %zu: bad range count", bi);
+    for (uint32_t r = 0; r < fb.n_ranges; r++) {
+      const auto& rg = fb.ranges[r];
+      if (rg.oracle >= n_oracles || (size_t)rg.first + rg.count > oracles[rg.oracle]->n_cols)
+        return fail(ctx, P2B_ERR_INVALID, "batch %zu range %u out of bounds", bi, r);
+      for (uint32_t k = 0; k < rg.count; k++) tabs[bi].push_back(oracles[rg.oracle]->d_coeffs + (size_t)(rg.first + k) * n);
+    }
+    if (tabs[bi].size() > max_m) max_m = tabs[bi].size();
+  }
+  uint32_t sum_ab = 0;
+  for (uint32_t l = 0; l < fp->n_layers; l++) sum_ab += fp->reduction_arity_bits[l];
+  const size_t n_final = (N >> sum_ab) >> rate_bits;
+
+  uint64_t *d_alpha = nullptr, *d_pw = nullptr, *d_ptrs = nullptr, *d_comp = nullptr, *d_quot = nullptr, *d_fin = nullptr;
+  uint64_t *d_coef = nullptr, *d_vals = nullptr, *d_final = nullptr, *d_chal = nullptr, *d_proof = nullptr;
+  std::vector<p2b_tree*> trees;
+  auto cleanup = [&](int code) {
+    for (uint64_t* p : {d_alpha, d_pw, d_ptrs, d_comp, d_quot, d_fin, d_coef, d_vals, d_final, d_chal, d_proof}) dfree(ctx, p);
+    for (p2b_tree* t : trees) p2b_tree_free(t);
+    return code;
+  };
+#define TRY(expr)                          \
+  do {                                     \
+    int rc__ = (expr);                     \
+    if (rc__ != P2B_OK) return cleanup(rc__); \
+  } while (0)
+#define CUP(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+#define LAUNCHP()                                                                                  \
+  do {                                                                                             \
+    ctx->launches++;                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+  TRY(dmalloc(ctx, &d_alpha, 2));
+  TRY(dmalloc(ctx, &d_pw, 2 * (max_m + 1)));
+  TRY(dmalloc(ctx, &d_ptrs, max_m));
+  TRY(dmalloc(ctx, &d_comp, 2 * n));
+  TRY(dmalloc(ctx, &d_quot, 2 * n));
+  TRY(dmalloc(ctx, &d_fin, 2 * n));
+  TRY(dmalloc(ctx, &d_coef, 2 * N));
+  TRY(dmalloc(ctx, &d_vals, 2 * N));
+  TRY(dmalloc(ctx, &d_final, 2 * (n_final ? n_final : 1)));
+  TRY(dmalloc(ctx, &d_chal, fp->num_query_rounds ? fp->num_query_rounds : 1));
+  TRY(dmalloc(ctx, &d_proof, proof_len));
+
+  stage_begin(ctx, ST_OTHER);
+  // alpha = challenger.get_extension_challenge()
+  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_alpha);
+  LAUNCHP();
+  CUP(cudaMemsetAsync(d_fin, 0, 2 * n * sizeof(uint64_t), ctx->stream));
+  for (size_t bi = 0; bi < n_batches; bi++) {
+    const uint32_t m = (uint32_t)tabs[bi].size();
+    // the table is pageable host memory: cudaMemcpyAsync stages it before returning
+    CUP(cudaMemcpyAsync(d_ptrs, tabs[bi].data(), m * sizeof(uint64_t*), cudaMemcpyHostToDevice, ctx->stream));
+    provk::k_ext_powers<<<1, 32, 0, ctx->stream>>>(d_alpha, m, d_pw);
+    LAUNCHP();
+    provk::k_reduce_polys<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint64_t* const*)d_ptrs, m, n, d_pw, d_comp, d_comp + n);
+    LAUNCHP();
+    provk::k_divide_by_linear<<<1, 1024, 0, ctx->stream>>>(d_comp, d_comp + n, n, batches[bi].point[0] % GL_P,
+                                                          batches[bi].point[1] % GL_P, d_quot, d_quot + n);
+    LAUNCHP();
+    provk::k_shift_add<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_fin, d_fin + n, d_quot, d_quot + n, n, d_pw + 2 * m);
+    LAUNCHP();
+  }
+  // lde_final_poly = final_poly.lde(rate_bits) (zero padded coefficient planes); lde_final_values = coset_fft(7)
+  CUP(cudaMemsetAsync(d_coef, 0, 2 * N * sizeof(uint64_t), ctx->stream));
+  CUP(cudaMemcpyAsync(d_coef, d_fin, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  CUP(cudaMemcpyAsync(d_coef + N, d_fin + n, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  stage_begin(ctx, ST_LDE);
+  TRY(run_lde(ctx, d_fin, n, d_vals, 2, log_n, rate_bits, 7));
+  stage_end(ctx);
+  // fri_proof: commit phase
+  TRY(fri_commit_core(ctx, d_coef, nullptr, d_vals, N, log_N, fp->reduction_arity_bits, fp->n_layers, rate_bits,
+                      fp->cap_height, ch, trees, d_final));
+  uint64_t pow_witness = 0;
+  TRY(p2b_fri_pow(ctx, ch, fp->proof_of_work_bits, &pow_witness));
+  // query rounds: indices squeezed on the device, then one gather kernel per (oracle | layer, leaf | path)
+  stage_begin(ctx, ST_OTHER);
+  const uint32_t nq = fp->num_query_rounds;
+  size_t off = 0;
+  for (uint32_t l = 0; l < fp->n_layers; l++) {
+    CUP(cudaMemcpyAsync(d_proof + off, trees[l]->d_levels + 4 * level_off(trees[l]->n_leaves, trees[l]->log_leaves - trees[l]->cap_height),
+                        ((size_t)4 << fp->cap_height) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    off += (size_t)4 << fp->cap_height;
+  }
+  size_t per_query = 0;
+  for (size_t o = 0; o < n_oracles; o++) per_query += oracles[o]->n_cols + 4 * (size_t)(log_N - oracles[o]->cap_height);
+  {
+    uint32_t lc = log_N;
+    for (uint32_t l = 0; l < fp->n_layers; l++) {
+      lc -= fp->reduction_arity_bits[l];
+      per_query += ((size_t)2 << fp->reduction_arity_bits[l]) + 4 * (size_t)(lc - fp->cap_height);
+    }
+  }
+  if (nq) {
+    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, nq, d_chal);
+    LAUNCHP();
+    size_t qoff = off;
+    for (size_t o = 0; o < n_oracles; o++) {
+      const p2b_batch* b = oracles[o];
+      const uint32_t L = log_N - b->cap_height;
+      provk::k_query_leaf_colmajor<<<nq, 128, 0, ctx->stream>>>(b->d_lde, N, (uint32_t)b->n_cols, d_chal, log_N, d_proof + qoff, per_query);
+      LAUNCHP();
+      qoff += b->n_cols;
+      provk::k_query_siblings<<<nq, 128, 0, ctx->stream>>>(b->tree.d_levels, N, L, d_chal, log_N, 0, d_proof + qoff, per_query);
+      LAUNCHP();
+      qoff += 4 * (size_t)L;
+    }
+    uint32_t shift = 0;
+    for (uint32_t l = 0; l < fp->n_layers; l++) {
+      const uint32_t ab = fp->reduction_arity_bits[l];
+      shift += ab;
+      const p2b_tree* t = trees[l];
+      const uint32_t L = t->log_leaves - t->cap_height;
+      provk::k_query_leaf_rowmajor<<<nq, 128, 0, ctx->stream>>>(t->d_leaves_rm, (uint32_t)t->leaf_len, d_chal, log_N, shift, d_proof + qoff, per_query);
+      LAUNCHP();
+      qoff += t->leaf_len;
+      provk::k_query_siblings<<<nq, 128, 0, ctx->stream>>>(t->d_levels, t->n_leaves, L, d_chal, log_N, shift, d_proof + qoff, per_query);
+      LAUNCHP();
+      qoff += 4 * (size_t)L;
+    }
+  }
+  off += (size_t)nq * per_query;
+  CUP(cudaMemcpyAsync(d_proof + off, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  off += 2 * n_final;
+  CUP(cudaMemcpyAsync(d_proof + off, &pow_witness, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  off += 1;
+  stage_end(ctx);
+  CUP(cudaMemcpyAsync(proof_out, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUP(cudaStreamSynchronize(ctx->stream));
+  return cleanup(off == proof_len ? P2B_OK : fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
+#undef TRY
+#undef CUP
+#undef LAUNCHP
 }

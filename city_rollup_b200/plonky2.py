@@ -269,6 +269,14 @@ class PolynomialBatch:
         self.ctx.check(self.ctx.lib.p2b_batch_values(self.h, col, _ptr(o)))
         return o
 
+    def eval_ext(self, point, first=0, count=None):
+        """polynomials[first .. first+count] evaluated at the extension point (OpeningSet's eval_commitment)
+        -> (count, 2) array"""
+        count = self.n_cols - first if count is None else count
+        o = np.zeros((max(count, 1), 2), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_eval_ext(self.h, _ptr(_felts(point)), first, count, _ptr(o)))
+        return o[:count]
+
     def get_lde_values(self, index, step=1):
         """PolynomialBatch::get_lde_values(index, step)"""
         o = np.zeros(self.n_cols, np.uint64)
@@ -447,3 +455,129 @@ def compute_quotient_polys(ctx, circuit, constants_sigmas_commitment, public_inp
                                           _ptr(_felts(betas)), _ptr(_felts(gammas)), _ptr(_felts(alphas)), rate_bits,
                                           cap_height, C.byref(h)))
     return PolynomialBatch(ctx, h)
+
+
+class FriParams:
+    """plonky2 FriParams / FriConfig as the reference serialises them
+    (city_common_circuit/src/verify_template/ser_data.rs:56-154)"""
+
+    def __init__(self, rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28,
+                 reduction_arity_bits=(4, 4)):
+        self.rate_bits, self.cap_height = rate_bits, cap_height
+        self.proof_of_work_bits, self.num_query_rounds = proof_of_work_bits, num_query_rounds
+        self.reduction_arity_bits = list(reduction_arity_bits)
+
+    def struct(self):
+        s = _lib.FriParamsStruct(self.rate_bits, self.cap_height, self.proof_of_work_bits, self.num_query_rounds,
+                                 len(self.reduction_arity_bits))
+        for i, a in enumerate(self.reduction_arity_bits):
+            s.reduction_arity_bits[i] = a
+        return s
+
+
+def prove_openings(ctx, instance_batches, oracles, challenger, fri_params):
+    """PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing) -> FriProof as a dict.
+    instance_batches: [(point (2,), [(oracle_index, first, count), ...]), ...] (FriInstanceInfo.batches)."""
+    nb = len(instance_batches)
+    fb = (_lib.FriBatchStruct * nb)()
+    for i, (point, ranges) in enumerate(instance_batches):
+        fb[i].point[0], fb[i].point[1] = int(point[0]), int(point[1])
+        fb[i].n_ranges = len(ranges)
+        for j, (o, first, count) in enumerate(ranges):
+            fb[i].ranges[j] = _lib.FriRange(o, first, count)
+    handles = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
+    ps = fri_params.struct()
+    n_words = int(ctx.lib.p2b_fri_proof_len(handles, len(oracles), C.byref(ps)))
+    if n_words == 0:
+        raise P2BError(-1, "inconsistent FRI parameters")
+    buf = np.zeros(n_words, np.uint64)
+    ctx.check(ctx.lib.p2b_prove_openings(ctx.h, handles, len(oracles), fb, nb, challenger.h, C.byref(ps), _ptr(buf),
+                                         n_words))
+    # split the flat buffer in FriProof's field order
+    log_N = oracles[0].degree_log + fri_params.rate_bits
+    cap_words = 4 << fri_params.cap_height
+    pos = 0
+    caps = []
+    for _ in fri_params.reduction_arity_bits:
+        caps.append(buf[pos:pos + cap_words].reshape(-1, 4))
+        pos += cap_words
+    rounds = []
+    for _ in range(fri_params.num_query_rounds):
+        initial = []
+        for o in oracles:
+            L = log_N - o.merkle_tree.cap_height
+            leaf = buf[pos:pos + o.n_cols]
+            pos += o.n_cols
+            sib = buf[pos:pos + 4 * L].reshape(-1, 4)
+            pos += 4 * L
+            initial.append((leaf, sib))
+        steps = []
+        lc = log_N
+        for a in fri_params.reduction_arity_bits:
+            lc -= a
+            ev = buf[pos:pos + (2 << a)].reshape(-1, 2)
+            pos += 2 << a
+            L = lc - fri_params.cap_height
+            sib = buf[pos:pos + 4 * L].reshape(-1, 4)
+            pos += 4 * L
+            steps.append((ev, sib))
+        rounds.append(dict(initial_trees_proof=initial, steps=steps))
+    n_final = ((1 << log_N) >> sum(fri_params.reduction_arity_bits)) >> fri_params.rate_bits
+    final_poly = buf[pos:pos + 2 * n_final].reshape(-1, 2)
+    pos += 2 * n_final
+    pow_witness = int(buf[pos])
+    assert pos + 1 == n_words
+    return dict(commit_phase_merkle_caps=caps, query_round_proofs=rounds, final_poly=final_poly, pow_witness=pow_witness)
+
+
+def prove(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params):
+    """plonk::prover::prove_with_partition_witness from the filled witness onwards (witness generation is the
+    caller's: SURVEY.md §8 scope), for circuits without lookups / blinding:
+    wires commit -> betas, gammas -> Z / partial products commit -> alphas -> quotient commit -> zeta ->
+    openings -> FRI proof.  Returns ProofWithPublicInputs as a dict (all field elements canonical)."""
+    d = circuit.desc
+    nch, rb, ch_ = d["num_challenges"], fri_params.rate_bits, fri_params.cap_height
+    public_inputs = [int(x) for x in public_inputs]
+    public_inputs_hash = ctx.hash_no_pad(public_inputs)
+    wires = PolynomialBatch.from_values(ctx, wire_values, rb, False, ch_, keep_values=True)
+    challenger = Challenger(ctx)
+    challenger.observe_hash(circuit_digest)
+    challenger.observe_hash(public_inputs_hash)
+    challenger.observe_cap(wires)
+    betas = challenger.get_n_challenges(nch)
+    gammas = challenger.get_n_challenges(nch)
+    zs_pp = all_wires_permutation_partial_products(ctx, circuit, constants_sigmas_commitment, wires, betas, gammas,
+                                                   rb, ch_)
+    challenger.observe_cap(zs_pp)
+    alphas = challenger.get_n_challenges(nch)
+    quotient = compute_quotient_polys(ctx, circuit, constants_sigmas_commitment, public_inputs_hash, wires, zs_pp,
+                                      betas, gammas, alphas, rb, ch_)
+    challenger.observe_cap(quotient)
+    zeta = challenger.get_extension_challenge()
+    n = 1 << d["degree_bits"]
+    # zeta^n != 1 is required (plonky2 fails the proof otherwise); g = primitive n-th root
+    g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - d["degree_bits"]), P) if d["degree_bits"] else 1
+    zeta_next = [zeta[0] * g % P, zeta[1] * g % P]
+    cs = constants_sigmas_commitment
+    nc = d["num_constants"]
+    cs_z = cs.eval_ext(zeta)
+    openings = dict(constants=cs_z[:nc], plonk_sigmas=cs_z[nc:], wires=wires.eval_ext(zeta))
+    zs_z = zs_pp.eval_ext(zeta)
+    openings["plonk_zs"], openings["partial_products"] = zs_z[:nch], zs_z[nch:]
+    openings["plonk_zs_next"] = zs_pp.eval_ext(zeta_next, 0, nch)
+    openings["quotient_polys"] = quotient.eval_ext(zeta)
+    # challenger.observe_openings(&openings.to_fri_openings()): the zeta batch, then the zeta_next batch
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "plonk_zs_next"):
+        challenger.observe_extension_elements(openings[k])
+    oracles = [cs, wires, zs_pp, quotient]
+    instance = [(zeta, [(o, 0, oracles[o].n_cols) for o in range(4)]), (zeta_next, [(2, 0, nch)])]
+    opening_proof = prove_openings(ctx, instance, oracles, challenger, fri_params)
+    proof = dict(wires_cap=wires.cap, plonk_zs_partial_products_cap=zs_pp.cap, quotient_polys_cap=quotient.cap,
+                 openings=openings, opening_proof=opening_proof, public_inputs=public_inputs)
+    for b in (quotient, zs_pp, wires):
+        b.free()
+    challenger.free()
+    return proof
+
+
+P = 0xFFFFFFFF00000001

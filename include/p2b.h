@@ -232,6 +232,42 @@ int p2b_fri_commit(p2b_ctx *ctx, const uint64_t *coeffs_ext, const uint64_t *val
  * squeezes the response like the reference. */
 int p2b_fri_pow(p2b_ctx *ctx, p2b_challenger *challenger, uint32_t pow_bits, uint64_t *witness_out);
 
+/* ---------------------------------------------------------------- openings + FRI proof --- */
+/* OpeningSet::new's eval_commitment: polynomials first .. first+count of the batch, evaluated at the
+ * extension point {point[0], point[1]} -> out[2 * count] */
+int p2b_batch_eval_ext(p2b_batch *b, const uint64_t *point, size_t first, size_t count, uint64_t *out);
+
+/* FriBatchInfo: an opening point and the polynomials opened there, as ranges of (oracle, first, count) */
+#define P2B_MAX_FRI_RANGES 8
+typedef struct {
+  uint64_t point[2];
+  uint32_t n_ranges;
+  struct {
+    uint32_t oracle, first, count;
+  } ranges[P2B_MAX_FRI_RANGES];
+} p2b_fri_batch;
+/* FriParams / FriConfig (city_common_circuit/src/verify_template/ser_data.rs:56-154) */
+#define P2B_MAX_FRI_LAYERS 16
+typedef struct {
+  uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds;
+  uint32_t n_layers;
+  uint32_t reduction_arity_bits[P2B_MAX_FRI_LAYERS];
+} p2b_fri_params;
+/* Number of u64 words p2b_prove_openings writes for these oracles and parameters. */
+size_t p2b_fri_proof_len(const p2b_batch *const *oracles, size_t n_oracles, const p2b_fri_params *params);
+/* PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing): squeezes alpha, builds
+ * final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i) over the batches, its LDE, then fri_proof:
+ * commit phase, proof of work (minimal witness), query rounds.  All oracles must share degree and rate_bits =
+ * params->rate_bits.  Output (u64 words, no length prefixes, every element canonical) in FriProof's field order:
+ *   commit_phase_merkle_caps   n_layers x (4 << cap_height)
+ *   query_round_proofs         num_query_rounds x { per oracle: leaf (n_cols) , siblings 4 x (log2(leaves) - cap_height);
+ *                                                   per layer: evals 2 x arity, siblings 4 x (layer height - cap_height) }
+ *   final_poly                 2 x (n << rate_bits >> sum(arity_bits) >> rate_bits)
+ *   pow_witness                1 */
+int p2b_prove_openings(p2b_ctx *ctx, const p2b_batch *const *oracles, size_t n_oracles, const p2b_fri_batch *batches,
+                       size_t n_batches, p2b_challenger *challenger, const p2b_fri_params *params, uint64_t *proof_out,
+                       size_t proof_cap);
+
 #ifdef __cplusplus
 }
 #endif

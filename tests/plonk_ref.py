@@ -321,7 +321,7 @@ class SyntheticCircuit:
     """Random satisfiable circuit over a list of gates [(kind, p0, p1)], split into selector groups."""
 
     def __init__(self, degree_bits, gates, groups, seed, num_wires=135, num_routed=80, num_gate_consts=2,
-                 num_challenges=2, quotient_degree_factor=8, link_prob=0.3):
+                 num_challenges=2, quotient_degree_factor=8, link_prob=0.3, pi_hash=None):
         rng = random.Random(seed)
         self.degree_bits, self.n = degree_bits, 1 << degree_bits
         n = self.n
@@ -332,7 +332,7 @@ class SyntheticCircuit:
         self.num_challenges, self.qdf = num_challenges, quotient_degree_factor
         self.num_pp = -(-num_routed // quotient_degree_factor) - 1
         self.k_is = [pow(7, j, P) for j in range(num_routed)]
-        self.pi_hash = [rng.randrange(P) for _ in range(4)]
+        self.pi_hash = [rng.randrange(P) for _ in range(4)] if pi_hash is None else [int(x) for x in pi_hash]
         sel_of = {}
         for gi, (a, b) in enumerate(groups):
             for g in range(a, b):

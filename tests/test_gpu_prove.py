@@ -1,0 +1,73 @@
+"""GPU: the complete prover flow behind the C ABI (wires commit -> Z / partial products -> quotient -> openings ->
+prove_openings: final polynomial, FRI commit phase, proof of work, query rounds) against the oracle-built proof
+(tests/verifier_ref.py::oracle_prove), word for word, and through the restated plonky2 verifier."""
+import numpy as np
+import pytest
+
+import p2oracle as O
+import plonk_ref as R
+import verifier_ref as V
+from test_plonk_oracle import ALL_GATES
+from test_prove_oracle import FP_SMALL, make_case
+
+pytestmark = pytest.mark.gpu
+FULL_GROUPS = [(0, 4), (4, 5), (5, 8), (8, 10)]
+# the FRI / Plonk parameters of every stored City Rollup proof (city_common_circuit/src/circuits/zk_signature2/mod.rs:33-57)
+FP_CITY = dict(rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, reduction_arity_bits=[4, 4])
+
+
+@pytest.fixture(scope="module")
+def m():
+    import city_rollup_b200 as mod
+
+    mod.load()
+    return mod
+
+
+@pytest.fixture(scope="module")
+def ctx(m):
+    c = m.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_prove(ctx, m, circ, digest, pis, fp):
+    cd = m.CircuitData(ctx, circ.desc())
+    cs = m.PolynomialBatch.from_values(ctx, circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"],
+                                       keep_values=True)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"],
+                         fp["reduction_arity_bits"])
+    proof = m.prove(ctx, cd, cs, digest, circ.wire_values(), pis, params)
+    cs_cap = cs.cap
+    cs.free()
+    cd.free()
+    return proof, cs_cap
+
+
+@pytest.mark.parametrize("degree_bits,gates,groups,seed,fp", [
+    (6, ALL_GATES, FULL_GROUPS, 51, FP_SMALL),
+    (5, ALL_GATES[:5], [(0, 4), (4, 5)], 52, dict(FP_SMALL, cap_height=0, reduction_arity_bits=[1, 2, 1], num_query_rounds=3)),
+    (9, ALL_GATES, FULL_GROUPS, 53, dict(FP_SMALL, cap_height=4, reduction_arity_bits=[4, 4], proof_of_work_bits=10)),
+    (12, ALL_GATES, FULL_GROUPS, 54, FP_CITY),
+])
+def test_gpu_proof_equals_oracle_proof_and_verifies(ctx, m, degree_bits, gates, groups, seed, fp):
+    circ, digest, pis = make_case(degree_bits, gates, groups, seed)
+    got, cs_cap = gpu_prove(ctx, m, circ, digest, pis, fp)
+    ref, ref_cs_cap = V.oracle_prove(circ, digest, pis, fp)
+    assert (cs_cap == ref_cs_cap).all()
+    assert V.proofs_equal(got, ref) is None, V.proofs_equal(got, ref)
+    assert V.verify(circ, cs_cap, digest, got, fp)
+
+
+def test_gpu_openings_match_direct_evaluation(ctx, m):
+    rng = np.random.default_rng(5)
+    cols = [rng.integers(0, R.P, 64, dtype=np.uint64) for _ in range(5)]
+    b = m.PolynomialBatch.from_coeffs(ctx, cols, 1, False, 0)
+    z = [12345678901234567, 0xFFFFFFFF00000000]
+    got = b.eval_ext(z, 1, 3)
+    for i in range(3):
+        e = R.horner_ext(cols[1 + i], R.Ext(*z))
+        assert [int(got[i][0]), int(got[i][1])] == [e.a, e.b]
+    with pytest.raises(m.P2BError):
+        b.eval_ext(z, 3, 3)
+    b.free()
