@@ -254,3 +254,107 @@ def test_k3_fri_fold_convention_on_stored_proofs(params, proofs):
             x1 = pow(x0, 16, P)
             e1 = O.fri_compute_evaluation(x1, (xi >> 4) & 15, 4, rnd["steps"][1][0], list(beta1))
             assert tuple(e1) == final_eval(pow(x1, 16, P))
+
+
+# --------------------------------------------------------------------------------------------------
+# K3, opening part: the verifier's fri_combine_initial on the stored proofs.  It depends on two transcript
+# values that cannot be recomputed (the circuit digest is not in the dump): the FRI batching challenge alpha and
+# the opening point zeta.  Both are SOLVED from the proofs themselves: with U(a) = a^2 sum_i a^i (p_i(x) - y_i)
+# over the 256 polynomials opened at zeta (oracle order constants|sigmas, wires, Zs|partial products, quotient)
+# and V(a) = sum_j a^j (Z_j(x) - z_next_j), every query round gives
+#       E (x - zeta)(x - g zeta) = U (x - g zeta) + V (x - zeta),       E = the opened layer-0 FRI evaluation,
+# a quadratic in zeta whose coefficients are polynomials in alpha.  Three rounds make a 3x3 determinant that
+# must vanish at the true alpha; the gcd of two such determinants (degree ~500 over GF(p^2)) is linear and gives
+# alpha, two rounds then give zeta, and ALL 28 rounds must satisfy the identity.  This pins the opening order,
+# the two opening batches, the alpha bookkeeping (reduce / shift), the point convention x = 7 w^bitrev(index)
+# and g = primitive n-th root — i.e. exactly what the prover's prove_openings has to produce.
+def _padd(a, b):
+    n = max(len(a), len(b))
+    a = a + [(0, 0)] * (n - len(a))
+    b = b + [(0, 0)] * (n - len(b))
+    return [((x[0] + y[0]) % P, (x[1] + y[1]) % P) for x, y in zip(a, b)]
+
+
+def _pscale(a, s):
+    return [_emul(x, s) for x in a]
+
+
+def _pmul(a, b):
+    out = [[0, 0] for _ in range(len(a) + len(b) - 1)]
+    for i, x in enumerate(a):
+        if x == (0, 0):
+            continue
+        x0, x1 = x
+        for j, y in enumerate(b):
+            o = out[i + j]
+            o[0] += x0 * y[0] + 7 * x1 * y[1]
+            o[1] += x0 * y[1] + x1 * y[0]
+    return [(o[0] % P, o[1] % P) for o in out]
+
+
+def _peval(a, x):
+    acc = (0, 0)
+    for c in reversed(a):
+        acc = _emul(acc, x)
+        acc = ((acc[0] + c[0]) % P, (acc[1] + c[1]) % P)
+    return acc
+
+
+@pytest.mark.parametrize("which", [0, 3])  # a circuit-64 (zk signature) and a circuit-65 (secp256k1) proof
+def test_k3_fri_combine_initial_on_stored_proof(params, proofs, which):
+    p = proofs[which]
+    log_N = params["degree_bits"] + params["rate_bits"]
+    w = O.root_of_unity(log_N)
+    g = O.root_of_unity(params["degree_bits"])
+    op = p["openings"]
+    ys = [tuple(int(c) for c in e) for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products",
+                                             "quotient_polys") for e in op[k]]
+    ys_next = [tuple(int(c) for c in e) for e in op["plonk_zs_next"]]
+    nch = len(ys_next)
+    assert len(ys) == sum(params["num_leaves_per_oracle"])
+    # the constants|sigmas leaves (oracle 0) verify against no cap we hold, but they are needed: take them as given
+    rows = []
+    for rnd in p["query_rounds"]:
+        x_index = O.merkle_find_index(rnd["initial"][3][0], rnd["initial"][3][1], p["quotient_cap"])
+        x = 7 * pow(w, int(format(x_index, f"0{log_N}b")[::-1], 2), P) % P
+        evals = [int(v) for leaf, _ in rnd["initial"] for v in leaf]
+        zs_leaf = [int(v) for v in rnd["initial"][2][0][:nch]]
+        E = tuple(int(c) for c in rnd["steps"][0][0][x_index & 15])
+        U = [(0, 0), (0, 0)] + [((e - y[0]) % P, (-y[1]) % P) for e, y in zip(evals, ys)]
+        V = [((e - y[0]) % P, (-y[1]) % P) for e, y in zip(zs_leaf, ys_next)]
+        a = _emul(E, (g, 0))
+        b = _padd(_padd(_pscale(U, (g, 0)), V), [_emul(E, ((-x * (1 + g)) % P, 0))])
+        c = _padd(_pscale(_padd(U, V), ((-x) % P, 0)), [_emul(E, (x * x % P, 0))])
+        rows.append((a, b, c, x, E, U, V))
+
+    def det(i, j, k):
+        (a1, b1, c1), (a2, b2, c2), (a3, b3, c3) = (rows[t][:3] for t in (i, j, k))
+        neg = lambda poly: [((-u[0]) % P, (-u[1]) % P) for u in poly]
+        m1 = _padd(_pmul(b2, c3), neg(_pmul(b3, c2)))
+        m2 = _padd(_pmul(b1, c3), neg(_pmul(b3, c1)))
+        m3 = _padd(_pmul(b1, c2), neg(_pmul(b2, c1)))
+        return _padd(_padd(_pscale(m1, a1), neg(_pscale(m2, a2))), _pscale(m3, a3))
+
+    gg = _poly_gcd(det(0, 1, 2), det(0, 1, 3))
+    assert len(gg) == 2, f"expected a unique common root, gcd has degree {len(gg) - 1}"
+    alpha = _emul(((-gg[0][0]) % P, (-gg[0][1]) % P), _einv(gg[1]))
+    # zeta from rounds 0 and 1: (a1 b2 - a2 b1) zeta + (a1 c2 - a2 c1) = 0
+    a1, b1, c1 = rows[0][0], _peval(rows[0][1], alpha), _peval(rows[0][2], alpha)
+    a2, b2, c2 = rows[1][0], _peval(rows[1][1], alpha), _peval(rows[1][2], alpha)
+    lin = _esub(_emul(a1, b2), _emul(a2, b1))
+    con = _esub(_emul(a1, c2), _emul(a2, c1))
+    zeta = _emul(((-con[0]) % P, (-con[1]) % P), _einv(lin))
+    # zeta is outside H (plonky2 aborts otherwise) and every one of the 28 rounds agrees
+    zn = (1, 0)
+    zp = zeta
+    for _ in range(params["degree_bits"]):
+        zp = _emul(zp, zp)
+    assert zp != (1, 0)
+    for a, b, c, x, E, U, V in rows:
+        u, v = _peval(U, alpha), _peval(V, alpha)
+        s = ((x - zeta[0]) % P, (-zeta[1]) % P)
+        gz = _emul(zeta, (g, 0))
+        t = ((x - gz[0]) % P, (-gz[1]) % P)
+        total = _emul(u, _einv(s))
+        nxt = _emul(v, _einv(t))
+        assert ((total[0] + nxt[0]) % P, (total[1] + nxt[1]) % P) == E
