@@ -73,6 +73,8 @@ SIGNATURES = {
     "p2b_batch_eval_ext": (C.c_int, [vp, u64p, sz, sz, u64p]),
     "p2b_fri_proof_len": (sz, [C.POINTER(vp), sz, vp]),
     "p2b_prove_openings": (C.c_int, [vp, C.POINTER(vp), sz, vp, sz, vp, vp, u64p, sz]),
+    "p2b_proof_len": (sz, [vp, vp, vp, sz]),
+    "p2b_prove": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp, u64p, sz]),
 }
 
 

@@ -3,7 +3,7 @@
 // Replaces plonky2 0.2.2 iop/challenger.rs (Challenger<F, PoseidonHash>), fri/prover.rs
 // (fri_committed_trees' fold `reduce_with_powers(chunk, beta)`, fri_proof_of_work) — SURVEY.md A.7/A.9;
 // FRI parameters as dumped at city_common_circuit/src/circuits/zk_signature2/mod.rs:38-50.
-// The transcript state lives in HBM and is advanced by single-thread kernels, so the commit loop
+// The transcript state lives in HBM and is advanced by one-warp kernels (a warp-cooperative permutation), so the commit loop
 // (tree -> observe cap -> beta -> fold -> coset NTT) never synchronises with the host.
 #pragma once
 #include "poseidon.cuh"
@@ -14,42 +14,64 @@ namespace frik {
 constexpr int CH_WORDS = 30;
 constexpr int CH_NIN = 12, CH_IN = 13, CH_NOUT = 21, CH_OUT = 22;
 
-__device__ __forceinline__ void duplexing(uint64_t* st) {
-  uint64_t s[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = st[i];
-  uint32_t n_in = (uint32_t)st[CH_NIN];
-  for (uint32_t i = 0; i < n_in; i++) s[i] = st[CH_IN + i];  // overwrite mode
-  poseidon::permute(s);
-#pragma unroll
-  for (int i = 0; i < 12; i++) st[i] = s[i];
-#pragma unroll
-  for (int i = 0; i < 8; i++) st[CH_OUT + i] = s[i];
-  st[CH_NIN] = 0;
-  st[CH_NOUT] = 8;
+// Challenger::duplexing on a state held in shared memory, one permutation shared by the warp
+// (poseidon::coop_permute_nc); all 32 lanes call, lanes 16..31 mirror 0..15
+__device__ __forceinline__ void duplexing_coop(uint64_t* st, uint32_t lane) {
+  const uint32_t l = lane & 15;
+  const uint32_t n_in = (uint32_t)st[CH_NIN];
+  uint64_t s = l < 12 ? st[l] : 0;
+  if (l < n_in) s = st[CH_IN + l];  // overwrite mode
+  __syncwarp();
+  s = gl::canon(poseidon::coop_permute_nc(s, l));
+  if (lane < 12) st[lane] = s;
+  if (lane < 8) st[CH_OUT + lane] = s;
+  if (lane == 0) {
+    st[CH_NIN] = 0;
+    st[CH_NOUT] = 8;
+  }
+  __syncwarp();
 }
 
-// Challenger::observe_elements
-__global__ void k_challenger_observe(uint64_t* __restrict__ st, const uint64_t* __restrict__ elems, size_t n) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  for (size_t i = 0; i < n; i++) {
-    st[CH_NOUT] = 0;
-    uint32_t k = (uint32_t)st[CH_NIN];
-    st[CH_IN + k] = gl::canon(elems[i]);
-    st[CH_NIN] = k + 1;
-    if (k + 1 == 8) duplexing(st);
+// Challenger::observe_elements; launch <<<1, 32>>>
+__global__ void k_challenger_observe(uint64_t* __restrict__ g_st, const uint64_t* __restrict__ elems, size_t n) {
+  __shared__ uint64_t st[32];
+  const uint32_t lane = threadIdx.x;
+  if (lane < CH_WORDS) st[lane] = g_st[lane];
+  __syncwarp();
+  size_t i = 0;
+  while (i < n) {
+    const uint32_t k = (uint32_t)st[CH_NIN];
+    const uint32_t take = (uint32_t)((n - i) < (size_t)(8 - k) ? (n - i) : (size_t)(8 - k));
+    __syncwarp();
+    if (lane < take) st[CH_IN + k + lane] = gl::canon(elems[i + lane]);
+    if (lane == 0) {
+      st[CH_NOUT] = 0;
+      st[CH_NIN] = k + take;
+    }
+    __syncwarp();
+    i += take;
+    if (k + take == 8) duplexing_coop(st, lane);
   }
+  __syncwarp();
+  if (lane < CH_WORDS) g_st[lane] = st[lane];
 }
 
-// Challenger::get_n_challenges
-__global__ void k_challenger_get(uint64_t* __restrict__ st, size_t n, uint64_t* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Challenger::get_n_challenges; launch <<<1, 32>>>
+__global__ void k_challenger_get(uint64_t* __restrict__ g_st, size_t n, uint64_t* __restrict__ out) {
+  __shared__ uint64_t st[32];
+  const uint32_t lane = threadIdx.x;
+  if (lane < CH_WORDS) st[lane] = g_st[lane];
+  __syncwarp();
   for (size_t i = 0; i < n; i++) {
-    if (st[CH_NIN] != 0 || st[CH_NOUT] == 0) duplexing(st);
-    uint32_t k = (uint32_t)st[CH_NOUT] - 1;
-    out[i] = st[CH_OUT + k];
-    st[CH_NOUT] = k;
+    if (st[CH_NIN] != 0 || st[CH_NOUT] == 0) duplexing_coop(st, lane);
+    if (lane == 0) {
+      const uint32_t k = (uint32_t)st[CH_NOUT] - 1;
+      out[i] = st[CH_OUT + k];
+      st[CH_NOUT] = k;
+    }
+    __syncwarp();
   }
+  if (lane < CH_WORDS) g_st[lane] = st[lane];
 }
 
 __global__ void k_deinterleave(const uint64_t* __restrict__ in, size_t len, uint64_t* __restrict__ c0,

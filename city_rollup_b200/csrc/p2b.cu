@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -27,6 +28,10 @@ struct p2b_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // Every context allocates from its OWN stream-ordered pool: with the shared default pool a block freed on one
+  // context's stream is handed to another context's next allocation behind an internal event dependency, which
+  // chains the streams of concurrently proving contexts together.
+  cudaMemPool_t pool = nullptr;
   bool poisoned = false;
   std::string err;
   uint64_t launches = 0;
@@ -97,6 +102,8 @@ struct p2b_circuit {
   p2b_circuit_desc d{};
   plonk::Gate* d_gates = nullptr;
   uint64_t* d_k_is = nullptr;
+  uint64_t* d_zh = nullptr;  // ZeroPolyOnCoset: Z_H on the 2^mdb cosets of the quotient LDE, then the inverses
+  uint32_t mdb = 0;          // log2(quotient_degree_factor)
 };
 
 struct p2b_challenger {
@@ -149,7 +156,7 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 static int dmalloc(p2b_ctx* ctx, uint64_t** p, size_t n_u64) {
   *p = nullptr;
   if (n_u64 == 0) n_u64 = 1;
-  CU(ctx, cudaMallocAsync((void**)p, n_u64 * sizeof(uint64_t), ctx->stream));
+  CU(ctx, cudaMallocFromPoolAsync((void**)p, n_u64 * sizeof(uint64_t), ctx->pool, ctx->stream));
   return P2B_OK;
 }
 static void dfree(p2b_ctx* ctx, void* p) {
@@ -215,10 +222,14 @@ static int ctx_setup(p2b_ctx* ctx) {
   CU(ctx, cudaEventCreate(&ctx->ev0));
   CU(ctx, cudaEventCreate(&ctx->ev1));
   // keep freed blocks cached in the stream-ordered pool (no trimming at sync points)
-  cudaMemPool_t pool;
-  CU(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  cudaMemPoolProps props{};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = ctx->device;
+  CU(ctx, cudaMemPoolCreate(&ctx->pool, &props));
   uint64_t thresh = UINT64_MAX;
-  CU(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  CU(ctx, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   int rc;
@@ -308,6 +319,7 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   if (ctx->cur_ev) cudaEventDestroy(ctx->cur_ev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -710,12 +722,27 @@ static size_t levels_len(size_t n_leaves, uint32_t cap_height) { return 2 * n_le
 static size_t level_off(size_t n_leaves, uint32_t i) { return 2 * n_leaves - 2 * (n_leaves >> i); }
 
 // leaf digests must already be in t->d_levels[0 .. n_leaves)
+// widest level handled with 16 lanes per node; override with P2B_COOP_MAX_NODES for tuning
+static size_t coop_max_nodes() {
+  static const size_t v = [] {
+    const char* e = getenv("P2B_COOP_MAX_NODES");
+    return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)2048;
+  }();
+  return v;
+}
+#define COOP_MAX_NODES coop_max_nodes()
 static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
   uint32_t L = t->log_leaves - t->cap_height;
   for (uint32_t i = 0; i < L; i++) {
     size_t n_par = t->n_leaves >> (i + 1);
-    hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
-                                                                  t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);
+    const uint64_t* child = t->d_levels + 4 * level_off(t->n_leaves, i);
+    uint64_t* parent = t->d_levels + 4 * level_off(t->n_leaves, i + 1);
+    // wide levels are throughput bound (one permutation per thread); the narrow top of the tree is a chain of
+    // dependent levels, where 16 lanes per node cut the latency of each
+    if (n_par > COOP_MAX_NODES)
+      hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(child, parent, n_par);
+    else
+      hashk::k_tree_level_coop<<<cdiv(n_par * 16, 256), 256, 0, ctx->stream>>>(child, parent, n_par);
     LAUNCH_CHECK(ctx);
   }
   return P2B_OK;
@@ -987,9 +1014,27 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
   static_assert(sizeof(plonk::Gate) == sizeof(p2b_gate), "gate layout");
   int rc = dmalloc(ctx, (uint64_t**)&c->d_gates, (d.n_gates * sizeof(p2b_gate) + 7) / 8);
   if (rc == P2B_OK) rc = dmalloc(ctx, &c->d_k_is, d.num_routed_wires);
+  while ((1u << c->mdb) < d.quotient_degree_factor) c->mdb++;
+  // ZeroPolyOnCoset::new(degree_bits, mdb): Z_H(7 w^i) = 7^n w_{2^mdb}^(i mod 2^mdb) - 1, and the inverses
+  std::vector<uint64_t> zh((size_t)2 << c->mdb);
+  {
+    const uint64_t G = 1753635133440165772ull;
+    const uint32_t mdb = c->mdb;
+    uint64_t g_pow_n = h_powmod(7, (uint64_t)1 << d.degree_bits), wr = mdb ? h_powmod(G, (uint64_t)1 << (32 - mdb)) : 1, xr = 1;
+    for (size_t i = 0; i < ((size_t)1 << mdb); i++) {
+      const uint64_t v = h_mulmod(g_pow_n, xr);
+      zh[i] = v ? v - 1 : GL_P - 1;
+      if (zh[i] == 0 && rc == P2B_OK) rc = fail(ctx, P2B_ERR_INVALID, "Z_H vanishes on the quotient coset");
+      zh[((size_t)1 << mdb) + i] = h_powmod(zh[i], GL_P - 2);
+      xr = h_mulmod(xr, wr);
+    }
+  }
+  if (rc == P2B_OK) rc = dmalloc(ctx, &c->d_zh, zh.size());
   if (rc == P2B_OK) {
     // pageable sources: the copies are complete (staged) when cudaMemcpyAsync returns
     cudaError_t e = cudaMemcpyAsync(c->d_gates, d.gates, d.n_gates * sizeof(p2b_gate), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(c->d_zh, zh.data(), zh.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(c->d_k_is, d.k_is, d.num_routed_wires * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1008,6 +1053,7 @@ extern "C" void p2b_circuit_free(p2b_circuit* c) {
   cudaSetDevice(c->ctx->device);
   dfree(c->ctx, c->d_gates);
   dfree(c->ctx, c->d_k_is);
+  dfree(c->ctx, c->d_zh);
   delete c;
 }
 
@@ -1025,11 +1071,21 @@ static int check_plonk_batches(p2b_ctx* ctx, const p2b_circuit* c, const p2b_bat
   return P2B_OK;
 }
 
-extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs,
-                                              const p2b_batch* wires, const uint64_t* betas, const uint64_t* gammas,
-                                              uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
-  CHECK_CTX(ctx);
-  if (!out || !betas || !gammas) return fail(ctx, P2B_ERR_INVALID, "null argument");
+// uploads n host field elements (reduced mod p) to a fresh device buffer
+static int upload_felts(p2b_ctx* ctx, const uint64_t* h, size_t n, uint64_t** d_out) {
+  std::vector<uint64_t> tmp(n ? n : 1);
+  for (size_t i = 0; i < n; i++) tmp[i] = h[i] % GL_P;
+  int rc = dmalloc(ctx, d_out, n);
+  if (rc) return rc;
+  // pageable source: staged before cudaMemcpyAsync returns
+  CU(ctx, cudaMemcpyAsync(*d_out, tmp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  return P2B_OK;
+}
+
+// d_betas / d_gammas: num_challenges elements each, on the device
+static int zs_pp_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
+                      const uint64_t* d_betas, const uint64_t* d_gammas, uint32_t rate_bits, uint32_t cap_height,
+                      p2b_batch** out) {
   *out = nullptr;
   int rc = check_plonk_batches(ctx, c, cs, wires);
   if (rc) return rc;
@@ -1057,10 +1113,8 @@ extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c
   pp.sigmas = cs->d_values + (size_t)d.num_constants * n;
   pp.k_is = c->d_k_is;
   pp.local = d_local;
-  for (uint32_t i = 0; i < nch; i++) {
-    pp.betas[i] = betas[i] % GL_P;
-    pp.gammas[i] = gammas[i] % GL_P;
-  }
+  pp.betas = d_betas;
+  pp.gammas = d_gammas;
   pp.log_n = d.degree_bits;
   pp.num_routed = d.num_routed_wires;
   pp.chunk = d.quotient_degree_factor;
@@ -1078,59 +1132,47 @@ extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c
   return batch_build(ctx, d_out, true, n_cols, d.degree_bits, rate_bits, cap_height, out, true);
 }
 
-extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
-                                   const p2b_batch* zs, const uint64_t* pi_hash, const uint64_t* betas,
-                                   const uint64_t* gammas, const uint64_t* alphas, uint32_t rate_bits,
-                                   uint32_t cap_height, p2b_batch** out) {
+extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs,
+                                              const p2b_batch* wires, const uint64_t* betas, const uint64_t* gammas,
+                                              uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
   CHECK_CTX(ctx);
-  if (!out || !betas || !gammas || !alphas || !pi_hash || !zs) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (!out || !betas || !gammas || !c) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const uint32_t nch = c->d.num_challenges;
+  std::vector<uint64_t> h(2 * nch);
+  for (uint32_t i = 0; i < nch; i++) h[i] = betas[i], h[nch + i] = gammas[i];
+  uint64_t* d_ch = nullptr;
+  int rc = upload_felts(ctx, h.data(), h.size(), &d_ch);
+  if (rc == P2B_OK) rc = zs_pp_core(ctx, c, cs, wires, d_ch, d_ch + nch, rate_bits, cap_height, out);
+  dfree(ctx, d_ch);
+  return rc;
+}
+
+// all challenge / hash arguments on the device
+static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
+                         const p2b_batch* zs, const uint64_t* d_pi_hash, const uint64_t* d_betas, const uint64_t* d_gammas,
+                         const uint64_t* d_alphas, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
   *out = nullptr;
   int rc = check_plonk_batches(ctx, c, cs, wires);
   if (rc) return rc;
   const p2b_circuit_desc& d = c->d;
-  const uint32_t nch = d.num_challenges, npp = d.num_partial_products;
-  if (zs->ctx != ctx || zs->log_n != d.degree_bits || zs->n_cols != (size_t)nch * (1 + npp) || zs->rate_bits != cs->rate_bits)
+  const uint32_t nch = d.num_challenges, npp = d.num_partial_products, mdb = c->mdb;
+  if (!zs || zs->ctx != ctx || zs->log_n != d.degree_bits || zs->n_cols != (size_t)nch * (1 + npp) || zs->rate_bits != cs->rate_bits)
     return fail(ctx, P2B_ERR_INVALID, "zs_partial_products batch does not match the circuit");
-  uint32_t mdb = 0;
-  while ((1u << mdb) < d.quotient_degree_factor) mdb++;
   if (mdb > cs->rate_bits)
     return fail(ctx, P2B_ERR_INVALID, "quotient_degree_factor %u exceeds the LDE rate 2^%u", d.quotient_degree_factor, cs->rate_bits);
   const uint32_t log_lde = d.degree_bits + mdb;
   if (log_lde > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "quotient LDE of 2^%u points", log_lde);
   const size_t n = (size_t)1 << d.degree_bits, lde_size = (size_t)1 << log_lde;
   const uint32_t n_terms = nch * (npp + 2) + d.num_gate_constraints;
-  // host-side small tables: powers of alpha, Z_H on the coset and its inverses (ZeroPolyOnCoset)
-  std::vector<uint64_t> h_tab((size_t)nch * n_terms + ((size_t)2 << mdb));
-  for (uint32_t i = 0; i < nch; i++) {
-    uint64_t a = alphas[i] % GL_P, p = 1;
-    for (uint32_t k = 0; k < n_terms; k++) {
-      h_tab[(size_t)i * n_terms + k] = p;
-      p = h_mulmod(p, a);
-    }
-  }
-  {
-    const uint64_t G = 1753635133440165772ull;
-    uint64_t g_pow_n = h_powmod(7, n), wr = mdb ? h_powmod(G, (uint64_t)1 << (32 - mdb)) : 1, xr = 1;
-    uint64_t* zh = h_tab.data() + (size_t)nch * n_terms;
-    for (size_t i = 0; i < ((size_t)1 << mdb); i++) {
-      const uint64_t v = h_mulmod(g_pow_n, xr);
-      zh[i] = v ? v - 1 : GL_P - 1;
-      if (zh[i] == 0) return fail(ctx, P2B_ERR_INVALID, "Z_H vanishes on the quotient coset");
-      zh[((size_t)1 << mdb) + i] = h_powmod(zh[i], GL_P - 2);
-      xr = h_mulmod(xr, wr);
-    }
-  }
-  uint64_t *d_tab = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr;
-  if ((rc = dmalloc(ctx, &d_tab, h_tab.size()))) return rc;
+  uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr;
+  if ((rc = dmalloc(ctx, &d_apow, (size_t)nch * n_terms))) return rc;
   if ((rc = dmalloc(ctx, &d_q, (size_t)nch * lde_size)) == P2B_OK) rc = dmalloc(ctx, &d_coeffs, (size_t)nch * lde_size);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_tmp, (size_t)nch * lde_size);
   if (rc == P2B_OK) {
-    // pageable host vector: the runtime stages the copy before returning
-    cudaError_t e = cudaMemcpyAsync(d_tab, h_tab.data(), h_tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
-  }
-  if (rc == P2B_OK) {
     stage_begin(ctx, ST_OTHER);
+    plonk::k_build_apow<<<nch, 32, 0, ctx->stream>>>(d_alphas, n_terms, d_apow);
+    ctx->launches++;
     plonk::QuotientParams qp{};
     qp.cs_lde = cs->d_lde;
     qp.wires_lde = wires->d_lde;
@@ -1138,14 +1180,12 @@ extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b
     qp.N = n << cs->rate_bits;
     qp.gates = c->d_gates;
     qp.k_is = c->d_k_is;
-    qp.apow = d_tab;
-    qp.zh = d_tab + (size_t)nch * n_terms;
+    qp.apow = d_apow;
+    qp.zh = c->d_zh;
     qp.out = d_q;
-    for (uint32_t i = 0; i < nch; i++) {
-      qp.betas[i] = betas[i] % GL_P;
-      qp.gammas[i] = gammas[i] % GL_P;
-    }
-    for (int i = 0; i < 4; i++) qp.pi_hash[i] = pi_hash[i] % GL_P;
+    qp.betas = d_betas;
+    qp.gammas = d_gammas;
+    qp.pi_hash = d_pi_hash;
     qp.degree_bits = d.degree_bits;
     qp.mdb = mdb;
     qp.num_routed = d.num_routed_wires;
@@ -1170,7 +1210,7 @@ extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b
     }
     stage_end(ctx);
   }
-  dfree(ctx, d_tab);
+  dfree(ctx, d_apow);
   dfree(ctx, d_q);
   dfree(ctx, d_tmp);
   if (rc != P2B_OK) {
@@ -1179,6 +1219,25 @@ extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b
   }
   // [challenge][chunk][n] coefficients = num_challenges * quotient_degree_factor polynomials of degree < n
   return batch_build(ctx, d_coeffs, false, (size_t)nch * d.quotient_degree_factor, d.degree_bits, rate_bits, cap_height, out);
+}
+
+extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
+                                   const p2b_batch* zs, const uint64_t* pi_hash, const uint64_t* betas,
+                                   const uint64_t* gammas, const uint64_t* alphas, uint32_t rate_bits,
+                                   uint32_t cap_height, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  if (!out || !betas || !gammas || !alphas || !pi_hash || !zs || !c) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const uint32_t nch = c->d.num_challenges;
+  std::vector<uint64_t> h(3 * nch + 4);
+  for (uint32_t i = 0; i < nch; i++) h[i] = betas[i], h[nch + i] = gammas[i], h[2 * nch + i] = alphas[i];
+  for (int i = 0; i < 4; i++) h[3 * nch + i] = pi_hash[i];
+  uint64_t* d_ch = nullptr;
+  int rc = upload_felts(ctx, h.data(), h.size(), &d_ch);
+  if (rc == P2B_OK)
+    rc = quotient_core(ctx, c, cs, wires, zs, d_ch + 3 * nch, d_ch, d_ch + nch, d_ch + 2 * nch, rate_bits, cap_height, out);
+  dfree(ctx, d_ch);
+  return rc;
 }
 
 extern "C" int p2b_batch_leaf(p2b_batch* b, size_t leaf_index, uint64_t* out) {
@@ -1525,7 +1584,10 @@ static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_val
       frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(pl, pl + cur, cur, t->d_leaves_rm);
       LAUNCHF();
     }
-    hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+    if (n_leaves > COOP_MAX_NODES)
+      hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+    else
+      hashk::k_leaf_hash_rowmajor_coop<<<cdiv(n_leaves * 16, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
     LAUNCHF();
     if ((rc = build_levels(ctx, t))) return cleanup(rc);
     // observe_cap, beta = get_extension_challenge (device resident)
@@ -1631,9 +1693,10 @@ extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, 
   uint64_t* d_best = nullptr;
   int rc = dmalloc(ctx, &d_best, 1);
   if (rc) return rc;
-  const uint64_t chunk = (uint64_t)1 << 20;
+  // the minimal witness is geometric with mean 2^pow_bits: search 4x that first (98% hit rate), then double
+  uint64_t chunk = (uint64_t)1 << (pow_bits + 2 < 14 ? 14 : pow_bits + 2 > 24 ? 24 : pow_bits + 2);
   uint64_t found = ~0ull;
-  for (uint64_t base = 0; found == ~0ull; base += chunk) {
+  for (uint64_t base = 0; found == ~0ull; base += chunk, chunk = chunk < ((uint64_t)1 << 24) ? chunk * 2 : chunk) {
     CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
     frik::k_pow_search<<<cdiv(chunk, 256), 256, 0, ctx->stream>>>(ch->d_state, base, chunk, pow_bits, (unsigned long long*)d_best);
     LAUNCH_CHECK(ctx);
@@ -1660,21 +1723,28 @@ extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, 
 }
 
 // ------------------------------------------------------------------------------------------------ openings + FRI proof
+// d_point: extension point on the device; d_out: 2 * count words on the device
+static int eval_ext_core(p2b_ctx* ctx, const p2b_batch* b, const uint64_t* d_point, size_t first, size_t count, uint64_t* d_out) {
+  if (count == 0) return P2B_OK;
+  const size_t n = (size_t)1 << b->log_n;
+  provk::k_eval_polys_ext<<<(unsigned)count, 256, 0, ctx->stream>>>(b->d_coeffs + first * n, n, d_point, d_out);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
 extern "C" int p2b_batch_eval_ext(p2b_batch* b, const uint64_t* point, size_t first, size_t count, uint64_t* out) {
   if (!b || !point || !out) return P2B_ERR_INVALID;
   p2b_ctx* ctx = b->ctx;
   CHECK_CTX(ctx);
   if (first + count > b->n_cols || first + count < first) return fail(ctx, P2B_ERR_INVALID, "polynomial range out of bounds");
   if (count == 0) return P2B_OK;
-  const size_t n = (size_t)1 << b->log_n;
-  uint64_t* d_out = nullptr;
-  int rc = dmalloc(ctx, &d_out, 2 * count);
-  if (rc) return rc;
-  provk::k_eval_polys_ext<<<(unsigned)count, 256, 0, ctx->stream>>>(b->d_coeffs + first * n, n, point[0] % GL_P,
-                                                                    point[1] % GL_P, d_out);
-  LAUNCH_CHECK(ctx);
-  rc = d2h(ctx, out, d_out, 2 * count);
+  uint64_t *d_out = nullptr, *d_pt = nullptr;
+  int rc = upload_felts(ctx, point, 2, &d_pt);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_out, 2 * count);
+  if (rc == P2B_OK) rc = eval_ext_core(ctx, b, d_pt, first, count, d_out);
+  if (rc == P2B_OK) rc = d2h(ctx, out, d_out, 2 * count);
   dfree(ctx, d_out);
+  dfree(ctx, d_pt);
   return rc;
 }
 
@@ -1712,11 +1782,12 @@ extern "C" size_t p2b_fri_proof_len(const p2b_batch* const* oracles, size_t n_or
   return fri_proof_len_impl(oracles, n_oracles, fp);
 }
 
-extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
-                                  const p2b_fri_batch* batches, size_t n_batches, p2b_challenger* ch,
-                                  const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
-  CHECK_CTX(ctx);
-  if (!batches || !ch || !proof_out || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
+// d_points: n_batches extension points on the device (2 words each); d_proof: fri_proof_len words on the device.
+// The only host synchronisation inside is the proof-of-work search.
+static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
+                               const p2b_fri_batch* batches, size_t n_batches, const uint64_t* d_points,
+                               p2b_challenger* ch, const p2b_fri_params* fp, uint64_t* d_proof) {
+  if (!batches || !ch || !d_proof || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
   if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
   int rc = check_fri_params(ctx, oracles, n_oracles, fp);
   if (rc) return rc;
@@ -1727,7 +1798,6 @@ extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles,
   for (size_t o = 0; o < n_oracles; o++)
     if (oracles[o]->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "oracle of another context");
   const size_t proof_len = fri_proof_len_impl(oracles, n_oracles, fp);
-  if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
   // polynomial pointer tables of every batch
   std::vector<std::vector<const uint64_t*>> tabs(n_batches);
   size_t max_m = 0;
@@ -1747,10 +1817,10 @@ extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles,
   const size_t n_final = (N >> sum_ab) >> rate_bits;
 
   uint64_t *d_alpha = nullptr, *d_pw = nullptr, *d_ptrs = nullptr, *d_comp = nullptr, *d_quot = nullptr, *d_fin = nullptr;
-  uint64_t *d_coef = nullptr, *d_vals = nullptr, *d_final = nullptr, *d_chal = nullptr, *d_proof = nullptr;
+  uint64_t *d_coef = nullptr, *d_vals = nullptr, *d_final = nullptr, *d_chal = nullptr;
   std::vector<p2b_tree*> trees;
   auto cleanup = [&](int code) {
-    for (uint64_t* p : {d_alpha, d_pw, d_ptrs, d_comp, d_quot, d_fin, d_coef, d_vals, d_final, d_chal, d_proof}) dfree(ctx, p);
+    for (uint64_t* p : {d_alpha, d_pw, d_ptrs, d_comp, d_quot, d_fin, d_coef, d_vals, d_final, d_chal}) dfree(ctx, p);
     for (p2b_tree* t : trees) p2b_tree_free(t);
     return code;
   };
@@ -1782,7 +1852,6 @@ extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles,
   TRY(dmalloc(ctx, &d_vals, 2 * N));
   TRY(dmalloc(ctx, &d_final, 2 * (n_final ? n_final : 1)));
   TRY(dmalloc(ctx, &d_chal, fp->num_query_rounds ? fp->num_query_rounds : 1));
-  TRY(dmalloc(ctx, &d_proof, proof_len));
 
   stage_begin(ctx, ST_OTHER);
   // alpha = challenger.get_extension_challenge()
@@ -1797,8 +1866,7 @@ extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles,
     LAUNCHP();
     provk::k_reduce_polys<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint64_t* const*)d_ptrs, m, n, d_pw, d_comp, d_comp + n);
     LAUNCHP();
-    provk::k_divide_by_linear<<<1, 1024, 0, ctx->stream>>>(d_comp, d_comp + n, n, batches[bi].point[0] % GL_P,
-                                                          batches[bi].point[1] % GL_P, d_quot, d_quot + n);
+    provk::k_divide_by_linear<<<1, 1024, 0, ctx->stream>>>(d_comp, d_comp + n, n, d_points + 2 * bi, d_quot, d_quot + n);
     LAUNCHP();
     provk::k_shift_add<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_fin, d_fin + n, d_quot, d_quot + n, n, d_pw + 2 * m);
     LAUNCHP();
@@ -1867,10 +1935,181 @@ extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles,
   CUP(cudaMemcpyAsync(d_proof + off, &pow_witness, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   off += 1;
   stage_end(ctx);
-  CUP(cudaMemcpyAsync(proof_out, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUP(cudaStreamSynchronize(ctx->stream));
   return cleanup(off == proof_len ? P2B_OK : fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
 #undef TRY
 #undef CUP
 #undef LAUNCHP
+}
+
+extern "C" int p2b_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
+                                  const p2b_fri_batch* batches, size_t n_batches, p2b_challenger* ch,
+                                  const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+  CHECK_CTX(ctx);
+  if (!batches || !ch || !proof_out || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  int rc = check_fri_params(ctx, oracles, n_oracles, fp);
+  if (rc) return rc;
+  uint32_t log_len = 0;
+  if ((rc = check_fri_args(ctx, ((size_t)1 << oracles[0]->log_n) << fp->rate_bits, fp->reduction_arity_bits, fp->n_layers,
+                           fp->rate_bits, &log_len)))
+    return rc;
+  const size_t proof_len = fri_proof_len_impl(oracles, n_oracles, fp);
+  if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
+  std::vector<uint64_t> pts(2 * n_batches);
+  for (size_t i = 0; i < n_batches; i++) pts[2 * i] = batches[i].point[0], pts[2 * i + 1] = batches[i].point[1];
+  uint64_t *d_pts = nullptr, *d_proof = nullptr;
+  rc = upload_felts(ctx, pts.data(), pts.size(), &d_pts);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_proof, proof_len);
+  if (rc == P2B_OK) rc = prove_openings_core(ctx, oracles, n_oracles, batches, n_batches, d_pts, ch, fp, d_proof);
+  if (rc == P2B_OK) rc = d2h(ctx, proof_out, d_proof, proof_len);
+  dfree(ctx, d_pts);
+  dfree(ctx, d_proof);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ prove
+static size_t proof_len_impl(const p2b_circuit* c, const p2b_batch* cs, const p2b_fri_params* fp, size_t n_pis,
+                             size_t* fri_len_out) {
+  const p2b_circuit_desc& d = c->d;
+  const uint32_t nch = d.num_challenges;
+  // widths of the four oracles: constants|sigmas, wires, Zs|partial products, quotient chunks
+  p2b_batch shape[4];
+  for (int i = 0; i < 4; i++) shape[i].log_n = d.degree_bits, shape[i].rate_bits = fp->rate_bits, shape[i].cap_height = fp->cap_height;
+  shape[0].cap_height = cs->cap_height;
+  shape[0].n_cols = cs->n_cols;
+  shape[1].n_cols = d.num_wires;
+  shape[2].n_cols = (size_t)nch * (1 + d.num_partial_products);
+  shape[3].n_cols = (size_t)nch * d.quotient_degree_factor;
+  const p2b_batch* ptrs[4] = {&shape[0], &shape[1], &shape[2], &shape[3]};
+  const size_t fri_len = fri_proof_len_impl(ptrs, 4, fp);
+  if (fri_len_out) *fri_len_out = fri_len;
+  const size_t n_open = cs->n_cols + d.num_wires + shape[2].n_cols + nch + shape[3].n_cols;
+  return 3 * ((size_t)4 << fp->cap_height) + 2 * n_open + fri_len + n_pis;
+}
+
+extern "C" size_t p2b_proof_len(const p2b_circuit* c, const p2b_batch* cs, const p2b_fri_params* fp, size_t n_public_inputs) {
+  if (!c || !cs || !fp || fp->n_layers > P2B_MAX_FRI_LAYERS) return 0;
+  uint32_t sum = 0;
+  for (uint32_t l = 0; l < fp->n_layers; l++) sum += fp->reduction_arity_bits[l];
+  if (sum > c->d.degree_bits) return 0;
+  return proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
+}
+
+extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                         const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                         const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+  CHECK_CTX(ctx);
+  if (!c || !cs || !circuit_digest || !wire_cols || !fp || !proof_out || (n_public_inputs && !public_inputs))
+    return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (c->ctx != ctx || cs->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "handle of another context");
+  if (fp->n_layers > P2B_MAX_FRI_LAYERS) return fail(ctx, P2B_ERR_INVALID, "too many FRI layers");
+  if (cs->rate_bits != fp->rate_bits) return fail(ctx, P2B_ERR_INVALID, "constants_sigmas rate_bits differ from the FRI parameters");
+  const p2b_circuit_desc& d = c->d;
+  const uint32_t nch = d.num_challenges, rb = fp->rate_bits, caph = fp->cap_height;
+  size_t fri_len = 0;
+  const size_t proof_len = proof_len_impl(c, cs, fp, n_public_inputs, &fri_len);
+  if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
+  const size_t cap_words = (size_t)4 << caph;
+  const size_t w_zs = (size_t)nch * (1 + d.num_partial_products), w_q = (size_t)nch * d.quotient_degree_factor;
+
+  p2b_batch *wires = nullptr, *zs = nullptr, *qt = nullptr;
+  p2b_challenger* ch = nullptr;
+  uint64_t *d_small = nullptr, *d_proof = nullptr, *d_pis = nullptr;
+  auto cleanup = [&](int code) {
+    p2b_batch_free(qt);
+    p2b_batch_free(zs);
+    p2b_batch_free(wires);
+    p2b_challenger_free(ch);
+    dfree(ctx, d_small);
+    dfree(ctx, d_proof);
+    dfree(ctx, d_pis);
+    return code;
+  };
+#define TRY(expr)                             \
+  do {                                        \
+    int rc__ = (expr);                        \
+    if (rc__ != P2B_OK) return cleanup(rc__); \
+  } while (0)
+#define CUP(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+  // small device block: digest[4] | pi_hash[4] | betas[nch] | gammas[nch] | alphas[nch] | zeta[2] | zeta_next[2]
+  std::vector<uint64_t> h_small(8 + 3 * nch + 4, 0);
+  for (int i = 0; i < 4; i++) h_small[i] = circuit_digest[i];
+  TRY(upload_felts(ctx, h_small.data(), h_small.size(), &d_small));
+  uint64_t *d_digest = d_small, *d_pih = d_small + 4, *d_betas = d_small + 8, *d_gammas = d_betas + nch,
+           *d_alphas = d_gammas + nch, *d_zeta = d_alphas + nch, *d_zeta_next = d_zeta + 2;
+  TRY(dmalloc(ctx, &d_proof, proof_len));
+  // public_inputs_hash = PoseidonHash::hash_no_pad(public_inputs)
+  TRY(upload_felts(ctx, public_inputs, n_public_inputs, &d_pis));
+  hashk::k_hash_no_pad_single<<<1, 32, 0, ctx->stream>>>(d_pis, n_public_inputs, d_pih);
+  ctx->launches++;
+  // wires commitment
+  TRY(batch_from_host(ctx, wire_cols, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
+  TRY(p2b_challenger_new(ctx, &ch));
+  TRY(challenger_observe_dev(ch, d_digest, 4));
+  TRY(challenger_observe_dev(ch, d_pih, 4));
+  TRY(p2b_challenger_observe_cap(ch, &wires->tree));
+  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2 * nch, d_betas);  // betas then gammas
+  ctx->launches++;
+  TRY(zs_pp_core(ctx, c, cs, wires, d_betas, d_gammas, rb, caph, &zs));
+  TRY(p2b_challenger_observe_cap(ch, &zs->tree));
+  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, nch, d_alphas);
+  ctx->launches++;
+  TRY(quotient_core(ctx, c, cs, wires, zs, d_pih, d_betas, d_gammas, d_alphas, rb, caph, &qt));
+  TRY(p2b_challenger_observe_cap(ch, &qt->tree));
+  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_zeta);
+  ctx->launches++;
+  {
+    const uint64_t G = 1753635133440165772ull;
+    const uint64_t g = d.degree_bits ? h_powmod(G, (uint64_t)1 << (32 - d.degree_bits)) : 1;
+    provk::k_ext_scale<<<1, 32, 0, ctx->stream>>>(d_zeta, g, d_zeta_next);
+    ctx->launches++;
+  }
+  // proof layout: caps | openings (OpeningSet field order) | FRI proof | public inputs
+  size_t off = 0;
+  for (p2b_batch* b : {wires, zs, qt}) {
+    const p2b_tree& t = b->tree;
+    CUP(cudaMemcpyAsync(d_proof + off, t.d_levels + 4 * level_off(t.n_leaves, t.log_leaves - t.cap_height),
+                        cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    off += cap_words;
+  }
+  uint64_t* o_constants = d_proof + off;  // constants | sigmas contiguous = all of constants_sigmas
+  uint64_t* o_wires = o_constants + 2 * cs->n_cols;
+  uint64_t* o_zs = o_wires + 2 * (size_t)d.num_wires;
+  uint64_t* o_zs_next = o_zs + 2 * (size_t)nch;
+  uint64_t* o_pp = o_zs_next + 2 * (size_t)nch;
+  uint64_t* o_quot = o_pp + 2 * (w_zs - nch);
+  TRY(eval_ext_core(ctx, cs, d_zeta, 0, cs->n_cols, o_constants));
+  TRY(eval_ext_core(ctx, wires, d_zeta, 0, d.num_wires, o_wires));
+  TRY(eval_ext_core(ctx, zs, d_zeta, 0, nch, o_zs));
+  TRY(eval_ext_core(ctx, zs, d_zeta_next, 0, nch, o_zs_next));
+  TRY(eval_ext_core(ctx, zs, d_zeta, nch, w_zs - nch, o_pp));
+  TRY(eval_ext_core(ctx, qt, d_zeta, 0, w_q, o_quot));
+  off += 2 * (cs->n_cols + d.num_wires + w_zs + nch + w_q);
+  // challenger.observe_openings(&openings.to_fri_openings()): the zeta batch in FRI order, then zs_next
+  TRY(challenger_observe_dev(ch, o_constants, 2 * (cs->n_cols + d.num_wires + nch)));
+  TRY(challenger_observe_dev(ch, o_pp, 2 * (w_zs - nch + w_q)));
+  TRY(challenger_observe_dev(ch, o_zs_next, 2 * (size_t)nch));
+  // FRI instance (CommonCircuitData::get_fri_instance): everything at zeta, the Zs again at g * zeta
+  const p2b_batch* oracles[4] = {cs, wires, zs, qt};
+  p2b_fri_batch fb[2] = {};
+  fb[0].n_ranges = 4;
+  for (uint32_t o = 0; o < 4; o++) fb[0].ranges[o] = {o, 0, (uint32_t)oracles[o]->n_cols};
+  fb[1].n_ranges = 1;
+  fb[1].ranges[0] = {2, 0, nch};
+  TRY(check_fri_params(ctx, oracles, 4, fp));
+  TRY(prove_openings_core(ctx, oracles, 4, fb, 2, d_zeta, ch, fp, d_proof + off));  // d_zeta | d_zeta_next are adjacent
+  off += fri_len;
+  if (n_public_inputs)
+    CUP(cudaMemcpyAsync(d_proof + off, d_pis, n_public_inputs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  off += n_public_inputs;
+  if (off != proof_len) return cleanup(fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
+  CUP(cudaMemcpyAsync(proof_out, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUP(cudaStreamSynchronize(ctx->stream));
+  return cleanup(P2B_OK);
+#undef TRY
+#undef CUP
 }

@@ -60,7 +60,8 @@ struct PpParams {
   const uint64_t* sigmas;  // num_routed x n values on H
   const uint64_t* k_is;
   uint64_t* local;         // [challenge][chunk][n]: prefix products of the row's chunk quotients
-  uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
+  const uint64_t* betas;   // device: the transcript's challenges never have to visit the host
+  const uint64_t* gammas;
   uint32_t log_n, num_routed, chunk, n_chunks;
   ntt2::RootTables roots;
 };
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) k_pp_rows(PpParams P) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t ch = blockIdx.y;
-  const uint64_t beta = P.betas[ch], gamma = P.gammas[ch];
+  const uint64_t beta = gl::canon(P.betas[ch]), gamma = gl::canon(P.gammas[ch]);
   const uint64_t bx = fmul(beta, ntt2::root_pow(P.roots, P.log_n, i));  // beta * w^i
   uint64_t acc = 1;
   uint64_t* out = P.local + (size_t)ch * P.n_chunks * n + i;
@@ -357,8 +358,9 @@ struct QuotientParams {
   const uint64_t* apow;       // [challenge][n_terms] powers of alpha
   const uint64_t* zh;         // [2^mdb] Z_H on the coset, then [2^mdb] inverses
   uint64_t* out;              // [challenge][lde_size], natural order
-  uint64_t betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
-  uint64_t pi_hash[4];
+  const uint64_t* betas;      // device
+  const uint64_t* gammas;     // device
+  const uint64_t* pi_hash;    // device, 4 canonical elements
   uint32_t degree_bits, mdb;  // lde_size = 2^(degree_bits + mdb)
   uint32_t num_routed, num_constants, num_selectors, n_chal, chunk, num_pp, n_gates, n_terms;
   ntt2::RootTables roots;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
     for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + k], term));
   }
   for (uint32_t cc = 0; cc < nch; cc++) {
-    const uint64_t beta = P.betas[cc], gamma = P.gammas[cc];
+    const uint64_t beta = gl::canon(P.betas[cc]), gamma = gl::canon(P.gammas[cc]);
     const uint64_t bx = fmul(beta, x);
     for (uint32_t k = 0; k <= npp; k++) {
       uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
@@ -428,6 +430,18 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
     for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(filter, acc.a[c]));
   }
   for (uint32_t c = 0; c < nch; c++) P.out[(size_t)c * lde_size + i] = fmul(res[c], z_h_inv);
+}
+
+// apow[c * n_terms + k] = alphas[c]^k
+__global__ void k_build_apow(const uint64_t* __restrict__ alphas, uint32_t n_terms, uint64_t* __restrict__ apow) {
+  const uint32_t c = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const uint64_t a = gl::canon(alphas[c]);
+  uint64_t p = 1;
+  for (uint32_t k = 0; k < n_terms; k++) {
+    apow[(size_t)c * n_terms + k] = p;
+    p = fmul(p, a);
+  }
 }
 
 // coefficient k of every column *= base^k  (the second half of coset_ifft: divide by shift^k)

@@ -144,6 +144,51 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
   for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
 }
 
+// ---- warp-cooperative permutation (latency path) --------------------------------------------------------
+// A single permutation on one thread is a ~23k-instruction dependent stream (25-30 us): fine when a kernel has
+// 10^5 independent permutations in flight, ruinous for the transcript (one sponge), the top levels of a Merkle
+// tree and the small FRI layers, which are chains of a handful of permutations.  Here 16 lanes share one
+// permutation: lane l < 12 holds state element l, the S-boxes of a full round run in parallel, and the MDS
+// row of lane l gathers the other lanes with shuffles (the circulant makes the multiplier of step i the same
+// on every lane).  About 5 us per permutation.
+__device__ const uint64_t RC_G[372] = {  // the round constants again, in global memory: per-lane indexed loads
+#include "poseidon_rc.inc"
+};
+
+__device__ __forceinline__ uint64_t coop_mds(uint64_t s, uint32_t l) {
+  constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  uint64_t acc_lo = 0, acc_hi = 0;  // sums over the low / high 32-bit halves, < 2^42
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    uint32_t src = l + i;
+    if (src >= 12) src -= 12;
+    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)s, src, 16);
+    const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(s >> 32), src, 16);
+    const uint32_t c = C[i] + ((i == 0 && l == 0) ? 8u : 0u);  // diag(8, 0, ..., 0)
+    acc_lo += (uint64_t)lo * c;
+    acc_hi += (uint64_t)hi * c;
+  }
+  // acc_lo + 2^32 acc_hi mod p with 2^64 = 2^32 - 1
+  const uint32_t b_hi = (uint32_t)(acc_hi >> 32);
+  const uint64_t x = (acc_lo & 0xFFFFFFFFull) | (acc_hi << 32);
+  const uint64_t y = (((acc_lo >> 32) + b_hi) << 32) - b_hi;
+  uint64_t r = x + y;
+  if (r < x) r += GL_EPS;  // wrapped: r < 2^43, no second carry
+  return r;
+}
+
+// lane = threadIdx & 15; every lane of the warp must call (full-mask shuffles); lanes 12..15 carry garbage
+__device__ __forceinline__ uint64_t coop_permute_nc(uint64_t s, uint32_t l) {
+  const uint32_t lc = l < 12 ? l : 0;
+#pragma unroll 1
+  for (int r = 0; r < 30; r++) {
+    s = gl::add_nc(s, RC_G[12 * r + lc]);
+    if (r < 4 || r >= 26 || l == 0) s = sbox7(s);
+    s = coop_mds(s, l);
+  }
+  return s;
+}
+
 // two_to_one(l, r) = permute([l, r, 0,0,0,0])[0..4]
 __device__ __forceinline__ void two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
   uint64_t s[12] = {l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], 0, 0, 0, 0};

@@ -34,13 +34,13 @@ __device__ __forceinline__ ext2 ext_pow(ext2 b, size_t e) {
 }
 
 // out[p] = poly_p(point): one CTA per polynomial (column-major coefficients, n each)
-__global__ void __launch_bounds__(256) k_eval_polys_ext(const uint64_t* __restrict__ coeffs, size_t n, uint64_t z0,
-                                                         uint64_t z1, uint64_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_eval_polys_ext(const uint64_t* __restrict__ coeffs, size_t n,
+                                                         const uint64_t* __restrict__ zp, uint64_t* __restrict__ out) {
   __shared__ uint64_t s0[256], s1[256];
   const uint64_t* c = coeffs + (size_t)blockIdx.x * n;
   const uint32_t tid = threadIdx.x;
   const size_t per = (n + 255) / 256, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
-  const ext2 z{z0, z1};
+  const ext2 z{gl::canon(zp[0]), gl::canon(zp[1])};
   ext2 acc{0, 0};
   for (size_t k = hi; k-- > lo;) acc = horner_step(acc, z, gl::canon(c[k]));
   if (lo < n) acc = gl::ext_mul(acc, ext_pow(z, lo));
@@ -88,14 +88,14 @@ __global__ void __launch_bounds__(256) k_reduce_polys(const uint64_t* const* __r
 }
 
 // PolynomialCoeffs::divide_by_linear(z) followed by the zero pad: q[k-1] = b_k, b_k = b_{k+1} z + c_k, q[n-1] = 0.
-// One CTA of 1024 threads: local recurrences, a serial pass over the 1024 chunk carries, local recurrences again.
+// One CTA of 1024 threads: local recurrences, a log-step scan of the 1024 chunk carries, local recurrences again.
 __global__ void __launch_bounds__(1024) k_divide_by_linear(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1,
-                                                            size_t n, uint64_t z0, uint64_t z1, uint64_t* __restrict__ q0,
+                                                            size_t n, const uint64_t* __restrict__ zptr, uint64_t* __restrict__ q0,
                                                             uint64_t* __restrict__ q1) {
   __shared__ uint64_t L0[1024], L1[1024], Z0[1024], Z1[1024];
   const uint32_t tid = threadIdx.x;
   const size_t per = (n + 1023) / 1024, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
-  const ext2 z{z0, z1};
+  const ext2 z{gl::canon(zptr[0]), gl::canon(zptr[1])};
   ext2 acc{0, 0}, zp{1, 0};
   if (lo < n)
     for (size_t k = hi; k-- > lo;) {
@@ -104,17 +104,26 @@ __global__ void __launch_bounds__(1024) k_divide_by_linear(const uint64_t* __res
     }
   L0[tid] = acc.c0, L1[tid] = acc.c1, Z0[tid] = zp.c0, Z1[tid] = zp.c1;
   __syncthreads();
-  if (tid == 0) {  // carry into chunk t = b at the start of chunk t + 1
-    ext2 carry{0, 0};
-    for (int t = 1023; t >= 0; t--) {
-      ext2 l{L0[t], L1[t]}, p{Z0[t], Z1[t]};
-      L0[t] = carry.c0, L1[t] = carry.c1;
-      carry = gl::ext_add(l, gl::ext_mul(p, carry));
+  // suffix scan of the affine maps b_in -> L_t + Z_t b_in (composition towards lower t), Hillis-Steele:
+  // after the scan (L_t, Z_t) maps the carry into chunk t+k-1 ... here all the way from b_n = 0, so the value
+  // entering chunk t is the L of chunk t + 1.
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    ext2 l{L0[tid], L1[tid]}, p{Z0[tid], Z1[tid]};
+    const bool has = tid + off < 1024;
+    ext2 l2{0, 0}, p2{1, 0};
+    if (has) l2 = ext2{L0[tid + off], L1[tid + off]}, p2 = ext2{Z0[tid + off], Z1[tid + off]};
+    __syncthreads();
+    if (has) {
+      l = gl::ext_add(l, gl::ext_mul(p, l2));  // apply this chunk after the ones to its right
+      p = gl::ext_mul(p, p2);
+      L0[tid] = l.c0, L1[tid] = l.c1, Z0[tid] = p.c0, Z1[tid] = p.c1;
     }
+    __syncthreads();
   }
+  const ext2 carry_in = tid + 1 < 1024 ? ext2{L0[tid + 1], L1[tid + 1]} : ext2{0, 0};
   __syncthreads();
   if (lo >= n) return;
-  acc = ext2{L0[tid], L1[tid]};
+  acc = carry_in;
   for (size_t k = hi; k-- > lo;) {
     acc = gl::ext_add(gl::ext_mul(acc, z), ext2{c0[k], c1[k]});
     if (k >= 1) q0[k - 1] = acc.c0, q1[k - 1] = acc.c1;
@@ -131,6 +140,13 @@ __global__ void __launch_bounds__(256) k_shift_add(uint64_t* __restrict__ f0, ui
   ext2 r = gl::ext_mul(ext2{f0[k], f1[k]}, ext2{s[0], s[1]});
   f0[k] = gl::add(r.c0, q0[k]);
   f1[k] = gl::add(r.c1, q1[k]);
+}
+
+// out = g * z for a base-field g (zeta_next = g * zeta)
+__global__ void k_ext_scale(const uint64_t* __restrict__ z, uint64_t g, uint64_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out[0] = gl::mul(z[0], g);
+  out[1] = gl::mul(z[1], g);
 }
 
 // ---------------------------------------------------------------------------------------------- query rounds

@@ -493,10 +493,16 @@ def prove_openings(ctx, instance_batches, oracles, challenger, fri_params):
     buf = np.zeros(n_words, np.uint64)
     ctx.check(ctx.lib.p2b_prove_openings(ctx.h, handles, len(oracles), fb, nb, challenger.h, C.byref(ps), _ptr(buf),
                                          n_words))
-    # split the flat buffer in FriProof's field order
-    log_N = oracles[0].degree_log + fri_params.rate_bits
+    widths = [(o.n_cols, o.merkle_tree.cap_height) for o in oracles]
+    proof, pos = _parse_fri_proof(buf, 0, widths, oracles[0].degree_log, fri_params)
+    assert pos == n_words
+    return proof
+
+
+def _parse_fri_proof(buf, pos, widths, degree_log, fri_params):
+    """split the flat words p2b_prove_openings writes (FriProof's field order); widths = [(n_cols, cap_height)]"""
+    log_N = degree_log + fri_params.rate_bits
     cap_words = 4 << fri_params.cap_height
-    pos = 0
     caps = []
     for _ in fri_params.reduction_arity_bits:
         caps.append(buf[pos:pos + cap_words].reshape(-1, 4))
@@ -504,10 +510,10 @@ def prove_openings(ctx, instance_batches, oracles, challenger, fri_params):
     rounds = []
     for _ in range(fri_params.num_query_rounds):
         initial = []
-        for o in oracles:
-            L = log_N - o.merkle_tree.cap_height
-            leaf = buf[pos:pos + o.n_cols]
-            pos += o.n_cols
+        for n_cols, cap_h in widths:
+            L = log_N - cap_h
+            leaf = buf[pos:pos + n_cols]
+            pos += n_cols
             sib = buf[pos:pos + 4 * L].reshape(-1, 4)
             pos += 4 * L
             initial.append((leaf, sib))
@@ -526,8 +532,55 @@ def prove_openings(ctx, instance_batches, oracles, challenger, fri_params):
     final_poly = buf[pos:pos + 2 * n_final].reshape(-1, 2)
     pos += 2 * n_final
     pow_witness = int(buf[pos])
-    assert pos + 1 == n_words
-    return dict(commit_phase_merkle_caps=caps, query_round_proofs=rounds, final_poly=final_poly, pow_witness=pow_witness)
+    pos += 1
+    return dict(commit_phase_merkle_caps=caps, query_round_proofs=rounds, final_poly=final_poly,
+                pow_witness=pow_witness), pos
+
+
+def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params,
+                 raw=False):
+    """The same flow as prove() in ONE library call (p2b_prove): the transcript never leaves the device and the
+    host synchronises only for the proof-of-work search and the final download.  This is the call a patched
+    `CircuitData::prove` makes after witness generation (INTEGRATION.md)."""
+    d = circuit.desc
+    cols, ptrs, log_n = PolynomialBatch._cols(wire_values)
+    if len(cols) != d["num_wires"] or log_n != d["degree_bits"]:
+        raise ValueError("witness shape does not match the circuit")
+    pis = _felts(public_inputs) if len(public_inputs) else np.zeros(1, np.uint64)
+    ps = fri_params.struct()
+    cs = constants_sigmas_commitment
+    n_words = int(ctx.lib.p2b_proof_len(circuit.h, cs.h, C.byref(ps), len(public_inputs)))
+    if n_words == 0:
+        raise P2BError(-1, "inconsistent FRI parameters")
+    buf = np.zeros(n_words, np.uint64)
+    ctx.check(ctx.lib.p2b_prove(ctx.h, circuit.h, cs.h, _ptr(_felts(circuit_digest)), ptrs, _ptr(pis),
+                                len(public_inputs), C.byref(ps), _ptr(buf), n_words))
+    if raw:
+        return buf
+    nch, nc, nr = d["num_challenges"], d["num_constants"], d["num_routed_wires"]
+    npp, qdf = d["num_partial_products"], d["quotient_degree_factor"]
+    cap_words = 4 << fri_params.cap_height
+    pos = 0
+
+    def take(n_words_, shape):
+        nonlocal pos
+        a = buf[pos:pos + n_words_].reshape(shape)
+        pos += n_words_
+        return a
+
+    proof = dict(wires_cap=take(cap_words, (-1, 4)), plonk_zs_partial_products_cap=take(cap_words, (-1, 4)),
+                 quotient_polys_cap=take(cap_words, (-1, 4)))
+    op = {}
+    for k, cnt in (("constants", nc), ("plonk_sigmas", nr), ("wires", d["num_wires"]), ("plonk_zs", nch),
+                   ("plonk_zs_next", nch), ("partial_products", nch * npp), ("quotient_polys", nch * qdf)):
+        op[k] = take(2 * cnt, (-1, 2))
+    proof["openings"] = op
+    widths = [(cs.n_cols, cs.merkle_tree.cap_height), (d["num_wires"], fri_params.cap_height),
+              (nch * (1 + npp), fri_params.cap_height), (nch * qdf, fri_params.cap_height)]
+    proof["opening_proof"], pos = _parse_fri_proof(buf, pos, widths, d["degree_bits"], fri_params)
+    proof["public_inputs"] = [int(x) for x in buf[pos:pos + len(public_inputs)]]
+    assert pos + len(public_inputs) == n_words
+    return proof
 
 
 def prove(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params):

@@ -268,6 +268,26 @@ int p2b_prove_openings(p2b_ctx *ctx, const p2b_batch *const *oracles, size_t n_o
                        size_t n_batches, p2b_challenger *challenger, const p2b_fri_params *params, uint64_t *proof_out,
                        size_t proof_cap);
 
+/* ---------------------------------------------------------------- prove ------------------ */
+/* plonk::prover::prove_with_partition_witness from the filled witness onwards — what every
+ * `circuit_data.prove(pw)` call site of the reference spends its time in after witness
+ * generation — in ONE call: wires commit, betas/gammas, Z / partial products commit, alphas, quotient commit,
+ * zeta, openings, prove_openings.  The transcript stays on the device: the only host synchronisations are the
+ * proof-of-work search and the final download.  wire_cols[w] = witness.wire_values[w] (2^degree_bits values);
+ * constants_sigmas = prover_data.constants_sigmas_commitment (built with P2B_KEEP_VALUES).
+ * Output (u64 words, canonical, no length prefixes) in ProofWithPublicInputs' field order:
+ *   wires_cap | plonk_zs_partial_products_cap | quotient_polys_cap              3 x (4 << cap_height)
+ *   openings: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys
+ *             (2 words per extension element)
+ *   opening_proof: as p2b_prove_openings writes it
+ *   public_inputs                                                               n_public_inputs
+ * The proof-of-work witness is the minimal one (the reference's is schedule dependent). */
+size_t p2b_proof_len(const p2b_circuit *circuit, const p2b_batch *constants_sigmas, const p2b_fri_params *params,
+                     size_t n_public_inputs);
+int p2b_prove(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+              const uint64_t *circuit_digest, const uint64_t *const *wire_cols, const uint64_t *public_inputs,
+              size_t n_public_inputs, const p2b_fri_params *params, uint64_t *proof_out, size_t proof_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,8 @@ def gpu_prove(ctx, m, circ, digest, pis, fp):
     params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"],
                          fp["reduction_arity_bits"])
     proof = m.prove(ctx, cd, cs, digest, circ.wire_values(), pis, params)
+    native = m.prove_native(ctx, cd, cs, digest, circ.wire_values(), pis, params)
+    assert V.proofs_equal(native, proof) is None, "p2b_prove differs from the stage-by-stage flow: %s" % V.proofs_equal(native, proof)
     cs_cap = cs.cap
     cs.free()
     cd.free()

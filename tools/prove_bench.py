@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Throughput of complete synthetic proofs at the City Rollup shape (2^12 rows x 135 wires, rate 8, cap 4,
+16-bit PoW, 28 queries, arities [4,4]): one context, then several contexts on separate host threads / CUDA
+streams of the same GPU (the worker model of SURVEY.md §8(e): independent jobs, no collective).
+Prints one JSON object.  Development / measurement tool (bench.py embeds the same measurement)."""
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import city_rollup_b200 as m  # noqa: E402
+
+
+def build_case(degree_bits=12, seed=7):
+    import p2oracle as O
+    import plonk_ref as R
+    from test_plonk_oracle import ALL_GATES
+
+    pis = [seed, 2, 3, 4]
+    circ = R.SyntheticCircuit(degree_bits, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], seed, pi_hash=O.hash_no_pad(pis))
+    return circ, [1, 2, 3, 4], pis
+
+
+def run(n_ctx, n_proofs, circ, digest, pis, device=0):
+    params = m.FriParams(3, 4, 16, 28, [4, 4])
+    ctxs = [m.Context(device) for _ in range(n_ctx)]
+    state = []
+    for c in ctxs:
+        cd = m.CircuitData(c, circ.desc())
+        cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), 3, False, 4, keep_values=True)
+        state.append((cd, cs))
+    wv = circ.wire_values()
+    wires = []
+    for c in ctxs:  # witness columns in pinned host memory, one matrix per context: a single DMA per proof
+        w = c.pinned_empty((len(wv), wv[0].size))
+        for j, col in enumerate(wv):
+            w[j] = col
+        wires.append([w[j] for j in range(len(wv))])
+
+    def worker(i, k):
+        c = ctxs[i]
+        cd, cs = state[i]
+        for _ in range(k):
+            m.prove_native(c, cd, cs, digest, wires[i], pis, params, raw=True)
+
+    worker(0, 1)  # warm-up (tables, pools)
+    for i in range(1, n_ctx):
+        worker(i, 1)
+    per = n_proofs // n_ctx
+    th = [threading.Thread(target=worker, args=(i, per)) for i in range(n_ctx)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    for (cd, cs), c in zip(state, ctxs):
+        cs.free()
+        cd.free()
+        c.close()
+    return per * n_ctx / dt, dt / per * 1e3
+
+
+if __name__ == "__main__":
+    circ, digest, pis = build_case()
+    out = {}
+    for n_ctx in (1, 2, 4, 8, 12):
+        pps, ms = run(n_ctx, 48 * n_ctx, circ, digest, pis)
+        out[f"ctx{n_ctx}"] = {"proofs_per_s": round(pps, 2), "ms_per_proof_per_ctx": round(ms, 2)}
+    # stage profile of one proof
+    c = m.Context(0)
+    cd = m.CircuitData(c, circ.desc())
+    cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), 3, False, 4, keep_values=True)
+    params = m.FriParams(3, 4, 16, 28, [4, 4])
+    m.prove_native(c, cd, cs, digest, circ.wire_values(), pis, params)
+    c.profile_enable(True)
+    c.profile_read()
+    l0 = c.launch_count()
+    wv = circ.wire_values()
+    t0 = time.perf_counter()
+    m.prove_native(c, cd, cs, digest, wv, pis, params, raw=True)
+    out["one_proof_wall_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+    ms, cnt = c.profile_read()
+    out["stage_ms"] = {k: round(v, 3) for k, v in ms.items()}
+    out["launches_per_proof"] = c.launch_count() - l0
+    print(json.dumps(out))
