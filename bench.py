@@ -281,7 +281,7 @@ def run_cuda(args):
     }
     lde_bytes = 8 * N_COLS * n * 2 + 8 * N_COLS * (n << RATE_BITS)
     roofline_hbm = {
-        "kernels": "k_ntt_rows/k_ntt_cols (iNTT + 8 coset NTTs writing the leaf-ordered LDE)",
+        "kernels": "ntt2::k_strided + ntt2::k_row4096 (iNTT + 8 coset NTTs writing the leaf-ordered LDE)",
         "bound": "hbm", "achieved": lde_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": lde_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("ntt"),
         "peak_source": hbm_src, "algorithmic_bytes_per_step": lde_bytes, "ms_per_step": ntt_ms,
@@ -342,6 +342,22 @@ def run_cuda(args):
         except Exception as e:  # noqa: BLE001
             m2 = {"error": str(e)[:200]}
 
+    # ---- M1: complete synthetic proofs per second at the City Rollup shape (BASELINE.json metric, first half)
+    m1 = None
+    if world == 1 and not args.no_m1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import prove_bench as PB
+            circ, digest, pis = PB.build_case()
+            m1 = {"shape": "2^12 rows x 135 wires, 10 gate types, rate 8, cap 4, 16-bit PoW, 28 queries, arities [4,4] "
+                           "(city_common_circuit/src/circuits/zk_signature2/mod.rs:33-57); synthetic witness",
+                  "call": "p2b_prove (witness columns in pinned host memory -> proof words on the host)"}
+            for n_ctx in (1, 8):
+                pps, ms_pp = PB.run(n_ctx, 40 * n_ctx, circ, digest, pis, device=local)
+                m1[f"contexts_{n_ctx}"] = {"proofs_per_s": pps, "ms_per_proof_per_context": ms_pp}
+        except Exception as e:  # noqa: BLE001
+            m1 = {"error": str(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -355,6 +371,7 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N_COLS * n,
                 "d2h_bytes_per_step": 32 << CAP_HEIGHT, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "m2_lde_merkle_2p20x135": m2,
+        "m1_synthetic_proofs": m1,
     }
     print(json.dumps(line))
     ctx.close()
@@ -371,6 +388,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-m2", action="store_true")
+    ap.add_argument("--no-m1", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

@@ -10,18 +10,24 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import city_rollup_b200 as m  # noqa: E402
 
 
 def build_case(degree_bits=12, seed=7):
-    import p2oracle as O
+    """synthetic satisfiable circuit over the whole gate set (tests/plonk_ref.py is the witness generator; the
+    public-inputs hash comes from the GPU library, not from the oracle)"""
     import plonk_ref as R
-    from test_plonk_oracle import ALL_GATES
 
+    gates = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0),
+             (R.GATE_POSEIDON, 0, 0), (R.GATE_BASE_SUM, 63, 0), (R.GATE_U32_ARITHMETIC, 3, 0),
+             (R.GATE_U32_ADD_MANY, 3, 5), (R.GATE_U32_SUBTRACTION, 6, 0), (R.GATE_U32_RANGE_CHECK, 7, 0)]
     pis = [seed, 2, 3, 4]
-    circ = R.SyntheticCircuit(degree_bits, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], seed, pi_hash=O.hash_no_pad(pis))
+    c = m.Context(0)
+    pih = [int(x) for x in c.hash_no_pad(pis)]
+    c.close()
+    circ = R.SyntheticCircuit(degree_bits, gates, [(0, 4), (4, 5), (5, 8), (8, 10)], seed, pi_hash=pih)
     return circ, [1, 2, 3, 4], pis
 
 
