@@ -81,14 +81,24 @@ class MerkleTree {
 class PolynomialBatch {
  public:
   // from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)
+  // keep_values keeps the values on H in HBM (the witness columns / sigmas the Z stage reads again)
   static PolynomialBatch from_values(const Context& ctx, const std::vector<std::vector<F>>& values, size_t rate_bits,
-                                     bool blinding, size_t cap_height) {
-    return build(ctx, values, rate_bits, blinding, cap_height, true);
+                                     bool blinding, size_t cap_height, bool keep_values = false) {
+    return build(ctx, values, rate_bits, blinding, cap_height, true, keep_values);
   }
   // from_coeffs(polynomials, rate_bits, blinding, cap_height, timing, fft_root_table)
   static PolynomialBatch from_coeffs(const Context& ctx, const std::vector<std::vector<F>>& polys, size_t rate_bits,
                                      bool blinding, size_t cap_height) {
-    return build(ctx, polys, rate_bits, blinding, cap_height, false);
+    return build(ctx, polys, rate_bits, blinding, cap_height, false, false);
+  }
+  // adopt a handle produced by a prover stage (Z / partial products, quotient chunks)
+  PolynomialBatch(const Context& c, p2b_batch* b) : ctx_(&c), b_(b) {}
+  // OpeningSet's eval_commitment: polynomials [first, first + count) at an extension point
+  std::vector<Ext> eval_ext(const Ext& point, size_t first, size_t count) const {
+    std::vector<Ext> out(count ? count : 1);
+    ctx_->check(p2b_batch_eval_ext(b_, point.data(), first, count, out[0].data()));
+    out.resize(count);
+    return out;
   }
   PolynomialBatch(PolynomialBatch&& o) noexcept : ctx_(o.ctx_), b_(std::exchange(o.b_, nullptr)) {}
   ~PolynomialBatch() { if (b_) p2b_batch_free(b_); }
@@ -109,7 +119,7 @@ class PolynomialBatch {
  private:
   PolynomialBatch(const Context* c, p2b_batch* b) : ctx_(c), b_(b) {}
   static PolynomialBatch build(const Context& ctx, const std::vector<std::vector<F>>& cols, size_t rate_bits, bool blinding,
-                               size_t cap_height, bool values) {
+                               size_t cap_height, bool values, bool keep_values) {
     if (cols.empty()) throw Error(P2B_ERR_INVALID, "empty batch");
     size_t n = cols[0].size();
     uint32_t log_n = 0;
@@ -122,7 +132,7 @@ class PolynomialBatch {
     }
     p2b_batch* b = nullptr;
     auto fn = values ? p2b_batch_from_values : p2b_batch_from_coeffs;
-    ctx.check(fn(ctx.get(), ptrs.data(), ptrs.size(), log_n, (uint32_t)rate_bits, (uint32_t)cap_height, blinding ? 1u : 0u, &b));
+    ctx.check(fn(ctx.get(), ptrs.data(), ptrs.size(), log_n, (uint32_t)rate_bits, (uint32_t)cap_height, (blinding ? 2u : 0u) | (keep_values ? P2B_KEEP_VALUES : 0u), &b));
     return PolynomialBatch(&ctx, b);
   }
   const Context* ctx_;
@@ -176,6 +186,66 @@ inline F fri_proof_of_work(const Context& ctx, Challenger& challenger, uint32_t 
   F w = 0;
   ctx.check(p2b_fri_pow(ctx.get(), challenger.get(), proof_of_work_bits, &w));
   return w;
+}
+
+// The slice of CommonCircuitData the prover stages read (gates + selectors_info, counts, k_is), uploaded once
+class CircuitData {
+ public:
+  CircuitData(const Context& ctx, p2b_circuit_desc desc, std::vector<p2b_gate> gates, std::vector<F> k_is)
+      : ctx_(&ctx), gates_(std::move(gates)), k_is_(std::move(k_is)), desc_(desc) {
+    desc_.gates = gates_.data();
+    desc_.n_gates = (uint32_t)gates_.size();
+    desc_.k_is = k_is_.data();
+    ctx.check(p2b_circuit_new(ctx.get(), &desc_, &c_));
+  }
+  ~CircuitData() { p2b_circuit_free(c_); }
+  CircuitData(const CircuitData&) = delete;
+  const p2b_circuit_desc& desc() const { return desc_; }
+  p2b_circuit* get() const { return c_; }
+
+ private:
+  const Context* ctx_;
+  std::vector<p2b_gate> gates_;
+  std::vector<F> k_is_;
+  p2b_circuit_desc desc_;
+  p2b_circuit* c_ = nullptr;
+};
+
+// plonk::prover::all_wires_permutation_partial_products + the commit of [Zs, partial products]
+inline PolynomialBatch all_wires_permutation_partial_products(const Context& ctx, const CircuitData& circuit,
+                                                              const PolynomialBatch& constants_sigmas, const PolynomialBatch& wires,
+                                                              const std::vector<F>& betas, const std::vector<F>& gammas,
+                                                              uint32_t rate_bits, uint32_t cap_height) {
+  p2b_batch* out = nullptr;
+  ctx.check(p2b_zs_partial_products_commit(ctx.get(), circuit.get(), constants_sigmas.get(), wires.get(), betas.data(),
+                                           gammas.data(), rate_bits, cap_height, &out));
+  return PolynomialBatch(ctx, out);
+}
+
+// plonk::prover::compute_quotient_polys + chunking + from_coeffs
+inline PolynomialBatch compute_quotient_polys(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
+                                              const HashOut& public_inputs_hash, const PolynomialBatch& wires,
+                                              const PolynomialBatch& zs_partial_products, const std::vector<F>& betas,
+                                              const std::vector<F>& gammas, const std::vector<F>& alphas, uint32_t rate_bits,
+                                              uint32_t cap_height) {
+  p2b_batch* out = nullptr;
+  ctx.check(p2b_quotient_commit(ctx.get(), circuit.get(), constants_sigmas.get(), wires.get(), zs_partial_products.get(),
+                                public_inputs_hash.data(), betas.data(), gammas.data(), alphas.data(), rate_bits, cap_height, &out));
+  return PolynomialBatch(ctx, out);
+}
+
+// plonk::prover::prove_with_partition_witness after witness generation, one library call; returns the flat proof words
+// (ProofWithPublicInputs field order, include/p2b.h)
+inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
+                            const HashOut& circuit_digest, const std::vector<std::vector<F>>& wire_values,
+                            const std::vector<F>& public_inputs, const p2b_fri_params& params) {
+  std::vector<const F*> cols;
+  for (auto& c : wire_values) cols.push_back(c.data());
+  std::vector<F> out(p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size()));
+  if (out.empty()) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
+  ctx.check(p2b_prove(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), cols.data(), public_inputs.data(),
+                      public_inputs.size(), &params, out.data(), out.size()));
+  return out;
 }
 
 }  // namespace plonky2_b200

@@ -9,6 +9,29 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct p2b_batch { _p: [u8; 0] }
 #[repr(C)] pub struct p2b_tree { _p: [u8; 0] }
 #[repr(C)] pub struct p2b_challenger { _p: [u8; 0] }
+#[repr(C)] pub struct p2b_circuit { _p: [u8; 0] }
+
+pub const P2B_KEEP_VALUES: u32 = 1;
+
+/// `p2b_gate`: one entry of `common_data.gates` with its selector layout (`selectors_info`).
+#[repr(C)] #[derive(Clone, Copy, Debug)]
+pub struct p2b_gate { pub kind: u32, pub p0: u32, pub p1: u32, pub selector_index: u32, pub group_start: u32, pub group_end: u32, pub row: u32 }
+/// `p2b_circuit_desc`: the slice of `CommonCircuitData` the prover stages read.
+#[repr(C)]
+pub struct p2b_circuit_desc {
+    pub degree_bits: u32, pub num_wires: u32, pub num_routed_wires: u32, pub num_constants: u32, pub num_selectors: u32,
+    pub num_challenges: u32, pub quotient_degree_factor: u32, pub num_partial_products: u32, pub num_gate_constraints: u32,
+    pub n_gates: u32, pub gates: *const p2b_gate, pub k_is: *const u64,
+}
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct p2b_fri_range { pub oracle: u32, pub first: u32, pub count: u32 }
+#[repr(C)]
+pub struct p2b_fri_batch { pub point: [u64; 2], pub n_ranges: u32, pub ranges: [p2b_fri_range; 8] }
+#[repr(C)]
+pub struct p2b_fri_params {
+    pub rate_bits: u32, pub cap_height: u32, pub proof_of_work_bits: u32, pub num_query_rounds: u32,
+    pub n_layers: u32, pub reduction_arity_bits: [u32; 16],
+}
 
 extern "C" {
     pub fn p2b_version() -> c_int;
@@ -72,6 +95,26 @@ extern "C" {
         arity_bits: *const u32, n_layers: usize, rate_bits: u32, cap_height: u32,
         challenger: *mut p2b_challenger, layers_out: *mut *mut p2b_tree, final_poly_out: *mut u64) -> c_int;
     pub fn p2b_fri_pow(ctx: *mut p2b_ctx, challenger: *mut p2b_challenger, pow_bits: u32, witness_out: *mut u64) -> c_int;
+
+    pub fn p2b_batch_values(b: *mut p2b_batch, col: usize, out: *mut u64) -> c_int;
+    pub fn p2b_circuit_new(ctx: *mut p2b_ctx, desc: *const p2b_circuit_desc, out: *mut *mut p2b_circuit) -> c_int;
+    pub fn p2b_circuit_free(c: *mut p2b_circuit);
+    pub fn p2b_zs_partial_products_commit(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        wires: *const p2b_batch, betas: *const u64, gammas: *const u64, rate_bits: u32, cap_height: u32,
+        out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_quotient_commit(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        wires: *const p2b_batch, zs_partial_products: *const p2b_batch, pi_hash: *const u64, betas: *const u64,
+        gammas: *const u64, alphas: *const u64, rate_bits: u32, cap_height: u32, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_eval_ext(b: *mut p2b_batch, point: *const u64, first: usize, count: usize, out: *mut u64) -> c_int;
+    pub fn p2b_fri_proof_len(oracles: *const *const p2b_batch, n_oracles: usize, params: *const p2b_fri_params) -> usize;
+    pub fn p2b_prove_openings(ctx: *mut p2b_ctx, oracles: *const *const p2b_batch, n_oracles: usize,
+        batches: *const p2b_fri_batch, n_batches: usize, challenger: *mut p2b_challenger, params: *const p2b_fri_params,
+        proof_out: *mut u64, proof_cap: usize) -> c_int;
+    pub fn p2b_proof_len(circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch, params: *const p2b_fri_params,
+        n_public_inputs: usize) -> usize;
+    pub fn p2b_prove(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
+        params: *const p2b_fri_params, proof_out: *mut u64, proof_cap: usize) -> c_int;
 }
 
 /// Error type the patched plonky2 converts into `anyhow::Error` (the reference propagates it with `?`
@@ -118,4 +161,25 @@ pub fn batch_from_values(ctx: &Context, cols: &[&[u64]], rate_bits: usize, cap_h
         p2b_batch_from_values(ctx.0, ptrs.as_ptr(), ptrs.len(), n.trailing_zeros(), rate_bits as u32, cap_height as u32, 0, &mut h)
     })?;
     Ok(Batch(h))
+}
+
+
+/// Owning handle of the uploaded circuit description (built once per `CircuitData`, next to
+/// `prover_only.constants_sigmas_commitment`).
+pub struct Circuit(pub *mut p2b_circuit);
+unsafe impl Send for Circuit {}
+impl Drop for Circuit { fn drop(&mut self) { unsafe { p2b_circuit_free(self.0) } } }
+
+/// `prove_with_partition_witness` after witness generation: the flat proof words in `ProofWithPublicInputs`
+/// field order (see include/p2b.h); the patched plonky2 re-wraps them into `ProofWithPublicInputs<F, C, 2>`.
+pub fn prove(ctx: &Context, circuit: &Circuit, constants_sigmas: &Batch, circuit_digest: &[u64; 4],
+             wire_values: &[&[u64]], public_inputs: &[u64], params: &p2b_fri_params) -> Result<Vec<u64>, P2bError> {
+    let ptrs: Vec<*const u64> = wire_values.iter().map(|c| c.as_ptr()).collect();
+    let len = unsafe { p2b_proof_len(circuit.0, constants_sigmas.0, params, public_inputs.len()) };
+    let mut out = vec![0u64; len];
+    ctx.check(unsafe {
+        p2b_prove(ctx.0, circuit.0, constants_sigmas.0, circuit_digest.as_ptr(), ptrs.as_ptr(), public_inputs.as_ptr(),
+                  public_inputs.len(), params, out.as_mut_ptr(), len)
+    })?;
+    Ok(out)
 }
