@@ -32,6 +32,10 @@ struct p2b_ctx {
   // context's stream is handed to another context's next allocation behind an internal event dependency, which
   // chains the streams of concurrently proving contexts together.
   cudaMemPool_t pool = nullptr;
+  // second stream + events: host-to-device copies of a batch run ahead of the transforms of the previous
+  // column group (batch_from_host)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
   bool poisoned = false;
   std::string err;
   uint64_t launches = 0;
@@ -230,6 +234,7 @@ static int ctx_setup(p2b_ctx* ctx) {
   CU(ctx, cudaMemPoolCreate(&ctx->pool, &props));
   uint64_t thresh = UINT64_MAX;
   CU(ctx, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CU(ctx, cudaFuncSetAttribute(nttk::k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   int rc;
@@ -319,6 +324,8 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   if (ctx->cur_ev) cudaEventDestroy(ctx->cur_ev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -844,11 +851,99 @@ static int upload_cols(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols,
   return P2B_OK;
 }
 
+static cudaEvent_t copy_event(p2b_ctx* ctx, size_t i) {
+  while (ctx->copy_events.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ctx->copy_events.push_back(e);
+  }
+  return ctx->copy_events[i];
+}
+
+// from_values / from_coeffs of host columns, pipelined: the columns are uploaded in groups on the copy stream and
+// the transforms of group g (inverse NTT, LDE) run on the compute stream while group g+1 is still in flight, so
+// that for a wide batch only the first group's copy and the leaf hashing are exposed.
+static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n,
+                                     uint32_t rate_bits, uint32_t cap_height, bool is_values, bool keep_values,
+                                     p2b_batch** out) {
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  const size_t group = 16;
+  p2b_batch* b = new (std::nothrow) p2b_batch();
+  if (!b) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  b->ctx = ctx;
+  b->n_cols = n_cols;
+  b->log_n = log_n;
+  b->rate_bits = rate_bits;
+  b->cap_height = cap_height;
+  b->tree.owned_by_batch = true;
+  uint64_t* d_in = nullptr;
+  int rc = dmalloc(ctx, &d_in, n_cols * n);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &b->d_lde, n_cols * N);
+  if (rc == P2B_OK && is_values) rc = dmalloc(ctx, &b->d_coeffs, n_cols * n);
+  auto bail = [&](int code) {
+    cudaStreamSynchronize(ctx->copy_stream);  // no copy may still target buffers that are about to be freed
+    if (d_in != b->d_coeffs && d_in != b->d_values) dfree(ctx, d_in);
+    p2b_batch_free(b);
+    return code;
+  };
+  if (rc) return bail(rc);
+  if (!is_values) b->d_coeffs = d_in;
+  // the copy stream must not write before the (stream-ordered) allocations have happened
+  cudaEvent_t ev0 = copy_event(ctx, 0);
+  if (!ev0) return bail(fail(ctx, P2B_ERR_CUDA, "cudaEventCreate failed"));
+  if (cudaEventRecord(ev0, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ev0, 0) != cudaSuccess)
+    return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));
+  stage_begin(ctx, ST_H2D);
+  size_t gi = 0;
+  for (size_t c0 = 0; c0 < n_cols; c0 += group, gi++) {
+    const size_t c1 = c0 + group < n_cols ? c0 + group : n_cols;
+    size_t c = c0;
+    while (c < c1) {  // one DMA per run of columns contiguous in host memory
+      size_t e = c + 1;
+      while (e < c1 && cols[e] == cols[e - 1] + n) e++;
+      if (!cols[c]) return bail(fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c));
+      cudaError_t err = cudaMemcpyAsync(d_in + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (err != cudaSuccess) return bail(fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(err)));
+      c = e;
+    }
+    cudaEvent_t ev = copy_event(ctx, gi + 1);
+    if (!ev || cudaEventRecord(ev, ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ev, 0) != cudaSuccess)
+      return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));
+    const size_t k = c1 - c0;
+    if (is_values) {
+      stage_begin(ctx, ST_INTT);
+      rc = run_intt(ctx, d_in + c0 * n, b->d_coeffs + c0 * n, b->d_lde + c0 * N, k, log_n, N);
+      if (rc) return bail(rc);
+    }
+    stage_begin(ctx, ST_LDE);
+    rc = run_lde(ctx, b->d_coeffs + c0 * n, n, b->d_lde + c0 * N, k, log_n, rate_bits, 7);
+    if (rc) return bail(rc);
+  }
+  stage_end(ctx);
+  if (is_values) {
+    if (keep_values)
+      b->d_values = d_in;
+    else
+      dfree(ctx, d_in);
+  }
+  rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
+  if (rc != P2B_OK) {
+    d_in = nullptr;
+    return bail(rc);
+  }
+  *out = b;
+  return P2B_OK;
+}
+
 static int batch_from_host(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n, uint32_t rate_bits,
                            uint32_t cap_height, uint32_t flags, bool is_values, p2b_batch** out) {
   CHECK_CTX(ctx);
   int rc = check_batch_args(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, out);
   if (rc) return rc;
+  // wide batches of long columns: overlap the upload with the transforms, group by group
+  if (n_cols >= 32 && log_n >= 14)
+    return batch_from_host_pipelined(ctx, cols, n_cols, log_n, rate_bits, cap_height, is_values,
+                                     is_values && (flags & P2B_KEEP_VALUES), out);
   uint64_t* d_in = nullptr;
   stage_begin(ctx, ST_H2D);
   rc = upload_cols(ctx, cols, n_cols, (size_t)1 << log_n, &d_in);
@@ -999,6 +1094,16 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
       case plonk::GATE_U32_ADD_MANY: wires = (gt.p0 + 3 + 18) * gt.p1, cons = 21 * gt.p1; break;
       case plonk::GATE_U32_SUBTRACTION: wires = 21 * gt.p0, cons = 19 * gt.p0; break;
       case plonk::GATE_U32_RANGE_CHECK: wires = 17 * gt.p0, cons = 17 * gt.p0; break;
+      case plonk::GATE_U32_INTERLEAVE: wires = 34 * gt.p0, cons = 34 * gt.p0; break;
+      case plonk::GATE_UNINTERLEAVE_TO_U32:
+      case plonk::GATE_UNINTERLEAVE_TO_B32: wires = 67 * gt.p0, cons = 67 * gt.p0; break;
+      case plonk::GATE_COMPARISON: {
+        if (gt.p1 == 0 || gt.p0 == 0 || (gt.p0 + gt.p1 - 1) / gt.p1 > 8)
+          return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: ComparisonGate(%u, %u)", g, gt.p0, gt.p1);
+        const uint32_t cb = (gt.p0 + gt.p1 - 1) / gt.p1;
+        wires = 4 + 5 * gt.p1 + cb + 1, cons = 6 + 5 * gt.p1 + cb;
+        break;
+      }
       default: break;
     }
     if (wires > d.num_wires || consts > d.num_constants - d.num_selectors || cons > d.num_gate_constraints)

@@ -10,7 +10,8 @@
 //   gates/{noop,constant,public_input,arithmetic_base,base_sum,poseidon}.rs  eval_unfiltered_base_*
 // and the in-tree gates of the reference (scalar eval_unfiltered is the specification):
 //   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150, add_many_u32.rs:87-135,
-//   subtraction_u32.rs:82-125, range_check_u32.rs:51-75.
+//   subtraction_u32.rs:82-125, range_check_u32.rs:51-75, interleave_u32.rs:86-127, uninterleave_to_u32.rs:93-136,
+//   uninterleave_to_b32.rs:97-141, comparison.rs:96-170.
 //
 // Design.  One thread = one point of the quotient LDE coset.  plonky2 materialises every constraint of
 // every gate for a batch of 32 points and then reduces them with the powers of alpha; here every constraint
@@ -40,7 +41,11 @@ enum GateKind : uint32_t {
   GATE_U32_ADD_MANY = 7,
   GATE_U32_SUBTRACTION = 8,
   GATE_U32_RANGE_CHECK = 9,
-  GATE_KIND_COUNT = 10
+  GATE_U32_INTERLEAVE = 10,
+  GATE_UNINTERLEAVE_TO_U32 = 11,
+  GATE_UNINTERLEAVE_TO_B32 = 12,
+  GATE_COMPARISON = 13,
+  GATE_KIND_COUNT = 14
 };
 
 struct Gate {  // mirrors p2b_gate (include/p2b.h)
@@ -340,6 +345,84 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
         acc.push(fsub(comb, v.w(i)));
         for (int j = 0; j < 16; j++) acc.push(limb4_product(v.w(nl + 16 * i + j)));
       }
+      break;
+    }
+    case GATE_U32_INTERLEAVE: {  // 32 big-endian bits per op after the 2 * ops routed wires
+      const uint32_t ops = g.p0;
+      for (uint32_t i = 0; i < ops; i++) {
+        uint64_t cx = 0, cxi = 0;
+        for (int j = 0; j < 32; j++) {
+          const uint64_t b = v.w(2 * ops + 32 * i + j);
+          cx = fadd(fadd(cx, cx), b);
+          cxi = fadd(fmul(cxi, 4), b);
+        }
+        acc.push(fsub(cx, v.w(2 * i)));
+        acc.push(fsub(cxi, v.w(2 * i + 1)));
+        for (int j = 0; j < 32; j++) {
+          const uint64_t b = v.w(2 * ops + 32 * i + j);
+          acc.push(fmul(b, fsub(b, 1)));
+        }
+      }
+      break;
+    }
+    case GATE_UNINTERLEAVE_TO_U32:
+    case GATE_UNINTERLEAVE_TO_B32: {  // 64 big-endian bits per op after the 3 * ops routed wires
+      const uint32_t ops = g.p0;
+      const bool b32 = g.kind == GATE_UNINTERLEAVE_TO_B32;
+      for (uint32_t i = 0; i < ops; i++) {
+        uint64_t cx = 0, ce = 0, co = 0;
+        for (int j = 0; j < 64; j++) cx = fadd(fadd(cx, cx), v.w(3 * ops + 64 * i + j));
+        acc.push(fsub(cx, v.w(3 * i)));
+        for (int j = 0; j < 32; j++) {
+          const uint64_t coeff = b32 ? (1ull << (2 * (31 - j))) : (1ull << (31 - j));
+          ce = fadd(ce, fmul(coeff, v.w(3 * ops + 64 * i + 2 * j)));
+          co = fadd(co, fmul(coeff, v.w(3 * ops + 64 * i + 2 * j + 1)));
+        }
+        acc.push(fsub(ce, v.w(3 * i + 1)));
+        acc.push(fsub(co, v.w(3 * i + 2)));
+        for (int j = 0; j < 64; j++) {
+          const uint64_t b = v.w(3 * ops + 64 * i + j);
+          acc.push(fmul(b, fsub(b, 1)));
+        }
+      }
+      break;
+    }
+    case GATE_COMPARISON: {  // p0 = num_bits, p1 = num_chunks
+      const uint32_t nc = g.p1, cb = (g.p0 + nc - 1) / nc;
+      uint64_t f_comb = 0, s_comb = 0;
+      for (uint32_t i = nc; i-- > 0;) {
+        f_comb = fadd(fmul(f_comb, 1ull << cb), v.w(4 + i));
+        s_comb = fadd(fmul(s_comb, 1ull << cb), v.w(4 + nc + i));
+      }
+      acc.push(fsub(f_comb, v.w(0)));
+      acc.push(fsub(s_comb, v.w(1)));
+      uint64_t msd = 0;
+      for (uint32_t i = 0; i < nc; i++) {
+        const uint64_t fc = v.w(4 + i), sc = v.w(4 + nc + i);
+        uint64_t fp = 1, sp = 1;
+        for (uint64_t x = 0; x < (1ull << cb); x++) {
+          fp = fmul(fp, fsub(fc, x));
+          sp = fmul(sp, fsub(sc, x));
+        }
+        acc.push(fp);
+        acc.push(sp);
+        const uint64_t diff = fsub(sc, fc);
+        const uint64_t dummy = v.w(4 + 2 * nc + i), eq = v.w(4 + 3 * nc + i), inter = v.w(4 + 4 * nc + i);
+        acc.push(fsub(fmul(diff, dummy), fsub(1, eq)));
+        acc.push(fmul(eq, diff));
+        acc.push(fsub(inter, fmul(eq, msd)));
+        msd = fadd(inter, fmul(fsub(1, eq), diff));
+      }
+      const uint64_t msd_w = v.w(3);
+      acc.push(fsub(msd_w, msd));
+      uint64_t comb = 0;
+      for (uint32_t b = 0; b <= cb; b++) {
+        const uint64_t bit = v.w(4 + 5 * nc + b);
+        acc.push(fmul(bit, fsub(1, bit)));
+      }
+      for (uint32_t b = cb + 1; b-- > 0;) comb = fadd(fadd(comb, comb), v.w(4 + 5 * nc + b));
+      acc.push(fsub(fadd(1ull << cb, msd_w), comb));
+      acc.push(fsub(v.w(2), v.w(4 + 5 * nc + cb)));
       break;
     }
     default:

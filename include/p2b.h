@@ -139,7 +139,11 @@ typedef enum {
   P2B_GATE_U32_ARITHMETIC = 6,  /* city_common_circuit/src/u32/gates/arithmetic_u32.rs  { num_ops = p0 } */
   P2B_GATE_U32_ADD_MANY = 7,    /* .../add_many_u32.rs { num_addends = p0, num_ops = p1 } */
   P2B_GATE_U32_SUBTRACTION = 8, /* .../subtraction_u32.rs { num_ops = p0 } */
-  P2B_GATE_U32_RANGE_CHECK = 9  /* .../range_check_u32.rs { num_input_limbs = p0 } */
+  P2B_GATE_U32_RANGE_CHECK = 9, /* .../range_check_u32.rs { num_input_limbs = p0 } */
+  P2B_GATE_U32_INTERLEAVE = 10, /* .../interleave_u32.rs { num_ops = p0 } */
+  P2B_GATE_UNINTERLEAVE_TO_U32 = 11, /* .../uninterleave_to_u32.rs { num_ops = p0 } */
+  P2B_GATE_UNINTERLEAVE_TO_B32 = 12, /* .../uninterleave_to_b32.rs { num_ops = p0 } */
+  P2B_GATE_COMPARISON = 13      /* .../comparison.rs { num_bits = p0, num_chunks = p1 } ((32, 16) in pad_circuit.rs:33) */
 } p2b_gate_kind;
 typedef struct {
   uint32_t kind, p0, p1;

@@ -126,7 +126,11 @@ enum {
   P2O_GATE_U32_ARITHMETIC = 6,  /* p0 = num_ops */
   P2O_GATE_U32_ADD_MANY = 7,    /* p0 = num_addends, p1 = num_ops */
   P2O_GATE_U32_SUBTRACTION = 8, /* p0 = num_ops */
-  P2O_GATE_U32_RANGE_CHECK = 9  /* p0 = num_input_limbs */
+  P2O_GATE_U32_RANGE_CHECK = 9, /* p0 = num_input_limbs */
+  P2O_GATE_U32_INTERLEAVE = 10, /* p0 = num_ops */
+  P2O_GATE_UNINTERLEAVE_TO_U32 = 11, /* p0 = num_ops */
+  P2O_GATE_UNINTERLEAVE_TO_B32 = 12, /* p0 = num_ops */
+  P2O_GATE_COMPARISON = 13      /* p0 = num_bits, p1 = num_chunks */
 };
 typedef struct {
   uint32_t kind, p0, p1;

@@ -12,6 +12,9 @@
  *   city_common_circuit/src/u32/gates/add_many_u32.rs:87-135    (U32AddManyGate)
  *   city_common_circuit/src/u32/gates/subtraction_u32.rs:82-125 (U32SubtractionGate)
  *   city_common_circuit/src/u32/gates/range_check_u32.rs:51-75  (U32RangeCheckGate)
+ *   city_common_circuit/src/u32/gates/interleave_u32.rs:86-127  (U32InterleaveGate)
+ *   city_common_circuit/src/u32/gates/uninterleave_to_u32.rs:93-136, uninterleave_to_b32.rs:97-141
+ *   city_common_circuit/src/u32/gates/comparison.rs:96-170      (ComparisonGate; (32, 16) at builder/pad_circuit.rs:33)
  * Parameters a circuit is described by follow city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145.
  * PARITY STATUS: unpinned by reference fixtures; checked in tests/ against an independent
  * extension-field evaluation of the verifier identity vanishing(zeta) = Z_H(zeta) * t(zeta).
@@ -288,6 +291,76 @@ static unsigned eval_gate(const p2o_gate *g, const gate_vars *v, uint64_t *out) 
           out[k++] = prod;
         }
       }
+      return k;
+    }
+    case P2O_GATE_U32_INTERLEAVE: { /* p0 = num_ops; 2 routed wires per op, 32 big-endian bits */
+      const unsigned ops = g->p0;
+      for (unsigned i = 0; i < ops; i++) {
+        const uint64_t *bits = w + 2 * ops + 32 * i;
+        uint64_t cx = 0, cxi = 0;
+        for (int j = 0; j < 32; j++) { /* reduce_with_powers(bits.rev(), base) */
+          cx = gli_add(gli_mul(cx, 2), bits[j]);
+          cxi = gli_add(gli_mul(cxi, 4), bits[j]);
+        }
+        out[k++] = gli_sub(cx, w[2 * i]);
+        out[k++] = gli_sub(cxi, w[2 * i + 1]);
+        for (int j = 0; j < 32; j++) out[k++] = gli_mul(bits[j], gli_sub(bits[j], 1));
+      }
+      return k;
+    }
+    case P2O_GATE_UNINTERLEAVE_TO_U32:
+    case P2O_GATE_UNINTERLEAVE_TO_B32: { /* p0 = num_ops; 3 routed wires per op, 64 big-endian bits */
+      const unsigned ops = g->p0;
+      const int b32 = g->kind == P2O_GATE_UNINTERLEAVE_TO_B32;
+      for (unsigned i = 0; i < ops; i++) {
+        const uint64_t *bits = w + 3 * ops + 64 * i;
+        uint64_t cx = 0, ce = 0, co = 0;
+        for (int j = 0; j < 64; j++) cx = gli_add(gli_mul(cx, 2), bits[j]);
+        out[k++] = gli_sub(cx, w[3 * i]);
+        for (int j = 0; j < 32; j++) {
+          uint64_t coeff = b32 ? (1ull << (2 * (31 - j))) : (1ull << (31 - j));
+          ce = gli_add(ce, gli_mul(coeff, bits[2 * j]));
+          co = gli_add(co, gli_mul(coeff, bits[2 * j + 1]));
+        }
+        out[k++] = gli_sub(ce, w[3 * i + 1]);
+        out[k++] = gli_sub(co, w[3 * i + 2]);
+        for (int j = 0; j < 64; j++) out[k++] = gli_mul(bits[j], gli_sub(bits[j], 1));
+      }
+      return k;
+    }
+    case P2O_GATE_COMPARISON: { /* p0 = num_bits, p1 = num_chunks */
+      const unsigned nc = g->p1, cb = (g->p0 + nc - 1) / nc;
+      const uint64_t *fc = w + 4, *sc = w + 4 + nc;
+      uint64_t f_comb = 0, s_comb = 0;
+      for (unsigned i = nc; i-- > 0;) {
+        f_comb = gli_add(gli_mul(f_comb, 1ull << cb), fc[i]);
+        s_comb = gli_add(gli_mul(s_comb, 1ull << cb), sc[i]);
+      }
+      out[k++] = gli_sub(f_comb, w[0]);
+      out[k++] = gli_sub(s_comb, w[1]);
+      uint64_t msd = 0;
+      for (unsigned i = 0; i < nc; i++) {
+        uint64_t fp = 1, sp = 1;
+        for (uint64_t x = 0; x < (1ull << cb); x++) {
+          fp = gli_mul(fp, gli_sub(fc[i], x));
+          sp = gli_mul(sp, gli_sub(sc[i], x));
+        }
+        out[k++] = fp;
+        out[k++] = sp;
+        uint64_t diff = gli_sub(sc[i], fc[i]);
+        uint64_t dummy = w[4 + 2 * nc + i], eq = w[4 + 3 * nc + i], inter = w[4 + 4 * nc + i];
+        out[k++] = gli_sub(gli_mul(diff, dummy), gli_sub(1, eq));
+        out[k++] = gli_mul(eq, diff);
+        out[k++] = gli_sub(inter, gli_mul(eq, msd));
+        msd = gli_add(inter, gli_mul(gli_sub(1, eq), diff));
+      }
+      out[k++] = gli_sub(w[3], msd);
+      const uint64_t *bits = w + 4 + 5 * nc;
+      uint64_t comb = 0;
+      for (unsigned b = 0; b <= cb; b++) out[k++] = gli_mul(bits[b], gli_sub(1, bits[b]));
+      for (unsigned b = cb + 1; b-- > 0;) comb = gli_add(gli_mul(comb, 2), bits[b]);
+      out[k++] = gli_sub(gli_add(1ull << cb, w[3]), comb);
+      out[k++] = gli_sub(w[2], bits[cb]);
       return k;
     }
     default:

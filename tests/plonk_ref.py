@@ -24,7 +24,8 @@ PF = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(PF)  # derives FIRST / POST / INIT / W_HATS / VS from MDS + round constants, self-checks
 
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM, GATE_U32_ARITHMETIC,
- GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK) = range(10)
+ GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK, GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32,
+ GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON) = range(14)
 UNUSED_SELECTOR = 2**32 - 1
 
 
@@ -259,6 +260,74 @@ def eval_gate(kind, p0, p1, w, consts, pi_hash):
             for j in range(16):
                 limb = w[nl + 16 * i + j]
                 c.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+    elif kind == GATE_U32_INTERLEAVE:  # interleave_u32.rs:86-127; bits big-endian
+        ops = p0
+        for i in range(ops):
+            x, xi = w[2 * i], w[2 * i + 1]
+            bits = [w[2 * ops + 32 * i + j] for j in range(32)]
+            cx, cxi = w[0] * 0, w[0] * 0
+            for b in bits:  # reduce_with_powers(bits.rev(), base): Horner from the most significant bit
+                cx = cx * 2 + b
+                cxi = cxi * 4 + b
+            c.append(cx - x)
+            c.append(cxi - xi)
+            for b in bits:
+                c.append(b * (b - 1))
+    elif kind in (GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32):  # uninterleave_to_u32.rs:93-136 / _b32.rs:97-141
+        ops = p0
+        for i in range(ops):
+            xi, xe, xo = w[3 * i], w[3 * i + 1], w[3 * i + 2]
+            bits = [w[3 * ops + 64 * i + j] for j in range(64)]
+            cx = w[0] * 0
+            for b in bits:
+                cx = cx * 2 + b
+            c.append(cx - xi)
+            ce, co = w[0] * 0, w[0] * 0
+            for j in range(32):
+                coeff = (1 << (31 - j)) if kind == GATE_UNINTERLEAVE_TO_U32 else (1 << (2 * (31 - j)))
+                ce = ce + bits[2 * j] * coeff
+                co = co + bits[2 * j + 1] * coeff
+            c.append(ce - xe)
+            c.append(co - xo)
+            for b in bits:
+                c.append(b * (b - 1))
+    elif kind == GATE_COMPARISON:  # comparison.rs:96-170; p0 = num_bits, p1 = num_chunks
+        nb, nc = p0, p1
+        cb = -(-nb // nc)
+        first, second = w[0], w[1]
+        fc = [w[4 + i] for i in range(nc)]
+        sc = [w[4 + nc + i] for i in range(nc)]
+        f_comb, s_comb = w[0] * 0, w[0] * 0
+        for i in reversed(range(nc)):
+            f_comb = f_comb * (1 << cb) + fc[i]
+            s_comb = s_comb * (1 << cb) + sc[i]
+        c.append(f_comb - first)
+        c.append(s_comb - second)
+        msd = w[0] * 0
+        for i in range(nc):
+            fp = fc[i] * 0 + 1
+            sp = fp
+            for x in range(1 << cb):
+                fp = fp * (fc[i] - x)
+                sp = sp * (sc[i] - x)
+            c.append(fp)
+            c.append(sp)
+            diff = sc[i] - fc[i]
+            dummy, eq = w[4 + 2 * nc + i], w[4 + 3 * nc + i]
+            c.append(diff * dummy - (1 - eq))
+            c.append(eq * diff)
+            inter = w[4 + 4 * nc + i]
+            c.append(inter - eq * msd)
+            msd = inter + (1 - eq) * diff
+        c.append(w[3] - msd)
+        bits = [w[4 + 5 * nc + k] for k in range(cb + 1)]
+        for b in bits:
+            c.append(b * (1 - b))
+        comb = w[0] * 0
+        for b in reversed(bits):
+            comb = comb * 2 + b
+        c.append(w[3] + (1 << cb) - comb)
+        c.append(w[2] - bits[cb])
     else:
         raise ValueError(kind)
     return c
@@ -267,13 +336,16 @@ def eval_gate(kind, p0, p1, w, consts, pi_hash):
 def gate_degree(kind):
     return {GATE_NOOP: 0, GATE_CONSTANT: 1, GATE_PUBLIC_INPUT: 1, GATE_ARITHMETIC: 3, GATE_POSEIDON: 7,
             GATE_BASE_SUM: 2, GATE_U32_ARITHMETIC: 4, GATE_U32_ADD_MANY: 4, GATE_U32_SUBTRACTION: 4,
-            GATE_U32_RANGE_CHECK: 4}[kind]
+            GATE_U32_RANGE_CHECK: 4, GATE_U32_INTERLEAVE: 2, GATE_UNINTERLEAVE_TO_U32: 2, GATE_UNINTERLEAVE_TO_B32: 2,
+            GATE_COMPARISON: 4}[kind]  # ComparisonGate: 2^chunk_bits with chunk_bits = 2
 
 
 def gate_num_constraints(kind, p0, p1):
     return {GATE_NOOP: 0, GATE_CONSTANT: p0, GATE_PUBLIC_INPUT: 4, GATE_ARITHMETIC: p0, GATE_POSEIDON: 123,
             GATE_BASE_SUM: 1 + p0, GATE_U32_ARITHMETIC: p0 * 36, GATE_U32_ADD_MANY: p1 * 21,
-            GATE_U32_SUBTRACTION: p0 * 19, GATE_U32_RANGE_CHECK: p0 * 17}[kind]
+            GATE_U32_SUBTRACTION: p0 * 19, GATE_U32_RANGE_CHECK: p0 * 17, GATE_U32_INTERLEAVE: p0 * 34,
+            GATE_UNINTERLEAVE_TO_U32: p0 * 67, GATE_UNINTERLEAVE_TO_B32: p0 * 67,
+            GATE_COMPARISON: 6 + 5 * p1 + -(-p0 // max(p1, 1))}[kind]
 
 
 # ------------------------------------------------------------------------------------------ witness generation
@@ -425,6 +497,51 @@ class SyntheticCircuit:
                     v = rng.randrange(2**32)
                     row[o] = v
                     row[p0 + 16 * o:p0 + 16 * (o + 1)] = _limbs2(v, 16)
+            elif kind == GATE_U32_INTERLEAVE:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                for o in range(p0):
+                    x = rng.randrange(2**32)
+                    bits = [(x >> (31 - j)) & 1 for j in range(32)]
+                    row[2 * o] = x
+                    row[2 * o + 1] = sum(b << (2 * (31 - j)) for j, b in enumerate(bits))
+                    row[2 * p0 + 32 * o:2 * p0 + 32 * (o + 1)] = bits
+            elif kind in (GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32):
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                for o in range(p0):
+                    x = rng.randrange(2**63)
+                    bits = [(x >> (63 - j)) & 1 for j in range(64)]
+                    step = 1 if kind == GATE_UNINTERLEAVE_TO_U32 else 2
+                    ev = sum(bits[2 * j] << (step * (31 - j)) for j in range(32))
+                    od = sum(bits[2 * j + 1] << (step * (31 - j)) for j in range(32))
+                    row[3 * o:3 * o + 3] = [x, ev, od]
+                    row[3 * p0 + 64 * o:3 * p0 + 64 * (o + 1)] = bits
+            elif kind == GATE_COMPARISON:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                nb, nc = p0, p1
+                cb = -(-nb // nc)
+                a, b = rng.randrange(2**nb), rng.randrange(2**nb)
+                if i % 3 == 0:
+                    b = a  # equal inputs
+                elif i % 3 == 1:
+                    b = (a & ~0xFF) | (b & 0xFF)  # equal high chunks
+                fc = [(a >> (cb * k)) & ((1 << cb) - 1) for k in range(nc)]
+                sc = [(b >> (cb * k)) & ((1 << cb) - 1) for k in range(nc)]
+                msd = 0
+                row[0], row[1] = a, b
+                for k in range(nc):
+                    diff = (sc[k] - fc[k]) % P
+                    eq = 1 if diff == 0 else 0
+                    inter = eq * msd % P
+                    row[4 + k], row[4 + nc + k] = fc[k], sc[k]
+                    row[4 + 2 * nc + k] = 1 if eq else pow(diff, P - 2, P)
+                    row[4 + 3 * nc + k] = eq
+                    row[4 + 4 * nc + k] = inter
+                    msd = (inter + (1 - eq) * diff) % P
+                row[3] = msd
+                comb = ((1 << cb) + msd) % P
+                bits = [(comb >> k) & 1 for k in range(cb + 1)]
+                row[4 + 5 * nc:4 + 5 * nc + cb + 1] = bits
+                row[2] = bits[cb]
             for c in range(num_gate_consts):
                 consts[self.num_selectors + c][i] = gc[c]
             for c in range(num_wires):

@@ -13,6 +13,11 @@ P = R.P
 ALL_GATES = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0),
              (R.GATE_POSEIDON, 0, 0), (R.GATE_BASE_SUM, 63, 0), (R.GATE_U32_ARITHMETIC, 3, 0),
              (R.GATE_U32_ADD_MANY, 3, 5), (R.GATE_U32_SUBTRACTION, 6, 0), (R.GATE_U32_RANGE_CHECK, 7, 0)]
+# the in-tree bit-manipulation / comparison gates, with the parameters the reference registers
+# (city_common_circuit/src/builder/pad_circuit.rs:31-55: ComparisonGate::new(32, 16))
+MORE_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_U32_INTERLEAVE, 3, 0), (R.GATE_UNINTERLEAVE_TO_U32, 2, 0),
+              (R.GATE_UNINTERLEAVE_TO_B32, 2, 0), (R.GATE_COMPARISON, 32, 16), (R.GATE_POSEIDON, 0, 0)]
+MORE_GROUPS = [(0, 3), (3, 5), (5, 6)]
 
 
 def prove_plonk_part(circ, seed, rate_bits=3, cap_height=1):
@@ -57,6 +62,7 @@ def check_verifier_identity(circ, pr, seed):
     (4, ALL_GATES[:4], [(0, 4)], 1),
     (5, ALL_GATES[:5], [(0, 4), (4, 5)], 2),
     (6, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 3),
+    (5, MORE_GATES, MORE_GROUPS, 4),
 ])
 def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)
