@@ -154,14 +154,14 @@ def _check_batch(ctx, m, cols, rate_bits, cap_height, from_values, sample_only=F
 @pytest.mark.parametrize("log_n,n_cols,rate_bits,cap_height", [
     (0, 3, 3, 0), (1, 2, 3, 1), (2, 5, 3, 4), (3, 9, 1, 0), (5, 20, 3, 4), (8, 16, 3, 4), (10, 135, 3, 4),
     (12, 135, 3, 4), (12, 20, 3, 4), (12, 16, 3, 4), (12, 85, 3, 4), (12, 1, 0, 0), (13, 17, 3, 4),
-    (14, 20, 3, 4), (15, 8, 2, 4), (16, 4, 3, 4), (17, 2, 3, 4), (18, 2, 2, 4), (19, 1, 1, 4)])
+    (14, 20, 3, 4), (14, 37, 3, 4), (15, 8, 2, 4), (16, 4, 3, 4), (17, 2, 3, 4), (18, 2, 2, 4), (19, 1, 1, 4)])
 def test_batch_from_values(ctx, m, log_n, n_cols, rate_bits, cap_height):
     cols = [rand_felts(0x5EED0001 + c, 1 << log_n, canonical=(c % 3 != 0)) for c in range(n_cols)]
     _check_batch(ctx, m, cols, rate_bits, cap_height, True)
 
 
 @pytest.mark.parametrize("log_n,n_cols,rate_bits,cap_height", [
-    (4, 16, 3, 4), (12, 16, 3, 4), (13, 16, 3, 4), (16, 2, 3, 4)])
+    (4, 16, 3, 4), (12, 16, 3, 4), (13, 16, 3, 4), (14, 33, 2, 4), (16, 2, 3, 4)])
 def test_batch_from_coeffs(ctx, m, log_n, n_cols, rate_bits, cap_height):
     cols = [rand_felts(0xC0EFF + c, 1 << log_n, canonical=(c % 2 == 0)) for c in range(n_cols)]
     _check_batch(ctx, m, cols, rate_bits, cap_height, False)
