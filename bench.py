@@ -161,7 +161,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -373,14 +373,46 @@ def run_cuda(args):
         "gpu_launches": int(launches), "clocks": clocks, "m2_lde_merkle_2p20x135": m2,
         "m1_synthetic_proofs": m1,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+class StdoutGuard:
+    """Everything a library prints to fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr;
+    the one JSON line is written to the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+GUARD = None
+
+
+def emit(line):
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line)
+
+
 def main():
+    global GUARD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -391,9 +423,11 @@ def main():
     ap.add_argument("--no-m1", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_cuda(args)
+    with StdoutGuard() as g:
+        GUARD = g
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_cuda(args)
 
 
 if __name__ == "__main__":
