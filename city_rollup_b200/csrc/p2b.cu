@@ -1097,6 +1097,17 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
       case plonk::GATE_U32_INTERLEAVE: wires = 34 * gt.p0, cons = 34 * gt.p0; break;
       case plonk::GATE_UNINTERLEAVE_TO_U32:
       case plonk::GATE_UNINTERLEAVE_TO_B32: wires = 67 * gt.p0, cons = 67 * gt.p0; break;
+      case plonk::GATE_ARITHMETIC_EXT: wires = 8 * gt.p0, consts = 2, cons = 2 * gt.p0; break;
+      case plonk::GATE_MUL_EXT: wires = 6 * gt.p0, consts = 1, cons = 2 * gt.p0; break;
+      case plonk::GATE_REDUCING: wires = gt.p0 ? 6 + gt.p0 + 2 * (gt.p0 - 1) : 6, cons = 2 * gt.p0; break;
+      case plonk::GATE_REDUCING_EXT: wires = gt.p0 ? 6 + 2 * gt.p0 + 2 * (gt.p0 - 1) : 6, cons = 2 * gt.p0; break;
+      case plonk::GATE_RANDOM_ACCESS: {
+        const uint32_t copies = gt.p1 & 0xFFFF, extra = gt.p1 >> 16;
+        if (gt.p0 == 0 || gt.p0 > 6) return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: RandomAccessGate bits %u", g, gt.p0);
+        wires = (2 + (1u << gt.p0) + gt.p0) * copies + extra, consts = extra, cons = (gt.p0 + 2) * copies + extra;
+        break;
+      }
+      case plonk::GATE_POSEIDON_MDS: wires = 48, cons = 24; break;
       case plonk::GATE_COMPARISON: {
         if (gt.p1 == 0 || gt.p0 == 0 || (gt.p0 + gt.p1 - 1) / gt.p1 > 8)
           return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: ComparisonGate(%u, %u)", g, gt.p0, gt.p1);

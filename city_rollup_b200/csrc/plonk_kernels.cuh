@@ -7,7 +7,8 @@
 //   plonk/vanishing_poly.rs  eval_vanishing_poly_base_batch, evaluate_gate_constraints_base_batch
 //   plonk/plonk_common.rs    ZeroPolyOnCoset::{eval, eval_inverse, eval_l_0}, reduce_with_powers_multi
 //   gates/gate.rs            eval_filtered_base_batch / compute_filter
-//   gates/{noop,constant,public_input,arithmetic_base,base_sum,poseidon}.rs  eval_unfiltered_base_*
+//   gates/{noop,constant,public_input,arithmetic_base,base_sum,poseidon,arithmetic_extension,
+//          multiplication_extension,reducing,reducing_extension,random_access,poseidon_mds}.rs  eval_unfiltered_base_*
 // and the in-tree gates of the reference (scalar eval_unfiltered is the specification):
 //   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150, add_many_u32.rs:87-135,
 //   subtraction_u32.rs:82-125, range_check_u32.rs:51-75, interleave_u32.rs:86-127, uninterleave_to_u32.rs:93-136,
@@ -45,7 +46,13 @@ enum GateKind : uint32_t {
   GATE_UNINTERLEAVE_TO_U32 = 11,
   GATE_UNINTERLEAVE_TO_B32 = 12,
   GATE_COMPARISON = 13,
-  GATE_KIND_COUNT = 14
+  GATE_ARITHMETIC_EXT = 14,
+  GATE_MUL_EXT = 15,
+  GATE_REDUCING = 16,
+  GATE_REDUCING_EXT = 17,
+  GATE_RANDOM_ACCESS = 18,
+  GATE_POSEIDON_MDS = 19,
+  GATE_KIND_COUNT = 20
 };
 
 struct Gate {  // mirrors p2b_gate (include/p2b.h)
@@ -147,6 +154,12 @@ struct Acc {
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
       if (ch < (int)n_chal) a[ch] = fadd(a[ch], fmul(c, apow[ch * stride + q]));
     q++;
+  }
+  // constraint number q + k of the gate, without advancing
+  __device__ __forceinline__ void push_at(uint32_t k, uint64_t c) {
+#pragma unroll
+    for (int ch = 0; ch < MAX_CHALLENGES; ch++)
+      if (ch < (int)n_chal) a[ch] = fadd(a[ch], fmul(c, apow[ch * stride + q + k]));
   }
 };
 
@@ -423,6 +436,78 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
       for (uint32_t b = cb + 1; b-- > 0;) comb = fadd(fadd(comb, comb), v.w(4 + 5 * nc + b));
       acc.push(fsub(fadd(1ull << cb, msd_w), comb));
       acc.push(fsub(v.w(2), v.w(4 + 5 * nc + cb)));
+      break;
+    }
+    case GATE_ARITHMETIC_EXT:
+    case GATE_MUL_EXT: {  // extension elements in wire pairs; output - (m0 m1 c0 [+ addend c1]) per component
+      const bool arith = g.kind == GATE_ARITHMETIC_EXT;
+      const uint32_t per = arith ? 8 : 6;
+      const uint64_t c0 = v.c(0), c1 = arith ? v.c(1) : 0;
+      for (uint32_t i = 0; i < g.p0; i++) {
+        const uint32_t q = per * i;
+        const gl::ext2 prod = gl::ext_mul(gl::ext2{v.w(q), v.w(q + 1)}, gl::ext2{v.w(q + 2), v.w(q + 3)});
+        uint64_t r0 = fmul(prod.c0, c0), r1 = fmul(prod.c1, c0);
+        if (arith) r0 = fadd(r0, fmul(v.w(q + 4), c1)), r1 = fadd(r1, fmul(v.w(q + 5), c1));
+        acc.push(fsub(v.w(q + per - 2), r0));
+        acc.push(fsub(v.w(q + per - 1), r1));
+      }
+      break;
+    }
+    case GATE_REDUCING:
+    case GATE_REDUCING_EXT: {  // output 0..2, alpha 2..4, old_acc 4..6, coefficients from 6, accumulators after them
+      const uint32_t n = g.p0;
+      const bool ext = g.kind == GATE_REDUCING_EXT;
+      const uint32_t start_accs = 6 + (ext ? 2 * n : n);
+      const gl::ext2 alpha{v.w(2), v.w(3)};
+      gl::ext2 a{v.w(4), v.w(5)};
+      for (uint32_t i = 0; i < n; i++) {
+        const gl::ext2 t = gl::ext_mul(a, alpha);
+        const uint32_t nx = i == n - 1 ? 0 : start_accs + 2 * i;
+        const gl::ext2 nxt{v.w(nx), v.w(nx + 1)};
+        const uint64_t k0 = ext ? v.w(6 + 2 * i) : v.w(6 + i), k1 = ext ? v.w(7 + 2 * i) : 0;
+        acc.push(fsub(fadd(t.c0, k0), nxt.c0));
+        acc.push(fsub(fadd(t.c1, k1), nxt.c1));
+        a = nxt;
+      }
+      break;
+    }
+    case GATE_RANDOM_ACCESS: {  // p0 = bits (<= 6), p1 = num_copies | num_extra_constants << 16
+      const uint32_t bits = g.p0, copies = g.p1 & 0xFFFF, extra = g.p1 >> 16, vec = 1u << bits;
+      const uint32_t routed = (2 + vec) * copies + extra;
+      for (uint32_t cp = 0; cp < copies; cp++) {
+        const uint32_t q = (2 + vec) * cp, bq = routed + cp * bits;
+        uint64_t rec = 0, items[64];
+        for (uint32_t t = 0; t < bits; t++) {
+          const uint64_t b = v.w(bq + t);
+          acc.push(fmul(b, fsub(b, 1)));
+        }
+        for (uint32_t t = bits; t-- > 0;) rec = fadd(fadd(rec, rec), v.w(bq + t));
+        acc.push(fsub(rec, v.w(q)));
+        for (uint32_t t = 0; t < vec; t++) items[t] = v.w(q + 2 + t);
+        uint32_t len = vec;
+        for (uint32_t t = 0; t < bits; t++) {
+          const uint64_t b = v.w(bq + t);
+          len >>= 1;
+          for (uint32_t u = 0; u < len; u++) items[u] = fadd(items[2 * u], fmul(b, fsub(items[2 * u + 1], items[2 * u])));
+        }
+        acc.push(fsub(items[0], v.w(q + 1)));
+      }
+      for (uint32_t t = 0; t < extra; t++) acc.push(fsub(v.c(t), v.w((2 + vec) * copies + t)));
+      break;
+    }
+    case GATE_POSEIDON_MDS: {  // the MDS layer on 12 extension elements, componentwise
+      for (int t = 0; t < 2; t++) {
+        uint64_t s[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = v.w(2 * i + t);
+        mds_plain(s);
+        // constraints are ordered (row, component): remember the accumulator slot of each
+        for (int r = 0; r < 12; r++) {
+          const uint64_t cst = fsub(s[r], v.w(24 + 2 * r + t));
+          acc.push_at(2 * r + t, cst);
+        }
+      }
+      acc.q += 24;
       break;
     }
     default:

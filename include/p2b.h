@@ -143,7 +143,13 @@ typedef enum {
   P2B_GATE_U32_INTERLEAVE = 10, /* .../interleave_u32.rs { num_ops = p0 } */
   P2B_GATE_UNINTERLEAVE_TO_U32 = 11, /* .../uninterleave_to_u32.rs { num_ops = p0 } */
   P2B_GATE_UNINTERLEAVE_TO_B32 = 12, /* .../uninterleave_to_b32.rs { num_ops = p0 } */
-  P2B_GATE_COMPARISON = 13      /* .../comparison.rs { num_bits = p0, num_chunks = p1 } ((32, 16) in pad_circuit.rs:33) */
+  P2B_GATE_COMPARISON = 13,     /* .../comparison.rs { num_bits = p0, num_chunks = p1 } ((32, 16) in pad_circuit.rs:33) */
+  P2B_GATE_ARITHMETIC_EXT = 14, /* plonky2 ArithmeticExtensionGate { num_ops = p0 } */
+  P2B_GATE_MUL_EXT = 15,        /* MulExtensionGate { num_ops = p0 } */
+  P2B_GATE_REDUCING = 16,       /* ReducingGate { num_coeffs = p0 } (43 in pad_circuit.rs) */
+  P2B_GATE_REDUCING_EXT = 17,   /* ReducingExtensionGate { num_coeffs = p0 } (32) */
+  P2B_GATE_RANDOM_ACCESS = 18,  /* RandomAccessGate { bits = p0, num_copies = p1 & 0xFFFF, num_extra_constants = p1 >> 16 } */
+  P2B_GATE_POSEIDON_MDS = 19    /* PoseidonMdsGate */
 } p2b_gate_kind;
 typedef struct {
   uint32_t kind, p0, p1;

@@ -130,7 +130,13 @@ enum {
   P2O_GATE_U32_INTERLEAVE = 10, /* p0 = num_ops */
   P2O_GATE_UNINTERLEAVE_TO_U32 = 11, /* p0 = num_ops */
   P2O_GATE_UNINTERLEAVE_TO_B32 = 12, /* p0 = num_ops */
-  P2O_GATE_COMPARISON = 13      /* p0 = num_bits, p1 = num_chunks */
+  P2O_GATE_COMPARISON = 13,     /* p0 = num_bits, p1 = num_chunks */
+  P2O_GATE_ARITHMETIC_EXT = 14, /* p0 = num_ops */
+  P2O_GATE_MUL_EXT = 15,        /* p0 = num_ops */
+  P2O_GATE_REDUCING = 16,       /* p0 = num_coeffs */
+  P2O_GATE_REDUCING_EXT = 17,   /* p0 = num_coeffs */
+  P2O_GATE_RANDOM_ACCESS = 18,  /* p0 = bits, p1 = num_copies | num_extra_constants << 16 */
+  P2O_GATE_POSEIDON_MDS = 19
 };
 typedef struct {
   uint32_t kind, p0, p1;

@@ -316,6 +316,8 @@ def merkle_find_index(leaf, siblings, cap):
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM = range(6)
 GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK = 6, 7, 8, 9
 GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON = 10, 11, 12, 13
+(GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_REDUCING, GATE_REDUCING_EXT, GATE_RANDOM_ACCESS,
+ GATE_POSEIDON_MDS) = range(14, 20)
 
 
 class GateStruct(C.Structure):

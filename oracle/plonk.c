@@ -7,6 +7,8 @@
  *   plonk/plonk_common.rs    ZeroPolyOnCoset, reduce_with_powers_multi, check_partial_products
  *   gates/gate.rs        eval_filtered_base_batch / compute_filter (selector groups, UNUSED_SELECTOR)
  *   gates/{noop,constant,public_input,arithmetic_base,poseidon,base_sum}.rs   eval_unfiltered_base_one
+ *   gates/{arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,
+ *          poseidon_mds}.rs                                                    eval_unfiltered_base_one
  * and, for the gates that live in the reference tree itself, the reference's scalar eval_unfiltered:
  *   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150  (U32ArithmeticGate)
  *   city_common_circuit/src/u32/gates/add_many_u32.rs:87-135    (U32AddManyGate)
@@ -120,6 +122,14 @@ static void mds_layer(uint64_t s[12]) {
     o[r] = acc;
   }
   memcpy(s, o, sizeof o);
+}
+
+/* extension elements held in two wires: (a0 + a1 X)(b0 + b1 X), X^2 = 7 */
+static inline void e2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t o[2]) {
+  uint64_t c0 = gli_add(gli_mul(a[0], b[0]), gli_mul(7, gli_mul(a[1], b[1])));
+  uint64_t c1 = gli_add(gli_mul(a[0], b[1]), gli_mul(a[1], b[0]));
+  o[0] = c0;
+  o[1] = c1;
 }
 
 /* returns the number of constraints written to `out` */
@@ -361,6 +371,71 @@ static unsigned eval_gate(const p2o_gate *g, const gate_vars *v, uint64_t *out) 
       for (unsigned b = cb + 1; b-- > 0;) comb = gli_add(gli_mul(comb, 2), bits[b]);
       out[k++] = gli_sub(gli_add(1ull << cb, w[3]), comb);
       out[k++] = gli_sub(w[2], bits[cb]);
+      return k;
+    }
+    case P2O_GATE_ARITHMETIC_EXT:
+    case P2O_GATE_MUL_EXT: { /* p0 = num_ops; output - (m0 * m1 * c0 [+ addend * c1]) componentwise */
+      const int arith = g->kind == P2O_GATE_ARITHMETIC_EXT;
+      const unsigned per = arith ? 8 : 6;
+      for (unsigned i = 0; i < g->p0; i++) {
+        const uint64_t *q = w + per * i;
+        uint64_t prod[2];
+        e2_mul(q, q + 2, prod);
+        for (int t = 0; t < 2; t++) {
+          uint64_t computed = gli_mul(prod[t], v->consts[0]);
+          if (arith) computed = gli_add(computed, gli_mul(q[4 + t], v->consts[1]));
+          out[k++] = gli_sub(q[per - 2 + t], computed);
+        }
+      }
+      return k;
+    }
+    case P2O_GATE_REDUCING:
+    case P2O_GATE_REDUCING_EXT: { /* p0 = num_coeffs; output 0..2, alpha 2..4, old_acc 4..6, coeffs from 6 */
+      const unsigned n = g->p0;
+      const int ext = g->kind == P2O_GATE_REDUCING_EXT;
+      const unsigned start_accs = 6 + (ext ? 2 * n : n);
+      uint64_t acc[2] = {w[4], w[5]};
+      for (unsigned i = 0; i < n; i++) {
+        uint64_t t[2];
+        e2_mul(acc, w + 2, t);
+        const uint64_t *nxt = i == n - 1 ? w : w + start_accs + 2 * i;
+        uint64_t c0 = ext ? w[6 + 2 * i] : w[6 + i], c1 = ext ? w[7 + 2 * i] : 0;
+        out[k++] = gli_sub(gli_add(t[0], c0), nxt[0]);
+        out[k++] = gli_sub(gli_add(t[1], c1), nxt[1]);
+        acc[0] = nxt[0];
+        acc[1] = nxt[1];
+      }
+      return k;
+    }
+    case P2O_GATE_RANDOM_ACCESS: { /* p0 = bits, p1 = num_copies | num_extra_constants << 16 */
+      const unsigned bits = g->p0, copies = g->p1 & 0xFFFF, extra = g->p1 >> 16, vec = 1u << bits;
+      const unsigned routed = (2 + vec) * copies + extra;
+      for (unsigned cp = 0; cp < copies; cp++) {
+        const uint64_t *q = w + (2 + vec) * cp, *b = w + routed + cp * bits;
+        uint64_t rec = 0, items[64];
+        for (unsigned t = 0; t < bits; t++) out[k++] = gli_mul(b[t], gli_sub(b[t], 1));
+        for (unsigned t = bits; t-- > 0;) rec = gli_add(gli_add(rec, rec), b[t]);
+        out[k++] = gli_sub(rec, q[0]);
+        for (unsigned t = 0; t < vec; t++) items[t] = q[2 + t];
+        unsigned len = vec;
+        for (unsigned t = 0; t < bits; t++) {
+          len >>= 1;
+          for (unsigned u = 0; u < len; u++)
+            items[u] = gli_add(items[2 * u], gli_mul(b[t], gli_sub(items[2 * u + 1], items[2 * u])));
+        }
+        out[k++] = gli_sub(items[0], q[1]);
+      }
+      for (unsigned t = 0; t < extra; t++) out[k++] = gli_sub(v->consts[t], w[(2 + vec) * copies + t]);
+      return k;
+    }
+    case P2O_GATE_POSEIDON_MDS: { /* inputs 12 x 2 wires, outputs 12 x 2 wires: the MDS layer componentwise */
+      for (int r = 0; r < 12; r++)
+        for (int t = 0; t < 2; t++) {
+          uint64_t acc = 0;
+          for (int i = 0; i < 12; i++) acc = gli_add(acc, gli_mul(w[2 * ((i + r) % 12) + t], MDS_CIRC[i]));
+          if (r == 0) acc = gli_add(acc, gli_mul(w[t], 8));
+          out[k++] = gli_sub(acc, w[24 + 2 * r + t]);
+        }
       return k;
     }
     default:

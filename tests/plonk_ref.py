@@ -25,7 +25,8 @@ _spec.loader.exec_module(PF)  # derives FIRST / POST / INIT / W_HATS / VS from M
 
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM, GATE_U32_ARITHMETIC,
  GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK, GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32,
- GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON) = range(14)
+ GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON, GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_REDUCING, GATE_REDUCING_EXT,
+ GATE_RANDOM_ACCESS, GATE_POSEIDON_MDS) = range(20)
 UNUSED_SELECTOR = 2**32 - 1
 
 
@@ -109,6 +110,34 @@ class Fp:
 
     def __eq__(self, o):
         return self.a == Fp.of(o).a
+
+
+class Alg:
+    """ExtensionAlgebra element c0 + c1 Y, Y^2 = 7, over any field-like component type (plonky2
+    field/extension/algebra.rs): how a D = 2 extension element stored in two wires is multiplied both by the
+    prover (components in F) and by the verifier (components in F_ext)."""
+    __slots__ = ("c0", "c1")
+
+    def __init__(self, c0, c1):
+        self.c0, self.c1 = c0, c1
+
+    def __add__(self, o):
+        return Alg(self.c0 + o.c0, self.c1 + o.c1)
+
+    def __sub__(self, o):
+        return Alg(self.c0 - o.c0, self.c1 - o.c1)
+
+    def __mul__(self, o):
+        if isinstance(o, Alg):
+            return Alg(self.c0 * o.c0 + self.c1 * o.c1 * W, self.c0 * o.c1 + self.c1 * o.c0)
+        return Alg(self.c0 * o, self.c1 * o)  # scalar_mul
+
+    def parts(self):
+        return [self.c0, self.c1]
+
+
+def _ext_at(w, start):
+    return Alg(w[start], w[start + 1])
 
 
 # ------------------------------------------------------------------------------------------ gates (scalar form)
@@ -328,6 +357,51 @@ def eval_gate(kind, p0, p1, w, consts, pi_hash):
             comb = comb * 2 + b
         c.append(w[3] + (1 << cb) - comb)
         c.append(w[2] - bits[cb])
+    elif kind == GATE_ARITHMETIC_EXT:  # gates/arithmetic_extension.rs; 4 D wires per op
+        for i in range(p0):
+            m0, m1, ad, out = (_ext_at(w, 8 * i + 2 * k) for k in range(4))
+            c.extend((out - (m0 * m1 * consts[0] + ad * consts[1])).parts())
+    elif kind == GATE_MUL_EXT:  # gates/multiplication_extension.rs; 3 D wires per op
+        for i in range(p0):
+            m0, m1, out = (_ext_at(w, 6 * i + 2 * k) for k in range(3))
+            c.extend((out - m0 * m1 * consts[0]).parts())
+    elif kind in (GATE_REDUCING, GATE_REDUCING_EXT):  # gates/reducing.rs, reducing_extension.rs
+        n = p0
+        ext = kind == GATE_REDUCING_EXT
+        alpha, acc = _ext_at(w, 2), _ext_at(w, 4)
+        start_accs = 6 + (2 * n if ext else n)
+        for i in range(n):
+            coeff = _ext_at(w, 6 + 2 * i) if ext else Alg(w[6 + i], w[0] * 0)
+            nxt = _ext_at(w, 0) if i == n - 1 else _ext_at(w, start_accs + 2 * i)
+            c.extend((acc * alpha + coeff - nxt).parts())
+            acc = nxt
+    elif kind == GATE_RANDOM_ACCESS:  # gates/random_access.rs; p0 = bits, p1 = num_copies | num_extra_constants << 16
+        bits, copies, extra = p0, p1 & 0xFFFF, p1 >> 16
+        vec = 1 << bits
+        routed = (2 + vec) * copies + extra
+        for cp in range(copies):
+            base = (2 + vec) * cp
+            b = [w[routed + cp * bits + k] for k in range(bits)]
+            for x in b:
+                c.append(x * (x - 1))
+            rec = w[0] * 0
+            for x in reversed(b):
+                rec = rec * 2 + x
+            c.append(rec - w[base])
+            items = [w[base + 2 + k] for k in range(vec)]
+            for x in b:
+                items = [items[2 * k] + x * (items[2 * k + 1] - items[2 * k]) for k in range(len(items) // 2)]
+            c.append(items[0] - w[base + 1])
+        for k in range(extra):
+            c.append(consts[k] - w[(2 + vec) * copies + k])
+    elif kind == GATE_POSEIDON_MDS:  # gates/poseidon_mds.rs; inputs 12 x D, outputs 12 x D
+        ins = [_ext_at(w, 2 * i) for i in range(12)]
+        for r in range(12):
+            acc = ins[r] * 0
+            for i in range(12):
+                acc = acc + ins[(i + r) % 12] * PF.CIRC[i]
+            acc = acc + ins[r] * PF.DIAG[r]
+            c.extend((acc - _ext_at(w, 24 + 2 * r)).parts())
     else:
         raise ValueError(kind)
     return c
@@ -337,7 +411,10 @@ def gate_degree(kind):
     return {GATE_NOOP: 0, GATE_CONSTANT: 1, GATE_PUBLIC_INPUT: 1, GATE_ARITHMETIC: 3, GATE_POSEIDON: 7,
             GATE_BASE_SUM: 2, GATE_U32_ARITHMETIC: 4, GATE_U32_ADD_MANY: 4, GATE_U32_SUBTRACTION: 4,
             GATE_U32_RANGE_CHECK: 4, GATE_U32_INTERLEAVE: 2, GATE_UNINTERLEAVE_TO_U32: 2, GATE_UNINTERLEAVE_TO_B32: 2,
-            GATE_COMPARISON: 4}[kind]  # ComparisonGate: 2^chunk_bits with chunk_bits = 2
+            GATE_COMPARISON: 4,  # ComparisonGate: 2^chunk_bits with chunk_bits = 2
+            GATE_ARITHMETIC_EXT: 3, GATE_MUL_EXT: 3, GATE_REDUCING: 2, GATE_REDUCING_EXT: 2,
+            GATE_RANDOM_ACCESS: 5,  # bits + 1 with bits = 4
+            GATE_POSEIDON_MDS: 1}[kind]
 
 
 def gate_num_constraints(kind, p0, p1):
@@ -345,7 +422,9 @@ def gate_num_constraints(kind, p0, p1):
             GATE_BASE_SUM: 1 + p0, GATE_U32_ARITHMETIC: p0 * 36, GATE_U32_ADD_MANY: p1 * 21,
             GATE_U32_SUBTRACTION: p0 * 19, GATE_U32_RANGE_CHECK: p0 * 17, GATE_U32_INTERLEAVE: p0 * 34,
             GATE_UNINTERLEAVE_TO_U32: p0 * 67, GATE_UNINTERLEAVE_TO_B32: p0 * 67,
-            GATE_COMPARISON: 6 + 5 * p1 + -(-p0 // max(p1, 1))}[kind]
+            GATE_COMPARISON: 6 + 5 * p1 + -(-p0 // max(p1, 1)), GATE_ARITHMETIC_EXT: 2 * p0, GATE_MUL_EXT: 2 * p0,
+            GATE_REDUCING: 2 * p0, GATE_REDUCING_EXT: 2 * p0,
+            GATE_RANDOM_ACCESS: (p0 + 2) * (p1 & 0xFFFF) + (p1 >> 16), GATE_POSEIDON_MDS: 24}[kind]
 
 
 # ------------------------------------------------------------------------------------------ witness generation
@@ -542,6 +621,44 @@ class SyntheticCircuit:
                 bits = [(comb >> k) & 1 for k in range(cb + 1)]
                 row[4 + 5 * nc:4 + 5 * nc + cb + 1] = bits
                 row[2] = bits[cb]
+            elif kind in (GATE_ARITHMETIC_EXT, GATE_MUL_EXT):
+                per = 8 if kind == GATE_ARITHMETIC_EXT else 6
+                row = [pick(i, c) if c < per * p0 and c % per < per - 2 else rng.randrange(P) for c in range(num_wires)]
+                for o in range(p0):
+                    m0, m1 = Ext(row[per * o], row[per * o + 1]), Ext(row[per * o + 2], row[per * o + 3])
+                    out = m0 * m1 * gc[0]
+                    if kind == GATE_ARITHMETIC_EXT:
+                        out = out + Ext(row[per * o + 4], row[per * o + 5]) * gc[1]
+                    row[per * o + per - 2], row[per * o + per - 1] = out.a, out.b
+            elif kind in (GATE_REDUCING, GATE_REDUCING_EXT):
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                ext = kind == GATE_REDUCING_EXT
+                alpha, acc = Ext(row[2], row[3]), Ext(row[4], row[5])
+                start_accs = 6 + (2 * p0 if ext else p0)
+                for k in range(p0):
+                    coeff = Ext(row[6 + 2 * k], row[7 + 2 * k]) if ext else Ext(row[6 + k])
+                    acc = acc * alpha + coeff
+                    pos = 0 if k == p0 - 1 else start_accs + 2 * k
+                    row[pos], row[pos + 1] = acc.a, acc.b
+            elif kind == GATE_RANDOM_ACCESS:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                bits, copies, extra = p0, p1 & 0xFFFF, p1 >> 16
+                vec = 1 << bits
+                routed = (2 + vec) * copies + extra
+                for cp in range(copies):
+                    base = (2 + vec) * cp
+                    idx = rng.randrange(vec)
+                    row[base] = idx
+                    row[base + 1] = row[base + 2 + idx]
+                    row[routed + cp * bits:routed + (cp + 1) * bits] = [(idx >> k) & 1 for k in range(bits)]
+                for k in range(extra):
+                    row[(2 + vec) * copies + k] = gc[k]
+            elif kind == GATE_POSEIDON_MDS:
+                row = [pick(i, c) if c < 24 else rng.randrange(P) for c in range(num_wires)]
+                for part in range(2):
+                    v = PF.matvec(PF.M, [row[2 * k + part] for k in range(12)])
+                    for r in range(12):
+                        row[24 + 2 * r + part] = v[r]
             for c in range(num_gate_consts):
                 consts[self.num_selectors + c][i] = gc[c]
             for c in range(num_wires):

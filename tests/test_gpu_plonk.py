@@ -11,7 +11,8 @@ import pytest
 
 import p2oracle as O
 import plonk_ref as R
-from test_plonk_oracle import ALL_GATES, MORE_GATES, MORE_GROUPS, check_verifier_identity
+from test_plonk_oracle import (ALL_GATES, EXT_GATES, EXT_GROUPS, MORE_GATES, MORE_GROUPS,
+                               check_verifier_identity)
 
 pytestmark = pytest.mark.gpu
 P = R.P
@@ -48,6 +49,7 @@ def run_gpu(ctx, m, circ, betas, gammas, alphas, rate_bits, cap_height):
     (6, ALL_GATES, FULL_GROUPS, 23, 4),
     (9, ALL_GATES, FULL_GROUPS, 24, 4),
     (7, MORE_GATES, MORE_GROUPS, 26, 3),
+    (7, EXT_GATES, EXT_GROUPS, 27, 4),
     (12, ALL_GATES, FULL_GROUPS, 25, 4),
 ])
 def test_plonk_stages_match_oracle(ctx, m, degree_bits, gates, groups, seed, cap_height):

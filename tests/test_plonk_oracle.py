@@ -18,6 +18,11 @@ ALL_GATES = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT,
 MORE_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_U32_INTERLEAVE, 3, 0), (R.GATE_UNINTERLEAVE_TO_U32, 2, 0),
               (R.GATE_UNINTERLEAVE_TO_B32, 2, 0), (R.GATE_COMPARISON, 32, 16), (R.GATE_POSEIDON, 0, 0)]
 MORE_GROUPS = [(0, 3), (3, 5), (5, 6)]
+# upstream extension-field gates of the recursion gate set, with the parameters standard_recursion_config gives
+# them (ReducingGate(43) / ReducingExtensionGate(32) / RandomAccessGate(bits 4): builder/pad_circuit.rs:31-55)
+EXT_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_ARITHMETIC_EXT, 10, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_REDUCING, 43, 0),
+             (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_POSEIDON_MDS, 0, 0)]
+EXT_GROUPS = [(0, 3), (3, 6), (6, 7)]
 
 
 def prove_plonk_part(circ, seed, rate_bits=3, cap_height=1):
@@ -63,6 +68,7 @@ def check_verifier_identity(circ, pr, seed):
     (5, ALL_GATES[:5], [(0, 4), (4, 5)], 2),
     (6, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 3),
     (5, MORE_GATES, MORE_GROUPS, 4),
+    (5, EXT_GATES, EXT_GROUPS, 5),
 ])
 def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)
