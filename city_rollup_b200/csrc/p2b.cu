@@ -1108,6 +1108,13 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
         break;
       }
       case plonk::GATE_POSEIDON_MDS: wires = 48, cons = 24; break;
+      case plonk::GATE_COSET_INTERPOLATION: {
+        if (gt.p0 == 0 || gt.p0 > 6 || gt.p1 < 2 || gt.p1 > (1u << gt.p0))
+          return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: CosetInterpolationGate(%u, degree %u)", g, gt.p0, gt.p1);
+        const uint32_t np = 1u << gt.p0, n_int = (np - 2) / (gt.p1 - 1);
+        wires = 1 + 2 * np + 4 + 2 * (2 * n_int + 1), cons = 4 + 4 * n_int;
+        break;
+      }
       case plonk::GATE_COMPARISON: {
         if (gt.p1 == 0 || gt.p0 == 0 || (gt.p0 + gt.p1 - 1) / gt.p1 > 8)
           return fail(ctx, P2B_ERR_UNSUPPORTED, "gate %u: ComparisonGate(%u, %u)", g, gt.p0, gt.p1);

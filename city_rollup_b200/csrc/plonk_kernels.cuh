@@ -8,7 +8,8 @@
 //   plonk/plonk_common.rs    ZeroPolyOnCoset::{eval, eval_inverse, eval_l_0}, reduce_with_powers_multi
 //   gates/gate.rs            eval_filtered_base_batch / compute_filter
 //   gates/{noop,constant,public_input,arithmetic_base,base_sum,poseidon,arithmetic_extension,
-//          multiplication_extension,reducing,reducing_extension,random_access,poseidon_mds}.rs  eval_unfiltered_base_*
+//          multiplication_extension,reducing,reducing_extension,random_access,poseidon_mds,
+//          coset_interpolation}.rs  eval_unfiltered_base_*
 // and the in-tree gates of the reference (scalar eval_unfiltered is the specification):
 //   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150, add_many_u32.rs:87-135,
 //   subtraction_u32.rs:82-125, range_check_u32.rs:51-75, interleave_u32.rs:86-127, uninterleave_to_u32.rs:93-136,
@@ -52,7 +53,8 @@ enum GateKind : uint32_t {
   GATE_REDUCING_EXT = 17,
   GATE_RANDOM_ACCESS = 18,
   GATE_POSEIDON_MDS = 19,
-  GATE_KIND_COUNT = 20
+  GATE_COSET_INTERPOLATION = 20,
+  GATE_KIND_COUNT = 21
 };
 
 struct Gate {  // mirrors p2b_gate (include/p2b.h)
@@ -168,6 +170,7 @@ struct Vars {
   size_t N;
   const uint64_t* consts;  // ditto, already past the selector columns
   const uint64_t* pi_hash;
+  ntt2::RootTables roots;
   __device__ __forceinline__ uint64_t w(uint32_t j) const { return wires[(size_t)j * N]; }
   __device__ __forceinline__ uint64_t c(uint32_t j) const { return consts[(size_t)j * N]; }
 };
@@ -510,6 +513,40 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
       acc.q += 24;
       break;
     }
+    case GATE_COSET_INTERPOLATION: {  // p0 = subgroup_bits, p1 = degree; barycentric weights of the subgroup = x_i / n
+      const uint32_t n = 1u << g.p0, degree = g.p1, n_int = (n - 2) / (degree - 1);
+      const uint32_t pt = 1 + 2 * n, val = pt + 2, ie0 = pt + 4, ip0 = ie0 + 2 * n_int, sh = ie0 + 4 * n_int;
+      const uint64_t gen = ntt2::root_pow(v.roots, g.p0, 1), ninv = GL_P - ((GL_P - 1) >> g.p0);
+      const uint64_t shift = v.w(0);
+      const gl::ext2 z{v.w(sh), v.w(sh + 1)};
+      acc.push(fsub(v.w(pt), fmul(z.c0, shift)));
+      acc.push(fsub(v.w(pt + 1), fmul(z.c1, shift)));
+      gl::ext2 ev{0, 0}, pr{1, 0};
+      uint64_t x = 1;
+      uint32_t i = 0, hi = degree;
+      for (uint32_t c = 0; c <= n_int; c++) {
+        for (; i < hi && i < n; i++) {  // partial_interpolate
+          const gl::ext2 term{fsub(z.c0, x), z.c1};
+          const uint64_t wt = fmul(x, ninv);
+          const gl::ext2 wv{fmul(v.w(1 + 2 * i), wt), fmul(v.w(2 + 2 * i), wt)};
+          ev = gl::ext_add(gl::ext_mul(ev, term), gl::ext_mul(wv, pr));
+          pr = gl::ext_mul(pr, term);
+          x = fmul(x, gen);
+        }
+        if (c == n_int) break;
+        const gl::ext2 ie{v.w(ie0 + 2 * c), v.w(ie0 + 2 * c + 1)}, ip{v.w(ip0 + 2 * c), v.w(ip0 + 2 * c + 1)};
+        acc.push(fsub(ie.c0, ev.c0));
+        acc.push(fsub(ie.c1, ev.c1));
+        acc.push(fsub(ip.c0, pr.c0));
+        acc.push(fsub(ip.c1, pr.c1));
+        ev = ie;
+        pr = ip;
+        hi = 1 + (degree - 1) * (c + 1) + degree - 1;  // the next chunk starts where this one ended
+      }
+      acc.push(fsub(v.w(val), ev.c0));
+      acc.push(fsub(v.w(val + 1), ev.c1));
+      break;
+    }
     default:
       break;
   }
@@ -578,7 +615,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
     }
   }
   // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
-  Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash};
+  Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
   const uint32_t gate_base = nch * (npp + 2);
   for (uint32_t g = 0; g < P.n_gates; g++) {
     const Gate gate = P.gates[g];

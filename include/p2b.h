@@ -149,7 +149,8 @@ typedef enum {
   P2B_GATE_REDUCING = 16,       /* ReducingGate { num_coeffs = p0 } (43 in pad_circuit.rs) */
   P2B_GATE_REDUCING_EXT = 17,   /* ReducingExtensionGate { num_coeffs = p0 } (32) */
   P2B_GATE_RANDOM_ACCESS = 18,  /* RandomAccessGate { bits = p0, num_copies = p1 & 0xFFFF, num_extra_constants = p1 >> 16 } */
-  P2B_GATE_POSEIDON_MDS = 19    /* PoseidonMdsGate */
+  P2B_GATE_POSEIDON_MDS = 19,   /* PoseidonMdsGate */
+  P2B_GATE_COSET_INTERPOLATION = 20 /* CosetInterpolationGate { subgroup_bits = p0, degree = p1 } (with_max_degree(4, 8): degree 6) */
 } p2b_gate_kind;
 typedef struct {
   uint32_t kind, p0, p1;

@@ -136,7 +136,8 @@ enum {
   P2O_GATE_REDUCING = 16,       /* p0 = num_coeffs */
   P2O_GATE_REDUCING_EXT = 17,   /* p0 = num_coeffs */
   P2O_GATE_RANDOM_ACCESS = 18,  /* p0 = bits, p1 = num_copies | num_extra_constants << 16 */
-  P2O_GATE_POSEIDON_MDS = 19
+  P2O_GATE_POSEIDON_MDS = 19,
+  P2O_GATE_COSET_INTERPOLATION = 20 /* p0 = subgroup_bits, p1 = degree */
 };
 typedef struct {
   uint32_t kind, p0, p1;
@@ -152,6 +153,9 @@ typedef struct {
   const p2o_gate *gates;
   const uint64_t *k_is; /* num_routed_wires */
 } p2o_circuit;
+/* unfiltered constraints of one gate at one point: wires / consts (after the selectors) / pi_hash canonical */
+unsigned plonk_eval_gate(const p2o_gate *g, const uint64_t *wires, const uint64_t *consts, const uint64_t *pi_hash,
+                         uint64_t *out);
 /* wires: num_wires x n, sigmas: num_routed_wires x n (values on H, column-major).
  * out: num_challenges * (1 + num_partial_products) columns x n: [Z_0.., partial products of challenge 0, ...] */
 void plonk_partial_products_and_zs(const p2o_circuit *c, const uint64_t *wires, const uint64_t *sigmas,

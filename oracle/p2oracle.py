@@ -318,6 +318,7 @@ GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHE
 GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON = 10, 11, 12, 13
 (GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_REDUCING, GATE_REDUCING_EXT, GATE_RANDOM_ACCESS,
  GATE_POSEIDON_MDS) = range(14, 20)
+GATE_COSET_INTERPOLATION = 20
 
 
 class GateStruct(C.Structure):
@@ -366,3 +367,12 @@ def compute_quotient_polys(desc, rate_bits, cs_leaves, wires_leaves, zs_leaves, 
                                        _p(arr(zs_leaves)), _p(arr(pi_hash)), _p(arr(betas)), _p(arr(gammas)),
                                        _p(arr(alphas)), _p(out))
     return out
+
+
+def eval_gate(kind, p0, p1, wires, consts, pi_hash, max_constraints=256):
+    """unfiltered constraints of one gate on one row of (canonical) values"""
+    g = GateStruct(kind, p0, p1, 0, 0, 1, 0)
+    out = np.zeros(max_constraints, np.uint64)
+    lib().plonk_eval_gate.restype = C.c_uint
+    k = lib().plonk_eval_gate(C.byref(g), _p(arr(wires)), _p(arr(consts)), _p(arr(pi_hash)), _p(out))
+    return [int(x) for x in out[:k]]

@@ -8,7 +8,7 @@
  *   gates/gate.rs        eval_filtered_base_batch / compute_filter (selector groups, UNUSED_SELECTOR)
  *   gates/{noop,constant,public_input,arithmetic_base,poseidon,base_sum}.rs   eval_unfiltered_base_one
  *   gates/{arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,
- *          poseidon_mds}.rs                                                    eval_unfiltered_base_one
+ *          poseidon_mds,coset_interpolation}.rs                                eval_unfiltered_base_one
  * and, for the gates that live in the reference tree itself, the reference's scalar eval_unfiltered:
  *   city_common_circuit/src/u32/gates/arithmetic_u32.rs:88-150  (U32ArithmeticGate)
  *   city_common_circuit/src/u32/gates/add_many_u32.rs:87-135    (U32AddManyGate)
@@ -438,9 +438,57 @@ static unsigned eval_gate(const p2o_gate *g, const gate_vars *v, uint64_t *out) 
         }
       return k;
     }
+    case P2O_GATE_COSET_INTERPOLATION: { /* p0 = subgroup_bits, p1 = degree (with_max_degree(4, 8) -> 6) */
+      const unsigned n = 1u << g->p0, degree = g->p1, n_int = (n - 2) / (degree - 1);
+      const unsigned pt = 1 + 2 * n, val = pt + 2, ie0 = pt + 4, ip0 = ie0 + 2 * n_int, sh = ie0 + 4 * n_int;
+      uint64_t dom[64], wts[64];
+      /* barycentric weights of the subgroup: 1 / prod_{j != i} (x_i - x_j) = x_i / n */
+      uint64_t gen = gl_root_of_unity(g->p0), ninv = gl_inv(n);
+      dom[0] = 1;
+      for (unsigned i = 1; i < n; i++) dom[i] = gli_mul(dom[i - 1], gen);
+      for (unsigned i = 0; i < n; i++) wts[i] = gli_mul(dom[i], ninv);
+      const uint64_t shift = w[0];
+      out[k++] = gli_sub(w[pt], gli_mul(w[sh], shift));
+      out[k++] = gli_sub(w[pt + 1], gli_mul(w[sh + 1], shift));
+      uint64_t ev[2] = {0, 0}, pr[2] = {1, 0};
+      unsigned lo = 0, hi = degree;
+      for (unsigned c = 0; c <= n_int; c++) {
+        for (unsigned i = lo; i < hi && i < n; i++) { /* partial_interpolate */
+          uint64_t term[2] = {gli_sub(w[sh], dom[i]), w[sh + 1]};
+          uint64_t wv[2] = {gli_mul(w[1 + 2 * i], wts[i]), gli_mul(w[2 + 2 * i], wts[i])};
+          uint64_t a[2], b[2];
+          e2_mul(ev, term, a);
+          e2_mul(wv, pr, b);
+          ev[0] = gli_add(a[0], b[0]);
+          ev[1] = gli_add(a[1], b[1]);
+          e2_mul(pr, term, a);
+          pr[0] = a[0];
+          pr[1] = a[1];
+        }
+        if (c == n_int) break;
+        out[k++] = gli_sub(w[ie0 + 2 * c], ev[0]);
+        out[k++] = gli_sub(w[ie0 + 2 * c + 1], ev[1]);
+        out[k++] = gli_sub(w[ip0 + 2 * c], pr[0]);
+        out[k++] = gli_sub(w[ip0 + 2 * c + 1], pr[1]);
+        ev[0] = w[ie0 + 2 * c], ev[1] = w[ie0 + 2 * c + 1];
+        pr[0] = w[ip0 + 2 * c], pr[1] = w[ip0 + 2 * c + 1];
+        lo = 1 + (degree - 1) * (c + 1);
+        hi = lo + degree - 1;
+      }
+      out[k++] = gli_sub(w[val], ev[0]);
+      out[k++] = gli_sub(w[val + 1], ev[1]);
+      return k;
+    }
     default:
       return 0;
   }
+}
+
+/* unfiltered constraints of one gate at one point (test hook: compared gate by gate with the Python restatement) */
+unsigned plonk_eval_gate(const p2o_gate *g, const uint64_t *wires, const uint64_t *consts, const uint64_t *pi_hash,
+                         uint64_t *out) {
+  gate_vars v = {consts, wires, pi_hash};
+  return eval_gate(g, &v, out);
 }
 
 /* gates/gate.rs compute_filter */

@@ -26,7 +26,7 @@ _spec.loader.exec_module(PF)  # derives FIRST / POST / INIT / W_HATS / VS from M
 (GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON, GATE_BASE_SUM, GATE_U32_ARITHMETIC,
  GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK, GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32,
  GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON, GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_REDUCING, GATE_REDUCING_EXT,
- GATE_RANDOM_ACCESS, GATE_POSEIDON_MDS) = range(20)
+ GATE_RANDOM_ACCESS, GATE_POSEIDON_MDS, GATE_COSET_INTERPOLATION) = range(21)
 UNUSED_SELECTOR = 2**32 - 1
 
 
@@ -402,8 +402,58 @@ def eval_gate(kind, p0, p1, w, consts, pi_hash):
                 acc = acc + ins[(i + r) % 12] * PF.CIRC[i]
             acc = acc + ins[r] * PF.DIAG[r]
             c.extend((acc - _ext_at(w, 24 + 2 * r)).parts())
+    elif kind == GATE_COSET_INTERPOLATION:  # gates/coset_interpolation.rs; p0 = subgroup_bits, p1 = degree
+        c.extend(coset_interpolation_constraints(p0, p1, w))
     else:
         raise ValueError(kind)
+    return c
+
+
+def coset_interpolation_layout(bits, degree):
+    n = 1 << bits
+    n_int = (n - 2) // (degree - 1)
+    start_point = 1 + 2 * n
+    start_int = start_point + 4
+    return dict(n=n, n_int=n_int, point=start_point, value=start_point + 2, inter_eval=start_int,
+                inter_prod=start_int + 2 * n_int, shifted=start_int + 4 * n_int, end=start_int + 2 * (2 * n_int + 1))
+
+
+def coset_interpolation_constraints(bits, degree, w):
+    """barycentric interpolation over shift * H in chunks of `degree` (first) / `degree - 1` points; the weights of
+    the subgroup H are x_i / n"""
+    L = coset_interpolation_layout(bits, degree)
+    n = L["n"]
+    g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - bits), P)
+    dom = [pow(g, i, P) for i in range(n)]
+    ninv = pow(n, P - 2, P)
+    wts = [x * ninv % P for x in dom]
+    for i in range(n):  # the definition plonky2 uses: 1 / prod_{j != i} (x_i - x_j)
+        if i < 3:
+            d = 1
+            for j in range(n):
+                if j != i:
+                    d = d * (dom[i] - dom[j]) % P
+            assert wts[i] == pow(d, P - 2, P)
+    shift = w[0]
+    values = [_ext_at(w, 1 + 2 * i) for i in range(n)]
+    point, shifted = _ext_at(w, L["point"]), _ext_at(w, L["shifted"])
+    c = (point - shifted * shift).parts()
+    one, zero = w[0] * 0 + 1, w[0] * 0
+
+    def partial(lo, hi, ev, prod):
+        for i in range(lo, hi):
+            term = Alg(shifted.c0 - dom[i], shifted.c1)
+            ev, prod = ev * term + values[i] * wts[i] * prod, prod * term
+        return ev, prod
+
+    ev, prod = partial(0, degree, Alg(zero, zero), Alg(one, zero))
+    for i in range(L["n_int"]):
+        ie, ip = _ext_at(w, L["inter_eval"] + 2 * i), _ext_at(w, L["inter_prod"] + 2 * i)
+        c.extend((ie - ev).parts())
+        c.extend((ip - prod).parts())
+        lo = 1 + (degree - 1) * (i + 1)
+        ev, prod = partial(lo, min(lo + degree - 1, n), ie, ip)
+    c.extend((_ext_at(w, L["value"]) - ev).parts())
     return c
 
 
@@ -414,7 +464,7 @@ def gate_degree(kind):
             GATE_COMPARISON: 4,  # ComparisonGate: 2^chunk_bits with chunk_bits = 2
             GATE_ARITHMETIC_EXT: 3, GATE_MUL_EXT: 3, GATE_REDUCING: 2, GATE_REDUCING_EXT: 2,
             GATE_RANDOM_ACCESS: 5,  # bits + 1 with bits = 4
-            GATE_POSEIDON_MDS: 1}[kind]
+            GATE_POSEIDON_MDS: 1, GATE_COSET_INTERPOLATION: 6}[kind]  # with_max_degree(4, 8) -> degree 6
 
 
 def gate_num_constraints(kind, p0, p1):
@@ -424,7 +474,8 @@ def gate_num_constraints(kind, p0, p1):
             GATE_UNINTERLEAVE_TO_U32: p0 * 67, GATE_UNINTERLEAVE_TO_B32: p0 * 67,
             GATE_COMPARISON: 6 + 5 * p1 + -(-p0 // max(p1, 1)), GATE_ARITHMETIC_EXT: 2 * p0, GATE_MUL_EXT: 2 * p0,
             GATE_REDUCING: 2 * p0, GATE_REDUCING_EXT: 2 * p0,
-            GATE_RANDOM_ACCESS: (p0 + 2) * (p1 & 0xFFFF) + (p1 >> 16), GATE_POSEIDON_MDS: 24}[kind]
+            GATE_RANDOM_ACCESS: (p0 + 2) * (p1 & 0xFFFF) + (p1 >> 16), GATE_POSEIDON_MDS: 24,
+            GATE_COSET_INTERPOLATION: 4 + 4 * (((1 << p0) - 2) // max(p1 - 1, 1))}[kind]
 
 
 # ------------------------------------------------------------------------------------------ witness generation
@@ -659,6 +710,44 @@ class SyntheticCircuit:
                     v = PF.matvec(PF.M, [row[2 * k + part] for k in range(12)])
                     for r in range(12):
                         row[24 + 2 * r + part] = v[r]
+            elif kind == GATE_COSET_INTERPOLATION:
+                row = [rng.randrange(P) for _ in range(num_wires)]
+                L = coset_interpolation_layout(p0, p1)
+                npts = L["n"]
+                g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - p0), P)
+                dom = [pow(g, k, P) for k in range(npts)]
+                ninv = pow(npts, P - 2, P)
+                shift = row[0] or 1
+                row[0] = shift
+                point = Ext(row[L["point"]], row[L["point"] + 1])
+                shifted = point * pow(shift, P - 2, P)
+                row[L["shifted"]], row[L["shifted"] + 1] = shifted.a, shifted.b
+                vals = [Ext(row[1 + 2 * k], row[2 + 2 * k]) for k in range(npts)]
+                ev, prod = Ext(0), Ext(1)
+
+                def part(lo, hi, ev, prod):
+                    for k in range(lo, hi):
+                        term = shifted - dom[k]
+                        ev, prod = ev * term + vals[k] * (dom[k] * ninv % P) * prod, prod * term
+                    return ev, prod
+
+                ev, prod = part(0, p1, ev, prod)
+                for k in range(L["n_int"]):
+                    row[L["inter_eval"] + 2 * k], row[L["inter_eval"] + 2 * k + 1] = ev.a, ev.b
+                    row[L["inter_prod"] + 2 * k], row[L["inter_prod"] + 2 * k + 1] = prod.a, prod.b
+                    lo = 1 + (p1 - 1) * (k + 1)
+                    ev, prod = part(lo, min(lo + p1 - 1, npts), ev, prod)
+                row[L["value"]], row[L["value"] + 1] = ev.a, ev.b
+                # semantic check: the gate's output is the Lagrange interpolant through (shift x_k, a_k) at `point`
+                lag = Ext(0)
+                for k in range(npts):
+                    num, den = Ext(1), 1
+                    for j in range(npts):
+                        if j != k:
+                            num = num * (point - shift * dom[j])
+                            den = den * (shift * (dom[k] - dom[j])) % P
+                    lag = lag + vals[k] * num * pow(den, P - 2, P)
+                assert lag == ev, "CosetInterpolationGate restatement does not interpolate"
             for c in range(num_gate_consts):
                 consts[self.num_selectors + c][i] = gc[c]
             for c in range(num_wires):

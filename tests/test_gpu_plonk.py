@@ -11,7 +11,7 @@ import pytest
 
 import p2oracle as O
 import plonk_ref as R
-from test_plonk_oracle import (ALL_GATES, EXT_GATES, EXT_GROUPS, MORE_GATES, MORE_GROUPS,
+from test_plonk_oracle import (ALL_GATES, COSET_GATES, COSET_GROUPS, EXT_GATES, EXT_GROUPS, MORE_GATES, MORE_GROUPS,
                                check_verifier_identity)
 
 pytestmark = pytest.mark.gpu
@@ -50,6 +50,7 @@ def run_gpu(ctx, m, circ, betas, gammas, alphas, rate_bits, cap_height):
     (9, ALL_GATES, FULL_GROUPS, 24, 4),
     (7, MORE_GATES, MORE_GROUPS, 26, 3),
     (7, EXT_GATES, EXT_GROUPS, 27, 4),
+    (6, COSET_GATES, COSET_GROUPS, 28, 2),
     (12, ALL_GATES, FULL_GROUPS, 25, 4),
 ])
 def test_plonk_stages_match_oracle(ctx, m, degree_bits, gates, groups, seed, cap_height):

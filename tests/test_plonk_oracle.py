@@ -23,6 +23,9 @@ MORE_GROUPS = [(0, 3), (3, 5), (5, 6)]
 EXT_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_ARITHMETIC_EXT, 10, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_REDUCING, 43, 0),
              (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_POSEIDON_MDS, 0, 0)]
 EXT_GROUPS = [(0, 3), (3, 6), (6, 7)]
+# CosetInterpolationGate::with_max_degree(4, max_quotient_degree_factor = 8): degree 6, two intermediates
+COSET_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_COSET_INTERPOLATION, 4, 6), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0)]
+COSET_GROUPS = [(0, 2), (2, 4)]
 
 
 def prove_plonk_part(circ, seed, rate_bits=3, cap_height=1):
@@ -69,6 +72,7 @@ def check_verifier_identity(circ, pr, seed):
     (6, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 3),
     (5, MORE_GATES, MORE_GROUPS, 4),
     (5, EXT_GATES, EXT_GROUPS, 5),
+    (5, COSET_GATES, COSET_GROUPS, 6),
 ])
 def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)
@@ -87,3 +91,18 @@ def test_broken_witness_is_detected():
     pr = prove_plonk_part(circ, 11)
     with pytest.raises(AssertionError):
         check_verifier_identity(circ, pr, 12)
+
+
+@pytest.mark.parametrize("gate", ALL_GATES + MORE_GATES[1:5] + EXT_GATES[1:] + COSET_GATES[1:2])
+def test_gate_formulas_agree_on_random_rows(gate):
+    """every gate evaluator of the C oracle vs the Python restatement on unconstrained random rows (the constraint
+    POLYNOMIALS agree, not only their zero sets)"""
+    kind, p0, p1 = gate
+    rng = random.Random(kind * 1000 + p0)
+    for _ in range(3):
+        w = [rng.randrange(P) for _ in range(135)]
+        c = [rng.randrange(P) for _ in range(2)]
+        pi = [rng.randrange(P) for _ in range(4)]
+        ref = [x.a for x in R.eval_gate(kind, p0, p1, [R.Fp(x) for x in w], [R.Fp(x) for x in c], [R.Fp(x) for x in pi])]
+        assert len(ref) == R.gate_num_constraints(kind, p0, p1)
+        assert O.eval_gate(kind, p0, p1, w, c, pi) == ref
