@@ -349,7 +349,7 @@ def run_cuda(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import prove_bench as PB
             circ, digest, pis = PB.build_case()
-            m1 = {"shape": "2^12 rows x 135 wires, 10 gate types, rate 8, cap 4, 16-bit PoW, 28 queries, arities [4,4] "
+            m1 = {"shape": "2^12 rows x 135 wires, the 13 gate types of the recursion circuits (123 gate constraints), rate 8, cap 4, 16-bit PoW, 28 queries, arities [4,4] "
                            "(city_common_circuit/src/circuits/zk_signature2/mod.rs:33-57); synthetic witness",
                   "call": "p2b_prove (witness columns in pinned host memory -> proof words on the host)"}
             for n_ctx in (1, 8):

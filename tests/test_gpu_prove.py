@@ -7,7 +7,7 @@ import pytest
 import p2oracle as O
 import plonk_ref as R
 import verifier_ref as V
-from test_plonk_oracle import ALL_GATES
+from test_plonk_oracle import ALL_GATES, RECURSION_GATES, RECURSION_GROUPS
 from test_prove_oracle import FP_SMALL, make_case
 
 pytestmark = pytest.mark.gpu
@@ -51,6 +51,7 @@ def gpu_prove(ctx, m, circ, digest, pis, fp):
     (5, ALL_GATES[:5], [(0, 4), (4, 5)], 52, dict(FP_SMALL, cap_height=0, reduction_arity_bits=[1, 2, 1], num_query_rounds=3)),
     (9, ALL_GATES, FULL_GROUPS, 53, dict(FP_SMALL, cap_height=4, reduction_arity_bits=[4, 4], proof_of_work_bits=10)),
     (12, ALL_GATES, FULL_GROUPS, 54, FP_CITY),
+    (10, RECURSION_GATES, RECURSION_GROUPS, 55, FP_CITY),
 ])
 def test_gpu_proof_equals_oracle_proof_and_verifies(ctx, m, degree_bits, gates, groups, seed, fp):
     circ, digest, pis = make_case(degree_bits, gates, groups, seed)

@@ -23,6 +23,13 @@ MORE_GROUPS = [(0, 3), (3, 5), (5, 6)]
 EXT_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_ARITHMETIC_EXT, 10, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_REDUCING, 43, 0),
              (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_POSEIDON_MDS, 0, 0)]
 EXT_GROUPS = [(0, 3), (3, 6), (6, 7)]
+# the 13 gate types of plonky2's standard recursion circuits = the gate set of the proofs stored in
+# qbench_data/example.bin (135 wires, num_gate_constraints 123: zk_signature2/mod.rs:54-57)
+RECURSION_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_BASE_SUM, 63, 0),
+                   (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_REDUCING, 43, 0), (R.GATE_ARITHMETIC_EXT, 10, 0),
+                   (R.GATE_ARITHMETIC, 20, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_POSEIDON_MDS, 0, 0),
+                   (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_COSET_INTERPOLATION, 4, 6), (R.GATE_POSEIDON, 0, 0)]
+RECURSION_GROUPS = [(0, 6), (6, 10), (10, 12), (12, 13)]
 # CosetInterpolationGate::with_max_degree(4, max_quotient_degree_factor = 8): degree 6, two intermediates
 COSET_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_COSET_INTERPOLATION, 4, 6), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0)]
 COSET_GROUPS = [(0, 2), (2, 4)]
@@ -73,6 +80,7 @@ def check_verifier_identity(circ, pr, seed):
     (5, MORE_GATES, MORE_GROUPS, 4),
     (5, EXT_GATES, EXT_GROUPS, 5),
     (5, COSET_GATES, COSET_GROUPS, 6),
+    (6, RECURSION_GATES, RECURSION_GROUPS, 7),
 ])
 def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)

@@ -20,14 +20,20 @@ def build_case(degree_bits=12, seed=7):
     public-inputs hash comes from the GPU library, not from the oracle)"""
     import plonk_ref as R
 
-    gates = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0),
-             (R.GATE_POSEIDON, 0, 0), (R.GATE_BASE_SUM, 63, 0), (R.GATE_U32_ARITHMETIC, 3, 0),
-             (R.GATE_U32_ADD_MANY, 3, 5), (R.GATE_U32_SUBTRACTION, 6, 0), (R.GATE_U32_RANGE_CHECK, 7, 0)]
+    # the 13 gate types of plonky2's standard recursion circuits (the gate set of the proofs stored in the
+    # reference's qbench_data/example.bin: 135 wires, 123 gate constraints), in selector groups that respect the
+    # degree bound group size + gate degree <= 8
+    gates = [(R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_BASE_SUM, 63, 0),
+             (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_REDUCING, 43, 0),
+             (R.GATE_ARITHMETIC_EXT, 10, 0), (R.GATE_ARITHMETIC, 20, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_POSEIDON_MDS, 0, 0),
+             (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_COSET_INTERPOLATION, 4, 6),
+             (R.GATE_POSEIDON, 0, 0)]
+    groups = [(0, 6), (6, 10), (10, 12), (12, 13)]
     pis = [seed, 2, 3, 4]
     c = m.Context(0)
     pih = [int(x) for x in c.hash_no_pad(pis)]
     c.close()
-    circ = R.SyntheticCircuit(degree_bits, gates, [(0, 4), (4, 5), (5, 8), (8, 10)], seed, pi_hash=pih)
+    circ = R.SyntheticCircuit(degree_bits, gates, groups, seed, pi_hash=pih)
     return circ, [1, 2, 3, 4], pis
 
 
