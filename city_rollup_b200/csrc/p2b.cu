@@ -1288,8 +1288,13 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   if (log_lde > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "quotient LDE of 2^%u points", log_lde);
   const size_t n = (size_t)1 << d.degree_bits, lde_size = (size_t)1 << log_lde;
   const uint32_t n_terms = nch * (npp + 2) + d.num_gate_constraints;
-  uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr;
+  uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr, *d_parts = nullptr;
+  const uint32_t n_parts = 1 + d.n_gates;
   if ((rc = dmalloc(ctx, &d_apow, (size_t)nch * n_terms))) return rc;
+  if ((rc = dmalloc(ctx, &d_parts, (size_t)n_parts * nch * lde_size))) {
+    dfree(ctx, d_apow);
+    return rc;
+  }
   if ((rc = dmalloc(ctx, &d_q, (size_t)nch * lde_size)) == P2B_OK) rc = dmalloc(ctx, &d_coeffs, (size_t)nch * lde_size);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_tmp, (size_t)nch * lde_size);
   if (rc == P2B_OK) {
@@ -1305,7 +1310,7 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.k_is = c->d_k_is;
     qp.apow = d_apow;
     qp.zh = c->d_zh;
-    qp.out = d_q;
+    qp.parts = d_parts;
     qp.betas = d_betas;
     qp.gammas = d_gammas;
     qp.pi_hash = d_pi_hash;
@@ -1320,7 +1325,10 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.n_gates = d.n_gates;
     qp.n_terms = n_terms;
     qp.roots = ctx->roots();
-    plonk::k_quotient<<<cdiv(lde_size, 128), 128, 0, ctx->stream>>>(qp);
+    plonk::k_quotient<<<dim3(cdiv(lde_size, 128), n_parts), 128, 0, ctx->stream>>>(qp);
+    LAUNCH_CHECK(ctx);
+    plonk::k_quotient_combine<<<dim3(cdiv(lde_size, 256), nch), 256, 0, ctx->stream>>>(d_parts, n_parts, nch, log_lde, mdb,
+                                                                                       c->d_zh, d_q);
     LAUNCH_CHECK(ctx);
     stage_end(ctx);
     // values.coset_ifft(7): ifft, then coefficient k / 7^k
@@ -1334,6 +1342,7 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     stage_end(ctx);
   }
   dfree(ctx, d_apow);
+  dfree(ctx, d_parts);
   dfree(ctx, d_q);
   dfree(ctx, d_tmp);
   if (rc != P2B_OK) {

@@ -562,7 +562,7 @@ struct QuotientParams {
   const uint64_t* k_is;
   const uint64_t* apow;       // [challenge][n_terms] powers of alpha
   const uint64_t* zh;         // [2^mdb] Z_H on the coset, then [2^mdb] inverses
-  uint64_t* out;              // [challenge][lde_size], natural order
+  uint64_t* parts;            // [1 + n_gates][challenge][lde_size], natural order
   const uint64_t* betas;      // device
   const uint64_t* gammas;     // device
   const uint64_t* pi_hash;    // device, 4 canonical elements
@@ -571,54 +571,61 @@ struct QuotientParams {
   ntt2::RootTables roots;
 };
 
+// grid = (lde_size / 128, 1 + n_gates): row 0 of the grid evaluates the permutation argument (L_0 (Z - 1) and the
+// partial-product checks), row 1 + g evaluates gate g.  A point's work is a long dependent instruction stream
+// (the PoseidonGate alone is a whole permutation), and one thread per point leaves a 2^12-row proof with 7 warps
+// per SM; splitting by term group puts (1 + n_gates) times as many independent streams in flight.  Each part
+// writes its alpha-weighted sum to parts[part][challenge][point]; k_quotient_combine adds them (field addition
+// is exact, so the order is irrelevant) and divides by Z_H.
 __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
   const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (leaf >= lde_size) return;
   const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
-  const size_t i_next = (i + ((size_t)1 << P.mdb)) & (lde_size - 1);
-  const size_t leaf_next = ntt2::brev((uint32_t)i_next, log_lde);
-  const uint32_t zi = (uint32_t)(i & (((size_t)1 << P.mdb) - 1));
-  const uint64_t x = fmul(7, ntt2::root_pow(P.roots, log_lde, i));
-  const uint64_t z_h = P.zh[zi], z_h_inv = P.zh[((size_t)1 << P.mdb) + zi];
-  const uint64_t l0 = fmul(z_h, gl::inv(fmul((uint64_t)1 << P.degree_bits, fsub(x, 1))));
   const uint32_t nch = P.n_chal, npp = P.num_pp;
   const uint64_t* cs = P.cs_lde + leaf;
   const uint64_t* wr = P.wires_lde + leaf;
-  const uint64_t* zs = P.zs_lde + leaf;
   const size_t N = P.N;
   uint64_t res[MAX_CHALLENGES];
-  // vanishing_z_1_terms (terms 0 .. nch-1), then the partial-product checks of every challenge
-  // (terms nch + cc * (npp + 1) + k); each term is weighted by every challenge's own power of alpha
 #pragma unroll
   for (int c = 0; c < MAX_CHALLENGES; c++) res[c] = 0;
-  for (uint32_t k = 0; k < nch; k++) {
-    const uint64_t term = fmul(l0, fsub(gl::canon(zs[(size_t)k * N]), 1));
-    for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + k], term));
-  }
-  for (uint32_t cc = 0; cc < nch; cc++) {
-    const uint64_t beta = gl::canon(P.betas[cc]), gamma = gl::canon(P.gammas[cc]);
-    const uint64_t bx = fmul(beta, x);
-    for (uint32_t k = 0; k <= npp; k++) {
-      uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
-      uint64_t next = k == npp ? P.zs_lde[(size_t)cc * N + leaf_next] : zs[(size_t)(nch + cc * npp + k) * N];
-      uint64_t np = 1, dp = 1;
-      for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
-        uint64_t wv = gl::canon(wr[(size_t)j * N]);
-        np = fmul(np, fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma));
-        dp = fmul(dp, fadd(fadd(wv, fmul(beta, gl::canon(cs[(size_t)(P.num_constants + j) * N]))), gamma));
-      }
-      const uint64_t term = fsub(fmul(gl::canon(prev), np), fmul(gl::canon(next), dp));
-      const uint32_t idx = nch + cc * (npp + 1) + k;
-      for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + idx], term));
+  const uint32_t part = blockIdx.y;
+  if (part == 0) {
+    const size_t i_next = (i + ((size_t)1 << P.mdb)) & (lde_size - 1);
+    const size_t leaf_next = ntt2::brev((uint32_t)i_next, log_lde);
+    const uint32_t zi = (uint32_t)(i & (((size_t)1 << P.mdb) - 1));
+    const uint64_t x = fmul(7, ntt2::root_pow(P.roots, log_lde, i));
+    const uint64_t z_h = P.zh[zi];
+    const uint64_t l0 = fmul(z_h, gl::inv(fmul((uint64_t)1 << P.degree_bits, fsub(x, 1))));
+    const uint64_t* zs = P.zs_lde + leaf;
+    // vanishing_z_1_terms (terms 0 .. nch-1), then the partial-product checks of every challenge
+    // (terms nch + cc * (npp + 1) + k); each term is weighted by every challenge's own power of alpha
+    for (uint32_t k = 0; k < nch; k++) {
+      const uint64_t term = fmul(l0, fsub(gl::canon(zs[(size_t)k * N]), 1));
+      for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + k], term));
     }
-  }
-  // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
-  Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
-  const uint32_t gate_base = nch * (npp + 2);
-  for (uint32_t g = 0; g < P.n_gates; g++) {
-    const Gate gate = P.gates[g];
+    for (uint32_t cc = 0; cc < nch; cc++) {
+      const uint64_t beta = gl::canon(P.betas[cc]), gamma = gl::canon(P.gammas[cc]);
+      const uint64_t bx = fmul(beta, x);
+      for (uint32_t k = 0; k <= npp; k++) {
+        uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
+        uint64_t next = k == npp ? P.zs_lde[(size_t)cc * N + leaf_next] : zs[(size_t)(nch + cc * npp + k) * N];
+        uint64_t np = 1, dp = 1;
+        for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
+          uint64_t wv = gl::canon(wr[(size_t)j * N]);
+          np = fmul(np, fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma));
+          dp = fmul(dp, fadd(fadd(wv, fmul(beta, gl::canon(cs[(size_t)(P.num_constants + j) * N]))), gamma));
+        }
+        const uint64_t term = fsub(fmul(gl::canon(prev), np), fmul(gl::canon(next), dp));
+        const uint32_t idx = nch + cc * (npp + 1) + k;
+        for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + idx], term));
+      }
+    }
+  } else {
+    // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
+    Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
+    const Gate gate = P.gates[part - 1];
     const uint64_t s = gl::canon(cs[(size_t)gate.selector_index * N]);
     uint64_t filter = 1;
     for (uint32_t q = gate.group_start; q < gate.group_end; q++)
@@ -627,14 +634,28 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
     Acc acc;
 #pragma unroll
     for (int c = 0; c < MAX_CHALLENGES; c++) acc.a[c] = 0;
-    acc.apow = P.apow + gate_base;
+    acc.apow = P.apow + nch * (npp + 2);
     acc.stride = P.n_terms;
     acc.n_chal = nch;
     acc.q = 0;
     eval_gate(gate, v, acc);
-    for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(filter, acc.a[c]));
+    for (uint32_t c = 0; c < nch; c++) res[c] = fmul(filter, acc.a[c]);
   }
-  for (uint32_t c = 0; c < nch; c++) P.out[(size_t)c * lde_size + i] = fmul(res[c], z_h_inv);
+  for (uint32_t c = 0; c < nch; c++) P.parts[((size_t)part * nch + c) * lde_size + i] = res[c];
+}
+
+// out[c][i] = (sum over parts) / Z_H(x_i)
+__global__ void __launch_bounds__(256) k_quotient_combine(const uint64_t* __restrict__ parts, uint32_t n_parts, uint32_t n_chal,
+                                                           uint32_t log_lde, uint32_t mdb, const uint64_t* __restrict__ zh,
+                                                           uint64_t* __restrict__ out) {
+  const size_t lde_size = (size_t)1 << log_lde;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lde_size) return;
+  const uint32_t c = blockIdx.y;
+  uint64_t acc = 0;
+  for (uint32_t p = 0; p < n_parts; p++) acc = fadd(acc, parts[((size_t)p * n_chal + c) * lde_size + i]);
+  const uint64_t z_h_inv = zh[((size_t)1 << mdb) + (i & (((size_t)1 << mdb) - 1))];
+  out[(size_t)c * lde_size + i] = fmul(acc, z_h_inv);
 }
 
 // apow[c * n_terms + k] = alphas[c]^k

@@ -157,7 +157,9 @@ __device__ const uint64_t RC_G[372] = {  // the round constants again, in global
 
 __device__ __forceinline__ uint64_t coop_mds(uint64_t s, uint32_t l) {
   constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  uint64_t acc_lo = 0, acc_hi = 0;  // sums over the low / high 32-bit halves, < 2^42
+  // this path is latency bound (one warp, one dependent chain): the 12 products are independent and summed
+  // as a tree (4 partial sums) instead of one 12-deep multiply-add chain
+  uint64_t lo4[4] = {0, 0, 0, 0}, hi4[4] = {0, 0, 0, 0};  // sums over the low / high 32-bit halves, < 2^42
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     uint32_t src = l + i;
@@ -165,9 +167,11 @@ __device__ __forceinline__ uint64_t coop_mds(uint64_t s, uint32_t l) {
     const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)s, src, 16);
     const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(s >> 32), src, 16);
     const uint32_t c = C[i] + ((i == 0 && l == 0) ? 8u : 0u);  // diag(8, 0, ..., 0)
-    acc_lo += (uint64_t)lo * c;
-    acc_hi += (uint64_t)hi * c;
+    lo4[i & 3] += (uint64_t)lo * c;
+    hi4[i & 3] += (uint64_t)hi * c;
   }
+  const uint64_t acc_lo = (lo4[0] + lo4[1]) + (lo4[2] + lo4[3]);
+  const uint64_t acc_hi = (hi4[0] + hi4[1]) + (hi4[2] + hi4[3]);
   // acc_lo + 2^32 acc_hi mod p with 2^64 = 2^32 - 1
   const uint32_t b_hi = (uint32_t)(acc_hi >> 32);
   const uint64_t x = (acc_lo & 0xFFFFFFFFull) | (acc_hi << 32);
@@ -180,9 +184,11 @@ __device__ __forceinline__ uint64_t coop_mds(uint64_t s, uint32_t l) {
 // lane = threadIdx & 15; every lane of the warp must call (full-mask shuffles); lanes 12..15 carry garbage
 __device__ __forceinline__ uint64_t coop_permute_nc(uint64_t s, uint32_t l) {
   const uint32_t lc = l < 12 ? l : 0;
+  uint64_t rc = RC_G[lc];
 #pragma unroll 1
   for (int r = 0; r < 30; r++) {
-    s = gl::add_nc(s, RC_G[12 * r + lc]);
+    s = gl::add_nc(s, rc);
+    rc = RC_G[12 * (r + 1) + lc];  // next round's constant (row 30 is zero padding): off the critical path
     if (r < 4 || r >= 26 || l == 0) s = sbox7(s);
     s = coop_mds(s, l);
   }

@@ -45,12 +45,47 @@ void run(uint64_t* d, int sms) {
          a.numRegs, occ, occ * BLOCK / 32, best, perms / best / 1e6, 1.965e9 * sms / (perms / (best * 1e-3)));
 }
 
+// latency of the warp-cooperative permutation: one warp, a chain of dependent permutations
+__global__ void k_coop_latency(uint64_t* io, int iters, long long* cycles) {
+  const uint32_t l = threadIdx.x & 15;
+  uint64_t s = io[threadIdx.x];
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) s = poseidon::coop_permute_nc(s, l);
+  long long t1 = clock64();
+  io[threadIdx.x] = s;
+  if (threadIdx.x == 0) *cycles = (t1 - t0) / iters;
+}
+__global__ void k_single_latency(uint64_t* io, int iters, long long* cycles) {
+  uint64_t s[12];
+  for (int i = 0; i < 12; i++) s[i] = io[i];
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) poseidon::permute_nc(s);
+  long long t1 = clock64();
+  for (int i = 0; i < 12; i++) io[i] = s[i];
+  *cycles = (t1 - t0) / iters;
+}
+
 int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
   uint64_t* d;
   cudaMalloc(&d, (size_t)p.multiProcessorCount * 8 * 4 * 256 * 8);
   cudaMemset(d, 1, (size_t)p.multiProcessorCount * 8 * 4 * 256 * 8);
+  {
+    long long* dc;
+    cudaMalloc(&dc, 8);
+    long long hc = 0;
+    for (int rep = 0; rep < 2; rep++) {
+      k_coop_latency<<<1, 32>>>(d, 64, dc);
+      cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    }
+    printf("coop permutation latency: %lld cycles\n", hc);
+    for (int rep = 0; rep < 2; rep++) {
+      k_single_latency<<<1, 1>>>(d, 16, dc);
+      cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    }
+    printf("single-thread permutation latency: %lld cycles\n", hc);
+  }
   run<256, 1>(d, p.multiProcessorCount);
   run<256, 2>(d, p.multiProcessorCount);
   run<256, 3>(d, p.multiProcessorCount);
