@@ -36,6 +36,11 @@ struct p2b_ctx {
   // column group (batch_from_host)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
+  // pinned double buffer for pageable host columns (plonky2's Vec<PolynomialValues>: one pageable allocation per
+  // column): the worker thread memcpy's into one half while the DMA of the other half is in flight
+  uint64_t* h_upload[2] = {nullptr, nullptr};
+  cudaEvent_t upload_done[2] = {nullptr, nullptr};
+  int upload_half = 0;
   bool poisoned = false;
   std::string err;
   uint64_t launches = 0;
@@ -315,6 +320,10 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   for (auto& kv : ctx->tw_cache) dfree(ctx, kv.second);
   for (auto& kv : ctx->cp_cache) dfree(ctx, kv.second);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->h_upload[i]) cudaFreeHost(ctx->h_upload[i]);
+    if (ctx->upload_done[i]) cudaEventDestroy(ctx->upload_done[i]);
+  }
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) {
     cudaEventDestroy(r.a);
@@ -835,20 +844,66 @@ static int batch_build(p2b_ctx* ctx, uint64_t* d_in /* owned, n_cols x n */, boo
   return P2B_OK;
 }
 
+static const size_t UPLOAD_HALF_WORDS = (size_t)1 << 20;  // 8 MiB per half
+
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // unregistered memory reports an error on old drivers: not sticky
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Host columns [c0, c1) -> d_dst (column c at d_dst + c * n) on `stream`.  Pinned memory (p2b_host_alloc,
+// cudaHostRegister) goes by direct DMA, one copy per run of contiguous columns; pageable memory is staged through
+// the context's pinned double buffer — one memcpy + one DMA per 8 MiB instead of a synchronous, internally staged
+// cudaMemcpy per column (135 of them for a witness).
+static int h2d_cols(p2b_ctx* ctx, cudaStream_t stream, const uint64_t* const* cols, size_t c0, size_t c1, size_t n,
+                    uint64_t* d_dst) {
+  size_t c = c0;
+  while (c < c1) {
+    if (!cols[c]) return fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c);
+    size_t e = c + 1;
+    while (e < c1 && cols[e] == cols[e - 1] + n) e++;
+    if (host_ptr_is_pinned(cols[c])) {
+      CU(ctx, cudaMemcpyAsync(d_dst + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+      c = e;
+      continue;
+    }
+    // pageable: pack as many whole columns (or pieces of a long one) as fit into the current half
+    size_t off = 0;  // words already sent of column c
+    while (c < e) {
+      const int h = ctx->upload_half;
+      if (!ctx->h_upload[h]) {
+        CU(ctx, cudaMallocHost((void**)&ctx->h_upload[h], UPLOAD_HALF_WORDS * sizeof(uint64_t)));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->upload_done[h], cudaEventDisableTiming));
+      } else {
+        CU(ctx, cudaEventSynchronize(ctx->upload_done[h]));  // the previous DMA out of this half has finished
+      }
+      size_t filled = 0;
+      const size_t first_c = c, first_off = off;
+      while (c < e && filled < UPLOAD_HALF_WORDS) {
+        const size_t take = (n - off) < (UPLOAD_HALF_WORDS - filled) ? (n - off) : (UPLOAD_HALF_WORDS - filled);
+        memcpy(ctx->h_upload[h] + filled, cols[c] + off, take * sizeof(uint64_t));
+        filled += take;
+        off += take;
+        if (off == n) c++, off = 0;
+      }
+      // the packed words are contiguous in the destination too (column-major, consecutive columns)
+      CU(ctx, cudaMemcpyAsync(d_dst + first_c * n + first_off, ctx->h_upload[h], filled * sizeof(uint64_t),
+                              cudaMemcpyHostToDevice, stream));
+      CU(ctx, cudaEventRecord(ctx->upload_done[h], stream));
+      ctx->upload_half ^= 1;
+    }
+  }
+  return P2B_OK;
+}
+
 static int upload_cols(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, size_t n, uint64_t** d_out) {
   int rc = dmalloc(ctx, d_out, n_cols * n);
   if (rc) return rc;
-  // one DMA per run of columns that are contiguous in host memory (a single copy when the caller
-  // keeps the matrix in one allocation; one per column for plonky2's Vec<PolynomialValues>)
-  size_t c = 0;
-  while (c < n_cols) {
-    size_t e = c + 1;
-    while (e < n_cols && cols[e] == cols[e - 1] + n) e++;
-    if (!cols[c]) return fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c);
-    CU(ctx, cudaMemcpyAsync(*d_out + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    c = e;
-  }
-  return P2B_OK;
+  return h2d_cols(ctx, ctx->stream, cols, 0, n_cols, n, *d_out);
 }
 
 static cudaEvent_t copy_event(p2b_ctx* ctx, size_t i) {
@@ -897,15 +952,8 @@ static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, 
   size_t gi = 0;
   for (size_t c0 = 0; c0 < n_cols; c0 += group, gi++) {
     const size_t c1 = c0 + group < n_cols ? c0 + group : n_cols;
-    size_t c = c0;
-    while (c < c1) {  // one DMA per run of columns contiguous in host memory
-      size_t e = c + 1;
-      while (e < c1 && cols[e] == cols[e - 1] + n) e++;
-      if (!cols[c]) return bail(fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c));
-      cudaError_t err = cudaMemcpyAsync(d_in + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream);
-      if (err != cudaSuccess) return bail(fail(ctx, P2B_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(err)));
-      c = e;
-    }
+    rc = h2d_cols(ctx, ctx->copy_stream, cols, c0, c1, n, d_in);
+    if (rc) return bail(rc);
     cudaEvent_t ev = copy_event(ctx, gi + 1);
     if (!ev || cudaEventRecord(ev, ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ev, 0) != cudaSuccess)
       return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));

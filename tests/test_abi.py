@@ -59,3 +59,19 @@ def test_product_never_imports_oracle():
                 assert "p2oracle" not in txt and "oracle/" not in txt.replace("oracle/ is test", ""), (dirpath, f)
     for f in ("include/p2b.h",):
         assert "p2oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_cpp_host_mirror_compiles(lib, tmp_path):
+    """the header-only C++ mirror (city_rollup_b200/cpp/plonky2_b200.hpp) and the native job loop built on it
+    (tools/prove_bench.cpp) compile and link against libp2b.so"""
+    import shutil
+    import subprocess
+
+    import city_rollup_b200 as m
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    out = tmp_path / "prove_bench_cpp"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", ROOT, os.path.join(ROOT, "tools", "prove_bench.cpp"),
+                           "-L", os.path.dirname(m.SO_PATH), "-lp2b", "-lpthread", "-o", str(out)])
+    assert out.exists()

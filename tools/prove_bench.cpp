@@ -1,0 +1,109 @@
+// prove_bench.cpp — native (C++17) job loop over the C ABI through the header-only mirror
+// city_rollup_b200/cpp/plonky2_b200.hpp: T worker threads, one p2b context each (the reference's one-worker-
+// per-process model, city_rollup_core_worker/src/actors/simple.rs:32-56, several workers per GPU), every worker
+// proving the same synthetic City-shaped circuit in a loop.  Input: a case file written by
+// tools/dump_prove_case.py (circuit description, constants|sigmas values, witness columns, expected proof
+// words).  Checks every proof word for word against the expected one and prints one JSON line.
+//
+// Build: g++ -O2 -std=c++17 -I. tools/prove_bench.cpp -Lcity_rollup_b200 -lp2b -Wl,-rpath,'$ORIGIN/../city_rollup_b200' -lpthread -o tools/prove_bench_cpp
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+#include "city_rollup_b200/cpp/plonky2_b200.hpp"
+
+using namespace plonky2_b200;
+
+struct Case {
+  p2b_circuit_desc desc{};
+  std::vector<p2b_gate> gates;
+  std::vector<F> k_is;
+  std::vector<std::vector<F>> cs_values, wire_values;
+  HashOut digest{};
+  std::vector<F> public_inputs, expected;
+  p2b_fri_params params{};
+};
+
+static std::vector<uint64_t> read_words(std::ifstream& f, size_t n) {
+  std::vector<uint64_t> v(n);
+  f.read(reinterpret_cast<char*>(v.data()), n * 8);
+  if (!f) throw std::runtime_error("case file truncated");
+  return v;
+}
+
+static Case load_case(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+  Case c;
+  auto hdr = read_words(f, 16);
+  if (hdr[0] != 0x70326263617365ull) throw std::runtime_error("bad magic");
+  uint32_t* d = &c.desc.degree_bits;  // the nine leading u32 fields + n_gates, in declaration order
+  for (int i = 0; i < 10; i++) d[i] = (uint32_t)hdr[1 + i];
+  const size_t n = size_t(1) << c.desc.degree_bits, n_pis = hdr[11], n_expected = hdr[12];
+  auto g = read_words(f, 7 * c.desc.n_gates);
+  for (uint32_t i = 0; i < c.desc.n_gates; i++) {
+    p2b_gate gt{};
+    uint32_t* q = &gt.kind;
+    for (int k = 0; k < 7; k++) q[k] = (uint32_t)g[7 * i + k];
+    c.gates.push_back(gt);
+  }
+  c.k_is = read_words(f, c.desc.num_routed_wires);
+  for (uint32_t i = 0; i < c.desc.num_constants + c.desc.num_routed_wires; i++) c.cs_values.push_back(read_words(f, n));
+  for (uint32_t i = 0; i < c.desc.num_wires; i++) c.wire_values.push_back(read_words(f, n));
+  auto dg = read_words(f, 4);
+  std::copy(dg.begin(), dg.end(), c.digest.begin());
+  c.public_inputs = read_words(f, n_pis);
+  auto fp = read_words(f, 5 + 16);
+  uint32_t* pp = &c.params.rate_bits;
+  for (int i = 0; i < 5 + 16; i++) pp[i] = (uint32_t)fp[i];
+  c.expected = read_words(f, n_expected);
+  return c;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s case.bin [threads=8] [proofs_per_thread=40] [device=0]\n", argv[0]);
+    return 2;
+  }
+  try {
+    Case cs = load_case(argv[1]);
+    const int threads = argc > 2 ? atoi(argv[2]) : 8, per = argc > 3 ? atoi(argv[3]) : 40, device = argc > 4 ? atoi(argv[4]) : 0;
+    std::atomic<int> mismatches{0}, ready{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> pool;
+    std::vector<double> secs(threads, 0.0);
+    for (int t = 0; t < threads; t++) {
+      pool.emplace_back([&, t] {
+        Context ctx(device);
+        CircuitData circuit(ctx, cs.desc, cs.gates, cs.k_is);
+        PolynomialBatch constants_sigmas =
+            PolynomialBatch::from_values(ctx, cs.cs_values, cs.params.rate_bits, false, cs.params.cap_height, true);
+        auto warm = prove(ctx, circuit, constants_sigmas, cs.digest, cs.wire_values, cs.public_inputs, cs.params);
+        if (warm != cs.expected) mismatches++;
+        ready++;
+        while (!go.load()) std::this_thread::yield();
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < per; i++) {
+          auto proof = prove(ctx, circuit, constants_sigmas, cs.digest, cs.wire_values, cs.public_inputs, cs.params);
+          if (proof != cs.expected) mismatches++;
+        }
+        secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      });
+    }
+    while (ready.load() < threads) std::this_thread::yield();
+    auto t0 = std::chrono::steady_clock::now();
+    go = true;
+    for (auto& th : pool) th.join();
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"host\": \"c++ (plonky2_b200.hpp)\", \"threads\": %d, \"proofs\": %d, \"proofs_per_s\": %.2f, "
+           "\"ms_per_proof_per_thread\": %.3f, \"mismatching_proofs\": %d, \"proof_words\": %zu}\n",
+           threads, threads * per, threads * per / wall, wall / per * 1e3, mismatches.load(), cs.expected.size());
+    return mismatches.load() ? 1 : 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+}
