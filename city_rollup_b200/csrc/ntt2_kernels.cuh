@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t pad16(uint32_t i) { return i + (i >> 4); }
 // MODE 2: MODE 1 + index reversal (n - r) mod n and scaling: plonky2's ifft.
 // grid = (rows per column, n_cols); 256 threads, 16 elements per thread.
 template <int MODE, bool PRESCALE>
-__global__ void __launch_bounds__(256, 2) k_row4096(RowParams P) {
+__global__ void __launch_bounds__(256, 3) k_row4096(RowParams P) {
   __shared__ uint64_t sm[4096 + 256];
   const uint32_t tid = threadIdx.x;
   const uint32_t blk = tid >> 4, c = tid & 15;

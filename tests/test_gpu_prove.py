@@ -74,3 +74,25 @@ def test_gpu_openings_match_direct_evaluation(ctx, m):
     with pytest.raises(m.P2BError):
         b.eval_ext(z, 3, 3)
     b.free()
+
+
+def test_gpu_proof_2p14_rows_verifies(ctx, m):
+    """a larger circuit (2^14 rows: multi-pass NTT path, three FRI layers): too slow to rebuild through the Python
+    oracle prover, so the GPU proof goes straight through the restated verifier (which only needs the proof)"""
+    fp = dict(rate_bits=3, cap_height=4, proof_of_work_bits=12, num_query_rounds=10, reduction_arity_bits=[4, 4, 4])
+    gates = [(R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0)]
+    pis = [1, 2, 3, 4, 5]
+    circ = R.SyntheticCircuit(14, gates, [(0, 4)], 61, pi_hash=O.hash_no_pad(pis), link_prob=0.05)
+    digest = [9, 8, 7, 6]
+    cd = m.CircuitData(ctx, circ.desc())
+    cs = m.PolynomialBatch.from_values(ctx, circ.constants_sigmas_values(), 3, False, 4, keep_values=True)
+    proof = m.prove_native(ctx, cd, cs, digest, circ.wire_values(), pis, m.FriParams(3, 4, 12, 10, [4, 4, 4]))
+    assert V.verify(circ, cs.cap, digest, proof, fp)
+    bad = dict(proof, openings=dict(proof["openings"]))
+    w = bad["openings"]["wires"].copy()
+    w[7][1] ^= np.uint64(1)
+    bad["openings"]["wires"] = w
+    with pytest.raises(V.VerificationError):
+        V.verify(circ, cs.cap, digest, bad, fp)
+    cs.free()
+    cd.free()
