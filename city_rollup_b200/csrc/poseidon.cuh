@@ -51,12 +51,12 @@ __constant__ unsigned long long RCF[720] = {
 
 #define P2B_TWO52_HI 0x43300000u
 
-// a + 2^32 b (mod p) for a, b < 2^42 given as the bit patterns of 2^52 + a and 2^52 + b
+// a + 2^32 b (mod p) for a, b < 2^51 given as the bit patterns of 2^52 + a and 2^52 + b
 __device__ __forceinline__ uint64_t fold_f64(double ya, double yb) {
   uint32_t a_lo = (uint32_t)__double2loint(ya), a_hw = (uint32_t)__double2hiint(ya);
   uint32_t b_lo = (uint32_t)__double2loint(yb), b_hw = (uint32_t)__double2hiint(yb);
   uint32_t b_hi = b_hw - P2B_TWO52_HI;                   // bits >= 32 of b: weight 2^64 = 2^32 - 1
-  uint32_t m = a_hw + b_hw - 2u * P2B_TWO52_HI;          // a_hi + b_hi (< 2^11)
+  uint32_t m = a_hw + b_hw - 2u * P2B_TWO52_HI;          // a_hi + b_hi (< 2^20)
   uint32_t r0, r1;
   asm("{\n\t"
       ".reg .u32 yl,yh,c;\n\t"
@@ -74,18 +74,16 @@ __device__ __forceinline__ uint64_t fold_f64(double ya, double yb) {
   return gl::pack(r0, r1);
 }
 
-// one limb set: x[k] = limb k (any u32) -> y[r] = 2^52 + (MDS x)[r] + K[r]
-__device__ __forceinline__ void mds_limbs_f64(const uint32_t (&x)[12], const unsigned long long* __restrict__ init,
-                                              double (&y)[12]) {
+// one limb set: b[k] = the double 2^52 + limb_k (limb_k < 2^42)  ->  y[r] = 2^52 + (MDS limb)[r] + K[r]
+__device__ __forceinline__ void mds_limbs_biased(const double (&b)[12], const unsigned long long* __restrict__ init,
+                                                 double (&y)[12]) {
   constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
   constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
   double p[6], m[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    double a = __hiloint2double((int)P2B_TWO52_HI, (int)x[k]);      // 2^52 + x_k
-    double b = __hiloint2double((int)P2B_TWO52_HI, (int)x[k + 6]);  // 2^52 + x_{k+6}
-    m[k] = a - b;
-    p[k] = a + (b - 9007199254740992.0);  // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
+    m[k] = b[k] - b[k + 6];                          // the 2^52 biases cancel
+    p[k] = b[k] + (b[k + 6] - 9007199254740992.0);   // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
   }
 #pragma unroll
   for (int r = 0; r < 6; r++) {
@@ -108,18 +106,40 @@ __device__ __forceinline__ void mds_limbs_f64(const uint32_t (&x)[12], const uns
   }
 }
 
+__device__ __forceinline__ double biased_lo(uint64_t v) { return __hiloint2double((int)P2B_TWO52_HI, (int)(uint32_t)v); }
+__device__ __forceinline__ double biased_hi(uint64_t v) { return __hiloint2double((int)P2B_TWO52_HI, (int)(uint32_t)(v >> 32)); }
+
 // s <- MDS * s + rc(next round); `init` = the 24 chain initialisers of that round
 __device__ __forceinline__ void mds_layer(uint64_t (&s)[12], const unsigned long long* __restrict__ init) {
-  uint32_t x[12];
-  double ylo[12], yhi[12];
+  double b[12], ylo[12], yhi[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) x[i] = (uint32_t)s[i];
-  mds_limbs_f64(x, init, ylo);
+  for (int i = 0; i < 12; i++) b[i] = biased_lo(s[i]);
+  mds_limbs_biased(b, init, ylo);
 #pragma unroll
-  for (int i = 0; i < 12; i++) x[i] = (uint32_t)(s[i] >> 32);
-  mds_limbs_f64(x, init + 12, yhi);
+  for (int i = 0; i < 12; i++) b[i] = biased_hi(s[i]);
+  mds_limbs_biased(b, init + 12, yhi);
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = fold_f64(ylo[i], yhi[i]);
+}
+
+// Two consecutive partial rounds.  Only lane 0 goes through an S-box, so lanes 1..11 can stay in the FP64 domain
+// between the two MDS layers: the first layer's row sums (2^52 + a 41-bit integer) ARE valid biased limbs for
+// the second layer (its partial sums stay below 2^53: 264 * 2^41 + 2^52), and only lane 0 is folded to an
+// integer, raised to the 7th power and converted back.  Saves 11 folds and 22 conversions per pair of rounds.
+__device__ __forceinline__ void partial_round_pair(uint64_t (&s)[12], const unsigned long long* __restrict__ init) {
+  double blo[12], bhi[12], ylo[12], yhi[12];
+  s[0] = sbox7(s[0]);
+#pragma unroll
+  for (int i = 0; i < 12; i++) blo[i] = biased_lo(s[i]), bhi[i] = biased_hi(s[i]);
+  mds_limbs_biased(blo, init, ylo);
+  mds_limbs_biased(bhi, init + 12, yhi);
+  const uint64_t s0 = sbox7(fold_f64(ylo[0], yhi[0]));
+  ylo[0] = biased_lo(s0);
+  yhi[0] = biased_hi(s0);
+  mds_limbs_biased(ylo, init + 24, blo);
+  mds_limbs_biased(yhi, init + 36, bhi);
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = fold_f64(blo[i], bhi[i]);
 }
 
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).
@@ -127,14 +147,16 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_nc(s[i], RC[i]);  // RC entries are canonical
 #pragma unroll 1
-  for (int r = 0; r < 30; r++) {
+  for (int r = 0; r < 30;) {
     if (r < 4 || r >= 26) {
 #pragma unroll
       for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+      mds_layer(s, RCF + 24 * r);
+      r += 1;
     } else {
-      s[0] = sbox7(s[0]);
+      partial_round_pair(s, RCF + 24 * r);  // the 22 partial rounds, two at a time
+      r += 2;
     }
-    mds_layer(s, RCF + 24 * r);
   }
 }
 
