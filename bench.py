@@ -129,6 +129,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU run on ALL host cores
+    # (libgomp reads the variable when the oracle library is loaded)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import p2oracle as O
     from util import rand_felts
 

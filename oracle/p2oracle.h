@@ -43,7 +43,8 @@ void gl2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
 void gl2_inv(const uint64_t a[2], uint64_t out[2]);
 
 /* ---- Poseidon ---- */
-void poseidon_permute(uint64_t state[12]);
+void poseidon_permute(uint64_t state[12]);      /* the literal round structure */
+void poseidon_permute_fast(uint64_t state[12]); /* fast-partial-round form (what PoseidonGate constrains); same result */
 void poseidon_hash_no_pad(const uint64_t *in, size_t len, uint64_t out[4]);
 void poseidon_hash_or_noop(const uint64_t *in, size_t len, uint64_t out[4]);
 void poseidon_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);

@@ -111,3 +111,16 @@ def test_pow_is_minimal_and_valid():
     w = O.fri_proof_of_work(ch, 10)
     assert O.fri_pow_check(base, w, 10) == 1
     assert all(O.fri_pow_check(base, v, 10) == 0 for v in range(w))
+
+
+def test_poseidon_fast_partial_round_form_equals_permutation():
+    """the fast-partial-round schedule (tables derived in tools/gen_poseidon_fast_tables.py; the form PoseidonGate
+    constrains) computes the K1-pinned permutation"""
+    L = O.lib()
+    rng = np.random.default_rng(11)
+    for t in range(300):
+        s = rng.integers(0, 2**64, 12, dtype=np.uint64) if t > 1 else np.full(12, 2**64 - 1 if t else 0, dtype=np.uint64)
+        a, b = s.copy(), s.copy()
+        L.poseidon_permute(O._p(a))
+        L.poseidon_permute_fast(O._p(b))
+        assert (a == b).all()
