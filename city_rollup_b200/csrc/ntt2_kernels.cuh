@@ -59,6 +59,27 @@ __host__ __device__ constexpr uint32_t brev_c(uint32_t x, int bits) {
   return r;
 }
 
+// x * 2^E mod p for canonical x and 0 < E < 96 (E is a compile-time constant after unrolling), canonical result.
+// x << (E mod 32) is three 32-bit words y0, y1, y2 (funnel shifts) that land on word positions q .. q+2,
+// q = E / 32, and 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 reduce them with one or two modular add/subs:
+// ~15 instructions instead of the ~34 a general multiplication by the constant costs.
+__device__ __forceinline__ uint64_t mul_pow2c(uint64_t x, int E) {
+  const int r = E & 31, q = E >> 5;
+  const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+  const uint32_t y0 = xl << r;
+  const uint32_t y1 = r ? __funnelshift_l(xl, xh, r) : xh;
+  const uint32_t y2 = r ? (xh >> (32 - r)) : 0u;
+  auto eps_times = [](uint32_t v) { return ((uint64_t)v << 32) - v; };  // v * (2^32 - 1), canonical
+  uint64_t res;
+  if (q == 0)
+    res = gl::add_nc(gl::pack(y0, y1), eps_times(y2));                                   // y0 + 2^32 y1 + 2^64 y2
+  else if (q == 1)
+    res = gl::sub_nc(gl::add_nc(gl::pack(0u, y0), eps_times(y1)), (uint64_t)y2);           // 2^32 y0 + 2^64 y1 + 2^96 y2
+  else
+    res = gl::sub_nc(eps_times(y0), gl::pack(y1, y2));                                     // 2^64 y0 + 2^96 y1 + 2^128 y2
+  return gl::canon(res);
+}
+
 // In-register DIF of size 2^LOGR (LOGR <= 6): slot `pos` ends up holding output index brev(pos).
 // w_{2^k} = 2^(39 * 2^(6-k)) mod p, so w_{2h}^j = +-2^E with E known at compile time.
 template <int LOGR>
@@ -79,9 +100,9 @@ struct Dif {
           if (E == 0)
             x[i1] = subc(a, b);
           else if (E < 96)
-            x[i1] = mulc(subc(a, b), pow2_mod_p(E));
+            x[i1] = mul_pow2c(subc(a, b), E);
           else
-            x[i1] = mulc(subc(b, a), pow2_mod_p(E - 96));
+            x[i1] = mul_pow2c(subc(b, a), E - 96);
         }
       }
     }
