@@ -279,8 +279,13 @@ def run_cuda(args):
         "frac": leaf_gops / int_peak, "traffic": traffic.get("k_leaf_hash_colmajor"),
         "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM, "permutations_per_launch": leaf_perms,
         "ms_per_launch": leaf_ms,
-        "note": "the dominant kernel is integer-pipe bound (SURVEY.md §0.7), so its roofline is the measured "
-                "INT32 issue rate; the HBM-side kernels are in roofline_hbm",
+        "hbm_view": {"bound": "hbm", "algorithmic_bytes_per_launch": 8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS),
+                     "achieved": (8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS)) / (leaf_ms * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS)) / (leaf_ms * 1e-3) / 1e9 / hbm_peak},
+        "note": "the dominant kernel is integer-pipe bound (SURVEY.md §0.7: ~380 int32 ops per byte against a machine "
+                "balance of ~5), so its roofline is the measured INT32 issue rate; hbm_view gives the same launch against "
+                "the HBM peak (its DRAM traffic equals the algorithmic bytes); the HBM-side kernels are in roofline_hbm",
     }
     lde_bytes = 8 * N_COLS * n * 2 + 8 * N_COLS * (n << RATE_BITS)
     roofline_hbm = {
