@@ -27,7 +27,7 @@ __device__ __forceinline__ void load_digest(const uint64_t* __restrict__ src, ui
 // Leaf digests of a column-major matrix: leaf j = (data[c * col_stride + j])_{c < n_cols}.
 // hash_or_noop: n_cols <= 4 -> zero-padded copy, else overwrite-mode sponge, 8 columns per permutation.
 // Consecutive threads read consecutive j of the same column: every load is a full 256 B per warp.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k_leaf_hash_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t n_cols, size_t n_leaves,
                      uint64_t* __restrict__ digests) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
