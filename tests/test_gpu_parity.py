@@ -167,6 +167,35 @@ def test_batch_from_coeffs(ctx, m, log_n, n_cols, rate_bits, cap_height):
     _check_batch(ctx, m, cols, rate_bits, cap_height, False)
 
 
+def test_batch_random_shapes(ctx, m):
+    """seeded random shapes around the kernel-selection boundaries (generic smem NTT below 2^12, radix-16 path with
+    1..4 strided bits above it, pipelined upload for >= 32 columns at >= 2^14 rows), values and coefficients"""
+    rng = np.random.default_rng(20261018)
+    for case in range(10):
+        log_n = int(rng.integers(9, 16))
+        n_cols = int(rng.choice([1, 2, 7, 19, 33, 48]))
+        rate_bits = int(rng.integers(0, 4))
+        cap_height = int(rng.integers(0, min(5, log_n + rate_bits + 1)))
+        cols = [rand_felts(7000 + 100 * case + c, 1 << log_n, canonical=bool((c + case) % 2)) for c in range(n_cols)]
+        _check_batch(ctx, m, cols, rate_bits, cap_height, from_values=bool(case % 2 == 0), sample_only=log_n + rate_bits > 15)
+
+
+def test_pinned_and_pageable_inputs_agree(ctx, m):
+    """pinned host columns go by direct DMA, pageable ones through the staging double buffer (incl. a column longer
+    than one 8 MiB half): same batch"""
+    log_n, n_cols = 21, 2  # 16 MiB per column
+    pageable = [rand_felts(31 + c, 1 << log_n) for c in range(n_cols)]
+    pinned = ctx.pinned_empty((n_cols, 1 << log_n))
+    for c in range(n_cols):
+        pinned[c] = pageable[c]
+    a = m.PolynomialBatch.from_values(ctx, pageable, 1, False, 3)
+    b = m.PolynomialBatch.from_values(ctx, [pinned[c] for c in range(n_cols)], 1, False, 3)
+    assert (a.cap == b.cap).all()
+    assert (a.coeffs(1) == b.coeffs(1)).all()
+    a.free()
+    b.free()
+
+
 def test_batch_config1_shape_bit_exact(ctx, m):
     """BASELINE.json configs[1]: 2^16 rows x 135 wire columns, rate_bits 3, cap_height 4 — the full commit
     against the oracle (coefficients, sampled leaves, paths, cap)."""
