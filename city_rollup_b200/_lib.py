@@ -75,6 +75,10 @@ SIGNATURES = {
     "p2b_prove_openings": (C.c_int, [vp, C.POINTER(vp), sz, vp, sz, vp, vp, u64p, sz]),
     "p2b_proof_len": (sz, [vp, vp, vp, sz]),
     "p2b_prove": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp, u64p, sz]),
+    "p2b_proof_words": (sz, [vp, vp]),
+    "p2b_proof_bincode_len": (sz, [vp, vp]),
+    "p2b_proof_to_bincode": (C.c_int, [vp, vp, u64p, sz, C.POINTER(C.c_uint8), sz, C.POINTER(sz)]),
+    "p2b_proof_from_bincode": (C.c_int, [vp, vp, C.POINTER(C.c_uint8), sz, u64p, sz, C.POINTER(sz)]),
 }
 
 
@@ -89,6 +93,12 @@ class CircuitDescStruct(C.Structure):  # p2b_circuit_desc
                 ("num_selectors", u32), ("num_challenges", u32), ("quotient_degree_factor", u32),
                 ("num_partial_products", u32), ("num_gate_constraints", u32), ("n_gates", u32),
                 ("gates", C.POINTER(GateStruct)), ("k_is", u64p)]
+
+
+class ProofShapeStruct(C.Structure):  # p2b_proof_shape
+    _fields_ = [("degree_bits", u32), ("num_constants", u32), ("num_routed_wires", u32), ("num_wires", u32),
+                ("num_challenges", u32), ("num_partial_products", u32), ("quotient_degree_factor", u32),
+                ("constants_sigmas_cap_height", u32), ("n_public_inputs", u32)]
 
 
 class FriRange(C.Structure):

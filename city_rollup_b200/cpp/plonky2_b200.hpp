@@ -248,4 +248,24 @@ inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, cons
   return out;
 }
 
+// bincode::serialize(&ProofWithPublicInputs) / bincode::deserialize — the bytes the reference's proof store holds
+// (city_rollup_common/src/qworker/memory_proof_store/mod.rs:31-46,65-72) from / to the flat proof words
+inline std::vector<uint8_t> proof_to_bincode(const p2b_proof_shape& shape, const p2b_fri_params& params, const std::vector<F>& words) {
+  std::vector<uint8_t> out(p2b_proof_bincode_len(&shape, &params));
+  size_t written = 0;
+  const int rc = out.empty() ? (int)P2B_ERR_INVALID
+                             : p2b_proof_to_bincode(&shape, &params, words.data(), words.size(), out.data(), out.size(), &written);
+  if (rc != P2B_OK) throw Error(rc, "proof words do not match the shape");
+  out.resize(written);
+  return out;
+}
+inline std::vector<F> proof_from_bincode(const p2b_proof_shape& shape, const p2b_fri_params& params, const std::vector<uint8_t>& bytes) {
+  std::vector<F> words(p2b_proof_words(&shape, &params));
+  size_t n = 0;
+  const int rc = words.empty() ? (int)P2B_ERR_INVALID
+                               : p2b_proof_from_bincode(&shape, &params, bytes.data(), bytes.size(), words.data(), words.size(), &n);
+  if (rc != P2B_OK) throw Error(rc, "blob is not a proof of this shape");
+  return words;
+}
+
 }  // namespace plonky2_b200

@@ -634,3 +634,46 @@ def prove(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values
 
 
 P = 0xFFFFFFFF00000001
+
+
+# ----------------------------------------------------------------------------- proof bytes (bincode)
+def proof_shape(desc, n_public_inputs, constants_sigmas_cap_height):
+    """p2b_proof_shape from a CommonCircuitData-shaped dict (CircuitData.desc / tests/golden/circuit_params.json)"""
+    return _lib.ProofShapeStruct(desc["degree_bits"], desc["num_constants"], desc["num_routed_wires"],
+                                 desc["num_wires"], desc["num_challenges"], desc["num_partial_products"],
+                                 desc["quotient_degree_factor"], constants_sigmas_cap_height, n_public_inputs)
+
+
+def proof_to_bincode(shape, fri_params, words):
+    """`bincode::serialize(&proof_with_pis)` as the reference's proof store does it
+    (city_rollup_common/src/qworker/memory_proof_store/mod.rs:31-46): the u64 words of prove_native(raw=True)
+    -> the bytes the store holds."""
+    lib = _lib.load()
+    ps = fri_params.struct()
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    n = int(lib.p2b_proof_bincode_len(C.byref(shape), C.byref(ps)))
+    if n == 0:
+        raise P2BError(-1, "inconsistent proof shape / FRI parameters")
+    out = (C.c_uint8 * n)()
+    written = C.c_size_t()
+    rc = lib.p2b_proof_to_bincode(C.byref(shape), C.byref(ps), _ptr(words), len(words), out, n, C.byref(written))
+    if rc != 0:
+        raise P2BError(rc, "proof words do not match the shape (%d words)" % len(words))
+    return bytes(out[:written.value])
+
+
+def proof_from_bincode(shape, fri_params, blob):
+    """`bincode::deserialize::<ProofWithPublicInputs<F, C, D>>` (memory_proof_store/mod.rs:65-72) -> the u64 words
+    in p2b_prove's layout; raises P2BError when any length prefix disagrees with the shape."""
+    lib = _lib.load()
+    ps = fri_params.struct()
+    n = int(lib.p2b_proof_words(C.byref(shape), C.byref(ps)))
+    if n == 0:
+        raise P2BError(-1, "inconsistent proof shape / FRI parameters")
+    words = np.zeros(n, np.uint64)
+    buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob) if len(blob) else (C.c_uint8 * 1)()
+    got = C.c_size_t()
+    rc = lib.p2b_proof_from_bincode(C.byref(shape), C.byref(ps), buf, len(blob), _ptr(words), n, C.byref(got))
+    if rc != 0:
+        raise P2BError(rc, "blob is not a proof of this shape")
+    return words

@@ -299,6 +299,32 @@ int p2b_prove(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constan
               const uint64_t *circuit_digest, const uint64_t *const *wire_cols, const uint64_t *public_inputs,
               size_t n_public_inputs, const p2b_fri_params *params, uint64_t *proof_out, size_t proof_cap);
 
+/* ---------------------------------------------------------------- proof bytes ------------ */
+/* The byte form the reference stores and ships proofs in: `bincode::serialize(&ProofWithPublicInputs)`
+ * (city_rollup_common/src/qworker/memory_proof_store/mod.rs:31-46,65-72; city_redis_store/src/lib.rs:54-82) —
+ * bincode 1.3.3 defaults: little endian, every Vec prefixed by its u64 length.  The words p2b_prove writes are the
+ * same fields in the same order without the prefixes; these host-only helpers add / strip them for a given circuit
+ * shape (CommonCircuitData: city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145).  Pinned on the ten
+ * stored proofs of qbench_data/example.bin (tests/test_proof_bincode.py): blob -> words -> identical blob. */
+typedef struct {
+  uint32_t degree_bits;
+  uint32_t num_constants, num_routed_wires, num_wires; /* constants|sigmas width = num_constants + num_routed_wires */
+  uint32_t num_challenges, num_partial_products, quotient_degree_factor;
+  uint32_t constants_sigmas_cap_height; /* cap height of the circuit's constants_sigmas tree (= fri cap_height in plonky2) */
+  uint32_t n_public_inputs;
+} p2b_proof_shape;
+/* number of u64 words of a proof of this shape (= p2b_proof_len for the matching circuit); 0 on invalid arguments */
+size_t p2b_proof_words(const p2b_proof_shape *shape, const p2b_fri_params *params);
+/* number of bytes of its bincode form; 0 on invalid arguments */
+size_t p2b_proof_bincode_len(const p2b_proof_shape *shape, const p2b_fri_params *params);
+/* words (as written by p2b_prove) -> bincode bytes; *written (optional) = bytes produced */
+int p2b_proof_to_bincode(const p2b_proof_shape *shape, const p2b_fri_params *params, const uint64_t *words,
+                         size_t n_words, uint8_t *out, size_t out_cap, size_t *written);
+/* bincode bytes -> words; every length prefix is checked against the shape (P2B_ERR_INVALID on any mismatch, so a
+ * proof of another circuit is rejected instead of mis-sliced) */
+int p2b_proof_from_bincode(const p2b_proof_shape *shape, const p2b_fri_params *params, const uint8_t *bytes,
+                           size_t n_bytes, uint64_t *words_out, size_t words_cap, size_t *n_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,37 @@ extern "C" {
     pub fn p2b_prove(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
         circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
         params: *const p2b_fri_params, proof_out: *mut u64, proof_cap: usize) -> c_int;
+
+    pub fn p2b_proof_words(shape: *const p2b_proof_shape, params: *const p2b_fri_params) -> usize;
+    pub fn p2b_proof_bincode_len(shape: *const p2b_proof_shape, params: *const p2b_fri_params) -> usize;
+    pub fn p2b_proof_to_bincode(shape: *const p2b_proof_shape, params: *const p2b_fri_params, words: *const u64,
+        n_words: usize, out: *mut u8, out_cap: usize, written: *mut usize) -> c_int;
+    pub fn p2b_proof_from_bincode(shape: *const p2b_proof_shape, params: *const p2b_fri_params, bytes: *const u8,
+        n_bytes: usize, words_out: *mut u64, words_cap: usize, n_words: *mut usize) -> c_int;
+}
+
+/// `p2b_proof_shape`: what of `CommonCircuitData` fixes the layout of a proof
+/// (city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct p2b_proof_shape {
+    pub degree_bits: u32,
+    pub num_constants: u32, pub num_routed_wires: u32, pub num_wires: u32,
+    pub num_challenges: u32, pub num_partial_products: u32, pub quotient_degree_factor: u32,
+    pub constants_sigmas_cap_height: u32,
+    pub n_public_inputs: u32,
+}
+
+/// The bytes `bincode::serialize(&proof_with_pis)` produces (what the proof store keeps,
+/// city_rollup_common/src/qworker/memory_proof_store/mod.rs:31-46) straight from the proof words.
+pub fn proof_to_bincode(shape: &p2b_proof_shape, params: &p2b_fri_params, words: &[u64]) -> Result<Vec<u8>, P2bError> {
+    let cap = unsafe { p2b_proof_bincode_len(shape, params) };
+    let mut out = vec![0u8; cap];
+    let mut written = 0usize;
+    let rc = unsafe { p2b_proof_to_bincode(shape, params, words.as_ptr(), words.len(), out.as_mut_ptr(), cap, &mut written) };
+    if cap == 0 || rc != 0 { return Err(P2bError { code: rc, message: "proof words do not match the shape".into() }); }
+    out.truncate(written);
+    Ok(out)
 }
 
 /// Error type the patched plonky2 converts into `anyhow::Error` (the reference propagates it with `?`
