@@ -115,28 +115,41 @@ k_fold_coeffs(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1, 
   o1[i] = acc.c1;
 }
 
-// fri_proof_of_work: candidate w = base + thread; the duplex state is the sponge state with the pending
-// inputs written over its head and w at position n_in; response = state[7] after one permutation.
+// fri_proof_of_work: the duplex state is the sponge state with the pending inputs written over its head and the
+// candidate w at position n_in; response = state[7] after one permutation.  The MINIMAL witness is wanted (the
+// reference's rayon find_any is schedule dependent), and it is geometric with mean 2^pow_bits, so a
+// fixed chunk wastes most of its permutations.  Every thread walks the candidates base + tid, base + tid + T, ...
+// in increasing order and stops as soon as its candidate exceeds the best witness found so far: every candidate
+// below the final minimum is still evaluated by its owner (a stale read of `best` only delays a thread's exit),
+// and the launch ends one grid stride after the first hit.
 __global__ void __launch_bounds__(256)
 k_pow_search(const uint64_t* __restrict__ st, uint64_t base, uint64_t count, uint32_t pow_bits,
              unsigned long long* __restrict__ best) {
-  uint64_t off = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (off >= count) return;
-  uint64_t w = base + off;
-  if (w >= GL_P) return;
-  uint64_t s[12];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t s0[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = st[i];
-  uint32_t n_in = (uint32_t)st[CH_NIN];
+  for (int i = 0; i < 12; i++) s0[i] = st[i];
+  const uint32_t n_in = (uint32_t)st[CH_NIN];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if ((uint32_t)i < n_in) s[i] = st[CH_IN + i];
-    if ((uint32_t)i == n_in) s[i] = w;
+  for (int i = 0; i < 8; i++)
+    if ((uint32_t)i < n_in) s0[i] = st[CH_IN + i];
+  for (uint64_t off = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; off < count; off += stride) {
+    const uint64_t w = base + off;
+    // relaxed GPU-scope load: served by L2, where the atomicMin lands.  (Measured on B200: a plain `volatile` read
+    // here kept returning the initial value for the whole launch — every thread ran all its strides.)
+    unsigned long long cur;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(best) : "memory");
+    if (w >= GL_P || w > cur) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = ((uint32_t)i == n_in) ? w : s0[i];
+    poseidon::permute_nc(s);
+    const uint64_t resp = gl::canon(s[7]);
+    if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) {
+      atomicMin(best, (unsigned long long)w);
+      return;
+    }
   }
-  poseidon::permute_nc(s);
-  uint64_t resp = gl::canon(s[7]);
-  bool ok = pow_bits == 0 || (resp >> (64 - pow_bits)) == 0;
-  if (ok) atomicMin(best, (unsigned long long)w);
 }
 
 }  // namespace frik

@@ -63,6 +63,45 @@ __device__ __forceinline__ uint64_t mul_nc(uint64_t a, uint64_t b) {
 
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return canon(mul_nc(a, b)); }
 
+// (a*b + c) mod p, any u64 inputs (a*b + c < 2^128); result congruent, NOT necessarily < p.  One reduction for the
+// product and the addend: the accumulate step of the linearised partial rounds (poseidon::coop_partial_rounds),
+// where neither the running sum nor the product is canonical.
+__device__ __forceinline__ uint64_t mad_nc(uint64_t a, uint64_t b, uint64_t c) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,m,tl,th;\n\t"
+      "mul.lo.u32 x0, %2, %4;\n\t"
+      "mul.hi.u32 x1, %2, %4;\n\t"
+      "mul.lo.u32 x2, %3, %5;\n\t"
+      "mul.hi.u32 x3, %3, %5;\n\t"
+      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+      "madc.hi.cc.u32 x2, %2, %5, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "add.cc.u32 x0, x0, %6;\n\t"
+      "addc.cc.u32 x1, x1, %7;\n\t"
+      "addc.cc.u32 x2, x2, 0;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "sub.cc.u32 tl, x0, x3;\n\t"
+      "subc.cc.u32 th, x1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 tl, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      "mad.lo.cc.u32 tl, x2, 0xFFFFFFFF, tl;\n\t"
+      "madc.hi.cc.u32 th, x2, 0xFFFFFFFF, th;\n\t"
+      "addc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      "add.u32 %1, th, m;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"((uint32_t)c), "r"((uint32_t)(c >> 32)));
+  return pack(r0, r1);
+}
+
 // a + b mod p; requires a + b < 2^65 - 2^32 (true when at least one operand is canonical).
 // Result is a u64 congruent to the sum, not necessarily canonical.
 __device__ __forceinline__ uint64_t add_nc(uint64_t a, uint64_t b) {

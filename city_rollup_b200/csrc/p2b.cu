@@ -26,6 +26,7 @@ static thread_local std::string g_init_error;
 
 struct p2b_ctx {
   int device = 0;
+  int sm_count = 148;  // B200; read from the device at init (persistent-style grids are sized from it)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   // Every context allocates from its OWN stream-ordered pool: with the shared default pool a block freed on one
@@ -283,6 +284,8 @@ static int init_common(int device, void* stream, bool borrow, p2b_ctx** out) {
   p2b_ctx* ctx = new (std::nothrow) p2b_ctx();
   if (!ctx) return fail(nullptr, P2B_ERR_OOM, "host allocation failed");
   ctx->device = device;
+  if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0)
+    ctx->sm_count = 148;
   if (borrow) {
     ctx->stream = (cudaStream_t)stream;
   } else {
@@ -1873,12 +1876,17 @@ extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, 
   uint64_t* d_best = nullptr;
   int rc = dmalloc(ctx, &d_best, 1);
   if (rc) return rc;
-  // the minimal witness is geometric with mean 2^pow_bits: search 4x that first (98% hit rate), then double
-  uint64_t chunk = (uint64_t)1 << (pow_bits + 2 < 14 ? 14 : pow_bits + 2 > 24 ? 24 : pow_bits + 2);
+  // the minimal witness is geometric with mean 2^pow_bits; the kernel walks the candidates in increasing order and
+  // stops one grid stride after the first hit, so a launch may cover far more than it evaluates.  Grid: about half
+  // the mean per stride, between one and three CTAs per SM.
+  const uint64_t sms = (uint64_t)ctx->sm_count;
+  uint64_t blocks = (((uint64_t)1 << pow_bits) / 2 + 255) / 256;
+  blocks = blocks < sms ? sms : blocks > 3 * sms ? 3 * sms : blocks;
+  uint64_t chunk = (uint64_t)1 << (pow_bits + 4 < 18 ? 18 : pow_bits + 4);
   uint64_t found = ~0ull;
-  for (uint64_t base = 0; found == ~0ull; base += chunk, chunk = chunk < ((uint64_t)1 << 24) ? chunk * 2 : chunk) {
-    CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
-    frik::k_pow_search<<<cdiv(chunk, 256), 256, 0, ctx->stream>>>(ch->d_state, base, chunk, pow_bits, (unsigned long long*)d_best);
+  CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
+  for (uint64_t base = 0; found == ~0ull; base += chunk) {
+    frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, base, chunk, pow_bits, (unsigned long long*)d_best);
     LAUNCH_CHECK(ctx);
     rc = d2h(ctx, &found, d_best, 1);
     if (rc) break;

@@ -255,6 +255,91 @@ def test_large_batch_properties_2p20(ctx, m):
     bsum.free()
 
 
+def test_config3_commit_2p20x400_properties(ctx, m):
+    """BASELINE.json configs[2]: the 2^20 rows x 400 columns commit at full size (33.6 GB on the device).  No oracle
+    run at this size; size-independent properties instead: sampled leaves open against the cap (oracle hashing of
+    the 400-wide leaf, 19 siblings), the coefficients interpolate the input values, the LDE is their evaluation on
+    the shifted coset, and a column's LDE does not depend on the batch around it."""
+    import torch
+
+    log_n, rate, n_cols = 20, 3, 400
+    n, log_N = 1 << log_n, log_n + rate
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 60 << 30:
+        pytest.skip("needs ~45 GB of free device memory")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(400)
+    vals = torch.empty((n_cols, n), dtype=torch.int64, device="cuda")
+    vals.random_(0, 2**62, generator=g)
+    vals[3] -= 2**62  # a column of u64 values >= 2^63, with two explicit non-canonical ones (2^64 - 1 and p itself)
+    vals[3, 0] = -1
+    vals[3, 1] = -(2**32) + 1
+    torch.cuda.synchronize()  # the library works on its own stream
+    batch = m.PolynomialBatch.from_values_device(ctx, vals.data_ptr(), n_cols, log_n, rate, 4)
+    cap = batch.cap
+    assert cap.shape == (16, 4)
+    w = O.root_of_unity(log_N)
+    wn = O.root_of_unity(log_n)
+    cols = (0, 3, 399)
+    coeffs = {c: batch.coeffs(c) for c in cols}
+    for c in cols:
+        assert (coeffs[c] < np.uint64(P)).all()
+    samples = (0, 1, (1 << log_N) - 1, 5 << 19, 1234567)
+    for j in samples:
+        leaf = batch.leaf(j)
+        assert leaf.shape == (n_cols,) and (leaf < np.uint64(P)).all()
+        sib = batch.merkle_tree.prove(j)
+        assert sib.shape == (log_N - 4, 4)
+        assert O.merkle_verify(leaf, j, sib, cap)
+        bad = leaf.copy()
+        bad[217] ^= np.uint64(1)
+        assert not O.merkle_verify(bad, j, sib, cap)
+    for c in cols:
+        col_vals = vals[c].cpu().numpy().view(np.uint64)
+        for i in (0, 1, 777777):  # ifft really inverts
+            assert _horner(coeffs[c], pow(wn, i, P)) == int(col_vals[i]) % P
+        j = samples[-1]  # leaf j = the evaluation at 7 w^bitrev(j)
+        assert int(batch.leaf(j)[c]) == _horner(coeffs[c], 7 * pow(w, bitrev(j, log_N), P) % P)
+    sub = torch.stack([vals[c] for c in cols]).contiguous()
+    torch.cuda.synchronize()
+    small = m.PolynomialBatch.from_values_device(ctx, sub.data_ptr(), len(cols), log_n, rate, 4)
+    for j in samples:
+        big_leaf, small_leaf = batch.leaf(j), small.leaf(j)
+        for k, c in enumerate(cols):
+            assert big_leaf[c] == small_leaf[k]
+    small.free()
+    batch.free()
+    del vals, sub
+    torch.cuda.empty_cache()
+
+
+def test_config3_fri_commit_2p23_bit_exact(ctx, m):
+    """BASELINE.json configs[2], FRI part: fri_committed_trees over an extension polynomial of 8n = 2^23 points with
+    reduction_arity_bits [4,4,4,4] — the whole commit phase against the oracle (about ten seconds of CPU): caps,
+    final polynomial, transcript, sampled leaves and paths of every layer."""
+    log_n, rate_bits, cap_height, arity_bits = 20, 3, 4, [4, 4, 4, 4]
+    n = 1 << log_n
+    N = n << rate_bits
+    coeffs = np.zeros((N, 2), np.uint64)
+    coeffs[:n] = rand_felts(2023, (n, 2))
+    values = O.ext_coset_fft(coeffs, 7)
+    oc = O.Challenger()
+    oc.observe([1, 2, 3, 4])
+    ref = O.fri_committed_trees(coeffs, values, arity_bits, oc, rate_bits, cap_height)
+    gc = m.Challenger(ctx)
+    gc.observe_elements([1, 2, 3, 4])
+    trees, final = m.fri_committed_trees(ctx, coeffs, values, gc, arity_bits, rate_bits, cap_height)
+    assert final.shape == (16, 2) and (final == ref["final_poly"]).all()
+    assert len(trees) == 4
+    for l, t in enumerate(trees):
+        assert t.n_leaves == N >> (4 * (l + 1))
+        assert (t.cap == ref["caps"][l]).all(), l
+        for j in sorted({0, t.n_leaves - 1, t.n_leaves // 3}):
+            assert (t.get(j) == ref["leaves"][l][j]).all()
+            assert (t.prove(j) == O.merkle_prove(ref["digests"][l], t.n_leaves, cap_height, j)).all()
+    assert gc.export_state()[:12].tolist() == oc.state_words()[0]
+
+
 # ----------------------------------------------------------------------------- Challenger / FRI
 def test_challenger_matches_oracle(ctx, m):
     rng = np.random.default_rng(3)

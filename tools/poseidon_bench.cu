@@ -65,6 +65,34 @@ __global__ void k_single_latency(uint64_t* io, int iters, long long* cycles) {
   *cycles = (t1 - t0) / iters;
 }
 
+// dependent chains on one warp: cycles per field multiplication / per S-box
+template <int V>
+__global__ void k_mul_chain(uint64_t* io, int iters, long long* cycles) {
+  uint64_t x = io[threadIdx.x];
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+    if (V == 0) x = gl::mul_nc(x, x);
+    if (V == 2) x = poseidon::sbox7(x);
+    if (V == 4) x = gl::mad_nc(x, 0x123456789abcdef1ull, x);
+  }
+  long long t1 = clock64();
+  io[threadIdx.x] = x;
+  if (threadIdx.x == 0) *cycles = (t1 - t0) / iters;
+}
+
+// the two halves of the warp-cooperative permutation on their own
+__global__ void k_coop_parts(uint64_t* io, int iters, long long* cycles) {
+  const uint32_t l = threadIdx.x & 15;
+  uint64_t s = io[threadIdx.x];
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) s = poseidon::coop_partial_rounds(s, l);
+  long long t1 = clock64();
+  for (int it = 0; it < iters; it++) s = poseidon::coop_mds(poseidon::sbox7(gl::add_nc(s, poseidon::RC_G[l & 7])), l);
+  long long t2 = clock64();
+  io[threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[0] = (t1 - t0) / iters, cycles[1] = (t2 - t1) / iters;
+}
+
 int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
@@ -80,6 +108,29 @@ int main() {
       cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
     }
     printf("coop permutation latency: %lld cycles\n", hc);
+    k_coop_latency<<<1, 32>>>(d, 1, dc);  // one permutation per launch: cold L1 for the coefficient tables
+    cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    printf("coop permutation latency, single permutation in a fresh launch: %lld cycles\n", hc);
+    {
+      long long* dc2;
+      cudaMalloc(&dc2, 16);
+      long long h2[2] = {0, 0};
+      for (int rep = 0; rep < 2; rep++) {
+        k_coop_parts<<<1, 32>>>(d, 64, dc2);
+        cudaMemcpy(h2, dc2, 16, cudaMemcpyDeviceToHost);
+      }
+      printf("coop: 22 linearised partial rounds %lld cycles, one full round %lld cycles\n", h2[0], h2[1]);
+    }
+    const char* names[6] = {"mul_nc", "", "sbox7", "", "mad_nc", ""};
+    for (int v = 0; v < 6; v += 2) {
+      for (int rep = 0; rep < 2; rep++) {
+        if (v == 0) k_mul_chain<0><<<1, 32>>>(d, 512, dc);
+        if (v == 2) k_mul_chain<2><<<1, 32>>>(d, 512, dc);
+        if (v == 4) k_mul_chain<4><<<1, 32>>>(d, 512, dc);
+        cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+      }
+      printf("dependent chain, one warp: %s %lld cycles\n", names[v], hc);
+    }
     for (int rep = 0; rep < 2; rep++) {
       k_single_latency<<<1, 1>>>(d, 16, dc);
       cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);

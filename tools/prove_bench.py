@@ -15,7 +15,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import city_rollup_b200 as m  # noqa: E402
 
 
-def build_case(degree_bits=12, seed=7):
+def build_case(degree_bits=12, seed=7, device=0):
     """synthetic satisfiable circuit over the whole gate set (tests/plonk_ref.py is the witness generator; the
     public-inputs hash comes from the GPU library, not from the oracle)"""
     import plonk_ref as R
@@ -30,7 +30,7 @@ def build_case(degree_bits=12, seed=7):
              (R.GATE_POSEIDON, 0, 0)]
     groups = [(0, 6), (6, 10), (10, 12), (12, 13)]
     pis = [seed, 2, 3, 4]
-    c = m.Context(0)
+    c = m.Context(device)
     pih = [int(x) for x in c.hash_no_pad(pis)]
     c.close()
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed, pi_hash=pih)
