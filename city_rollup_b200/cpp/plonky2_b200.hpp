@@ -37,6 +37,8 @@ class Context {
     if (rc != P2B_OK) throw Error(rc, p2b_last_error(h_));
   }
   p2b_ctx* get() const { return h_; }
+  // sleep instead of spinning while waiting for the device (more proving threads than host cores)
+  void set_blocking_sync(bool on) const { check(p2b_set_blocking_sync(h_, on ? 1 : 0)); }
 
  private:
   p2b_ctx* h_ = nullptr;

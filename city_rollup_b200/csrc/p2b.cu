@@ -42,6 +42,10 @@ struct p2b_ctx {
   uint64_t* h_upload[2] = {nullptr, nullptr};
   cudaEvent_t upload_done[2] = {nullptr, nullptr};
   int upload_half = 0;
+  // host waits: spin (cudaStreamSynchronize, lowest latency, one busy core per waiting thread) or sleep on a
+  // blocking-sync event (p2b_set_blocking_sync: many contexts per host core)
+  bool blocking_sync = false;
+  cudaEvent_t ev_block = nullptr;
   bool poisoned = false;
   std::string err;
   uint64_t launches = 0;
@@ -202,6 +206,17 @@ static void stage_begin(p2b_ctx* ctx, int stage) {
   cudaEventRecord(ctx->cur_ev, ctx->stream);
 }
 
+// every host wait on the context's stream goes through here
+static cudaError_t ctx_sync(p2b_ctx* ctx) {
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+  if (!ctx->ev_block) {
+    cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_block);
+}
+
 extern "C" int p2b_profile_enable(p2b_ctx* ctx, int on) {
   CHECK_CTX(ctx);
   stage_end(ctx);
@@ -212,7 +227,7 @@ extern "C" int p2b_profile_read(p2b_ctx* ctx, float* ms_out, uint64_t* count_out
   CHECK_CTX(ctx);
   if (!ms_out) return P2B_ERR_INVALID;
   stage_end(ctx);
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   for (auto& r : ctx->recs) {
     float ms = 0;
     CU(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
@@ -265,7 +280,7 @@ static int ctx_setup(p2b_ctx* ctx) {
   LAUNCH_CHECK(ctx);
   ctx->h_stage_bytes = 1 << 20;
   CU(ctx, cudaMallocHost((void**)&ctx->h_stage, ctx->h_stage_bytes));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   ctx->launches = 0;
   return P2B_OK;
 }
@@ -284,6 +299,7 @@ static int init_common(int device, void* stream, bool borrow, p2b_ctx** out) {
   p2b_ctx* ctx = new (std::nothrow) p2b_ctx();
   if (!ctx) return fail(nullptr, P2B_ERR_OOM, "host allocation failed");
   ctx->device = device;
+  if (const char* m = getenv("P2B_SYNC")) ctx->blocking_sync = m[0] == 'b' || m[0] == 'B';  // P2B_SYNC=block | spin
   if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0)
     ctx->sm_count = 148;
   if (borrow) {
@@ -314,7 +330,7 @@ extern "C" int p2b_init_on_stream(int device, void* cuda_stream, p2b_ctx** out) 
 extern "C" void p2b_destroy(p2b_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  ctx_sync(ctx);
   dfree(ctx, ctx->d_w12);
   dfree(ctx, ctx->d_rlo);
   dfree(ctx, ctx->d_rhi);
@@ -327,13 +343,14 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
     if (ctx->h_upload[i]) cudaFreeHost(ctx->h_upload[i]);
     if (ctx->upload_done[i]) cudaEventDestroy(ctx->upload_done[i]);
   }
-  cudaStreamSynchronize(ctx->stream);
+  ctx_sync(ctx);
   for (auto& r : ctx->recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->cur_ev) cudaEventDestroy(ctx->cur_ev);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
@@ -345,9 +362,15 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
 
 extern "C" const char* p2b_last_error(const p2b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 
+extern "C" int p2b_set_blocking_sync(p2b_ctx* ctx, int on) {
+  CHECK_CTX(ctx);
+  ctx->blocking_sync = on != 0;
+  return P2B_OK;
+}
+
 extern "C" int p2b_synchronize(p2b_ctx* ctx) {
   CHECK_CTX(ctx);
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   return P2B_OK;
 }
 
@@ -379,9 +402,20 @@ extern "C" int p2b_timer_stop_ms(p2b_ctx* ctx, float* ms_out) {
 }
 
 // copy `n` u64 from device to a caller (pageable or pinned) buffer, synchronously
+// Device -> caller's buffer.  The caller's memory is normally pageable (a Rust Vec, a numpy array), and a copy into
+// pageable memory makes the driver spin inside cudaMemcpyAsync until everything queued before it has run — for
+// p2b_prove that is the whole proof.  Small results (caps, challenges, a 130 KB proof) therefore land in the
+// context's pinned staging buffer first, the wait goes through ctx_sync (which can sleep), then one memcpy.
 static int d2h(p2b_ctx* ctx, uint64_t* dst, const uint64_t* d_src, size_t n) {
-  CU(ctx, cudaMemcpyAsync(dst, d_src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t bytes = n * sizeof(uint64_t);
+  if (ctx->h_stage && bytes <= ctx->h_stage_bytes) {
+    CU(ctx, cudaMemcpyAsync(ctx->h_stage, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, ctx_sync(ctx));
+    memcpy(dst, ctx->h_stage, bytes);
+    return P2B_OK;
+  }
+  CU(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   return P2B_OK;
 }
 
@@ -1211,7 +1245,7 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
       e = cudaMemcpyAsync(c->d_zh, zh.data(), zh.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(c->d_k_is, d.k_is, d.num_routed_wires * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ctx_sync(ctx);
     if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "circuit upload: %s", cudaGetErrorString(e));
   }
   if (rc != P2B_OK) {
@@ -1656,7 +1690,7 @@ extern "C" int p2b_challenger_observe(p2b_challenger* c, const uint64_t* elems, 
   CU(ctx, cudaMemcpyAsync(d, elems, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   rc = challenger_observe_dev(c, d, n);
   // the H2D source may be pageable and reused by the caller right after we return
-  if (rc == P2B_OK) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (rc == P2B_OK) CU(ctx, ctx_sync(ctx));
   dfree(ctx, d);
   return rc;
 }
@@ -1696,7 +1730,7 @@ extern "C" int p2b_challenger_import(p2b_challenger* c, const uint64_t* in30) {
   CHECK_CTX(ctx);
   if (in30[12] > 8 || in30[21] > 8) return fail(ctx, P2B_ERR_INVALID, "buffer length > 8");
   CU(ctx, cudaMemcpyAsync(c->d_state, in30, frik::CH_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   return P2B_OK;
 }
 
@@ -1852,7 +1886,7 @@ extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const ui
                          d_final);
   if (rc == P2B_OK) {
     cudaError_t e = cudaMemcpyAsync(final_poly_out, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ctx_sync(ctx);
     if (e != cudaSuccess) {
       rc = fail(ctx, P2B_ERR_CUDA, "download: %s", cudaGetErrorString(e));
       for (p2b_tree* t : trees) p2b_tree_free(t);
@@ -1904,7 +1938,7 @@ extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, 
     frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 1, d_w + 1);
     ctx->launches++;
   }
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   dfree(ctx, d_w);
   *witness_out = found;
   return rc;
@@ -2295,8 +2329,7 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     CUP(cudaMemcpyAsync(d_proof + off, d_pis, n_public_inputs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   off += n_public_inputs;
   if (off != proof_len) return cleanup(fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
-  CUP(cudaMemcpyAsync(proof_out, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUP(cudaStreamSynchronize(ctx->stream));
+  TRY(d2h(ctx, proof_out, d_proof, proof_len));
   return cleanup(P2B_OK);
 #undef TRY
 #undef CUP

@@ -56,6 +56,10 @@ class Context:
         if rc != 0:
             raise P2BError(rc, self.lib.p2b_last_error(self.h).decode())
 
+    def set_blocking_sync(self, on=True):
+        """sleep instead of spinning while waiting for the device (many proving threads per host core)"""
+        self.check(self.lib.p2b_set_blocking_sync(self.h, 1 if on else 0))
+
     def synchronize(self):
         self.check(self.lib.p2b_synchronize(self.h))
 

@@ -59,6 +59,11 @@ void p2b_destroy(p2b_ctx *ctx);
 const char *p2b_last_error(const p2b_ctx *ctx);
 /* Blocks until all work enqueued on the context's stream has finished. */
 int p2b_synchronize(p2b_ctx *ctx);
+/* How the calling thread waits for the device inside the library: 0 (default) spins — lowest latency, the right
+ * choice for the reference's model of one worker process per GPU (city_rollup_core_worker/src/lib.rs:131-145); 1
+ * sleeps on a blocking-sync event, for hosts that run more proving threads than they have cores (several contexts
+ * per GPU times several GPUs).  The environment variable P2B_SYNC=block|spin sets the default of new contexts. */
+int p2b_set_blocking_sync(p2b_ctx *ctx, int on);
 /* Pinned host memory for inputs/outputs that should move by DMA without staging. */
 int p2b_host_alloc(p2b_ctx *ctx, size_t bytes, void **out);
 int p2b_host_free(p2b_ctx *ctx, void *p);

@@ -36,6 +36,7 @@ pub struct p2b_fri_params {
 extern "C" {
     pub fn p2b_version() -> c_int;
     pub fn p2b_init(device: c_int, out: *mut *mut p2b_ctx) -> c_int;
+    pub fn p2b_set_blocking_sync(ctx: *mut p2b_ctx, on: c_int) -> c_int;
     pub fn p2b_init_on_stream(device: c_int, stream: *mut c_void, out: *mut *mut p2b_ctx) -> c_int;
     pub fn p2b_destroy(ctx: *mut p2b_ctx);
     pub fn p2b_last_error(ctx: *const p2b_ctx) -> *const c_char;

@@ -78,6 +78,7 @@ int main(int argc, char** argv) {
     for (int t = 0; t < threads; t++) {
       pool.emplace_back([&, t] {
         Context ctx(device);
+        if (threads > 1) ctx.set_blocking_sync(true);  // several workers per GPU: sleep while waiting, do not spin
         CircuitData circuit(ctx, cs.desc, cs.gates, cs.k_is);
         PolynomialBatch constants_sigmas =
             PolynomialBatch::from_values(ctx, cs.cs_values, cs.params.rate_bits, false, cs.params.cap_height, true);

@@ -37,9 +37,13 @@ def build_case(degree_bits=12, seed=7, device=0):
     return circ, [1, 2, 3, 4], pis
 
 
-def run(n_ctx, n_proofs, circ, digest, pis, device=0):
+def run(n_ctx, n_proofs, circ, digest, pis, device=0, blocking=None, stats=None):
+    """blocking: None = the library default (spin, or P2B_SYNC); stats (dict) receives the host CPU seconds per proof"""
     params = m.FriParams(3, 4, 16, 28, [4, 4])
     ctxs = [m.Context(device) for _ in range(n_ctx)]
+    if blocking is not None:
+        for c in ctxs:
+            c.set_blocking_sync(blocking)
     state = []
     for c in ctxs:
         cd = m.CircuitData(c, circ.desc())
@@ -65,11 +69,14 @@ def run(n_ctx, n_proofs, circ, digest, pis, device=0):
     per = n_proofs // n_ctx
     th = [threading.Thread(target=worker, args=(i, per)) for i in range(n_ctx)]
     t0 = time.perf_counter()
+    c0 = time.process_time()
     for t in th:
         t.start()
     for t in th:
         t.join()
     dt = time.perf_counter() - t0
+    if stats is not None:
+        stats["cpu_s_per_proof"] = (time.process_time() - c0) / (per * n_ctx)
     for (cd, cs), c in zip(state, ctxs):
         cs.free()
         cd.free()
@@ -81,8 +88,12 @@ if __name__ == "__main__":
     circ, digest, pis = build_case()
     out = {}
     for n_ctx in (1, 2, 4, 8, 12):
-        pps, ms = run(n_ctx, 48 * n_ctx, circ, digest, pis)
-        out[f"ctx{n_ctx}"] = {"proofs_per_s": round(pps, 2), "ms_per_proof_per_ctx": round(ms, 2)}
+        for blocking in (False, True):
+            st = {}
+            pps, ms = run(n_ctx, 48 * n_ctx, circ, digest, pis, blocking=blocking, stats=st)
+            out[f"ctx{n_ctx}_{'block' if blocking else 'spin'}"] = {
+                "proofs_per_s": round(pps, 2), "ms_per_proof_per_ctx": round(ms, 2),
+                "host_cpu_ms_per_proof": round(st["cpu_s_per_proof"] * 1e3, 2)}
     # stage profile of one proof
     c = m.Context(0)
     cd = m.CircuitData(c, circ.desc())
