@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <new>
 #include <string>
@@ -2265,25 +2266,49 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
            *d_alphas = d_gammas + nch, *d_zeta = d_alphas + nch, *d_zeta_next = d_zeta + 2;
   TRY(dmalloc(ctx, &d_proof, proof_len));
   // public_inputs_hash = PoseidonHash::hash_no_pad(public_inputs)
+  // P2B_TRACE=1: phase-by-phase wall clock of one proof on stderr (each mark synchronises, so the phases are
+  // serialised GPU time + host time; a development aid, never on in measurements)
+  static const bool trace = getenv("P2B_TRACE") != nullptr;
+  auto now_us = [] {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  };
+  double t_prev = trace ? now_us() : 0, t_enq = t_prev;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const double t_e = now_us();
+    cudaStreamSynchronize(ctx->stream);
+    const double t = now_us();
+    fprintf(stderr, "[p2b_prove] %-22s enqueue %8.1f us, done +%8.1f us (phase %8.1f us)\n", what, t_e - t_enq, t - t_e, t - t_prev);
+    t_prev = t_enq = t;
+  };
   TRY(upload_felts(ctx, public_inputs, n_public_inputs, &d_pis));
   hashk::k_hash_no_pad_single<<<1, 32, 0, ctx->stream>>>(d_pis, n_public_inputs, d_pih);
   ctx->launches++;
+  mark("setup + pi hash");
   // wires commitment
   TRY(batch_from_host(ctx, wire_cols, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
+  mark("wires commit");
   TRY(p2b_challenger_new(ctx, &ch));
   TRY(challenger_observe_dev(ch, d_digest, 4));
   TRY(challenger_observe_dev(ch, d_pih, 4));
   TRY(p2b_challenger_observe_cap(ch, &wires->tree));
   frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2 * nch, d_betas);  // betas then gammas
   ctx->launches++;
+  mark("transcript: betas");
   TRY(zs_pp_core(ctx, c, cs, wires, d_betas, d_gammas, rb, caph, &zs));
+  mark("zs/pp + commit");
   TRY(p2b_challenger_observe_cap(ch, &zs->tree));
   frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, nch, d_alphas);
   ctx->launches++;
+  mark("transcript: alphas");
   TRY(quotient_core(ctx, c, cs, wires, zs, d_pih, d_betas, d_gammas, d_alphas, rb, caph, &qt));
+  mark("quotient + commit");
   TRY(p2b_challenger_observe_cap(ch, &qt->tree));
   frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_zeta);
   ctx->launches++;
+  mark("transcript: zeta");
   {
     const uint64_t G = 1753635133440165772ull;
     const uint64_t g = d.degree_bits ? h_powmod(G, (uint64_t)1 << (32 - d.degree_bits)) : 1;
@@ -2310,11 +2335,13 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   TRY(eval_ext_core(ctx, zs, d_zeta_next, 0, nch, o_zs_next));
   TRY(eval_ext_core(ctx, zs, d_zeta, nch, w_zs - nch, o_pp));
   TRY(eval_ext_core(ctx, qt, d_zeta, 0, w_q, o_quot));
+  mark("openings");
   off += 2 * (cs->n_cols + d.num_wires + w_zs + nch + w_q);
   // challenger.observe_openings(&openings.to_fri_openings()): the zeta batch in FRI order, then zs_next
   TRY(challenger_observe_dev(ch, o_constants, 2 * (cs->n_cols + d.num_wires + nch)));
   TRY(challenger_observe_dev(ch, o_pp, 2 * (w_zs - nch + w_q)));
   TRY(challenger_observe_dev(ch, o_zs_next, 2 * (size_t)nch));
+  mark("transcript: openings");
   // FRI instance (CommonCircuitData::get_fri_instance): everything at zeta, the Zs again at g * zeta
   const p2b_batch* oracles[4] = {cs, wires, zs, qt};
   p2b_fri_batch fb[2] = {};
@@ -2324,6 +2351,7 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   fb[1].ranges[0] = {2, 0, nch};
   TRY(check_fri_params(ctx, oracles, 4, fp));
   TRY(prove_openings_core(ctx, oracles, 4, fb, 2, d_zeta, ch, fp, d_proof + off));  // d_zeta | d_zeta_next are adjacent
+  mark("prove_openings (FRI)");
   off += fri_len;
   if (n_public_inputs)
     CUP(cudaMemcpyAsync(d_proof + off, d_pis, n_public_inputs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
