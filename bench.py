@@ -208,7 +208,7 @@ def run_cuda(args):
 
     def step_e2e(i):
         h = host[i & 1]
-        b = m.PolynomialBatch.from_values(ctx, [h[c] for c in range(N_COLS)], RATE_BITS, False, CAP_HEIGHT)
+        b = m.PolynomialBatch.from_values(ctx, h, RATE_BITS, False, CAP_HEIGHT)  # rows of the pinned matrix = columns
         cap = b.cap  # D2H of the result (16 digests), synchronises
         b.free()
         return cap

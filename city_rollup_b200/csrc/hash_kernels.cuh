@@ -62,6 +62,45 @@ k_leaf_hash_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint3
   store_digest(digests + 4 * j, out);
 }
 
+// The same sponge in column ranges: absorbs columns [c_begin, c_end) (c_begin a multiple of 8) of every leaf into a
+// sponge state kept in HBM between launches (state[i * n_leaves + j], i < 12: coalesced), starting from zero when
+// c_begin == 0 and writing the digest instead of the state when c_end == n_cols.  Used by the pipelined host upload
+// (p2b.cu batch_from_host_pipelined): leaf hashing of the columns that have arrived overlaps the upload of the rest.
+// Only for n_cols > 4 (hash_or_noop's copy case never gets here).
+__global__ void __launch_bounds__(256, 3)
+k_leaf_absorb_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t c_begin, uint32_t c_end,
+                       uint32_t n_cols, size_t n_leaves, uint64_t* __restrict__ state, uint64_t* __restrict__ digests) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_leaves) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = c_begin == 0 ? 0 : state[(size_t)i * n_leaves + j];
+  uint64_t nxt[8];
+  const uint64_t* p = data + j;
+#pragma unroll
+  for (int i = 0; i < 8; i++) nxt[i] = c_begin + i < c_end ? p[(size_t)(c_begin + i) * col_stride] : 0;
+  for (uint32_t c0 = c_begin; c0 < c_end; c0 += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (c0 + i < c_end) s[i] = nxt[i];
+    if (c0 + 8 < c_end) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (c0 + 8 + i < c_end) nxt[i] = p[(size_t)(c0 + 8 + i) * col_stride];
+    }
+    poseidon::permute_nc(s);
+  }
+  if (c_end == n_cols) {
+    uint64_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+    store_digest(digests + 4 * j, out);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; i++) state[(size_t)i * n_leaves + j] = s[i];
+  }
+}
+
 // Leaf digests of row-major leaves (MerkleTree::new's own input layout; FRI layer leaves).
 __global__ void __launch_bounds__(256)
 k_leaf_hash_rowmajor(const uint64_t* __restrict__ leaves, size_t leaf_len, size_t n_leaves,

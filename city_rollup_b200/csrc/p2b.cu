@@ -986,36 +986,72 @@ static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, 
   if (!ev0) return bail(fail(ctx, P2B_ERR_CUDA, "cudaEventCreate failed"));
   if (cudaEventRecord(ev0, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ev0, 0) != cudaSuccess)
     return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));
+  // The leaf sponge runs in column ranges as well (hashk::k_leaf_absorb_colmajor, state carried in HBM): the upload
+  // is the slower side of the copy/transform pipeline, so without this the GPU idles for most of the transfer and
+  // then hashes for 7 ms; with it the hashing of the first columns covers the rest of the upload.  Ranges of 48
+  // columns (6 permutations per leaf and launch) keep the number of launch tails small.
+  p2b_tree* t = &b->tree;
+  t->ctx = ctx;
+  t->n_leaves = N;
+  t->log_leaves = log_n + rate_bits;
+  t->cap_height = cap_height;
+  t->leaf_len = n_cols;
+  t->d_leaves_cm = b->d_lde;
+  uint64_t* d_sponge = nullptr;
+  rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(N, cap_height));
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_sponge, 12 * N);
+  if (rc) {
+    dfree(ctx, d_sponge);
+    return bail(rc);
+  }
+  const size_t hash_span = 48;
+  size_t hashed = 0;
   stage_begin(ctx, ST_H2D);
   size_t gi = 0;
   for (size_t c0 = 0; c0 < n_cols; c0 += group, gi++) {
     const size_t c1 = c0 + group < n_cols ? c0 + group : n_cols;
     rc = h2d_cols(ctx, ctx->copy_stream, cols, c0, c1, n, d_in);
-    if (rc) return bail(rc);
+    if (rc) break;
     cudaEvent_t ev = copy_event(ctx, gi + 1);
-    if (!ev || cudaEventRecord(ev, ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ev, 0) != cudaSuccess)
-      return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));
+    if (!ev || cudaEventRecord(ev, ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ev, 0) != cudaSuccess) {
+      rc = fail(ctx, P2B_ERR_CUDA, "event setup failed");
+      break;
+    }
     const size_t k = c1 - c0;
     if (is_values) {
       stage_begin(ctx, ST_INTT);
       rc = run_intt(ctx, d_in + c0 * n, b->d_coeffs + c0 * n, b->d_lde + c0 * N, k, log_n, N);
-      if (rc) return bail(rc);
+      if (rc) break;
     }
     stage_begin(ctx, ST_LDE);
     rc = run_lde(ctx, b->d_coeffs + c0 * n, n, b->d_lde + c0 * N, k, log_n, rate_bits, 7);
-    if (rc) return bail(rc);
+    if (rc) break;
+    if (c1 == n_cols || c1 - hashed >= hash_span) {  // group boundaries are multiples of 16, hence of the rate 8
+      stage_begin(ctx, ST_LEAF);
+      hashk::k_leaf_absorb_colmajor<<<cdiv(N, 256), 256, 0, ctx->stream>>>(b->d_lde, N, (uint32_t)hashed, (uint32_t)c1,
+                                                                         (uint32_t)n_cols, N, d_sponge, t->d_levels);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) {
+        rc = fail(ctx, P2B_ERR_CUDA, "k_leaf_absorb_colmajor launch failed");
+        break;
+      }
+      hashed = c1;
+    }
   }
+  dfree(ctx, d_sponge);
+  if (rc) {
+    stage_end(ctx);
+    return bail(rc);
+  }
+  stage_begin(ctx, ST_TREE);
+  rc = build_levels(ctx, t);
   stage_end(ctx);
+  if (rc) return bail(rc);
   if (is_values) {
     if (keep_values)
       b->d_values = d_in;
     else
       dfree(ctx, d_in);
-  }
-  rc = tree_from_colmajor(ctx, &b->tree, b->d_lde, N, log_n + rate_bits, n_cols, cap_height);
-  if (rc != P2B_OK) {
-    d_in = nullptr;
-    return bail(rc);
   }
   *out = b;
   return P2B_OK;

@@ -55,7 +55,7 @@ def run(n_ctx, n_proofs, circ, digest, pis, device=0, blocking=None, stats=None)
         w = c.pinned_empty((len(wv), wv[0].size))
         for j, col in enumerate(wv):
             w[j] = col
-        wires.append([w[j] for j in range(len(wv))])
+        wires.append(w)  # the (n_wires, n) matrix itself: its rows are the witness columns
 
     def worker(i, k):
         c = ctxs[i]
