@@ -236,8 +236,42 @@ inline PolynomialBatch compute_quotient_polys(const Context& ctx, const CircuitD
   return PolynomialBatch(ctx, out);
 }
 
+// Pinned host matrix (p2b_host_alloc): witness columns written here go to the device by one DMA instead of being
+// staged through the context's pinned double buffer.  Row r = column r of the batch.
+class PinnedColumns {
+ public:
+  PinnedColumns(const Context& ctx, size_t n_cols, size_t n) : ctx_(&ctx), n_cols_(n_cols), n_(n) {
+    void* p = nullptr;
+    ctx.check(p2b_host_alloc(ctx.get(), n_cols * n * sizeof(F), &p));
+    base_ = static_cast<F*>(p);
+    for (size_t c = 0; c < n_cols; c++) ptrs_.push_back(base_ + c * n);
+  }
+  ~PinnedColumns() { p2b_host_free(ctx_->get(), base_); }
+  PinnedColumns(const PinnedColumns&) = delete;
+  F* column(size_t c) { return base_ + c * n_; }
+  void fill(const std::vector<std::vector<F>>& cols) {
+    for (size_t c = 0; c < n_cols_ && c < cols.size(); c++) std::copy(cols[c].begin(), cols[c].end(), column(c));
+  }
+  const std::vector<const F*>& pointers() const { return ptrs_; }
+
+ private:
+  const Context* ctx_;
+  size_t n_cols_, n_;
+  F* base_ = nullptr;
+  std::vector<const F*> ptrs_;
+};
+
 // plonk::prover::prove_with_partition_witness after witness generation, one library call; returns the flat proof words
-// (ProofWithPublicInputs field order, include/p2b.h)
+// (ProofWithPublicInputs field order, include/p2b.h).  wire_cols: one pointer per witness column.
+inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
+                            const HashOut& circuit_digest, const std::vector<const F*>& wire_cols,
+                            const std::vector<F>& public_inputs, const p2b_fri_params& params) {
+  std::vector<F> out(p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size()));
+  if (out.empty()) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
+  ctx.check(p2b_prove(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), wire_cols.data(), public_inputs.data(),
+                      public_inputs.size(), &params, out.data(), out.size()));
+  return out;
+}
 inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
                             const HashOut& circuit_digest, const std::vector<std::vector<F>>& wire_values,
                             const std::vector<F>& public_inputs, const p2b_fri_params& params) {

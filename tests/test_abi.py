@@ -63,7 +63,7 @@ def test_product_never_imports_oracle():
 
 def test_cpp_host_mirror_compiles(lib, tmp_path):
     """the header-only C++ mirror (city_rollup_b200/cpp/plonky2_b200.hpp) and the native job loop built on it
-    (tools/prove_bench.cpp) compile and link against libp2b.so"""
+    (tools/prove_bench.cpp, tools/qbench_replay.cpp) compile and link against libp2b.so"""
     import shutil
     import subprocess
 
@@ -71,7 +71,8 @@ def test_cpp_host_mirror_compiles(lib, tmp_path):
 
     if not shutil.which("g++"):
         pytest.skip("no g++")
-    out = tmp_path / "prove_bench_cpp"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", ROOT, os.path.join(ROOT, "tools", "prove_bench.cpp"),
-                           "-L", os.path.dirname(m.SO_PATH), "-lp2b", "-lpthread", "-o", str(out)])
-    assert out.exists()
+    for src in ("prove_bench.cpp", "qbench_replay.cpp"):
+        out = tmp_path / src.replace(".cpp", "")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", ROOT, os.path.join(ROOT, "tools", src),
+                               "-L", os.path.dirname(m.SO_PATH), "-lp2b", "-lpthread", "-o", str(out)])
+        assert out.exists()

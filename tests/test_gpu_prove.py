@@ -1,6 +1,8 @@
 """GPU: the complete prover flow behind the C ABI (wires commit -> Z / partial products -> quotient -> openings ->
 prove_openings: final polynomial, FRI commit phase, proof of work, query rounds) against the oracle-built proof
 (tests/verifier_ref.py::oracle_prove), word for word, and through the restated plonky2 verifier."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,7 @@ from test_plonk_oracle import ALL_GATES, RECURSION_GATES, RECURSION_GROUPS
 from test_prove_oracle import FP_SMALL, make_case
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FULL_GROUPS = [(0, 4), (4, 5), (5, 8), (8, 10)]
 # the FRI / Plonk parameters of every stored City Rollup proof (city_common_circuit/src/circuits/zk_signature2/mod.rs:33-57)
 FP_CITY = dict(rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, reduction_arity_bits=[4, 4])
@@ -96,3 +99,35 @@ def test_gpu_proof_2p14_rows_verifies(ctx, m):
         V.verify(circ, cs.cap, digest, bad, fp)
     cs.free()
     cd.free()
+
+
+def test_qbench_replay_native_job_loop(ctx, m, tmp_path):
+    """tools/qbench_replay.cpp: the reference's level-counter job DAG (43 jobs / 67 proofs of a block shaped like
+    qbench_data/example.bin) through the C++ mirror on worker threads; every proof must equal the expected words, every
+    job must leave its bincode proof in the store, and the benchmark file must have the reference's
+    QWorkerJobBenchmark format (city_rollup_common/src/qworker/job_id.rs:194-202)."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    case = tmp_path / "case.bin"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_prove_case.py"), str(case), "10"])
+    exe = tmp_path / "qbench_replay"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", ROOT, os.path.join(ROOT, "tools", "qbench_replay.cpp"), "-L",
+                           os.path.dirname(m.SO_PATH), "-lp2b", "-lpthread", "-o", str(exe)])
+    out = tmp_path / "bench.json"
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(m.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    res = subprocess.run([str(exe), "-i", str(case), "-o", str(out), "-n", "2", "--contexts", "3"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr + res.stdout
+    summary = json.loads(res.stdout.strip().splitlines()[-1])
+    assert summary["jobs"] == summary["jobs_recorded"] == summary["stored_proofs"] == 2 * 43
+    assert summary["proofs"] == 2 * 67 and summary["mismatching_proofs"] == 0
+    bench = json.load(open(out))
+    assert len(bench) == 2 * 43
+    ids = {b["job_id"] for b in bench}
+    assert len(ids) == 2 * 43 and all(len(i) == 48 and i.startswith("00") for i in ids)
+    assert all(isinstance(b["duration"], int) for b in bench)
