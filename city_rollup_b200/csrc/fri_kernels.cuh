@@ -15,14 +15,13 @@ constexpr int CH_WORDS = 30;
 constexpr int CH_NIN = 12, CH_IN = 13, CH_NOUT = 21, CH_OUT = 22;
 
 // Challenger::duplexing on a state held in shared memory, one permutation shared by the warp
-// (poseidon::coop_permute_nc); all 32 lanes call, lanes 16..31 mirror 0..15
+// (poseidon::coop_permute_nc); all 32 lanes call
 __device__ __forceinline__ void duplexing_coop(uint64_t* st, uint32_t lane) {
-  const uint32_t l = lane & 15;
   const uint32_t n_in = (uint32_t)st[CH_NIN];
-  uint64_t s = l < 12 ? st[l] : 0;
-  if (l < n_in) s = st[CH_IN + l];  // overwrite mode
+  uint64_t s = lane < 12 ? st[lane] : 0;
+  if (lane < n_in) s = st[CH_IN + lane];  // overwrite mode (n_in <= 8)
   __syncwarp();
-  s = gl::canon(poseidon::coop_permute_nc(s, l));
+  s = gl::canon(poseidon::coop_permute_nc(s, lane));
   if (lane < 12) st[lane] = s;
   if (lane < 8) st[CH_OUT + lane] = s;
   if (lane == 0) {

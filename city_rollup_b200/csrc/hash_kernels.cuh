@@ -140,25 +140,25 @@ k_tree_level(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, 
   store_digest(parent + 4 * i, o);
 }
 
-// The same level for the narrow top of a tree: 16 lanes per node (poseidon::coop_permute_nc), ~5x lower latency
-// per level.  blockDim a multiple of 32; grid covers 16 * n_parents threads.
+// The same level for the narrow top of a tree: one warp per node (poseidon::coop_permute_nc), ~4x lower latency
+// per level.  blockDim a multiple of 32; grid covers 32 * n_parents threads.
 __global__ void __launch_bounds__(256)
 k_tree_level_coop(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, size_t n_parents) {
-  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const uint32_t l = threadIdx.x & 15;
-  const bool active = g < n_parents;  // idle groups still take part in the full-mask shuffles
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t l = threadIdx.x & 31;
+  const bool active = g < n_parents;  // idle warps still run (full-mask shuffles inside)
   const size_t gg = active ? g : 0;
   uint64_t s = l < 8 ? child[8 * gg + l] : 0;
   s = poseidon::coop_permute_nc(s, l);
   if (active && l < 4) parent[4 * gg + l] = gl::canon(s);
 }
 
-// Row-major leaves, 16 lanes per leaf (FRI layer leaves: few leaves, 4 permutations each)
+// Row-major leaves, one warp per leaf (FRI layer leaves: few leaves, 4 permutations each)
 __global__ void __launch_bounds__(256)
 k_leaf_hash_rowmajor_coop(const uint64_t* __restrict__ leaves, size_t leaf_len, size_t n_leaves,
                           uint64_t* __restrict__ digests) {
-  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const uint32_t l = threadIdx.x & 15;
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t l = threadIdx.x & 31;
   const bool active = g < n_leaves;
   const uint64_t* p = leaves + (active ? g : 0) * leaf_len;
   uint64_t s = 0;
@@ -167,6 +167,7 @@ k_leaf_hash_rowmajor_coop(const uint64_t* __restrict__ leaves, size_t leaf_len, 
   } else {
     for (size_t c0 = 0; c0 < leaf_len; c0 += 8) {
       if (l < 8 && c0 + l < leaf_len) s = p[c0 + l];
+      if (l >= 12) s = 0;
       s = poseidon::coop_permute_nc(s, l);
     }
     s = gl::canon(s);
@@ -264,10 +265,11 @@ k_transpose_to_rowmajor(const uint64_t* __restrict__ in, size_t col_stride, uint
 
 // hash_no_pad of one vector (public inputs hash, known-answer tests): one warp-cooperative sponge; <<<1, 32>>>
 __global__ void k_hash_no_pad_single(const uint64_t* __restrict__ in, size_t len, uint64_t* __restrict__ out) {
-  const uint32_t l = threadIdx.x & 15;
+  const uint32_t l = threadIdx.x & 31;
   uint64_t s = 0;
   for (size_t c0 = 0; c0 < len; c0 += 8) {
     if (l < 8 && c0 + l < len) s = in[c0 + l];
+    if (l >= 12) s = 0;
     s = poseidon::coop_permute_nc(s, l);
   }
   if (threadIdx.x < 4) out[threadIdx.x] = gl::canon(s);

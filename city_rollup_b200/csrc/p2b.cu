@@ -792,11 +792,11 @@ static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
     const uint64_t* child = t->d_levels + 4 * level_off(t->n_leaves, i);
     uint64_t* parent = t->d_levels + 4 * level_off(t->n_leaves, i + 1);
     // wide levels are throughput bound (one permutation per thread); the narrow top of the tree is a chain of
-    // dependent levels, where 16 lanes per node cut the latency of each
+    // dependent levels, where one warp per node cuts the latency of each
     if (n_par > COOP_MAX_NODES)
       hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(child, parent, n_par);
     else
-      hashk::k_tree_level_coop<<<cdiv(n_par * 16, 256), 256, 0, ctx->stream>>>(child, parent, n_par);
+      hashk::k_tree_level_coop<<<cdiv(n_par * 32, 256), 256, 0, ctx->stream>>>(child, parent, n_par);
     LAUNCH_CHECK(ctx);
   }
   return P2B_OK;
@@ -1841,7 +1841,7 @@ static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_val
     if (n_leaves > COOP_MAX_NODES)
       hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
     else
-      hashk::k_leaf_hash_rowmajor_coop<<<cdiv(n_leaves * 16, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+      hashk::k_leaf_hash_rowmajor_coop<<<cdiv(n_leaves * 32, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
     LAUNCHF();
     if ((rc = build_levels(ctx, t))) return cleanup(rc);
     // observe_cap, beta = get_extension_challenge (device resident)

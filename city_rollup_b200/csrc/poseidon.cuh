@@ -169,10 +169,10 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 // ---- warp-cooperative permutation (latency path) --------------------------------------------------------
 // A single permutation on one thread is a ~23k-instruction dependent stream (25-30 us): fine when a kernel has
 // 10^5 independent permutations in flight, ruinous for the transcript (one sponge), the top levels of a Merkle
-// tree and the small FRI layers, which are chains of a handful of permutations.  Here 16 lanes share one
+// tree and the small FRI layers, which are chains of a handful of permutations.  Here a warp shares one
 // permutation: lane l < 12 holds state element l, the S-boxes of a full round run in parallel, and the MDS
 // row of lane l gathers the other lanes with shuffles (the circulant makes the multiplier of step i the same
-// on every lane).  The 22 partial rounds are linearised (coop_partial_rounds below).
+// on every lane).  21 of the 22 partial rounds are linearised over all 32 lanes (coop_partial_rounds21 below).
 __device__ const uint64_t RC_G[372] = {  // the round constants again, in global memory: per-lane indexed loads
 #include "poseidon_rc.inc"
 };
@@ -203,59 +203,51 @@ __device__ __forceinline__ uint64_t coop_mds(uint64_t s, uint32_t l) {
   return r;
 }
 
-// The 22 partial rounds as ONE dependent chain of S-boxes (tables and derivation: tools/gen_poseidon_partial_linear.py).
-// Only lane 0 passes an S-box in a partial round, so the S-box input x_r of partial round r and the state after the
-// last one are affine in the entering state s and the S-box outputs sb_0..sb_{r-1}:
-//     x_r = X[r].s + XC[r] + sum_{k<r} C[r][k] sb_k,     out_i = O[i].s + OC[i] + sum_k D[i][k] sb_k.
-// The 16 lanes keep the 34 forms in three accumulators each (slot 0: x_l, slot 1: x_{16+l}, slot 2: out_l); a round
-// is "broadcast x_r, every lane computes sb_r = x_r^7, every lane adds coefficient * sb_r to its accumulators":
-// shuffle + S-box + one multiply-add on the critical path instead of S-box + a 12-term cross-lane MDS layer
-// (~2.5x shorter per round).  The s-dependent part of slots 1 and 2 is accumulated inside the first 12 rounds,
-// where it fills the issue slots the S-box chain leaves empty.
+// The first 21 of the 22 partial rounds as ONE dependent chain of S-boxes (tables and derivation:
+// tools/gen_poseidon_partial_linear.py).  Only lane 0 passes an S-box in a partial round, so the S-box input x_r of
+// partial round r and the state after any number of them are affine in the entering state s and the earlier S-box
+// outputs:   x_r = X[r].s + XC[r] + sum_{k<r} C[r][k] sb_k,     sb_r = x_r^7.
+// x_0 is s_0 plus a constant; the other 32 forms (x_1..x_20, and the 12 state elements after the 21st round) take one
+// accumulator in each of the 32 lanes.  A round is "every lane raises the broadcast x_r to the 7th power and adds
+// coefficient * sb_r to its accumulator, lane r broadcasts x_{r+1}": ~110 instructions instead of the ~190 of
+// S-box + cross-lane MDS layer — and a lone warp is bound by its instruction count (one issue per ~2.7 cycles,
+// profiles/r01_coop_permutation_latency_v2.txt), not by the dependency chain.  The 22nd partial round and the full
+// rounds run the ordinary way on lanes 0..11.
 #include "poseidon_partial_lin.inc"
 
-__device__ __forceinline__ uint64_t shfl64_16(uint64_t v, uint32_t src) {
-  const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src, 16);
-  const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src, 16);
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, uint32_t src) {
+  const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src);
+  const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src);
   return gl::pack(lo, hi);
 }
 
-// s = element l of the state after the 4th full round's MDS layer (the constants of round 4 not yet added);
-// returns element l of the state after the MDS layer of the last partial round (constants of round 26 not yet added)
-__device__ __forceinline__ uint64_t coop_partial_rounds(uint64_t s, uint32_t l) {
-  uint64_t a0, a1 = PL_CONST[16 + l], a2 = PL_CONST[32 + l];
-  {  // slot 0 is needed from the first rounds on: four independent multiply-add chains, not one 12-deep chain
-    uint64_t q[4] = {PL_CONST[l], 0, 0, 0};
+// s (lanes 0..11) = the state after the 4th full round's MDS layer (constants of round 4 not yet added); returns, in
+// lanes 0..11, the state after the MDS layer of the 21st partial round (constants of round 25 not yet added)
+__device__ __forceinline__ uint64_t coop_partial_rounds21(uint64_t s, uint32_t lane) {
+  uint64_t sb = sbox7(gl::add_nc(shfl64(s, 0), PL_X0_CONST));  // independent of the accumulator set-up below
+  uint64_t acc;
+  {  // the s-dependent part of this lane's form: four independent multiply-add chains, not one 12-deep chain
+    uint64_t q[4] = {PL_CONST[lane], 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 12; i++) q[i & 3] = gl::mad_nc(PL_INIT[i * 16 + l], shfl64_16(s, i), q[i & 3]);
-    a0 = gl::add_nc(gl::add_nc(gl::canon(q[0]), q[1]), gl::canon(gl::add_nc(gl::canon(q[2]), q[3])));
+    for (int i = 0; i < 12; i++) q[i & 3] = gl::mad_nc(PL_INIT[i * 32 + lane], shfl64(s, i), q[i & 3]);
+    acc = gl::add_nc(gl::add_nc(gl::canon(q[0]), q[1]), gl::canon(gl::add_nc(gl::canon(q[2]), q[3])));
   }
-  uint64_t c0 = PL_SB[l], c1 = PL_SB[16 + l], c2 = PL_SB[32 + l];
-  // not unrolled: measured 14.1k cycles for the 22 rounds against 12.0k fully unrolled when the code is hot, but
-  // the latency path mostly runs one or a few permutations per launch, where the larger code costs more than it saves
+  uint64_t c = PL_SB[lane];
 #pragma unroll 1
-  for (int r = 0; r < 22; r++) {
-    const uint64_t x = shfl64_16(r < 16 ? a0 : a1, r & 15);
-    // next round's coefficients (row 22 does not exist: re-read row 21) and, in the first 12 rounds, the
-    // s-dependent terms of slots 1 and 2: independent of the S-box below
-    const int rn = r < 21 ? r + 1 : 21;
-    const uint64_t n0 = PL_SB[(rn * 3 + 0) * 16 + l], n1 = PL_SB[(rn * 3 + 1) * 16 + l], n2 = PL_SB[(rn * 3 + 2) * 16 + l];
-    if (r < 12) {
-      const uint64_t v = shfl64_16(s, r);
-      a1 = gl::mad_nc(PL_INIT[(12 + r) * 16 + l], v, a1);
-      a2 = gl::mad_nc(PL_INIT[(24 + r) * 16 + l], v, a2);
-    }
-    const uint64_t sb = sbox7(x);
-    a0 = gl::mad_nc(c0, sb, a0);
-    a1 = gl::mad_nc(c1, sb, a1);
-    a2 = gl::mad_nc(c2, sb, a2);
-    c0 = n0, c1 = n1, c2 = n2;
+  for (int r = 0; r < 21; r++) {
+    const uint64_t cn = PL_SB[(r < 20 ? r + 1 : 20) * 32 + lane];  // next round's coefficient: off the critical path
+    acc = gl::mad_nc(c, sb, acc);
+    if (r < 20) sb = sbox7(shfl64(acc, r));  // lane r now holds x_{r+1}
+    c = cn;
   }
-  return a2;
+  return shfl64(acc, 20 + (lane < 12 ? lane : 0));
 }
 
-// lane = threadIdx & 15; every lane of the warp must call (full-mask shuffles); lanes 12..15 carry garbage
-__device__ __forceinline__ uint64_t coop_permute_nc(uint64_t s, uint32_t l) {
+// One permutation shared by a warp.  lane = threadIdx & 31; lanes 0..11 hold the state elements, lanes 12..31 pass
+// anything (they only work in the linearised partial rounds) and get garbage back; every lane of the warp must call
+// (full-mask shuffles).
+__device__ __forceinline__ uint64_t coop_permute_nc(uint64_t s, uint32_t lane) {
+  const uint32_t l = lane & 15;  // the full rounds run in 16-lane shuffle segments; the upper one computes garbage
   const uint32_t lc = l < 12 ? l : 0;
   uint64_t rc = RC_G[lc];
 #pragma unroll 1
@@ -264,7 +256,11 @@ __device__ __forceinline__ uint64_t coop_permute_nc(uint64_t s, uint32_t l) {
     rc = RC_G[12 * (r + 1) + lc];  // next round's constant: off the critical path
     s = coop_mds(sbox7(s), l);
   }
-  s = coop_partial_rounds(s, l);
+  s = coop_partial_rounds21(s, lane);
+  // partial round 22 (round 25), then the last four full rounds
+  s = gl::add_nc(s, RC_G[12 * 25 + lc]);
+  if (l == 0) s = sbox7(s);
+  s = coop_mds(s, l);
   rc = RC_G[12 * 26 + lc];
 #pragma unroll 1
   for (int r = 26; r < 30; r++) {
