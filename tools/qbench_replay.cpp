@@ -128,6 +128,21 @@ void plan_block(Block& blk, uint64_t checkpoint_id) {
   link(blk, sh, gl);
 }
 
+// BASELINE.json configs[4]: a binary aggregation tree over 2^k leaf proofs — 2^k leaf jobs (circuit 6, an L2 transfer)
+// and 2^k - 1 two-verifier aggregation jobs (circuit 7), level-synchronous exactly like the reference's tree prover
+// (city_common_circuit/src/treeprover/: every level waits for the one below); one `prove` per job
+void plan_agg_tree(Block& blk, uint64_t checkpoint_id, int log_leaves) {
+  blk.checkpoint_id = checkpoint_id;
+  int prev = add_level(blk, TRANSFER_L2, 2, 0, 1 << log_leaves, 1);
+  blk.entry_levels.push_back(prev);
+  uint32_t sub = 1;
+  for (int n = 1 << (log_leaves - 1); n >= 1; n /= 2, sub++) {
+    const int lv = add_level(blk, TRANSFER_L2_AGG, 2, sub, n, 1);
+    link(blk, prev, lv);
+    prev = lv;
+  }
+}
+
 std::string hex(const std::array<uint8_t, 24>& b) {
   static const char* d = "0123456789abcdef";
   std::string s;
@@ -140,7 +155,7 @@ std::string hex(const std::array<uint8_t, 24>& b) {
 int main(int argc, char** argv) {
   const char* case_path = nullptr;
   const char* out_path = nullptr;
-  int n_gpus = 1, ctx_per_gpu = 8, n_blocks = 4;
+  int n_gpus = 1, ctx_per_gpu = 8, n_blocks = 4, agg_tree = -1;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -149,9 +164,10 @@ int main(int argc, char** argv) {
     else if (a == "-n") n_blocks = atoi(val());
     else if (a == "--gpus") n_gpus = atoi(val());
     else if (a == "--contexts") ctx_per_gpu = atoi(val());
+    else if (a == "--agg-tree") agg_tree = atoi(val());
   }
-  if (!case_path || n_gpus < 1 || ctx_per_gpu < 1 || n_blocks < 1) {
-    fprintf(stderr, "usage: %s -i case.bin [-o bench.json] [-n blocks=4] [--gpus G=1] [--contexts W=8]\n", argv[0]);
+  if (!case_path || n_gpus < 1 || ctx_per_gpu < 1 || n_blocks < 1 || agg_tree == 0 || agg_tree > 20) {
+    fprintf(stderr, "usage: %s -i case.bin [-o bench.json] [-n blocks=4] [--gpus G=1] [--contexts W=8] [--agg-tree log2_leaves]\n", argv[0]);
     return 2;
   }
   try {
@@ -168,7 +184,10 @@ int main(int argc, char** argv) {
     shape.n_public_inputs = (uint32_t)cs.public_inputs.size();
 
     std::deque<Block> blocks(n_blocks);
-    for (int b = 0; b < n_blocks; b++) plan_block(blocks[b], 4 + (uint64_t)b);  // example.bin is checkpoint 4
+    for (int b = 0; b < n_blocks; b++) {
+      if (agg_tree > 0) plan_agg_tree(blocks[b], 4 + (uint64_t)b, agg_tree);
+      else plan_block(blocks[b], 4 + (uint64_t)b);  // example.bin is checkpoint 4
+    }
     size_t total_jobs = 0, total_proofs = 0;
     for (auto& b : blocks)
       for (auto& j : b.jobs) total_jobs++, total_proofs += (size_t)j.n_proofs;
@@ -284,11 +303,13 @@ int main(int argc, char** argv) {
       fprintf(f, "\n]\n");
       fclose(f);
     }
-    printf("{\"harness\": \"qbench replay (job DAG of qbench_data/example.bin, synthetic City-shaped circuit)\", \"gpus\": %d, "
+    printf("{\"harness\": \"%s\", \"rows_log2\": %u, \"gpus\": %d, "
            "\"contexts_per_gpu\": %d, \"blocks\": %d, \"jobs\": %zu, \"jobs_recorded\": %zu, \"proofs\": %zu, \"wall_s\": %.4f, "
            "\"proofs_per_s\": %.2f, \"jobs_per_s\": %.2f, \"sum_job_duration_ms\": %.0f, \"worker_busy_fraction\": %.3f, "
            "\"stored_proofs\": %zu, \"stored_bytes\": %zu, \"mismatching_proofs\": %d}\n",
-           n_gpus, ctx_per_gpu, n_blocks, total_jobs, recorded, total_proofs, wall, total_proofs / wall, total_jobs / wall, sum_ms,
+           agg_tree > 0 ? "binary aggregation tree, level-synchronous (synthetic City-shaped circuit)"
+                        : "qbench replay (job DAG of qbench_data/example.bin, synthetic City-shaped circuit)",
+           cs.desc.degree_bits, n_gpus, ctx_per_gpu, n_blocks, total_jobs, recorded, total_proofs, wall, total_proofs / wall, total_jobs / wall, sum_ms,
            busy_sum / (wall * n_gpus * ctx_per_gpu), store.size(), stored_bytes, mismatches.load());
     return (mismatches.load() || recorded != total_jobs || store.size() != total_jobs) ? 1 : 0;
   } catch (const std::exception& e) {
