@@ -124,3 +124,33 @@ def test_poseidon_fast_partial_round_form_equals_permutation():
         L.poseidon_permute(O._p(a))
         L.poseidon_permute_fast(O._p(b))
         assert (a == b).all()
+
+
+def test_linearised_partial_round_tables_are_the_generated_ones(tmp_path):
+    """city_rollup_b200/csrc/poseidon_partial_lin.inc (the one-warp permutation's 21 linearised partial rounds) is
+    exactly what tools/gen_poseidon_partial_linear.py derives from the K1-pinned round constants and the MDS matrix
+    (the generator checks its forms against the naive partial rounds before writing)."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_pl", os.path.join(root, "tools", "gen_poseidon_partial_linear.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    xs, outs = g.derive()
+    assert len(xs) == 21 and len(outs) == 12
+    import random
+
+    rng = random.Random(5)
+    s = [rng.randrange(g.P) for _ in range(12)]
+    assert g.partial_rounds_linear(s, xs, outs) == g.partial_rounds_naive(s)
+    committed = open(os.path.join(root, "city_rollup_b200", "csrc", "poseidon_partial_lin.inc")).read()
+    forms = [xs[l + 1] for l in range(20)] + outs
+    # spot-check the committed table against the derivation: constants, first and last S-box coefficient rows
+    assert "#define PL_X0_CONST 0x%016xull" % xs[0][-1] in committed
+    for l in (0, 19, 20, 31):
+        assert "0x%016xull" % forms[l][-1] in committed
+        assert "0x%016xull" % forms[l][12] in committed
+    # x_{l+1} must not depend on S-box outputs it cannot have seen
+    for l in range(20):
+        assert all(forms[l][12 + k] == 0 for k in range(l + 1, 21))
