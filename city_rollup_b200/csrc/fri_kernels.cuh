@@ -108,7 +108,7 @@ k_fold_coeffs(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1, 
   for (uint32_t j = arity; j-- > 0;) {
     acc = gl::ext_mul(acc, b);
     size_t k = (i << arity_bits) + j;
-    acc = gl::ext_add(acc, gl::ext2{c0[k], c1[k]});
+    acc = gl::ext_add(acc, gl::ext2{gl::canon(c0[k]), gl::canon(c1[k])});  // layer 0 reads the caller's raw words
   }
   o0[i] = acc.c0;
   o1[i] = acc.c1;

@@ -19,8 +19,13 @@ namespace gl {
 
 __device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// any u64 -> canonical
-__device__ __forceinline__ uint64_t canon(uint64_t a) { return a >= GL_P ? a - GL_P : a; }
+// any u64 -> canonical.  a >= p  <=>  the high word is 2^32 - 1 and the low word is not 0, and then a - p = (lo - 1, 0):
+// four instructions instead of the six of a 64-bit compare + subtract + select.
+__device__ __forceinline__ uint64_t canon(uint64_t a) {
+  uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+  const bool ge = (hi == 0xFFFFFFFFu) & (lo != 0u);
+  return pack(lo - (ge ? 1u : 0u), ge ? 0u : hi);
+}
 
 // (a*b) mod p, any u64 inputs; result is a u64 congruent to the product, NOT necessarily < p.
 __device__ __forceinline__ uint64_t mul_nc(uint64_t a, uint64_t b) {
@@ -134,9 +139,28 @@ __device__ __forceinline__ uint64_t sub_nc(uint64_t a, uint64_t b) {
       : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
   return pack(r0, r1);
 }
-// canonical in (both), canonical out
-__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return canon(add_nc(a, b)); }
-__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return canon(sub_nc(a, b)); }
+// Canonical in (BOTH operands), canonical out — the arithmetic of the constraint evaluators and the prover kernels,
+// where every value is canonical (ncu on k_quotient at 2^16 rows: a quarter of all executed instructions were the
+// generic canon() behind add / sub / mul).  a + b = a - (p - b): no intermediate exceeds 64 bits, and a borrow means
+// "add p back", i.e. subtract 2^32 - 1 modulo 2^64.  7 instructions (was 12).
+__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) {
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 nl,nh,m;\n\t"
+      "sub.cc.u32 nl, 1, %4;\n\t"  // p - b  (b < p: no borrow out)
+      "subc.u32 nh, 0xFFFFFFFF, %5;\n\t"
+      "sub.cc.u32 %0, %2, nl;\n\t"
+      "subc.cc.u32 %1, %3, nh;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+  return pack(r0, r1);
+}
+// a - b for canonical a, b: sub_nc's result is then already canonical (no borrow: a - b < p; borrow: a - b + p < p)
+__device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return sub_nc(a, b); }
 __device__ __forceinline__ uint64_t neg(uint64_t a) { return a ? GL_P - a : 0; }  // a canonical
 
 __device__ __forceinline__ uint64_t pow(uint64_t a, uint64_t e) {

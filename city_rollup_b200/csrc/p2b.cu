@@ -1485,7 +1485,7 @@ extern "C" int p2b_quotient_commit(p2b_ctx* ctx, const p2b_circuit* c, const p2b
   const uint32_t nch = c->d.num_challenges;
   std::vector<uint64_t> h(3 * nch + 4);
   for (uint32_t i = 0; i < nch; i++) h[i] = betas[i], h[nch + i] = gammas[i], h[2 * nch + i] = alphas[i];
-  for (int i = 0; i < 4; i++) h[3 * nch + i] = pi_hash[i];
+  for (int i = 0; i < 4; i++) h[3 * nch + i] = pi_hash[i] >= GL_P ? pi_hash[i] - GL_P : pi_hash[i];  // the kernels subtract it
   uint64_t* d_ch = nullptr;
   int rc = upload_felts(ctx, h.data(), h.size(), &d_ch);
   if (rc == P2B_OK)

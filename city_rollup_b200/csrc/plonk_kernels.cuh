@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(256) k_pp_finish(const uint64_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ gate evaluators
-// Accumulates filter-free sum_q alpha^q c_q for every challenge
+// Accumulates filter-free sum_q alpha^q c_q for every challenge.  The running sums are NOT canonical (one fused
+// multiply-add + reduction per constraint and challenge, gl::mad_nc); whoever reads a[] multiplies it (fmul) or
+// canonicalises it.
 struct Acc {
   uint64_t a[MAX_CHALLENGES];
   const uint64_t* apow;  // [challenge][stride] powers of alpha, already offset to the first gate term
@@ -154,14 +156,14 @@ struct Acc {
   __device__ __forceinline__ void push(uint64_t c) {
 #pragma unroll
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) a[ch] = fadd(a[ch], fmul(c, apow[ch * stride + q]));
+      if (ch < (int)n_chal) a[ch] = gl::mad_nc(c, apow[ch * stride + q], a[ch]);
     q++;
   }
   // constraint number q + k of the gate, without advancing
   __device__ __forceinline__ void push_at(uint32_t k, uint64_t c) {
 #pragma unroll
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) a[ch] = fadd(a[ch], fmul(c, apow[ch * stride + q + k]));
+      if (ch < (int)n_chal) a[ch] = gl::mad_nc(c, apow[ch * stride + q + k], a[ch]);
   }
 };
 
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
     // (terms nch + cc * (npp + 1) + k); each term is weighted by every challenge's own power of alpha
     for (uint32_t k = 0; k < nch; k++) {
       const uint64_t term = fmul(l0, fsub(gl::canon(zs[(size_t)k * N]), 1));
-      for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + k], term));
+      for (uint32_t c = 0; c < nch; c++) res[c] = gl::mad_nc(P.apow[(size_t)c * P.n_terms + k], term, res[c]);
     }
     for (uint32_t cc = 0; cc < nch; cc++) {
       const uint64_t beta = gl::canon(P.betas[cc]), gamma = gl::canon(P.gammas[cc]);
@@ -619,9 +621,10 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
         }
         const uint64_t term = fsub(fmul(gl::canon(prev), np), fmul(gl::canon(next), dp));
         const uint32_t idx = nch + cc * (npp + 1) + k;
-        for (uint32_t c = 0; c < nch; c++) res[c] = fadd(res[c], fmul(P.apow[(size_t)c * P.n_terms + idx], term));
+        for (uint32_t c = 0; c < nch; c++) res[c] = gl::mad_nc(P.apow[(size_t)c * P.n_terms + idx], term, res[c]);
       }
     }
+    for (uint32_t c = 0; c < nch; c++) res[c] = gl::canon(res[c]);  // k_quotient_combine adds canonical parts
   } else {
     // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
     Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};

@@ -20,7 +20,7 @@ using gl::ext2;
 // acc * z + c for a base-field coefficient c
 __device__ __forceinline__ ext2 horner_step(ext2 acc, ext2 z, uint64_t c) {
   ext2 r = gl::ext_mul(acc, z);
-  r.c0 = gl::add(r.c0, c);
+  r.c0 = gl::add(r.c0, gl::canon(c));  // coefficients of a from_coeffs batch are the caller's raw words
   return r;
 }
 __device__ __forceinline__ ext2 ext_pow(ext2 b, size_t e) {

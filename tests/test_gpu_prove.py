@@ -79,6 +79,54 @@ def test_gpu_openings_match_direct_evaluation(ctx, m):
     b.free()
 
 
+def test_noncanonical_words_at_the_api(ctx, m):
+    """GoldilocksField is a transparent u64 and the reference hands over non-canonical words in places
+    (city_crypto/src/hash/qhashout.rs:149-152): coefficients >= p given to from_coeffs must evaluate, extend and fold
+    like their canonical representatives (the constraint / prover kernels use strict canonical-in arithmetic, so every
+    raw load has to be canonicalised first)."""
+    P = R.P
+    rng = np.random.default_rng(11)
+    canonical = [rng.integers(0, P, 64, dtype=np.uint64) for _ in range(3)]
+    raw = [c.copy() for c in canonical]
+    for c in raw:  # sprinkle representatives x + p (possible for x < 2^32 - 1) and the extremes p, 2^64 - 1
+        c[3] = np.uint64(7)
+        c[9] = np.uint64(0)
+        c[17] = np.uint64(2**32 - 2)
+    canonical = [c.copy() for c in raw]
+    for c in raw:
+        c[3] = np.uint64(7 + P)
+        c[9] = np.uint64(P)
+        c[17] = np.uint64(2**64 - 1)
+    a = m.PolynomialBatch.from_coeffs(ctx, canonical, 2, False, 1)
+    b = m.PolynomialBatch.from_coeffs(ctx, raw, 2, False, 1)
+    assert (a.cap == b.cap).all() and (a.leaves() == b.leaves()).all()
+    z = [0xFFFFFFFF00000000, 3]
+    assert (a.eval_ext(z) == b.eval_ext(z)).all()
+    for i in range(3):
+        e = R.horner_ext(canonical[i], R.Ext(*z))
+        assert [int(b.eval_ext(z)[i][0]), int(b.eval_ext(z)[i][1])] == [e.a, e.b]
+    a.free()
+    b.free()
+    # FRI commit phase on raw extension coefficients / values
+    n, rate_bits = 64, 1
+    N = n << rate_bits
+    coeffs = np.zeros((N, 2), np.uint64)
+    coeffs[:n] = np.stack([canonical[0], canonical[1]], axis=1)
+    values = O.ext_coset_fft(coeffs, 7)
+    coeffs_raw, values_raw = coeffs.copy(), values.copy()
+    coeffs_raw[:n] = np.stack([raw[0], raw[1]], axis=1)
+    small = values_raw < np.uint64(2**32 - 1)
+    values_raw[small] += np.uint64(P)
+    outs = []
+    for cf, vl in ((coeffs, values), (coeffs_raw, values_raw)):
+        ch = m.Challenger(ctx)
+        ch.observe_elements([1, 2, 3])
+        trees, final = m.fri_committed_trees(ctx, cf, vl, ch, [2, 1], rate_bits, 1)
+        outs.append(([t.cap.copy() for t in trees], final.copy(), ch.export_state()[:12].tolist()))
+    assert all((x == y).all() for x, y in zip(outs[0][0], outs[1][0]))
+    assert (outs[0][1] == outs[1][1]).all() and outs[0][2] == outs[1][2]
+
+
 def test_gpu_proof_2p14_rows_verifies(ctx, m):
     """a larger circuit (2^14 rows: multi-pass NTT path, three FRI layers): too slow to rebuild through the Python
     oracle prover, so the GPU proof goes straight through the restated verifier (which only needs the proof)"""
