@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libp2b.so")
+SO_PATH = os.environ.get("P2B_LIB") or os.path.join(_HERE, "libp2b.so")  # P2B_LIB: an alternative build (kernel tuning)
 
 u64 = C.c_uint64
 u64p = C.POINTER(C.c_uint64)

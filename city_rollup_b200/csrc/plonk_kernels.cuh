@@ -579,7 +579,12 @@ struct QuotientParams {
 // per SM; splitting by term group puts (1 + n_gates) times as many independent streams in flight.  Each part
 // writes its alpha-weighted sum to parts[part][challenge][point]; k_quotient_combine adds them (field addition
 // is exact, so the order is irrelevant) and divides by Z_H.
-__global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
+// 8 CTAs of 128 threads per SM (64 registers, some spills in the widest gates): the kernel waits on its loads (44 % of
+// the stall samples were long-scoreboard at 5 CTAs per SM); measured at 2^14 rows: 5 CTAs 1.78 ms, 6: 1.70, 8: 1.65, 10: 1.69
+#ifndef P2B_QUOT_MINB
+#define P2B_QUOT_MINB 8
+#endif
+__global__ void __launch_bounds__(128, P2B_QUOT_MINB) k_quotient(QuotientParams P) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
   const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,22 +612,51 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientParams P) {
       const uint64_t term = fmul(l0, fsub(gl::canon(zs[(size_t)k * N]), 1));
       for (uint32_t c = 0; c < nch; c++) res[c] = gl::mad_nc(P.apow[(size_t)c * P.n_terms + k], term, res[c]);
     }
-    for (uint32_t cc = 0; cc < nch; cc++) {
-      const uint64_t beta = gl::canon(P.betas[cc]), gamma = gl::canon(P.gammas[cc]);
-      const uint64_t bx = fmul(beta, x);
-      for (uint32_t k = 0; k <= npp; k++) {
-        uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
-        uint64_t next = k == npp ? P.zs_lde[(size_t)cc * N + leaf_next] : zs[(size_t)(nch + cc * npp + k) * N];
-        uint64_t np = 1, dp = 1;
-        for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
-          uint64_t wv = gl::canon(wr[(size_t)j * N]);
-          np = fmul(np, fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma));
-          dp = fmul(dp, fadd(fadd(wv, fmul(beta, gl::canon(cs[(size_t)(P.num_constants + j) * N]))), gamma));
-        }
-        const uint64_t term = fsub(fmul(gl::canon(prev), np), fmul(gl::canon(next), dp));
-        const uint32_t idx = nch + cc * (npp + 1) + k;
-        for (uint32_t c = 0; c < nch; c++) res[c] = gl::mad_nc(P.apow[(size_t)c * P.n_terms + idx], term, res[c]);
+    // Every routed wire and its sigma are loaded ONCE for all challenges, four wires at a time before any of them is
+    // used (the loads of this loop were the largest long-scoreboard stall of the kernel: one dependent DRAM round
+    // trip per wire and challenge), and the challenges' products are independent multiply chains.
+    uint64_t beta[MAX_CHALLENGES], gamma[MAX_CHALLENGES], bx[MAX_CHALLENGES];
+#pragma unroll
+    for (int cc = 0; cc < MAX_CHALLENGES; cc++)
+      if (cc < (int)nch) {
+        beta[cc] = gl::canon(P.betas[cc]), gamma[cc] = gl::canon(P.gammas[cc]);
+        bx[cc] = fmul(beta[cc], x);
       }
+    for (uint32_t k = 0; k <= npp; k++) {
+      uint64_t np[MAX_CHALLENGES], dp[MAX_CHALLENGES];
+#pragma unroll
+      for (int cc = 0; cc < MAX_CHALLENGES; cc++) np[cc] = 1, dp[cc] = 1;
+      const uint32_t j_end = (k + 1) * P.chunk < P.num_routed ? (k + 1) * P.chunk : P.num_routed;
+      for (uint32_t j0 = k * P.chunk; j0 < j_end; j0 += 4) {
+        uint64_t wv[4], sg[4], kj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t j = j0 + u < j_end ? j0 + u : j_end - 1;  // clamped: the tail re-reads the last wire, unused
+          wv[u] = wr[(size_t)j * N];
+          sg[u] = cs[(size_t)(P.num_constants + j) * N];
+          kj[u] = P.k_is[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (j0 + u >= j_end) break;
+          const uint64_t w_c = gl::canon(wv[u]), s_c = gl::canon(sg[u]);
+#pragma unroll
+          for (int cc = 0; cc < MAX_CHALLENGES; cc++)
+            if (cc < (int)nch) {
+              np[cc] = fmul(np[cc], fadd(fadd(w_c, fmul(bx[cc], kj[u])), gamma[cc]));
+              dp[cc] = fmul(dp[cc], fadd(fadd(w_c, fmul(beta[cc], s_c)), gamma[cc]));
+            }
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < MAX_CHALLENGES; cc++)
+        if (cc < (int)nch) {
+          const uint64_t prev = k == 0 ? zs[(size_t)cc * N] : zs[(size_t)(nch + cc * npp + k - 1) * N];
+          const uint64_t next = k == npp ? P.zs_lde[(size_t)cc * N + leaf_next] : zs[(size_t)(nch + cc * npp + k) * N];
+          const uint64_t term = fsub(fmul(gl::canon(prev), np[cc]), fmul(gl::canon(next), dp[cc]));
+          const uint32_t idx = nch + cc * (npp + 1) + k;
+          for (uint32_t c = 0; c < nch; c++) res[c] = gl::mad_nc(P.apow[(size_t)c * P.n_terms + idx], term, res[c]);
+        }
     }
     for (uint32_t c = 0; c < nch; c++) res[c] = gl::canon(res[c]);  // k_quotient_combine adds canonical parts
   } else {
