@@ -66,6 +66,70 @@ __device__ __forceinline__ uint64_t mul_nc(uint64_t a, uint64_t b) {
   return pack(r0, r1);
 }
 
+// ---- variants for kernels that also keep the FP64 pipe busy (Poseidon) ------------------------------------
+// On B200 the 32x32->64 multiplies (IMAD.WIDE / IMAD.HI, ~4.3 cycles per warp instruction) and DFMA (~2.3) do not
+// overlap: tools/int32_peak.cu `mix_dfma_imadwide` runs at exactly the sum of the two, and in every ncu capture of the
+// leaf-hash kernel fmaheavy% + fp64% = 98-99 %.  Where DFMA work runs beside the field multiplications, each wide
+// multiply removed is worth two DFMAs, and the ALU pipe has room.  mul_nc_lw / sqr_nc are mul_nc with
+//   * x2 * (2^32 - 1) formed as (x2 << 32) - x2 with carries (4 IADD3 instead of IADD3 + IMAD.HI + SEL), and
+//   * for squares, ONE cross product a0*a1 doubled by a funnel shift instead of two accumulating IMAD.WIDE.
+#define P2B_GL_REDUCE_LW                                                                                        \
+  "sub.cc.u32 tl, x0, x3;\n\t"                                                                                  \
+  "subc.cc.u32 th, x1, 0;\n\t"                                                                                  \
+  "subc.u32 m, 0, 0;\n\t"                                                                                       \
+  "sub.cc.u32 tl, tl, m;\n\t"                                                                                   \
+  "subc.u32 th, th, 0;\n\t"                                                                                     \
+  /* r = t + (x2 << 32) - x2: low word borrows b, high word gains u = x2 - b (>= 0: b = 1 implies x2 >= 1) */   \
+  "sub.cc.u32 tl, tl, x2;\n\t"                                                                                  \
+  "subc.u32 m, x2, 0;\n\t"                                                                                      \
+  "add.cc.u32 th, th, m;\n\t"                                                                                   \
+  "addc.u32 m, 0, 0;\n\t"                                                                                       \
+  /* on carry add 2^32 - 1 */                                                                                   \
+  "sub.cc.u32 %0, tl, m;\n\t"                                                                                   \
+  "subc.u32 th, th, 0;\n\t"                                                                                     \
+  "add.u32 %1, th, m;\n\t"
+__device__ __forceinline__ uint64_t mul_nc_lw(uint64_t a, uint64_t b) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,m,tl,th;\n\t"
+      "mul.lo.u32 x0, %2, %4;\n\t"
+      "mul.hi.u32 x1, %2, %4;\n\t"
+      "mul.lo.u32 x2, %3, %5;\n\t"
+      "mul.hi.u32 x3, %3, %5;\n\t"
+      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+      "madc.hi.cc.u32 x2, %2, %5, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t" P2B_GL_REDUCE_LW "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack(r0, r1);
+}
+// (a*a) mod p, any u64 input; result congruent, NOT necessarily < p
+__device__ __forceinline__ uint64_t sqr_nc(uint64_t a) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,c0,c1,d0,d1,d2,m,tl,th;\n\t"
+      "mul.lo.u32 x0, %2, %2;\n\t"
+      "mul.hi.u32 x1, %2, %2;\n\t"
+      "mul.lo.u32 x2, %3, %3;\n\t"
+      "mul.hi.u32 x3, %3, %3;\n\t"
+      "mul.lo.u32 c0, %2, %3;\n\t"
+      "mul.hi.u32 c1, %2, %3;\n\t"
+      "shl.b32 d0, c0, 1;\n\t"               // 2 * a0 * a1 = d2:d1:d0
+      "shf.l.wrap.b32 d1, c0, c1, 1;\n\t"
+      "shr.u32 d2, c1, 31;\n\t"
+      "add.cc.u32 x1, x1, d0;\n\t"
+      "addc.cc.u32 x2, x2, d1;\n\t"
+      "addc.u32 x3, x3, d2;\n\t" P2B_GL_REDUCE_LW "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1));
+  return pack(r0, r1);
+}
+
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return canon(mul_nc(a, b)); }
 
 // (a*b + c) mod p, any u64 inputs (a*b + c < 2^128); result congruent, NOT necessarily < p.  One reduction for the

@@ -8,6 +8,10 @@
 #pragma once
 #include "poseidon.cuh"
 
+#ifndef P2B_LEAF_MINB
+#define P2B_LEAF_MINB 2  // resident CTAs of 256 threads per SM for the leaf sponge kernels (tuning: profiles/r01_summary.md)
+#endif
+
 namespace hashk {
 
 __device__ __forceinline__ void store_digest(uint64_t* __restrict__ dst, const uint64_t d[4]) {
@@ -27,7 +31,7 @@ __device__ __forceinline__ void load_digest(const uint64_t* __restrict__ src, ui
 // Leaf digests of a column-major matrix: leaf j = (data[c * col_stride + j])_{c < n_cols}.
 // hash_or_noop: n_cols <= 4 -> zero-padded copy, else overwrite-mode sponge, 8 columns per permutation.
 // Consecutive threads read consecutive j of the same column: every load is a full 256 B per warp.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, P2B_LEAF_MINB)
 k_leaf_hash_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t n_cols, size_t n_leaves,
                      uint64_t* __restrict__ digests) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +71,7 @@ k_leaf_hash_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint3
 // c_begin == 0 and writing the digest instead of the state when c_end == n_cols.  Used by the pipelined host upload
 // (p2b.cu batch_from_host_pipelined): leaf hashing of the columns that have arrived overlaps the upload of the rest.
 // Only for n_cols > 4 (hash_or_noop's copy case never gets here).
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, P2B_LEAF_MINB)
 k_leaf_absorb_colmajor(const uint64_t* __restrict__ data, size_t col_stride, uint32_t c_begin, uint32_t c_end,
                        uint32_t n_cols, size_t n_leaves, uint64_t* __restrict__ state, uint64_t* __restrict__ digests) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,13 +6,15 @@
 // `PoseidonGoldilocksConfig`, the only config the reference instantiates
 // (city_rollup_core_worker/src/lib.rs:25-26; wrappers at city_crypto/src/hash/traits/hasher.rs:77-159).
 //
-// Schedule (one permutation per thread, state in registers):
+// Schedule (one permutation per thread, state in registers; "v6", details at permute_nc below):
 //   * the round-constant layer of round r+1 is folded into the MDS accumulators of round r;
-//   * S-box x^7 = 4 Goldilocks multiplications with non-canonical (u64) intermediates;
+//   * S-box x^7 = 2 squarings + 2 multiplications with non-canonical (u64) intermediates; the last product is
+//     not reduced but handed to the MDS layer as two limbs;
 //   * the MDS layer (circulant [17,15,41,16,2,28,13,13,39,18,34,20] + diag(8,0,..)) runs on the FP64 pipe
-//     as exact integer arithmetic on the two 32-bit limbs of every lane (see mds_layer below), then one
-//     integer fold per lane using 2^64 = 2^32 - 1.  (History, profiles/r01_summary.md: v1 IMAD.WIDE MDS
-//     saturated the FMA-heavy pipe; v2 22/21/21-bit limbs on plain IMAD; v3 = this.)
+//     as exact integer arithmetic on the two 32-bit limbs of every lane (see mds_limbs_biased below), then one
+//     integer fold per lane using 2^64 = 2^32 - 1 where a 64-bit integer is needed (S-box inputs), a 6-instruction
+//     lazy fold where it is not.  (History, profiles/r01_summary.md: v1 IMAD.WIDE MDS saturated the FMA-heavy
+//     pipe; v2 22/21/21-bit limbs on plain IMAD; v3 FP64 MDS; v6 = this.)
 //   * nothing is canonicalised until the digest is written.
 #pragma once
 #include "gl64.cuh"
@@ -25,10 +27,17 @@ __constant__ uint64_t RC[372] = {
 };
 
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
+#ifdef P2B_SBOX_V3  // tuning builds only
   uint64_t x2 = gl::mul_nc(x, x);
   uint64_t x4 = gl::mul_nc(x2, x2);
   uint64_t x3 = gl::mul_nc(x, x2);
   return gl::mul_nc(x3, x4);
+#else  // 14 wide multiplies instead of 20 (they share an execution unit with the DFMAs of the MDS layers, gl64.cuh)
+  uint64_t x2 = gl::sqr_nc(x);
+  uint64_t x4 = gl::sqr_nc(x2);
+  uint64_t x3 = gl::mul_nc_lw(x, x2);
+  return gl::mul_nc_lw(x3, x4);
+#endif
 }
 
 // ---- MDS layer on the FP64 pipe -----------------------------------------------------------------------
@@ -50,6 +59,11 @@ __constant__ unsigned long long RCF[720] = {
 };
 
 #define P2B_TWO52_HI 0x43300000u
+
+// a + b / a - b on the FP64 pipe (issuing them as DFMA with a unit multiplier was measured and is slower:
+// profiles/r01_poseidon_v6_experiments.md)
+__device__ __forceinline__ double dadd(double a, double b) { return a + b; }
+__device__ __forceinline__ double dsub(double a, double b) { return a - b; }
 
 // a + 2^32 b (mod p) for a, b < 2^51 given as the bit patterns of 2^52 + a and 2^52 + b
 __device__ __forceinline__ uint64_t fold_f64(double ya, double yb) {
@@ -82,8 +96,8 @@ __device__ __forceinline__ void mds_limbs_biased(const double (&b)[12], const un
   double p[6], m[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    m[k] = b[k] - b[k + 6];                          // the 2^52 biases cancel
-    p[k] = b[k] + (b[k + 6] - 9007199254740992.0);   // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
+    m[k] = dsub(b[k], b[k + 6]);                              // the 2^52 biases cancel
+    p[k] = dadd(b[k], dsub(b[k + 6], 9007199254740992.0));   // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
   }
 #pragma unroll
   for (int r = 0; r < 6; r++) {
@@ -101,8 +115,8 @@ __device__ __forceinline__ void mds_limbs_biased(const double (&b)[12], const un
       P = fma(2., m[0], P);
       M = fma(2., p[0], M);
     }
-    y[r] = P + M;
-    y[r + 6] = P - M;
+    y[r] = dadd(P, M);
+    y[r + 6] = dsub(P, M);
   }
 }
 
@@ -142,10 +156,222 @@ __device__ __forceinline__ void partial_round_pair(uint64_t (&s)[12], const unsi
   for (int i = 0; i < 12; i++) s[i] = fold_f64(blo[i], bhi[i]);
 }
 
+// ---- v6 schedule --------------------------------------------------------------------------------------------
+// Measured on B200 (profiles/r01_poseidon_v6_experiments.md): the permutation kernels run at ~0.65 warp
+// instructions per cycle per scheduler whatever the occupancy and however the integer and FP64 streams are
+// interleaved (S-box pairs fenced into their own basic blocks beside the previous pair's chain terms: no gain; wide
+// multiplies traded for ALU instructions: 1 %), and time follows the instruction count.  v6 removes instructions:
+//   * the two MDS layers of a partial-round pair are chained: the second layer takes the first layer's P / M chains
+//     (p_k = 2 P_k, m_k = 2 M_k) instead of its outputs — 10 outputs, their bias and 15 p / m less per limb set;
+//   * the last multiplication of every S-box is not reduced: the 128-bit product x3:x2:x1:x0 goes to the MDS layer as
+//     the limbs lo = x0 - x2 - x3 + 2^33, hi = x1 + x2 (6 instructions instead of 12 + 2 moves);
+//   * lanes 1..11 between two pairs are folded lazily to limbs of 33 bits (6 instructions instead of 10 + 2 moves).
+// The constant offsets that keep those limbs non-negative pass through the linear layer and are taken out of the chain
+// initialisers (RC6, tools/gen_poseidon_v6_tables.py — which also checks this schedule operation by operation in
+// exact integer arithmetic, incl. every FP64 bound, against the plain permutation).
+__constant__ unsigned long long RC6[720] = {
+#include "poseidon_rc_v6.inc"
+};
+#define P2B_LAZY_OFFSET 0x40000u  // OL = 2^18 (gen_poseidon_v6_tables.py)
+
+__device__ __forceinline__ void pm_from_biased(double bk, double bk6, double& p, double& m) {
+  m = dsub(bk, bk6);                               // the 2^52 biases cancel
+  p = dadd(bk, dsub(bk6, 9007199254740992.0));     // (2^52 + x_k) + (x_{k+6} - 2^52): both steps exact
+}
+// chain terms of input pair k for row pair r of one limb set
+template <int r, int k>
+__device__ __forceinline__ void mds_term(double& P, double& M, double pk, double mk) {
+  constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
+  constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
+  constexpr int j = (k - r + 12) % 12;
+  constexpr double d = Dh[j % 6] + ((r == 0 && k == 0) ? 2. : 0.);
+  constexpr double e = (j < 6 ? Eh[j % 6] : -Eh[j % 6]) + ((r == 0 && k == 0) ? 2. : 0.);
+  P = fma(d, pk, P);
+  M = fma(e, mk, M);
+  if (r == 0 && k == 0) {  // diag(8, 0, ..): + 4 x_0 = 2 p_0 + 2 m_0 on both chains
+    P = fma(2., mk, P);
+    M = fma(2., pk, M);
+  }
+}
+template <int k>
+__device__ __forceinline__ void mds_terms_k(double (&P)[6], double (&M)[6], double pk, double mk) {
+  mds_term<0, k>(P[0], M[0], pk, mk);
+  mds_term<1, k>(P[1], M[1], pk, mk);
+  mds_term<2, k>(P[2], M[2], pk, mk);
+  mds_term<3, k>(P[3], M[3], pk, mk);
+  mds_term<4, k>(P[4], M[4], pk, mk);
+  mds_term<5, k>(P[5], M[5], pk, mk);
+}
+// the same for a row pair k >= 1 given as the PREVIOUS layer's chains (its P chain without the 2^52 bias)
+template <int r, int k>
+__device__ __forceinline__ void mds_term_chained(double& P, double& M, double Pk, double Mk) {
+  constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
+  constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
+  constexpr int j = (k - r + 12) % 12;
+  constexpr double d2 = 2. * Dh[j % 6];
+  constexpr double e2 = 2. * (j < 6 ? Eh[j % 6] : -Eh[j % 6]);
+  P = fma(d2, Pk, P);
+  M = fma(e2, Mk, M);
+}
+template <int k>
+__device__ __forceinline__ void mds_terms_k_chained(double (&P)[6], double (&M)[6], double Pk, double Mk) {
+  mds_term_chained<0, k>(P[0], M[0], Pk, Mk);
+  mds_term_chained<1, k>(P[1], M[1], Pk, Mk);
+  mds_term_chained<2, k>(P[2], M[2], Pk, Mk);
+  mds_term_chained<3, k>(P[3], M[3], Pk, Mk);
+  mds_term_chained<4, k>(P[4], M[4], Pk, Mk);
+  mds_term_chained<5, k>(P[5], M[5], Pk, Mk);
+}
+__device__ __forceinline__ void mds_chain_init(double (&P)[6], double (&M)[6], const unsigned long long* __restrict__ init) {
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    P[r] = __longlong_as_double((long long)init[2 * r]);
+    M[r] = __longlong_as_double((long long)init[2 * r + 1]);
+  }
+}
+
+// x^7 in limb form: blo = 2^52 + (x0 - x2 - x3 + 2^33), bhi = 2^52 + (x1 + x2) for the unreduced last product
+__device__ __forceinline__ void sbox7_limbs(uint64_t x, double& blo, double& bhi) {
+#ifdef P2B_SBOX_V3  // tuning builds only
+  const uint64_t x2 = gl::mul_nc(x, x);
+  const uint64_t x4 = gl::mul_nc(x2, x2);
+  const uint64_t x3 = gl::mul_nc(x, x2);
+#else
+  const uint64_t x2 = gl::sqr_nc(x);
+  const uint64_t x4 = gl::sqr_nc(x2);
+  const uint64_t x3 = gl::mul_nc_lw(x, x2);
+#endif
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,l0,l1,h0,h1;\n\t"
+      "mul.lo.u32 x0, %2, %4;\n\t"
+      "mul.hi.u32 x1, %2, %4;\n\t"
+      "mul.lo.u32 x2, %3, %5;\n\t"
+      "mul.hi.u32 x3, %3, %5;\n\t"
+      "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+      "madc.hi.cc.u32 x2, %2, %5, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "sub.cc.u32 l0, x0, x2;\n\t"           // (2 : x0) - x2 - x3, the 2 sitting on top of the exponent word
+      "subc.u32 l1, 0x43300002, 0;\n\t"
+      "sub.cc.u32 l0, l0, x3;\n\t"
+      "subc.u32 l1, l1, 0;\n\t"
+      "add.cc.u32 h0, x1, x2;\n\t"
+      "addc.u32 h1, 0x43300000, 0;\n\t"
+      "mov.b64 %0, {l0, l1};\n\t"
+      "mov.b64 %1, {h0, h1};\n\t"
+      "}"
+      : "=d"(blo), "=d"(bhi)
+      : "r"((uint32_t)x3), "r"((uint32_t)(x3 >> 32)), "r"((uint32_t)x4), "r"((uint32_t)(x4 >> 32)));
+}
+// row sums a, b (as 2^52 + a, 2^52 + b; a, b < 2^50) -> limbs lo = a_lo - b_hi + 2^18, hi = b_lo + a_hi + b_hi
+__device__ __forceinline__ void lazy_fold(double ya, double yb, double& blo, double& bhi) {
+  asm("{\n\t"
+      ".reg .u32 al,ah,bl,bh,u,t,l1,h1;\n\t"
+      "mov.b64 {al, ah}, %2;\n\t"
+      "mov.b64 {bl, bh}, %3;\n\t"
+      "sub.u32 u, 0x43340000, bh;\n\t"       // 2^18 - b_hi
+      "add.cc.u32 al, al, u;\n\t"
+      "addc.u32 l1, 0x43300000, 0;\n\t"
+      "add.u32 t, ah, bh;\n\t"
+      "add.u32 t, t, 0x79a00000;\n\t"        // - 2 * 0x43300000 (mod 2^32)
+      "add.cc.u32 bl, bl, t;\n\t"
+      "addc.u32 h1, 0x43300000, 0;\n\t"
+      "mov.b64 %0, {al, l1};\n\t"
+      "mov.b64 %1, {bl, h1};\n\t"
+      "}"
+      : "=d"(blo), "=d"(bhi)
+      : "d"(ya), "d"(yb));
+}
+// a 64-bit lane -> the limbs a lazy fold would have produced (lo + 2^18, hi)
+__device__ __forceinline__ void limbs_from_u64(uint64_t v, double& blo, double& bhi) {
+  asm("{\n\t"
+      ".reg .u32 l0,l1;\n\t"
+      "add.cc.u32 l0, %2, 0x40000;\n\t"
+      "addc.u32 l1, 0x43300000, 0;\n\t"
+      "mov.b64 %0, {l0, l1};\n\t"
+      "mov.b64 %1, {%3, 0x43300000};\n\t"
+      "}"
+      : "=d"(blo), "=d"(bhi)
+      : "r"((uint32_t)v), "r"((uint32_t)(v >> 32)));
+}
+
+// One full round: s <- MDS * sbox(s) + rc(next round)
+__device__ __forceinline__ void full_round_v6(uint64_t (&s)[12], const unsigned long long* __restrict__ init) {
+  double blo[12], bhi[12], ylo[12], yhi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) sbox7_limbs(s[i], blo[i], bhi[i]);
+  mds_limbs_biased(blo, init, ylo);
+  mds_limbs_biased(bhi, init + 12, yhi);
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = fold_f64(ylo[i], yhi[i]);
+}
+
+// Two consecutive partial rounds r, r + 1.  s0 = lane 0 (a 64-bit integer: it passes the S-boxes), zlo / zhi[1..11] =
+// the other lanes in limb form; all updated in place.
+// `vz` = lane_varying_zero(): with a warp-uniform table index ptxas loads the initialisers into UNIFORM registers, a
+// DFMA takes only one non-register operand, and every chain then starts with two moves that put its multiplier (an
+// immediate otherwise) into a register pair — 65 extra instructions per pair.
+__device__ __forceinline__ uint32_t lane_varying_zero() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));  // < 2^31 on every lane
+  return m >> 31;
+}
+__device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
+                                                      uint32_t vz) {
+  const unsigned long long* __restrict__ initA = RC6 + 24 * (r + vz);
+  const unsigned long long* __restrict__ initB = initA + 24;
+  double Pl[6], Ml[6], Ph[6], Mh[6];  // first layer
+  double Ql[6], Nl[6], Qh[6], Nh[6];  // second layer
+  double b0l, b0h, p0l, m0l, p0h, m0h;
+  // ---- first layer: lanes 1..11 on the FP64 pipe beside the S-box of lane 0
+  sbox7_limbs(s0, b0l, b0h);
+  mds_chain_init(Pl, Ml, initA);
+  mds_chain_init(Ph, Mh, initA + 12);
+#define P2B_PR_K(k)                                         \
+  {                                                         \
+    double p, m;                                            \
+    pm_from_biased(zlo[k], zlo[k + 6], p, m);               \
+    mds_terms_k<k>(Pl, Ml, p, m);                           \
+    pm_from_biased(zhi[k], zhi[k + 6], p, m);               \
+    mds_terms_k<k>(Ph, Mh, p, m);                           \
+  }
+  P2B_PR_K(1) P2B_PR_K(2) P2B_PR_K(3) P2B_PR_K(4) P2B_PR_K(5)
+#undef P2B_PR_K
+  pm_from_biased(b0l, zlo[6], p0l, m0l);
+  pm_from_biased(b0h, zhi[6], p0h, m0h);
+  mds_terms_k<0>(Pl, Ml, p0l, m0l);
+  mds_terms_k<0>(Ph, Mh, p0h, m0h);
+  const double y0l = dadd(Pl[0], Ml[0]), y0h = dadd(Ph[0], Mh[0]);  // lanes 0 and 6 (biased): the only outputs formed
+  const double y6l = dsub(Pl[0], Ml[0]), y6h = dsub(Ph[0], Mh[0]);
+  // ---- second layer
+  sbox7_limbs(fold_f64(y0l, y0h), b0l, b0h);
+  mds_chain_init(Ql, Nl, initB);
+  mds_chain_init(Qh, Nh, initB + 12);
+#define P2B_PR_K(k)                                   \
+  mds_terms_k_chained<k>(Ql, Nl, Pl[k], Ml[k]);       \
+  mds_terms_k_chained<k>(Qh, Nh, Ph[k], Mh[k]);
+  P2B_PR_K(1) P2B_PR_K(2) P2B_PR_K(3) P2B_PR_K(4) P2B_PR_K(5)
+#undef P2B_PR_K
+  pm_from_biased(b0l, y6l, p0l, m0l);
+  pm_from_biased(b0h, y6h, p0h, m0h);
+  mds_terms_k<0>(Ql, Nl, p0l, m0l);
+  mds_terms_k<0>(Qh, Nh, p0h, m0h);
+  s0 = fold_f64(dadd(Ql[0], Nl[0]), dadd(Qh[0], Nh[0]));
+  lazy_fold(dsub(Ql[0], Nl[0]), dsub(Qh[0], Nh[0]), zlo[6], zhi[6]);
+#pragma unroll
+  for (int i = 1; i < 6; i++) {
+    lazy_fold(dadd(Ql[i], Nl[i]), dadd(Qh[i], Nh[i]), zlo[i], zhi[i]);
+    lazy_fold(dsub(Ql[i], Nl[i]), dsub(Qh[i], Nh[i]), zlo[i + 6], zhi[i + 6]);
+  }
+}
+
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).
 __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_nc(s[i], RC[i]);  // RC entries are canonical
+#ifdef P2B_POSEIDON_V3  // the previous schedule (tuning builds: tools/poseidon_bench.cu)
 #pragma unroll 1
   for (int r = 0; r < 30;) {
     if (r < 4 || r >= 26) {
@@ -158,6 +384,27 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
       r += 2;
     }
   }
+#else
+  // one copy of each loop body: the full rounds of both ends share theirs through the outer loop
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) full_round_v6(s, RC6 + 24 * (26 * half + i));
+    if (half == 0) {
+      double zlo[12], zhi[12];
+      zlo[0] = zhi[0] = 0.;
+#pragma unroll
+      for (int i = 1; i < 12; i++) limbs_from_u64(s[i], zlo[i], zhi[i]);
+      uint64_t s0 = s[0];
+      const uint32_t vz = lane_varying_zero();
+#pragma unroll 1
+      for (int r = 4; r < 26; r += 2) partial_round_pair_v6(s0, zlo, zhi, r, vz);
+      s[0] = s0;
+#pragma unroll
+      for (int i = 1; i < 12; i++) s[i] = gl::sub_nc(fold_f64(zlo[i], zhi[i]), (uint64_t)P2B_LAZY_OFFSET);
+    }
+  }
+#endif
 }
 
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {

@@ -1,0 +1,333 @@
+#!/usr/bin/env python3
+"""Generates city_rollup_b200/csrc/poseidon_rc_v6.inc — the chain initialisers of the v6 Poseidon schedule
+(poseidon.cuh permute_nc) — and checks the schedule itself, operation by operation, in exact integer arithmetic.
+
+v6 keeps lanes in "limb form" (two non-negative integers lo, hi with lo + 2^32 hi = value mod p, carried as the
+doubles 2^52 + lo, 2^52 + hi) wherever a 64-bit canonical-ish integer is not needed:
+  * the last multiplication of an S-box is not reduced: its 128-bit product x3:x2:x1:x0 becomes the limbs
+        lo = x0 - x2 - x3 + OS,   hi = x1 + x2          (2^64 = 2^32 - 1, 2^96 = -1 mod p;  OS = 2^33 keeps lo >= 0)
+  * lanes 1..11 between two partial-round pairs are "lazily folded": from the row sums a, b (lo / hi limb set)
+        lo = a_lo - b_hi + OL,    hi = b_lo + a_hi + b_hi   (OL = 2^18)
+    instead of a full reduction to 64 bits and a new split.
+The constant offsets OS / OL go through the (linear) MDS layer and are subtracted from the chain initialisers here.
+
+Layer kinds (round r = the round whose MDS layer it is; the constants of round r + 1 are folded in):
+  F  r in 0..3, 26..29   all twelve inputs are S-box limbs
+  A  r = 4, 6, .., 24    lane 0 S-box limbs, lanes 1..11 lazily folded; the P chains of the row pairs 1..5 carry no 2^52
+  B  r = 5, 7, .., 25    lanes 1..5 / 7..11 come as the A chains themselves (p_k = 2 P_k, m_k = 2 M_k), lane 6 is A's
+                         biased output, lane 0 S-box limbs
+Output index: ((r * 2 + limb) * 6 + row_pair) * 2 + {0: P_init, 1: M_init}, as double bit patterns.
+
+`python tools/gen_poseidon_v6_tables.py --check N` runs the model on N random states against the plain permutation.
+"""
+import os
+import random
+import re
+import struct
+import sys
+
+P = 2**64 - 2**32 + 1
+EPS = 2**32 - 1
+M32 = 2**32 - 1
+M64 = 2**64 - 1
+TWO52 = 2**52
+OS = 2**33
+OL = 2**18
+here = os.path.dirname(os.path.abspath(__file__))
+src = open(os.path.join(here, "..", "city_rollup_b200", "csrc", "poseidon_rc.inc")).read()
+src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+RC = [int(x, 16) for x in re.findall(r"0x[0-9a-fA-F]+", src)]
+assert len(RC) == 360
+RC += [0] * 12
+CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+DH = [15, 14, 40, 17, 18, 24]
+EH = [2, 1, 1, -1, -16, 4]
+FULL = [0, 1, 2, 3, 26, 27, 28, 29]
+
+
+def kind(r):
+    return "F" if r in FULL else ("A" if r % 2 == 0 else "B")
+
+
+def coef(r, k):
+    """(d, e) of input pair k in row pair r, incl. the diag(8,0,..) share of (0,0)"""
+    j = (k - r + 12) % 12
+    d = DH[j % 6]
+    e = EH[j] if j < 6 else -EH[j - 6]
+    if r == 0 and k == 0:
+        d += 2
+        e += 2
+    return d, e
+
+
+def chains(p, m, Pi, Mi, scale=None):
+    """P[r], M[r] from p_k, m_k (lists of 6; entries may be None = skipped) on top of Pi / Mi"""
+    Pn, Mn = list(Pi), list(Mi)
+    for r in range(6):
+        for k in range(6):
+            if p[k] is None:
+                continue
+            d, e = coef(r, k)
+            Pn[r] += d * p[k]
+            Mn[r] += e * m[k]
+            if r == 0 and k == 0:
+                Pn[r] += 2 * m[k]
+                Mn[r] += 2 * p[k]
+    return Pn, Mn
+
+
+def reps(v):
+    out = []
+    for j in range(4):
+        w = v + j * P
+        for t in range(4):
+            lo = (w & 0xFFFFFFFF) + (t << 32)
+            hi = (w >> 32) - t
+            if 0 <= hi < 2**34:
+                out.append((lo, hi))
+    return out
+
+
+def lift(r):
+    """Z[i]: what stays added to the lo row sum i so that it cannot go negative (the S-box limb lo = x0 - x2 - x3 and
+    the lazily folded lo = a_lo - b_hi are signed once their offsets are taken out).  The same amount is taken out
+    of the constant, whose representation (lo, hi) is searched for (constant - Z) mod p."""
+    kd = kind(r)
+    if kd == "F":
+        return [2**42] * 12  # 272 * 2^33
+    if kd == "A":  # only the row pair 0 is formed as (biased) outputs; the chained rows may be negative
+        return [2**38 if i % 6 == 0 else 0 for i in range(12)]
+    return [2**47] * 12  # B: 272 * (what the chained rows of A can be short of) + its own lane 0
+
+
+def layer_inits(r):
+    """chain initialisers of the MDS layer of round r: [limb][row pair] = (P_init, M_init)"""
+    kd = kind(r)
+    # offsets of the lo limbs of the twelve inputs, as they enter p_k / m_k
+    if kd == "F":
+        off = [OS] * 12
+    elif kd == "A":
+        off = [OS] + [OL] * 11
+    else:  # B: the chained pairs carry nothing, lane 6 nothing, lane 0 the S-box offset
+        off = [OS] + [0] * 11
+    p = [off[k] + off[k + 6] for k in range(6)]
+    m = [off[k] - off[k + 6] for k in range(6)]
+    Po, Mo = chains(p, m, [0] * 6, [0] * 6)
+    row_off = [Po[i] + Mo[i] for i in range(6)] + [Po[i] - Mo[i] for i in range(6)]
+    Z = lift(r)
+    k = [(RC[12 * (r + 1) + i] - Z[i]) % P for i in range(12)]
+    out = [[None] * 6, [None] * 6]
+    for rr in range(6):
+        best = None
+        for a in reps(k[rr]):
+            for b in reps(k[rr + 6]):
+                if (a[0] + b[0]) % 2 == 0 and (a[1] + b[1]) % 2 == 0:
+                    cost = max(a[0], a[1], b[0], b[1])
+                    if best is None or cost < best[0]:
+                        best = (cost, a, b)
+        assert best is not None
+        _, a, b = best
+        c = [a[0] + Z[rr] - row_off[rr], a[1]]
+        d = [b[0] + Z[rr + 6] - row_off[rr + 6], b[1]]
+        for limb in range(2):
+            assert (c[limb] + d[limb]) % 2 == 0
+            pi, mi = (c[limb] + d[limb]) // 2, (c[limb] - d[limb]) // 2
+            if not (kd == "A" and rr >= 1):
+                pi += TWO52
+            out[limb][rr] = (pi, mi)
+    return out
+
+
+INITS = [layer_inits(r) for r in range(30)]
+
+
+# ---- exact model of the device arithmetic ---------------------------------------------------------------
+def chk53(x):
+    assert abs(x) < 2**53, "FP64 exactness bound exceeded"
+    return x
+
+
+def mul_red(a, b):
+    """gl::mul_nc / mul_nc_lw / sqr_nc: the u64 they return"""
+    x = a * b
+    x0, x1, x2, x3 = x & M32, (x >> 32) & M32, (x >> 64) & M32, x >> 96
+    t = (x1 << 32 | x0) - x3
+    if t < 0:
+        t = (t - EPS) & M64
+    r = t + x2 * EPS
+    if r > M64:
+        r = (r & M64) + EPS
+        assert r <= M64
+    return r
+
+
+def sbox_limbs(x):
+    """x^7 in limb form: (lo + OS, hi)"""
+    x2 = mul_red(x, x)
+    x4 = mul_red(x2, x2)
+    x3 = mul_red(x, x2)
+    y = x3 * x4
+    y0, y1, y2, y3 = y & M32, (y >> 32) & M32, (y >> 64) & M32, y >> 96
+    lo = y0 - y2 - y3 + OS
+    hi = y1 + y2
+    assert 0 <= lo < 2**35 and 0 <= hi < 2**34
+    return lo, hi
+
+
+def fold(ya, yb):
+    """poseidon::fold_f64 on the biased doubles ya, yb: the u64 it returns"""
+    a, b = ya - TWO52, yb - TWO52
+    assert 0 <= a < 2**51 and 0 <= b < 2**51
+    a_lo, a_hi, b_lo, b_hi = a & M32, a >> 32, b & M32, b >> 32
+    mm = a_hi + b_hi
+    Y = (mm << 32) - b_hi
+    X = a_lo | (b_lo << 32)
+    r = X + Y
+    if r > M64:
+        r = (r & M64) + EPS
+        assert r <= M64
+    return r
+
+
+def lazy_fold(ya, yb):
+    a, b = ya - TWO52, yb - TWO52
+    assert 0 <= a < 2**50 and 0 <= b < 2**50
+    a_lo, a_hi, b_lo, b_hi = a & M32, a >> 32, b & M32, b >> 32
+    lo = a_lo + (OL - b_hi)
+    hi = b_lo + a_hi + b_hi
+    assert 0 <= lo < 2**34 and 0 <= hi < 2**34
+    return lo, hi
+
+
+def mds_plain(lo, hi, r):
+    """F layer: limbs (with offsets) of all lanes -> biased outputs"""
+    y = [[None] * 12, [None] * 12]
+    for limb, v in enumerate((lo, hi)):
+        p = [chk53(v[k] + v[k + 6]) for k in range(6)]
+        m = [chk53(v[k] - v[k + 6]) for k in range(6)]
+        Pn, Mn = chains(p, m, [INITS[r][limb][rr][0] for rr in range(6)], [INITS[r][limb][rr][1] for rr in range(6)])
+        for rr in range(6):
+            chk53(Pn[rr]), chk53(Mn[rr])
+            y[limb][rr] = Pn[rr] + Mn[rr]
+            y[limb][rr + 6] = Pn[rr] - Mn[rr]
+            assert TWO52 <= y[limb][rr] < 2 * TWO52 and TWO52 <= y[limb][rr + 6] < 2 * TWO52
+    return y
+
+
+def permute_v6(state):
+    s = [(x + c) % 2**64 if x + c < 2**64 else (x + c - 2**64 + EPS) for x, c in zip(state, RC[:12])]  # add_nc
+    r = 0
+    lo = hi = None  # limb-form lanes 1..11 entering a pair
+    while r < 30:
+        if kind(r) == "F":
+            L = [sbox_limbs(x) for x in s]
+            y = mds_plain([a for a, _ in L], [b for _, b in L], r)
+            if r == 3:  # lane 0 to an integer, the others lazily folded
+                s0 = fold(y[0][0], y[1][0])
+                lz = [None] + [lazy_fold(y[0][i], y[1][i]) for i in range(1, 12)]
+            else:
+                s = [fold(y[0][i], y[1][i]) for i in range(12)]
+            r += 1
+        else:
+            # ---- layer A
+            l0 = sbox_limbs(s0)
+            PA, MA = [None, None], [None, None]
+            for limb in range(2):
+                v = [l0[limb]] + [lz[i][limb] for i in range(1, 12)]
+                p = [chk53(v[k] + v[k + 6]) for k in range(6)]
+                m = [chk53(v[k] - v[k + 6]) for k in range(6)]
+                PA[limb], MA[limb] = chains(p, m, [INITS[r][limb][rr][0] for rr in range(6)],
+                                            [INITS[r][limb][rr][1] for rr in range(6)])
+                for rr in range(6):
+                    chk53(PA[limb][rr]), chk53(MA[limb][rr])
+            y0 = [PA[l][0] + MA[l][0] for l in range(2)]
+            y6 = [PA[l][0] - MA[l][0] for l in range(2)]
+            for v in y0 + y6:
+                assert TWO52 <= v < 2 * TWO52
+            # ---- layer B
+            t0 = sbox_limbs(fold(y0[0], y0[1]))
+            y = [[None] * 12, [None] * 12]
+            for limb in range(2):
+                p0 = chk53(t0[limb] + (y6[limb] - TWO52))
+                m0 = chk53(t0[limb] - (y6[limb] - TWO52))
+                p = [p0] + [2 * PA[limb][k] for k in range(1, 6)]
+                m = [m0] + [2 * MA[limb][k] for k in range(1, 6)]
+                Pn, Mn = chains(p, m, [INITS[r + 1][limb][rr][0] for rr in range(6)],
+                                [INITS[r + 1][limb][rr][1] for rr in range(6)])
+                for rr in range(6):
+                    chk53(Pn[rr]), chk53(Mn[rr])
+                    y[limb][rr] = Pn[rr] + Mn[rr]
+                    y[limb][rr + 6] = Pn[rr] - Mn[rr]
+                    assert TWO52 <= y[limb][rr] < 2 * TWO52 and TWO52 <= y[limb][rr + 6] < 2 * TWO52
+            if r + 1 == 25:
+                s = [fold(y[0][i], y[1][i]) for i in range(12)]
+            else:
+                s0 = fold(y[0][0], y[1][0])
+                lz = [None] + [lazy_fold(y[0][i], y[1][i]) for i in range(1, 12)]
+            r += 2
+    return s
+
+
+def permute_ref(state):
+    s = [x % P for x in state]
+    for r in range(30):
+        s = [(x + c) % P for x, c in zip(s, RC[12 * r : 12 * r + 12])]
+        if r < 4 or r >= 26:
+            s = [pow(x, 7, P) for x in s]
+        else:
+            s[0] = pow(s[0], 7, P)
+        s = [(sum(CIRC[(k - i) % 12] * s[k] for k in range(12)) + (8 * s[0] if i == 0 else 0)) % P for i in range(12)]
+    return s
+
+
+def bits(x):
+    assert float(x) == x
+    return struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        rnd = random.Random(1)
+        cases = [[0] * 12, [M64] * 12, [P - 1] * 12, [EPS] * 12, [2**32] * 12]
+        cases += [[rnd.getrandbits(64) for _ in range(12)] for _ in range(int(sys.argv[2]))]
+        for st in cases:
+            got = [x % P for x in permute_v6(st)]
+            assert got == permute_ref(st), st
+        print("v6 model == plain permutation on", len(cases), "states")
+        return
+    if len(sys.argv) > 2 and sys.argv[1] == "--corners":
+        # every FP64 bound (asserts in the model) with the limb-form values pinned to the corners of their ranges
+        # instead of coming from real S-boxes / folds: the row sums are monotone in them
+        rnd = random.Random(2)
+        g = globals()
+        real_fold, real_lazy = fold, lazy_fold
+
+        def corner_sbox(x):
+            return rnd.choice([0, 2**33 + 2**32 - 1]), rnd.choice([0, 2**33 - 2])
+
+        def corner_lazy(ya, yb):
+            real_lazy(ya, yb)  # its own asserts
+            return rnd.choice([0, 2**32 + 2**18 - 1]), rnd.choice([0, 2**32 + 2**19])
+
+        g["sbox_limbs"], g["lazy_fold"] = corner_sbox, corner_lazy
+        for _ in range(int(sys.argv[2])):
+            permute_v6([0] * 12)
+        print("FP64 bounds hold on", sys.argv[2], "corner walks")
+        return
+    path = os.path.join(here, "..", "city_rollup_b200", "csrc", "poseidon_rc_v6.inc")
+    with open(path, "w") as f:
+        f.write("/* Generated by tools/gen_poseidon_v6_tables.py from poseidon_rc.inc: chain initialisers (P_init, M_init) of the\n"
+                " * v6 MDS layers per round, limb set (lo, hi) and row pair, with the S-box / lazy-fold limb offsets removed;\n"
+                " * double bit patterns. */\n")
+        n = 0
+        for r in range(30):
+            for limb in range(2):
+                for rr in range(6):
+                    a, b = INITS[r][limb][rr]
+                    f.write("  0x%016xull, 0x%016xull,%s" % (bits(a), bits(b), "\n" if n % 2 == 1 else ""))
+                    n += 1
+    print(n * 2, "entries ->", path)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,7 @@
 // launch bounds (occupancy vs registers).  Development tool; prints clk/perm/SM at the max clock.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../city_rollup_b200/csrc -o poseidon_bench poseidon_bench.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "poseidon.cuh"
 
@@ -145,5 +146,14 @@ int main() {
   run<128, 6>(d, p.multiProcessorCount);
   run<128, 8>(d, p.multiProcessorCount);
   run<64, 8>(d, p.multiProcessorCount);
+  {  // the same launch sequence leaves the same buffer behind whatever the schedule: compare across builds
+    size_t n = (size_t)p.multiProcessorCount * 8 * 4 * 256;
+    uint64_t* h = (uint64_t*)malloc(n * 8);
+    cudaMemcpy(h, d, n * 8, cudaMemcpyDeviceToHost);
+    uint64_t x = 0;
+    for (size_t i = 0; i < n; i++) x = x * 0x9E3779B97F4A7C15ull + h[i];
+    printf("buffer checksum %016llx\n", (unsigned long long)x);
+    free(h);
+  }
   return 0;
 }
