@@ -9,3 +9,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/prove_launches_$V.csv python tools/prove_once.py > gpurun_out/ncu_prove_$V.log 2>&1
 python tools/prove_trace.py 2>&1 | tail -10 > gpurun_out/prove_trace_$V.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+# one ncu --set full capture of the dominant kernel (after the plain runs above), raw page exported next to it
+ncu --set full --clock-control none --import-source on -k regex:k_leaf_hash_colmajor -c 1 -f -o gpurun_out/prof_leaf_$V python bench.py --steps 1 --warmup 1 --no-m2 --no-m1 --no-cpu-baseline > gpurun_out/ncu_full_$V.log 2>&1
+ncu -i gpurun_out/prof_leaf_$V.ncu-rep --page raw --csv > gpurun_out/prof_leaf_${V}_ncu_raw.csv 2>/dev/null
