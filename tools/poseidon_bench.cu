@@ -94,6 +94,55 @@ __global__ void k_coop_parts(uint64_t* io, int iters, long long* cycles) {
   if (threadIdx.x == 0) cycles[0] = (t1 - t0) / iters, cycles[1] = (t2 - t1) / iters;
 }
 
+// ---- throughput of the two instruction streams on their own (what bounds the permutation kernels?) ----------
+// KIND 0: twelve independent S-boxes per iteration (integer pipes only); 1: one FP64 MDS layer per iteration (both
+// limb sets, values fed back: the arithmetic is data independent); 2: both, independent of each other.
+template <int KIND>
+__global__ void __launch_bounds__(256, 2) k_stream(uint64_t* io, int iters) {
+  size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  uint64_t s[12];
+  double b[12], y[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = io[t] + i, b[i] = (double)(i + 1) + (double)(uint32_t)io[t];
+  for (int it = 0; it < iters; it++) {
+    if (KIND == 0 || KIND == 2) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = poseidon::sbox7(s[i]);
+    }
+    if (KIND == 1 || KIND == 2) {
+      poseidon::mds_limbs_biased(b, poseidon::RCF + 24 * (it % 30), y);
+      poseidon::mds_limbs_biased(y, poseidon::RCF + 24 * (it % 30) + 12, b);
+    }
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= s[i] ^ (uint64_t)__double_as_longlong(b[i]);
+  io[t] = r;
+}
+template <int KIND>
+void run_stream(uint64_t* d, int sms, const char* name) {
+  int blocks = sms * 2 * 4, iters = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_stream<KIND><<<blocks, 256>>>(d, iters);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k_stream<KIND><<<blocks, 256>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  // cycles one scheduler (SM sub-partition) spends per warp iteration: 16 warps per SM = 4 per scheduler
+  double warp_iters_per_smsp = (double)blocks * 8 * iters / (sms * 4.0);
+  printf("stream %-28s: %.3f ms, %.1f cycles per warp iteration per scheduler\n", name, best,
+         best * 1e-3 * 1.965e9 / warp_iters_per_smsp);
+}
+
 int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
@@ -138,6 +187,9 @@ int main() {
     }
     printf("single-thread permutation latency: %lld cycles\n", hc);
   }
+  run_stream<0>(d, p.multiProcessorCount, "12 S-boxes");
+  run_stream<1>(d, p.multiProcessorCount, "2 MDS limb sets (FP64)");
+  run_stream<2>(d, p.multiProcessorCount, "12 S-boxes + 2 MDS limb sets");
   run<256, 1>(d, p.multiProcessorCount);
   run<256, 2>(d, p.multiProcessorCount);
   run<256, 3>(d, p.multiProcessorCount);
