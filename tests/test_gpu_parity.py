@@ -43,6 +43,19 @@ def test_poseidon_permutation_random_and_noncanonical(ctx):
     assert (got < np.uint64(P)).all()
 
 
+def test_poseidon_permutation_carry_patterns(ctx):
+    """states drawn from the words that stress the carry / borrow paths of the limb-form schedule (all-ones and
+    all-zero 32-bit halves, p - 1, p, 2^64 - 1), plus a larger random batch; bit-exact against the oracle"""
+    rng = np.random.default_rng(23)
+    words = np.array([0, 1, 2**32 - 1, 2**32, 2**32 + 1, 2**64 - 2**32, P - 1, P, P + 1, 2**64 - 1, 2**63, 2**33 - 1],
+                     dtype=np.uint64)
+    states = np.concatenate([words[rng.integers(0, len(words), (2048, 12))],
+                             rand_felts(29, (4096, 12), canonical=False)])
+    got = ctx.poseidon_permute(states)
+    for i in range(states.shape[0]):
+        assert (got[i] == O.permute(states[i])).all(), i
+
+
 def test_k1_k2_zero_hash_chains_on_gpu(ctx, golden_dir):
     """city_crypto/src/hash/cached_zero_hashes.rs:10-1036 and :1039-2066, computed by the CUDA kernels"""
     z = json.load(open(os.path.join(golden_dir, "zero_hashes.json")))
