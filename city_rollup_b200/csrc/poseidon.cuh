@@ -88,6 +88,29 @@ __device__ __forceinline__ uint64_t fold_f64(double ya, double yb) {
   return gl::pack(r0, r1);
 }
 
+// The same for b >= 2^32 (every v6 layer adds 2^32 to its hi row sums and takes 2^64 out of the constant: lift_hi in
+// tools/gen_poseidon_v6_tables.py): -b_hi is then 2^32 - b_hi in 32 bits, its "no borrow" is the carry of a plain add,
+// and a_hi + b_hi - 1 >= 0 — 8 instructions instead of 10.
+__device__ __forceinline__ uint64_t fold_f64_b1(double ya, double yb) {
+  uint32_t a_lo = (uint32_t)__double2loint(ya), a_hw = (uint32_t)__double2hiint(ya);
+  uint32_t b_lo = (uint32_t)__double2loint(yb), b_hw = (uint32_t)__double2hiint(yb);
+  uint32_t nb = P2B_TWO52_HI - b_hw;                          // 2^32 - b_hi
+  uint32_t m1 = a_hw + b_hw - (2u * P2B_TWO52_HI + 1u);       // a_hi + b_hi - 1
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u32 lo,hi,c;\n\t"
+      "add.cc.u32 lo, %2, %4;\n\t"     // a_lo - b_hi + 2^32 [no borrow]
+      "addc.cc.u32 hi, %3, %5;\n\t"    // b_lo + a_hi + b_hi - [borrow]
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, lo, c;\n\t"      // + c * (2^32 - 1)
+      "subc.u32 hi, hi, 0;\n\t"
+      "add.u32 %1, hi, c;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a_lo), "r"(b_lo), "r"(nb), "r"(m1));
+  return gl::pack(r0, r1);
+}
+
 // one limb set: b[k] = the double 2^52 + limb_k (limb_k < 2^42)  ->  y[r] = 2^52 + (MDS limb)[r] + K[r]
 __device__ __forceinline__ void mds_limbs_biased(const double (&b)[12], const unsigned long long* __restrict__ init,
                                                  double (&y)[12]) {
@@ -305,7 +328,7 @@ __device__ __forceinline__ void full_round_v6(uint64_t (&s)[12], const unsigned 
   mds_limbs_biased(blo, init, ylo);
   mds_limbs_biased(bhi, init + 12, yhi);
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = fold_f64(ylo[i], yhi[i]);
+  for (int i = 0; i < 12; i++) s[i] = fold_f64_b1(ylo[i], yhi[i]);
 }
 
 // Two consecutive partial rounds r, r + 1.  s0 = lane 0 (a 64-bit integer: it passes the S-boxes), zlo / zhi[1..11] =
@@ -346,7 +369,7 @@ __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo
   const double y0l = dadd(Pl[0], Ml[0]), y0h = dadd(Ph[0], Mh[0]);  // lanes 0 and 6 (biased): the only outputs formed
   const double y6l = dsub(Pl[0], Ml[0]), y6h = dsub(Ph[0], Mh[0]);
   // ---- second layer
-  sbox7_limbs(fold_f64(y0l, y0h), b0l, b0h);
+  sbox7_limbs(fold_f64_b1(y0l, y0h), b0l, b0h);
   mds_chain_init(Ql, Nl, initB);
   mds_chain_init(Qh, Nh, initB + 12);
 #define P2B_PR_K(k)                                   \
@@ -358,7 +381,7 @@ __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo
   pm_from_biased(b0h, y6h, p0h, m0h);
   mds_terms_k<0>(Ql, Nl, p0l, m0l);
   mds_terms_k<0>(Qh, Nh, p0h, m0h);
-  s0 = fold_f64(dadd(Ql[0], Nl[0]), dadd(Qh[0], Nh[0]));
+  s0 = fold_f64_b1(dadd(Ql[0], Nl[0]), dadd(Qh[0], Nh[0]));
   lazy_fold(dsub(Ql[0], Nl[0]), dsub(Qh[0], Nh[0]), zlo[6], zhi[6]);
 #pragma unroll
   for (int i = 1; i < 6; i++) {

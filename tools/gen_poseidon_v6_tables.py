@@ -100,6 +100,15 @@ def lift(r):
     return [2**47] * 12  # B: 272 * (what the chained rows of A can be short of) + its own lane 0
 
 
+def lift_hi(r):
+    """2^32 added to the hi row sum i (and 2^64 = 2^32 - 1 mod p taken out of the constant): the 64-bit fold of
+    poseidon::fold_f64 then always sees b_hi >= 1 and needs no separate borrow path.  Rows that are never formed
+    (the chained row pairs of an A layer) get nothing."""
+    if kind(r) == "A":
+        return [1 if i % 6 == 0 else 0 for i in range(12)]
+    return [1] * 12
+
+
 def layer_inits(r):
     """chain initialisers of the MDS layer of round r: [limb][row pair] = (P_init, M_init)"""
     kd = kind(r)
@@ -115,7 +124,8 @@ def layer_inits(r):
     Po, Mo = chains(p, m, [0] * 6, [0] * 6)
     row_off = [Po[i] + Mo[i] for i in range(6)] + [Po[i] - Mo[i] for i in range(6)]
     Z = lift(r)
-    k = [(RC[12 * (r + 1) + i] - Z[i]) % P for i in range(12)]
+    Zh = lift_hi(r)
+    k = [(RC[12 * (r + 1) + i] - Z[i] - (Zh[i] << 64)) % P for i in range(12)]
     out = [[None] * 6, [None] * 6]
     for rr in range(6):
         best = None
@@ -127,8 +137,8 @@ def layer_inits(r):
                         best = (cost, a, b)
         assert best is not None
         _, a, b = best
-        c = [a[0] + Z[rr] - row_off[rr], a[1]]
-        d = [b[0] + Z[rr + 6] - row_off[rr + 6], b[1]]
+        c = [a[0] + Z[rr] - row_off[rr], a[1] + (Zh[rr] << 32)]
+        d = [b[0] + Z[rr + 6] - row_off[rr + 6], b[1] + (Zh[rr + 6] << 32)]
         for limb in range(2):
             assert (c[limb] + d[limb]) % 2 == 0
             pi, mi = (c[limb] + d[limb]) // 2, (c[limb] - d[limb]) // 2
@@ -175,7 +185,25 @@ def sbox_limbs(x):
 
 
 def fold(ya, yb):
-    """poseidon::fold_f64 on the biased doubles ya, yb: the u64 it returns"""
+    """poseidon::fold_f64 on the biased doubles ya, yb: the u64 it returns.  Needs b >= 2^32 (lift_hi)."""
+    a, b = ya - TWO52, yb - TWO52
+    assert 0 <= a < 2**51 and 2**32 <= b < 2**51
+    a_lo, a_hi, b_lo, b_hi = a & M32, a >> 32, b & M32, b >> 32
+    nb = (2**32 - b_hi) & M32
+    m1 = a_hi + b_hi - 1
+    lo = a_lo + nb
+    cf = lo >> 32
+    lo &= M32
+    hi = b_lo + m1 + cf
+    c = hi >> 32
+    hi &= M32
+    r = (hi << 32 | lo) + c * EPS
+    assert r <= M64
+    return r
+
+
+def fold_any(ya, yb):
+    """poseidon::fold_f64_any: the same without the b >= 2^32 requirement (limbs that did not come out of a lifted layer)"""
     a, b = ya - TWO52, yb - TWO52
     assert 0 <= a < 2**51 and 0 <= b < 2**51
     a_lo, a_hi, b_lo, b_hi = a & M32, a >> 32, b & M32, b >> 32
@@ -186,6 +214,14 @@ def fold(ya, yb):
     if r > M64:
         r = (r & M64) + EPS
         assert r <= M64
+    return r
+
+
+def sub_nc(a, b):
+    """gl::sub_nc for canonical b"""
+    r = a - b
+    if r < 0:
+        r = (r - EPS) & M64
     return r
 
 
@@ -222,11 +258,10 @@ def permute_v6(state):
         if kind(r) == "F":
             L = [sbox_limbs(x) for x in s]
             y = mds_plain([a for a, _ in L], [b for _, b in L], r)
-            if r == 3:  # lane 0 to an integer, the others lazily folded
-                s0 = fold(y[0][0], y[1][0])
-                lz = [None] + [lazy_fold(y[0][i], y[1][i]) for i in range(1, 12)]
-            else:
-                s = [fold(y[0][i], y[1][i]) for i in range(12)]
+            s = [fold(y[0][i], y[1][i]) for i in range(12)]
+            if r == 3:  # limbs_from_u64: what a lazy fold would have produced
+                s0 = s[0]
+                lz = [None] + [((s[i] & M32) + OL, s[i] >> 32) for i in range(1, 12)]
             r += 1
         else:
             # ---- layer A
@@ -259,11 +294,10 @@ def permute_v6(state):
                     y[limb][rr] = Pn[rr] + Mn[rr]
                     y[limb][rr + 6] = Pn[rr] - Mn[rr]
                     assert TWO52 <= y[limb][rr] < 2 * TWO52 and TWO52 <= y[limb][rr + 6] < 2 * TWO52
-            if r + 1 == 25:
-                s = [fold(y[0][i], y[1][i]) for i in range(12)]
-            else:
-                s0 = fold(y[0][0], y[1][0])
-                lz = [None] + [lazy_fold(y[0][i], y[1][i]) for i in range(1, 12)]
+            s0 = fold(y[0][0], y[1][0])
+            lz = [None] + [lazy_fold(y[0][i], y[1][i]) for i in range(1, 12)]
+            if r + 1 == 25:  # back to 64-bit integers for the last four full rounds
+                s = [s0] + [sub_nc(fold_any(TWO52 + lz[i][0], TWO52 + lz[i][1]), OL) for i in range(1, 12)]
             r += 2
     return s
 
