@@ -988,8 +988,9 @@ static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, 
     return bail(fail(ctx, P2B_ERR_CUDA, "event setup failed"));
   // The leaf sponge runs in column ranges as well (hashk::k_leaf_absorb_colmajor, state carried in HBM): the upload
   // is the slower side of the copy/transform pipeline, so without this the GPU idles for most of the transfer and
-  // then hashes for 7 ms; with it the hashing of the first columns covers the rest of the upload.  Ranges of 48
-  // columns (6 permutations per leaf and launch) keep the number of launch tails small.
+  // then hashes for 7 ms; with it the hashing of the first columns covers the rest of the upload.  The first range
+  // is one upload group (16 columns: hashing starts after 0.15 ms of transfer instead of 0.45 ms at 2^16 rows), the
+  // ranges then grow to 48 columns (6 permutations per leaf and launch) to keep the number of launch tails small.
   p2b_tree* t = &b->tree;
   t->ctx = ctx;
   t->n_leaves = N;
@@ -1004,7 +1005,7 @@ static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, 
     dfree(ctx, d_sponge);
     return bail(rc);
   }
-  const size_t hash_span = 48;
+  size_t hash_span = group;
   size_t hashed = 0;
   stage_begin(ctx, ST_H2D);
   size_t gi = 0;
@@ -1036,6 +1037,7 @@ static int batch_from_host_pipelined(p2b_ctx* ctx, const uint64_t* const* cols, 
         break;
       }
       hashed = c1;
+      if (hash_span < 48) hash_span = hash_span * 2 < 48 ? hash_span * 2 : 48;
     }
   }
   dfree(ctx, d_sponge);
