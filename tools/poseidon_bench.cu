@@ -119,6 +119,48 @@ __global__ void __launch_bounds__(256, 2) k_stream(uint64_t* io, int iters) {
   for (int i = 0; i < 12; i++) r ^= s[i] ^ (uint64_t)__double_as_longlong(b[i]);
   io[t] = r;
 }
+// the S-box stream with NSB independent S-boxes per thread and iteration (ILP) at BLOCK x MINB threads per SM (occupancy)
+template <int NSB, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_sbox_ilp(uint64_t* io, int iters) {
+  size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  uint64_t s[NSB];
+#pragma unroll
+  for (int i = 0; i < NSB; i++) s[i] = io[t] + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NSB; i++) s[i] = poseidon::sbox7(s[i]);
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < NSB; i++) r ^= s[i];
+  io[t] = r;
+}
+template <int NSB, int BLOCK, int MINB>
+void run_sbox_ilp(uint64_t* d, int sms) {
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sbox_ilp<NSB, BLOCK, MINB>, BLOCK, 0);
+  int blocks = sms * occ, iters = 3072 / NSB;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_sbox_ilp<NSB, BLOCK, MINB><<<blocks, BLOCK>>>(d, iters);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k_sbox_ilp<NSB, BLOCK, MINB><<<blocks, BLOCK>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  // cycles one scheduler spends per warp S-box
+  double warp_sboxes_per_smsp = (double)blocks * (BLOCK / 32) * iters * NSB / (sms * 4.0);
+  printf("S-box stream: %2d independent per thread, %2d warps/SM: %.1f cycles per warp S-box per scheduler\n", NSB,
+         occ * BLOCK / 32, best * 1e-3 * 1.965e9 / warp_sboxes_per_smsp);
+}
+
 template <int KIND>
 void run_stream(uint64_t* d, int sms, const char* name) {
   int blocks = sms * 2 * 4, iters = 256;
@@ -187,6 +229,17 @@ int main() {
     }
     printf("single-thread permutation latency: %lld cycles\n", hc);
   }
+  run_sbox_ilp<1, 256, 1>(d, p.multiProcessorCount);
+  run_sbox_ilp<1, 256, 4>(d, p.multiProcessorCount);
+  run_sbox_ilp<1, 256, 8>(d, p.multiProcessorCount);
+  run_sbox_ilp<2, 256, 4>(d, p.multiProcessorCount);
+  run_sbox_ilp<4, 256, 1>(d, p.multiProcessorCount);
+  run_sbox_ilp<4, 256, 2>(d, p.multiProcessorCount);
+  run_sbox_ilp<4, 256, 4>(d, p.multiProcessorCount);
+  run_sbox_ilp<4, 256, 8>(d, p.multiProcessorCount);
+  run_sbox_ilp<12, 256, 1>(d, p.multiProcessorCount);
+  run_sbox_ilp<12, 256, 2>(d, p.multiProcessorCount);
+  run_sbox_ilp<12, 256, 3>(d, p.multiProcessorCount);
   run_stream<0>(d, p.multiProcessorCount, "12 S-boxes");
   run_stream<1>(d, p.multiProcessorCount, "2 MDS limb sets (FP64)");
   run_stream<2>(d, p.multiProcessorCount, "12 S-boxes + 2 MDS limb sets");
