@@ -161,6 +161,85 @@ void run_sbox_ilp(uint64_t* d, int sms) {
          occ * BLOCK / 32, best * 1e-3 * 1.965e9 / warp_sboxes_per_smsp);
 }
 
+// ---- the field multiplication in parts: which half of the 31 cycles per multiplication is where? ----------------
+// 12 independent chains per thread.  KIND 0: 64x64->128 product only (words xor-folded back to 64 bits), 1: the
+// 128->64 reduction only (input words derived from the state with two xors), 2: mul_nc_lw, 3: sqr_nc, 4: mul_nc
+template <int KIND>
+__device__ __forceinline__ uint64_t part(uint64_t a, uint64_t b) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+  uint32_t r0, r1;
+  if (KIND == 0) {
+    asm("{\n\t"
+        ".reg .u32 x0,x1,x2,x3;\n\t"
+        "mul.lo.u32 x0, %2, %4;\n\t"
+        "mul.hi.u32 x1, %2, %4;\n\t"
+        "mul.lo.u32 x2, %3, %5;\n\t"
+        "mul.hi.u32 x3, %3, %5;\n\t"
+        "mad.lo.cc.u32 x1, %2, %5, x1;\n\t"
+        "madc.hi.cc.u32 x2, %2, %5, x2;\n\t"
+        "addc.u32 x3, x3, 0;\n\t"
+        "mad.lo.cc.u32 x1, %3, %4, x1;\n\t"
+        "madc.hi.cc.u32 x2, %3, %4, x2;\n\t"
+        "addc.u32 x3, x3, 0;\n\t"
+        "xor.b32 %0, x0, x2;\n\t"
+        "xor.b32 %1, x1, x3;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl::pack(r0, r1);
+  }
+  if (KIND == 1) {
+    asm("{\n\t"
+        ".reg .u32 x0,x1,x2,x3,m,tl,th;\n\t"
+        "mov.u32 x0, %2;\n\t"
+        "mov.u32 x1, %3;\n\t"
+        "xor.b32 x2, %2, %4;\n\t"
+        "xor.b32 x3, %3, %5;\n\t" P2B_GL_REDUCE_LW "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl::pack(r0, r1);
+  }
+  if (KIND == 2) return gl::mul_nc_lw(a, b);
+  if (KIND == 3) return gl::sqr_nc(a);
+  return gl::mul_nc(a, b);
+}
+template <int KIND>
+__global__ void __launch_bounds__(256, 2) k_parts(uint64_t* io, int iters) {
+  size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  uint64_t s[12], c[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = io[t] + i, c[i] = io[t] * (2 * i + 3);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = part<KIND>(s[i], c[i]);
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= s[i];
+  io[t] = r;
+}
+template <int KIND>
+void run_parts(uint64_t* d, int sms, const char* name) {
+  int blocks = sms * 2 * 4, iters = 1024;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_parts<KIND><<<blocks, 256>>>(d, iters);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k_parts<KIND><<<blocks, 256>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  double warp_ops_per_smsp = (double)blocks * 8 * iters * 12 / (sms * 4.0);
+  printf("part %-34s: %.2f cycles per warp operation per scheduler\n", name, best * 1e-3 * 1.965e9 / warp_ops_per_smsp);
+}
+
 template <int KIND>
 void run_stream(uint64_t* d, int sms, const char* name) {
   int blocks = sms * 2 * 4, iters = 256;
@@ -229,6 +308,11 @@ int main() {
     }
     printf("single-thread permutation latency: %lld cycles\n", hc);
   }
+  run_parts<0>(d, p.multiProcessorCount, "64x64->128 product (+2 xor)");
+  run_parts<1>(d, p.multiProcessorCount, "128->64 reduction (+2 xor)");
+  run_parts<2>(d, p.multiProcessorCount, "mul_nc_lw");
+  run_parts<3>(d, p.multiProcessorCount, "sqr_nc");
+  run_parts<4>(d, p.multiProcessorCount, "mul_nc");
   run_sbox_ilp<1, 256, 1>(d, p.multiProcessorCount);
   run_sbox_ilp<1, 256, 4>(d, p.multiProcessorCount);
   run_sbox_ilp<1, 256, 8>(d, p.multiProcessorCount);
