@@ -45,6 +45,11 @@ EH = [2, 1, 1, -1, -16, 4]
 FULL = [0, 1, 2, 3, 26, 27, 28, 29]
 
 
+def chk53(x):
+    assert abs(x) < 2**53, "FP64 exactness bound exceeded"
+    return x
+
+
 def kind(r):
     return "F" if r in FULL else ("A" if r % 2 == 0 else "B")
 
@@ -73,6 +78,38 @@ def chains(p, m, Pi, Mi, scale=None):
             if r == 0 and k == 0:
                 Pn[r] += 2 * m[k]
                 Mn[r] += 2 * p[k]
+    return Pn, Mn
+
+
+HT = [-1, -2, 8, 1, 2, -8]  # (Dh[j] - Dh[j + 3]) / 2 extended antiperiodically; (Dh[j] + Dh[j + 3]) / 2 = [16, 16, 32]
+
+
+def chains_split(p, m, STi, Mi):
+    """The same P[r], M[r] the way the device forms them: the cyclic half (P) is split once more by
+    x^6 - 1 = (x^3 - 1)(x^3 + 1): with u_k = p_k + p_{k+3}, v_k = p_k - p_{k+3} (k < 3),
+        S[r] = sI[r] + 16 (u_0 + u_1 + u_2) + 16 u_{(r+2) mod 3},   T[r] = tI[r] + sum_k HT[(k - r) mod 6] v_k,
+        P[r] = S[r] + T[r],  P[r + 3] = S[r] - T[r]      (30 FP64 instructions instead of 36)
+    STi = [sI[0..2], tI[0..2]] = (P_init[r] +- P_init[r + 3]) / 2.  Every intermediate is checked against 2^53."""
+    u = [chk53(p[k] + p[k + 3]) for k in range(3)]
+    v = [chk53(p[k] - p[k + 3]) for k in range(3)]
+    U = chk53(chk53(u[0] + u[1]) + u[2])
+    Pn = [None] * 6
+    for r in range(3):
+        S = chk53(STi[r] + 16 * U)
+        S = chk53(S + 16 * u[(r + 2) % 3])
+        T = STi[3 + r]
+        for k in range(3):
+            T = chk53(T + HT[(k - r) % 6] * v[k])
+        Pn[r] = chk53(S + T)
+        Pn[r + 3] = chk53(S - T)
+    Pn[0] = chk53(chk53(Pn[0] + 2 * p[0]) + 2 * m[0])
+    Mn = list(Mi)
+    for r in range(6):
+        for k in range(6):
+            _, e = coef(r, k)
+            Mn[r] = chk53(Mn[r] + e * m[k])
+        if r == 0:
+            Mn[r] = chk53(Mn[r] + 2 * p[0])
     return Pn, Mn
 
 
@@ -127,24 +164,38 @@ def layer_inits(r):
     Zh = lift_hi(r)
     k = [(RC[12 * (r + 1) + i] - Z[i] - (Zh[i] << 64)) % P for i in range(12)]
     out = [[None] * 6, [None] * 6]
-    for rr in range(6):
+    for rr in range(3):  # row pairs rr and rr + 3 together: (P_init[rr] +- P_init[rr + 3]) / 2 must be integers
         best = None
         for a in reps(k[rr]):
             for b in reps(k[rr + 6]):
-                if (a[0] + b[0]) % 2 == 0 and (a[1] + b[1]) % 2 == 0:
-                    cost = max(a[0], a[1], b[0], b[1])
-                    if best is None or cost < best[0]:
-                        best = (cost, a, b)
+                if (a[0] + b[0]) % 2 or (a[1] + b[1]) % 2:
+                    continue
+                for a3 in reps(k[rr + 3]):
+                    for b3 in reps(k[rr + 9]):
+                        if (a3[0] + b3[0]) % 2 or (a3[1] + b3[1]) % 2:
+                            continue
+                        if any(((a[l] + b[l]) // 2 + (a3[l] + b3[l]) // 2) % 2 for l in range(2)):
+                            continue
+                        cost = max(a + b + a3 + b3)
+                        if best is None or cost < best[0]:
+                            best = (cost, a, b, a3, b3)
         assert best is not None
-        _, a, b = best
-        c = [a[0] + Z[rr] - row_off[rr], a[1] + (Zh[rr] << 32)]
-        d = [b[0] + Z[rr + 6] - row_off[rr + 6], b[1] + (Zh[rr + 6] << 32)]
+        _, a, b, a3, b3 = best
+        full = {}
+        for q, (aa, bb) in ((rr, (a, b)), (rr + 3, (a3, b3))):
+            c = [aa[0] + Z[q] - row_off[q], aa[1] + (Zh[q] << 32)]
+            d = [bb[0] + Z[q + 6] - row_off[q + 6], bb[1] + (Zh[q + 6] << 32)]
+            for limb in range(2):
+                assert (c[limb] + d[limb]) % 2 == 0
+                pi, mi = (c[limb] + d[limb]) // 2, (c[limb] - d[limb]) // 2
+                if not (kd == "A" and q >= 1):
+                    pi += TWO52
+                full[(limb, q)] = (pi, mi)
         for limb in range(2):
-            assert (c[limb] + d[limb]) % 2 == 0
-            pi, mi = (c[limb] + d[limb]) // 2, (c[limb] - d[limb]) // 2
-            if not (kd == "A" and rr >= 1):
-                pi += TWO52
-            out[limb][rr] = (pi, mi)
+            pa, pb = full[(limb, rr)][0], full[(limb, rr + 3)][0]
+            assert (pa + pb) % 2 == 0
+            out[limb][rr] = ((pa + pb) // 2, full[(limb, rr)][1])        # slot rr: sI[rr]
+            out[limb][rr + 3] = ((pa - pb) // 2, full[(limb, rr + 3)][1])  # slot rr + 3: tI[rr]
     return out
 
 
@@ -152,11 +203,6 @@ INITS = [layer_inits(r) for r in range(30)]
 
 
 # ---- exact model of the device arithmetic ---------------------------------------------------------------
-def chk53(x):
-    assert abs(x) < 2**53, "FP64 exactness bound exceeded"
-    return x
-
-
 def mul_red(a, b):
     """gl::mul_nc / mul_nc_lw / sqr_nc: the u64 they return"""
     x = a * b
@@ -241,7 +287,7 @@ def mds_plain(lo, hi, r):
     for limb, v in enumerate((lo, hi)):
         p = [chk53(v[k] + v[k + 6]) for k in range(6)]
         m = [chk53(v[k] - v[k + 6]) for k in range(6)]
-        Pn, Mn = chains(p, m, [INITS[r][limb][rr][0] for rr in range(6)], [INITS[r][limb][rr][1] for rr in range(6)])
+        Pn, Mn = chains_split(p, m, [INITS[r][limb][rr][0] for rr in range(6)], [INITS[r][limb][rr][1] for rr in range(6)])
         for rr in range(6):
             chk53(Pn[rr]), chk53(Mn[rr])
             y[limb][rr] = Pn[rr] + Mn[rr]
@@ -271,8 +317,8 @@ def permute_v6(state):
                 v = [l0[limb]] + [lz[i][limb] for i in range(1, 12)]
                 p = [chk53(v[k] + v[k + 6]) for k in range(6)]
                 m = [chk53(v[k] - v[k + 6]) for k in range(6)]
-                PA[limb], MA[limb] = chains(p, m, [INITS[r][limb][rr][0] for rr in range(6)],
-                                            [INITS[r][limb][rr][1] for rr in range(6)])
+                PA[limb], MA[limb] = chains_split(p, m, [INITS[r][limb][rr][0] for rr in range(6)],
+                                                  [INITS[r][limb][rr][1] for rr in range(6)])
                 for rr in range(6):
                     chk53(PA[limb][rr]), chk53(MA[limb][rr])
             y0 = [PA[l][0] + MA[l][0] for l in range(2)]
@@ -287,8 +333,8 @@ def permute_v6(state):
                 m0 = chk53(t0[limb] - (y6[limb] - TWO52))
                 p = [p0] + [2 * PA[limb][k] for k in range(1, 6)]
                 m = [m0] + [2 * MA[limb][k] for k in range(1, 6)]
-                Pn, Mn = chains(p, m, [INITS[r + 1][limb][rr][0] for rr in range(6)],
-                                [INITS[r + 1][limb][rr][1] for rr in range(6)])
+                Pn, Mn = chains_split(p, m, [INITS[r + 1][limb][rr][0] for rr in range(6)],
+                                      [INITS[r + 1][limb][rr][1] for rr in range(6)])
                 for rr in range(6):
                     chk53(Pn[rr]), chk53(Mn[rr])
                     y[limb][rr] = Pn[rr] + Mn[rr]
