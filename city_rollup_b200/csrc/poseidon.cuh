@@ -188,7 +188,11 @@ __device__ __forceinline__ void partial_round_pair(uint64_t (&s)[12], const unsi
 //     (p_k = 2 P_k, m_k = 2 M_k) instead of its outputs — 10 outputs, their bias and 15 p / m less per limb set;
 //   * the last multiplication of every S-box is not reduced: the 128-bit product x3:x2:x1:x0 goes to the MDS layer as
 //     the limbs lo = x0 - x2 - x3 + 2^33, hi = x1 + x2 (6 instructions instead of 12 + 2 moves);
-//   * lanes 1..11 between two pairs are folded lazily to limbs of 33 bits (6 instructions instead of 10 + 2 moves).
+//   * lanes 1..11 between two pairs are folded lazily to limbs of 33 bits (6 instructions instead of 10 + 2 moves);
+//   * every layer's hi row sums are lifted by 2^32 (and 2^64 taken out of the constant), which shortens the 64-bit
+//     fold to 8 instructions (fold_f64_b1);
+//   * the P chains of a layer are split once more by x^6 - 1 = (x^3 - 1)(x^3 + 1) (p_rows_split: 31 instead of 37 FP64
+//     instructions per limb set).
 // The constant offsets that keep those limbs non-negative pass through the linear layer and are taken out of the chain
 // initialisers (RC6, tools/gen_poseidon_v6_tables.py — which also checks this schedule operation by operation in
 // exact integer arithmetic, incl. every FP64 bound, against the plain permutation).

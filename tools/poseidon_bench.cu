@@ -1,5 +1,9 @@
 // poseidon_bench.cu — pure permutation throughput of city_rollup_b200/csrc/poseidon.cuh for different
-// launch bounds (occupancy vs registers).  Development tool; prints clk/perm/SM at the max clock.
+// launch bounds (occupancy vs registers), the latency of the warp-cooperative permutation, and the stream / part
+// microbenchmarks behind profiles/r01_poseidon_v6_experiments.md (S-box and FP64 layer streams alone and together,
+// S-box throughput against ILP and occupancy, the field multiplication split into product and reduction).
+// Development tool; prints clk/perm/SM at the max clock and a checksum of the buffer it leaves behind (builds with
+// -DP2B_POSEIDON_V3 / -DP2B_SBOX_V3 select the previous schedule / S-box and must leave the same checksum).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../city_rollup_b200/csrc -o poseidon_bench poseidon_bench.cu
 #include <cstdio>
 #include <cstdlib>
