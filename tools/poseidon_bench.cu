@@ -222,6 +222,28 @@ __global__ void __launch_bounds__(256, 2) k_parts(uint64_t* io, int iters) {
   for (int i = 0; i < 12; i++) r ^= s[i];
   io[t] = r;
 }
+// KIND 5 (round-2 question): the product of chain i and the reduction of chain i + 6 in the same iteration, independent
+// of each other — if this runs at max(20, 24) cycles the two halves of mul_nc fail to overlap because of their
+// dependency (latency / ILP inside a multiplication), if at their sum the two integer pipes do not overlap for this
+// instruction mix whatever the dependencies
+__global__ void __launch_bounds__(256, 2) k_parts_indep(uint64_t* io, int iters) {
+  size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  uint64_t s[12], c[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = io[t] + i, c[i] = io[t] * (2 * i + 3);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      s[i] = part<0>(s[i], c[i]);
+      s[i + 6] = part<1>(s[i + 6], c[i + 6]);
+    }
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= s[i];
+  io[t] = r;
+}
+
 template <int KIND>
 void run_parts(uint64_t* d, int sms, const char* name) {
   int blocks = sms * 2 * 4, iters = 1024;
@@ -317,6 +339,26 @@ int main() {
   run_parts<2>(d, p.multiProcessorCount, "mul_nc_lw");
   run_parts<3>(d, p.multiProcessorCount, "sqr_nc");
   run_parts<4>(d, p.multiProcessorCount, "mul_nc");
+  {
+    int blocks = p.multiProcessorCount * 2 * 4, iters = 1024;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_parts_indep<<<blocks, 256>>>(d, iters);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+      cudaEventRecord(e0);
+      k_parts_indep<<<blocks, 256>>>(d, iters);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < best) best = ms;
+    }
+    double pairs_per_smsp = (double)blocks * 8 * iters * 6 / (p.multiProcessorCount * 4.0);
+    printf("part %-34s: %.2f cycles per warp (product + independent reduction) per scheduler\n", "product || reduction", best * 1e-3 * 1.965e9 / pairs_per_smsp);
+  }
   run_sbox_ilp<1, 256, 1>(d, p.multiProcessorCount);
   run_sbox_ilp<1, 256, 4>(d, p.multiProcessorCount);
   run_sbox_ilp<1, 256, 8>(d, p.multiProcessorCount);
