@@ -75,6 +75,29 @@ __global__ void __launch_bounds__(256) k(uint64_t* out, uint32_t a, uint32_t b) 
           asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
           asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dm), "d"(da));
           asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        } else if (KIND == 18) {  // IMAD.HI + IADD3 1:1
+          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+        } else if (KIND == 19) {  // IMAD.WIDE accumulate + 2 IADD3
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[i]), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+        } else if (KIND == 20) {  // IMAD.WIDE accumulate + 4 IADD3
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[i]), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(b), "r"(a));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+        } else if (KIND == 21) {  // IMAD.WIDE without addend (low word fed back) + 2 IADD3
+          uint64_t t;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"((uint32_t)acc[i]), "r"((uint32_t)(acc[i] >> 32)));
+          acc[i] = t;
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(y[i]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1; add.u32 %0, %0, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+        } else if (KIND == 22) {  // IMAD.WIDE without addend alone
+          uint64_t t;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"((uint32_t)acc[i]), "r"((uint32_t)(acc[i] >> 32)));
+          acc[i] = t;
         } else if (KIND == 17) {  // I2F.F64.U32 conversion
           asm volatile("cvt.rn.f64.u32 %0, %1;" : "=d"(dd[i]) : "r"(x[i]));
           asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(x[i]), "=r"(y[i]) : "d"(dd[i]));
@@ -138,6 +161,12 @@ int main() {
   run<15>("mix_dfma_imadwide", 2, d, sms);
   run<16>("mix_2dfma_imad_iadd3", 4, d, sms);
   run<17>("cvt_f64_u32_plus_mov", 1, d, sms);
+  // do the wide multiplies run beside ALU work? (profiles/r01_poseidon_v6_experiments.md)
+  run<18>("mix_imadhi_iadd3", 2, d, sms);
+  run<19>("mix_imadwide_2iadd3", 3, d, sms);
+  run<20>("mix_imadwide_4iadd3", 5, d, sms);
+  run<21>("mix_imadwide_rz_2iadd3", 3, d, sms);
+  run<22>("imadwide_rz", 1, d, sms);
   printf("  \"note\": \"thread-level instructions per second; per_sm_per_clk normalised to 1965 MHz max clock\"\n}\n");
   return 0;
 }
