@@ -1,16 +1,25 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the B200-native Plonky2 hot path (BASELINE.json).
+"""bench.py — headline benchmark of the B200-native Plonky2 hot path, on BASELINE.json's metric:
+"proofs/sec on qbench worker jobs at 1/2/4/8 B200; LDE+Merkle ms at 2^20 rows".
 
-A *step* is one PolynomialBatch::from_values commit (iNTT -> rate-8 coset LDE -> Poseidon Merkle tree,
-cap_height 4) of BASELINE.json configs[1]: 2^16 rows x 135 wire columns — one GPU, synthetic witnesses
-(SplitMix64).  `value` is whole-job commits/s with the inputs already resident in
-HBM; `e2e` is the same commit through the C-ABI host entry point (p2b_batch_from_values with pinned host
-columns: H2D inside the timed region, cap read back).  With --gpus N (torchrun, one rank per GPU) every
-rank commits its own independent batch — the path shards by independent proof jobs, no collective on the
-data path — and value = N * steps / max-over-ranks time.
+M1 (the line's `value`): complete proofs per second through p2b_prove at the shape of City Rollup's worker jobs —
+2^12 rows x 135 wires (the op circuits are padded to exactly 2^12 rows), the gate set of the op
+circuits (city_common_circuit/src/builder/pad_circuit.rs:31-55 + the in-tree u32 gates), rate 8, cap 4, 16-bit
+proof of work, 28 queries, arities [4,4] (zk_signature2/mod.rs:33-57), synthetic witness.  The job loop mirrors the
+reference's worker (city_rollup_core_worker/src/actors/simple.rs:32-113: pop a job, prove, store the proof) with
+CONTEXTS worker threads per GPU, one p2b context (= one CUDA stream) each — independent jobs, no collective on the
+proof path.  A *step* is PROOFS_PER_STEP proofs per GPU (every worker proves
+PROOFS_PER_STEP / CONTEXTS jobs).
+  value  witness already resident in HBM (p2b_prove_dev), proof read back; device time = CUDA events on the
+         contexts' streams, earliest start to latest stop, max over ranks
+  e2e    the same jobs through p2b_prove with HOST witness buffers: pinned host memory (`value`) and pageable
+         separately allocated columns, plonky2's Vec<PolynomialValues> (`pageable_value`); H2D of the witness and D2H of
+         the proof inside the timed region
+M2: one PolynomialBatch::from_values commit of 2^20 rows x 135 columns (ms), N=1 only, with its stage split.
 
-`--impl reference` times the CPU restatement of the same commit (oracle/, OpenMP, all host threads): the
-reference's own prover is Rust in an un-vendored dependency and cannot be built here.
+`--impl reference` times the CPU prover of the same jobs (oracle/prove.c, C + OpenMP on all host threads — the
+reference's own Rust prover lives in an un-vendored dependency and cannot be built here) on the same
+config / metric / unit, each step a bounded sample (one proof), plus the M2 commit on a scaled sample.
 """
 import argparse
 import json
@@ -18,27 +27,55 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 import numpy as np  # noqa: E402
 
-LOG_N, N_COLS, RATE_BITS, CAP_HEIGHT = 16, 135, 3, 4
-METRIC = "PolynomialBatch commits/sec (LDE+Merkle): 2^16 rows x 135 cols, rate_bits=3, cap_height=4"
-UNIT = "commits/s"
-WORKLOAD = "standalone PolynomialBatch::from_values commit: 2^16 rows x 135 wire columns, rate_bits=3, Poseidon Merkle cap_height=4 (BASELINE.json configs[1])"
+DEGREE_BITS, N_WIRES, RATE_BITS, CAP_HEIGHT = 12, 135, 3, 4
+FP = dict(rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, reduction_arity_bits=[4, 4])
+CONTEXTS = 8
+PROOFS_PER_STEP = 32
+METRIC = "proofs/sec on qbench-shaped worker jobs (2^12 rows x 135 wires, City op-circuit gate set, 28 queries); LDE+Merkle ms at 2^20 rows x 135 cols beside it"
+UNIT = "proofs/s"
+WORKLOAD = ("City Rollup worker proof jobs: CircuitData::prove at 2^12 rows x 135 wires, 21 gate kinds (add_city_common_gates + "
+            "u32 gates), rate_bits=3, cap_height=4, pow 16 bits, 28 queries, arities [4,4], synthetic witness (BASELINE.json "
+            "metric M1 / configs[3] job shape); M2 = standalone commit 2^20 rows x 135 cols")
+M2_LOG_N = 20
 
-# Algorithmic int32-op model of one Poseidon permutation (DESIGN.md "Rooflines"): the oracle's scalar
-# schedule with a field multiplication = 4 32x32 multiplies + 14 32-bit add/carry ops (18), a modular
-# add = 5, and the MDS layer on 32-bit halves = 2*144 multiply-adds + 12 * 6 fold ops:
-#   full round  : 12 lanes * 4 mul * 18 + (288 + 72)           = 1224
-#   partial     : 1 lane  * 4 mul * 18 + (288 + 72)            =  432
-#   first layer : 12 adds * 5                                   =   60
+# Algorithmic int32-op model of one Poseidon permutation: a field multiplication = 4 32x32 multiplies
+# + 14 32-bit add/carry ops (18), a modular add = 5, the MDS layer on 32-bit halves = 2*144 multiply-adds + 12*6 folds:
+#   full round 12 * 4 * 18 + 360 = 1224; partial round 4 * 18 + 360 = 432; first constant layer 60
 OPS_PER_PERM = 8 * 1224 + 22 * 432 + 60  # = 19356
+
+
+def config_dict():
+    """the same keys on both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "rows": 1 << DEGREE_BITS, "wires": N_WIRES, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
+            "pow_bits": 16, "queries": 28, "arity_bits": [4, 4], "gate_set": "city (21 kinds, 6 selector groups)",
+            "proofs_per_step": PROOFS_PER_STEP, "contexts_per_gpu": CONTEXTS,
+            "sharding": "independent proof jobs per GPU, no data-path collective",
+            "l2": "8 proofs in flight x ~60 MB of LDE / coefficient / digest working set each > 126 MB L2; nothing is reused across proofs"}
+
+
+def perms_per_proof(circ_desc):
+    """Poseidon permutations of one proof: leaf sponges and tree nodes of the three commits, FRI layers, PoW mean, transcript"""
+    n, N = 1 << DEGREE_BITS, (1 << DEGREE_BITS) << RATE_BITS
+    nch = circ_desc["num_challenges"]
+    widths = [N_WIRES, nch * (1 + circ_desc["num_partial_products"]), nch * circ_desc["quotient_degree_factor"]]
+    leaf = sum(-(-w // 8) * N for w in widths)
+    nodes = 3 * (N - (1 << CAP_HEIGHT))
+    fri, ln = 0, N
+    for a in FP["reduction_arity_bits"]:
+        ln >>= a
+        fri += ln * ((2 << a) // 8) + ln - (1 << CAP_HEIGHT)
+    return {"leaf": leaf, "nodes": nodes, "fri": fri, "pow_mean": 1 << FP["proof_of_work_bits"], "transcript": 110,
+            "total": leaf + nodes + fri + (1 << FP["proof_of_work_bits"]) + 110}
 
 
 def algorithmic_bytes(n_cols, log_n, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
@@ -46,11 +83,6 @@ def algorithmic_bytes(n_cols, log_n, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT)
     n = 1 << log_n
     N = n << rate_bits
     return 8 * n_cols * n * 2 + 8 * n_cols * N + 2 * (N - (1 << cap_height)) * 32
-
-
-def n_perms(n_cols, log_n, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
-    N = (1 << log_n) << rate_bits
-    return -(-n_cols // 8) * N, N - (1 << cap_height)
 
 
 def load_json(path, default=None):
@@ -109,20 +141,36 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def synth_columns(seed_base, n_cols, log_n, out):
-    from util import rand_felts
-    for c in range(n_cols):
-        out[c] = rand_felts(seed_base + c, 1 << log_n)
+def build_job(pi_hash_fn):
+    """the synthetic City-shaped circuit + witness (tests/plonk_ref.py is the witness generator)"""
+    import plonk_ref as R
+    from test_plonk_oracle import CITY_GATES, CITY_GROUPS
+
+    pis = [7, 2, 3, 4]
+    circ = R.SyntheticCircuit(DEGREE_BITS, CITY_GATES, CITY_GROUPS, 7, pi_hash=[int(x) for x in pi_hash_fn(pis)])
+    return circ, [1, 2, 3, 4], pis
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_commit_seconds(O, cols, reps=1):
-    best = 1e30
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.batch_from_values(cols, RATE_BITS, CAP_HEIGHT, want_leaves=True, want_digests=True)
-        best = min(best, time.perf_counter() - t0)
-    return best
+def cpu_commit_seconds(O, cols):
+    t0 = time.perf_counter()
+    O.batch_from_values(cols, RATE_BITS, CAP_HEIGHT, want_leaves=True, want_digests=True)
+    return time.perf_counter() - t0
+
+
+def cpu_m2_sample(O, budget_s=8.0):
+    """the M2 commit on the CPU, on a row sample scaled linearly to 2^20 rows"""
+    from util import rand_felts
+
+    probe = [rand_felts(0x5EED0001 + c, 1 << 10) for c in range(N_WIRES)]
+    t_probe = cpu_commit_seconds(O, probe)
+    log_rows = 10
+    while log_rows < M2_LOG_N and t_probe * (1 << (log_rows + 1 - 10)) * 1.15 < budget_s:
+        log_rows += 1
+    cols = [rand_felts(0x5EED0001 + c, 1 << log_rows) for c in range(N_WIRES)] if log_rows > 10 else probe
+    dt = cpu_commit_seconds(O, cols)
+    return {"lde_merkle_ms": dt * 1e3 * (1 << (M2_LOG_N - log_rows)), "rows": 1 << M2_LOG_N, "cols": N_WIRES,
+            "sample": f"2^{log_rows} of 2^{M2_LOG_N} rows x {N_WIRES} cols, scaled linearly in rows", "sample_seconds": dt}
 
 
 def run_reference(args):
@@ -133,35 +181,31 @@ def run_reference(args):
     # (libgomp reads the variable when the oracle library is loaded)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import p2oracle as O
-    from util import rand_felts
 
     cores = O.num_threads()
-    # bounded sample: probe a 2^12-row commit, then pick the largest row count whose K+W steps fit ~150 s
-    probe = [rand_felts(0x5EED0001 + c, 1 << 12) for c in range(N_COLS)]
-    t_probe = cpu_commit_seconds(O, probe)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    log_rows = LOG_N
-    while log_rows > 12 and t_probe * (1 << (log_rows - 12)) * 1.15 > budget:
-        log_rows -= 1
-    cols = [rand_felts(0x5EED0001 + c, 1 << log_rows) for c in range(N_COLS)]
-    for _ in range(args.warmup):
-        cpu_commit_seconds(O, cols)
+    circ, digest, pis = build_job(O.hash_no_pad)
+    pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), FP)
+    wv = circ.wire_values()
+    for _ in range(max(1, min(args.warmup, 2))):
+        pd.prove(digest, wv, pis)
+    steps = args.steps
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_commit_seconds(O, cols)
-    dt = (time.perf_counter() - t0) / args.steps
-    frac = (1 << log_rows) / float(1 << LOG_N)
-    value = frac / dt  # commits of the full workload per second (work is linear in rows up to log factors)
-    sample = (f"one full commit per step" if log_rows == LOG_N else
-              f"2^{log_rows} of 2^{LOG_N} rows x {N_COLS} cols per step, scaled linearly in rows")
+    for _ in range(steps):
+        pd.prove(digest, wv, pis)
+    dt = (time.perf_counter() - t0) / steps  # seconds per proof
+    value = 1.0 / dt
+    sample = f"1 proof per step (the CUDA arm's step is {PROOFS_PER_STEP} proofs per GPU); proofs/s = 1 / seconds per proof"
+    m2 = cpu_m2_sample(O)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / frac, "higher_is_better": True,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * PROOFS_PER_STEP, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": config_dict(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "CPU restatement (oracle/, C + OpenMP); the Rust reference cannot be built here"},
+                         "ms_per_proof": dt * 1e3,
+                         "note": "CPU restatement of the prover (oracle/prove.c, C + OpenMP); the Rust reference cannot be built here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "m2_lde_merkle_2p20x135": m2,
         "gpu_launches": 0,
     }
     emit(json.dumps(line))
@@ -169,6 +213,95 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+class ProofFarm:
+    """CONTEXTS worker threads of one GPU, each with its own p2b context / stream, proving the same job shape"""
+
+    def __init__(self, m, device, n_ctx, circ, digest, pis):
+        import torch
+
+        self.m, self.n_ctx, self.digest, self.pis = m, n_ctx, digest, pis
+        self.params = m.FriParams(FP["rate_bits"], FP["cap_height"], FP["proof_of_work_bits"], FP["num_query_rounds"],
+                                  FP["reduction_arity_bits"])
+        self.ctxs = [m.Context(device) for _ in range(n_ctx)]
+        for c in self.ctxs:
+            c.set_blocking_sync(n_ctx > 1)  # sleep while waiting: 8 workers per GPU x 8 GPUs share the host cores
+        self.state = []
+        wv = circ.wire_values()
+        stacked = np.stack(wv)
+        self.dev, self.pinned, self.pageable = [], [], []
+        for c in self.ctxs:
+            cd = m.CircuitData(c, circ.desc())
+            cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), RATE_BITS, False, CAP_HEIGHT, keep_values=True)
+            self.state.append((cd, cs))
+            self.dev.append(torch.from_numpy(stacked.view(np.int64)).cuda())
+            w = c.pinned_empty(stacked.shape)
+            w[:] = stacked
+            self.pinned.append(w)
+            self.pageable.append([col.copy() for col in wv])  # one allocation per column, as plonky2's witness
+        torch.cuda.synchronize()
+        self.n_words = None
+
+    def prove_one(self, i, mode):
+        c = self.ctxs[i]
+        cd, cs = self.state[i]
+        if mode == "dev":
+            return self.m.prove_native_device(c, cd, cs, self.digest, self.dev[i].data_ptr(), self.pis, self.params)
+        src = self.pinned[i] if mode == "pinned" else self.pageable[i]
+        return self.m.prove_native(c, cd, cs, self.digest, src, self.pis, self.params, raw=True)
+
+    def run(self, mode, per_ctx, warm):
+        """every worker: `warm` untimed proofs, a thread barrier, then `per_ctx` timed proofs between its context's
+        CUDA timer events.  -> (device ms from the earliest start to the latest stop, kernels launched, wall s, cpu s)"""
+        bar = threading.Barrier(self.n_ctx + 1)
+        launches = [0] * self.n_ctx
+        err = []
+
+        def worker(i):
+            try:
+                c = self.ctxs[i]
+                for _ in range(warm):
+                    self.prove_one(i, mode)
+                bar.wait()
+                bar.wait()
+                l0 = c.launch_count()
+                c.timer_start()
+                for _ in range(per_ctx):
+                    w = self.prove_one(i, mode)
+                c.timer_stop_ms()
+                launches[i] = c.launch_count() - l0
+                self.n_words = w.size
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+                try:
+                    bar.abort()
+                except Exception:
+                    pass
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(self.n_ctx)]
+        for t in th:
+            t.start()
+        bar.wait()  # all warm
+        self.before_timed()
+        t0, c0 = time.perf_counter(), time.process_time()
+        bar.wait()
+        for t in th:
+            t.join()
+        wall, cpu = time.perf_counter() - t0, time.process_time() - c0
+        if err:
+            raise err[0]
+        ms = max(a.timer_span_ms(b) for a in self.ctxs for b in self.ctxs)
+        return ms, sum(launches), wall, cpu
+
+    def before_timed(self):
+        pass
+
+    def close(self):
+        for (cd, cs), c in zip(self.state, self.ctxs):
+            cs.free()
+            cd.free()
+            c.close()
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -185,125 +318,63 @@ def run_cuda(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = m.Context(local)
-    n = 1 << LOG_N
-    # two independent pinned input batches, alternated between steps (each step's working set, 0.74 GB of
-    # LDE + digests, is itself ~6x the 126 MB L2, so nothing survives in L2 from one step to the next)
-    host = [ctx.pinned_empty((N_COLS, n)) for _ in range(2)]
-    for b, h in enumerate(host):
-        synth_columns(0x5EED0001 + 1000 * b + 100000 * rank, N_COLS, LOG_N, h)
-    dev = [torch.from_numpy(h.view(np.int64).copy()).cuda() for h in host]  # resident copies for the device-timed arm
-    torch.cuda.synchronize()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step_dev(i):
-        b = m.PolynomialBatch.from_values_device(ctx, dev[i & 1].data_ptr(), N_COLS, LOG_N, RATE_BITS, CAP_HEIGHT)
-        b.free()
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
-    def step_e2e(i):
-        h = host[i & 1]
-        b = m.PolynomialBatch.from_values(ctx, h, RATE_BITS, False, CAP_HEIGHT)  # rows of the pinned matrix = columns
-        cap = b.cap  # D2H of the result (16 digests), synchronises
-        b.free()
-        return cap
+    c0 = m.Context(local)
+    circ, digest, pis = build_job(c0.hash_no_pad)
+    c0.close()
+    n_ctx = args.contexts
+    per_ctx_step = max(1, PROOFS_PER_STEP // n_ctx)
+    proofs_per_step = per_ctx_step * n_ctx
+    farm = ProofFarm(m, local, n_ctx, circ, digest, pis)
+    farm.before_timed = barrier  # every rank's workers are warm before any rank starts its timed region
+    warm = args.warmup * per_ctx_step  # W whole warm-up steps
 
-    # ---- device-resident throughput (value) + per-stage roofline timing
-    for i in range(args.warmup):
-        step_dev(i)
-    ctx.synchronize()
-    ctx.profile_enable(True)
-    ctx.profile_read()
-    barrier()
+    # ---- value: witness resident in HBM
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ctx.launch_count()
-    ctx.timer_start()
-    for i in range(args.steps):
-        step_dev(i)
-    ms = ctx.timer_stop_ms()
-    launches = ctx.launch_count() - l0
+    ms_dev, launches, wall_dev, cpu_dev = farm.run("dev", per_ctx_step * args.steps, warm)
     barrier()
     clocks = sampler.stop() if sampler else None
-    stage_ms, stage_launches = ctx.profile_read()
-    ctx.profile_enable(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * args.steps / (ms_max * 1e-3)
+    ms_dev = max_over_ranks(ms_dev)
+    total_proofs = world * proofs_per_step * args.steps
+    value = total_proofs / (ms_dev * 1e-3)
+    launches_all = sum_over_ranks(launches)
 
-    # ---- end-to-end through the host C ABI (pinned host columns -> cap on the host)
-    for i in range(max(1, args.warmup // 2)):
-        step_e2e(i)
+    # ---- e2e: host witness buffers through p2b_prove (pinned, then pageable per-column allocations)
+    ms_pin, _, wall_pin, cpu_pin = farm.run("pinned", per_ctx_step * args.steps, 2)
     barrier()
-    ctx.timer_start()
-    for i in range(args.steps):
-        step_e2e(i)
-    ms_e2e = ctx.timer_stop_ms()
+    ms_pin = max_over_ranks(ms_pin)
+    ms_pag, _, wall_pag, cpu_pag = farm.run("pageable", per_ctx_step * args.steps, 2)
     barrier()
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(t.item()) * 1e-3)
-
-    # ---- M1: complete synthetic proofs per second at the City Rollup shape (BASELINE.json metric, first half).
-    # Independent proof jobs per GPU: every rank proves its own jobs, no collective on the proof
-    # path; the multi-GPU aggregate = all proofs / the slowest rank's wall time.
-    def measure_m1():
-        if args.no_m1:
-            return None
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import prove_bench as PB
-            circ, digest, pis = PB.build_case(device=local)
-            out = {"shape": "2^12 rows x 135 wires, the 13 gate types of the recursion circuits (123 gate constraints), rate 8, cap 4, 16-bit PoW, 28 queries, arities [4,4] "
-                            "(city_common_circuit/src/circuits/zk_signature2/mod.rs:33-57); synthetic witness",
-                   "call": "p2b_prove (witness columns in pinned host memory -> proof words on the host)"}
-            for n_ctx in ((1, 8) if world == 1 else (8,)):
-                n_proofs = 40 * n_ctx
-                barrier()
-                # one context = the reference's one-job-at-a-time worker: spin-wait (lowest latency); several contexts
-                # per GPU: sleep on a blocking-sync event (about 1.2 ms of host CPU per proof instead of a busy core
-                # per waiting thread, which is what lets 8 GPUs x 8 contexts share the box's host cores)
-                # a 40-proof sample lasts 0.17 s and a single host hiccup (the nvidia-smi clock sampler, a page-in)
-                # can add half of that: the one-context figure is the best of three samples, and says so
-                reps = 3 if n_ctx == 1 else 1
-                st, pps, ms_pp = {}, 0.0, 0.0
-                for _ in range(reps):
-                    st_i = {}
-                    pps_i, ms_i = PB.run(n_ctx, n_proofs, circ, digest, pis, device=local, blocking=n_ctx > 1, stats=st_i)
-                    if pps_i > pps:
-                        st, pps, ms_pp = st_i, pps_i, ms_i
-                if world > 1:
-                    tt = torch.tensor([n_proofs / pps], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    pps = world * n_proofs / float(tt.item())
-                out[f"contexts_{n_ctx}"] = {"proofs_per_s": pps, "ms_per_proof_per_context": ms_pp,
-                                            "host_cpu_ms_per_proof": st["cpu_s_per_proof"] * 1e3,
-                                            "host_wait": "block" if n_ctx > 1 else "spin",
-                                            "proofs_per_sample": n_proofs, "samples": reps}
-            if world > 1:
-                out["aggregate"] = "sum over %d GPUs, 8 contexts each; wall time = slowest rank" % world
-            return out
-        except Exception as e:  # noqa: BLE001
-            if world > 1:
-                raise  # a rank that dropped out would leave the others waiting in the barrier
-            return {"error": str(e)[:200]}
-
-    m1 = measure_m1() if world > 1 else None
+    ms_pag = max_over_ranks(ms_pag)
+    n_words = farm.n_words
+    h2d = proofs_per_step * N_WIRES * (1 << DEGREE_BITS) * 8
+    d2h = proofs_per_step * n_words * 8
 
     if rank != 0:
-        ctx.close()
+        farm.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- rooflines (rank 0)
+    # ---- rank 0: one worker alone (the reference's one-job-at-a-time worker) + stage profile for the roofline
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
     hbm_peak = peaks.get("hbm_gbs")
     hbm_src = "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback (B200_PROFILING.md)"
@@ -313,111 +384,140 @@ def run_cuda(args):
     int_src = "measured (profiles/int32_peak.json: IMAD+IADD3 dual-issue microbenchmark)" if int_peak else \
         "nominal 148 SMs x 128 lanes x 1.965 GHz"
     int_peak = int_peak or 148 * 128 * 1.965
-    leaf_perms, node_perms = n_perms(N_COLS, LOG_N)
-    leaf_ms = stage_ms["leaf_hash"] / args.steps
-    tree_ms = stage_ms["tree_levels"] / args.steps
-    ntt_ms = (stage_ms["intt"] + stage_ms["lde"]) / args.steps
     traffic = load_json(os.path.join(ROOT, "profiles", "ncu_traffic.json"), {})
-    leaf_gops = leaf_perms * OPS_PER_PERM / (leaf_ms * 1e-3) / 1e9
-    roofline = {
-        "kernel": "k_leaf_hash_colmajor (Poseidon sponge over the 135-wide LDE rows; %.0f%% of the step)"
-                  % (100.0 * leaf_ms / (ms / args.steps)),
-        "bound": "int32", "achieved": leaf_gops, "peak": int_peak, "unit": "Gop/s (int32)",
-        "frac": leaf_gops / int_peak, "traffic": traffic.get("k_leaf_hash_colmajor"),
-        "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM, "permutations_per_launch": leaf_perms,
-        "ms_per_launch": leaf_ms,
-        "hbm_view": {"bound": "hbm", "algorithmic_bytes_per_launch": 8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS),
-                     "achieved": (8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS)) / (leaf_ms * 1e-3) / 1e9,
-                     "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (8 * N_COLS * (n << RATE_BITS) + 32 * (n << RATE_BITS)) / (leaf_ms * 1e-3) / 1e9 / hbm_peak},
-        "note": "the dominant kernel is integer-pipe bound (SURVEY.md §0.7: ~380 int32 ops per byte against a machine "
-                "balance of ~5), so its roofline is the measured INT32 issue rate; hbm_view gives the same launch against "
-                "the HBM peak (its DRAM traffic equals the algorithmic bytes); the HBM-side kernels are in roofline_hbm",
-    }
-    lde_bytes = 8 * N_COLS * n * 2 + 8 * N_COLS * (n << RATE_BITS)
-    roofline_hbm = {
-        "kernels": "ntt2::k_strided + ntt2::k_row4096 (iNTT + 8 coset NTTs writing the leaf-ordered LDE)",
-        "bound": "hbm", "achieved": lde_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": lde_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("ntt"),
-        "peak_source": hbm_src, "algorithmic_bytes_per_step": lde_bytes, "ms_per_step": ntt_ms,
-        "whole_commit": {"algorithmic_bytes": algorithmic_bytes(N_COLS, LOG_N),
-                         "achieved": algorithmic_bytes(N_COLS, LOG_N) / (ms / args.steps * 1e-3) / 1e9,
-                         "frac": algorithmic_bytes(N_COLS, LOG_N) / (ms / args.steps * 1e-3) / 1e9 / hbm_peak},
-    }
 
-    # ---- CPU baseline beside it (bounded sample, rank 0 only, N=1 only)
+    single = None
+    roofline = None
+    try:
+        c = farm.ctxs[0]
+        c.set_blocking_sync(False)
+        n1 = 24
+        for _ in range(3):
+            farm.prove_one(0, "dev")
+        best = 1e30
+        for _ in range(3):
+            c.timer_start()
+            for _ in range(n1):
+                farm.prove_one(0, "dev")
+            best = min(best, c.timer_stop_ms() / n1)
+        c.profile_enable(True)
+        c.profile_read()
+        for _ in range(n1):
+            farm.prove_one(0, "dev")
+        st_ms, st_cnt = c.profile_read()
+        c.profile_enable(False)
+        c.set_blocking_sync(n_ctx > 1)
+        single = {"proofs_per_s": 1e3 / best, "ms_per_proof": best, "note": "one context, one proof at a time (spin wait), best of 3 x 24",
+                  "stage_ms_per_proof": {k: v / n1 for k, v in st_ms.items() if v}}
+        pp = perms_per_proof(circ.desc())
+        leaf_ms = st_ms["leaf_hash"] / n1
+        leaf_launches = st_cnt["leaf_hash"] / n1
+        leaf_gops = pp["leaf"] * OPS_PER_PERM / (leaf_ms * 1e-3) / 1e9
+        lde_bytes = 8 * (1 << DEGREE_BITS) * (1 << RATE_BITS) * sum(
+            [N_WIRES, 20, 16]) + 32 * 3 * ((1 << DEGREE_BITS) << RATE_BITS)
+        roofline = {
+            "kernel": "k_leaf_hash_colmajor (Poseidon sponge over the LDE rows of the three commits of a proof: 17 + 3 + 2 "
+                      "permutations per leaf, 2^15 leaves), the largest kernel of the step",
+            "bound": "int32", "achieved": leaf_gops, "peak": int_peak, "unit": "Gop/s (int32)", "frac": leaf_gops / int_peak,
+            "traffic": traffic.get("k_leaf_hash_colmajor_m1"),
+            "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM, "permutations_per_proof_in_kernel": pp["leaf"],
+            "ms_per_proof_in_kernel": leaf_ms, "launches_per_proof": leaf_launches,
+            "timed": "CUDA events around the stage on the context's stream, one worker alone (the kernels of 8 workers overlap)",
+            "share_of_single_worker_proof": leaf_ms / best,
+            "whole_proof": {"permutations_per_proof": pp, "achieved_gperm_s": pp["total"] * value / world / 1e9,
+                            "int32_frac_all_permutations": pp["total"] * value / world * OPS_PER_PERM / 1e9 / int_peak,
+                            "note": "all Poseidon work of a proof at the measured proofs/s of one GPU against the INT32 issue peak"},
+            "hbm_view": {"bound": "hbm", "algorithmic_bytes_per_proof": lde_bytes,
+                         "achieved": lde_bytes / (leaf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": lde_bytes / (leaf_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+            "note": "integer-issue bound (SURVEY.md §0.7); `frac` uses the fixed 19356-op scalar model of a permutation; the "
+                    "executed-instruction fraction of the same kernel is in profiles/ (ncu)",
+        }
+    except Exception as e:  # noqa: BLE001
+        single = {"error": str(e)[:200]}
+
+    # ---- CPU baseline beside it (bounded sample, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import p2oracle as O
-        from util import rand_felts
         cores = O.num_threads()
-        probe = [rand_felts(0x5EED0001 + c, 1 << 12) for c in range(N_COLS)]
-        t_probe = cpu_commit_seconds(O, probe)
-        log_rows = LOG_N
-        while log_rows > 12 and t_probe * (1 << (log_rows - 12)) * 1.15 > 25.0:
-            log_rows -= 1
-        cols = [host[0][c][: 1 << log_rows].copy() for c in range(N_COLS)]
-        dt = cpu_commit_seconds(O, cols)
-        frac = (1 << log_rows) / float(n)
-        cpu = {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": ("one full commit" if log_rows == LOG_N else
-                          f"2^{log_rows} of 2^{LOG_N} rows x {N_COLS} cols, scaled linearly in rows"),
-               "seconds": dt,
-               "note": "CPU restatement (oracle/, C + OpenMP) — the Rust reference cannot be built here"}
+        pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), FP)
+        wv = circ.wire_values()
+        ref_words = pd.prove(digest, wv, pis)  # warm-up + the checker: the GPU proof of the same job must equal it
+        same = bool((farm.prove_one(0, "pinned") == ref_words).all())
+        t0, k = time.perf_counter(), 0
+        while k < 3 or (time.perf_counter() - t0 < 12.0 and k < 64):
+            pd.prove(digest, wv, pis)
+            k += 1
+        dt = (time.perf_counter() - t0) / k
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_proof": dt * 1e3,
+               "sample": f"{k} proofs of the same job, one at a time on all host threads",
+               "gpu_proof_equals_cpu_proof": same,
+               "note": "CPU restatement of the prover (oracle/prove.c, C + OpenMP) — the Rust reference cannot be built here"}
+        if not args.no_m2:
+            cpu["m2_lde_merkle_2p20x135"] = cpu_m2_sample(O, 6.0)
+        pd.free()
+    farm.close()
 
-    # ---- M2: LDE+Merkle ms at 2^20 rows x 135 cols (BASELINE.json metric, second half), N=1 only
+    # ---- M2: LDE+Merkle ms at 2^20 rows x 135 cols, N=1 only
     m2 = None
     if world == 1 and not args.no_m2:
         try:
-            big = torch.empty((N_COLS, 1 << 20), dtype=torch.int64, device="cuda")
+            ctx = m.Context(local)
+            big = torch.empty((N_WIRES, 1 << M2_LOG_N), dtype=torch.int64, device="cuda")
             g = torch.Generator(device="cuda")
             g.manual_seed(7)
             big.random_(0, 2**62, generator=g)
+            torch.cuda.synchronize()
             times = []
             ctx.profile_enable(True)
             ctx.profile_read()
-            for i in range(3):
+            for i in range(4):
                 ctx.timer_start()
-                b = m.PolynomialBatch.from_values_device(ctx, big.data_ptr(), N_COLS, 20, RATE_BITS, CAP_HEIGHT)
+                b = m.PolynomialBatch.from_values_device(ctx, big.data_ptr(), N_WIRES, M2_LOG_N, RATE_BITS, CAP_HEIGHT)
                 times.append(ctx.timer_stop_ms())
                 b.free()
                 if i == 0:
                     ctx.profile_read()  # drop the warm-up run
             st, _ = ctx.profile_read()
             ctx.profile_enable(False)
-            ab = algorithmic_bytes(N_COLS, 20)
-            lde_b = 8 * N_COLS * (1 << 20) * 10
-            ntt2 = (st["intt"] + st["lde"]) / 2
-            m2 = {"rows": 1 << 20, "cols": N_COLS, "lde_merkle_ms": min(times[1:]),
-                  "ntt_lde_ms": ntt2, "leaf_hash_ms": st["leaf_hash"] / 2, "tree_levels_ms": st["tree_levels"] / 2,
+            ab = algorithmic_bytes(N_WIRES, M2_LOG_N)
+            lde_b = 8 * N_WIRES * (1 << M2_LOG_N) * 10
+            ntt2 = (st["intt"] + st["lde"]) / 3
+            leaf2 = st["leaf_hash"] / 3
+            leaf_perms = -(-N_WIRES // 8) * ((1 << M2_LOG_N) << RATE_BITS)
+            m2 = {"rows": 1 << M2_LOG_N, "cols": N_WIRES, "lde_merkle_ms": min(times[1:]),
+                  "ntt_lde_ms": ntt2, "leaf_hash_ms": leaf2, "tree_levels_ms": st["tree_levels"] / 3,
                   "ntt_lde_hbm_frac": lde_b / (ntt2 * 1e-3) / 1e9 / hbm_peak,
+                  "ntt_lde_dram_traffic": traffic.get("ntt_2p20"),
                   "whole_commit_hbm_frac": ab / (min(times[1:]) * 1e-3) / 1e9 / hbm_peak,
-                  "poseidon_int32_frac": n_perms(N_COLS, 20)[0] * OPS_PER_PERM / (st["leaf_hash"] / 2 * 1e-3) / 1e9 / int_peak}
+                  "poseidon_int32_frac": leaf_perms * OPS_PER_PERM / (leaf2 * 1e-3) / 1e9 / int_peak,
+                  "leaf_hash_gperm_s": leaf_perms / (leaf2 * 1e-3) / 1e9,
+                  "working_set": "11.9 GB per commit >> L2"}
             del big
+            ctx.close()
         except Exception as e:  # noqa: BLE001
             m2 = {"error": str(e)[:200]}
 
-    # ---- M1 (single GPU; the multi-GPU measurement ran above, before the other ranks left)
-    if world == 1:
-        m1 = measure_m1()
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows": n, "cols": N_COLS, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
-                   "sharding": "independent commits per GPU, no data-path collective",
-                   "l2": "per-step working set 0.74 GB > 126 MB L2; two input batches alternated"},
-        "roofline": roofline, "roofline_hbm": roofline_hbm,
-        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},
+        "config": config_dict() if n_ctx == CONTEXTS else dict(config_dict(), contexts_per_gpu=n_ctx, proofs_per_step=proofs_per_step),
+        "roofline": roofline,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N_COLS * n,
-                "d2h_bytes_per_step": 32 << CAP_HEIGHT, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "m2_lde_merkle_2p20x135": m2,
-        "m1_synthetic_proofs": m1,
+        "e2e": {"value": total_proofs / (ms_pin * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_pin / args.steps, "host_buffers": "pinned (one matrix per worker)",
+                "pageable_value": total_proofs / (ms_pag * 1e-3), "pageable_ms_per_step": ms_pag / args.steps,
+                "pageable_buffers": "135 separately allocated pageable columns per job (plonky2's Vec<PolynomialValues>)",
+                "host_cpu_ms_per_proof": {"dev": cpu_dev / (proofs_per_step * args.steps) * 1e3,
+                                          "pinned": cpu_pin / (proofs_per_step * args.steps) * 1e3,
+                                          "pageable": cpu_pag / (proofs_per_step * args.steps) * 1e3}},
+        "gpu_launches": int(launches_all), "launches_per_proof": launches_all / total_proofs,
+        "clocks": clocks, "single_worker": single, "m2_lde_merkle_2p20x135": m2,
+        "proof_words": n_words,
     }
     emit(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -461,9 +561,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--contexts", type=int, default=CONTEXTS, help="worker threads (p2b contexts) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-m2", action="store_true")
-    ap.add_argument("--no-m1", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     with StdoutGuard() as g:

@@ -28,6 +28,7 @@ SIGNATURES = {
     "p2b_launch_count": (u64, [vp]),
     "p2b_timer_start": (C.c_int, [vp]),
     "p2b_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "p2b_timer_span_ms": (C.c_int, [vp, vp, C.POINTER(C.c_float)]),
     "p2b_profile_enable": (C.c_int, [vp, C.c_int]),
     "p2b_profile_read": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
     "p2b_batch_from_values": (C.c_int, [vp, C.POINTER(u64p), sz, u32, u32, u32, u32, C.POINTER(vp)]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "p2b_batch_dev_lde": (vp, [vp]),
     "p2b_batch_dev_coeffs": (vp, [vp]),
     "p2b_batch_values": (C.c_int, [vp, sz, u64p]),
+    "p2b_batch_lde_col": (C.c_int, [vp, sz, u64p]),
     "p2b_circuit_new": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "p2b_circuit_free": (None, [vp]),
     "p2b_zs_partial_products_commit": (C.c_int, [vp, vp, vp, vp, u64p, u64p, u32, u32, C.POINTER(vp)]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "p2b_prove_openings": (C.c_int, [vp, C.POINTER(vp), sz, vp, sz, vp, vp, u64p, sz]),
     "p2b_proof_len": (sz, [vp, vp, vp, sz]),
     "p2b_prove": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp, u64p, sz]),
+    "p2b_prove_dev": (C.c_int, [vp, vp, vp, u64p, vp, u64p, sz, vp, u64p, sz]),
     "p2b_proof_words": (sz, [vp, vp]),
     "p2b_proof_bincode_len": (sz, [vp, vp]),
     "p2b_proof_to_bincode": (C.c_int, [vp, vp, u64p, sz, C.POINTER(C.c_uint8), sz, C.POINTER(sz)]),

@@ -402,6 +402,14 @@ extern "C" int p2b_timer_stop_ms(p2b_ctx* ctx, float* ms_out) {
   return P2B_OK;
 }
 
+extern "C" int p2b_timer_span_ms(p2b_ctx* first, p2b_ctx* last, float* ms_out) {
+  CHECK_CTX(last);
+  if (!first || !ms_out || first->device != last->device) return fail(last, P2B_ERR_INVALID, "contexts of one device expected");
+  CU(last, cudaEventSynchronize(last->ev1));
+  CU(last, cudaEventElapsedTime(ms_out, first->ev0, last->ev1));
+  return P2B_OK;
+}
+
 // copy `n` u64 from device to a caller (pageable or pinned) buffer, synchronously
 // Device -> caller's buffer.  The caller's memory is normally pageable (a Rust Vec, a numpy array), and a copy into
 // pageable memory makes the driver spin inside cudaMemcpyAsync until everything queued before it has run — for
@@ -1184,6 +1192,15 @@ extern "C" int p2b_batch_values(p2b_batch* b, size_t col, uint64_t* out) {
   return d2h(ctx, out, b->d_values + col * n, n);
 }
 
+extern "C" int p2b_batch_lde_col(p2b_batch* b, size_t col, uint64_t* out) {
+  if (!b || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  if (col >= b->n_cols) return fail(ctx, P2B_ERR_INVALID, "column %zu out of range", col);
+  const size_t N = (size_t)1 << (b->log_n + b->rate_bits);
+  return d2h(ctx, out, b->d_lde + col * N, N);
+}
+
 // ------------------------------------------------------------------------------------------------ PLONK stages
 extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_circuit** out) {
   CHECK_CTX(ctx);
@@ -1767,7 +1784,9 @@ extern "C" int p2b_challenger_import(p2b_challenger* c, const uint64_t* in30) {
   if (!c || !in30) return P2B_ERR_INVALID;
   p2b_ctx* ctx = c->ctx;
   CHECK_CTX(ctx);
-  if (in30[12] > 8 || in30[21] > 8) return fail(ctx, P2B_ERR_INVALID, "buffer length > 8");
+  // Challenger invariant: observe() duplexes as soon as the input buffer holds RATE = 8 elements, so a stored
+  // buffer is always shorter; 8 would make the proof-of-work candidate land in a capacity lane
+  if (in30[12] >= 8 || in30[21] > 8) return fail(ctx, P2B_ERR_INVALID, "input buffer length must be < 8, output buffer length <= 8");
   CU(ctx, cudaMemcpyAsync(c->d_state, in30, frik::CH_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, ctx_sync(ctx));
   return P2B_OK;
@@ -2255,17 +2274,30 @@ extern "C" size_t p2b_proof_len(const p2b_circuit* c, const p2b_batch* cs, const
   return proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
 }
 
-extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
-                         const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
-                         const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+// wire_cols (host column pointers) or d_wires (device, column-major): exactly one is non-null
+static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                      const uint64_t* const* wire_cols, const uint64_t* d_wires, const uint64_t* public_inputs,
+                      size_t n_public_inputs, const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
   CHECK_CTX(ctx);
-  if (!c || !cs || !circuit_digest || !wire_cols || !fp || !proof_out || (n_public_inputs && !public_inputs))
+  if (!c || !cs || !circuit_digest || (!wire_cols && !d_wires) || !fp || !proof_out || (n_public_inputs && !public_inputs))
     return fail(ctx, P2B_ERR_INVALID, "null argument");
   if (c->ctx != ctx || cs->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "handle of another context");
   if (fp->n_layers > P2B_MAX_FRI_LAYERS) return fail(ctx, P2B_ERR_INVALID, "too many FRI layers");
   if (cs->rate_bits != fp->rate_bits) return fail(ctx, P2B_ERR_INVALID, "constants_sigmas rate_bits differ from the FRI parameters");
   const p2b_circuit_desc& d = c->d;
   const uint32_t nch = d.num_challenges, rb = fp->rate_bits, caph = fp->cap_height;
+  {
+    // validate the FRI parameters before any length is derived from them (unsigned underflow otherwise)
+    uint32_t log_len = 0;
+    int rc0 = check_fri_args(ctx, ((size_t)1 << d.degree_bits) << rb, fp->reduction_arity_bits, fp->n_layers, rb, &log_len);
+    if (rc0) return rc0;
+    uint32_t lc = log_len;
+    for (uint32_t l = 0; l < fp->n_layers; l++) {
+      lc -= fp->reduction_arity_bits[l];
+      if (caph > lc) return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds the height %u of FRI layer %u", caph, lc, l);
+    }
+    if (caph > d.degree_bits + rb || cs->cap_height > d.degree_bits + rb) return fail(ctx, P2B_ERR_INVALID, "cap_height too large");
+  }
   size_t fri_len = 0;
   const size_t proof_len = proof_len_impl(c, cs, fp, n_public_inputs, &fri_len);
   if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
@@ -2326,7 +2358,10 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   ctx->launches++;
   mark("setup + pi hash");
   // wires commitment
-  TRY(batch_from_host(ctx, wire_cols, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
+  if (wire_cols)
+    TRY(batch_from_host(ctx, wire_cols, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
+  else
+    TRY(batch_from_dev(ctx, d_wires, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
   mark("wires commit");
   TRY(p2b_challenger_new(ctx, &ch));
   TRY(challenger_observe_dev(ch, d_digest, 4));
@@ -2399,4 +2434,17 @@ extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   return cleanup(P2B_OK);
 #undef TRY
 #undef CUP
+}
+
+extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                         const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                         const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+  if (ctx && !wire_cols) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  return prove_impl(ctx, c, cs, circuit_digest, wire_cols, nullptr, public_inputs, n_public_inputs, fp, proof_out, proof_cap);
+}
+extern "C" int p2b_prove_dev(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                             const uint64_t* d_wire_values, const uint64_t* public_inputs, size_t n_public_inputs,
+                             const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
+  if (ctx && !d_wire_values) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  return prove_impl(ctx, c, cs, circuit_digest, nullptr, d_wire_values, public_inputs, n_public_inputs, fp, proof_out, proof_cap);
 }

@@ -74,6 +74,12 @@ class Context:
         self.check(self.lib.p2b_timer_stop_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def timer_span_ms(self, last):
+        """ms from this context's timer_start to `last`'s timer_stop_ms (contexts of one device working side by side)"""
+        ms = C.c_float()
+        last.check(self.lib.p2b_timer_span_ms(self.h, last.h, C.byref(ms)))
+        return float(ms.value)
+
     STAGES = ("h2d", "intt", "lde", "leaf_hash", "tree_levels", "fri_fold_ntt", "transcript", "other")
 
     def profile_enable(self, on=True):
@@ -294,6 +300,12 @@ class PolynomialBatch:
         o = np.zeros((max(count, 1), 2), np.uint64)
         self.ctx.check(self.ctx.lib.p2b_batch_eval_ext(self.h, _ptr(_felts(point)), first, count, _ptr(o)))
         return o[:count]
+
+    def lde_col(self, col):
+        """the whole LDE of polynomial `col` in leaf order (column `col` of batch.merkle_tree.leaves)"""
+        o = np.zeros(1 << (self.degree_log + self.rate_bits), np.uint64)
+        self.ctx.check(self.ctx.lib.p2b_batch_lde_col(self.h, col, _ptr(o)))
+        return o
 
     def get_lde_values(self, index, step=1):
         """PolynomialBatch::get_lde_values(index, step)"""
@@ -575,6 +587,27 @@ def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
                                 len(public_inputs), C.byref(ps), _ptr(buf), n_words))
     if raw:
         return buf
+    return parse_proof_words(circuit.desc, cs, fri_params, buf, len(public_inputs))
+
+
+def prove_native_device(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values_dev_ptr, public_inputs,
+                        fri_params):
+    """p2b_prove_dev: the witness (num_wires x 2^degree_bits u64, column-major) already lives in HBM -> proof words"""
+    pis = _felts(public_inputs) if len(public_inputs) else np.zeros(1, np.uint64)
+    ps = fri_params.struct()
+    cs = constants_sigmas_commitment
+    n_words = int(ctx.lib.p2b_proof_len(circuit.h, cs.h, C.byref(ps), len(public_inputs)))
+    if n_words == 0:
+        raise P2BError(-1, "inconsistent FRI parameters")
+    buf = np.zeros(n_words, np.uint64)
+    ctx.check(ctx.lib.p2b_prove_dev(ctx.h, circuit.h, cs.h, _ptr(_felts(circuit_digest)), C.c_void_p(wire_values_dev_ptr),
+                                    _ptr(pis), len(public_inputs), C.byref(ps), _ptr(buf), n_words))
+    return buf
+
+
+def parse_proof_words(d, cs, fri_params, buf, n_public_inputs):
+    """flat words (p2b_prove's output) -> proof dict in ProofWithPublicInputs' field names"""
+    n_words = buf.size
     nch, nc, nr = d["num_challenges"], d["num_constants"], d["num_routed_wires"]
     npp, qdf = d["num_partial_products"], d["quotient_degree_factor"]
     cap_words = 4 << fri_params.cap_height
@@ -596,8 +629,8 @@ def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
     widths = [(cs.n_cols, cs.merkle_tree.cap_height), (d["num_wires"], fri_params.cap_height),
               (nch * (1 + npp), fri_params.cap_height), (nch * qdf, fri_params.cap_height)]
     proof["opening_proof"], pos = _parse_fri_proof(buf, pos, widths, d["degree_bits"], fri_params)
-    proof["public_inputs"] = [int(x) for x in buf[pos:pos + len(public_inputs)]]
-    assert pos + len(public_inputs) == n_words
+    proof["public_inputs"] = [int(x) for x in buf[pos:pos + n_public_inputs]]
+    assert pos + n_public_inputs == n_words
     return proof
 
 

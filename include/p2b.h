@@ -72,6 +72,9 @@ uint64_t p2b_launch_count(const p2b_ctx *ctx);
 /* CUDA-event timing on the context's stream (bench.py times kernels on the launching stream). */
 int p2b_timer_start(p2b_ctx *ctx);
 int p2b_timer_stop_ms(p2b_ctx *ctx, float *ms_out); /* synchronises on the stop event */
+/* Several contexts of one device working side by side (one worker thread each): ms from `first`'s
+ * p2b_timer_start event to `last`'s p2b_timer_stop_ms event. */
+int p2b_timer_span_ms(p2b_ctx *first, p2b_ctx *last, float *ms_out);
 
 /* Per-stage device timing (CUDA events recorded on the context's stream around each stage of the
  * batch / FRI pipelines).  Stages: 0 h2d, 1 intt, 2 lde, 3 leaf_hash, 4 tree_levels, 5 fri_fold_ntt,
@@ -125,6 +128,8 @@ int p2b_batch_leaves(p2b_batch *b, uint64_t *out);
 const uint64_t *p2b_batch_dev_lde(const p2b_batch *b);
 const uint64_t *p2b_batch_dev_coeffs(const p2b_batch *b);
 
+/* the whole LDE of polynomial `col` in leaf order: out[j] = batch.merkle_tree.leaves[j][col], j < 2^(log_n+rate_bits) */
+int p2b_batch_lde_col(p2b_batch *b, size_t col, uint64_t *out);
 /* values on H of column `col` (batches built from values with P2B_KEEP_VALUES) -> out[2^log_n] */
 int p2b_batch_values(p2b_batch *b, size_t col, uint64_t *out);
 
@@ -303,6 +308,12 @@ size_t p2b_proof_len(const p2b_circuit *circuit, const p2b_batch *constants_sigm
 int p2b_prove(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
               const uint64_t *circuit_digest, const uint64_t *const *wire_cols, const uint64_t *public_inputs,
               size_t n_public_inputs, const p2b_fri_params *params, uint64_t *proof_out, size_t proof_cap);
+
+/* The same with the witness already in HBM: d_wire_values is a device pointer to num_wires x 2^degree_bits u64,
+ * column-major (a GPU witness generator, or bench.py's device-resident arm).  The proof still lands on the host. */
+int p2b_prove_dev(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+                  const uint64_t *circuit_digest, const uint64_t *d_wire_values, const uint64_t *public_inputs,
+                  size_t n_public_inputs, const p2b_fri_params *params, uint64_t *proof_out, size_t proof_cap);
 
 /* ---------------------------------------------------------------- proof bytes ------------ */
 /* The byte form the reference stores and ships proofs in: `bincode::serialize(&ProofWithPublicInputs)`

@@ -88,6 +88,8 @@ void batch_from_coeffs(const uint64_t *const *cols, size_t n_cols, unsigned log_
   size_t n = (size_t)1 << log_n, N = n << rate_bits;
   unsigned log_N = log_n + rate_bits;
   uint64_t *leaves = leaves_out ? leaves_out : (uint64_t *)malloc(N * n_cols * sizeof(uint64_t));
+  uint32_t *rev = (uint32_t *)malloc(N * sizeof(uint32_t)); /* reverse_index_bits permutation, shared by all columns */
+  for (size_t j = 0; j < N; j++) rev[j] = (uint32_t)bitrev(j, log_N);
 #pragma omp parallel
   {
     uint64_t *buf = (uint64_t *)malloc(N * sizeof(uint64_t));
@@ -96,10 +98,11 @@ void batch_from_coeffs(const uint64_t *const *cols, size_t n_cols, unsigned log_
       memcpy(buf, cols[c], n * sizeof(uint64_t));
       memset(buf + n, 0, (N - n) * sizeof(uint64_t)); /* lde(rate_bits) */
       gl_coset_fft(buf, log_N, 7);                     /* coset_fft(F::coset_shift()) */
-      for (size_t j = 0; j < N; j++) leaves[j * n_cols + c] = buf[bitrev(j, log_N)];
+      for (size_t j = 0; j < N; j++) leaves[j * n_cols + c] = buf[rev[j]];
     }
     free(buf);
   }
+  free(rev);
   if (digests_out || cap_out) {
     size_t n_cap = (size_t)1 << cap_height;
     uint64_t *dg = digests_out ? digests_out : (uint64_t *)malloc(2 * (N - n_cap) * 32 + 32);

@@ -168,6 +168,27 @@ void plonk_compute_quotient_polys(const p2o_circuit *c, unsigned rate_bits, cons
                                   const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
                                   uint64_t *out_chunks);
 
+/* ---- the whole prover (prove.c): what `circuit_data.prove(pw)` runs after witness generation ---- */
+typedef struct {
+  uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds;
+  uint32_t n_layers;
+  uint32_t reduction_arity_bits[16];
+} p2o_fri_params; /* FriParams (city_common_circuit/src/verify_template/ser_data.rs:56-154); same layout as p2b_fri_params */
+/* prover_data.constants_sigmas_commitment + prover_data.sigmas: built once per circuit (CircuitBuilder::build), not per proof.
+ * cs_cols: num_constants + num_routed_wires columns of 2^degree_bits values on H */
+typedef struct p2o_prover_data p2o_prover_data;
+p2o_prover_data *p2o_prover_data_new(const p2o_circuit *c, const uint64_t *const *cs_cols, unsigned rate_bits,
+                                     unsigned cap_height);
+void p2o_prover_data_free(p2o_prover_data *pd);
+void p2o_prover_data_cap(const p2o_prover_data *pd, uint64_t *out);
+/* number of u64 words of a proof (0 on inconsistent parameters); equals p2b_proof_len */
+size_t p2o_proof_len(const p2o_circuit *c, unsigned cs_cap_height, const p2o_fri_params *fp, size_t n_pis);
+/* prove_with_partition_witness from the filled witness onwards; writes the words p2b_prove writes (include/p2b.h) and
+ * returns their number (0 on failure).  The proof-of-work witness is the minimal one. */
+size_t p2o_prove(const p2o_circuit *c, const p2o_prover_data *pd, const uint64_t *circuit_digest,
+                 const uint64_t *const *wire_cols, const uint64_t *public_inputs, size_t n_pis,
+                 const p2o_fri_params *fp, uint64_t *out, size_t out_cap);
+
 unsigned p2o_num_threads(void);
 
 #ifdef __cplusplus

@@ -376,3 +376,59 @@ def eval_gate(kind, p0, p1, wires, consts, pi_hash, max_constraints=256):
     lib().plonk_eval_gate.restype = C.c_uint
     k = lib().plonk_eval_gate(C.byref(g), _p(arr(wires)), _p(arr(consts)), _p(arr(pi_hash)), _p(out))
     return [int(x) for x in out[:k]]
+
+
+# ---- the whole prover (prove.c) ----
+class FriParamsStruct(C.Structure):
+    _fields_ = [("rate_bits", C.c_uint32), ("cap_height", C.c_uint32), ("proof_of_work_bits", C.c_uint32),
+                ("num_query_rounds", C.c_uint32), ("n_layers", C.c_uint32), ("reduction_arity_bits", C.c_uint32 * 16)]
+
+
+def fri_params_struct(fp):
+    """fp: dict(rate_bits, cap_height, proof_of_work_bits, num_query_rounds, reduction_arity_bits)"""
+    ab = list(fp["reduction_arity_bits"])
+    return FriParamsStruct(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], len(ab),
+                           (C.c_uint32 * 16)(*ab))
+
+
+class ProverData:
+    """prover_data.constants_sigmas_commitment of a circuit, built once (not part of a proof's time)"""
+
+    def __init__(self, desc, constants_sigmas_values, fp):
+        L = lib()
+        L.p2o_prover_data_new.restype = C.c_void_p
+        self.desc = desc
+        self.cs = circuit_struct(desc)
+        self.fp = fp
+        cols, ptrs = _colptrs(constants_sigmas_values)
+        self.h = C.c_void_p(L.p2o_prover_data_new(C.byref(self.cs), ptrs, C.c_uint(fp["rate_bits"]), C.c_uint(fp["cap_height"])))
+        self.cap = np.zeros((1 << fp["cap_height"], 4), np.uint64)
+        L.p2o_prover_data_cap(self.h, _p(self.cap))
+
+    def prove(self, circuit_digest, wire_values, public_inputs):
+        """-> the flat proof words (the ones p2b_prove writes)"""
+        L = lib()
+        L.p2o_proof_len.restype = C.c_size_t
+        L.p2o_prove.restype = C.c_size_t
+        fps = fri_params_struct(self.fp)
+        n_pis = len(public_inputs)
+        n_words = int(L.p2o_proof_len(C.byref(self.cs), C.c_uint(self.fp["cap_height"]), C.byref(fps), C.c_size_t(n_pis)))
+        assert n_words, "inconsistent FRI parameters"
+        out = np.zeros(n_words, np.uint64)
+        cols, ptrs = _colptrs(wire_values)
+        pis = arr(public_inputs) if n_pis else np.zeros(1, np.uint64)
+        got = int(L.p2o_prove(C.byref(self.cs), self.h, _p(arr(circuit_digest)), ptrs, _p(pis), C.c_size_t(n_pis),
+                              C.byref(fps), _p(out), C.c_size_t(n_words)))
+        assert got == n_words, "p2o_prove failed"
+        return out
+
+    def free(self):
+        if self.h:
+            lib().p2o_prover_data_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -268,6 +268,46 @@ def test_large_batch_properties_2p20(ctx, m):
     bsum.free()
 
 
+def test_m2_shape_2p20x135_against_oracle(ctx, m):
+    """The M2 shape of BASELINE.json's metric (2^20 rows x 135 columns, rate 8, cap 4) at full size: three sampled
+    columns are compared with the oracle ELEMENT FOR ELEMENT — 2^20 coefficients and 2^23 LDE values each — and eight
+    sampled leaves open against the GPU cap through the oracle's leaf hashing and Merkle verification."""
+    import torch
+
+    log_n, rate, n_cols = 20, 3, 135
+    n, log_N = 1 << log_n, log_n + rate
+    g = torch.Generator(device="cuda")
+    g.manual_seed(135)
+    vals = torch.empty((n_cols, n), dtype=torch.int64, device="cuda")
+    vals.random_(0, 2**62, generator=g)
+    vals[67] -= 2**62  # a column with words >= 2^63, incl. non-canonical ones
+    vals[67, 5] = -1
+    torch.cuda.synchronize()
+    batch = m.PolynomialBatch.from_values_device(ctx, vals.data_ptr(), n_cols, log_n, rate, 4)
+    cap = batch.cap
+    rev = np.arange(1 << log_N, dtype=np.uint64)
+    out = np.zeros_like(rev)
+    for b in range(log_N):  # vectorised reverse_index_bits
+        out |= ((rev >> np.uint64(b)) & np.uint64(1)) << np.uint64(log_N - 1 - b)
+    ref_lde = {}
+    for c in (0, 67, 134):
+        col = vals[c].cpu().numpy().view(np.uint64)
+        coeffs = O.ifft(col)
+        assert (batch.coeffs(c) == coeffs).all(), "coefficients of column %d" % c
+        padded = np.zeros(1 << log_N, np.uint64)
+        padded[:n] = coeffs
+        ref_lde[c] = O.coset_fft(padded, 7)[out]  # leaf j holds LDE row bitrev(j)
+        assert (batch.lde_col(c) == ref_lde[c]).all(), "LDE of column %d" % c
+    for j in (0, 1, (1 << log_N) - 1, 5 << 19, 1234567, 7654321, 1 << 22, (1 << 22) + 1):
+        leaf = batch.leaf(j)
+        for c, lde in ref_lde.items():
+            assert leaf[c] == lde[j]
+        assert O.merkle_verify(leaf, j, batch.merkle_tree.prove(j), cap)
+    batch.free()
+    del vals
+    torch.cuda.empty_cache()
+
+
 def test_config3_commit_2p20x400_properties(ctx, m):
     """BASELINE.json configs[2]: the 2^20 rows x 400 columns commit at full size (33.6 GB on the device).  No oracle
     run at this size; size-independent properties instead: sampled leaves open against the cap (oracle hashing of

@@ -9,7 +9,7 @@ import pytest
 import p2oracle as O
 import plonk_ref as R
 import verifier_ref as V
-from test_plonk_oracle import ALL_GATES, RECURSION_GATES, RECURSION_GROUPS
+from test_plonk_oracle import ALL_GATES, CITY_GATES, CITY_GROUPS, RECURSION_GATES, RECURSION_GROUPS
 from test_prove_oracle import FP_SMALL, make_case
 
 pytestmark = pytest.mark.gpu
@@ -63,6 +63,53 @@ def test_gpu_proof_equals_oracle_proof_and_verifies(ctx, m, degree_bits, gates, 
     assert (cs_cap == ref_cs_cap).all()
     assert V.proofs_equal(got, ref) is None, V.proofs_equal(got, ref)
     assert V.verify(circ, cs_cap, digest, got, fp)
+
+
+@pytest.mark.parametrize("name,gates,groups,seed", [
+    ("recursion", RECURSION_GATES, RECURSION_GROUPS, 61),  # the gate set of the proofs stored in qbench_data/example.bin
+    ("city", CITY_GATES, CITY_GROUPS, 62),                 # add_city_common_gates + the in-tree u32 gates: bench.py's M1 circuit
+])
+def test_city_shape_proof_equals_c_oracle(ctx, m, name, gates, groups, seed):
+    """EXACTLY the M1 case of bench.py — 2^12 rows x 135 wires, 28 queries, 16-bit PoW, arities [4, 4] — through p2b_prove
+    (host witness) and p2b_prove_dev (witness in HBM), word for word against the C oracle prover (oracle/prove.c), and
+    through the restated verifier."""
+    import torch
+
+    circ, digest, pis = make_case(12, gates, groups, seed)
+    cd = m.CircuitData(ctx, circ.desc())
+    cs = m.PolynomialBatch.from_values(ctx, circ.constants_sigmas_values(), 3, False, 4, keep_values=True)
+    params = m.FriParams(3, 4, 16, 28, [4, 4])
+    wv = circ.wire_values()
+    got = m.prove_native(ctx, cd, cs, digest, wv, pis, params, raw=True)
+    dev = torch.from_numpy(np.stack(wv).view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    got_dev = m.prove_native_device(ctx, cd, cs, digest, dev.data_ptr(), pis, params)
+    want, ref_cs_cap = V.oracle_prove_c(circ, digest, pis, FP_CITY)
+    assert (cs.cap == ref_cs_cap).all()
+    assert got.shape == want.shape
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, "%s: first differing proof word %d of %d" % (name, bad[0], want.size)
+    assert (got_dev == want).all(), "p2b_prove_dev differs"
+    assert V.verify(circ, cs.cap, digest, V.parse_proof(circ, FP_CITY, got, len(pis)), FP_CITY)
+    cs.free()
+    cd.free()
+
+
+def test_prove_rejects_inconsistent_fri_parameters(ctx, m):
+    """p2b_prove validates the FRI parameters before deriving any length from them (no unsigned underflow, no
+    misleading 'buffer too small')"""
+    circ, digest, pis = make_case(5, ALL_GATES[:5], [(0, 4), (4, 5)], 63)
+    cd = m.CircuitData(ctx, circ.desc())
+    cs = m.PolynomialBatch.from_values(ctx, circ.constants_sigmas_values(), 3, False, 2, keep_values=True)
+    for bad in (m.FriParams(3, 2, 6, 4, [4, 4, 4]),      # reduces below the blow-up
+                m.FriParams(3, 7, 6, 4, [3, 2]),         # cap higher than a layer
+                m.FriParams(3, 2, 6, 4, [3, 7])):        # arity out of range
+        with pytest.raises(m.P2BError):
+            m.prove_native(ctx, cd, cs, digest, circ.wire_values(), pis, bad, raw=True)
+    ok = m.prove_native(ctx, cd, cs, digest, circ.wire_values(), pis, m.FriParams(3, 2, 6, 4, [3, 2]), raw=True)
+    assert ok.size > 0
+    cs.free()
+    cd.free()
 
 
 def test_gpu_openings_match_direct_evaluation(ctx, m):

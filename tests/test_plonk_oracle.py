@@ -30,6 +30,20 @@ RECURSION_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_
                    (R.GATE_ARITHMETIC, 20, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_POSEIDON_MDS, 0, 0),
                    (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_COSET_INTERPOLATION, 4, 6), (R.GATE_POSEIDON, 0, 0)]
 RECURSION_GROUPS = [(0, 6), (6, 10), (10, 12), (12, 13)]
+# The gate set a City Rollup op circuit carries: add_city_common_gates (city_common_circuit/src/builder/pad_circuit.rs:31-55:
+# Constant, Comparison(32, 16), RandomAccess(4), Poseidon, PoseidonMds, Reducing(43), ReducingExtension(32), Arithmetic,
+# ArithmeticExtension, MulExtension, BaseSum<2>, + the coset gate) next to Noop / PublicInput, plus the seven other in-tree
+# u32 gates its gadgets add (city_common_circuit/src/u32/gates/*.rs) — all 21 gate kinds.  Selector groups as plonky2 forms
+# them: gates sorted by degree, packed greedily while group size + max gate degree <= 8.
+CITY_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_POSEIDON_MDS, 0, 0),
+              (R.GATE_BASE_SUM, 63, 0), (R.GATE_REDUCING_EXT, 32, 0),
+              (R.GATE_REDUCING, 43, 0), (R.GATE_U32_INTERLEAVE, 3, 0), (R.GATE_UNINTERLEAVE_TO_U32, 2, 0),
+              (R.GATE_UNINTERLEAVE_TO_B32, 2, 0), (R.GATE_ARITHMETIC_EXT, 10, 0),
+              (R.GATE_ARITHMETIC, 20, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_COMPARISON, 32, 16), (R.GATE_U32_ARITHMETIC, 3, 0),
+              (R.GATE_U32_ADD_MANY, 3, 5), (R.GATE_U32_SUBTRACTION, 6, 0), (R.GATE_U32_RANGE_CHECK, 7, 0),
+              (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_COSET_INTERPOLATION, 4, 6),
+              (R.GATE_POSEIDON, 0, 0)]
+CITY_GROUPS = [(0, 6), (6, 11), (11, 15), (15, 18), (18, 20), (20, 21)]
 # CosetInterpolationGate::with_max_degree(4, max_quotient_degree_factor = 8): degree 6, two intermediates
 COSET_GATES = [(R.GATE_NOOP, 0, 0), (R.GATE_COSET_INTERPOLATION, 4, 6), (R.GATE_CONSTANT, 2, 0), (R.GATE_ARITHMETIC, 20, 0)]
 COSET_GROUPS = [(0, 2), (2, 4)]
@@ -81,6 +95,7 @@ def check_verifier_identity(circ, pr, seed):
     (5, EXT_GATES, EXT_GROUPS, 5),
     (5, COSET_GATES, COSET_GROUPS, 6),
     (6, RECURSION_GATES, RECURSION_GROUPS, 7),
+    (6, CITY_GATES, CITY_GROUPS, 8),
 ])
 def test_quotient_satisfies_verifier_identity(degree_bits, gates, groups, seed):
     circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)

@@ -8,7 +8,7 @@ import pytest
 import p2oracle as O
 import plonk_ref as R
 import verifier_ref as V
-from test_plonk_oracle import ALL_GATES
+from test_plonk_oracle import ALL_GATES, CITY_GATES, CITY_GROUPS
 
 FP_SMALL = dict(rate_bits=3, cap_height=2, proof_of_work_bits=6, num_query_rounds=4, reduction_arity_bits=[3, 2])
 
@@ -50,3 +50,32 @@ def test_tampered_proof_rejected(case, what):
         bad["public_inputs"][0] += 1
     with pytest.raises(V.VerificationError):
         V.verify(circ, cs_cap, digest, bad, FP_SMALL)
+
+
+@pytest.mark.parametrize("degree_bits,gates,groups,seed,fp", [
+    (6, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 41, FP_SMALL),
+    (5, ALL_GATES[:5], [(0, 4), (4, 5)], 42, dict(FP_SMALL, cap_height=0, reduction_arity_bits=[1, 2, 1], num_query_rounds=3)),
+    (7, ALL_GATES, [(0, 4), (4, 5), (5, 8), (8, 10)], 43, dict(FP_SMALL, cap_height=4, reduction_arity_bits=[4], proof_of_work_bits=9)),
+    (6, CITY_GATES, CITY_GROUPS, 44, FP_SMALL),
+])
+def test_c_prover_equals_python_composition(degree_bits, gates, groups, seed, fp):
+    """oracle/prove.c::p2o_prove (the C composition timed by bench.py's reference arm and compared with p2b_prove at
+    the City shape) against the independent Python composition of the same primitives, word for word"""
+    circ, digest, pis = make_case(degree_bits, gates, groups, seed)
+    ref, ref_cap = V.oracle_prove(circ, digest, pis, fp)
+    got, cap = V.oracle_prove_c(circ, digest, pis, fp)
+    assert (cap == ref_cap).all()
+    want = V.flatten_proof(ref)
+    assert got.shape == want.shape
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, "first differing word %d of %d" % (bad[0], want.size)
+
+
+def test_city_gate_set_proof_verifies():
+    """a proof over the gate set of the City Rollup op circuits (all 21 gate kinds, six selector groups) from the C
+    prover is accepted by the restated verifier"""
+    circ, digest, pis = make_case(6, CITY_GATES, CITY_GROUPS, 45)
+    words, cs_cap = V.oracle_prove_c(circ, digest, pis, FP_SMALL)
+    proof = V.parse_proof(circ, FP_SMALL, words, len(pis))
+    assert (V.flatten_proof(proof) == words).all()
+    assert V.verify(circ, cs_cap, digest, proof, FP_SMALL)

@@ -242,3 +242,77 @@ def proofs_equal(a, b):
     if a["public_inputs"] != b["public_inputs"]:
         return "public_inputs"
     return None
+
+
+def flatten_proof(proof):
+    """proof dict -> the flat u64 words p2b_prove / p2o_prove write (include/p2b.h: ProofWithPublicInputs' field
+    order, no length prefixes)"""
+    parts = [np.asarray(proof[k], dtype=np.uint64).reshape(-1)
+             for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap")]
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys"):
+        parts.append(np.asarray(proof["openings"][k], dtype=np.uint64).reshape(-1))
+    fri = proof["opening_proof"]
+    for cap in fri["commit_phase_merkle_caps"]:
+        parts.append(np.asarray(cap, dtype=np.uint64).reshape(-1))
+    for rnd in fri["query_round_proofs"]:
+        for leaf, sib in rnd["initial_trees_proof"]:
+            parts += [np.asarray(leaf, dtype=np.uint64).reshape(-1), np.asarray(sib, dtype=np.uint64).reshape(-1)]
+        for ev, sib in rnd["steps"]:
+            parts += [np.asarray(ev, dtype=np.uint64).reshape(-1), np.asarray(sib, dtype=np.uint64).reshape(-1)]
+    parts.append(np.asarray(fri["final_poly"], dtype=np.uint64).reshape(-1))
+    parts.append(np.array([fri["pow_witness"]], dtype=np.uint64))
+    parts.append(np.array(proof["public_inputs"], dtype=np.uint64).reshape(-1))
+    return np.concatenate(parts)
+
+
+def oracle_prove_c(circ, circuit_digest, public_inputs, fp):
+    """the same proof from the C composition (oracle/prove.c::p2o_prove) -> (flat words, constants_sigmas cap)"""
+    pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), fp)
+    words = pd.prove(circuit_digest, circ.wire_values(), public_inputs)
+    cap = pd.cap.copy()
+    pd.free()
+    return words, cap
+
+
+def parse_proof(circ, fp, words, n_public_inputs):
+    """flat words -> proof dict (inverse of flatten_proof)"""
+    words = np.asarray(words, dtype=np.uint64)
+    nch, nc, nr, nw = circ.num_challenges, circ.num_constants, circ.num_routed, circ.num_wires
+    npp, qdf, cap_h, rb = circ.num_pp, circ.qdf, fp["cap_height"], fp["rate_bits"]
+    log_N = circ.degree_bits + rb
+    pos = 0
+
+    def take(k, shape):
+        nonlocal pos
+        a = words[pos:pos + k].reshape(shape).copy()
+        pos += k
+        return a
+
+    cw = 4 << cap_h
+    proof = dict(wires_cap=take(cw, (-1, 4)), plonk_zs_partial_products_cap=take(cw, (-1, 4)), quotient_polys_cap=take(cw, (-1, 4)))
+    op = {}
+    for k, cnt in (("constants", nc), ("plonk_sigmas", nr), ("wires", nw), ("plonk_zs", nch), ("plonk_zs_next", nch),
+                   ("partial_products", nch * npp), ("quotient_polys", nch * qdf)):
+        op[k] = take(2 * cnt, (-1, 2))
+    proof["openings"] = op
+    caps = [take(cw, (-1, 4)) for _ in fp["reduction_arity_bits"]]
+    rounds = []
+    for _ in range(fp["num_query_rounds"]):
+        initial = []
+        for w in (nc + nr, nw, nch * (1 + npp), nch * qdf):
+            leaf = take(w, (-1,))
+            initial.append((leaf, take(4 * (log_N - cap_h), (-1, 4))))
+        steps, lc = [], log_N
+        for a in fp["reduction_arity_bits"]:
+            lc -= a
+            ev = take(2 << a, (-1, 2))
+            steps.append((ev, take(4 * (lc - cap_h), (-1, 4))))
+        rounds.append(dict(initial_trees_proof=initial, steps=steps))
+    n_final = ((1 << log_N) >> sum(fp["reduction_arity_bits"])) >> rb
+    final_poly = take(2 * n_final, (-1, 2))
+    pow_witness = int(take(1, (-1,))[0])
+    proof["opening_proof"] = dict(commit_phase_merkle_caps=caps, query_round_proofs=rounds, final_poly=final_poly,
+                                  pow_witness=pow_witness)
+    proof["public_inputs"] = [int(x) for x in take(n_public_inputs, (-1,))]
+    assert pos == words.size
+    return proof

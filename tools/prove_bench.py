@@ -15,20 +15,17 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import city_rollup_b200 as m  # noqa: E402
 
 
-def build_case(degree_bits=12, seed=7, device=0):
+def build_case(degree_bits=12, seed=7, device=0, gate_set="city"):
     """synthetic satisfiable circuit over the whole gate set (tests/plonk_ref.py is the witness generator; the
     public-inputs hash comes from the GPU library, not from the oracle)"""
     import plonk_ref as R
 
-    # the 13 gate types of plonky2's standard recursion circuits (the gate set of the proofs stored in the
-    # reference's qbench_data/example.bin: 135 wires, 123 gate constraints), in selector groups that respect the
-    # degree bound group size + gate degree <= 8
-    gates = [(R.GATE_NOOP, 0, 0), (R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_INPUT, 0, 0), (R.GATE_BASE_SUM, 63, 0),
-             (R.GATE_REDUCING_EXT, 32, 0), (R.GATE_REDUCING, 43, 0),
-             (R.GATE_ARITHMETIC_EXT, 10, 0), (R.GATE_ARITHMETIC, 20, 0), (R.GATE_MUL_EXT, 13, 0), (R.GATE_POSEIDON_MDS, 0, 0),
-             (R.GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (R.GATE_COSET_INTERPOLATION, 4, 6),
-             (R.GATE_POSEIDON, 0, 0)]
-    groups = [(0, 6), (6, 10), (10, 12), (12, 13)]
+    # The gate set a City Rollup op circuit carries (city_common_circuit/src/builder/pad_circuit.rs:31-55
+    # add_city_common_gates + the in-tree u32 gates its gadgets add, city_common_circuit/src/u32/gates/*.rs): all 21
+    # gate kinds in the six selector groups plonky2 forms for them (tests/test_plonk_oracle.py CITY_GATES); `recursion`
+    # = the 13 gate types of the proofs stored in qbench_data/example.bin (135 wires, 123 gate constraints).
+    from test_plonk_oracle import CITY_GATES, CITY_GROUPS, RECURSION_GATES, RECURSION_GROUPS
+    gates, groups = (CITY_GATES, CITY_GROUPS) if gate_set == "city" else (RECURSION_GATES, RECURSION_GROUPS)
     pis = [seed, 2, 3, 4]
     c = m.Context(device)
     pih = [int(x) for x in c.hash_no_pad(pis)]
