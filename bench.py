@@ -144,7 +144,7 @@ class ClockSampler:
 def build_job(pi_hash_fn):
     """the synthetic City-shaped circuit + witness (tests/plonk_ref.py is the witness generator)"""
     import plonk_ref as R
-    from test_plonk_oracle import CITY_GATES, CITY_GROUPS
+    from plonk_ref import CITY_GATES, CITY_GROUPS
 
     pis = [7, 2, 3, 4]
     circ = R.SyntheticCircuit(DEGREE_BITS, CITY_GATES, CITY_GROUPS, 7, pi_hash=[int(x) for x in pi_hash_fn(pis)])

@@ -840,3 +840,43 @@ def eval_vanishing_poly_ext(circ, zeta, consts_z, sigmas_z, wires_z, zs_z, zs_ne
             acc = acc * alphas[i] + tv
         out.append(acc)
     return out, z_h, zeta_n
+
+
+# ------------------------------------------------------------------------------------------ gate sets of the test / bench circuits
+ALL_GATES = [(GATE_PUBLIC_INPUT, 0, 0), (GATE_NOOP, 0, 0), (GATE_CONSTANT, 2, 0), (GATE_ARITHMETIC, 20, 0),
+             (GATE_POSEIDON, 0, 0), (GATE_BASE_SUM, 63, 0), (GATE_U32_ARITHMETIC, 3, 0),
+             (GATE_U32_ADD_MANY, 3, 5), (GATE_U32_SUBTRACTION, 6, 0), (GATE_U32_RANGE_CHECK, 7, 0)]
+# the in-tree bit-manipulation / comparison gates, with the parameters the reference registers
+# (city_common_circuit/src/builder/pad_circuit.rs:31-55: ComparisonGate::new(32, 16))
+MORE_GATES = [(GATE_NOOP, 0, 0), (GATE_U32_INTERLEAVE, 3, 0), (GATE_UNINTERLEAVE_TO_U32, 2, 0),
+              (GATE_UNINTERLEAVE_TO_B32, 2, 0), (GATE_COMPARISON, 32, 16), (GATE_POSEIDON, 0, 0)]
+MORE_GROUPS = [(0, 3), (3, 5), (5, 6)]
+# upstream extension-field gates of the recursion gate set, with the parameters standard_recursion_config gives
+# them (ReducingGate(43) / ReducingExtensionGate(32) / RandomAccessGate(bits 4): builder/pad_circuit.rs:31-55)
+EXT_GATES = [(GATE_NOOP, 0, 0), (GATE_ARITHMETIC_EXT, 10, 0), (GATE_MUL_EXT, 13, 0), (GATE_REDUCING, 43, 0),
+             (GATE_REDUCING_EXT, 32, 0), (GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (GATE_POSEIDON_MDS, 0, 0)]
+EXT_GROUPS = [(0, 3), (3, 6), (6, 7)]
+# the 13 gate types of plonky2's standard recursion circuits = the gate set of the proofs stored in
+# qbench_data/example.bin (135 wires, num_gate_constraints 123: zk_signature2/mod.rs:54-57)
+RECURSION_GATES = [(GATE_NOOP, 0, 0), (GATE_CONSTANT, 2, 0), (GATE_PUBLIC_INPUT, 0, 0), (GATE_BASE_SUM, 63, 0),
+                   (GATE_REDUCING_EXT, 32, 0), (GATE_REDUCING, 43, 0), (GATE_ARITHMETIC_EXT, 10, 0),
+                   (GATE_ARITHMETIC, 20, 0), (GATE_MUL_EXT, 13, 0), (GATE_POSEIDON_MDS, 0, 0),
+                   (GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (GATE_COSET_INTERPOLATION, 4, 6), (GATE_POSEIDON, 0, 0)]
+RECURSION_GROUPS = [(0, 6), (6, 10), (10, 12), (12, 13)]
+# The gate set a City Rollup op circuit carries: add_city_common_gates (city_common_circuit/src/builder/pad_circuit.rs:31-55:
+# Constant, Comparison(32, 16), RandomAccess(4), Poseidon, PoseidonMds, Reducing(43), ReducingExtension(32), Arithmetic,
+# ArithmeticExtension, MulExtension, BaseSum<2>, + the coset gate) next to Noop / PublicInput, plus the seven other in-tree
+# u32 gates its gadgets add (city_common_circuit/src/u32/gates/*.rs) — all 21 gate kinds.  Selector groups as plonky2 forms
+# them: gates sorted by degree, packed greedily while group size + max gate degree <= 8.
+CITY_GATES = [(GATE_NOOP, 0, 0), (GATE_CONSTANT, 2, 0), (GATE_PUBLIC_INPUT, 0, 0), (GATE_POSEIDON_MDS, 0, 0),
+              (GATE_BASE_SUM, 63, 0), (GATE_REDUCING_EXT, 32, 0),
+              (GATE_REDUCING, 43, 0), (GATE_U32_INTERLEAVE, 3, 0), (GATE_UNINTERLEAVE_TO_U32, 2, 0),
+              (GATE_UNINTERLEAVE_TO_B32, 2, 0), (GATE_ARITHMETIC_EXT, 10, 0),
+              (GATE_ARITHMETIC, 20, 0), (GATE_MUL_EXT, 13, 0), (GATE_COMPARISON, 32, 16), (GATE_U32_ARITHMETIC, 3, 0),
+              (GATE_U32_ADD_MANY, 3, 5), (GATE_U32_SUBTRACTION, 6, 0), (GATE_U32_RANGE_CHECK, 7, 0),
+              (GATE_RANDOM_ACCESS, 4, 4 | (2 << 16)), (GATE_COSET_INTERPOLATION, 4, 6),
+              (GATE_POSEIDON, 0, 0)]
+CITY_GROUPS = [(0, 6), (6, 11), (11, 15), (15, 18), (18, 20), (20, 21)]
+# CosetInterpolationGate::with_max_degree(4, max_quotient_degree_factor = 8): degree 6, two intermediates
+COSET_GATES = [(GATE_NOOP, 0, 0), (GATE_COSET_INTERPOLATION, 4, 6), (GATE_CONSTANT, 2, 0), (GATE_ARITHMETIC, 20, 0)]
+COSET_GROUPS = [(0, 2), (2, 4)]

@@ -24,7 +24,7 @@ def build_case(degree_bits=12, seed=7, device=0, gate_set="city"):
     # add_city_common_gates + the in-tree u32 gates its gadgets add, city_common_circuit/src/u32/gates/*.rs): all 21
     # gate kinds in the six selector groups plonky2 forms for them (tests/test_plonk_oracle.py CITY_GATES); `recursion`
     # = the 13 gate types of the proofs stored in qbench_data/example.bin (135 wires, 123 gate constraints).
-    from test_plonk_oracle import CITY_GATES, CITY_GROUPS, RECURSION_GATES, RECURSION_GROUPS
+    from plonk_ref import CITY_GATES, CITY_GROUPS, RECURSION_GATES, RECURSION_GROUPS
     gates, groups = (CITY_GATES, CITY_GROUPS) if gate_set == "city" else (RECURSION_GATES, RECURSION_GROUPS)
     pis = [seed, 2, 3, 4]
     c = m.Context(device)
