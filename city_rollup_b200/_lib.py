@@ -36,6 +36,10 @@ SIGNATURES = {
     "p2b_batch_from_values_dev": (C.c_int, [vp, vp, sz, u32, u32, u32, u32, C.POINTER(vp)]),
     "p2b_batch_from_coeffs_dev": (C.c_int, [vp, vp, sz, u32, u32, u32, u32, C.POINTER(vp)]),
     "p2b_batch_free": (None, [vp]),
+    "p2b_batch_attach": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "p2b_batch_export_len": (sz, [vp]),
+    "p2b_batch_export": (C.c_int, [vp, C.POINTER(C.c_uint8), sz, C.POINTER(sz)]),
+    "p2b_batch_import": (C.c_int, [vp, C.POINTER(C.c_uint8), sz, C.POINTER(vp)]),
     "p2b_batch_n_cols": (sz, [vp]),
     "p2b_batch_degree_log": (u32, [vp]),
     "p2b_batch_rate_bits": (u32, [vp]),
@@ -79,6 +83,10 @@ SIGNATURES = {
     "p2b_proof_len": (sz, [vp, vp, vp, sz]),
     "p2b_prove": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp, u64p, sz]),
     "p2b_prove_dev": (C.c_int, [vp, vp, vp, u64p, vp, u64p, sz, vp, u64p, sz]),
+    "p2b_prove_submit": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp]),
+    "p2b_prove_poll": (C.c_int, [vp]),
+    "p2b_prove_collect": (C.c_int, [vp, u64p, sz]),
+    "p2b_plan_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
     "p2b_proof_words": (sz, [vp, vp]),
     "p2b_proof_bincode_len": (sz, [vp, vp]),
     "p2b_proof_to_bincode": (C.c_int, [vp, vp, u64p, sz, C.POINTER(C.c_uint8), sz, C.POINTER(sz)]),

@@ -3,6 +3,7 @@
 // No CPU fallback: every entry point fails with P2B_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 
 #include "../../include/p2b.h"
 #include "fri_kernels.cuh"
+#include "fused_kernels.cuh"
 #include "hash_kernels.cuh"
 #include "ntt2_kernels.cuh"
 #include "ntt_kernels.cuh"
@@ -24,6 +26,31 @@
 #define P2B_VERSION 100
 
 static thread_local std::string g_init_error;
+
+// a captured proof (see "CUDA-graph plans" below)
+struct ProvePlan {
+  enum { SEEN = 0, READY = 1, FAILED = -1 };
+  uint64_t circuit_id = 0, cs_id = 0;
+  p2b_fri_params fp{};
+  size_t n_pis = 0;
+  bool dev_src = false;
+  int state = SEEN;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  // pinned host block the graph's copy nodes read: parameter words and pointer tables, bump-allocated during capture
+  uint64_t* h_pin = nullptr;
+  size_t pin_cap = 0, pin_used = 0;
+  uint64_t *h_digest = nullptr, *h_pis = nullptr;  // slots inside h_pin, refreshed before every launch
+  uint64_t* h_wires = nullptr;                     // pinned staging matrix for host witnesses
+  uint64_t* h_proof = nullptr;                     // pinned: where the graph leaves the proof words
+  uint64_t* d_wires_dst = nullptr;                 // destination of the witness copy node
+  cudaGraphNode_t wires_node{};
+  bool has_wires_node = false;
+  const void* cur_src = nullptr;  // what the witness copy node currently reads
+  size_t proof_len = 0, wires_words = 0;
+  uint32_t n_kernels = 0;
+  uint64_t last_use = 0;
+};
 
 struct p2b_ctx {
   int device = 0;
@@ -85,6 +112,28 @@ struct p2b_ctx {
   // small pinned staging buffer for accessor results
   uint64_t* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // device scratch words of the fused kernels: [0] the "CTAs done" counter of fusedk::k_tree_subtree (self-resetting),
+  // [1] the best proof-of-work witness of the current search
+  uint64_t* d_scratch = nullptr;
+  // old-path (n < 2^12) coset power tables, keyed like cp_cache: FRI layers of every proof reuse the same few
+  struct SmallCp {
+    uint64_t *lo, *hi;
+    uint32_t hi_count;
+  };
+  std::map<CpKey, SmallCp> small_cp_cache;
+  // prove plans (CUDA graphs) and the proof submitted but not yet collected
+  std::vector<ProvePlan*> plans;
+  ProvePlan* cap = nullptr;  // non-null while prove_body runs under stream capture
+  uint64_t plan_clock = 0;
+  std::string plan_note;
+  size_t pending_words = 0, pending_pow_index = 0;
+  const uint64_t* pending_src = nullptr;
+  uint64_t* h_proof = nullptr;  // pinned landing buffer of eagerly proven proofs
+  size_t h_proof_bytes = 0;
+  // completion of the last DMA that read caller-owned pinned memory (host-input entry points wait on it before
+  // returning, so the caller may refill its buffers)
+  cudaEvent_t ev_h2d = nullptr;
+  bool h2d_event_pending = false;
   nttk::Tables tables() const { return nttk::Tables{d_w12, d_rlo, d_rhi}; }
   ntt2::RootTables roots() const { return ntt2::RootTables{d_rlo, d_rhi}; }
 };
@@ -102,8 +151,15 @@ struct p2b_tree {
   bool owned_by_batch = false;
 };
 
+static uint64_t next_object_id() {
+  static std::atomic<uint64_t> n{1};
+  return n.fetch_add(1);
+}
+
 struct p2b_batch {
   p2b_ctx* ctx = nullptr;
+  uint64_t id = next_object_id();  // never reused: prove plans are keyed by it
+  bool view = false;               // a read-only view of another context's batch (p2b_batch_attach): owns nothing
   size_t n_cols = 0;
   uint32_t log_n = 0, rate_bits = 0, cap_height = 0;
   uint64_t* d_coeffs = nullptr;  // n_cols x n
@@ -114,6 +170,7 @@ struct p2b_batch {
 
 struct p2b_circuit {
   p2b_ctx* ctx = nullptr;
+  uint64_t id = next_object_id();
   p2b_circuit_desc d{};
   plonk::Gate* d_gates = nullptr;
   uint64_t* d_k_is = nullptr;
@@ -141,6 +198,9 @@ static int fail(p2b_ctx* ctx, int code, const char* fmt, ...) {
   }
   return code;
 }
+
+static void plans_clear(p2b_ctx* ctx);
+static void plans_forget(p2b_ctx* ctx, uint64_t circuit_id, uint64_t batch_id);
 
 #define CU(ctx, call)                                                                              \
   do {                                                                                             \
@@ -171,11 +231,26 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 static int dmalloc(p2b_ctx* ctx, uint64_t** p, size_t n_u64) {
   *p = nullptr;
   if (n_u64 == 0) n_u64 = 1;
+  if (ctx->cap) {
+    // under stream capture the allocation becomes a memory node of the graph (fixed address, owned by the graph)
+    CU(ctx, cudaMallocAsync((void**)p, n_u64 * sizeof(uint64_t), ctx->stream));
+    return P2B_OK;
+  }
   CU(ctx, cudaMallocFromPoolAsync((void**)p, n_u64 * sizeof(uint64_t), ctx->pool, ctx->stream));
   return P2B_OK;
 }
 static void dfree(p2b_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
+}
+// tables that outlive the call that builds them (caches): never from a plan's arena
+static int dmalloc_persistent(p2b_ctx* ctx, uint64_t** p, size_t n_u64, bool persistent) {
+  if (persistent && ctx->cap)
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "a table cache is cold during stream capture (the first proof of a shape runs eagerly to warm it)");
+  return dmalloc(ctx, p, n_u64);
+}
+static bool trace_enabled() {
+  static const bool v = getenv("P2B_TRACE") != nullptr;
+  return v;
 }
 
 // ---- stage timing -----------------------------------------------------------------------------
@@ -279,6 +354,8 @@ static int ctx_setup(p2b_ctx* ctx) {
   if ((rc = dmalloc(ctx, &ctx->d_t2, 256))) return rc;
   ntt2::k_build_row_tables<<<16, 256, 0, ctx->stream>>>(ctx->roots(), ctx->d_t1, ctx->d_t2);
   LAUNCH_CHECK(ctx);
+  if ((rc = dmalloc(ctx, &ctx->d_scratch, 4))) return rc;
+  CU(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 4 * sizeof(uint64_t), ctx->stream));
   ctx->h_stage_bytes = 1 << 20;
   CU(ctx, cudaMallocHost((void**)&ctx->h_stage, ctx->h_stage_bytes));
   CU(ctx, ctx_sync(ctx));
@@ -332,6 +409,9 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   ctx_sync(ctx);
+  plans_clear(ctx);
+  if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
+  if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
   dfree(ctx, ctx->d_w12);
   dfree(ctx, ctx->d_rlo);
   dfree(ctx, ctx->d_rhi);
@@ -339,6 +419,11 @@ extern "C" void p2b_destroy(p2b_ctx* ctx) {
   dfree(ctx, ctx->d_t2);
   for (auto& kv : ctx->tw_cache) dfree(ctx, kv.second);
   for (auto& kv : ctx->cp_cache) dfree(ctx, kv.second);
+  for (auto& kv : ctx->small_cp_cache) {
+    dfree(ctx, kv.second.lo);
+    dfree(ctx, kv.second.hi);
+  }
+  dfree(ctx, ctx->d_scratch);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (int i = 0; i < 2; i++) {
     if (ctx->h_upload[i]) cudaFreeHost(ctx->h_upload[i]);
@@ -455,7 +540,7 @@ static int ntt2_get_tw(p2b_ctx* ctx, uint32_t log_m, uint32_t d, const uint64_t*
   if (it == ctx->tw_cache.end()) {
     uint64_t* p = nullptr;
     int rc;
-    if ((rc = dmalloc(ctx, &p, (size_t)1 << log_m))) return rc;
+    if ((rc = dmalloc_persistent(ctx, &p, (size_t)1 << log_m, true))) return rc;
     ntt2::k_build_tw<<<cdiv((size_t)1 << log_m, 256), 256, 0, ctx->stream>>>(ctx->roots(), log_m, d, p);
     LAUNCH_CHECK(ctx);
     it = ctx->tw_cache.emplace(key, p).first;
@@ -484,7 +569,10 @@ static int ntt2_get_cp(p2b_ctx* ctx, uint64_t shift, uint32_t log_n, uint32_t ra
     const size_t n = (size_t)1 << log_n, bytes = (n << rate_bits) * 8;
     // bounded cache: FRI layers of different proofs reuse the same few shifts; drop everything if a caller
     // cycles through many distinct domains
+    if (ctx->cap)
+      return fail(ctx, P2B_ERR_UNSUPPORTED, "a table cache is cold during stream capture (the first proof of a shape runs eagerly to warm it)");
     if (ctx->cp_cache_bytes + bytes > ((size_t)4 << 30)) {
+      plans_clear(ctx);  // captured graphs hold pointers into the tables that are about to go
       for (auto& kv : ctx->cp_cache) dfree(ctx, kv.second);
       ctx->cp_cache.clear();
       ctx->cp_cache_bytes = 0;
@@ -682,8 +770,18 @@ static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uin
   uint64_t *d_lo = nullptr, *d_hi = nullptr;
   uint32_t hi_count = (uint32_t)(n > 4096 ? n >> 12 : 1);
   int rc;
-  if ((rc = dmalloc(ctx, &d_lo, (size_t)n_cosets * 4096))) return rc;
-  if ((rc = dmalloc(ctx, &d_hi, (size_t)n_cosets * hi_count))) return rc;
+  // small transforms (the FRI layers of every proof) keep their tables for the life of the context
+  const bool cache_tables = log_n < 12;
+  p2b_ctx::CpKey ckey{shift % GL_P, log_n, rate_bits};
+  auto cit = cache_tables ? ctx->small_cp_cache.find(ckey) : ctx->small_cp_cache.end();
+  const bool have_tables = cit != ctx->small_cp_cache.end();
+  if (have_tables) {
+    d_lo = cit->second.lo;
+    d_hi = cit->second.hi;
+  } else {
+    if ((rc = dmalloc_persistent(ctx, &d_lo, (size_t)n_cosets * 4096, cache_tables))) return rc;
+    if ((rc = dmalloc_persistent(ctx, &d_hi, (size_t)n_cosets * hi_count, cache_tables))) return rc;
+  }
   auto mulmod = [](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); };
   auto powmod = [&](uint64_t a, uint64_t e) {
     uint64_t r = 1;
@@ -698,7 +796,7 @@ static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uin
   const uint64_t G = 1753635133440165772ull;
   const uint32_t log_N = log_n + rate_bits;
   uint64_t wN = powmod(G, (uint64_t)1 << (32 - log_N));
-  for (uint32_t t = 0; t < n_cosets; t++) {
+  for (uint32_t t = 0; t < n_cosets && !have_tables; t++) {
     uint64_t st = mulmod(shift % GL_P, powmod(wN, t));
     nttk::k_pow_table<<<cdiv(4096, 256), 256, 0, ctx->stream>>>(st, 4096, d_lo + (size_t)t * 4096);
     LAUNCH_CHECK(ctx);
@@ -706,6 +804,7 @@ static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uin
                                                                     d_hi + (size_t)t * hi_count);
     LAUNCH_CHECK(ctx);
   }
+  if (cache_tables && !have_tables) ctx->small_cp_cache.emplace(ckey, p2b_ctx::SmallCp{d_lo, d_hi, hi_count});
   cpw.lo = d_lo;
   cpw.hi = d_hi;
   cpw.hi_count = hi_count;
@@ -774,8 +873,10 @@ static int run_lde(p2b_ctx* ctx, const uint64_t* d_coeffs, size_t in_stride, uin
     nttk::k_ntt_rows<<<grid, 256, smem, ctx->stream>>>(rp);
     LAUNCH_CHECK(ctx);
   }
-  dfree(ctx, d_lo);
-  dfree(ctx, d_hi);
+  if (!cache_tables) {
+    dfree(ctx, d_lo);
+    dfree(ctx, d_hi);
+  }
   return P2B_OK;
 }
 
@@ -793,8 +894,36 @@ static size_t coop_max_nodes() {
   return v;
 }
 #define COOP_MAX_NODES coop_max_nodes()
+// P2B_FUSED_TREE=0: one launch per level (the round-1 path), for A/B measurements
+static bool fused_tree() {
+  static const bool v = [] {
+    const char* e = getenv("P2B_FUSED_TREE");
+    return !e || e[0] != '0';
+  }();
+  return v;
+}
 static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
   uint32_t L = t->log_leaves - t->cap_height;
+  if (fused_tree() && L > 0) {
+    // wide levels at full throughput (one permutation per thread, the whole GPU), then everything from a level of at
+    // most 2^15 digests up to the cap in ONE launch (fusedk::k_tree_subtree)
+    uint32_t i = 0;
+    while (i < L && (t->n_leaves >> i) > ((size_t)1 << 15)) {
+      const size_t n_par = t->n_leaves >> (i + 1);
+      hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
+                                                                      t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);
+      LAUNCH_CHECK(ctx);
+      i++;
+    }
+    if (i < L) {
+      const uint32_t log_first = t->log_leaves - i;
+      const unsigned grid = log_first > (uint32_t)fusedk::SUB_LOG ? 1u << (log_first - fusedk::SUB_LOG) : 1u;
+      fusedk::k_tree_subtree<<<grid, 256, 0, ctx->stream>>>(t->d_levels, t->n_leaves, i, log_first, L - i,
+                                                           (unsigned int*)ctx->d_scratch);
+      LAUNCH_CHECK(ctx);
+    }
+    return P2B_OK;
+  }
   for (uint32_t i = 0; i < L; i++) {
     size_t n_par = t->n_leaves >> (i + 1);
     const uint64_t* child = t->d_levels + 4 * level_off(t->n_leaves, i);
@@ -914,6 +1043,10 @@ static int h2d_cols(p2b_ctx* ctx, cudaStream_t stream, const uint64_t* const* co
     while (e < c1 && cols[e] == cols[e - 1] + n) e++;
     if (host_ptr_is_pinned(cols[c])) {
       CU(ctx, cudaMemcpyAsync(d_dst + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+      // the DMA reads the caller's memory: remember where it ends (the host-input entry points wait for it)
+      if (!ctx->ev_h2d) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+      CU(ctx, cudaEventRecord(ctx->ev_h2d, stream));
+      ctx->h2d_event_pending = true;
       c = e;
       continue;
     }
@@ -1135,13 +1268,23 @@ static int batch_from_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, u
   return batch_build(ctx, d_in, false, n_cols, log_n, rate_bits, cap_height, out);
 }
 
+// Pinned sources are read by DMA after the call has enqueued its work: wait for the UPLOAD (not for the transforms) so
+// that the caller may refill its buffers as soon as the entry point returns.
+static int wait_for_upload(p2b_ctx* ctx, int rc) {
+  if (ctx && ctx->h2d_event_pending) {
+    ctx->h2d_event_pending = false;
+    cudaError_t e = cudaEventSynchronize(ctx->ev_h2d);
+    if (e != cudaSuccess && rc == P2B_OK) return fail(ctx, P2B_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
 extern "C" int p2b_batch_from_values(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n,
                                      uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
-  return batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, true, out);
+  return wait_for_upload(ctx, batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, true, out));
 }
 extern "C" int p2b_batch_from_coeffs(p2b_ctx* ctx, const uint64_t* const* cols, size_t n_cols, uint32_t log_n,
                                      uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
-  return batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, false, out);
+  return wait_for_upload(ctx, batch_from_host(ctx, cols, n_cols, log_n, rate_bits, cap_height, flags, false, out));
 }
 extern "C" int p2b_batch_from_values_dev(p2b_ctx* ctx, const uint64_t* d_cols, size_t n_cols, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, uint32_t flags, p2b_batch** out) {
@@ -1156,11 +1299,130 @@ extern "C" void p2b_batch_free(p2b_batch* b) {
   if (!b) return;
   p2b_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
+  if (!ctx->plans.empty() && !ctx->cap) plans_forget(ctx, 0, b->id);
+  if (b->view) {
+    delete b;
+    return;
+  }
   dfree(ctx, b->d_coeffs);
   dfree(ctx, b->d_lde);
   dfree(ctx, b->d_values);
   dfree(ctx, b->tree.d_levels);
   delete b;
+}
+
+// ---- circuit-data reuse -------------------------------------------------------------------------
+// prover_data.constants_sigmas_commitment is built once per circuit (CircuitBuilder::build: minutes for the whole
+// toolbox, city_rollup_core_worker_qbench/src/qbench.rs:21; at job time for the sighash wrappers,
+// city_rollup_circuit/src/sighash_circuits/sighash_wrapper.rs:142-148) and read by every proof of that circuit.
+// p2b_batch_attach shares ONE device copy between the contexts of a device; p2b_batch_export / import carry it across
+// processes as coefficients (+ values) + cap, the LDE and the tree being recomputed on the device and checked
+// against the stored cap.
+extern "C" int p2b_batch_attach(p2b_ctx* ctx, const p2b_batch* src, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  if (!src || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (src->ctx->device != ctx->device) return fail(ctx, P2B_ERR_INVALID, "the batch lives on device %d, this context on %d", src->ctx->device, ctx->device);
+  p2b_batch* v = new (std::nothrow) p2b_batch();
+  if (!v) return fail(ctx, P2B_ERR_OOM, "host allocation failed");
+  const uint64_t id = v->id;
+  *v = *src;  // device pointers are shared
+  v->id = id;
+  v->ctx = ctx;
+  v->view = true;
+  v->tree.ctx = ctx;
+  v->tree.owned_by_batch = true;
+  if (src->ctx != ctx) {
+    // everything the owner has enqueued for this batch must be done before this context's stream reads it
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, src->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+    if (ev) cudaEventDestroy(ev);
+    if (e != cudaSuccess) {
+      delete v;
+      return fail(ctx, P2B_ERR_CUDA, "p2b_batch_attach: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = v;
+  return P2B_OK;
+}
+
+static const uint64_t P2B_EXPORT_MAGIC = 0x3148435441423250ull;  // "P2BATCH1"
+extern "C" size_t p2b_batch_export_len(const p2b_batch* b) {
+  if (!b) return 0;
+  const size_t n = (size_t)1 << b->log_n;
+  return 8 * (8 + ((size_t)4 << b->cap_height) + b->n_cols * n * (b->d_values ? 2 : 1));
+}
+extern "C" int p2b_batch_export(p2b_batch* b, uint8_t* out, size_t out_cap, size_t* written) {
+  if (!b || !out) return P2B_ERR_INVALID;
+  p2b_ctx* ctx = b->ctx;
+  CHECK_CTX(ctx);
+  const size_t need = p2b_batch_export_len(b);
+  if (out_cap < need) return fail(ctx, P2B_ERR_INVALID, "export buffer too small: %zu < %zu bytes", out_cap, need);
+  const size_t n = (size_t)1 << b->log_n, cap_words = (size_t)4 << b->cap_height;
+  uint64_t hdr[8] = {P2B_EXPORT_MAGIC, 1, b->n_cols, b->log_n, b->rate_bits, b->cap_height, b->d_values ? 1u : 0u, 0};
+  memcpy(out, hdr, sizeof hdr);
+  uint64_t* w = (uint64_t*)(out + sizeof hdr);  // callers hand over malloc'ed (8-byte aligned) buffers; memcpy below otherwise
+  std::vector<uint64_t> tmp(cap_words);
+  int rc = p2b_tree_cap(&b->tree, tmp.data());
+  if (rc) return rc;
+  memcpy(w, tmp.data(), cap_words * 8);
+  uint8_t* p = (uint8_t*)(w + cap_words);
+  // large copies straight into the caller's buffer (pageable or pinned)
+  CU(ctx, cudaMemcpyAsync(p, b->d_coeffs, b->n_cols * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (b->d_values) CU(ctx, cudaMemcpyAsync(p + b->n_cols * n * 8, b->d_values, b->n_cols * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, ctx_sync(ctx));
+  if (written) *written = need;
+  return P2B_OK;
+}
+extern "C" int p2b_batch_import(p2b_ctx* ctx, const uint8_t* bytes, size_t n_bytes, p2b_batch** out) {
+  CHECK_CTX(ctx);
+  if (!bytes || !out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  *out = nullptr;
+  uint64_t hdr[8];
+  if (n_bytes < sizeof hdr) return fail(ctx, P2B_ERR_INVALID, "truncated batch export");
+  memcpy(hdr, bytes, sizeof hdr);
+  if (hdr[0] != P2B_EXPORT_MAGIC || hdr[1] != 1) return fail(ctx, P2B_ERR_INVALID, "not a p2b batch export (magic / version)");
+  const size_t n_cols = hdr[2];
+  const uint32_t log_n = (uint32_t)hdr[3], rate_bits = (uint32_t)hdr[4], cap_height = (uint32_t)hdr[5];
+  const bool has_values = hdr[6] != 0;
+  if (hdr[3] > 24 || hdr[4] > 6 || hdr[5] > 30 || n_cols == 0 || n_cols > 65535) return fail(ctx, P2B_ERR_INVALID, "corrupt batch export header");
+  const size_t n = (size_t)1 << log_n, cap_words = (size_t)4 << cap_height;
+  if (cap_height > log_n + rate_bits) return fail(ctx, P2B_ERR_INVALID, "corrupt batch export header");
+  const size_t need = 8 * (8 + cap_words + n_cols * n * (has_values ? 2 : 1));
+  if (n_bytes != need) return fail(ctx, P2B_ERR_INVALID, "batch export is %zu bytes, its header says %zu", n_bytes, need);
+  const uint8_t* p = bytes + sizeof hdr + cap_words * 8;
+  uint64_t *d_coeffs = nullptr, *d_values = nullptr;
+  int rc = dmalloc(ctx, &d_coeffs, n_cols * n);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d_coeffs, p, n_cols * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && has_values) {
+    rc = dmalloc(ctx, &d_values, n_cols * n);
+    if (rc == P2B_OK) e = cudaMemcpyAsync(d_values, p + n_cols * n * 8, n_cols * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e != cudaSuccess || rc != P2B_OK) {
+    dfree(ctx, d_coeffs);
+    dfree(ctx, d_values);
+    return rc != P2B_OK ? rc : fail(ctx, P2B_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  p2b_batch* b = nullptr;
+  rc = batch_build(ctx, d_coeffs, false, n_cols, log_n, rate_bits, cap_height, &b);  // LDE + tree recomputed on the device
+  if (rc != P2B_OK) {
+    dfree(ctx, d_values);
+    return rc;
+  }
+  b->d_values = d_values;
+  std::vector<uint64_t> cap(cap_words);
+  rc = p2b_tree_cap(&b->tree, cap.data());
+  if (rc == P2B_OK && memcmp(cap.data(), bytes + sizeof hdr, cap_words * 8) != 0)
+    rc = fail(ctx, P2B_ERR_INVALID, "batch export is corrupt: the recomputed Merkle cap differs from the stored one");
+  if (rc != P2B_OK) {
+    p2b_batch_free(b);
+    return rc;
+  }
+  *out = b;
+  return P2B_OK;
 }
 
 extern "C" size_t p2b_batch_n_cols(const p2b_batch* b) { return b ? b->n_cols : 0; }
@@ -1315,6 +1577,7 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
 extern "C" void p2b_circuit_free(p2b_circuit* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
+  if (!c->ctx->plans.empty()) plans_forget(c->ctx, c->id, 0);
   dfree(c->ctx, c->d_gates);
   dfree(c->ctx, c->d_k_is);
   dfree(c->ctx, c->d_zh);
@@ -1332,6 +1595,26 @@ static int check_plonk_batches(p2b_ctx* ctx, const p2b_circuit* c, const p2b_bat
   if (wires->n_cols != c->d.num_wires)
     return fail(ctx, P2B_ERR_INVALID, "wires has %zu columns, expected %u", wires->n_cols, c->d.num_wires);
   if (cs->rate_bits != wires->rate_bits) return fail(ctx, P2B_ERR_INVALID, "rate_bits differ");
+  return P2B_OK;
+}
+
+// n words of host data (pointer tables, parameters) -> device.  The source is pageable: cudaMemcpyAsync stages it
+// before returning, so the caller may free it right away.
+// Under stream capture the copy node must read memory that is still there at launch time: the words are parked in a
+// slot of the plan's pinned block (returned through `slot`, so that the launcher can refresh per-proof inputs).
+static int h2d_small(p2b_ctx* ctx, uint64_t* d_dst, const void* h_src, size_t n_u64, uint64_t** slot = nullptr) {
+  if (ctx->cap) {
+    ProvePlan* pl = ctx->cap;
+    const size_t need = n_u64 ? n_u64 : 1;
+    if (pl->pin_used + need > pl->pin_cap) return fail(ctx, P2B_ERR_UNSUPPORTED, "prove plan: pinned block too small");
+    uint64_t* h = pl->h_pin + pl->pin_used;
+    pl->pin_used += need;
+    if (n_u64) memcpy(h, h_src, n_u64 * sizeof(uint64_t));
+    if (slot) *slot = h;
+    h_src = h;
+  }
+  if (n_u64 == 0) return P2B_OK;
+  CU(ctx, cudaMemcpyAsync(d_dst, h_src, n_u64 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   return P2B_OK;
 }
 
@@ -1412,10 +1695,14 @@ extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c
   return rc;
 }
 
+static uint32_t quotient_n_terms(const p2b_circuit_desc& d) {
+  return d.num_challenges * (d.num_partial_products + 2) + d.num_gate_constraints;
+}
 // all challenge / hash arguments on the device
 static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_batch* wires,
                          const p2b_batch* zs, const uint64_t* d_pi_hash, const uint64_t* d_betas, const uint64_t* d_gammas,
-                         const uint64_t* d_alphas, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out) {
+                         const uint64_t* d_alphas, uint32_t rate_bits, uint32_t cap_height, p2b_batch** out,
+                         const uint64_t* d_apow_ready = nullptr /* [challenge][n_terms] powers of alpha, if the caller built them */) {
   *out = nullptr;
   int rc = check_plonk_batches(ctx, c, cs, wires);
   if (rc) return rc;
@@ -1431,7 +1718,7 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   const uint32_t n_terms = nch * (npp + 2) + d.num_gate_constraints;
   uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr, *d_parts = nullptr;
   const uint32_t n_parts = 1 + d.n_gates;
-  if ((rc = dmalloc(ctx, &d_apow, (size_t)nch * n_terms))) return rc;
+  if (!d_apow_ready && (rc = dmalloc(ctx, &d_apow, (size_t)nch * n_terms))) return rc;
   if ((rc = dmalloc(ctx, &d_parts, (size_t)n_parts * nch * lde_size))) {
     dfree(ctx, d_apow);
     return rc;
@@ -1440,8 +1727,10 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_tmp, (size_t)nch * lde_size);
   if (rc == P2B_OK) {
     stage_begin(ctx, ST_OTHER);
-    plonk::k_build_apow<<<nch, 32, 0, ctx->stream>>>(d_alphas, n_terms, d_apow);
-    ctx->launches++;
+    if (!d_apow_ready) {
+      plonk::k_build_apow<<<nch, 32, 0, ctx->stream>>>(d_alphas, n_terms, d_apow);
+      ctx->launches++;
+    }
     plonk::QuotientParams qp{};
     qp.cs_lde = cs->d_lde;
     qp.wires_lde = wires->d_lde;
@@ -1449,7 +1738,7 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.N = n << cs->rate_bits;
     qp.gates = c->d_gates;
     qp.k_is = c->d_k_is;
-    qp.apow = d_apow;
+    qp.apow = d_apow_ready ? d_apow_ready : d_apow;
     qp.zh = c->d_zh;
     qp.parts = d_parts;
     qp.betas = d_betas;
@@ -1793,21 +2082,64 @@ extern "C" int p2b_challenger_import(p2b_challenger* c, const uint64_t* in30) {
 }
 
 // ------------------------------------------------------------------------------------------------ FRI
+// One transcript step in one launch (fusedk::k_transcript): observe the given device segments in order, then squeeze
+// n_out challenges into d_out.
+struct TrSegs {
+  const uint64_t* p[fusedk::TR_MAX_SEGS];
+  size_t n[fusedk::TR_MAX_SEGS];
+  uint32_t count = 0;
+  void add(const uint64_t* ptr, size_t len) {
+    if (len == 0) return;
+    p[count] = ptr;
+    n[count] = len;
+    count++;
+  }
+};
+static int transcript_step(p2b_ctx* ctx, uint64_t* d_state, bool reset, const TrSegs& segs, uint64_t* d_out, uint32_t n_out,
+                           uint64_t scale_g = 0, uint64_t* pow_tab = nullptr, uint32_t pow_n = 0, uint64_t* ext_tab = nullptr,
+                           uint32_t ext_n = 0) {
+  fusedk::TranscriptParams tp{};
+  tp.state = d_state;
+  tp.n_seg = segs.count;
+  for (uint32_t i = 0; i < segs.count; i++) {
+    tp.seg[i] = segs.p[i];
+    tp.seg_len[i] = (uint32_t)segs.n[i];
+  }
+  tp.reset = reset ? 1u : 0u;
+  tp.out = d_out;
+  tp.n_out = n_out;
+  tp.scale_g = scale_g;
+  tp.pow_tab = pow_tab;
+  tp.pow_n = pow_n;
+  tp.ext_tab = ext_tab;
+  tp.ext_n = ext_n;
+  fusedk::k_transcript<<<1, 32, 0, ctx->stream>>>(tp);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+static const uint64_t* tree_cap_ptr(const p2b_tree* t) {
+  return t->d_levels + 4 * level_off(t->n_leaves, t->log_leaves - t->cap_height);
+}
+
 // fri_committed_trees on device-resident inputs.
-//   d_coef      coefficients as two planes (c0 | c1) of `len` each; overwritten by the folds
+//   d_coef      coefficients as two planes (c0 | c1) of `len` each (read only; the folds ping-pong between two
+//               scratch buffers)
 //   d_vals_nat  layer-0 values, interleaved, natural order (bit-reversed here), or nullptr
 //   d_vals_leaf layer-0 values as two planes of `len` in leaf (bit-reversed) order, or nullptr
 //   d_final     receives the final polynomial, interleaved, 2 * (len >> sum(arity) >> rate_bits) words
-// On success `trees` owns the layer trees; on failure they are freed.
-static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_vals_nat, const uint64_t* d_vals_leaf,
+// On success `trees` owns the layer trees; on failure they are freed.  The final polynomial is observed.
+static int fri_commit_core(p2b_ctx* ctx, const uint64_t* d_coef, const uint64_t* d_vals_nat, const uint64_t* d_vals_leaf,
                            size_t len, uint32_t log_len, const uint32_t* arity_bits, size_t n_layers, uint32_t rate_bits,
                            uint32_t cap_height, p2b_challenger* ch, std::vector<p2b_tree*>& trees, uint64_t* d_final) {
-  uint64_t *d_tmp = nullptr, *d_beta = nullptr, *d_planes = nullptr;
-  int rc = dmalloc(ctx, &d_tmp, 2 * len);
+  uint64_t *d_fold[2] = {nullptr, nullptr}, *d_beta = nullptr, *d_planes = nullptr;
+  const size_t fold_words = n_layers ? 2 * (len >> arity_bits[0]) : 1;
+  int rc = dmalloc(ctx, &d_fold[0], fold_words);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_fold[1], fold_words);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_beta, 2);
-  if (rc == P2B_OK) rc = dmalloc(ctx, &d_planes, 2 * len);
+  if (rc == P2B_OK) rc = dmalloc(ctx, &d_planes, fold_words);
   auto cleanup = [&](int code) {
-    dfree(ctx, d_tmp);
+    dfree(ctx, d_fold[0]);
+    dfree(ctx, d_fold[1]);
     dfree(ctx, d_beta);
     dfree(ctx, d_planes);
     if (code != P2B_OK) {
@@ -1817,12 +2149,6 @@ static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_val
     return code;
   };
   if (rc) return cleanup(rc);
-#define CUF(call)                                                                                  \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess)                                                                        \
-      return cleanup(fail(ctx, P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
-  } while (0)
 #define LAUNCHF()                                                                                  \
   do {                                                                                             \
     ctx->launches++;                                                                               \
@@ -1833,6 +2159,7 @@ static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_val
   size_t cur = len;
   uint32_t log_cur = log_len;
   uint64_t shift = 7;
+  const uint64_t* src = d_coef;  // planes src | src + cur
   for (size_t l = 0; l < n_layers; l++) {
     const uint32_t ab = arity_bits[l];
     const size_t n_leaves = cur >> ab, leaf_len = (size_t)2 << ab;
@@ -1853,42 +2180,56 @@ static int fri_commit_core(p2b_ctx* ctx, uint64_t* d_coef, const uint64_t* d_val
       // natural order interleaved -> leaf order (bit-reversed), row-major leaves
       frik::k_bitrev_ext<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(d_vals_nat, log_cur, t->d_leaves_rm);
       LAUNCHF();
+      if (n_leaves > COOP_MAX_NODES)
+        hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+      else
+        hashk::k_leaf_hash_rowmajor_coop<<<cdiv(n_leaves * 32, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+      LAUNCHF();
     } else {
       // planes in leaf order: the caller's LDE (layer 0) or the coset NTT of the folded coefficients
       const uint64_t* pl = l == 0 ? d_vals_leaf : d_planes;
-      frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(pl, pl + cur, cur, t->d_leaves_rm);
-      LAUNCHF();
+      if (n_leaves > COOP_MAX_NODES) {
+        frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(pl, pl + cur, cur, t->d_leaves_rm);
+        LAUNCHF();
+        hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+        LAUNCHF();
+      } else {
+        fusedk::k_leaf_hash_planes_coop<<<cdiv(n_leaves * 32, 256), 256, 0, ctx->stream>>>(pl, pl + cur, ab, n_leaves, t->d_leaves_rm,
+                                                                                           t->d_levels);
+        LAUNCHF();
+      }
     }
-    if (n_leaves > COOP_MAX_NODES)
-      hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
-    else
-      hashk::k_leaf_hash_rowmajor_coop<<<cdiv(n_leaves * 32, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
-    LAUNCHF();
     if ((rc = build_levels(ctx, t))) return cleanup(rc);
-    // observe_cap, beta = get_extension_challenge (device resident)
-    if ((rc = p2b_challenger_observe_cap(ch, t))) return cleanup(rc);
-    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_beta);
+    // observe_cap, beta = get_extension_challenge (device resident), one launch
+    {
+      TrSegs sg;
+      sg.add(tree_cap_ptr(t), (size_t)4 << cap_height);
+      if ((rc = transcript_step(ctx, ch->d_state, false, sg, d_beta, 2))) return cleanup(rc);
+    }
+    // fold: coeffs[i] = sum_j coeffs[i*arity + j] * beta^j, into the other scratch buffer
+    uint64_t* dst = d_fold[l & 1];
+    frik::k_fold_coeffs<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(src, src + cur, cur, ab, d_beta, dst, dst + n_leaves);
     LAUNCHF();
-    // fold: coeffs[i] = sum_j coeffs[i*arity + j] * beta^j
-    frik::k_fold_coeffs<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, cur, ab, d_beta, d_tmp, d_tmp + n_leaves);
-    LAUNCHF();
-    CUF(cudaMemcpyAsync(d_coef, d_tmp, 2 * n_leaves * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    src = dst;
     cur = n_leaves;
     log_cur -= ab;
     for (uint32_t k = 0; k < ab; k++) shift = h_mulmod(shift, shift);
     if (l + 1 < n_layers) {
       // values of the next layer = coset NTT (shift) of the folded coefficients, leaf order, 2 planes
-      if ((rc = run_lde(ctx, d_coef, cur, d_planes, 2, log_cur, 0, shift))) return cleanup(rc);
+      if ((rc = run_lde(ctx, src, cur, d_planes, 2, log_cur, 0, shift))) return cleanup(rc);
     }
     stage_end(ctx);
   }
   // final polynomial: first cur >> rate_bits coefficients (the rest are zero for a valid codeword)
   size_t n_final = cur >> rate_bits;
-  frik::k_interleave<<<cdiv(n_final, 256), 256, 0, ctx->stream>>>(d_coef, d_coef + cur, n_final, d_final);
+  frik::k_interleave<<<cdiv(n_final, 256), 256, 0, ctx->stream>>>(src, src + cur, n_final, d_final);
   LAUNCHF();
-  if ((rc = challenger_observe_dev(ch, d_final, 2 * n_final))) return cleanup(rc);
+  {
+    TrSegs sg;
+    sg.add(d_final, 2 * n_final);
+    if ((rc = transcript_step(ctx, ch->d_state, false, sg, nullptr, 0))) return cleanup(rc);
+  }
   return cleanup(P2B_OK);
-#undef CUF
 #undef LAUNCHF
 }
 
@@ -1960,45 +2301,39 @@ extern "C" int p2b_fri_commit(p2b_ctx* ctx, const uint64_t* coeffs_ext, const ui
   return rc;
 }
 
+// fri_proof_of_work without a host round trip: ONE search launch (every thread walks its candidates in increasing
+// order and leaves as soon as its candidate exceeds the best witness found so far, so the launch ends one grid stride
+// after the first hit however large the range is), then fusedk::k_pow_finish observes the witness, squeezes the
+// response and the n_queries query-index challenges (d_chal; may be null with n_queries == 0), and stores the witness
+// at d_witness_out.
+static int fri_pow_dev(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint64_t* d_witness_out, uint32_t n_queries,
+                       uint64_t* d_chal) {
+  if (pow_bits > 40) return fail(ctx, P2B_ERR_UNSUPPORTED, "pow_bits > 40");
+  unsigned long long* d_best = (unsigned long long*)(ctx->d_scratch + 1);
+  // the minimal witness is geometric with mean 2^pow_bits.  Grid: about half the mean per stride, between one and
+  // three CTAs per SM.
+  const uint64_t sms = (uint64_t)ctx->sm_count;
+  uint64_t blocks = (((uint64_t)1 << pow_bits) / 2 + 255) / 256;
+  blocks = blocks < sms ? sms : blocks > 3 * sms ? 3 * sms : blocks;
+  CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
+  frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, 0, GL_P, pow_bits, d_best);
+  LAUNCH_CHECK(ctx);
+  fusedk::k_pow_finish<<<1, 32, 0, ctx->stream>>>(ch->d_state, d_best, d_witness_out, n_queries, d_chal);
+  LAUNCH_CHECK(ctx);
+  return P2B_OK;
+}
+
 extern "C" int p2b_fri_pow(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint64_t* witness_out) {
   CHECK_CTX(ctx);
   if (!ch || !witness_out) return fail(ctx, P2B_ERR_INVALID, "null argument");
   if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
-  if (pow_bits > 40) return fail(ctx, P2B_ERR_UNSUPPORTED, "pow_bits > 40");
-  uint64_t* d_best = nullptr;
-  int rc = dmalloc(ctx, &d_best, 1);
-  if (rc) return rc;
-  // the minimal witness is geometric with mean 2^pow_bits; the kernel walks the candidates in increasing order and
-  // stops one grid stride after the first hit, so a launch may cover far more than it evaluates.  Grid: about half
-  // the mean per stride, between one and three CTAs per SM.
-  const uint64_t sms = (uint64_t)ctx->sm_count;
-  uint64_t blocks = (((uint64_t)1 << pow_bits) / 2 + 255) / 256;
-  blocks = blocks < sms ? sms : blocks > 3 * sms ? 3 * sms : blocks;
-  uint64_t chunk = (uint64_t)1 << (pow_bits + 4 < 18 ? 18 : pow_bits + 4);
-  uint64_t found = ~0ull;
-  CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
-  for (uint64_t base = 0; found == ~0ull; base += chunk) {
-    frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, base, chunk, pow_bits, (unsigned long long*)d_best);
-    LAUNCH_CHECK(ctx);
-    rc = d2h(ctx, &found, d_best, 1);
-    if (rc) break;
-    if (base + chunk < base) break;
-  }
-  dfree(ctx, d_best);
-  if (rc) return rc;
-  if (found == ~0ull) return fail(ctx, P2B_ERR_INVALID, "no proof-of-work witness found");
-  // challenger.observe_element(w); pow_response = challenger.get_challenge()
   uint64_t* d_w = nullptr;
-  if ((rc = dmalloc(ctx, &d_w, 2))) return rc;
-  CU(ctx, cudaMemcpyAsync(d_w, &found, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  rc = challenger_observe_dev(ch, d_w, 1);
-  if (rc == P2B_OK) {
-    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 1, d_w + 1);
-    ctx->launches++;
-  }
-  CU(ctx, ctx_sync(ctx));
+  int rc = dmalloc(ctx, &d_w, 1);
+  if (rc) return rc;
+  rc = fri_pow_dev(ctx, ch, pow_bits, d_w, 0, nullptr);
+  if (rc == P2B_OK) rc = d2h(ctx, witness_out, d_w, 1);
   dfree(ctx, d_w);
-  *witness_out = found;
+  if (rc == P2B_OK && *witness_out == ~0ull) return fail(ctx, P2B_ERR_INVALID, "no proof-of-work witness found");
   return rc;
 }
 
@@ -2062,11 +2397,11 @@ extern "C" size_t p2b_fri_proof_len(const p2b_batch* const* oracles, size_t n_or
   return fri_proof_len_impl(oracles, n_oracles, fp);
 }
 
+// The general form (any number of opening batches): one launch per step, as in round 1.
 // d_points: n_batches extension points on the device (2 words each); d_proof: fri_proof_len words on the device.
-// The only host synchronisation inside is the proof-of-work search.
-static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
+static int prove_openings_generic(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
                                const p2b_fri_batch* batches, size_t n_batches, const uint64_t* d_points,
-                               p2b_challenger* ch, const p2b_fri_params* fp, uint64_t* d_proof) {
+                               p2b_challenger* ch, const p2b_fri_params* fp, uint64_t* d_proof, const TrSegs* pre) {
   if (!batches || !ch || !d_proof || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
   if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
   int rc = check_fri_params(ctx, oracles, n_oracles, fp);
@@ -2135,8 +2470,10 @@ static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, si
 
   stage_begin(ctx, ST_OTHER);
   // alpha = challenger.get_extension_challenge()
-  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_alpha);
-  LAUNCHP();
+  {
+    TrSegs none;
+    TRY(transcript_step(ctx, ch->d_state, false, pre ? *pre : none, d_alpha, 2));
+  }
   CUP(cudaMemsetAsync(d_fin, 0, 2 * n * sizeof(uint64_t), ctx->stream));
   for (size_t bi = 0; bi < n_batches; bi++) {
     const uint32_t m = (uint32_t)tabs[bi].size();
@@ -2161,8 +2498,7 @@ static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, si
   // fri_proof: commit phase
   TRY(fri_commit_core(ctx, d_coef, nullptr, d_vals, N, log_N, fp->reduction_arity_bits, fp->n_layers, rate_bits,
                       fp->cap_height, ch, trees, d_final));
-  uint64_t pow_witness = 0;
-  TRY(p2b_fri_pow(ctx, ch, fp->proof_of_work_bits, &pow_witness));
+  TRY(fri_pow_dev(ctx, ch, fp->proof_of_work_bits, d_proof + (proof_len - 1), fp->num_query_rounds, d_chal));
   // query rounds: indices squeezed on the device, then one gather kernel per (oracle | layer, leaf | path)
   stage_begin(ctx, ST_OTHER);
   const uint32_t nq = fp->num_query_rounds;
@@ -2182,8 +2518,6 @@ static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, si
     }
   }
   if (nq) {
-    frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, nq, d_chal);
-    LAUNCHP();
     size_t qoff = off;
     for (size_t o = 0; o < n_oracles; o++) {
       const p2b_batch* b = oracles[o];
@@ -2212,12 +2546,176 @@ static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, si
   off += (size_t)nq * per_query;
   CUP(cudaMemcpyAsync(d_proof + off, d_final, 2 * n_final * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   off += 2 * n_final;
-  CUP(cudaMemcpyAsync(d_proof + off, &pow_witness, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  off += 1;
+  off += 1;  // pow_witness: written by k_pow_finish
   stage_end(ctx);
   return cleanup(off == proof_len ? P2B_OK : fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
 #undef TRY
 #undef CUP
+#undef LAUNCHP
+}
+
+// PolynomialBatch::prove_openings on device-resident oracles.
+// d_points: n_batches extension points on the device (2 words each); d_proof: fri_proof_len words on the device;
+// pre: segments to observe before alpha is squeezed (p2b_prove hands over the openings here so that "observe the
+// openings, squeeze alpha, build the alpha powers" is one launch).  No host synchronisation inside.
+// The two-batch instance of every plonky2 circuit without lookups (everything at zeta, the Zs again at g zeta) takes
+// the fused path below; anything else goes through prove_openings_generic.
+static int prove_openings_core(p2b_ctx* ctx, const p2b_batch* const* oracles, size_t n_oracles,
+                               const p2b_fri_batch* batches, size_t n_batches, const uint64_t* d_points,
+                               p2b_challenger* ch, const p2b_fri_params* fp, uint64_t* d_proof, const TrSegs* pre = nullptr) {
+  if (!batches || !ch || !d_proof || n_batches == 0) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (n_batches != 2 || n_oracles > (size_t)fusedk::Q_MAX_ORACLES)
+    return prove_openings_generic(ctx, oracles, n_oracles, batches, n_batches, d_points, ch, fp, d_proof, pre);
+  if (ch->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "challenger belongs to a different context");
+  int rc = check_fri_params(ctx, oracles, n_oracles, fp);
+  if (rc) return rc;
+  const uint32_t log_n = oracles[0]->log_n, rate_bits = fp->rate_bits, log_N = log_n + rate_bits;
+  const size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  uint32_t log_len = 0;
+  if ((rc = check_fri_args(ctx, N, fp->reduction_arity_bits, fp->n_layers, rate_bits, &log_len))) return rc;
+  for (size_t o = 0; o < n_oracles; o++)
+    if (oracles[o]->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "oracle of another context");
+  const size_t proof_len = fri_proof_len_impl(oracles, n_oracles, fp);
+  // polynomial pointer tables of the two batches, back to back
+  std::vector<const uint64_t*> tab;
+  size_t m[2] = {0, 0};
+  for (size_t bi = 0; bi < 2; bi++) {
+    const p2b_fri_batch& fb = batches[bi];
+    if (fb.n_ranges == 0 || fb.n_ranges > P2B_MAX_FRI_RANGES) return fail(ctx, P2B_ERR_INVALID, "batch %zu: bad range count", bi);
+    for (uint32_t r = 0; r < fb.n_ranges; r++) {
+      const auto& rg = fb.ranges[r];
+      if (rg.oracle >= n_oracles || (size_t)rg.first + rg.count > oracles[rg.oracle]->n_cols)
+        return fail(ctx, P2B_ERR_INVALID, "batch %zu range %u out of bounds", bi, r);
+      for (uint32_t k = 0; k < rg.count; k++) tab.push_back(oracles[rg.oracle]->d_coeffs + (size_t)(rg.first + k) * n);
+      m[bi] += rg.count;
+    }
+  }
+  const size_t max_m = m[0] > m[1] ? m[0] : m[1];
+  uint32_t sum_ab = 0;
+  for (uint32_t l = 0; l < fp->n_layers; l++) sum_ab += fp->reduction_arity_bits[l];
+  const size_t n_final = (N >> sum_ab) >> rate_bits;
+  const size_t row_ctas = (n + 255) / 256;
+  uint32_t slices = (uint32_t)((2 * (size_t)ctx->sm_count + row_ctas - 1) / row_ctas);
+  slices = slices < 1 ? 1 : slices > 16 ? 16 : slices;
+  if (slices > m[0]) slices = m[0] ? (uint32_t)m[0] : 1;
+
+  uint64_t *d_alpha = nullptr, *d_pw = nullptr, *d_ptrs = nullptr, *d_part = nullptr, *d_comp = nullptr, *d_quot = nullptr;
+  uint64_t *d_fin = nullptr, *d_coef = nullptr, *d_vals = nullptr, *d_final = nullptr, *d_chal = nullptr;
+  std::vector<p2b_tree*> trees;
+  auto cleanup = [&](int code) {
+    for (uint64_t* q : {d_alpha, d_pw, d_ptrs, d_part, d_comp, d_quot, d_fin, d_coef, d_vals, d_final, d_chal}) dfree(ctx, q);
+    for (p2b_tree* t : trees) p2b_tree_free(t);
+    return code;
+  };
+#define TRY(expr)                          \
+  do {                                     \
+    int rc__ = (expr);                     \
+    if (rc__ != P2B_OK) return cleanup(rc__); \
+  } while (0)
+#define LAUNCHP()                                                                                  \
+  do {                                                                                             \
+    ctx->launches++;                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+  TRY(dmalloc(ctx, &d_alpha, 2));
+  TRY(dmalloc(ctx, &d_pw, 2 * (max_m + 1)));
+  TRY(dmalloc(ctx, &d_ptrs, tab.size()));
+  TRY(dmalloc(ctx, &d_part, (size_t)slices * 2 * n));
+  TRY(dmalloc(ctx, &d_comp, 4 * n));  // batch 1's reduction | batch 0's summed reduction
+  TRY(dmalloc(ctx, &d_quot, 4 * n));
+  TRY(dmalloc(ctx, &d_fin, 2 * n));
+  TRY(dmalloc(ctx, &d_coef, 2 * N));
+  TRY(dmalloc(ctx, &d_vals, 2 * N));
+  TRY(dmalloc(ctx, &d_final, 2 * (n_final ? n_final : 1)));
+  TRY(dmalloc(ctx, &d_chal, fp->num_query_rounds ? fp->num_query_rounds : 1));
+
+  stage_begin(ctx, ST_OTHER);
+  TRY(h2d_small(ctx, d_ptrs, tab.data(), tab.size()));
+  // [observe the openings;] alpha = challenger.get_extension_challenge(); alpha^0 .. alpha^max_m
+  {
+    TrSegs none;
+    TRY(transcript_step(ctx, ch->d_state, false, pre ? *pre : none, d_alpha, 2, 0, nullptr, 0, d_pw, (uint32_t)max_m));
+  }
+  // final_poly = sum over the batches of alpha-shifted (reduce_polys_base(batch) / (X - point))
+  fusedk::k_reduce_polys2<<<dim3((unsigned)row_ctas, slices + 1), 256, 0, ctx->stream>>>(
+      (const uint64_t* const*)d_ptrs, (uint32_t)m[0], (const uint64_t* const*)(d_ptrs + m[0]), (uint32_t)m[1], n, d_pw, slices, d_part,
+      d_comp);
+  LAUNCHP();
+  fusedk::k_divide_by_linear2<<<2, 1024, 0, ctx->stream>>>(d_part, slices, d_comp, n, d_points, d_quot, d_comp + 2 * n);
+  LAUNCHP();
+  // lde_final_poly = final_poly.lde(rate_bits) (zero padded coefficient planes); lde_final_values = coset_fft(7)
+  fusedk::k_final_poly_combine<<<cdiv(N, 256), 256, 0, ctx->stream>>>(d_quot, n, N, d_pw + 2 * m[1], d_fin, d_coef);
+  LAUNCHP();
+  stage_begin(ctx, ST_LDE);
+  TRY(run_lde(ctx, d_fin, n, d_vals, 2, log_n, rate_bits, 7));
+  stage_end(ctx);
+  // fri_proof: commit phase, proof of work, query indices
+  TRY(fri_commit_core(ctx, d_coef, nullptr, d_vals, N, log_N, fp->reduction_arity_bits, fp->n_layers, rate_bits,
+                      fp->cap_height, ch, trees, d_final));
+  const uint32_t nq = fp->num_query_rounds;
+  TRY(fri_pow_dev(ctx, ch, fp->proof_of_work_bits, d_proof + (proof_len - 1), nq, d_chal));
+  // proof words: commit-phase caps | query rounds | final polynomial | pow witness
+  stage_begin(ctx, ST_OTHER);
+  const size_t cap_words = (size_t)4 << fp->cap_height;
+  fusedk::QueryParams qp{};
+  size_t per_query = 0;
+  for (size_t o = 0; o < n_oracles; o++) {
+    const p2b_batch* b = oracles[o];
+    qp.o_data[o] = b->d_lde;
+    qp.o_levels[o] = b->tree.d_levels;
+    qp.o_cols[o] = (uint32_t)b->n_cols;
+    qp.o_L[o] = log_N - b->cap_height;
+    qp.o_off[o] = (uint32_t)per_query;
+    per_query += b->n_cols + 4 * (size_t)(log_N - b->cap_height);
+  }
+  {
+    uint32_t shift = 0;
+    for (uint32_t l = 0; l < fp->n_layers; l++) {
+      const p2b_tree* t = trees[l];
+      shift += fp->reduction_arity_bits[l];
+      qp.l_leaves[l] = t->d_leaves_rm;
+      qp.l_levels[l] = t->d_levels;
+      qp.l_leaf_len[l] = (uint32_t)t->leaf_len;
+      qp.l_L[l] = t->log_leaves - t->cap_height;
+      qp.l_shift[l] = shift;
+      qp.l_log_leaves[l] = t->log_leaves;
+      qp.l_off[l] = (uint32_t)per_query;
+      per_query += t->leaf_len + 4 * (size_t)(t->log_leaves - t->cap_height);
+    }
+  }
+  size_t off = 0;
+  fusedk::CopyParams cp{};
+  for (uint32_t l = 0; l < fp->n_layers; l++) {
+    cp.src[cp.n] = tree_cap_ptr(trees[l]);
+    cp.dst[cp.n] = d_proof + off;
+    cp.len[cp.n] = (uint32_t)cap_words;
+    cp.n++;
+    off += cap_words;
+  }
+  if (nq) {
+    qp.n_oracles = (uint32_t)n_oracles;
+    qp.n_layers = fp->n_layers;
+    qp.log_lde = log_N;
+    qp.N = N;
+    qp.per_query = per_query;
+    qp.chal = d_chal;
+    qp.out = d_proof + off;
+    fusedk::k_query_all<<<dim3(nq, (unsigned)(n_oracles + fp->n_layers)), 128, 0, ctx->stream>>>(qp);
+    LAUNCHP();
+  }
+  off += (size_t)nq * per_query;
+  cp.src[cp.n] = d_final;
+  cp.dst[cp.n] = d_proof + off;
+  cp.len[cp.n] = (uint32_t)(2 * n_final);
+  cp.n++;
+  off += 2 * n_final + 1;  // + pow_witness, written by k_pow_finish
+  fusedk::k_copy_multi<<<cp.n, 256, 0, ctx->stream>>>(cp);
+  LAUNCHP();
+  stage_end(ctx);
+  return cleanup(off == proof_len ? P2B_OK : fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
+#undef TRY
 #undef LAUNCHP
 }
 
@@ -2274,39 +2772,23 @@ extern "C" size_t p2b_proof_len(const p2b_circuit* c, const p2b_batch* cs, const
   return proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
 }
 
+// ---- the body of a proof: everything is ENQUEUED on the context's stream, nothing waits for the device.  It runs
+// either eagerly or under stream capture (ctx->cap != nullptr), in which case every host source it copies from is a
+// slot of the plan's pinned block.  The proof words land in h_proof_dst (pinned host memory).
 // wire_cols (host column pointers) or d_wires (device, column-major): exactly one is non-null
-static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+static int prove_body(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
                       const uint64_t* const* wire_cols, const uint64_t* d_wires, const uint64_t* public_inputs,
-                      size_t n_public_inputs, const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
-  CHECK_CTX(ctx);
-  if (!c || !cs || !circuit_digest || (!wire_cols && !d_wires) || !fp || !proof_out || (n_public_inputs && !public_inputs))
-    return fail(ctx, P2B_ERR_INVALID, "null argument");
-  if (c->ctx != ctx || cs->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "handle of another context");
-  if (fp->n_layers > P2B_MAX_FRI_LAYERS) return fail(ctx, P2B_ERR_INVALID, "too many FRI layers");
-  if (cs->rate_bits != fp->rate_bits) return fail(ctx, P2B_ERR_INVALID, "constants_sigmas rate_bits differ from the FRI parameters");
+                      size_t n_public_inputs, const p2b_fri_params* fp, uint64_t* h_proof_dst) {
   const p2b_circuit_desc& d = c->d;
   const uint32_t nch = d.num_challenges, rb = fp->rate_bits, caph = fp->cap_height;
-  {
-    // validate the FRI parameters before any length is derived from them (unsigned underflow otherwise)
-    uint32_t log_len = 0;
-    int rc0 = check_fri_args(ctx, ((size_t)1 << d.degree_bits) << rb, fp->reduction_arity_bits, fp->n_layers, rb, &log_len);
-    if (rc0) return rc0;
-    uint32_t lc = log_len;
-    for (uint32_t l = 0; l < fp->n_layers; l++) {
-      lc -= fp->reduction_arity_bits[l];
-      if (caph > lc) return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds the height %u of FRI layer %u", caph, lc, l);
-    }
-    if (caph > d.degree_bits + rb || cs->cap_height > d.degree_bits + rb) return fail(ctx, P2B_ERR_INVALID, "cap_height too large");
-  }
   size_t fri_len = 0;
   const size_t proof_len = proof_len_impl(c, cs, fp, n_public_inputs, &fri_len);
-  if (proof_cap < proof_len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, proof_len);
   const size_t cap_words = (size_t)4 << caph;
   const size_t w_zs = (size_t)nch * (1 + d.num_partial_products), w_q = (size_t)nch * d.quotient_degree_factor;
 
   p2b_batch *wires = nullptr, *zs = nullptr, *qt = nullptr;
   p2b_challenger* ch = nullptr;
-  uint64_t *d_small = nullptr, *d_proof = nullptr, *d_pis = nullptr;
+  uint64_t *d_small = nullptr, *d_proof = nullptr;
   auto cleanup = [&](int code) {
     p2b_batch_free(qt);
     p2b_batch_free(zs);
@@ -2314,7 +2796,6 @@ static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
     p2b_challenger_free(ch);
     dfree(ctx, d_small);
     dfree(ctx, d_proof);
-    dfree(ctx, d_pis);
     return code;
   };
 #define TRY(expr)                             \
@@ -2328,17 +2809,19 @@ static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
     if (e__ != cudaSuccess)                                                                        \
       return cleanup(fail(ctx, P2B_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
   } while (0)
-  // small device block: digest[4] | pi_hash[4] | betas[nch] | gammas[nch] | alphas[nch] | zeta[2] | zeta_next[2]
+  // small device block: digest[4] | pi_hash[4] | betas[nch] | gammas[nch] | alphas[nch] | zeta[2] | zeta_next[2] |
+  // apow[nch * n_terms] (the powers of alpha the quotient's reduce_with_powers needs)
+  const uint32_t n_terms = quotient_n_terms(d);
   std::vector<uint64_t> h_small(8 + 3 * nch + 4, 0);
-  for (int i = 0; i < 4; i++) h_small[i] = circuit_digest[i];
-  TRY(upload_felts(ctx, h_small.data(), h_small.size(), &d_small));
+  for (int i = 0; i < 4; i++) h_small[i] = circuit_digest[i] % GL_P;
+  TRY(dmalloc(ctx, &d_small, h_small.size() + (size_t)nch * n_terms));
+  TRY(h2d_small(ctx, d_small, h_small.data(), h_small.size(), ctx->cap ? &ctx->cap->h_digest : nullptr));
   uint64_t *d_digest = d_small, *d_pih = d_small + 4, *d_betas = d_small + 8, *d_gammas = d_betas + nch,
-           *d_alphas = d_gammas + nch, *d_zeta = d_alphas + nch, *d_zeta_next = d_zeta + 2;
+           *d_alphas = d_gammas + nch, *d_zeta = d_alphas + nch, *d_zeta_next = d_zeta + 2, *d_apow = d_zeta_next + 2;
   TRY(dmalloc(ctx, &d_proof, proof_len));
-  // public_inputs_hash = PoseidonHash::hash_no_pad(public_inputs)
   // P2B_TRACE=1: phase-by-phase wall clock of one proof on stderr (each mark synchronises, so the phases are
   // serialised GPU time + host time; a development aid, never on in measurements)
-  static const bool trace = getenv("P2B_TRACE") != nullptr;
+  const bool trace = trace_enabled() && !ctx->cap;
   auto now_us = [] {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -2353,68 +2836,120 @@ static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
     fprintf(stderr, "[p2b_prove] %-22s enqueue %8.1f us, done +%8.1f us (phase %8.1f us)\n", what, t_e - t_enq, t - t_e, t - t_prev);
     t_prev = t_enq = t;
   };
-  TRY(upload_felts(ctx, public_inputs, n_public_inputs, &d_pis));
+  // public_inputs_hash = PoseidonHash::hash_no_pad(public_inputs); the public inputs go straight to their place at
+  // the end of the proof
+  uint64_t* d_pis = d_proof + (proof_len - n_public_inputs);
+  {
+    std::vector<uint64_t> pis(n_public_inputs ? n_public_inputs : 1);
+    for (size_t i = 0; i < n_public_inputs; i++) pis[i] = public_inputs[i] % GL_P;
+    TRY(h2d_small(ctx, d_pis, pis.data(), n_public_inputs, ctx->cap ? &ctx->cap->h_pis : nullptr));
+  }
   hashk::k_hash_no_pad_single<<<1, 32, 0, ctx->stream>>>(d_pis, n_public_inputs, d_pih);
   ctx->launches++;
   mark("setup + pi hash");
   // wires commitment
-  if (wire_cols)
+  if (ctx->cap) {
+    // under capture: ONE copy node into a buffer of the graph's own (host source = the plan's pinned staging matrix,
+    // device source = the caller's matrix); its source is re-pointed before every launch
+    const size_t n = (size_t)1 << d.degree_bits;
+    uint64_t* d_in = nullptr;
+    TRY(dmalloc(ctx, &d_in, (size_t)d.num_wires * n));
+    ctx->cap->d_wires_dst = d_in;
+    cudaError_t e = cudaMemcpyAsync(d_in, wire_cols ? ctx->cap->h_wires : d_wires, (size_t)d.num_wires * n * sizeof(uint64_t),
+                                    wire_cols ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      dfree(ctx, d_in);
+      return cleanup(fail(ctx, P2B_ERR_CUDA, "witness copy: %s", cudaGetErrorString(e)));
+    }
+    TRY(batch_build(ctx, d_in, true, d.num_wires, d.degree_bits, rb, caph, &wires, true));
+  } else if (wire_cols) {
     TRY(batch_from_host(ctx, wire_cols, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
-  else
+  } else {
     TRY(batch_from_dev(ctx, d_wires, d.num_wires, d.degree_bits, rb, caph, P2B_KEEP_VALUES, true, &wires));
+  }
   mark("wires commit");
   TRY(p2b_challenger_new(ctx, &ch));
-  TRY(challenger_observe_dev(ch, d_digest, 4));
-  TRY(challenger_observe_dev(ch, d_pih, 4));
-  TRY(p2b_challenger_observe_cap(ch, &wires->tree));
-  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2 * nch, d_betas);  // betas then gammas
-  ctx->launches++;
+  {  // observe circuit digest, public inputs hash, wires cap; betas then gammas
+    TrSegs sg;
+    sg.add(d_digest, 4);
+    sg.add(d_pih, 4);
+    sg.add(tree_cap_ptr(&wires->tree), cap_words);
+    TRY(transcript_step(ctx, ch->d_state, true, sg, d_betas, 2 * nch));
+  }
   mark("transcript: betas");
   TRY(zs_pp_core(ctx, c, cs, wires, d_betas, d_gammas, rb, caph, &zs));
   mark("zs/pp + commit");
-  TRY(p2b_challenger_observe_cap(ch, &zs->tree));
-  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, nch, d_alphas);
-  ctx->launches++;
+  {  // observe the Z / partial products cap; alphas and their powers
+    TrSegs sg;
+    sg.add(tree_cap_ptr(&zs->tree), cap_words);
+    TRY(transcript_step(ctx, ch->d_state, false, sg, d_alphas, nch, 0, d_apow, n_terms));
+  }
   mark("transcript: alphas");
-  TRY(quotient_core(ctx, c, cs, wires, zs, d_pih, d_betas, d_gammas, d_alphas, rb, caph, &qt));
+  TRY(quotient_core(ctx, c, cs, wires, zs, d_pih, d_betas, d_gammas, d_alphas, rb, caph, &qt, d_apow));
   mark("quotient + commit");
-  TRY(p2b_challenger_observe_cap(ch, &qt->tree));
-  frik::k_challenger_get<<<1, 32, 0, ctx->stream>>>(ch->d_state, 2, d_zeta);
-  ctx->launches++;
-  mark("transcript: zeta");
-  {
+  {  // observe the quotient cap; zeta, and zeta_next = g * zeta
     const uint64_t G = 1753635133440165772ull;
     const uint64_t g = d.degree_bits ? h_powmod(G, (uint64_t)1 << (32 - d.degree_bits)) : 1;
-    provk::k_ext_scale<<<1, 32, 0, ctx->stream>>>(d_zeta, g, d_zeta_next);
-    ctx->launches++;
+    TrSegs sg;
+    sg.add(tree_cap_ptr(&qt->tree), cap_words);
+    TRY(transcript_step(ctx, ch->d_state, false, sg, d_zeta, 2, g));  // d_zeta | d_zeta_next are adjacent
   }
+  mark("transcript: zeta");
   // proof layout: caps | openings (OpeningSet field order) | FRI proof | public inputs
   size_t off = 0;
+  fusedk::CopyParams cpy{};
   for (p2b_batch* b : {wires, zs, qt}) {
-    const p2b_tree& t = b->tree;
-    CUP(cudaMemcpyAsync(d_proof + off, t.d_levels + 4 * level_off(t.n_leaves, t.log_leaves - t.cap_height),
-                        cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    cpy.src[cpy.n] = tree_cap_ptr(&b->tree);
+    cpy.dst[cpy.n] = d_proof + off;
+    cpy.len[cpy.n] = (uint32_t)cap_words;
+    cpy.n++;
     off += cap_words;
   }
+  fusedk::k_copy_multi<<<cpy.n, 256, 0, ctx->stream>>>(cpy);
+  ctx->launches++;
   uint64_t* o_constants = d_proof + off;  // constants | sigmas contiguous = all of constants_sigmas
   uint64_t* o_wires = o_constants + 2 * cs->n_cols;
   uint64_t* o_zs = o_wires + 2 * (size_t)d.num_wires;
   uint64_t* o_zs_next = o_zs + 2 * (size_t)nch;
   uint64_t* o_pp = o_zs_next + 2 * (size_t)nch;
   uint64_t* o_quot = o_pp + 2 * (w_zs - nch);
-  TRY(eval_ext_core(ctx, cs, d_zeta, 0, cs->n_cols, o_constants));
-  TRY(eval_ext_core(ctx, wires, d_zeta, 0, d.num_wires, o_wires));
-  TRY(eval_ext_core(ctx, zs, d_zeta, 0, nch, o_zs));
-  TRY(eval_ext_core(ctx, zs, d_zeta_next, 0, nch, o_zs_next));
-  TRY(eval_ext_core(ctx, zs, d_zeta, nch, w_zs - nch, o_pp));
-  TRY(eval_ext_core(ctx, qt, d_zeta, 0, w_q, o_quot));
+  {
+    // OpeningSet::new: every opened polynomial in one launch (point 0 = zeta, point 1 = g zeta)
+    fusedk::EvalParams ep{};
+    const size_t n = (size_t)1 << d.degree_bits;
+    struct R {
+      const uint64_t* c;
+      size_t count;
+      uint32_t pt;
+      uint64_t* o;
+    } rs[6] = {{cs->d_coeffs, cs->n_cols, 0, o_constants},        {wires->d_coeffs, d.num_wires, 0, o_wires},
+               {zs->d_coeffs, nch, 0, o_zs},                      {zs->d_coeffs, nch, 1, o_zs_next},
+               {zs->d_coeffs + (size_t)nch * n, w_zs - nch, 0, o_pp}, {qt->d_coeffs, w_q, 0, o_quot}};
+    uint32_t total = 0;
+    for (int i = 0; i < 6; i++) {
+      if (rs[i].count == 0) continue;
+      const uint32_t k = ep.n_ranges++;
+      ep.coeffs[k] = rs[i].c;
+      ep.out[k] = rs[i].o;
+      ep.point[k] = rs[i].pt;
+      ep.first_cta[k] = total;
+      total += (uint32_t)rs[i].count;
+    }
+    ep.first_cta[ep.n_ranges] = total;
+    ep.n = n;
+    ep.points = d_zeta;
+    fusedk::k_eval_polys_multi<<<total, 256, 0, ctx->stream>>>(ep);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(ctx, P2B_ERR_CUDA, "k_eval_polys_multi launch failed"));
+  }
   mark("openings");
   off += 2 * (cs->n_cols + d.num_wires + w_zs + nch + w_q);
-  // challenger.observe_openings(&openings.to_fri_openings()): the zeta batch in FRI order, then zs_next
-  TRY(challenger_observe_dev(ch, o_constants, 2 * (cs->n_cols + d.num_wires + nch)));
-  TRY(challenger_observe_dev(ch, o_pp, 2 * (w_zs - nch + w_q)));
-  TRY(challenger_observe_dev(ch, o_zs_next, 2 * (size_t)nch));
-  mark("transcript: openings");
+  // challenger.observe_openings(&openings.to_fri_openings()): the zeta batch in FRI order, then zs_next — handed to
+  // prove_openings, whose first launch observes them and squeezes alpha
+  TrSegs open_segs;
+  open_segs.add(o_constants, 2 * (cs->n_cols + d.num_wires + nch));
+  open_segs.add(o_pp, 2 * (w_zs - nch + w_q));
+  open_segs.add(o_zs_next, 2 * (size_t)nch);
   // FRI instance (CommonCircuitData::get_fri_instance): everything at zeta, the Zs again at g * zeta
   const p2b_batch* oracles[4] = {cs, wires, zs, qt};
   p2b_fri_batch fb[2] = {};
@@ -2423,28 +2958,334 @@ static int prove_impl(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
   fb[1].n_ranges = 1;
   fb[1].ranges[0] = {2, 0, nch};
   TRY(check_fri_params(ctx, oracles, 4, fp));
-  TRY(prove_openings_core(ctx, oracles, 4, fb, 2, d_zeta, ch, fp, d_proof + off));  // d_zeta | d_zeta_next are adjacent
+  TRY(prove_openings_core(ctx, oracles, 4, fb, 2, d_zeta, ch, fp, d_proof + off, &open_segs));
   mark("prove_openings (FRI)");
-  off += fri_len;
-  if (n_public_inputs)
-    CUP(cudaMemcpyAsync(d_proof + off, d_pis, n_public_inputs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-  off += n_public_inputs;
+  off += fri_len + n_public_inputs;
   if (off != proof_len) return cleanup(fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
-  TRY(d2h(ctx, proof_out, d_proof, proof_len));
+  CUP(cudaMemcpyAsync(h_proof_dst, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   return cleanup(P2B_OK);
 #undef TRY
 #undef CUP
 }
 
+// ---- CUDA-graph plans -------------------------------------------------------------------------------------------
+// A worker proves the same few circuits over and over (city_rollup_core_worker/src/actors/simple.rs:57-113), and a
+// 2^12-row proof is ~50 dependent launches plus ~40 stream-ordered allocations: for a job this small the host side of
+// every launch is visible.  The second proof of a given (circuit, constants_sigmas, FRI parameters, public-input count,
+// witness location) on a context is therefore CAPTURED — prove_body runs once under stream capture, its allocations
+// becoming memory nodes of the graph — and every later proof of that shape is one cudaGraphLaunch after the inputs
+// have been put where the graph reads them: circuit digest, public inputs and pointer tables in the plan's pinned
+// block, the witness through one copy node whose source is re-pointed before each launch.
+// P2B_GRAPH=0 disables the plans (every proof runs prove_body eagerly).
+static bool graphs_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("P2B_GRAPH");
+    return !e || e[0] != '0';
+  }();
+  return v;
+}
+
+static void plan_destroy(p2b_ctx* ctx, ProvePlan* pl) {
+  if (!pl) return;
+  if (pl->exec) {
+    ctx_sync(ctx);  // a launch of this graph may still be in flight
+    cudaGraphExecDestroy(pl->exec);
+  }
+  if (pl->graph) cudaGraphDestroy(pl->graph);
+  if (pl->h_pin) cudaFreeHost(pl->h_pin);
+  if (pl->h_wires) cudaFreeHost(pl->h_wires);
+  if (pl->h_proof) cudaFreeHost(pl->h_proof);
+  delete pl;
+}
+
+// drops the plans that refer to a circuit / batch that is being freed (ids are never reused)
+static void plans_forget(p2b_ctx* ctx, uint64_t circuit_id, uint64_t batch_id) {
+  for (size_t i = 0; i < ctx->plans.size();) {
+    ProvePlan* pl = ctx->plans[i];
+    if ((circuit_id && pl->circuit_id == circuit_id) || (batch_id && pl->cs_id == batch_id)) {
+      plan_destroy(ctx, pl);
+      ctx->plans.erase(ctx->plans.begin() + i);
+    } else {
+      i++;
+    }
+  }
+}
+static void plans_clear(p2b_ctx* ctx) {
+  for (ProvePlan* pl : ctx->plans) plan_destroy(ctx, pl);
+  ctx->plans.clear();
+  cudaDeviceGraphMemTrim(ctx->device);
+}
+
+static ProvePlan* plan_find(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const p2b_fri_params* fp, size_t n_pis,
+                            bool dev_src) {
+  for (ProvePlan* pl : ctx->plans)
+    if (pl->circuit_id == c->id && pl->cs_id == cs->id && pl->n_pis == n_pis && pl->dev_src == dev_src &&
+        memcmp(&pl->fp, fp, sizeof(*fp)) == 0)
+      return pl;
+  return nullptr;
+}
+
+// capture prove_body into pl->exec.  Any failure leaves the plan in state FAILED (eager from then on) and the
+// context healthy.
+static int plan_capture(p2b_ctx* ctx, ProvePlan* pl, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                        const uint64_t* const* wire_cols, const uint64_t* d_wires, const uint64_t* public_inputs,
+                        size_t n_public_inputs, const p2b_fri_params* fp) {
+  pl->state = ProvePlan::FAILED;
+  const size_t n = (size_t)1 << c->d.degree_bits;
+  pl->wires_words = (size_t)c->d.num_wires * n;
+  pl->proof_len = proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
+  pl->pin_cap = 4096 + 2 * (cs->n_cols + c->d.num_wires + 64) + n_public_inputs;
+  if (cudaMallocHost((void**)&pl->h_pin, pl->pin_cap * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMallocHost((void**)&pl->h_proof, pl->proof_len * sizeof(uint64_t)) != cudaSuccess ||
+      (!pl->dev_src && cudaMallocHost((void**)&pl->h_wires, pl->wires_words * sizeof(uint64_t)) != cudaSuccess)) {
+    cudaGetLastError();
+    return fail(ctx, P2B_ERR_OOM, "pinned host allocation for a prove plan failed");
+  }
+  pl->pin_used = 0;
+  const uint64_t launches0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "stream capture unavailable");
+  }
+  ctx->cap = pl;
+  const bool was_poisoned = ctx->poisoned;
+  int rc = prove_body(ctx, c, cs, circuit_digest, wire_cols, d_wires, public_inputs, n_public_inputs, fp, pl->h_proof);
+  ctx->cap = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  pl->n_kernels = (uint32_t)(ctx->launches - launches0);
+  ctx->launches = launches0;  // nothing ran
+  if (rc != P2B_OK || e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    ctx->poisoned = was_poisoned;  // an error raised while capturing says nothing about the device
+    return rc != P2B_OK ? rc : fail(ctx, P2B_ERR_UNSUPPORTED, "stream capture failed: %s", cudaGetErrorString(e));
+  }
+  pl->graph = g;
+  if (cudaGraphInstantiate(&pl->exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    pl->exec = nullptr;
+    return fail(ctx, P2B_ERR_UNSUPPORTED, "cudaGraphInstantiate failed");
+  }
+  // the witness copy node: the memcpy node that writes pl->d_wires_dst
+  size_t n_nodes = 0;
+  cudaGraphGetNodes(g, nullptr, &n_nodes);
+  std::vector<cudaGraphNode_t> nodes(n_nodes);
+  if (n_nodes) cudaGraphGetNodes(g, nodes.data(), &n_nodes);
+  pl->has_wires_node = false;
+  for (cudaGraphNode_t nd : nodes) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeMemcpy) continue;
+    cudaMemcpy3DParms mp{};
+    if (cudaGraphMemcpyNodeGetParams(nd, &mp) != cudaSuccess) continue;
+    if (mp.dstPtr.ptr == (void*)pl->d_wires_dst) {
+      pl->wires_node = nd;
+      pl->has_wires_node = true;
+      break;
+    }
+  }
+  cudaGetLastError();
+  if (!pl->has_wires_node) return fail(ctx, P2B_ERR_UNSUPPORTED, "prove plan: witness copy node not found");
+  pl->state = ProvePlan::READY;
+  return P2B_OK;
+}
+
+static bool cols_contiguous(const uint64_t* const* cols, size_t n_cols, size_t n) {
+  for (size_t i = 1; i < n_cols; i++)
+    if (cols[i] != cols[0] + i * n) return false;
+  return true;
+}
+
+// one launch of a READY plan
+static int plan_launch(p2b_ctx* ctx, ProvePlan* pl, const p2b_circuit* c, const uint64_t* circuit_digest,
+                       const uint64_t* const* wire_cols, const uint64_t* d_wires, const uint64_t* public_inputs,
+                       size_t n_public_inputs, bool caller_keeps_buffers) {
+  const size_t n = (size_t)1 << c->d.degree_bits;
+  for (int i = 0; i < 4; i++) pl->h_digest[i] = circuit_digest[i] % GL_P;
+  for (size_t i = 0; i < n_public_inputs; i++) pl->h_pis[i] = public_inputs[i] % GL_P;
+  const void* src;
+  cudaMemcpyKind kind;
+  if (pl->dev_src) {
+    src = d_wires;
+    kind = cudaMemcpyDeviceToDevice;
+  } else {
+    kind = cudaMemcpyHostToDevice;
+    // a contiguous pinned matrix goes by DMA straight from the caller's memory when the caller keeps it untouched
+    // until the proof is collected (the blocking p2b_prove); everything else is packed into the plan's pinned matrix
+    if (caller_keeps_buffers && cols_contiguous(wire_cols, c->d.num_wires, n) && host_ptr_is_pinned(wire_cols[0])) {
+      src = wire_cols[0];
+    } else {
+      for (uint32_t w = 0; w < c->d.num_wires; w++) {
+        if (!wire_cols[w]) return fail(ctx, P2B_ERR_INVALID, "cols[%u] is null", w);
+        memcpy(pl->h_wires + (size_t)w * n, wire_cols[w], n * sizeof(uint64_t));
+      }
+      src = pl->h_wires;
+    }
+  }
+  if (src != pl->cur_src) {
+    CU(ctx, cudaGraphExecMemcpyNodeSetParams1D(pl->exec, pl->wires_node, pl->d_wires_dst, src, pl->wires_words * sizeof(uint64_t), kind));
+    pl->cur_src = src;
+  }
+  CU(ctx, cudaGraphLaunch(pl->exec, ctx->stream));
+  ctx->launches += pl->n_kernels;
+  pl->last_use = ++ctx->plan_clock;
+  return P2B_OK;
+}
+
+// p2b_prove_submit / p2b_prove_dev_submit: validate, pick eager or graph, enqueue.  The proof is then pending on the
+// context until prove_collect.
+static int prove_submit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                        const uint64_t* const* wire_cols, const uint64_t* d_wires, const uint64_t* public_inputs,
+                        size_t n_public_inputs, const p2b_fri_params* fp, bool caller_keeps_buffers) {
+  CHECK_CTX(ctx);
+  if (!c || !cs || !circuit_digest || (!wire_cols && !d_wires) || !fp || (n_public_inputs && !public_inputs))
+    return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ctx->pending_words) return fail(ctx, P2B_ERR_INVALID, "a submitted proof has not been collected yet (p2b_prove_collect)");
+  if (c->ctx != ctx || cs->ctx != ctx) return fail(ctx, P2B_ERR_INVALID, "handle of another context");
+  if (fp->n_layers > P2B_MAX_FRI_LAYERS) return fail(ctx, P2B_ERR_INVALID, "too many FRI layers");
+  if (cs->rate_bits != fp->rate_bits) return fail(ctx, P2B_ERR_INVALID, "constants_sigmas rate_bits differ from the FRI parameters");
+  const p2b_circuit_desc& d = c->d;
+  const uint32_t rb = fp->rate_bits, caph = fp->cap_height;
+  {
+    // validate the FRI parameters before any length is derived from them (unsigned underflow otherwise)
+    uint32_t log_len = 0;
+    int rc0 = check_fri_args(ctx, ((size_t)1 << d.degree_bits) << rb, fp->reduction_arity_bits, fp->n_layers, rb, &log_len);
+    if (rc0) return rc0;
+    uint32_t lc = log_len;
+    for (uint32_t l = 0; l < fp->n_layers; l++) {
+      lc -= fp->reduction_arity_bits[l];
+      if (caph > lc) return fail(ctx, P2B_ERR_INVALID, "cap_height %u exceeds the height %u of FRI layer %u", caph, lc, l);
+    }
+    if (caph > d.degree_bits + rb || cs->cap_height > d.degree_bits + rb) return fail(ctx, P2B_ERR_INVALID, "cap_height too large");
+  }
+  if (cs->log_n != d.degree_bits || cs->n_cols != (size_t)d.num_constants + d.num_routed_wires)
+    return fail(ctx, P2B_ERR_INVALID, "constants_sigmas (2^%u x %zu) does not match the circuit (2^%u x %u)", cs->log_n, cs->n_cols,
+                d.degree_bits, d.num_constants + d.num_routed_wires);
+  int rc = P2B_OK;
+  const size_t proof_len = proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
+  const bool dev_src = d_wires != nullptr;
+  // small proofs only: a large one is bound by its kernels, and its host upload is pipelined against the transforms
+  const bool want_graph = graphs_enabled() && !ctx->profiling && !trace_enabled() && d.degree_bits <= 14;
+  ProvePlan* pl = want_graph ? plan_find(ctx, c, cs, fp, n_public_inputs, dev_src) : nullptr;
+  if (pl && pl->state == ProvePlan::SEEN) {
+    rc = plan_capture(ctx, pl, c, cs, circuit_digest, wire_cols, d_wires, public_inputs, n_public_inputs, fp);
+    if (rc != P2B_OK) {
+      if (ctx->poisoned) return rc;
+      ctx->plan_note = ctx->err;  // why this shape stays on the eager path (p2b_plan_info)
+    }
+  }
+  if (pl && pl->state == ProvePlan::READY) {
+    rc = plan_launch(ctx, pl, c, circuit_digest, wire_cols, d_wires, public_inputs, n_public_inputs, caller_keeps_buffers);
+    if (rc) return rc;
+    ctx->pending_src = pl->h_proof;
+  } else {
+    // eager
+    if (proof_len * sizeof(uint64_t) > ctx->h_proof_bytes) {
+      if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
+      ctx->h_proof = nullptr;
+      ctx->h_proof_bytes = 0;
+      CU(ctx, cudaMallocHost((void**)&ctx->h_proof, proof_len * sizeof(uint64_t)));
+      ctx->h_proof_bytes = proof_len * sizeof(uint64_t);
+    }
+    rc = prove_body(ctx, c, cs, circuit_digest, wire_cols, d_wires, public_inputs, n_public_inputs, fp, ctx->h_proof);
+    if (rc) return rc;
+    ctx->pending_src = ctx->h_proof;
+    if (want_graph && !pl) {
+      // first proof of this shape on this context: it has warmed the twiddle / coset tables; the next one is captured
+      if (ctx->plans.size() >= 16) {  // bounded: evict the least recently used plan
+        size_t lru = 0;
+        for (size_t i = 1; i < ctx->plans.size(); i++)
+          if (ctx->plans[i]->last_use < ctx->plans[lru]->last_use) lru = i;
+        plan_destroy(ctx, ctx->plans[lru]);
+        ctx->plans.erase(ctx->plans.begin() + lru);
+      }
+      ProvePlan* np = new (std::nothrow) ProvePlan();
+      if (np) {
+        np->circuit_id = c->id;
+        np->cs_id = cs->id;
+        np->fp = *fp;
+        np->n_pis = n_public_inputs;
+        np->dev_src = dev_src;
+        np->state = ProvePlan::SEEN;
+        np->last_use = ++ctx->plan_clock;
+        ctx->plans.push_back(np);
+      }
+    }
+  }
+  ctx->pending_words = proof_len;
+  ctx->pending_pow_index = proof_len - n_public_inputs - 1;
+  return P2B_OK;
+}
+
+static int prove_collect(p2b_ctx* ctx, uint64_t* proof_out, size_t proof_cap) {
+  CHECK_CTX(ctx);
+  if (!proof_out) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (!ctx->pending_words) return fail(ctx, P2B_ERR_INVALID, "no submitted proof to collect");
+  const size_t len = ctx->pending_words;
+  if (proof_cap < len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, len);
+  ctx->pending_words = 0;
+  ctx->h2d_event_pending = false;  // everything enqueued has finished once the stream is idle
+  CU(ctx, ctx_sync(ctx));
+  memcpy(proof_out, ctx->pending_src, len * sizeof(uint64_t));
+  if (proof_out[ctx->pending_pow_index] == ~0ull) return fail(ctx, P2B_ERR_INVALID, "no proof-of-work witness found");
+  return P2B_OK;
+}
+
 extern "C" int p2b_prove(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
                          const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
                          const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
-  if (ctx && !wire_cols) return fail(ctx, P2B_ERR_INVALID, "null argument");
-  return prove_impl(ctx, c, cs, circuit_digest, wire_cols, nullptr, public_inputs, n_public_inputs, fp, proof_out, proof_cap);
+  if (ctx && (!wire_cols || !proof_out)) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ctx && c && cs && fp && fp->n_layers <= P2B_MAX_FRI_LAYERS) {
+    const size_t need = p2b_proof_len(c, cs, fp, n_public_inputs);
+    if (need && proof_cap < need) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, need);
+  }
+  int rc = prove_submit(ctx, c, cs, circuit_digest, wire_cols, nullptr, public_inputs, n_public_inputs, fp, true);
+  return rc ? rc : prove_collect(ctx, proof_out, proof_cap);
 }
 extern "C" int p2b_prove_dev(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
                              const uint64_t* d_wire_values, const uint64_t* public_inputs, size_t n_public_inputs,
                              const p2b_fri_params* fp, uint64_t* proof_out, size_t proof_cap) {
-  if (ctx && !d_wire_values) return fail(ctx, P2B_ERR_INVALID, "null argument");
-  return prove_impl(ctx, c, cs, circuit_digest, nullptr, d_wire_values, public_inputs, n_public_inputs, fp, proof_out, proof_cap);
+  if (ctx && (!d_wire_values || !proof_out)) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  if (ctx && c && cs && fp && fp->n_layers <= P2B_MAX_FRI_LAYERS) {
+    const size_t need = p2b_proof_len(c, cs, fp, n_public_inputs);
+    if (need && proof_cap < need) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, need);
+  }
+  int rc = prove_submit(ctx, c, cs, circuit_digest, nullptr, d_wire_values, public_inputs, n_public_inputs, fp, true);
+  return rc ? rc : prove_collect(ctx, proof_out, proof_cap);
+}
+extern "C" int p2b_prove_submit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                                const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                                const p2b_fri_params* fp) {
+  if (ctx && !wire_cols) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  int rc = prove_submit(ctx, c, cs, circuit_digest, wire_cols, nullptr, public_inputs, n_public_inputs, fp, false);
+  // the caller may refill its witness buffers as soon as this returns: wait for the upload (not for the proof)
+  if (rc == P2B_OK && ctx->h2d_event_pending) {
+    ctx->h2d_event_pending = false;
+    CU(ctx, cudaEventSynchronize(ctx->ev_h2d));
+  }
+  return rc;
+}
+extern "C" int p2b_prove_poll(p2b_ctx* ctx) {
+  CHECK_CTX(ctx);
+  if (!ctx->pending_words) return fail(ctx, P2B_ERR_INVALID, "no submitted proof");
+  cudaError_t e = cudaStreamQuery(ctx->stream);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  return fail(ctx, P2B_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(e));
+}
+extern "C" int p2b_prove_collect(p2b_ctx* ctx, uint64_t* proof_out, size_t proof_cap) { return prove_collect(ctx, proof_out, proof_cap); }
+extern "C" int p2b_plan_info(p2b_ctx* ctx, uint32_t* n_ready, uint32_t* n_seen, uint32_t* n_failed, uint32_t* kernels_per_launch) {
+  CHECK_CTX(ctx);
+  uint32_t r = 0, sn = 0, f = 0, k = 0;
+  for (ProvePlan* pl : ctx->plans) {
+    if (pl->state == ProvePlan::READY) r++, k = pl->n_kernels;
+    else if (pl->state == ProvePlan::SEEN) sn++;
+    else f++;
+  }
+  if (n_ready) *n_ready = r;
+  if (n_seen) *n_seen = sn;
+  if (n_failed) *n_failed = f;
+  if (kernels_per_launch) *kernels_per_launch = k;
+  if (f) ctx->err = "prove plan not captured: " + ctx->plan_note;
+  return P2B_OK;
 }

@@ -146,24 +146,76 @@ __global__ void __launch_bounds__(256) k_pp_finish(const uint64_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ gate evaluators
-// Accumulates filter-free sum_q alpha^q c_q for every challenge.  The running sums are NOT canonical (one fused
-// multiply-add + reduction per constraint and challenge, gl::mad_nc); whoever reads a[] multiplies it (fmul) or
-// canonicalises it.
+// Accumulates filter-free sum_q alpha^q c_q for every challenge — WITHOUT reducing: each product c_q * alpha^q is a
+// 128-bit integer and a gate has at most a few hundred constraints, so the running sum fits five 32-bit words
+// (sum < 2^136).  A push is 8 multiply-adds and 5 carry adds per challenge (a reduced multiply-add, gl::mad_nc, is
+// 25 instructions), and the single reduction happens in value(): 2^128 = -2^32 (mod p).  Exact integer arithmetic,
+// so the field element is the same as plonky2's reduce_with_powers.
 struct Acc {
-  uint64_t a[MAX_CHALLENGES];
-  const uint64_t* apow;  // [challenge][stride] powers of alpha, already offset to the first gate term
+  uint32_t w[MAX_CHALLENGES][5];
+  const uint64_t* apow;  // [challenge][stride] powers of alpha (canonical), already offset to the first gate term
   uint32_t stride, n_chal, q;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int ch = 0; ch < MAX_CHALLENGES; ch++)
+#pragma unroll
+      for (int k = 0; k < 5; k++) w[ch][k] = 0;
+  }
+  __device__ __forceinline__ void add_product(int ch, uint64_t c, uint64_t a) {
+    const uint32_t c0 = (uint32_t)c, c1 = (uint32_t)(c >> 32), a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %8, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "+r"(w[ch][0]), "+r"(w[ch][1]), "+r"(w[ch][2]), "+r"(w[ch][3]), "+r"(w[ch][4])
+        : "r"(c0), "r"(c1), "r"(a0), "r"(a1));
+  }
+  // c: any u64 (canonical or not); the alpha powers are canonical
   __device__ __forceinline__ void push(uint64_t c) {
 #pragma unroll
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) a[ch] = gl::mad_nc(c, apow[ch * stride + q], a[ch]);
+      if (ch < (int)n_chal) add_product(ch, c, apow[ch * stride + q]);
     q++;
   }
   // constraint number q + k of the gate, without advancing
   __device__ __forceinline__ void push_at(uint32_t k, uint64_t c) {
 #pragma unroll
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) a[ch] = gl::mad_nc(c, apow[ch * stride + q + k], a[ch]);
+      if (ch < (int)n_chal) add_product(ch, c, apow[ch * stride + q + k]);
+  }
+  // the accumulated sum of challenge ch as a canonical field element
+  __device__ __forceinline__ uint64_t value(int ch) const {
+    // low 128 bits: x3:x2:x1:x0 -> (x1:x0) - x3 + x2 * (2^32 - 1), exactly gl::mul_nc's reduction
+    uint32_t r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m,tl,th;\n\t"
+        "sub.cc.u32 tl, %2, %5;\n\t"
+        "subc.cc.u32 th, %3, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 tl, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "mad.lo.cc.u32 tl, %4, 0xFFFFFFFF, tl;\n\t"
+        "madc.hi.cc.u32 th, %4, 0xFFFFFFFF, th;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "add.u32 %1, th, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(w[ch][0]), "r"(w[ch][1]), "r"(w[ch][2]), "r"(w[ch][3]));
+    // + w4 * 2^128 = - w4 * 2^32
+    return gl::sub(gl::canon(gl::pack(r0, r1)), gl::pack(0u, w[ch][4]));
   }
 };
 
@@ -265,7 +317,7 @@ __device__ void eval_poseidon_gate(const Vars& v, Acc& acc) {
   for (int i = 0; i < 12; i++) acc.push(fsub(s[i], v.w(12 + i)));
 }
 
-__device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
+__device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Acc& acc) {
   switch (g.kind) {
     case GATE_NOOP:
       break;
@@ -293,9 +345,6 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
       }
       break;
     }
-    case GATE_POSEIDON:
-      eval_poseidon_gate(v, acc);
-      break;
     case GATE_U32_ARITHMETIC: {
       const uint32_t ops = g.p0;
       for (uint32_t i = 0; i < ops; i++) {
@@ -476,6 +525,16 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
       }
       break;
     }
+    default:
+      break;
+  }
+}
+
+__device__ __forceinline__ void eval_gate_heavy(const Gate& g, const Vars& v, Acc& acc) {
+  switch (g.kind) {
+    case GATE_POSEIDON:
+      eval_poseidon_gate(v, acc);
+      break;
     case GATE_RANDOM_ACCESS: {  // p0 = bits (<= 6), p1 = num_copies | num_extra_constants << 16
       const uint32_t bits = g.p0, copies = g.p1 & 0xFFFF, extra = g.p1 >> 16, vec = 1u << bits;
       const uint32_t routed = (2 + vec) * copies + extra;
@@ -554,6 +613,7 @@ __device__ void eval_gate(const Gate& g, const Vars& v, Acc& acc) {
   }
 }
 
+
 // ------------------------------------------------------------------------------------------ quotient values
 struct QuotientParams {
   const uint64_t* cs_lde;     // constants || sigmas, column-major, leaf order, column stride N
@@ -573,18 +633,30 @@ struct QuotientParams {
   ntt2::RootTables roots;
 };
 
-// grid = (lde_size / 128, 1 + n_gates): row 0 of the grid evaluates the permutation argument (L_0 (Z - 1) and the
-// partial-product checks), row 1 + g evaluates gate g.  A point's work is a long dependent instruction stream
-// (the PoseidonGate alone is a whole permutation), and one thread per point leaves a 2^12-row proof with 7 warps
-// per SM; splitting by term group puts (1 + n_gates) times as many independent streams in flight.  Each part
-// writes its alpha-weighted sum to parts[part][challenge][point]; k_quotient_combine adds them (field addition
-// is exact, so the order is irrelevant) and divides by Z_H.
-// 8 CTAs of 128 threads per SM (64 registers, some spills in the widest gates): the kernel waits on its loads (44 % of
-// the stall samples were long-scoreboard at 5 CTAs per SM); measured at 2^14 rows: 5 CTAs 1.78 ms, 6: 1.70, 8: 1.65, 10: 1.69
+// One thread = (point, term group): group 0 is the permutation argument (L_0 (Z - 1) and the partial-product checks),
+// group 1 + g is gate g.  A point's work is a long dependent instruction stream (the PoseidonGate alone is a whole
+// permutation), and one thread per point leaves a 2^12-row proof with 7 warps per SM; splitting by term group puts
+// (1 + n_gates) times as many independent streams in flight.  Each group writes its alpha-weighted sum to
+// parts[group][challenge][point]; k_quotient_combine adds them (field addition is exact, so the order is irrelevant)
+// and divides by Z_H.
+// The groups are evaluated by THREE kernels, so that each gets the register budget its code needs (one kernel for
+// everything had to live in 64 registers and spilled ~2 KB per thread in the widest gates):
+//   k_quotient_perm            grid (lde_size / 128, 1)          the permutation argument
+//   k_quotient_gates<false>    grid (lde_size / 128, n_light)    gates whose evaluators are short loops over wires
+//   k_quotient_gates<true>     grid (lde_size / 128, n_heavy)    Poseidon, PoseidonMds, RandomAccess, CosetInterpolation
+//                                                                (state arrays: 12-element permutation state, 64 items)
+// gate_list[blockIdx.y] = index of the gate in P.gates.
+__device__ __forceinline__ bool gate_is_heavy(uint32_t kind) {
+  return kind == GATE_POSEIDON || kind == GATE_POSEIDON_MDS || kind == GATE_RANDOM_ACCESS || kind == GATE_COSET_INTERPOLATION;
+}
 #ifndef P2B_QUOT_MINB
 #define P2B_QUOT_MINB 8
 #endif
-__global__ void __launch_bounds__(128, P2B_QUOT_MINB) k_quotient(QuotientParams P) {
+#ifndef P2B_QUOT_HEAVY_MINB
+#define P2B_QUOT_HEAVY_MINB 4
+#endif
+
+__global__ void __launch_bounds__(128, 6) k_quotient_perm(QuotientParams P) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
   const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,8 +669,7 @@ __global__ void __launch_bounds__(128, P2B_QUOT_MINB) k_quotient(QuotientParams 
   uint64_t res[MAX_CHALLENGES];
 #pragma unroll
   for (int c = 0; c < MAX_CHALLENGES; c++) res[c] = 0;
-  const uint32_t part = blockIdx.y;
-  if (part == 0) {
+  {
     const size_t i_next = (i + ((size_t)1 << P.mdb)) & (lde_size - 1);
     const size_t leaf_next = ntt2::brev((uint32_t)i_next, log_lde);
     const uint32_t zi = (uint32_t)(i & (((size_t)1 << P.mdb) - 1));
@@ -659,26 +730,43 @@ __global__ void __launch_bounds__(128, P2B_QUOT_MINB) k_quotient(QuotientParams 
         }
     }
     for (uint32_t c = 0; c < nch; c++) res[c] = gl::canon(res[c]);  // k_quotient_combine adds canonical parts
-  } else {
-    // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
-    Vars v{wr, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
-    const Gate gate = P.gates[part - 1];
-    const uint64_t s = gl::canon(cs[(size_t)gate.selector_index * N]);
-    uint64_t filter = 1;
-    for (uint32_t q = gate.group_start; q < gate.group_end; q++)
-      if (q != gate.row) filter = fmul(filter, fsub(q, s));
-    if (P.num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
-    Acc acc;
-#pragma unroll
-    for (int c = 0; c < MAX_CHALLENGES; c++) acc.a[c] = 0;
-    acc.apow = P.apow + nch * (npp + 2);
-    acc.stride = P.n_terms;
-    acc.n_chal = nch;
-    acc.q = 0;
-    eval_gate(gate, v, acc);
-    for (uint32_t c = 0; c < nch; c++) res[c] = fmul(filter, acc.a[c]);
   }
-  for (uint32_t c = 0; c < nch; c++) P.parts[((size_t)part * nch + c) * lde_size + i] = res[c];
+  for (uint32_t c = 0; c < nch; c++) P.parts[(size_t)c * lde_size + i] = res[c];
+}
+
+template <bool HEAVY>
+__global__ void __launch_bounds__(128, HEAVY ? P2B_QUOT_HEAVY_MINB : P2B_QUOT_MINB)
+k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
+  const uint32_t log_lde = P.degree_bits + P.mdb;
+  const size_t lde_size = (size_t)1 << log_lde;
+  const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= lde_size) return;
+  const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
+  const uint32_t nch = P.n_chal, npp = P.num_pp;
+  const uint64_t* cs = P.cs_lde + leaf;
+  const size_t N = P.N;
+  const uint32_t g = gate_list[blockIdx.y];
+  // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
+  Vars v{P.wires_lde + leaf, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
+  const Gate gate = P.gates[g];
+  const uint64_t s = gl::canon(cs[(size_t)gate.selector_index * N]);
+  uint64_t filter = 1;
+  for (uint32_t q = gate.group_start; q < gate.group_end; q++)
+    if (q != gate.row) filter = fmul(filter, fsub(q, s));
+  if (P.num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
+  Acc acc;
+  acc.clear();
+  acc.apow = P.apow + nch * (npp + 2);
+  acc.stride = P.n_terms;
+  acc.n_chal = nch;
+  acc.q = 0;
+  if (HEAVY)
+    eval_gate_heavy(gate, v, acc);
+  else
+    eval_gate_light(gate, v, acc);
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++)
+    if (c < (int)nch) P.parts[((size_t)(1 + g) * nch + c) * lde_size + i] = fmul(filter, acc.value(c));
 }
 
 // out[c][i] = (sum over parts) / Z_H(x_i)

@@ -80,6 +80,13 @@ class Context:
         last.check(self.lib.p2b_timer_span_ms(self.h, last.h, C.byref(ms)))
         return float(ms.value)
 
+    def plan_info(self):
+        """prove plans (captured CUDA graphs) of this context: dict(ready, seen, failed, kernels_per_launch, note)"""
+        v = [C.c_uint32() for _ in range(4)]
+        self.check(self.lib.p2b_plan_info(self.h, *[C.byref(x) for x in v]))
+        note = self.lib.p2b_last_error(self.h).decode() if v[2].value else ""
+        return dict(ready=v[0].value, seen=v[1].value, failed=v[2].value, kernels_per_launch=v[3].value, note=note)
+
     STAGES = ("h2d", "intt", "lde", "leaf_hash", "tree_levels", "fri_fold_ntt", "transcript", "other")
 
     def profile_enable(self, on=True):
@@ -275,6 +282,31 @@ class PolynomialBatch:
         h = C.c_void_p()
         ctx.check(ctx.lib.p2b_batch_from_coeffs_dev(ctx.h, C.c_void_p(dev_ptr), n_cols, log_n, rate_bits,
                                                     cap_height, 0, C.byref(h)))
+        return cls(ctx, h)
+
+    def attach(self, ctx):
+        """a read-only view of this batch for another context of the same device (p2b_batch_attach): the contexts of a
+        GPU share one device copy of a circuit's constants|sigmas batch.  This batch must outlive the view."""
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_attach(ctx.h, self.h, C.byref(h)))
+        v = PolynomialBatch(ctx, h)
+        v._source = self
+        return v
+
+    def export(self):
+        """serialised form (bytes): header, cap, coefficients (+ kept values) — p2b_batch_export"""
+        n = int(self.ctx.lib.p2b_batch_export_len(self.h))
+        buf = np.zeros(n, np.uint8)
+        w = C.c_size_t()
+        self.ctx.check(self.ctx.lib.p2b_batch_export(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.byref(w)))
+        return buf[: w.value].tobytes()
+
+    @classmethod
+    def import_(cls, ctx, blob):
+        """p2b_batch_import: LDE and Merkle tree recomputed on the device, cap checked against the stored one"""
+        a = np.frombuffer(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2b_batch_import(ctx.h, a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size, C.byref(h)))
         return cls(ctx, h)
 
     @property
@@ -588,6 +620,37 @@ def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
     if raw:
         return buf
     return parse_proof_words(circuit.desc, cs, fri_params, buf, len(public_inputs))
+
+
+def prove_submit(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params):
+    """p2b_prove_submit: enqueue the whole proof and return; `wire_values` may be reused at once.  -> number of proof
+    words to hand to prove_collect.  One proof may be pending per context."""
+    keep, ptrs, log_n, n_cols = PolynomialBatch._cols(wire_values)
+    d = circuit.desc
+    if n_cols != d["num_wires"] or log_n != d["degree_bits"]:
+        raise ValueError("witness shape does not match the circuit")
+    pis = _felts(public_inputs) if len(public_inputs) else np.zeros(1, np.uint64)
+    ps = fri_params.struct()
+    cs = constants_sigmas_commitment
+    n_words = int(ctx.lib.p2b_proof_len(circuit.h, cs.h, C.byref(ps), len(public_inputs)))
+    if n_words == 0:
+        raise P2BError(-1, "inconsistent FRI parameters")
+    ctx.check(ctx.lib.p2b_prove_submit(ctx.h, circuit.h, cs.h, _ptr(_felts(circuit_digest)), ptrs, _ptr(pis),
+                                       len(public_inputs), C.byref(ps)))
+    return n_words
+
+
+def prove_poll(ctx):
+    rc = ctx.lib.p2b_prove_poll(ctx.h)
+    if rc < 0:
+        ctx.check(rc)
+    return rc == 1
+
+
+def prove_collect(ctx, n_words):
+    buf = np.zeros(n_words, np.uint64)
+    ctx.check(ctx.lib.p2b_prove_collect(ctx.h, _ptr(buf), n_words))
+    return buf
 
 
 def prove_native_device(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values_dev_ptr, public_inputs,

@@ -21,8 +21,9 @@
  *    opaque handles until the matching *_free; no handle may outlive its context.
  *  - A p2b_ctx is bound to one device and one CUDA stream and is NOT thread-safe; use one context per
  *    OS thread (several per GPU are fine and let small proofs overlap).
- *  - Host inputs may be pageable or pinned; pinned (p2b_host_alloc) buffers are copied with one
- *    asynchronous DMA per column group and are what bench.py uses.
+ *  - Host inputs may be pageable or pinned; pinned (p2b_host_alloc) buffers are copied by DMA without staging.
+ *    Every entry point that takes host input returns only after that input has been read (staged or uploaded): the
+ *    caller may refill its buffers at once, while the transforms are still running on the device.
  *  - There is no CPU fallback: if no CUDA device is usable p2b_init fails.
  */
 #ifndef P2B_H
@@ -132,6 +133,19 @@ const uint64_t *p2b_batch_dev_coeffs(const p2b_batch *b);
 int p2b_batch_lde_col(p2b_batch *b, size_t col, uint64_t *out);
 /* values on H of column `col` (batches built from values with P2B_KEEP_VALUES) -> out[2^log_n] */
 int p2b_batch_values(p2b_batch *b, size_t col, uint64_t *out);
+
+/* ---- circuit-data reuse.  prover_data.constants_sigmas_commitment is built once per circuit
+ * (CircuitBuilder::build: city_rollup_core_worker_qbench/src/qbench.rs:21, city_rollup_circuit/src/sighash_circuits/
+ * sighash_wrapper.rs:142-148) and read by every proof of it. */
+/* A read-only view of `src` for another context of the SAME device: the contexts of a GPU then share one device copy of
+ * the constants|sigmas batch.  `src` (and its context) must outlive the view; freeing the view frees nothing else. */
+int p2b_batch_attach(p2b_ctx *ctx, const p2b_batch *src, p2b_batch **out);
+/* Serialised form (host bytes): header, cap, coefficients (+ the values on H of a P2B_KEEP_VALUES batch).  import
+ * recomputes the LDE and the Merkle tree on the device and fails with P2B_ERR_INVALID when the recomputed cap differs
+ * from the stored one. */
+size_t p2b_batch_export_len(const p2b_batch *b);
+int p2b_batch_export(p2b_batch *b, uint8_t *out, size_t out_cap, size_t *written);
+int p2b_batch_import(p2b_ctx *ctx, const uint8_t *bytes, size_t n_bytes, p2b_batch **out);
 
 /* ---------------------------------------------------------------- PLONK stages ----------- */
 /* What the prover stages between the commitments need of plonky2's CommonCircuitData
@@ -314,6 +328,23 @@ int p2b_prove(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constan
 int p2b_prove_dev(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
                   const uint64_t *circuit_digest, const uint64_t *d_wire_values, const uint64_t *public_inputs,
                   size_t n_public_inputs, const p2b_fri_params *params, uint64_t *proof_out, size_t proof_cap);
+
+/* Asynchronous form for a worker that generates the next witness while the GPU proves (the reference's worker does
+ * witness generation and then a blocking prove, city_rollup_circuit/src/worker/traits.rs:143-160; the sighash jobs even
+ * prove a STARK inside witness generation, city_common_circuit/src/hash/accelerator/sha256/smartgadget.rs:518-523).
+ * p2b_prove_submit enqueues the whole proof and returns: the witness has been staged (pageable columns) or its upload
+ * has completed (pinned columns), so every buffer passed in may be reused at once.  One proof may be pending per
+ * context; one host thread can keep several contexts busy.  p2b_prove_poll: 1 = finished, 0 = still running.
+ * p2b_prove_collect waits and writes the proof words (as p2b_prove). */
+int p2b_prove_submit(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+                     const uint64_t *circuit_digest, const uint64_t *const *wire_cols, const uint64_t *public_inputs,
+                     size_t n_public_inputs, const p2b_fri_params *params);
+int p2b_prove_poll(p2b_ctx *ctx);
+int p2b_prove_collect(p2b_ctx *ctx, uint64_t *proof_out, size_t proof_cap);
+/* Prove plans: from the second proof of a given (circuit, constants_sigmas, parameters) on, a context replays the proof
+ * as ONE captured CUDA graph (P2B_GRAPH=0 turns this off).  Counts of this context's plans by state and the number of
+ * kernels one replay launches; after a failed capture p2b_last_error tells why that shape stays on the eager path. */
+int p2b_plan_info(p2b_ctx *ctx, uint32_t *n_ready, uint32_t *n_seen, uint32_t *n_failed, uint32_t *kernels_per_launch);
 
 /* ---------------------------------------------------------------- proof bytes ------------ */
 /* The byte form the reference stores and ships proofs in: `bincode::serialize(&ProofWithPublicInputs)`

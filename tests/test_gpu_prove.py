@@ -9,6 +9,7 @@ import pytest
 import p2oracle as O
 import plonk_ref as R
 import verifier_ref as V
+from util import rand_felts
 from test_plonk_oracle import ALL_GATES, CITY_GATES, CITY_GROUPS, RECURSION_GATES, RECURSION_GROUPS
 from test_prove_oracle import FP_SMALL, make_case
 
@@ -93,6 +94,146 @@ def test_city_shape_proof_equals_c_oracle(ctx, m, name, gates, groups, seed):
     assert V.verify(circ, cs.cap, digest, V.parse_proof(circ, FP_CITY, got, len(pis)), FP_CITY)
     cs.free()
     cd.free()
+
+
+def _random_witness(circ, seed):
+    """any words at all: the prover does not check satisfaction, and the oracle prover computes the same (invalid) proof"""
+    rng = np.random.default_rng(seed)
+    return [rng.integers(0, R.P, circ.n, dtype=np.uint64) for _ in range(circ.num_wires)]
+
+
+@pytest.mark.parametrize("degree_bits,fp", [(8, dict(FP_SMALL, cap_height=3, proof_of_work_bits=8)), (12, FP_CITY)])
+def test_replayed_plans_equal_the_oracle(m, degree_bits, fp):
+    """From its second proof of a shape on, a context replays a captured CUDA graph (p2b_plan_info says so).  Different
+    witnesses, public inputs and circuit digests through the SAME plan — host witness (pageable columns, one pageable
+    matrix, a pinned matrix), device witness, and the submit / collect form — must each equal the C oracle's proof
+    word for word; two circuits alternate on the context to exercise two plans side by side."""
+    import torch
+
+    c = m.Context(0)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], fp["reduction_arity_bits"])
+    cases = []
+    for k, (gates, groups) in enumerate(((RECURSION_GATES, RECURSION_GROUPS), (CITY_GATES, CITY_GROUPS))):
+        circ, digest, pis = make_case(degree_bits, gates, groups, 70 + k)
+        cd = m.CircuitData(c, circ.desc())
+        cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"], keep_values=True)
+        pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), fp)
+        cases.append((circ, cd, cs, pd))
+    pinned = c.pinned_empty((cases[0][0].num_wires, cases[0][0].n))
+    for it in range(5):
+        for k, (circ, cd, cs, pd) in enumerate(cases):
+            wv = circ.wire_values() if it == 0 else _random_witness(circ, 1000 * k + it)
+            digest = [it + 1, 2 * k + 5, 0xFFFFFFFF00000000 - it, 9]
+            pis = [it, k, 3, 0xFFFFFFFF00000001 + it]  # incl. a non-canonical word
+            want = pd.prove(digest, wv, pis)
+            mode = ("cols", "matrix", "pinned", "submit", "cols")[it]
+            if mode == "cols":
+                got = m.prove_native(c, cd, cs, digest, wv, pis, params, raw=True)
+            elif mode == "matrix":
+                got = m.prove_native(c, cd, cs, digest, np.stack(wv), pis, params, raw=True)
+            elif mode == "pinned":
+                pinned[:] = np.stack(wv)
+                got = m.prove_native(c, cd, cs, digest, pinned, pis, params, raw=True)
+            else:
+                scratch = np.stack(wv)
+                n_words = m.prove_submit(c, cd, cs, digest, scratch, pis, params)
+                scratch[:] = 0  # the witness buffer belongs to the caller again as soon as submit returns
+                got = m.prove_collect(c, n_words)
+            assert (got == want).all(), "iteration %d circuit %d (%s): first differing word %d" % (it, k, mode, np.nonzero(got != want)[0][0])
+            dev = torch.from_numpy(np.stack(wv).view(np.int64)).cuda()
+            torch.cuda.synchronize()
+            got_dev = m.prove_native_device(c, cd, cs, digest, dev.data_ptr(), pis, params)
+            assert (got_dev == want).all(), "iteration %d circuit %d: p2b_prove_dev differs" % (it, k)
+    info = c.plan_info()
+    if os.environ.get("P2B_GRAPH", "1") != "0":
+        assert info["failed"] == 0, info
+        assert info["ready"] == 4, info  # 2 circuits x (host, device) witness
+        assert 0 < info["kernels_per_launch"] <= 60, info
+    for circ, cd, cs, pd in cases:
+        pd.free()
+        cs.free()
+        cd.free()
+    c.close()
+
+
+def test_one_thread_drives_several_contexts(m):
+    """p2b_prove_submit / p2b_prove_collect: ONE host thread keeps three contexts busy (each with a proof in flight) and
+    shares ONE constants|sigmas batch between them (p2b_batch_attach); every proof equals the oracle's."""
+    fp = dict(FP_SMALL, cap_height=3, proof_of_work_bits=8)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], fp["reduction_arity_bits"])
+    circ, digest, pis = make_case(9, CITY_GATES, CITY_GROUPS, 81)
+    ctxs = [m.Context(0) for _ in range(3)]
+    owner = m.PolynomialBatch.from_values(ctxs[0], circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"], keep_values=True)
+    views = [owner] + [owner.attach(c) for c in ctxs[1:]]
+    cds = [m.CircuitData(c, circ.desc()) for c in ctxs]
+    pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), fp)
+    for rnd in range(4):
+        wvs = [circ.wire_values() if (rnd + i) % 3 == 0 else _random_witness(circ, 50 * rnd + i) for i in range(3)]
+        n_words = [m.prove_submit(c, cd, v, digest, np.stack(w), pis, params) for c, cd, v, w in zip(ctxs, cds, views, wvs)]
+        with pytest.raises(m.P2BError):  # one pending proof per context
+            m.prove_submit(ctxs[0], cds[0], views[0], digest, np.stack(wvs[0]), pis, params)
+        for c, nw, w in zip(ctxs, n_words, wvs):
+            got = m.prove_collect(c, nw)
+            assert (got == pd.prove(digest, w, pis)).all()
+    with pytest.raises(m.P2BError):
+        m.prove_collect(ctxs[1], n_words[1])  # nothing pending
+    for v in views[1:]:
+        v.free()
+    for cd in cds:
+        cd.free()
+    owner.free()
+    pd.free()
+    for c in ctxs:
+        c.close()
+
+
+def test_constants_sigmas_export_import_round_trip(ctx, m):
+    """p2b_batch_export / p2b_batch_import: the imported batch (coefficients + kept values + cap; LDE
+    and tree recomputed on the device) proves the same proof; a flipped byte is rejected through the cap check."""
+    fp = dict(FP_SMALL, cap_height=3, proof_of_work_bits=8)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], fp["reduction_arity_bits"])
+    circ, digest, pis = make_case(8, RECURSION_GATES, RECURSION_GROUPS, 91)
+    cd = m.CircuitData(ctx, circ.desc())
+    cs = m.PolynomialBatch.from_values(ctx, circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"], keep_values=True)
+    blob = cs.export()
+    c2 = m.Context(0)
+    cs2 = m.PolynomialBatch.import_(c2, blob)
+    assert (cs2.cap == cs.cap).all() and cs2.n_cols == cs.n_cols
+    for j in (0, 77, (1 << 11) - 1):
+        assert (cs2.leaf(j) == cs.leaf(j)).all()
+        assert (cs2.merkle_tree.prove(j) == cs.merkle_tree.prove(j)).all()
+    assert (cs2.values(3) == cs.values(3)).all()
+    cd2 = m.CircuitData(c2, circ.desc())
+    a = m.prove_native(ctx, cd, cs, digest, circ.wire_values(), pis, params, raw=True)
+    b = m.prove_native(c2, cd2, cs2, digest, circ.wire_values(), pis, params, raw=True)
+    assert (a == b).all()
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 1
+    with pytest.raises(m.P2BError) as e:
+        m.PolynomialBatch.import_(c2, bytes(bad))
+    assert "cap" in str(e.value)
+    with pytest.raises(m.P2BError):
+        m.PolynomialBatch.import_(c2, blob[:-8])
+    cs2.free()
+    cd2.free()
+    c2.close()
+    cs.free()
+    cd.free()
+
+
+def test_pinned_input_may_be_refilled_after_return(ctx, m):
+    """host-input entry points return only after their input has been read: overwriting a pinned witness / value buffer
+    right after the call must not change the result (the DMA used to be still in flight)"""
+    log_n, n_cols = 14, 40  # the pipelined upload path (>= 32 columns of >= 2^14 rows) and the plain one
+    for ln, nc in ((log_n, n_cols), (10, 20)):
+        src = ctx.pinned_empty((nc, 1 << ln))
+        orig = np.stack([rand_felts(900 + c, 1 << ln) for c in range(nc)])
+        src[:] = orig
+        b = m.PolynomialBatch.from_values(ctx, src, 3, False, 4)
+        src[:] = 0x1234567
+        ref = O.batch_from_values(list(orig), 3, 4, want_leaves=False, want_digests=False)
+        assert (b.cap == ref["cap"]).all()
+        b.free()
 
 
 def test_prove_rejects_inconsistent_fri_parameters(ctx, m):
