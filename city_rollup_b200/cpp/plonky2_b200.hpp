@@ -117,6 +117,26 @@ class PolynomialBatch {
     return out;
   }
   p2b_batch* get() const { return b_; }
+  // A read-only view for another context of the same device (p2b_batch_attach): the worker threads of a GPU share ONE
+  // device copy of a circuit's constants|sigmas batch.  *this must outlive the view.
+  PolynomialBatch attach(const Context& other) const {
+    p2b_batch* v = nullptr;
+    other.check(p2b_batch_attach(other.get(), b_, &v));
+    return PolynomialBatch(&other, v);
+  }
+  // bytes a later process imports instead of re-running CircuitBuilder::build's commitment (p2b_batch_export / import)
+  std::vector<uint8_t> export_bytes() const {
+    std::vector<uint8_t> out(p2b_batch_export_len(b_));
+    size_t written = 0;
+    ctx_->check(p2b_batch_export(b_, out.data(), out.size(), &written));
+    out.resize(written);
+    return out;
+  }
+  static PolynomialBatch import_bytes(const Context& ctx, const std::vector<uint8_t>& bytes) {
+    p2b_batch* b = nullptr;
+    ctx.check(p2b_batch_import(ctx.get(), bytes.data(), bytes.size(), &b));
+    return PolynomialBatch(&ctx, b);
+  }
 
  private:
   PolynomialBatch(const Context* c, p2b_batch* b) : ctx_(c), b_(b) {}
@@ -268,6 +288,7 @@ inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, cons
                             const std::vector<F>& public_inputs, const p2b_fri_params& params) {
   std::vector<F> out(p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size()));
   if (out.empty()) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
+  if (wire_cols.size() != circuit.desc().num_wires) throw Error(P2B_ERR_INVALID, "witness column count does not match the circuit");
   ctx.check(p2b_prove(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), wire_cols.data(), public_inputs.data(),
                       public_inputs.size(), &params, out.data(), out.size()));
   return out;
@@ -276,11 +297,39 @@ inline std::vector<F> prove(const Context& ctx, const CircuitData& circuit, cons
                             const HashOut& circuit_digest, const std::vector<std::vector<F>>& wire_values,
                             const std::vector<F>& public_inputs, const p2b_fri_params& params) {
   std::vector<const F*> cols;
-  for (auto& c : wire_values) cols.push_back(c.data());
+  if (wire_values.size() != circuit.desc().num_wires) throw Error(P2B_ERR_INVALID, "witness column count does not match the circuit");
+  for (auto& c : wire_values) {
+    if (c.size() != (size_t(1) << circuit.desc().degree_bits)) throw Error(P2B_ERR_INVALID, "witness column length does not match the circuit");
+    cols.push_back(c.data());
+  }
   std::vector<F> out(p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size()));
   if (out.empty()) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
   ctx.check(p2b_prove(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), cols.data(), public_inputs.data(),
                       public_inputs.size(), &params, out.data(), out.size()));
+  return out;
+}
+
+// The asynchronous form (p2b_prove_submit / poll / collect): submit returns once the proof is enqueued and the witness
+// has been read, so ONE host thread can keep several contexts busy, or generate the next witness meanwhile (the
+// reference does witness generation, then a blocking prove: city_rollup_circuit/src/worker/traits.rs:143-160).
+inline size_t prove_submit(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
+                           const HashOut& circuit_digest, const std::vector<const F*>& wire_cols,
+                           const std::vector<F>& public_inputs, const p2b_fri_params& params) {
+  const size_t len = p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size());
+  if (!len) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
+  if (wire_cols.size() != circuit.desc().num_wires) throw Error(P2B_ERR_INVALID, "witness column count does not match the circuit");
+  ctx.check(p2b_prove_submit(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), wire_cols.data(),
+                             public_inputs.data(), public_inputs.size(), &params));
+  return len;
+}
+inline bool prove_poll(const Context& ctx) {
+  const int rc = p2b_prove_poll(ctx.get());
+  if (rc < 0) ctx.check(rc);
+  return rc == 1;
+}
+inline std::vector<F> prove_collect(const Context& ctx, size_t len) {
+  std::vector<F> out(len);
+  ctx.check(p2b_prove_collect(ctx.get(), out.data(), out.size()));
   return out;
 }
 

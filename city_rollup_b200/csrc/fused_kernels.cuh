@@ -12,7 +12,7 @@
 //   k_eval_polys_multi  OpeningSet::new: every opened polynomial in one launch (was one per field of the set)
 //   k_query_all         fri_prover_query_rounds: every leaf row and Merkle path of every query in one launch
 //   k_reduce_polys2 / k_divide_by_linear2 / k_final_poly_combine   PolynomialBatch::prove_openings' final polynomial
-//   k_leaf_hash_planes_coop   FRI layer leaves hashed straight from the two value planes
+//   k_leaf_hash_planes[_coop] FRI layer leaves hashed straight from the two value planes (one thread / one warp per leaf)
 // Every result is bit-identical to the unfused kernels (same field operations on the same operands).
 #pragma once
 #include "fri_kernels.cuh"
@@ -27,11 +27,17 @@ using gl::ext2;
 // levels: the tree's digest array, leaf level first (hash_kernels.cuh); level `first` (n_first = 2^log_first digests)
 // is already there.  Grid = max(1, n_first >> 9) CTAs of 256 threads; L_rem = number of levels still to build
 // above level `first` (down to the cap).  CTA b climbs the subtree over digests [b * 512, (b + 1) * 512) of level
-// `first` in shared memory: one thread per node while a level has >= 32 nodes in the CTA (a full-throughput
-// permutation per thread), one warp per node below that (the warp-cooperative permutation: ~1/3 of the latency).
-// The CTA that finishes last (device-scope counter, reset before it leaves so that the launch can be replayed from a
-// CUDA graph) climbs what is left above the subtree roots the same way.
+// `first` in shared memory: one thread per node while a level has more than COOP_NODES nodes in the CTA (a
+// full-throughput permutation per thread), one warp per node for the last few (the warp-cooperative permutation: ~1/3
+// of the latency).  The CTA that finishes last (device-scope counter, reset before it leaves so that the launch can be
+// replayed from a CUDA graph) climbs what is left above the subtree roots the same way.
 constexpr int SUB_LOG = 9;
+// Levels with at most this many nodes in a CTA go to one warp per node.  A warp-cooperative permutation finishes in a
+// third of the time of a one-thread permutation but executes ~10x the instructions (5.5k warp instructions against
+// 16.5k thread instructions = 516 warp-instruction equivalents), and a worker GPU is throughput bound (8+ proofs in
+// flight): with 16 (every level below a full warp of nodes) the cooperative nodes were 2 % of a tree's nodes and 44 % of
+// k_tree_subtree's instructions.  4 keeps the last three levels of every subtree short.
+constexpr uint32_t COOP_NODES = 4;
 
 __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, uint32_t n_levels, uint64_t* __restrict__ levels,
                                               size_t n_leaves, uint32_t first_level, size_t node0) {
@@ -43,7 +49,7 @@ __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, 
     const uint32_t n_par = cur >> 1;
     base >>= 1;
     uint64_t* out = levels + 4 * (2 * n_leaves - 2 * (n_leaves >> (first_level + l + 1)));
-    if (n_par >= 32) {
+    if (n_par > COOP_NODES) {
       uint64_t o[4];
       const bool act = tid < n_par;
       if (act) poseidon::two_to_one(sm[2 * tid], sm[2 * tid + 1], o);
@@ -55,7 +61,7 @@ __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, 
       }
       __syncthreads();
     } else {
-      // warp-cooperative: node w, w + n_warps, ...  (n_par <= 16)
+      // warp-cooperative: node w, w + n_warps, ...  (n_par <= COOP_NODES <= n_warps: one node per warp)
       uint64_t res[2];
       uint32_t cnt = 0;
       for (uint32_t node = warp; node < n_par; node += n_warps) {
@@ -160,6 +166,42 @@ k_leaf_hash_planes_coop(const uint64_t* __restrict__ c0, const uint64_t* __restr
     s = gl::canon(s);
   }
   if (active && l < 4) digests[4 * g + l] = s;
+}
+
+// The same with one thread per leaf (the full-throughput permutation): layers with thousands of leaves.
+__global__ void __launch_bounds__(256)
+k_leaf_hash_planes(const uint64_t* __restrict__ c0, const uint64_t* __restrict__ c1, uint32_t arity_bits, size_t n_leaves,
+                   uint64_t* __restrict__ leaves_rm, uint64_t* __restrict__ digests) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_leaves) return;
+  const uint32_t arity = 1u << arity_bits, leaf_len = 2 * arity;
+  const uint64_t* p0 = c0 + (g << arity_bits);
+  const uint64_t* p1 = c1 + (g << arity_bits);
+  ulonglong2* row = reinterpret_cast<ulonglong2*>(leaves_rm + g * leaf_len);
+  uint64_t out[4];
+  if (leaf_len <= 4) {  // arity 2: hash_or_noop copies
+    const uint64_t a = gl::canon(p0[0]), b = gl::canon(p1[0]), c = gl::canon(p0[1]), d = gl::canon(p1[1]);
+    row[0] = make_ulonglong2(a, b);
+    row[1] = make_ulonglong2(c, d);
+    out[0] = a, out[1] = b, out[2] = c, out[3] = d;
+  } else {
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (uint32_t e0 = 0; e0 < arity; e0 += 4) {  // 4 extension elements = 8 words per permutation
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint64_t a = gl::canon(p0[e0 + k]), b = gl::canon(p1[e0 + k]);
+        row[e0 + k] = make_ulonglong2(a, b);
+        s[2 * k] = a;
+        s[2 * k + 1] = b;
+      }
+      poseidon::permute_nc(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+  }
+  hashk::store_digest(digests + 4 * g, out);
 }
 
 // ------------------------------------------------------------------------------------------------ transcript

@@ -176,6 +176,9 @@ struct p2b_circuit {
   uint64_t* d_k_is = nullptr;
   uint64_t* d_zh = nullptr;  // ZeroPolyOnCoset: Z_H on the 2^mdb cosets of the quotient LDE, then the inverses
   uint32_t mdb = 0;          // log2(quotient_degree_factor)
+  std::vector<uint32_t> gate_kinds;  // host copy of gates[g].kind
+  uint32_t* d_gate_list = nullptr;  // gate indices: the light gates, then the heavy ones (plonk::k_quotient_gates)
+  uint32_t n_light = 0, n_heavy = 0;
 };
 
 struct p2b_challenger {
@@ -1556,6 +1559,24 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
     }
   }
   if (rc == P2B_OK) rc = dmalloc(ctx, &c->d_zh, zh.size());
+  for (uint32_t g = 0; g < d.n_gates; g++) c->gate_kinds.push_back(d.gates[g].kind);
+  std::vector<uint32_t> gate_list;
+  for (int heavy = 0; heavy < 2; heavy++)
+    for (uint32_t g = 0; g < d.n_gates; g++) {
+      const uint32_t k = d.gates[g].kind;
+      const bool h = k == plonk::GATE_POSEIDON || k == plonk::GATE_POSEIDON_MDS || k == plonk::GATE_RANDOM_ACCESS ||
+                     k == plonk::GATE_COSET_INTERPOLATION;
+      if (k == plonk::GATE_NOOP) continue;  // no constraints: its part stays zero (k_quotient_combine skips it)
+      if (h == (heavy == 1)) {
+        gate_list.push_back(g);
+        (heavy ? c->n_heavy : c->n_light)++;
+      }
+    }
+  if (rc == P2B_OK) rc = dmalloc(ctx, (uint64_t**)&c->d_gate_list, (gate_list.size() + 2) / 2);
+  if (rc == P2B_OK && !gate_list.empty()) {
+    cudaError_t e = cudaMemcpyAsync(c->d_gate_list, gate_list.data(), gate_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, P2B_ERR_CUDA, "circuit upload: %s", cudaGetErrorString(e));
+  }
   if (rc == P2B_OK) {
     // pageable sources: the copies are complete (staged) when cudaMemcpyAsync returns
     cudaError_t e = cudaMemcpyAsync(c->d_gates, d.gates, d.n_gates * sizeof(p2b_gate), cudaMemcpyHostToDevice, ctx->stream);
@@ -1581,6 +1602,7 @@ extern "C" void p2b_circuit_free(p2b_circuit* c) {
   dfree(c->ctx, c->d_gates);
   dfree(c->ctx, c->d_k_is);
   dfree(c->ctx, c->d_zh);
+  dfree(c->ctx, c->d_gate_list);
   delete c;
 }
 
@@ -1695,6 +1717,7 @@ extern "C" int p2b_zs_partial_products_commit(p2b_ctx* ctx, const p2b_circuit* c
   return rc;
 }
 
+static bool d_gate_kinds_noop(const p2b_circuit* c, uint32_t g) { return c->gate_kinds[g] == plonk::GATE_NOOP; }
 static uint32_t quotient_n_terms(const p2b_circuit_desc& d) {
   return d.num_challenges * (d.num_partial_products + 2) + d.num_gate_constraints;
 }
@@ -1755,8 +1778,20 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.n_gates = d.n_gates;
     qp.n_terms = n_terms;
     qp.roots = ctx->roots();
-    plonk::k_quotient<<<dim3(cdiv(lde_size, 128), n_parts), 128, 0, ctx->stream>>>(qp);
+    // Noop gates have no constraints and no launch: their parts must read as zero
+    for (uint32_t g = 0; g < d.n_gates; g++)
+      if (d_gate_kinds_noop(c, g))
+        CU(ctx, cudaMemsetAsync(d_parts + (size_t)(1 + g) * nch * lde_size, 0, (size_t)nch * lde_size * sizeof(uint64_t), ctx->stream));
+    plonk::k_quotient_perm<<<dim3(cdiv(lde_size, 128), 1), 128, 0, ctx->stream>>>(qp);
     LAUNCH_CHECK(ctx);
+    if (c->n_light) {
+      plonk::k_quotient_gates<false><<<dim3(cdiv(lde_size, 128), c->n_light), 128, 0, ctx->stream>>>(qp, c->d_gate_list);
+      LAUNCH_CHECK(ctx);
+    }
+    if (c->n_heavy) {
+      plonk::k_quotient_gates<true><<<dim3(cdiv(lde_size, 128), c->n_heavy), 128, 0, ctx->stream>>>(qp, c->d_gate_list + c->n_light);
+      LAUNCH_CHECK(ctx);
+    }
     plonk::k_quotient_combine<<<dim3(cdiv(lde_size, 256), nch), 256, 0, ctx->stream>>>(d_parts, n_parts, nch, log_lde, mdb,
                                                                                        c->d_zh, d_q);
     LAUNCH_CHECK(ctx);
@@ -2188,10 +2223,11 @@ static int fri_commit_core(p2b_ctx* ctx, const uint64_t* d_coef, const uint64_t*
     } else {
       // planes in leaf order: the caller's LDE (layer 0) or the coset NTT of the folded coefficients
       const uint64_t* pl = l == 0 ? d_vals_leaf : d_planes;
-      if (n_leaves > COOP_MAX_NODES) {
-        frik::k_interleave<<<cdiv(cur, 256), 256, 0, ctx->stream>>>(pl, pl + cur, cur, t->d_leaves_rm);
-        LAUNCHF();
-        hashk::k_leaf_hash_rowmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(t->d_leaves_rm, leaf_len, n_leaves, t->d_levels);
+      // one thread per leaf for layers of >= 1024 leaves (arity >= 4: whole permutations of 4 extension elements), one
+      // warp per leaf below that: the cooperative permutation costs ~10x the instructions and only pays where a handful
+      // of leaves would otherwise leave the GPU waiting on one 23 us permutation chain
+      if (n_leaves >= 1024) {
+        fusedk::k_leaf_hash_planes<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(pl, pl + cur, ab, n_leaves, t->d_leaves_rm, t->d_levels);
         LAUNCHF();
       } else {
         fusedk::k_leaf_hash_planes_coop<<<cdiv(n_leaves * 32, 256), 256, 0, ctx->stream>>>(pl, pl + cur, ab, n_leaves, t->d_leaves_rm,
@@ -2312,9 +2348,12 @@ static int fri_pow_dev(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint
   unsigned long long* d_best = (unsigned long long*)(ctx->d_scratch + 1);
   // the minimal witness is geometric with mean 2^pow_bits.  Grid: about half the mean per stride, between one and
   // three CTAs per SM.
+  // Every thread of a stride evaluates its candidate even when the witness sits at the start of the stride, so a
+  // stride is wasted work on average half over: a quarter of the mean per stride (64 CTAs at 16 bits: ~5 strides of
+  // 23 us, ~1.15x the necessary permutations; 148 CTAs did ~2x), between 32 CTAs and one CTA per SM.
   const uint64_t sms = (uint64_t)ctx->sm_count;
-  uint64_t blocks = (((uint64_t)1 << pow_bits) / 2 + 255) / 256;
-  blocks = blocks < sms ? sms : blocks > 3 * sms ? 3 * sms : blocks;
+  uint64_t blocks = (((uint64_t)1 << pow_bits) / 4 + 255) / 256;
+  blocks = blocks < 32 ? 32 : blocks > sms ? sms : blocks;
   CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
   frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, 0, GL_P, pow_bits, d_best);
   LAUNCH_CHECK(ctx);

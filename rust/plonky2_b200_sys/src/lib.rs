@@ -117,6 +117,22 @@ extern "C" {
         circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
         params: *const p2b_fri_params, proof_out: *mut u64, proof_cap: usize) -> c_int;
 
+    pub fn p2b_prove_dev(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        circuit_digest: *const u64, d_wire_values: *const u64, public_inputs: *const u64, n_public_inputs: usize,
+        params: *const p2b_fri_params, proof_out: *mut u64, proof_cap: usize) -> c_int;
+    pub fn p2b_prove_submit(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
+        params: *const p2b_fri_params) -> c_int;
+    pub fn p2b_prove_poll(ctx: *mut p2b_ctx) -> c_int;
+    pub fn p2b_prove_collect(ctx: *mut p2b_ctx, proof_out: *mut u64, proof_cap: usize) -> c_int;
+    pub fn p2b_plan_info(ctx: *mut p2b_ctx, n_ready: *mut u32, n_seen: *mut u32, n_failed: *mut u32, kernels_per_launch: *mut u32) -> c_int;
+    pub fn p2b_batch_attach(ctx: *mut p2b_ctx, src: *const p2b_batch, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_export_len(b: *const p2b_batch) -> usize;
+    pub fn p2b_batch_export(b: *mut p2b_batch, out: *mut u8, out_cap: usize, written: *mut usize) -> c_int;
+    pub fn p2b_batch_import(ctx: *mut p2b_ctx, bytes: *const u8, n_bytes: usize, out: *mut *mut p2b_batch) -> c_int;
+    pub fn p2b_batch_lde_col(b: *mut p2b_batch, col: usize, out: *mut u64) -> c_int;
+    pub fn p2b_timer_span_ms(first: *mut p2b_ctx, last: *mut p2b_ctx, ms: *mut f32) -> c_int;
+
     pub fn p2b_proof_words(shape: *const p2b_proof_shape, params: *const p2b_fri_params) -> usize;
     pub fn p2b_proof_bincode_len(shape: *const p2b_proof_shape, params: *const p2b_fri_params) -> usize;
     pub fn p2b_proof_to_bincode(shape: *const p2b_proof_shape, params: *const p2b_fri_params, words: *const u64,
@@ -158,8 +174,9 @@ impl std::fmt::Display for P2bError {
 }
 impl std::error::Error for P2bError {}
 
-/// One context per worker thread (a p2b_ctx is not thread-safe).
-pub struct Context(pub *mut p2b_ctx);
+/// One context per worker thread (a p2b_ctx is not thread-safe).  `Batch` and `Circuit` borrow their context
+/// (`&'ctx Context`), so the borrow checker enforces the header's rule that no handle outlives its context.
+pub struct Context(*mut p2b_ctx);
 unsafe impl Send for Context {}
 impl Context {
     pub fn new(device: i32) -> Result<Self, P2bError> {
@@ -168,9 +185,11 @@ impl Context {
         if rc != 0 { return Err(P2bError { code: rc, message: last_error(std::ptr::null()) }); }
         Ok(Context(h))
     }
+    pub fn raw(&self) -> *mut p2b_ctx { self.0 }
     pub fn check(&self, rc: c_int) -> Result<(), P2bError> {
         if rc == 0 { Ok(()) } else { Err(P2bError { code: rc, message: last_error(self.0) }) }
     }
+    fn invalid(msg: impl Into<String>) -> P2bError { P2bError { code: -1, message: msg.into() } }
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { p2b_destroy(self.0) } } }
 
@@ -178,40 +197,136 @@ pub fn last_error(ctx: *const p2b_ctx) -> String {
     unsafe { CStr::from_ptr(p2b_last_error(ctx)).to_string_lossy().into_owned() }
 }
 
-/// Owning handle of a device-resident PolynomialBatch.
-pub struct Batch(pub *mut p2b_batch);
-unsafe impl Send for Batch {}
-impl Drop for Batch { fn drop(&mut self) { unsafe { p2b_batch_free(self.0) } } }
-
-/// `PolynomialBatch::from_values` for `F = GoldilocksField` (a transparent u64): one pointer per column.
-pub fn batch_from_values(ctx: &Context, cols: &[&[u64]], rate_bits: usize, cap_height: usize) -> Result<Batch, P2bError> {
+/// Columns of one power-of-two length: the checks every column-taking wrapper needs before it hands raw pointers to C.
+fn column_ptrs(cols: &[&[u64]], expect_cols: Option<usize>, expect_len: Option<usize>) -> Result<(Vec<*const u64>, u32), P2bError> {
+    if cols.is_empty() { return Err(Context::invalid("no columns")); }
+    if let Some(k) = expect_cols {
+        if cols.len() != k { return Err(Context::invalid(format!("{} columns given, the circuit has {}", cols.len(), k))); }
+    }
     let n = cols[0].len();
-    assert!(n.is_power_of_two() && cols.iter().all(|c| c.len() == n));
-    let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
-    let mut h = std::ptr::null_mut();
-    ctx.check(unsafe {
-        p2b_batch_from_values(ctx.0, ptrs.as_ptr(), ptrs.len(), n.trailing_zeros(), rate_bits as u32, cap_height as u32, 0, &mut h)
-    })?;
-    Ok(Batch(h))
+    if n == 0 || !n.is_power_of_two() { return Err(Context::invalid("column length must be a power of two")); }
+    if let Some(l) = expect_len {
+        if n != l { return Err(Context::invalid(format!("columns of {} values given, the circuit has 2^{} rows", n, l.trailing_zeros()))); }
+    }
+    if cols.iter().any(|c| c.len() != n) { return Err(Context::invalid("columns of different lengths")); }
+    Ok((cols.iter().map(|c| c.as_ptr()).collect(), n.trailing_zeros()))
 }
 
+/// Owning handle of a device-resident PolynomialBatch.
+pub struct Batch<'ctx> { h: *mut p2b_batch, ctx: &'ctx Context, n_cols: usize, log_n: u32 }
+unsafe impl<'ctx> Send for Batch<'ctx> {}
+impl<'ctx> Drop for Batch<'ctx> { fn drop(&mut self) { unsafe { p2b_batch_free(self.h) } } }
+impl<'ctx> Batch<'ctx> {
+    pub fn raw(&self) -> *mut p2b_batch { self.h }
+    pub fn n_cols(&self) -> usize { self.n_cols }
+    pub fn degree_log(&self) -> u32 { self.log_n }
+    fn wrap(ctx: &'ctx Context, h: *mut p2b_batch) -> Self {
+        let (n_cols, log_n) = unsafe { (p2b_batch_n_cols(h), p2b_batch_degree_log(h)) };
+        Batch { h, ctx, n_cols, log_n }
+    }
+    /// `PolynomialBatch::from_values` for `F = GoldilocksField` (a transparent u64): one pointer per column.
+    /// `keep_values` keeps the values on H in HBM (needed for `prover_data.constants_sigmas_commitment` and the wires).
+    pub fn from_values(ctx: &'ctx Context, cols: &[&[u64]], rate_bits: usize, cap_height: usize, keep_values: bool) -> Result<Self, P2bError> {
+        let (ptrs, log_n) = column_ptrs(cols, None, None)?;
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe {
+            p2b_batch_from_values(ctx.0, ptrs.as_ptr(), ptrs.len(), log_n, rate_bits as u32, cap_height as u32,
+                                  if keep_values { P2B_KEEP_VALUES } else { 0 }, &mut h)
+        })?;
+        Ok(Self::wrap(ctx, h))
+    }
+    /// A read-only view of this batch for another context of the same device: the worker threads of a GPU share one
+    /// device copy of a circuit's constants|sigmas batch.  The view cannot outlive `self` ('src: 'ctx2 is enforced).
+    pub fn attach<'c2>(&'c2 self, ctx: &'c2 Context) -> Result<Batch<'c2>, P2bError> {
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { p2b_batch_attach(ctx.0, self.h, &mut h) })?;
+        Ok(Batch::wrap(ctx, h))
+    }
+    /// Bytes a later process re-imports instead of re-running `CircuitBuilder::build`'s commitment.
+    pub fn export(&self) -> Result<Vec<u8>, P2bError> {
+        let cap = unsafe { p2b_batch_export_len(self.h) };
+        let mut out = vec![0u8; cap];
+        let mut written = 0usize;
+        self.ctx.check(unsafe { p2b_batch_export(self.h, out.as_mut_ptr(), cap, &mut written) })?;
+        out.truncate(written);
+        Ok(out)
+    }
+    pub fn import(ctx: &'ctx Context, bytes: &[u8]) -> Result<Self, P2bError> {
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { p2b_batch_import(ctx.0, bytes.as_ptr(), bytes.len(), &mut h) })?;
+        Ok(Self::wrap(ctx, h))
+    }
+}
 
 /// Owning handle of the uploaded circuit description (built once per `CircuitData`, next to
-/// `prover_only.constants_sigmas_commitment`).
-pub struct Circuit(pub *mut p2b_circuit);
-unsafe impl Send for Circuit {}
-impl Drop for Circuit { fn drop(&mut self) { unsafe { p2b_circuit_free(self.0) } } }
+/// `prover_only.constants_sigmas_commitment`).  Remembers the witness shape so that `prove` can validate it.
+pub struct Circuit<'ctx> { h: *mut p2b_circuit, ctx: &'ctx Context, num_wires: usize, degree_bits: u32 }
+unsafe impl<'ctx> Send for Circuit<'ctx> {}
+impl<'ctx> Drop for Circuit<'ctx> { fn drop(&mut self) { unsafe { p2b_circuit_free(self.h) } } }
+impl<'ctx> Circuit<'ctx> {
+    /// `gates` / `k_is` are the slices `desc` would point to; the pointers inside the C struct are filled in here.
+    pub fn new(ctx: &'ctx Context, mut desc: p2b_circuit_desc, gates: &[p2b_gate], k_is: &[u64]) -> Result<Self, P2bError> {
+        if k_is.len() != desc.num_routed_wires as usize { return Err(Context::invalid("k_is must have num_routed_wires entries")); }
+        desc.n_gates = gates.len() as u32;
+        desc.gates = gates.as_ptr();
+        desc.k_is = k_is.as_ptr();
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { p2b_circuit_new(ctx.0, &desc, &mut h) })?;
+        Ok(Circuit { h, ctx, num_wires: desc.num_wires as usize, degree_bits: desc.degree_bits })
+    }
+    pub fn raw(&self) -> *mut p2b_circuit { self.h }
+}
+
+fn same_ctx(ctx: &Context, circuit: &Circuit, cs: &Batch) -> Result<(), P2bError> {
+    if !std::ptr::eq(circuit.ctx, ctx) || !std::ptr::eq(cs.ctx, ctx) { return Err(Context::invalid("handle of another context")); }
+    Ok(())
+}
 
 /// `prove_with_partition_witness` after witness generation: the flat proof words in `ProofWithPublicInputs`
 /// field order (see include/p2b.h); the patched plonky2 re-wraps them into `ProofWithPublicInputs<F, C, 2>`.
+/// The witness shape is checked against the circuit here: the C side reads `num_wires` pointers of 2^degree_bits words.
 pub fn prove(ctx: &Context, circuit: &Circuit, constants_sigmas: &Batch, circuit_digest: &[u64; 4],
              wire_values: &[&[u64]], public_inputs: &[u64], params: &p2b_fri_params) -> Result<Vec<u64>, P2bError> {
-    let ptrs: Vec<*const u64> = wire_values.iter().map(|c| c.as_ptr()).collect();
-    let len = unsafe { p2b_proof_len(circuit.0, constants_sigmas.0, params, public_inputs.len()) };
+    same_ctx(ctx, circuit, constants_sigmas)?;
+    let (ptrs, _) = column_ptrs(wire_values, Some(circuit.num_wires), Some(1usize << circuit.degree_bits))?;
+    let len = unsafe { p2b_proof_len(circuit.h, constants_sigmas.h, params, public_inputs.len()) };
+    if len == 0 { return Err(Context::invalid("inconsistent FRI parameters")); }
     let mut out = vec![0u64; len];
     ctx.check(unsafe {
-        p2b_prove(ctx.0, circuit.0, constants_sigmas.0, circuit_digest.as_ptr(), ptrs.as_ptr(), public_inputs.as_ptr(),
+        p2b_prove(ctx.0, circuit.h, constants_sigmas.h, circuit_digest.as_ptr(), ptrs.as_ptr(), public_inputs.as_ptr(),
                   public_inputs.len(), params, out.as_mut_ptr(), len)
     })?;
     Ok(out)
+}
+
+/// A proof in flight on a context (`p2b_prove_submit`): the witness buffers are free again as soon as `submit`
+/// returns, so the worker thread generates the next witness while the GPU proves this one
+/// (city_rollup_circuit/src/worker/traits.rs:143-160 is witness generation followed by a blocking prove).
+/// One proof may be pending per context: a second `prove_submit` before `collect` fails with P2B_ERR_INVALID.
+pub struct PendingProof<'a> { ctx: &'a Context, len: usize }
+pub fn prove_submit<'a>(ctx: &'a Context, circuit: &Circuit, constants_sigmas: &Batch, circuit_digest: &[u64; 4],
+                        wire_values: &[&[u64]], public_inputs: &[u64], params: &p2b_fri_params) -> Result<PendingProof<'a>, P2bError> {
+    same_ctx(ctx, circuit, constants_sigmas)?;
+    let (ptrs, _) = column_ptrs(wire_values, Some(circuit.num_wires), Some(1usize << circuit.degree_bits))?;
+    let len = unsafe { p2b_proof_len(circuit.h, constants_sigmas.h, params, public_inputs.len()) };
+    if len == 0 { return Err(Context::invalid("inconsistent FRI parameters")); }
+    let rc = unsafe {
+        p2b_prove_submit(ctx.0, circuit.h, constants_sigmas.h, circuit_digest.as_ptr(), ptrs.as_ptr(), public_inputs.as_ptr(),
+                         public_inputs.len(), params)
+    };
+    ctx.check(rc)?;
+    Ok(PendingProof { ctx, len })
+}
+impl<'a> PendingProof<'a> {
+    pub fn is_finished(&self) -> Result<bool, P2bError> {
+        let rc = unsafe { p2b_prove_poll(self.ctx.0) };
+        if rc < 0 { self.ctx.check(rc)?; }
+        Ok(rc == 1)
+    }
+    pub fn collect(self) -> Result<Vec<u64>, P2bError> {
+        let mut out = vec![0u64; self.len];
+        let rc = unsafe { p2b_prove_collect(self.ctx.0, out.as_mut_ptr(), self.len) };
+        self.ctx.check(rc)?;
+        Ok(out)
+    }
 }

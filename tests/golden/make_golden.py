@@ -12,6 +12,8 @@ Plonky2 hot path:
          -> example_proofs.bin (concatenated proof blobs) + example_proofs.json (index)
   K4/K5  city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145
          -> circuit_params.json (FRI/Plonk parameters + the 80 k_is)
+  DAG    qbench_data/example.bin's job ids, level counters, goals and next-job lists
+         -> example_dag.bin (the dump with witness / proof payloads stripped; read by tools/qbench_replay.cpp)
 
 Usage:  python tests/golden/make_golden.py [/root/reference]
 """
@@ -61,6 +63,34 @@ def example_proofs():
     return b"".join(blobs), {"proofs": index, "source": "qbench_data/example.bin"}
 
 
+def example_dag():
+    """The job DAG of the dumped block, in the dump's own container format (bincode BlockProofStoreDump,
+    city_rollup_core_worker_qbench/src/dump.rs:16-27: DumpProofStoreConfig, then SimpleProofStoreMemory {proofs, counters}):
+    every key of the store is kept; the payload is kept only for the Counter entries (value / goal / next-jobs list,
+    city_rollup_common/src/qworker/proof_store.rs:60-89) and stripped (length 0) for witnesses and proofs, which the
+    native replay does not read.  1.4 MB -> a few KB."""
+    d = open(os.path.join(REF, "qbench_data/example.bin"), "rb").read()
+    off = 8 + 4 + 48
+    out = bytearray(d[:off])
+    (n,) = struct.unpack_from("<Q", d, off)
+    off += 8
+    out += struct.pack("<Q", n)
+    kept = 0
+    for _ in range(n):
+        kid = d[off : off + 24]
+        off += 24
+        (l,) = struct.unpack_from("<Q", d, off)
+        off += 8
+        payload = d[off : off + l] if kid[22] == 16 else b""  # ProvingJobDataType::Counter = 16
+        kept += 1 if payload else 0
+        out += kid + struct.pack("<Q", len(payload)) + payload
+        off += l
+    (nc,) = struct.unpack_from("<Q", d, off)
+    assert nc == 0 and off + 8 == len(d)
+    out += struct.pack("<Q", 0)
+    return bytes(out), kept
+
+
 def circuit_params():
     src = open(os.path.join(REF, "city_common_circuit/src/circuits/zk_signature2/mod.rs")).read()
     body = src[src.index("pub fn get_verifier_template_zk_signature") :]
@@ -101,4 +131,7 @@ if __name__ == "__main__":
     open(os.path.join(OUT, "example_proofs.bin"), "wb").write(blob)
     json.dump(idx, open(os.path.join(OUT, "example_proofs.json"), "w"), indent=1)
     json.dump(circuit_params(), open(os.path.join(OUT, "circuit_params.json"), "w"), indent=1)
+    dag, kept = example_dag()
+    open(os.path.join(OUT, "example_dag.bin"), "wb").write(dag)
+    print("example_dag.bin:", len(dag), "bytes,", kept, "counter entries kept")
     print("golden fixtures written to", OUT)

@@ -338,32 +338,45 @@ def test_gpu_proof_2p14_rows_verifies(ctx, m):
 
 
 def test_qbench_replay_native_job_loop(ctx, m, tmp_path):
-    """tools/qbench_replay.cpp: the reference's level-counter job DAG (43 jobs / 67 proofs of a block shaped like
-    qbench_data/example.bin) through the C++ mirror on worker threads; every proof must equal the expected words, every
-    job must leave its bincode proof in the store, and the benchmark file must have the reference's
+    """tools/qbench_replay.cpp: the job DAG READ FROM the dumped block (tests/golden/example_dag.bin = the counters, goals
+    and next-job lists of qbench_data/example.bin: 43 plonky2 jobs / 67 proofs, 3 Groth16 jobs skipped, 13 AggregateJobs
+    joins) through the C++ mirror, (a) on worker threads with blocking p2b_prove and (b) with ONE host thread driving four
+    contexts through p2b_prove_submit / collect.  Every proof must equal the words the CPU ORACLE computes for the case,
+    every job must leave its bincode proof in the store, and the benchmark file must have the reference's
     QWorkerJobBenchmark format (city_rollup_common/src/qworker/job_id.rs:194-202)."""
     import json
     import shutil
     import subprocess
     import sys
 
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import prove_bench as PB
+
     if not shutil.which("g++"):
         pytest.skip("no g++")
+    circ, digest, pis = PB.build_case(10)
+    expected, _ = V.oracle_prove_c(circ, digest, pis, FP_CITY)
+    np.save(tmp_path / "expected.npy", expected)
     case = tmp_path / "case.bin"
-    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_prove_case.py"), str(case), "10"])
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_prove_case.py"), str(case), "10", str(tmp_path / "expected.npy")])
     exe = tmp_path / "qbench_replay"
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", ROOT, os.path.join(ROOT, "tools", "qbench_replay.cpp"), "-L",
                            os.path.dirname(m.SO_PATH), "-lp2b", "-lpthread", "-o", str(exe)])
-    out = tmp_path / "bench.json"
+    dag = os.path.join(ROOT, "tests", "golden", "example_dag.bin")
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(m.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    res = subprocess.run([str(exe), "-i", str(case), "-o", str(out), "-n", "2", "--contexts", "3"], env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stderr + res.stdout
-    summary = json.loads(res.stdout.strip().splitlines()[-1])
-    assert summary["jobs"] == summary["jobs_recorded"] == summary["stored_proofs"] == 2 * 43
-    assert summary["proofs"] == 2 * 67 and summary["mismatching_proofs"] == 0
-    bench = json.load(open(out))
-    assert len(bench) == 2 * 43
-    ids = {b["job_id"] for b in bench}
-    assert len(ids) == 2 * 43 and all(len(i) == 48 and i.startswith("00") for i in ids)
-    assert all(isinstance(b["duration"], int) for b in bench)
+    for mode in (["--contexts", "3"], ["--async", "4"]):
+        out = tmp_path / "bench.json"
+        res = subprocess.run([str(exe), "-i", str(case), "-d", dag, "-o", str(out), "-n", "2"] + mode, env=env,
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr + res.stdout
+        summary = json.loads(res.stdout.strip().splitlines()[-1])
+        assert summary["proving_jobs"] == summary["jobs_recorded"] == summary["stored_proofs"] == 2 * 43
+        assert summary["jobs"] == 2 * 60  # + 3 Groth16 (skipped) + 13 AggregateJobs + NotifyOrchestratorComplete per block
+        assert summary["proofs"] == 2 * 67 and summary["mismatching_proofs"] == 0
+        if mode[0] == "--async":
+            assert summary["host_threads"] == 1 and summary["contexts_per_gpu"] == 4
+        bench = json.load(open(out))
+        assert len(bench) == 2 * 43
+        ids = {b["job_id"] for b in bench}
+        assert len(ids) == 2 * 43 and all(len(i) == 48 and i.startswith("00") for i in ids)
+        assert all(isinstance(b["duration"], int) for b in bench)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Writes the case file tools/prove_bench.cpp reads: the synthetic City-shaped circuit of tools/prove_bench.py
 (description, constants|sigmas values, witness columns, FRI parameters) and the proof words p2b_prove returns
-for it (computed here on the GPU; tests/test_gpu_prove.py holds the same flow to the oracle-built proof)."""
+for it (computed here on the GPU, or — argv[3], what tests/test_gpu_prove.py does — taken from a .npy the caller
+produced with the CPU oracle)."""
 import os
 import sys
 
@@ -20,6 +21,10 @@ c = m.Context(0)
 cd = m.CircuitData(c, d)
 cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), 3, False, 4, keep_values=True)
 words = m.prove_native(c, cd, cs, digest, circ.wire_values(), pis, params, raw=True)
+# tests hand over the expected words computed by the CPU oracle instead (argv[3] = .npy): the replay then checks every
+# GPU proof against an oracle-built proof, not against another GPU proof
+if len(sys.argv) > 3:
+    words = np.load(sys.argv[3]).astype(np.uint64)
 u = lambda xs: np.array([int(x) for x in xs], dtype=np.uint64)
 hdr = [0x70326263617365, d["degree_bits"], d["num_wires"], d["num_routed_wires"], d["num_constants"], d["num_selectors"],
        d["num_challenges"], d["quotient_degree_factor"], d["num_partial_products"], d["num_gate_constraints"],
