@@ -35,12 +35,16 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.pa
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# more hardware work queues than the default 8: 16 worker streams (+ their copy streams) otherwise share queues and
+# serialise behind each other (measured: 16 workers 665 -> 724 proofs/s).  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np  # noqa: E402
 
 DEGREE_BITS, N_WIRES, RATE_BITS, CAP_HEIGHT = 12, 135, 3, 4
 FP = dict(rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, reduction_arity_bits=[4, 4])
-CONTEXTS = 8
-PROOFS_PER_STEP = 32
+CONTEXTS = 16         # worker threads (p2b contexts / CUDA streams) per GPU: 8 -> 704, 12 -> 744, 16 -> 751, 24 -> 766 proofs/s
+PROOFS_PER_STEP = 64  # 4 jobs per worker and step
 METRIC = "proofs/sec on qbench-shaped worker jobs (2^12 rows x 135 wires, City op-circuit gate set, 28 queries); LDE+Merkle ms at 2^20 rows x 135 cols beside it"
 UNIT = "proofs/s"
 WORKLOAD = ("City Rollup worker proof jobs: CircuitData::prove at 2^12 rows x 135 wires, 21 gate kinds (add_city_common_gates + "
@@ -60,7 +64,7 @@ def config_dict():
             "pow_bits": 16, "queries": 28, "arity_bits": [4, 4], "gate_set": "city (21 kinds, 6 selector groups)",
             "proofs_per_step": PROOFS_PER_STEP, "contexts_per_gpu": CONTEXTS,
             "sharding": "independent proof jobs per GPU, no data-path collective",
-            "l2": "8 proofs in flight x ~60 MB of LDE / coefficient / digest working set each > 126 MB L2; nothing is reused across proofs"}
+            "l2": "16 proofs in flight x ~60 MB of LDE / coefficient / digest working set each > 126 MB L2; nothing is reused across proofs"}
 
 
 def perms_per_proof(circ_desc):
@@ -216,8 +220,15 @@ def run_reference(args):
 class ProofFarm:
     """CONTEXTS worker threads of one GPU, each with its own p2b context / stream, proving the same job shape"""
 
-    def __init__(self, m, device, n_ctx, circ, digest, pis):
-        import torch
+    def __init__(self, m, device, n_ctx, circ, digest, pis, to_device=None):
+        """to_device(np.int64 matrix) -> (object kept alive, device pointer); default = a torch CUDA tensor"""
+        if to_device is None:
+            import torch
+
+            def to_device(a):
+                t = torch.from_numpy(a).cuda()
+                torch.cuda.synchronize()
+                return t, t.data_ptr()
 
         self.m, self.n_ctx, self.digest, self.pis = m, n_ctx, digest, pis
         self.params = m.FriParams(FP["rate_bits"], FP["cap_height"], FP["proof_of_work_bits"], FP["num_query_rounds"],
@@ -233,19 +244,18 @@ class ProofFarm:
             cd = m.CircuitData(c, circ.desc())
             cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), RATE_BITS, False, CAP_HEIGHT, keep_values=True)
             self.state.append((cd, cs))
-            self.dev.append(torch.from_numpy(stacked.view(np.int64)).cuda())
+            self.dev.append(to_device(stacked.view(np.int64)))
             w = c.pinned_empty(stacked.shape)
             w[:] = stacked
             self.pinned.append(w)
             self.pageable.append([col.copy() for col in wv])  # one allocation per column, as plonky2's witness
-        torch.cuda.synchronize()
         self.n_words = None
 
     def prove_one(self, i, mode):
         c = self.ctxs[i]
         cd, cs = self.state[i]
         if mode == "dev":
-            return self.m.prove_native_device(c, cd, cs, self.digest, self.dev[i].data_ptr(), self.pis, self.params)
+            return self.m.prove_native_device(c, cd, cs, self.digest, self.dev[i][1], self.pis, self.params)
         src = self.pinned[i] if mode == "pinned" else self.pageable[i]
         return self.m.prove_native(c, cd, cs, self.digest, src, self.pis, self.params, raw=True)
 
@@ -302,6 +312,46 @@ class ProofFarm:
             c.close()
 
 
+class RankGroup:
+    """the only collectives of the benchmark: the barrier before a timed region and the max / sum over ranks of its
+    result (one process per GPU; the proof path itself has no collective).  device = "cuda" under NCCL, "cpu" under gloo."""
+
+    def __init__(self, world, device, sync=None):
+        self.world, self.device, self.sync = world, device, sync
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        if self.sync:
+            self.sync()
+
+    def _reduce(self, x, op):
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, "MAX")
+
+    def sum(self, x):
+        return self._reduce(x, "SUM")
+
+
+def timed_job_run(farm, group, mode, per_ctx, warm):
+    """one timed region on every rank -> (whole-job proofs/s over all ranks, max-over-ranks device ms, launches of all
+    ranks, this rank's wall s, this rank's host cpu s)"""
+    farm.before_timed = group.barrier  # every rank's workers are warm before any rank starts its timed region
+    ms, launches, wall, cpu = farm.run(mode, per_ctx, warm)
+    group.barrier()
+    ms = group.max(ms)
+    total = group.world * farm.n_ctx * per_ctx
+    return total / (ms * 1e-3), ms, group.sum(launches), wall, cpu
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -320,22 +370,7 @@ def run_cuda(args):
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    group = RankGroup(world, "cuda", torch.cuda.synchronize)
 
     c0 = m.Context(local)
     circ, digest, pis = build_job(c0.hash_no_pad)
@@ -344,26 +379,17 @@ def run_cuda(args):
     per_ctx_step = max(1, PROOFS_PER_STEP // n_ctx)
     proofs_per_step = per_ctx_step * n_ctx
     farm = ProofFarm(m, local, n_ctx, circ, digest, pis)
-    farm.before_timed = barrier  # every rank's workers are warm before any rank starts its timed region
     warm = args.warmup * per_ctx_step  # W whole warm-up steps
+    total_proofs = world * proofs_per_step * args.steps
 
     # ---- value: witness resident in HBM
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, launches, wall_dev, cpu_dev = farm.run("dev", per_ctx_step * args.steps, warm)
-    barrier()
+    value, ms_dev, launches_all, wall_dev, cpu_dev = timed_job_run(farm, group, "dev", per_ctx_step * args.steps, warm)
     clocks = sampler.stop() if sampler else None
-    ms_dev = max_over_ranks(ms_dev)
-    total_proofs = world * proofs_per_step * args.steps
-    value = total_proofs / (ms_dev * 1e-3)
-    launches_all = sum_over_ranks(launches)
 
     # ---- e2e: host witness buffers through p2b_prove (pinned, then pageable per-column allocations)
-    ms_pin, _, wall_pin, cpu_pin = farm.run("pinned", per_ctx_step * args.steps, 2)
-    barrier()
-    ms_pin = max_over_ranks(ms_pin)
-    ms_pag, _, wall_pag, cpu_pag = farm.run("pageable", per_ctx_step * args.steps, 2)
-    barrier()
-    ms_pag = max_over_ranks(ms_pag)
+    _, ms_pin, _, wall_pin, cpu_pin = timed_job_run(farm, group, "pinned", per_ctx_step * args.steps, 2)
+    _, ms_pag, _, wall_pag, cpu_pag = timed_job_run(farm, group, "pageable", per_ctx_step * args.steps, 2)
     n_words = farm.n_words
     h2d = proofs_per_step * N_WIRES * (1 << DEGREE_BITS) * 8
     d2h = proofs_per_step * n_words * 8

@@ -1739,11 +1739,16 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   if (log_lde > 24) return fail(ctx, P2B_ERR_UNSUPPORTED, "quotient LDE of 2^%u points", log_lde);
   const size_t n = (size_t)1 << d.degree_bits, lde_size = (size_t)1 << log_lde;
   const uint32_t n_terms = nch * (npp + 2) + d.num_gate_constraints;
-  uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr, *d_parts = nullptr;
+  uint64_t *d_apow = nullptr, *d_q = nullptr, *d_coeffs = nullptr, *d_tmp = nullptr, *d_parts = nullptr, *d_apow_g = nullptr;
   const uint32_t n_parts = 1 + d.n_gates;
   if (!d_apow_ready && (rc = dmalloc(ctx, &d_apow, (size_t)nch * n_terms))) return rc;
+  if ((rc = dmalloc(ctx, &d_apow_g, (size_t)(d.num_gate_constraints + 1) * plonk::MAX_CHALLENGES))) {
+    dfree(ctx, d_apow);
+    return rc;
+  }
   if ((rc = dmalloc(ctx, &d_parts, (size_t)n_parts * nch * lde_size))) {
     dfree(ctx, d_apow);
+    dfree(ctx, d_apow_g);
     return rc;
   }
   if ((rc = dmalloc(ctx, &d_q, (size_t)nch * lde_size)) == P2B_OK) rc = dmalloc(ctx, &d_coeffs, (size_t)nch * lde_size);
@@ -1762,6 +1767,9 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.gates = c->d_gates;
     qp.k_is = c->d_k_is;
     qp.apow = d_apow_ready ? d_apow_ready : d_apow;
+    qp.apow_gates = d_apow_g;
+    plonk::k_interleave_apow<<<cdiv(d.num_gate_constraints, 256), 256, 0, ctx->stream>>>(qp.apow, n_terms, nch * (npp + 2), nch, d_apow_g);
+    ctx->launches++;
     qp.zh = c->d_zh;
     qp.parts = d_parts;
     qp.betas = d_betas;
@@ -1784,12 +1792,23 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
         CU(ctx, cudaMemsetAsync(d_parts + (size_t)(1 + g) * nch * lde_size, 0, (size_t)nch * lde_size * sizeof(uint64_t), ctx->stream));
     plonk::k_quotient_perm<<<dim3(cdiv(lde_size, 128), 1), 128, 0, ctx->stream>>>(qp);
     LAUNCH_CHECK(ctx);
+    // large circuits: point-major CTA order, so that the wires stream from HBM once per kernel (see k_quotient_gates)
+    static const int force_pm = [] {
+      const char* e = getenv("P2B_QUOT_POINT_MAJOR");
+      return e ? atoi(e) : -1;
+    }();
+    qp.point_major = force_pm >= 0 ? (uint32_t)force_pm : ((size_t)d.num_wires * qp.N * 8 > ((size_t)48 << 20) ? 1u : 0u);
+    const unsigned pblocks = cdiv(lde_size, 128);
     if (c->n_light) {
-      plonk::k_quotient_gates<false><<<dim3(cdiv(lde_size, 128), c->n_light), 128, 0, ctx->stream>>>(qp, c->d_gate_list);
+      qp.list_len = c->n_light;
+      const dim3 grid = qp.point_major ? dim3(pblocks * c->n_light, 1) : dim3(pblocks, c->n_light);
+      plonk::k_quotient_gates<false><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list);
       LAUNCH_CHECK(ctx);
     }
     if (c->n_heavy) {
-      plonk::k_quotient_gates<true><<<dim3(cdiv(lde_size, 128), c->n_heavy), 128, 0, ctx->stream>>>(qp, c->d_gate_list + c->n_light);
+      qp.list_len = c->n_heavy;
+      const dim3 grid = qp.point_major ? dim3(pblocks * c->n_heavy, 1) : dim3(pblocks, c->n_heavy);
+      plonk::k_quotient_gates<true><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list + c->n_light);
       LAUNCH_CHECK(ctx);
     }
     plonk::k_quotient_combine<<<dim3(cdiv(lde_size, 256), nch), 256, 0, ctx->stream>>>(d_parts, n_parts, nch, log_lde, mdb,
@@ -1807,6 +1826,7 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     stage_end(ctx);
   }
   dfree(ctx, d_apow);
+  dfree(ctx, d_apow_g);
   dfree(ctx, d_parts);
   dfree(ctx, d_q);
   dfree(ctx, d_tmp);

@@ -153,8 +153,10 @@ __global__ void __launch_bounds__(256) k_pp_finish(const uint64_t* __restrict__ 
 // so the field element is the same as plonky2's reduce_with_powers.
 struct Acc {
   uint32_t w[MAX_CHALLENGES][5];
-  const uint64_t* apow;  // [challenge][stride] powers of alpha (canonical), already offset to the first gate term
-  uint32_t stride, n_chal, q;
+  // powers of alpha (canonical) as the GATE table [term][MAX_CHALLENGES] (QuotientParams::apow_gates): one running
+  // pointer, and the powers of all challenges for a term sit next to each other (one 16-byte load for two challenges)
+  const uint64_t* ap;
+  uint32_t n_chal;
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int ch = 0; ch < MAX_CHALLENGES; ch++)
@@ -181,19 +183,24 @@ struct Acc {
         : "+r"(w[ch][0]), "+r"(w[ch][1]), "+r"(w[ch][2]), "+r"(w[ch][3]), "+r"(w[ch][4])
         : "r"(c0), "r"(c1), "r"(a0), "r"(a1));
   }
+  __device__ __forceinline__ void weigh(const uint64_t* __restrict__ a, uint64_t c) {
+    const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(a);
+    add_product(0, c, a01.x);
+    if (n_chal > 1) add_product(1, c, a01.y);
+    if (n_chal > 2) {
+      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(a + 2);
+      add_product(2, c, a23.x);
+      if (n_chal > 3) add_product(3, c, a23.y);
+    }
+  }
   // c: any u64 (canonical or not); the alpha powers are canonical
   __device__ __forceinline__ void push(uint64_t c) {
-#pragma unroll
-    for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) add_product(ch, c, apow[ch * stride + q]);
-    q++;
+    weigh(ap, c);
+    ap += MAX_CHALLENGES;
   }
-  // constraint number q + k of the gate, without advancing
-  __device__ __forceinline__ void push_at(uint32_t k, uint64_t c) {
-#pragma unroll
-    for (int ch = 0; ch < MAX_CHALLENGES; ch++)
-      if (ch < (int)n_chal) add_product(ch, c, apow[ch * stride + q + k]);
-  }
+  // constraint number (current) + k of the gate, without advancing
+  __device__ __forceinline__ void push_at(uint32_t k, uint64_t c) { weigh(ap + (size_t)k * MAX_CHALLENGES, c); }
+  __device__ __forceinline__ void skip(uint32_t k) { ap += (size_t)k * MAX_CHALLENGES; }
   // the accumulated sum of challenge ch as a canonical field element
   __device__ __forceinline__ uint64_t value(int ch) const {
     // low 128 bits: x3:x2:x1:x0 -> (x1:x0) - x3 + x2 * (2^32 - 1), exactly gl::mul_nc's reduction
@@ -630,7 +637,7 @@ __device__ __forceinline__ void eval_gate_heavy(const Gate& g, const Vars& v, Ac
           acc.push_at(2 * r + t, cst);
         }
       }
-      acc.q += 24;
+      acc.skip(24);
       break;
     }
     case GATE_COSET_INTERPOLATION: {  // p0 = subgroup_bits, p1 = degree; barycentric weights of the subgroup = x_i / n
@@ -682,6 +689,7 @@ struct QuotientParams {
   const Gate* gates;
   const uint64_t* k_is;
   const uint64_t* apow;       // [challenge][n_terms] powers of alpha
+  const uint64_t* apow_gates; // [num_gate_constraints][MAX_CHALLENGES]: alpha_c^(n_chal * (num_pp + 2) + q), the gate terms
   const uint64_t* zh;         // [2^mdb] Z_H on the coset, then [2^mdb] inverses
   uint64_t* parts;            // [1 + n_gates][challenge][lde_size], natural order
   const uint64_t* betas;      // device
@@ -689,6 +697,7 @@ struct QuotientParams {
   const uint64_t* pi_hash;    // device, 4 canonical elements
   uint32_t degree_bits, mdb;  // lde_size = 2^(degree_bits + mdb)
   uint32_t num_routed, num_constants, num_selectors, n_chal, chunk, num_pp, n_gates, n_terms;
+  uint32_t point_major, list_len;  // k_quotient_gates' CTA -> (point block, gate) mapping, see there
   ntt2::RootTables roots;
 };
 
@@ -798,13 +807,19 @@ __global__ void __launch_bounds__(128, HEAVY ? P2B_QUOT_HEAVY_MINB : P2B_QUOT_MI
 k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
-  const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // gate-major (grid (points / 128, gates)): the CTAs resident together evaluate the same few gates — the smallest
+  // instruction footprint, right while the wires stay in L2 (a 2^12-row proof: 35 MB).  point-major (grid
+  // (gates * points / 128, 1), gate fastest): the CTAs resident together cover the same points for ALL gates, so a large
+  // circuit's wires are read from HBM once per kernel instead of once per gate (2^16 rows: 4.7 GB -> the compulsory 1 GB).
+  const uint32_t list_pos = P.point_major ? blockIdx.x % P.list_len : blockIdx.y;
+  const size_t point_block = P.point_major ? blockIdx.x / P.list_len : blockIdx.x;
+  const size_t leaf = point_block * blockDim.x + threadIdx.x;
   if (leaf >= lde_size) return;
   const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
-  const uint32_t nch = P.n_chal, npp = P.num_pp;
+  const uint32_t nch = P.n_chal;
   const uint64_t* cs = P.cs_lde + leaf;
   const size_t N = P.N;
-  const uint32_t g = gate_list[blockIdx.y];
+  const uint32_t g = gate_list[list_pos];
   // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
   Vars v{P.wires_lde + leaf, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
   const Gate gate = P.gates[g];
@@ -815,10 +830,8 @@ k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   if (P.num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
   Acc acc;
   acc.clear();
-  acc.apow = P.apow + nch * (npp + 2);
-  acc.stride = P.n_terms;
+  acc.ap = P.apow_gates;
   acc.n_chal = nch;
-  acc.q = 0;
   if (HEAVY)
     eval_gate_heavy(gate, v, acc);
   else
@@ -852,6 +865,15 @@ __global__ void k_build_apow(const uint64_t* __restrict__ alphas, uint32_t n_ter
     apow[(size_t)c * n_terms + k] = p;
     p = fmul(p, a);
   }
+}
+
+// apow_gates[q][c] = apow[c][first_gate_term + q] (zero for c >= n_chal)
+__global__ void __launch_bounds__(256) k_interleave_apow(const uint64_t* __restrict__ apow, uint32_t n_terms, uint32_t first_gate_term,
+                                                          uint32_t n_chal, uint64_t* __restrict__ out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (first_gate_term + q >= n_terms) return;
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++) out[(size_t)q * MAX_CHALLENGES + c] = c < (int)n_chal ? apow[(size_t)c * n_terms + first_gate_term + q] : 0;
 }
 
 // coefficient k of every column *= base^k  (the second half of coset_ifft: divide by shift^k)
