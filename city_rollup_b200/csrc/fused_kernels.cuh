@@ -220,6 +220,10 @@ struct TranscriptParams {
   //                      quotient's reduce_with_powers)
   //  ext_tab != nullptr: ext_tab[2 k .. 2 k + 2) = (out[0], out[1])^k as an extension element, k <= ext_n
   uint64_t scale_g;
+  // subgroup_check_bits = degree_bits + 1 (0 = no check): *subgroup_flag = 1 when (out[0], out[1])^(2^degree_bits) == 1,
+  // i.e. the opening point zeta lies in the subgroup H (plonky2's prover refuses: "Opening point is in the subgroup"), else 0
+  uint32_t subgroup_check_bits;
+  uint64_t* subgroup_flag;
   uint64_t* pow_tab;
   uint32_t pow_n;
   uint64_t* ext_tab;
@@ -276,6 +280,11 @@ __global__ void k_transcript(TranscriptParams P) {
   if (lane < frik::CH_WORDS) P.state[lane] = st[lane];
   if (P.n_out == 0 || P.n_out > 8) return;
   if (P.scale_g && lane < 2) P.out[2 + lane] = gl::mul(chal[lane], P.scale_g);
+  if (P.subgroup_check_bits && lane == 0) {
+    ext2 z{chal[0], chal[1]};
+    for (uint32_t k = 1; k < P.subgroup_check_bits; k++) z = gl::ext_mul(z, z);
+    *P.subgroup_flag = (z.c0 == 1 && z.c1 == 0) ? 1 : 0;
+  }
   if (P.pow_tab) {
     // lane l fills entries [l * per, (l + 1) * per) of every table
     const uint32_t per = (P.pow_n + 31) / 32;

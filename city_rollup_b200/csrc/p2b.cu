@@ -1792,12 +1792,15 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
         CU(ctx, cudaMemsetAsync(d_parts + (size_t)(1 + g) * nch * lde_size, 0, (size_t)nch * lde_size * sizeof(uint64_t), ctx->stream));
     plonk::k_quotient_perm<<<dim3(cdiv(lde_size, 128), 1), 128, 0, ctx->stream>>>(qp);
     LAUNCH_CHECK(ctx);
-    // large circuits: point-major CTA order, so that the wires stream from HBM once per kernel (see k_quotient_gates)
+    // CTA order: gate-major.  The point-major order (P2B_QUOT_POINT_MAJOR=1) reads a large circuit's wires from HBM
+    // once per kernel instead of once per gate, and is SLOWER: 5.05 against 3.54 ms at 2^16 rows with the recursion gate
+    // set, 0.64 against 0.49 ms at 2^12 rows with the City set (profiles/r02_summary.md) — with every gate's code live
+    // on every SM the kernels wait for instructions, not for HBM (4.6 GB at 2^16 rows is 0.7 ms of the 3.5).
     static const int force_pm = [] {
       const char* e = getenv("P2B_QUOT_POINT_MAJOR");
-      return e ? atoi(e) : -1;
+      return e ? atoi(e) : 0;
     }();
-    qp.point_major = force_pm >= 0 ? (uint32_t)force_pm : ((size_t)d.num_wires * qp.N * 8 > ((size_t)48 << 20) ? 1u : 0u);
+    qp.point_major = force_pm > 0 ? 1u : 0u;
     const unsigned pblocks = cdiv(lde_size, 128);
     if (c->n_light) {
       qp.list_len = c->n_light;
@@ -2152,7 +2155,7 @@ struct TrSegs {
 };
 static int transcript_step(p2b_ctx* ctx, uint64_t* d_state, bool reset, const TrSegs& segs, uint64_t* d_out, uint32_t n_out,
                            uint64_t scale_g = 0, uint64_t* pow_tab = nullptr, uint32_t pow_n = 0, uint64_t* ext_tab = nullptr,
-                           uint32_t ext_n = 0) {
+                           uint32_t ext_n = 0, uint32_t subgroup_check_bits = 0, uint64_t* subgroup_flag = nullptr) {
   fusedk::TranscriptParams tp{};
   tp.state = d_state;
   tp.n_seg = segs.count;
@@ -2168,6 +2171,8 @@ static int transcript_step(p2b_ctx* ctx, uint64_t* d_state, bool reset, const Tr
   tp.pow_n = pow_n;
   tp.ext_tab = ext_tab;
   tp.ext_n = ext_n;
+  tp.subgroup_check_bits = subgroup_check_bits;
+  tp.subgroup_flag = subgroup_flag;
   fusedk::k_transcript<<<1, 32, 0, ctx->stream>>>(tp);
   LAUNCH_CHECK(ctx);
   return P2B_OK;
@@ -2877,7 +2882,7 @@ static int prove_body(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
   TRY(h2d_small(ctx, d_small, h_small.data(), h_small.size(), ctx->cap ? &ctx->cap->h_digest : nullptr));
   uint64_t *d_digest = d_small, *d_pih = d_small + 4, *d_betas = d_small + 8, *d_gammas = d_betas + nch,
            *d_alphas = d_gammas + nch, *d_zeta = d_alphas + nch, *d_zeta_next = d_zeta + 2, *d_apow = d_zeta_next + 2;
-  TRY(dmalloc(ctx, &d_proof, proof_len));
+  TRY(dmalloc(ctx, &d_proof, proof_len + 1));  // + one status word: "zeta lies in the subgroup"
   // P2B_TRACE=1: phase-by-phase wall clock of one proof on stderr (each mark synchronises, so the phases are
   // serialised GPU time + host time; a development aid, never on in measurements)
   const bool trace = trace_enabled() && !ctx->cap;
@@ -2951,7 +2956,9 @@ static int prove_body(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
     const uint64_t g = d.degree_bits ? h_powmod(G, (uint64_t)1 << (32 - d.degree_bits)) : 1;
     TrSegs sg;
     sg.add(tree_cap_ptr(&qt->tree), cap_words);
-    TRY(transcript_step(ctx, ch->d_state, false, sg, d_zeta, 2, g));  // d_zeta | d_zeta_next are adjacent
+    // plonky2: ensure!(zeta.exp_power_of_2(degree_bits) != F::Extension::ONE, "Opening point is in the subgroup.")
+    TRY(transcript_step(ctx, ch->d_state, false, sg, d_zeta, 2, g, nullptr, 0, nullptr, 0, d.degree_bits + 1,
+                        d_proof + proof_len));  // d_zeta | d_zeta_next are adjacent
   }
   mark("transcript: zeta");
   // proof layout: caps | openings (OpeningSet field order) | FRI proof | public inputs
@@ -3021,7 +3028,7 @@ static int prove_body(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, c
   mark("prove_openings (FRI)");
   off += fri_len + n_public_inputs;
   if (off != proof_len) return cleanup(fail(ctx, P2B_ERR_INVALID, "internal: proof length mismatch"));
-  CUP(cudaMemcpyAsync(h_proof_dst, d_proof, proof_len * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUP(cudaMemcpyAsync(h_proof_dst, d_proof, (proof_len + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   return cleanup(P2B_OK);
 #undef TRY
 #undef CUP
@@ -3095,7 +3102,7 @@ static int plan_capture(p2b_ctx* ctx, ProvePlan* pl, const p2b_circuit* c, const
   pl->proof_len = proof_len_impl(c, cs, fp, n_public_inputs, nullptr);
   pl->pin_cap = 4096 + 2 * (cs->n_cols + c->d.num_wires + 64) + n_public_inputs;
   if (cudaMallocHost((void**)&pl->h_pin, pl->pin_cap * sizeof(uint64_t)) != cudaSuccess ||
-      cudaMallocHost((void**)&pl->h_proof, pl->proof_len * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMallocHost((void**)&pl->h_proof, (pl->proof_len + 1) * sizeof(uint64_t)) != cudaSuccess ||
       (!pl->dev_src && cudaMallocHost((void**)&pl->h_wires, pl->wires_words * sizeof(uint64_t)) != cudaSuccess)) {
     cudaGetLastError();
     return fail(ctx, P2B_ERR_OOM, "pinned host allocation for a prove plan failed");
@@ -3239,12 +3246,12 @@ static int prove_submit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs,
     ctx->pending_src = pl->h_proof;
   } else {
     // eager
-    if (proof_len * sizeof(uint64_t) > ctx->h_proof_bytes) {
+    if ((proof_len + 1) * sizeof(uint64_t) > ctx->h_proof_bytes) {
       if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
       ctx->h_proof = nullptr;
       ctx->h_proof_bytes = 0;
-      CU(ctx, cudaMallocHost((void**)&ctx->h_proof, proof_len * sizeof(uint64_t)));
-      ctx->h_proof_bytes = proof_len * sizeof(uint64_t);
+      CU(ctx, cudaMallocHost((void**)&ctx->h_proof, (proof_len + 1) * sizeof(uint64_t)));
+      ctx->h_proof_bytes = (proof_len + 1) * sizeof(uint64_t);
     }
     rc = prove_body(ctx, c, cs, circuit_digest, wire_cols, d_wires, public_inputs, n_public_inputs, fp, ctx->h_proof);
     if (rc) return rc;
@@ -3286,6 +3293,7 @@ static int prove_collect(p2b_ctx* ctx, uint64_t* proof_out, size_t proof_cap) {
   ctx->h2d_event_pending = false;  // everything enqueued has finished once the stream is idle
   CU(ctx, ctx_sync(ctx));
   memcpy(proof_out, ctx->pending_src, len * sizeof(uint64_t));
+  if (ctx->pending_src[len] != 0) return fail(ctx, P2B_ERR_INVALID, "Opening point is in the subgroup.");  // plonky2's own failure
   if (proof_out[ctx->pending_pow_index] == ~0ull) return fail(ctx, P2B_ERR_INVALID, "no proof-of-work witness found");
   return P2B_OK;
 }

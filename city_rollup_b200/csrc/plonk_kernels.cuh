@@ -89,8 +89,60 @@ __global__ void __launch_bounds__(256) k_pp_rows(PpParams P) {
   const uint32_t ch = blockIdx.y;
   const uint64_t beta = gl::canon(P.betas[ch]), gamma = gl::canon(P.gammas[ch]);
   const uint64_t bx = fmul(beta, ntt2::root_pow(P.roots, P.log_n, i));  // beta * w^i
-  uint64_t acc = 1;
   uint64_t* out = P.local + (size_t)ch * P.n_chunks * n + i;
+  // The chunk quotients np_k / dp_k need an inversion each (~2.8k instructions through Fermat); with up to
+  // PP_MAX_CHUNKS chunks their denominators are inverted together (Montgomery's trick: one inversion and three
+  // multiplications per chunk) — the inverse of a field element is unique, so the quotients are the same elements.
+  constexpr uint32_t PP_MAX_CHUNKS = 16;
+  if (P.n_chunks <= PP_MAX_CHUNKS) {
+    uint64_t np[PP_MAX_CHUNKS], pre[PP_MAX_CHUNKS];  // pre[k] = dp_0 * ... * dp_k
+    uint64_t run = 1;
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.n_chunks; k++) {
+      uint64_t num_p = 1, dp = 1;
+      for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
+        uint64_t wv = gl::canon(P.wires[(size_t)j * n + i]);
+        uint64_t num = fadd(fadd(wv, fmul(bx, P.k_is[j])), gamma);
+        uint64_t den = fadd(fadd(wv, fmul(beta, gl::canon(P.sigmas[(size_t)j * n + i]))), gamma);
+        num_p = fmul(num_p, num);
+        dp = fmul(dp, den);
+      }
+      np[k] = num_p;
+      // a zero denominator makes plonky2's batch inversion panic; here it would poison the whole row: keep the chunk's
+      // own inverse semantics (0^-1 = 0 through Fermat) by leaving zero factors out of the running product
+      pre[k] = dp;
+      run = dp ? fmul(run, dp) : run;
+    }
+    uint64_t inv_run = gl::inv(run);  // 1 / product of the non-zero denominators
+    // walk back: inv(dp_k) = inv_run * (product of the non-zero dp_j, j < k), then drop dp_k from inv_run
+    uint64_t q[PP_MAX_CHUNKS];
+    // prefix products of the non-zero denominators
+    uint64_t pref[PP_MAX_CHUNKS];
+    uint64_t pp = 1;
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.n_chunks; k++) {
+      pref[k] = pp;
+      if (pre[k]) pp = fmul(pp, pre[k]);
+    }
+#pragma unroll 1
+    for (uint32_t k = P.n_chunks; k-- > 0;) {
+      if (pre[k]) {
+        const uint64_t inv_k = fmul(inv_run, pref[k]);
+        inv_run = fmul(inv_run, pre[k]);
+        q[k] = fmul(np[k], inv_k);
+      } else {
+        q[k] = 0;
+      }
+    }
+    uint64_t acc = 1;
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.n_chunks; k++) {
+      acc = fmul(acc, q[k]);
+      out[(size_t)k * n] = acc;
+    }
+    return;
+  }
+  uint64_t acc = 1;
   for (uint32_t k = 0; k < P.n_chunks; k++) {
     uint64_t np = 1, dp = 1;
     for (uint32_t j = k * P.chunk; j < (k + 1) * P.chunk && j < P.num_routed; j++) {
@@ -807,10 +859,10 @@ __global__ void __launch_bounds__(128, HEAVY ? P2B_QUOT_HEAVY_MINB : P2B_QUOT_MI
 k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
-  // gate-major (grid (points / 128, gates)): the CTAs resident together evaluate the same few gates — the smallest
-  // instruction footprint, right while the wires stay in L2 (a 2^12-row proof: 35 MB).  point-major (grid
-  // (gates * points / 128, 1), gate fastest): the CTAs resident together cover the same points for ALL gates, so a large
-  // circuit's wires are read from HBM once per kernel instead of once per gate (2^16 rows: 4.7 GB -> the compulsory 1 GB).
+  // gate-major (grid (points / 128, gates), the default): the CTAs resident together evaluate the same few gates — the
+  // smallest instruction footprint.  point-major (grid (gates * points / 128, 1), gate fastest; P2B_QUOT_POINT_MAJOR=1):
+  // the CTAs resident together cover the same points for ALL gates, so a large circuit's wires are read from HBM once per
+  // kernel instead of once per gate (2^16 rows: 4.7 GB -> ~1 GB) — measured slower at every size (p2b.cu quotient_core).
   const uint32_t list_pos = P.point_major ? blockIdx.x % P.list_len : blockIdx.y;
   const size_t point_block = P.point_major ? blockIdx.x / P.list_len : blockIdx.x;
   const size_t leaf = point_block * blockDim.x + threadIdx.x;

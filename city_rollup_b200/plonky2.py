@@ -722,7 +722,13 @@ def prove(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values
     challenger.observe_cap(quotient)
     zeta = challenger.get_extension_challenge()
     n = 1 << d["degree_bits"]
-    # zeta^n != 1 is required (plonky2 fails the proof otherwise); g = primitive n-th root
+    # plonky2: ensure!(zeta.exp_power_of_2(degree_bits) != F::Extension::ONE, "Opening point is in the subgroup.")
+    z0, z1 = int(zeta[0]) % P, int(zeta[1]) % P
+    for _ in range(d["degree_bits"]):
+        z0, z1 = (z0 * z0 + 7 * z1 * z1) % P, (2 * z0 * z1) % P
+    if (z0, z1) == (1, 0):
+        raise P2BError(-1, "Opening point is in the subgroup.")
+    # g = primitive n-th root
     g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - d["degree_bits"]), P) if d["degree_bits"] else 1
     zeta_next = [zeta[0] * g % P, zeta[1] * g % P]
     cs = constants_sigmas_commitment
