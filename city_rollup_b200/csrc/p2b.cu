@@ -177,8 +177,11 @@ struct p2b_circuit {
   uint64_t* d_zh = nullptr;  // ZeroPolyOnCoset: Z_H on the 2^mdb cosets of the quotient LDE, then the inverses
   uint32_t mdb = 0;          // log2(quotient_degree_factor)
   std::vector<uint32_t> gate_kinds;  // host copy of gates[g].kind
-  uint32_t* d_gate_list = nullptr;  // gate indices: the light gates, then the heavy ones (plonk::k_quotient_gates)
-  uint32_t n_light = 0, n_heavy = 0;
+  // gate indices: the light gates evaluated directly, the heavy ones, then the EXTENDED gates (low constraint degree:
+  // evaluated on a sub-coset and extended by NTT, plonk::k_quotient_gates) of class 1 (2 n points) and class 2 (4 n);
+  // behind them the part list of k_quotient_combine (0 = permutation argument, 1 + g for every directly evaluated gate)
+  uint32_t* d_gate_list = nullptr;
+  uint32_t n_light = 0, n_heavy = 0, n_ext[3] = {0, 0, 0} /* index = log2(D) */, n_parts_direct = 0;
 };
 
 struct p2b_challenger {
@@ -1467,6 +1470,34 @@ extern "C" int p2b_batch_lde_col(p2b_batch* b, size_t col, uint64_t* out) {
 }
 
 // ------------------------------------------------------------------------------------------------ PLONK stages
+// Degree (in units of n - 1) of the gate's UNFILTERED constraints as polynomials in x: wires and constant columns count
+// 1 each.  Only gates whose evaluators are worth extending are listed; 0 = evaluate at every point of the quotient coset.
+//   arithmetic: w w c0 (3); base sum: l (l - 1) (2); u32 gates: limb range checks prod_{x<4} (limb - x) (4);
+//   interleave / uninterleave: b (b - 1) (2); comparison: prod_{x < 2^chunk_bits} (chunk - x), and eq * msd with
+//   msd = inter + (1 - eq) diff (3); extension arithmetic / multiplication: m0 m1 c0 (3); reducing: acc * alpha (2)
+static uint32_t gate_constraint_degree(const p2b_gate& gt) {
+  switch (gt.kind) {
+    case plonk::GATE_ARITHMETIC: return 3;
+    case plonk::GATE_BASE_SUM: return 2;
+    case plonk::GATE_U32_ARITHMETIC:
+    case plonk::GATE_U32_ADD_MANY:
+    case plonk::GATE_U32_SUBTRACTION:
+    case plonk::GATE_U32_RANGE_CHECK: return 4;
+    case plonk::GATE_U32_INTERLEAVE:
+    case plonk::GATE_UNINTERLEAVE_TO_U32:
+    case plonk::GATE_UNINTERLEAVE_TO_B32: return 2;
+    case plonk::GATE_COMPARISON: {
+      const uint32_t cb = (gt.p0 + gt.p1 - 1) / gt.p1, prod = 1u << cb;
+      return prod > 3 ? prod : 3;
+    }
+    case plonk::GATE_ARITHMETIC_EXT:
+    case plonk::GATE_MUL_EXT: return 3;
+    case plonk::GATE_REDUCING:
+    case plonk::GATE_REDUCING_EXT: return 2;
+    default: return 0;
+  }
+}
+
 extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_circuit** out) {
   CHECK_CTX(ctx);
   if (!desc || !out || !desc->gates || !desc->k_is) return fail(ctx, P2B_ERR_INVALID, "null argument");
@@ -1560,18 +1591,40 @@ extern "C" int p2b_circuit_new(p2b_ctx* ctx, const p2b_circuit_desc* desc, p2b_c
   }
   if (rc == P2B_OK) rc = dmalloc(ctx, &c->d_zh, zh.size());
   for (uint32_t g = 0; g < d.n_gates; g++) c->gate_kinds.push_back(d.gates[g].kind);
-  std::vector<uint32_t> gate_list;
-  for (int heavy = 0; heavy < 2; heavy++)
+  std::vector<uint32_t> gate_list, part_list{0};
+  // extension class of a gate: log2 of the smallest power of two >= its constraint degree, if that is below the
+  // quotient degree factor (and the gate is worth two NTT columns); 0 = evaluate at every point
+  static const bool ext_on = [] {
+    const char* e = getenv("P2B_QUOT_EXT");
+    return !e || atoi(e) != 0;
+  }();
+  auto ext_class = [&](const p2b_gate& gt) -> uint32_t {
+    const uint32_t deg = gate_constraint_degree(gt);
+    if (!ext_on || deg == 0) return 0;
+    uint32_t ld = 1;
+    while ((1u << ld) < deg) ld++;
+    return ld < c->mdb && ld <= 2 ? ld : 0;
+  };
+  for (int pass = 0; pass < 4; pass++)  // light direct, heavy direct, extended class 1, extended class 2
     for (uint32_t g = 0; g < d.n_gates; g++) {
       const uint32_t k = d.gates[g].kind;
       const bool h = k == plonk::GATE_POSEIDON || k == plonk::GATE_POSEIDON_MDS || k == plonk::GATE_RANDOM_ACCESS ||
                      k == plonk::GATE_COSET_INTERPOLATION;
-      if (k == plonk::GATE_NOOP) continue;  // no constraints: its part stays zero (k_quotient_combine skips it)
-      if (h == (heavy == 1)) {
+      if (k == plonk::GATE_NOOP) continue;  // no constraints, no part
+      const uint32_t ec = ext_class(d.gates[g]);
+      if (pass < 2) {
+        if (ec == 0 && h == (pass == 1)) {
+          gate_list.push_back(g);
+          part_list.push_back(1 + g);
+          (pass ? c->n_heavy : c->n_light)++;
+        }
+      } else if (ec == (uint32_t)(pass - 1)) {
         gate_list.push_back(g);
-        (heavy ? c->n_heavy : c->n_light)++;
+        c->n_ext[ec]++;
       }
     }
+  c->n_parts_direct = (uint32_t)part_list.size();
+  gate_list.insert(gate_list.end(), part_list.begin(), part_list.end());
   if (rc == P2B_OK) rc = dmalloc(ctx, (uint64_t**)&c->d_gate_list, (gate_list.size() + 2) / 2);
   if (rc == P2B_OK && !gate_list.empty()) {
     cudaError_t e = cudaMemcpyAsync(c->d_gate_list, gate_list.data(), gate_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
@@ -1753,6 +1806,18 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   }
   if ((rc = dmalloc(ctx, &d_q, (size_t)nch * lde_size)) == P2B_OK) rc = dmalloc(ctx, &d_coeffs, (size_t)nch * lde_size);
   if (rc == P2B_OK) rc = dmalloc(ctx, &d_tmp, (size_t)nch * lde_size);
+  // extended (low-degree) gates: values / coefficients / NTT scratch on the largest sub-coset, extended sums on all points
+  const uint32_t n_ext = c->n_ext[1] + c->n_ext[2];
+  uint64_t *d_ext_vals = nullptr, *d_ext_coeffs = nullptr, *d_ext_tmp = nullptr, *d_ext = nullptr;
+  if (n_ext) {
+    size_t sub = 0;
+    for (uint32_t ld = 1; ld <= 2; ld++)
+      if ((size_t)c->n_ext[ld] * nch * (n << ld) > sub) sub = (size_t)c->n_ext[ld] * nch * (n << ld);
+    if (rc == P2B_OK) rc = dmalloc(ctx, &d_ext_vals, sub);
+    if (rc == P2B_OK) rc = dmalloc(ctx, &d_ext_coeffs, sub);
+    if (rc == P2B_OK) rc = dmalloc(ctx, &d_ext_tmp, sub);
+    if (rc == P2B_OK) rc = dmalloc(ctx, &d_ext, (size_t)n_ext * nch * lde_size);
+  }
   if (rc == P2B_OK) {
     stage_begin(ctx, ST_OTHER);
     if (!d_apow_ready) {
@@ -1786,10 +1851,6 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     qp.n_gates = d.n_gates;
     qp.n_terms = n_terms;
     qp.roots = ctx->roots();
-    // Noop gates have no constraints and no launch: their parts must read as zero
-    for (uint32_t g = 0; g < d.n_gates; g++)
-      if (d_gate_kinds_noop(c, g))
-        CU(ctx, cudaMemsetAsync(d_parts + (size_t)(1 + g) * nch * lde_size, 0, (size_t)nch * lde_size * sizeof(uint64_t), ctx->stream));
     plonk::k_quotient_perm<<<dim3(cdiv(lde_size, 128), 1), 128, 0, ctx->stream>>>(qp);
     LAUNCH_CHECK(ctx);
     // CTA order: gate-major.  The point-major order (P2B_QUOT_POINT_MAJOR=1) reads a large circuit's wires from HBM
@@ -1805,22 +1866,43 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
     if (c->n_light) {
       qp.list_len = c->n_light;
       const dim3 grid = qp.point_major ? dim3(pblocks * c->n_light, 1) : dim3(pblocks, c->n_light);
-      plonk::k_quotient_gates<false><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list);
+      plonk::k_quotient_gates<false, false><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list);
       LAUNCH_CHECK(ctx);
     }
     if (c->n_heavy) {
       qp.list_len = c->n_heavy;
       const dim3 grid = qp.point_major ? dim3(pblocks * c->n_heavy, 1) : dim3(pblocks, c->n_heavy);
-      plonk::k_quotient_gates<true><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list + c->n_light);
+      plonk::k_quotient_gates<true, false><<<grid, 128, 0, ctx->stream>>>(qp, c->d_gate_list + c->n_light);
       LAUNCH_CHECK(ctx);
     }
-    plonk::k_quotient_combine<<<dim3(cdiv(lde_size, 256), nch), 256, 0, ctx->stream>>>(d_parts, n_parts, nch, log_lde, mdb,
-                                                                                       c->d_zh, d_q);
-    LAUNCH_CHECK(ctx);
+    // low-degree gates: unfiltered sums on the first D n leaves (natural order of that sub-coset), then
+    // iNTT (D n) + NTT to all 2^mdb n points, leaf order (see plonk::k_quotient_gates)
+    qp.point_major = 0;
+    for (uint32_t ld = 1; ld <= 2 && rc == P2B_OK; ld++) {
+      if (!c->n_ext[ld]) continue;
+      const uint32_t log_pts = d.degree_bits + ld;
+      const size_t pts = (size_t)1 << log_pts, cols = (size_t)c->n_ext[ld] * nch;
+      const uint32_t first = ld == 1 ? 0 : c->n_ext[1];
+      qp.list_len = c->n_ext[ld];
+      qp.ext_out = d_ext_vals;
+      qp.ext_log_pts = log_pts;
+      plonk::k_quotient_gates<false, true><<<dim3(cdiv(pts, 128), c->n_ext[ld]), 128, 0, ctx->stream>>>(
+          qp, c->d_gate_list + c->n_light + c->n_heavy + first);
+      LAUNCH_CHECK(ctx);
+      rc = run_intt(ctx, d_ext_vals, d_ext_coeffs, d_ext_tmp, cols, log_pts, pts);
+      if (rc == P2B_OK) rc = run_lde(ctx, d_ext_coeffs, pts, d_ext + (size_t)first * nch * lde_size, cols, log_pts, mdb - ld, 1);
+    }
+    if (rc == P2B_OK) {
+      const uint32_t* lists = c->d_gate_list + c->n_light + c->n_heavy;
+      plonk::k_quotient_combine<<<cdiv(lde_size, 256), 256, 0, ctx->stream>>>(
+          d_parts, lists + n_ext, c->n_parts_direct, d_ext, lists, n_ext, c->d_gates, cs->d_lde, qp.N, d.num_selectors, nch,
+          log_lde, mdb, c->d_zh, d_q);
+      LAUNCH_CHECK(ctx);
+    }
     stage_end(ctx);
     // values.coset_ifft(7): ifft, then coefficient k / 7^k
     stage_begin(ctx, ST_INTT);
-    rc = run_intt(ctx, d_q, d_coeffs, d_tmp, nch, log_lde, lde_size);
+    if (rc == P2B_OK) rc = run_intt(ctx, d_q, d_coeffs, d_tmp, nch, log_lde, lde_size);
     if (rc == P2B_OK) {
       plonk::k_scale_by_powers<<<dim3(cdiv(lde_size, 256 * 16), nch), 256, 0, ctx->stream>>>(d_coeffs, lde_size,
                                                                                             h_powmod(7, GL_P - 2));
@@ -1833,6 +1915,10 @@ static int quotient_core(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs
   dfree(ctx, d_parts);
   dfree(ctx, d_q);
   dfree(ctx, d_tmp);
+  dfree(ctx, d_ext_vals);
+  dfree(ctx, d_ext_coeffs);
+  dfree(ctx, d_ext_tmp);
+  dfree(ctx, d_ext);
   if (rc != P2B_OK) {
     dfree(ctx, d_coeffs);
     return rc;

@@ -341,6 +341,14 @@ __device__ __forceinline__ void mds_plain(uint64_t (&s)[12]) {
 }
 __device__ __forceinline__ uint64_t sbox7c(uint64_t x) { return gl::canon(poseidon::sbox7(x)); }
 
+// PoseidonGate (gates/poseidon.rs eval_unfiltered): the permutation with every S-box input replaced by a wire and the
+// difference to the computed input as a constraint.  plonky2 evaluates it in the "fast partial round" form; the S-box
+// inputs of that form are those of the plain permutation (lane 0 after the constant layer: the change of basis of the
+// fast form touches lanes 1..11 only and commutes with anything done to lane 0 — checked for the witness generator by
+// tests/test_plonk_oracle.py and, value for value on random points, by the GPU parity tests against the oracle's
+// fast-form evaluator), so the evaluator IS the leaf-hash permutation (poseidon.cuh, v6 schedule: MDS layers on the
+// FP64 pipe, two partial rounds per step) with hooks: ~21k instead of ~38k instructions per point with the fast-form
+// tables and 64-bit constant multiplications.
 __device__ void eval_poseidon_gate(const Vars& v, Acc& acc) {
   constexpr int SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 65, FULL1 = 87;
   const uint64_t swap = v.w(SWAP);
@@ -355,67 +363,56 @@ __device__ void eval_poseidon_gate(const Vars& v, Acc& acc) {
   }
 #pragma unroll
   for (int i = 8; i < 12; i++) s[i] = v.w(i);
-  uint32_t round = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl::add_nc(s[i], poseidon::RC[i]);
+  // first full rounds: s = S-box inputs (round constants included by the previous layer); wires from round 1 on
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = fadd(s[i], poseidon::RC[12 * round + i]);
     if (r != 0) {
 #pragma unroll
       for (int i = 0; i < 12; i++) {
-        uint64_t in = v.w(FULL0 + 12 * (r - 1) + i);
-        acc.push(fsub(s[i], in));
+        const uint64_t in = v.w(FULL0 + 12 * (r - 1) + i);
+        acc.push(gl::sub_nc(s[i], in));  // any u64 minus a canonical wire: congruent, which is all push needs
         s[i] = in;
       }
     }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = sbox7c(s[i]);
-    mds_plain(s);
-    round++;
+    poseidon::full_round_v6(s, poseidon::RC6 + 24 * r);
   }
+  {
+    double zlo[12], zhi[12];
+    zlo[0] = zhi[0] = 0.;
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = fadd(s[i], PFAST_FIRST[i]);
-  {  // mds_partial_layer_init
-    uint64_t o[12];
-    o[0] = s[0];
+    for (int i = 1; i < 12; i++) poseidon::limbs_from_u64(s[i], zlo[i], zhi[i]);
+    uint64_t s0 = s[0];
+    const uint32_t vz = poseidon::lane_varying_zero();
 #pragma unroll 1
-    for (int i = 0; i < 11; i++) {
-      uint64_t a = 0;
-#pragma unroll
-      for (int j = 0; j < 11; j++) a = fadd(a, fmul(PFAST_INIT[i * 11 + j], s[1 + j]));
-      o[1 + i] = a;
+    for (int r = 0; r < 22; r += 2) {
+      const uint64_t in0 = v.w(PARTIAL + r), in1 = v.w(PARTIAL + r + 1);
+      acc.push(gl::sub_nc(s0, in0));
+      s0 = in0;
+      uint64_t mid_computed = 0;
+      poseidon::partial_round_pair_v6_hook(s0, zlo, zhi, 4 + r, vz, [&](uint64_t x) {
+        mid_computed = x;
+        return in1;
+      });
+      acc.push(gl::sub_nc(mid_computed, in1));
     }
+    s[0] = s0;
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = o[i];
+    for (int i = 1; i < 12; i++) s[i] = gl::sub_nc(poseidon::fold_f64(zlo[i], zhi[i]), (uint64_t)P2B_LAZY_OFFSET);
   }
-#pragma unroll 1
-  for (int r = 0; r < 22; r++) {
-    uint64_t in = v.w(PARTIAL + r);
-    acc.push(fsub(s[0], in));
-    s[0] = sbox7c(in);
-    if (r < 21) s[0] = fadd(s[0], PFAST_POST[r]);
-    uint64_t d = fmul(s[0], 25);
-#pragma unroll
-    for (int i = 1; i < 12; i++) d = fadd(d, fmul(s[i], PFAST_W_HATS[r * 11 + i - 1]));
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = fadd(s[i], fmul(s[0], PFAST_VS[r * 11 + i - 1]));
-    s[0] = d;
-  }
-  round += 22;
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      s[i] = fadd(s[i], poseidon::RC[12 * round + i]);
-      uint64_t in = v.w(FULL1 + 12 * r + i);
-      acc.push(fsub(s[i], in));
-      s[i] = sbox7c(in);
+      const uint64_t in = v.w(FULL1 + 12 * r + i);
+      acc.push(gl::sub_nc(s[i], in));
+      s[i] = in;
     }
-    mds_plain(s);
-    round++;
+    poseidon::full_round_v6(s, poseidon::RC6 + 24 * (26 + r));
   }
 #pragma unroll
-  for (int i = 0; i < 12; i++) acc.push(fsub(s[i], v.w(12 + i)));
+  for (int i = 0; i < 12; i++) acc.push(gl::sub_nc(s[i], v.w(12 + i)));
 }
 
 __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Acc& acc) {
@@ -743,13 +740,17 @@ struct QuotientParams {
   const uint64_t* apow;       // [challenge][n_terms] powers of alpha
   const uint64_t* apow_gates; // [num_gate_constraints][MAX_CHALLENGES]: alpha_c^(n_chal * (num_pp + 2) + q), the gate terms
   const uint64_t* zh;         // [2^mdb] Z_H on the coset, then [2^mdb] inverses
-  uint64_t* parts;            // [1 + n_gates][challenge][lde_size], natural order
+  uint64_t* parts;            // [1 + n_gates][challenge][lde_size], LEAF order (k_quotient_combine un-reverses)
   const uint64_t* betas;      // device
   const uint64_t* gammas;     // device
   const uint64_t* pi_hash;    // device, 4 canonical elements
   uint32_t degree_bits, mdb;  // lde_size = 2^(degree_bits + mdb)
   uint32_t num_routed, num_constants, num_selectors, n_chal, chunk, num_pp, n_gates, n_terms;
   uint32_t point_major, list_len;  // k_quotient_gates' CTA -> (point block, gate) mapping, see there
+  // EXT launches of k_quotient_gates (low-degree gates, see there): the unfiltered sums of the first 2^ext_log_pts
+  // leaves go to ext_out[list position][challenge][2^ext_log_pts] in NATURAL order of that sub-coset
+  uint64_t* ext_out;
+  uint32_t ext_log_pts;
   ntt2::RootTables roots;
 };
 
@@ -775,6 +776,15 @@ __device__ __forceinline__ bool gate_is_heavy(uint32_t kind) {
 #ifndef P2B_QUOT_HEAVY_MINB
 #define P2B_QUOT_HEAVY_MINB 4
 #endif
+
+// compute_filter (gates/gate.rs): prod_{q in the gate's selector group, q != row} (q - s) * (UNUSED_SELECTOR - s)
+__device__ __forceinline__ uint64_t gate_filter(const Gate& gate, uint64_t s, uint32_t num_selectors) {
+  uint64_t filter = 1;
+  for (uint32_t q = gate.group_start; q < gate.group_end; q++)
+    if (q != gate.row) filter = fmul(filter, fsub(q, s));
+  if (num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
+  return filter;
+}
 
 __global__ void __launch_bounds__(128, 6) k_quotient_perm(QuotientParams P) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
@@ -851,14 +861,24 @@ __global__ void __launch_bounds__(128, 6) k_quotient_perm(QuotientParams P) {
     }
     for (uint32_t c = 0; c < nch; c++) res[c] = gl::canon(res[c]);  // k_quotient_combine adds canonical parts
   }
-  for (uint32_t c = 0; c < nch; c++) P.parts[(size_t)c * lde_size + i] = res[c];
+  for (uint32_t c = 0; c < nch; c++) P.parts[(size_t)c * lde_size + leaf] = res[c];
 }
 
-template <bool HEAVY>
+// EXT launches — low-degree gates.  The alpha-weighted constraint sum G_g(x) of gate g, WITHOUT its selector filter, is
+// a polynomial of degree <= d_g (n - 1) in x, where d_g is the gate's constraint degree (wires and constants are
+// polynomials of degree < n).  For d_g <= D < 2^mdb it is therefore fixed by its values on the sub-coset 7 <w_{D n}> —
+// the FIRST D n leaves of the leaf-ordered LDE — and its values on the whole quotient coset follow by one inverse NTT
+// of size D n and one forward NTT of size 2^mdb n (both cosets have the shift 7, so no rescaling); the filter, a
+// polynomial in the selector column, is multiplied in by k_quotient_combine at all points.  Field arithmetic is exact,
+// so the extended values ARE the directly evaluated ones (same field elements, bit for bit): a degree-2 gate
+// (booleans, base sums, reducing) costs a quarter and a degree-3/4 gate (arithmetic, u32 limbs, comparison) half of
+// the evaluator work, for two NTT columns per gate.
+template <bool HEAVY, bool EXT>
 __global__ void __launch_bounds__(128, HEAVY ? P2B_QUOT_HEAVY_MINB : P2B_QUOT_MINB)
 k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   const uint32_t log_lde = P.degree_bits + P.mdb;
   const size_t lde_size = (size_t)1 << log_lde;
+  const size_t n_pts = EXT ? (size_t)1 << P.ext_log_pts : lde_size;
   // gate-major (grid (points / 128, gates), the default): the CTAs resident together evaluate the same few gates — the
   // smallest instruction footprint.  point-major (grid (gates * points / 128, 1), gate fastest; P2B_QUOT_POINT_MAJOR=1):
   // the CTAs resident together cover the same points for ALL gates, so a large circuit's wires are read from HBM once per
@@ -866,8 +886,7 @@ k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   const uint32_t list_pos = P.point_major ? blockIdx.x % P.list_len : blockIdx.y;
   const size_t point_block = P.point_major ? blockIdx.x / P.list_len : blockIdx.x;
   const size_t leaf = point_block * blockDim.x + threadIdx.x;
-  if (leaf >= lde_size) return;
-  const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
+  if (leaf >= n_pts) return;
   const uint32_t nch = P.n_chal;
   const uint64_t* cs = P.cs_lde + leaf;
   const size_t N = P.N;
@@ -875,11 +894,6 @@ k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
   // gate constraints: every gate's constraint q lands on term nch*(npp+2) + q
   Vars v{P.wires_lde + leaf, N, cs + (size_t)P.num_selectors * N, P.pi_hash, P.roots};
   const Gate gate = P.gates[g];
-  const uint64_t s = gl::canon(cs[(size_t)gate.selector_index * N]);
-  uint64_t filter = 1;
-  for (uint32_t q = gate.group_start; q < gate.group_end; q++)
-    if (q != gate.row) filter = fmul(filter, fsub(q, s));
-  if (P.num_selectors > 1) filter = fmul(filter, fsub(P2B_UNUSED_SELECTOR, s));
   Acc acc;
   acc.clear();
   acc.ap = P.apow_gates;
@@ -888,23 +902,55 @@ k_quotient_gates(QuotientParams P, const uint32_t* __restrict__ gate_list) {
     eval_gate_heavy(gate, v, acc);
   else
     eval_gate_light(gate, v, acc);
+  if (EXT) {
+    const size_t idx = ntt2::brev((uint32_t)leaf, P.ext_log_pts);
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++)
+      if (c < (int)nch) P.ext_out[((size_t)list_pos * nch + c) * n_pts + idx] = acc.value(c);
+    return;
+  }
+  const uint64_t filter = gate_filter(gate, gl::canon(cs[(size_t)gate.selector_index * N]), P.num_selectors);
 #pragma unroll
   for (int c = 0; c < MAX_CHALLENGES; c++)
-    if (c < (int)nch) P.parts[((size_t)(1 + g) * nch + c) * lde_size + i] = fmul(filter, acc.value(c));
+    if (c < (int)nch) P.parts[((size_t)(1 + g) * nch + c) * lde_size + leaf] = fmul(filter, acc.value(c));
 }
 
-// out[c][i] = (sum over parts) / Z_H(x_i)
-__global__ void __launch_bounds__(256) k_quotient_combine(const uint64_t* __restrict__ parts, uint32_t n_parts, uint32_t n_chal,
-                                                           uint32_t log_lde, uint32_t mdb, const uint64_t* __restrict__ zh,
-                                                           uint64_t* __restrict__ out) {
+// out[c][i] = (sum over the direct parts + sum over the extended gates of filter * extended sum) / Z_H(x_i); one thread
+// per LEAF (parts, extended sums and selector columns are leaf-ordered: coalesced), the quotient values are stored in
+// natural order (i = bit-reversed leaf) for the coset iNTT that follows.
+//   part_list[0 .. n_direct)          indices into parts (0 = the permutation argument, 1 + g = gate g)
+//   ext_list[0 .. n_ext)              gate index of the extended sum ext[k] ([n_ext][challenge][lde_size], leaf order)
+__global__ void __launch_bounds__(256) k_quotient_combine(const uint64_t* __restrict__ parts, const uint32_t* __restrict__ part_list,
+                                                           uint32_t n_direct, const uint64_t* __restrict__ ext,
+                                                           const uint32_t* __restrict__ ext_list, uint32_t n_ext,
+                                                           const Gate* __restrict__ gates, const uint64_t* __restrict__ cs_lde,
+                                                           size_t N, uint32_t num_selectors, uint32_t n_chal, uint32_t log_lde,
+                                                           uint32_t mdb, const uint64_t* __restrict__ zh, uint64_t* __restrict__ out) {
   const size_t lde_size = (size_t)1 << log_lde;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= lde_size) return;
-  const uint32_t c = blockIdx.y;
-  uint64_t acc = 0;
-  for (uint32_t p = 0; p < n_parts; p++) acc = fadd(acc, parts[((size_t)p * n_chal + c) * lde_size + i]);
+  const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= lde_size) return;
+  const size_t i = ntt2::brev((uint32_t)leaf, log_lde);
+  uint64_t acc[MAX_CHALLENGES];
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
+  for (uint32_t p = 0; p < n_direct; p++) {
+    const uint64_t* src = parts + (size_t)part_list[p] * n_chal * lde_size + leaf;
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++)
+      if (c < (int)n_chal) acc[c] = fadd(acc[c], src[(size_t)c * lde_size]);
+  }
+  for (uint32_t k = 0; k < n_ext; k++) {
+    const Gate gate = gates[ext_list[k]];
+    const uint64_t filter = gate_filter(gate, gl::canon(cs_lde[(size_t)gate.selector_index * N + leaf]), num_selectors);
+    const uint64_t* src = ext + (size_t)k * n_chal * lde_size + leaf;
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++)
+      if (c < (int)n_chal) acc[c] = fadd(acc[c], fmul(filter, src[(size_t)c * lde_size]));
+  }
   const uint64_t z_h_inv = zh[((size_t)1 << mdb) + (i & (((size_t)1 << mdb) - 1))];
-  out[(size_t)c * lde_size + i] = fmul(acc, z_h_inv);
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++)
+    if (c < (int)n_chal) out[(size_t)c * lde_size + i] = fmul(acc[c], z_h_inv);
 }
 
 // apow[c * n_terms + k] = alphas[c]^k

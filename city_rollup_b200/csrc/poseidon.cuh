@@ -380,8 +380,11 @@ __device__ __forceinline__ uint32_t lane_varying_zero() {
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));  // < 2^31 on every lane
   return m >> 31;
 }
-__device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
-                                                      uint32_t vz) {
+// `mid` maps the computed S-box input of the second round to the value that is raised to the 7th power (identity for the
+// permutation; the PoseidonGate evaluator records the difference to the wire and continues with the wire).
+template <class MidHook>
+__device__ __forceinline__ void partial_round_pair_v6_hook(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
+                                                           uint32_t vz, MidHook&& mid) {
   const unsigned long long* __restrict__ initA = RC6 + 24 * (r + vz);
   const unsigned long long* __restrict__ initB = initA + 24;
   double Pl[6], Ml[6], Ph[6], Mh[6];  // first layer
@@ -406,7 +409,7 @@ __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo
   const double y0l = dadd(Pl[0], Ml[0]), y0h = dadd(Ph[0], Mh[0]);  // lanes 0 and 6 (biased): the only outputs formed
   const double y6l = dsub(Pl[0], Ml[0]), y6h = dsub(Ph[0], Mh[0]);
   // ---- second layer: the row pairs 1..5 of the first layer enter as its chains (halves of p_k / m_k)
-  sbox7_limbs(fold_f64_b1(y0l, y0h), b0l, b0h);
+  sbox7_limbs(mid(fold_f64_b1(y0l, y0h)), b0l, b0h);
   pm_from_biased(b0l, y6l, p0l, m0l);
   pm_from_biased(b0h, y6h, p0h, m0h);
   p_rows_split<true>(p0l, m0l, Pl, initB, Ql);
@@ -420,6 +423,11 @@ __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo
     lazy_fold(dadd(Ql[i], Nl[i]), dadd(Qh[i], Nh[i]), zlo[i], zhi[i]);
     lazy_fold(dsub(Ql[i], Nl[i]), dsub(Qh[i], Nh[i]), zlo[i + 6], zhi[i + 6]);
   }
+}
+
+__device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
+                                                      uint32_t vz) {
+  partial_round_pair_v6_hook(s0, zlo, zhi, r, vz, [](uint64_t x) { return x; });
 }
 
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).
