@@ -142,7 +142,14 @@ k_pow_search(const uint64_t* __restrict__ st, uint64_t base, uint64_t count, uin
     uint64_t s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = ((uint32_t)i == n_in) ? w : s0[i];
-    poseidon::permute_nc(s);
+    // a hit of another thread usually lands while this candidate is in flight (all threads finish a permutation at
+    // about the same time): look again a quarter of the way in
+    if (!poseidon::permute_nc_abortable(s, [&] {
+          unsigned long long now;
+          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(now) : "l"(best) : "memory");
+          return w > now;
+        }))
+      return;
     const uint64_t resp = gl::canon(s[7]);
     if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) {
       atomicMin(best, (unsigned long long)w);

@@ -2457,14 +2457,20 @@ static int fri_pow_dev(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint
                        uint64_t* d_chal) {
   if (pow_bits > 40) return fail(ctx, P2B_ERR_UNSUPPORTED, "pow_bits > 40");
   unsigned long long* d_best = (unsigned long long*)(ctx->d_scratch + 1);
-  // the minimal witness is geometric with mean 2^pow_bits.  Grid: about half the mean per stride, between one and
-  // three CTAs per SM.
-  // Every thread of a stride evaluates its candidate even when the witness sits at the start of the stride, so a
-  // stride is wasted work on average half over: a quarter of the mean per stride (64 CTAs at 16 bits: ~5 strides of
-  // 23 us, ~1.15x the necessary permutations; 148 CTAs did ~2x), between 32 CTAs and one CTA per SM.
+  // The minimal witness is geometric with mean 2^pow_bits.  Every thread of a stride evaluates its candidate even when
+  // the witness sits at the start of the stride (half a stride of wasted permutations on average), and the stride
+  // after the hit has usually started before the hit is visible (k_pow_search drops it a quarter of the way in): about
+  // 0.8 strides of waste.  With many proofs in flight only the permutation count matters, so the stride is an eighth
+  // of the mean (32 CTAs at 16 bits: ~9 strides of 23 us, ~1.1x the necessary permutations; 64 CTAs without the
+  // in-flight check did 1.37x, 148 CTAs ~2x), between 16 CTAs and one CTA per SM.  P2B_POW_BLOCKS overrides.
   const uint64_t sms = (uint64_t)ctx->sm_count;
-  uint64_t blocks = (((uint64_t)1 << pow_bits) / 4 + 255) / 256;
-  blocks = blocks < 32 ? 32 : blocks > sms ? sms : blocks;
+  static const int force_blocks = [] {
+    const char* e = getenv("P2B_POW_BLOCKS");
+    return e ? atoi(e) : 0;
+  }();
+  uint64_t blocks = (((uint64_t)1 << pow_bits) / 8 + 255) / 256;
+  blocks = blocks < 16 ? 16 : blocks > sms ? sms : blocks;
+  if (force_blocks > 0) blocks = (uint64_t)force_blocks;
   CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
   frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, 0, GL_P, pow_bits, d_best);
   LAUNCH_CHECK(ctx);

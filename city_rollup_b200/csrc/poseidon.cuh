@@ -431,7 +431,11 @@ __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo
 }
 
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).
-__device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
+// `abort_after_first_half()` is evaluated once, after the first four full rounds (about a quarter of the work); when
+// it returns true the permutation is abandoned (state undefined) and false is returned — the proof-of-work search
+// drops candidates this way that another thread's hit has made irrelevant in the meantime.
+template <class Abort>
+__device__ __forceinline__ bool permute_nc_abortable(uint64_t (&s)[12], Abort&& abort_after_first_half) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_nc(s[i], RC[i]);  // RC entries are canonical
 #ifdef P2B_POSEIDON_V3  // the previous schedule (tuning builds: tools/poseidon_bench.cu)
@@ -454,6 +458,7 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
 #pragma unroll 1
     for (int i = 0; i < 4; i++) full_round_v6(s, RC6 + 24 * (26 * half + i));
     if (half == 0) {
+      if (abort_after_first_half()) return false;
       double zlo[12], zhi[12];
       zlo[0] = zhi[0] = 0.;
 #pragma unroll
@@ -468,6 +473,10 @@ __device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
     }
   }
 #endif
+  return true;
+}
+__device__ __forceinline__ void permute_nc(uint64_t (&s)[12]) {
+  permute_nc_abortable(s, [] { return false; });
 }
 
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
