@@ -43,8 +43,10 @@ import numpy as np  # noqa: E402
 
 DEGREE_BITS, N_WIRES, RATE_BITS, CAP_HEIGHT = 12, 135, 3, 4
 FP = dict(rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, reduction_arity_bits=[4, 4])
-CONTEXTS = 16         # worker threads (p2b contexts / CUDA streams) per GPU: 8 -> 704, 12 -> 744, 16 -> 751, 24 -> 766 proofs/s
-PROOFS_PER_STEP = 64  # 4 jobs per worker and step
+# worker threads (p2b contexts / CUDA streams) per GPU; profiles/r02_bench_v12_c*.json: 12 -> 845, 16 -> 870, 20 -> 879,
+# 24 -> 890, 32 -> 895 proofs/s (workers sleep in a blocking sync while their proof runs: ~0.3 ms of host CPU per proof)
+CONTEXTS = 24
+PROOFS_PER_STEP = 96  # 4 jobs per worker and step
 METRIC = "proofs/sec on qbench-shaped worker jobs (2^12 rows x 135 wires, City op-circuit gate set, 28 queries); LDE+Merkle ms at 2^20 rows x 135 cols beside it"
 UNIT = "proofs/s"
 WORKLOAD = ("City Rollup worker proof jobs: CircuitData::prove at 2^12 rows x 135 wires, 21 gate kinds (add_city_common_gates + "
@@ -64,7 +66,7 @@ def config_dict():
             "pow_bits": 16, "queries": 28, "arity_bits": [4, 4], "gate_set": "city (21 kinds, 6 selector groups)",
             "proofs_per_step": PROOFS_PER_STEP, "contexts_per_gpu": CONTEXTS,
             "sharding": "independent proof jobs per GPU, no data-path collective",
-            "l2": "16 proofs in flight x ~60 MB of LDE / coefficient / digest working set each > 126 MB L2; nothing is reused across proofs"}
+            "l2": "24 proofs in flight x ~60 MB of LDE / coefficient / digest working set each > 126 MB L2; nothing is reused across proofs"}
 
 
 def perms_per_proof(circ_desc):

@@ -54,8 +54,25 @@ def run_gpu(ctx, m, circ, betas, gammas, alphas, rate_bits, cap_height):
     (12, ALL_GATES, FULL_GROUPS, 25, 4),
 ])
 def test_plonk_stages_match_oracle(ctx, m, degree_bits, gates, groups, seed, cap_height):
-    rate_bits = 3
-    circ = R.SyntheticCircuit(degree_bits, gates, groups, seed)
+    check_plonk_stages(ctx, m, R.SyntheticCircuit(degree_bits, gates, groups, seed), 3, cap_height, seed)
+
+
+@pytest.mark.parametrize("degree_bits,qdf,rate_bits,gates,groups,seed", [
+    # quotient_degree_factor 4: only the degree-2 gates can be evaluated on a sub-coset (2n of 4n points), the
+    # degree-3 ArithmeticGate is evaluated at every point
+    (6, 4, 3, [(R.GATE_CONSTANT, 2, 0), (R.GATE_BASE_SUM, 10, 0), (R.GATE_ARITHMETIC, 20, 0)], [(0, 2), (2, 3)], 41),
+    # quotient_degree_factor 2: no sub-coset is smaller than the quotient coset
+    (5, 2, 3, [(R.GATE_CONSTANT, 2, 0), (R.GATE_PUBLIC_INPUT, 0, 0)], [(0, 1), (1, 2)], 42),
+    # LDE rate 16 with quotient_degree_factor 8: the quotient coset is itself a sub-coset of the batches' LDE
+    (6, 8, 4, ALL_GATES, FULL_GROUPS, 43),
+])
+def test_plonk_stages_other_degree_factors(ctx, m, degree_bits, qdf, rate_bits, gates, groups, seed):
+    circ = R.SyntheticCircuit(degree_bits, gates, groups, seed, quotient_degree_factor=qdf)
+    check_plonk_stages(ctx, m, circ, rate_bits, 2, seed)
+
+
+def check_plonk_stages(ctx, m, circ, rate_bits, cap_height, seed):
+    degree_bits = circ.degree_bits
     rng = random.Random(seed + 1)
     nch = circ.num_challenges
     betas, gammas, alphas = ([rng.randrange(P) for _ in range(nch)] for _ in range(3))

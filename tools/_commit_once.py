@@ -17,8 +17,12 @@ t = torch.empty((n_cols, 1 << log_n), dtype=torch.int64, device="cuda")
 t.random_(0, 2**62, generator=g)
 torch.cuda.synchronize()
 for i in range(reps):
+    c.profile_enable(True)
+    c.profile_read()
     c.timer_start()
     b = m.PolynomialBatch.from_values_device(c, t.data_ptr(), n_cols, log_n, 3, 4)
     ms = c.timer_stop_ms()
+    st, cnt = c.profile_read()
+    c.profile_enable(False)
     b.free()
-    print("commit 2^%d x %d: %.3f ms" % (log_n, n_cols, ms), file=sys.stderr)
+    print("commit 2^%d x %d: %.3f ms  stages %s" % (log_n, n_cols, ms, {k: round(v, 3) for k, v in st.items() if v}), file=sys.stderr)
