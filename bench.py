@@ -450,7 +450,7 @@ def run_cuda(args):
             "traffic": traffic.get("k_leaf_hash_colmajor_m1"),
             "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM, "permutations_per_proof_in_kernel": pp["leaf"],
             "ms_per_proof_in_kernel": leaf_ms, "launches_per_proof": leaf_launches,
-            "timed": "CUDA events around the stage on the context's stream, one worker alone (the kernels of 8 workers overlap)",
+            "timed": "CUDA events around the stage on the context's stream, one worker alone (in the timed region the kernels of all workers overlap)",
             "share_of_single_worker_proof": leaf_ms / best,
             "whole_proof": {"permutations_per_proof": pp, "achieved_gperm_s": pp["total"] * value / world / 1e9,
                             "int32_frac_all_permutations": pp["total"] * value / world * OPS_PER_PERM / 1e9 / int_peak,
