@@ -34,10 +34,10 @@ using gl::ext2;
 constexpr int SUB_LOG = 9;
 // Levels with at most this many nodes in a CTA go to one warp per node.  A warp-cooperative permutation finishes in a
 // third of the time of a one-thread permutation but executes ~10x the instructions (5.5k warp instructions against
-// 16.5k thread instructions = 516 warp-instruction equivalents), and a worker GPU is throughput bound (8+ proofs in
-// flight): with 16 (every level below a full warp of nodes) the cooperative nodes were 2 % of a tree's nodes and 44 % of
-// k_tree_subtree's instructions.  4 keeps the last three levels of every subtree short.
-constexpr uint32_t COOP_NODES = 4;
+// 16.5k thread instructions = 516 warp-instruction equivalents).  The fused kernel only sees the last 2048 digests of
+// a tree (p2b.cu build_levels), so its cooperative nodes are a negligible share of a proof's instructions and the
+// threshold is set for latency: 16 (two permutations per warp: 15 us against 23).
+constexpr uint32_t COOP_NODES = 16;
 
 __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, uint32_t n_levels, uint64_t* __restrict__ levels,
                                               size_t n_leaves, uint32_t first_level, size_t node0) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, 
       }
       __syncthreads();
     } else {
-      // warp-cooperative: node w, w + n_warps, ...  (n_par <= COOP_NODES <= n_warps: one node per warp)
+      // warp-cooperative: node w, w + n_warps, ...  (n_par <= COOP_NODES <= 2 n_warps: at most two nodes per warp)
       uint64_t res[2];
       uint32_t cnt = 0;
       for (uint32_t node = warp; node < n_par; node += n_warps) {
@@ -84,7 +84,10 @@ __device__ __forceinline__ void climb_in_smem(uint64_t (*sm)[4], uint32_t n_in, 
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+#ifndef P2B_TREE_MINB
+#define P2B_TREE_MINB 1
+#endif
+__global__ void __launch_bounds__(256, P2B_TREE_MINB)
 k_tree_subtree(uint64_t* __restrict__ levels, size_t n_leaves, uint32_t first_level, uint32_t log_first, uint32_t L_rem,
                unsigned int* __restrict__ counter) {
   __shared__ uint64_t sm[1 << SUB_LOG][4];

@@ -912,9 +912,20 @@ static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
   uint32_t L = t->log_leaves - t->cap_height;
   if (fused_tree() && L > 0) {
     // wide levels at full throughput (one permutation per thread, the whole GPU), then everything from a level of at
-    // most 2^15 digests up to the cap in ONE launch (fusedk::k_tree_subtree)
+    // most 2^fuse_log digests up to the cap in ONE launch (fusedk::k_tree_subtree)
+    // P2B_TREE_FUSE_LOG: widest level (log2 digests) handed to the fused kernel.  A subtree CTA lives for all its
+    // dependent levels (23 us each) with ever fewer busy warps while it holds 40k registers: an SM that hosts one cannot
+    // host a leaf-hash CTA.  With many proofs in flight that costs throughput — measured at the City shape, 24 workers
+    // (profiles/r02_tree_fuse_sweep.txt): fused from 2^15 digests 891 proofs/s, 2^13 952, 2^11 969, 2^9 969 — and one proof
+    // alone loses little (271 -> 258 proofs/s for 12 more launches).  Default 2^11: one launch per level at full
+    // throughput down to 2048 digests, then four subtree CTAs.
+    static const uint32_t fuse_log = [] {
+      const char* e = getenv("P2B_TREE_FUSE_LOG");
+      const int v = e ? atoi(e) : 11;
+      return (uint32_t)(v < 1 ? 1 : v > 24 ? 24 : v);
+    }();
     uint32_t i = 0;
-    while (i < L && (t->n_leaves >> i) > ((size_t)1 << 15)) {
+    while (i < L && (t->n_leaves >> i) > ((size_t)1 << fuse_log)) {
       const size_t n_par = t->n_leaves >> (i + 1);
       hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
                                                                       t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);

@@ -148,7 +148,7 @@ def test_replayed_plans_equal_the_oracle(m, degree_bits, fp):
     if os.environ.get("P2B_GRAPH", "1") != "0":
         assert info["failed"] == 0, info
         assert info["ready"] == 4, info  # 2 circuits x (host, device) witness
-        assert 0 < info["kernels_per_launch"] <= 60, info
+        assert 0 < info["kernels_per_launch"] <= 72, info  # 58 with the Merkle trees fused from 2^15 digests; 70 since they are fused from 2^11 (+9 % proofs/s, p2b.cu build_levels)
     for circ, cd, cs, pd in cases:
         pd.free()
         cs.free()
