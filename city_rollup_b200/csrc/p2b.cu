@@ -908,6 +908,15 @@ static bool fused_tree() {
   }();
   return v;
 }
+// threads per CTA of the one-permutation-per-thread hash kernels (P2B_HASH_BLOCK: 64 / 128 / 256, tuning)
+static unsigned hash_block() {
+  static const unsigned v = [] {
+    const char* e = getenv("P2B_HASH_BLOCK");
+    const int b = e ? atoi(e) : 256;
+    return (unsigned)(b == 64 || b == 128 ? b : 256);
+  }();
+  return v;
+}
 static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
   uint32_t L = t->log_leaves - t->cap_height;
   if (fused_tree() && L > 0) {
@@ -927,7 +936,7 @@ static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
     uint32_t i = 0;
     while (i < L && (t->n_leaves >> i) > ((size_t)1 << fuse_log)) {
       const size_t n_par = t->n_leaves >> (i + 1);
-      hashk::k_tree_level<<<cdiv(n_par, 256), 256, 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
+      hashk::k_tree_level<<<cdiv(n_par, hash_block()), hash_block(), 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
                                                                       t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);
       LAUNCH_CHECK(ctx);
       i++;
@@ -967,7 +976,7 @@ static int tree_from_colmajor(p2b_ctx* ctx, p2b_tree* t, const uint64_t* d_data,
   int rc;
   if ((rc = dmalloc(ctx, &t->d_levels, 4 * levels_len(n_leaves, cap_height)))) return rc;
   stage_begin(ctx, ST_LEAF);
-  hashk::k_leaf_hash_colmajor<<<cdiv(n_leaves, 256), 256, 0, ctx->stream>>>(d_data, n_leaves, (uint32_t)n_cols, n_leaves,
+  hashk::k_leaf_hash_colmajor<<<cdiv(n_leaves, hash_block()), hash_block(), 0, ctx->stream>>>(d_data, n_leaves, (uint32_t)n_cols, n_leaves,
                                                                           t->d_levels);
   LAUNCH_CHECK(ctx);
   stage_begin(ctx, ST_TREE);

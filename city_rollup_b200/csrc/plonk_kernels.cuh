@@ -391,7 +391,7 @@ __device__ void eval_poseidon_gate(const Vars& v, Acc& acc) {
       acc.push(gl::sub_nc(s0, in0));
       s0 = in0;
       uint64_t mid_computed = 0;
-      poseidon::partial_round_pair_v6_hook(s0, zlo, zhi, 4 + r, vz, [&](uint64_t x) {
+      poseidon::P2B_PAIR_HOOK(s0, zlo, zhi, 4 + r, vz, [&](uint64_t x) {
         mid_computed = x;
         return in1;
       });

@@ -425,9 +425,119 @@ __device__ __forceinline__ void partial_round_pair_v6_hook(uint64_t& s0, double 
   }
 }
 
+// ---- Q schedule: the two MDS layers of a partial-round pair as ONE application of M^2 ---------------------------
+// With t = the state after the S-box of round r, u = M t + c_A, x2 = u_0 and y2 = x2^7 (or whatever `mid` puts in its
+// place), the state after round r + 1 is  M (u + e_0 (y2 - u_0)) + c_B = M^2 t + col_0(M) (y2 - u_0) + (M c_A + c_B),
+// and with M = C + 8 e_0 e_0^T (C the circulant), limb set by limb set:
+//     out_i = (C^2 t)_i + C[i][0] w + 8 [i == 0] y2 + const_i,        w = 8 t_0 + y2 - X2,  X2 = row 0 of the first layer.
+// C^2 is the circulant of C * C (row sum 2^16: 33-bit limbs stay below 2^50) and splits exactly like C:
+//     D2 = [5252, 5904, 5072, 4988, 6384, 5168], E2 = [54, -72, -486, 252, -162, -36],
+//     (D2[j] + D2[j+3]) / 2 = [5120, 6144, 5120], (D2[j] - D2[j+3]) / 2 = [132, -240, -48];
+// C[i][0] w enters the P / M chains with the coefficients lane 0 has in a plain C layer.  Rows 1..5 of the first layer are
+// never formed: 127 FP64 instructions per limb set and pair instead of 171 (the permutation kernels are bound by the
+// issue path FP64 shares with the wide integer multiplies).  Tables and the exact-arithmetic model:
+// tools/gen_poseidon_v6_tables.py (permute_q; every intermediate checked against 2^53, limbs at the corners of their ranges).
+__constant__ unsigned long long RCQ[308] = {
+#include "poseidon_rc_q.inc"
+};
+
+struct QLimbState {
+  double p[6], m[6], t0u, y0;
+};
+// first half: p / m of the twelve inputs, X2 = row 0 of the first layer (biased: 2^52 + row sum), t_0 without its bias
+__device__ __forceinline__ void q_first(double b0, const double (&z)[12], const unsigned long long* __restrict__ init,
+                                        QLimbState& q) {
+  constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
+  constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
+  pm_from_biased(b0, z[6], q.p[0], q.m[0]);
+#pragma unroll
+  for (int k = 1; k < 6; k++) pm_from_biased(z[k], z[k + 6], q.p[k], q.m[k]);
+  double P = __longlong_as_double((long long)init[0]);
+  double M = __longlong_as_double((long long)init[1]);
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    P = fma(Dh[k] + (k == 0 ? 2. : 0.), q.p[k], P);
+    M = fma(Eh[k] + (k == 0 ? 2. : 0.), q.m[k], M);
+  }
+  P = fma(2., q.m[0], P);  // the diagonal 8 t_0 = 4 p_0 + 4 m_0, half on each chain
+  M = fma(2., q.p[0], M);
+  q.y0 = dadd(P, M);
+  q.t0u = dsub(b0, 4503599627370496.0);
+}
+// second half: b0 = the biased limb of y2 -> the twelve biased row sums of the pair
+__device__ __forceinline__ void q_second(double b0, const QLimbState& q, const unsigned long long* __restrict__ init,
+                                         double (&y)[12]) {
+  constexpr double E2[6] = {54., -72., -486., 252., -162., -36.};
+  constexpr double H2[6] = {132., -240., -48., -132., 240., 48.};
+  constexpr double Dh[6] = {15., 14., 40., 17., 18., 24.};
+  constexpr double Eh[6] = {2., 1., 1., -1., -16., 4.};
+  const double d = dsub(b0, q.y0);               // y2 - X2: the 2^52 biases cancel
+  const double w = fma(8., q.t0u, d);
+  const double y2u = dsub(b0, 4503599627370496.0);
+  const double u0 = dadd(q.p[0], q.p[3]), v0 = dsub(q.p[0], q.p[3]);
+  const double u1 = dadd(q.p[1], q.p[4]), v1 = dsub(q.p[1], q.p[4]);
+  const double u2 = dadd(q.p[2], q.p[5]), v2 = dsub(q.p[2], q.p[5]);
+  const double U = dadd(dadd(u0, u1), u2);
+  const double uu[3] = {u0, u1, u2}, vv[3] = {v0, v1, v2};
+  double P[6], M[6];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double S = fma(5120., U, __longlong_as_double((long long)init[2 + r]));
+    S = fma(1024., uu[(r + 1) % 3], S);
+    double T = __longlong_as_double((long long)init[5 + r]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) T = fma(H2[(k - r + 6) % 6], vv[k], T);
+    P[r] = dadd(S, T);
+    P[r + 3] = dsub(S, T);
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    double Mr = __longlong_as_double((long long)init[8 + r]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int j = (k - r + 12) % 12;
+      Mr = fma(j < 6 ? E2[j] : -E2[j - 6], q.m[k], Mr);
+    }
+    // the rank-1 term C[i][0] w: lane 0's coefficients in a plain C layer
+    const int j0 = (12 - r) % 12;
+    P[r] = fma(Dh[j0 % 6], w, P[r]);
+    M[r] = fma(j0 < 6 ? Eh[j0] : -Eh[j0 - 6], w, Mr);
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    y[r] = dadd(P[r], M[r]);
+    y[r + 6] = dsub(P[r], M[r]);
+  }
+  y[0] = fma(8., y2u, y[0]);
+}
+
+// Two consecutive partial rounds r, r + 1 (r = 4, 6, .., 24), same contract as partial_round_pair_v6_hook.
+template <class MidHook>
+__device__ __forceinline__ void partial_round_pair_q_hook(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
+                                                          uint32_t vz, MidHook&& mid) {
+  const unsigned long long* __restrict__ init = RCQ + 28 * (((r - 4) >> 1) + vz);
+  double b0l, b0h;
+  QLimbState ql, qh;
+  sbox7_limbs(s0, b0l, b0h);
+  q_first(b0l, zlo, init, ql);
+  q_first(b0h, zhi, init + 14, qh);
+  sbox7_limbs(mid(fold_f64_b1(ql.y0, qh.y0)), b0l, b0h);
+  double ylo[12], yhi[12];
+  q_second(b0l, ql, init, ylo);
+  q_second(b0h, qh, init + 14, yhi);
+  s0 = fold_f64_b1(ylo[0], yhi[0]);
+#pragma unroll
+  for (int i = 1; i < 12; i++) lazy_fold(ylo[i], yhi[i], zlo[i], zhi[i]);
+}
+
+#ifdef P2B_POSEIDON_PAIR_AB  // the round-1 pair (two chained layers), for A/B measurements
+#define P2B_PAIR_HOOK partial_round_pair_v6_hook
+#else
+#define P2B_PAIR_HOOK partial_round_pair_q_hook
+#endif
 __device__ __forceinline__ void partial_round_pair_v6(uint64_t& s0, double (&zlo)[12], double (&zhi)[12], int r,
                                                       uint32_t vz) {
-  partial_round_pair_v6_hook(s0, zlo, zhi, r, vz, [](uint64_t x) { return x; });
+  P2B_PAIR_HOOK(s0, zlo, zhi, r, vz, [](uint64_t x) { return x; });
 }
 
 // In-place permutation.  Inputs: any u64.  Outputs: u64 congruent mod p (NOT canonical).

@@ -176,6 +176,25 @@ def test_v6_poseidon_schedule_model_and_tables():
         got = [x % g.P for x in g.permute_v6(st)]
         assert got == g.permute_ref(st)
         assert got == [int(x) for x in O.permute([x % g.P for x in st])]
+        # the Q schedule (a partial-round pair as one application of M^2): what permute_nc runs
+        assert [x % g.P for x in g.permute_q(st)] == got
+    # ... and with the S-box input of the second round of every pair replaced (the PoseidonGate evaluator's hook): the
+    # pair must equal two plain rounds with the same replacement
+    for _ in range(20):
+        r = rng.choice(range(4, 26, 2))
+        s0, vals, repl = rng.getrandbits(64), [rng.getrandbits(64) for _ in range(11)], rng.randrange(g.P)
+        lz = [None] + [((v & 0xFFFFFFFF) + g.OL, v >> 32) for v in vals]
+        st = [s0 % g.P] + [v % g.P for v in vals]
+        mds = lambda s: [(sum(g.CIRC[(k - i) % 12] * s[k] for k in range(12)) + (8 * s[0] if i == 0 else 0)) % g.P for i in range(12)]
+        st[0] = pow(st[0], 7, g.P)
+        st = [(x + c) % g.P for x, c in zip(mds(st), g.RC[12 * (r + 1):12 * (r + 2)])]
+        computed_x2 = st[0]
+        st[0] = pow(repl, 7, g.P)
+        st = [(x + c) % g.P for x, c in zip(mds(st), g.RC[12 * (r + 2):12 * (r + 3)])]
+        seen = []
+        s0n, lzn = g.pair_q(s0, lz, r, mid=lambda x: (seen.append(x), repl)[1])
+        assert seen[0] % g.P == computed_x2
+        assert [s0n % g.P] + [(lzn[i][0] - g.OL + (lzn[i][1] << 32)) % g.P for i in range(1, 12)] == st
     # committed table == generated table
     committed = open(os.path.join(root, "city_rollup_b200", "csrc", "poseidon_rc_v6.inc")).read()
     words = [int(x, 16) for x in __import__("re").findall(r"0x([0-9a-f]{16})ull", committed)]
@@ -185,6 +204,14 @@ def test_v6_poseidon_schedule_model_and_tables():
             for rr in range(6):
                 a, b = g.INITS[r][limb][rr]
                 want += [g.bits(a), g.bits(b)]
+    assert words == want
+    committed = open(os.path.join(root, "city_rollup_b200", "csrc", "poseidon_rc_q.inc")).read()
+    words = [int(x, 16) for x in __import__("re").findall(r"0x([0-9a-f]{16})ull", committed)]
+    want = []
+    for r in range(4, 26, 2):
+        x2, oi = g.Q_INITS[r]
+        for limb in range(2):
+            want += [g.bits(v) for v in [x2[limb][0], x2[limb][1]] + [oi[limb][rr][0] for rr in range(6)] + [oi[limb][rr][1] for rr in range(6)]]
     assert words == want
     # FP64 bounds at the corners of the limb ranges (asserts inside the model)
     real_sbox, real_lazy = g.sbox_limbs, g.lazy_fold
@@ -198,5 +225,6 @@ def test_v6_poseidon_schedule_model_and_tables():
         g.lazy_fold = corner_lazy
         for _ in range(200):
             g.permute_v6([0] * 12)
+            g.permute_q([0] * 12)
     finally:
         g.sbox_limbs, g.lazy_fold = real_sbox, real_lazy

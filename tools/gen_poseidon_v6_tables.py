@@ -18,6 +18,17 @@ Layer kinds (round r = the round whose MDS layer it is; the constants of round r
                          biased output, lane 0 S-box limbs
 Output index: ((r * 2 + limb) * 6 + row_pair) * 2 + {0: P_init, 1: M_init}, as double bit patterns.
 
+Q schedule (poseidon_rc_q.inc; what permute_nc runs): the two MDS layers of a partial-round pair (r, r + 1) as ONE
+application of M^2.  With t = the state after the S-box of round r, u = M t + c_A, x2 = u_0, y2 = x2^7:
+    state after round r + 1 = M (u + e_0 (y2 - u_0)) + c_B = M^2 t + col_0(M) (y2 - u_0) + (M c_A + c_B)
+and M = C + 8 e_0 e_0^T (C the circulant) gives, limb set by limb set,
+    out_i = (C^2 t)_i + C[i][0] w + 8 [i = 0] y2 + const_i,     w = 8 t_0 + y2 - X2,   X2 = row 0 of layer A (as before).
+C^2 is the circulant of C * C = [5306, 5832, 4586, 5240, 6222, 5132, 5198, 5976, 5558, 4736, 6546, 5204] (row sum 2^16) and
+splits exactly like C: D2 = [5252, 5904, 5072, 4988, 6384, 5168], E2 = [54, -72, -486, 252, -162, -36], and once more
+(D2[j] + D2[j+3]) / 2 = [5120, 6144, 5120], (D2[j] - D2[j+3]) / 2 = [132, -240, -48]; C[i][0] w enters the P / M chains with
+the coefficients lane 0 has in a plain C layer.  127 FP64 instructions per limb set and pair instead of 171: rows 1..5
+of layer A are never formed.  Table: per pair and limb set [P0x, M0x, sI[0..2], tI[0..2], M_init[0..5]].
+
 `python tools/gen_poseidon_v6_tables.py --check N` runs the model on N random states against the plain permutation.
 """
 import os
@@ -348,6 +359,192 @@ def permute_v6(state):
     return s
 
 
+
+# ---- Q schedule: a partial-round pair as one application of M^2 -----------------------------------------------
+C2 = [sum(CIRC[a] * CIRC[(m - a) % 12] for a in range(12)) for m in range(12)]
+D2 = [(C2[j] + C2[j + 6]) // 2 for j in range(6)]
+E2 = [(C2[j] - C2[j + 6]) // 2 for j in range(6)]
+S2 = [(D2[j] + D2[j + 3]) // 2 for j in range(3)]
+H2 = [(D2[j] - D2[j + 3]) // 2 for j in range(3)]
+H2 = H2 + [-x for x in H2]
+assert all((C2[j] + C2[j + 6]) % 2 == 0 for j in range(6)) and all((D2[j] + D2[j + 3]) % 2 == 0 for j in range(3))
+assert S2[0] == S2[2]  # S[r] = S2[0] (u_0 + u_1 + u_2) + (S2[1] - S2[0]) u_{(r+1) mod 3}
+ZQ_LO, ZQ_HI = 2**49, 2**49 + 2**32  # lifts of the output row sums (the rank-1 term - C[i][0] X2 can reach -2^48.6)
+
+
+def mds_entry(i, k):
+    return CIRC[(k - i) % 12] + (8 if i == 0 and k == 0 else 0)
+
+
+def coef2(r, k):
+    j = (k - r + 12) % 12
+    return D2[j % 6], (E2[j] if j < 6 else -E2[j - 6])
+
+
+def coef_lane0(r):
+    """(d, e) with which lane 0 enters row pair r of a plain C layer (no diagonal)"""
+    j = (0 - r + 12) % 12
+    return DH[j % 6], (EH[j] if j < 6 else -EH[j - 6])
+
+
+def reps_q(v):
+    out = []
+    for j in range(4):
+        w = v + j * P
+        for t in range(8):
+            lo = (w & 0xFFFFFFFF) + (t << 32)
+            hi = (w >> 32) - t
+            if 0 <= hi < 2**34:
+                out.append((lo, hi))
+    return out
+
+
+def q_inits(r):
+    """pair (r, r + 1): ({limb: (P0x, M0x)}, [limb][slot] = (sI / tI, M_init))"""
+    A = INITS[r]  # row pair 0 of the A layer: X2 = y0 = P[0] + M[0]
+    x2 = {limb: (A[limb][0][0] + A[limb][3][0], A[limb][0][1]) for limb in range(2)}
+    K0 = [x2[l][0] + x2[l][1] - TWO52 for l in range(2)]
+    off = [OS] + [OL] * 11
+    cA = [RC[12 * (r + 1) + i] for i in range(12)]
+    cB = [RC[12 * (r + 2) + i] for i in range(12)]
+    Mo0 = sum(mds_entry(0, k) * off[k] for k in range(12))
+    assert (Mo0 + K0[0] + (K0[1] << 32) - cA[0]) % P == 0
+    M2 = [[sum(mds_entry(i, j) * mds_entry(j, k) for j in range(12)) for k in range(12)] for i in range(12)]
+    row_off_lo = [sum(M2[i][k] * off[k] for k in range(12)) + mds_entry(i, 0) * (off[0] - Mo0 - K0[0]) for i in range(12)]
+    row_off_hi = [mds_entry(i, 0) * (-K0[1]) for i in range(12)]
+    row_off_lo[0] += 8 * K0[0]  # the device forms 8 (M t)_0 as 8 (X2 + d) = 8 y2: X2 includes K0
+    row_off_hi[0] += 8 * K0[1]
+    K = [(sum(mds_entry(i, k) * cA[k] for k in range(12)) - mds_entry(i, 0) * cA[0] + cB[i]) % P for i in range(12)]
+    k = [(K[i] - ZQ_LO - (ZQ_HI << 32)) % P for i in range(12)]
+    out = [[None] * 6, [None] * 6]
+    for rr in range(3):
+        best = None
+        for a in reps_q(k[rr]):
+            for b in reps_q(k[rr + 6]):
+                ca = [a[0] + ZQ_LO - row_off_lo[rr], a[1] + ZQ_HI - row_off_hi[rr]]
+                cb = [b[0] + ZQ_LO - row_off_lo[rr + 6], b[1] + ZQ_HI - row_off_hi[rr + 6]]
+                if (ca[0] + cb[0]) % 2 or (ca[1] + cb[1]) % 2:
+                    continue
+                for a3 in reps_q(k[rr + 3]):
+                    for b3 in reps_q(k[rr + 9]):
+                        ca3 = [a3[0] + ZQ_LO - row_off_lo[rr + 3], a3[1] + ZQ_HI - row_off_hi[rr + 3]]
+                        cb3 = [b3[0] + ZQ_LO - row_off_lo[rr + 9], b3[1] + ZQ_HI - row_off_hi[rr + 9]]
+                        if (ca3[0] + cb3[0]) % 2 or (ca3[1] + cb3[1]) % 2:
+                            continue
+                        if any(((ca[l] + cb[l]) // 2 + (ca3[l] + cb3[l]) // 2) % 2 for l in range(2)):
+                            continue
+                        cost = max(a + b + a3 + b3)
+                        if best is None or cost < best[0]:
+                            best = (cost, ca, cb, ca3, cb3)
+        assert best is not None
+        _, ca, cb, ca3, cb3 = best
+        for limb in range(2):
+            pa, ma = (ca[limb] + cb[limb]) // 2 + TWO52, (ca[limb] - cb[limb]) // 2
+            pb, mb = (ca3[limb] + cb3[limb]) // 2 + TWO52, (ca3[limb] - cb3[limb]) // 2
+            out[limb][rr] = ((pa + pb) // 2, ma)       # sI[rr], M_init[rr]
+            out[limb][rr + 3] = ((pa - pb) // 2, mb)   # tI[rr], M_init[rr + 3]
+    return x2, out
+
+
+Q_INITS = {r: q_inits(r) for r in range(4, 26, 2)}
+
+
+def fold_b1(ya, yb):
+    """poseidon::fold_f64_b1 with the range the Q outputs have"""
+    a, b = ya - TWO52, yb - TWO52
+    assert 0 <= a < 2**52 and 2**32 <= b < 2**52
+    a_lo, a_hi, b_lo, b_hi = a & M32, a >> 32, b & M32, b >> 32
+    nb = (2**32 - b_hi) & M32
+    m1 = a_hi + b_hi - 1
+    assert 0 <= m1 < 2**32
+    lo = a_lo + nb
+    cf = lo >> 32
+    lo &= M32
+    hi = b_lo + m1 + cf
+    c = hi >> 32
+    hi &= M32
+    assert c <= 1
+    r = (hi << 32 | lo) + c * EPS
+    assert r <= M64
+    return r
+
+
+def pair_q(s0, lz, r, mid=lambda x: x):
+    """poseidon::partial_round_pair_q: (s0, limb-form lanes 1..11) before round r -> the same before round r + 2"""
+    x2i, oi = Q_INITS[r]
+    l0 = sbox_limbs(s0)
+    y0, pm = [None, None], [None, None]
+    for limb in range(2):
+        v = [l0[limb]] + [lz[i][limb] for i in range(1, 12)]
+        p = [chk53(v[k] + v[k + 6]) for k in range(6)]
+        m = [chk53(v[k] - v[k + 6]) for k in range(6)]
+        pm[limb] = (p, m, v[0])
+        P0, M0 = x2i[limb]
+        for k in range(6):
+            d, e = coef(0, k)
+            P0 = chk53(P0 + d * p[k])
+            M0 = chk53(M0 + e * m[k])
+        P0 = chk53(P0 + 2 * m[0])
+        M0 = chk53(M0 + 2 * p[0])
+        y0[limb] = chk53(P0 + M0)
+        assert TWO52 <= y0[limb] < 2 * TWO52
+    t0 = sbox_limbs(mid(fold_b1(y0[0], y0[1])))
+    outs = [[None] * 12, [None] * 12]
+    for limb in range(2):
+        p, m, t0in = pm[limb]
+        d_ = chk53(t0[limb] - (y0[limb] - TWO52))
+        w = chk53(8 * t0in + d_)
+        u = [chk53(p[k] + p[k + 3]) for k in range(3)]
+        vv = [chk53(p[k] - p[k + 3]) for k in range(3)]
+        U = chk53(chk53(u[0] + u[1]) + u[2])
+        Pn = [None] * 6
+        for rr in range(3):
+            S = chk53(oi[limb][rr][0] + S2[0] * U)
+            S = chk53(S + (S2[1] - S2[0]) * u[(rr + 1) % 3])
+            T = oi[limb][rr + 3][0]
+            for k in range(3):
+                T = chk53(T + H2[(k - rr) % 6] * vv[k])
+            Pn[rr] = chk53(S + T)
+            Pn[rr + 3] = chk53(S - T)
+        Mn = [oi[limb][rr][1] for rr in range(6)]
+        for rr in range(6):
+            for k in range(6):
+                Mn[rr] = chk53(Mn[rr] + coef2(rr, k)[1] * m[k])
+        for rr in range(6):
+            dd, ee = coef_lane0(rr)
+            Pn[rr] = chk53(Pn[rr] + dd * w)
+            Mn[rr] = chk53(Mn[rr] + ee * w)
+        for rr in range(6):
+            outs[limb][rr] = chk53(Pn[rr] + Mn[rr])
+            outs[limb][rr + 6] = chk53(Pn[rr] - Mn[rr])
+        outs[limb][0] = chk53(outs[limb][0] + 8 * t0[limb])
+        for i in range(12):
+            assert TWO52 <= outs[limb][i] < TWO52 + 2**50  # lazy_fold needs b_hi <= OL = 2^18
+    s0n = fold_b1(outs[0][0], outs[1][0])
+    lzn = [None] + [lazy_fold(outs[0][i], outs[1][i]) for i in range(1, 12)]
+    return s0n, lzn
+
+
+def permute_q(state):
+    s = [(x + c) % 2**64 if x + c < 2**64 else (x + c - 2**64 + EPS) for x, c in zip(state, RC[:12])]  # add_nc
+    r = 0
+    while r < 30:
+        if kind(r) == "F":
+            L = [sbox_limbs(x) for x in s]
+            y = mds_plain([a for a, _ in L], [b for _, b in L], r)
+            s = [fold(y[0][i], y[1][i]) for i in range(12)]
+            if r == 3:
+                s0 = s[0]
+                lz = [None] + [((s[i] & M32) + OL, s[i] >> 32) for i in range(1, 12)]
+            r += 1
+        else:
+            s0, lz = pair_q(s0, lz, r)
+            if r + 1 == 25:
+                s = [s0] + [sub_nc(fold_any(TWO52 + lz[i][0], TWO52 + lz[i][1]), OL) for i in range(1, 12)]
+            r += 2
+    return s
+
+
 def permute_ref(state):
     s = [x % P for x in state]
     for r in range(30):
@@ -371,9 +568,10 @@ def main():
         cases = [[0] * 12, [M64] * 12, [P - 1] * 12, [EPS] * 12, [2**32] * 12]
         cases += [[rnd.getrandbits(64) for _ in range(12)] for _ in range(int(sys.argv[2]))]
         for st in cases:
-            got = [x % P for x in permute_v6(st)]
-            assert got == permute_ref(st), st
-        print("v6 model == plain permutation on", len(cases), "states")
+            want = permute_ref(st)
+            assert [x % P for x in permute_v6(st)] == want, st
+            assert [x % P for x in permute_q(st)] == want, st
+        print("v6 model (A / B pairs) and Q model (M^2 pairs) == plain permutation on", len(cases), "states")
         return
     if len(sys.argv) > 2 and sys.argv[1] == "--corners":
         # every FP64 bound (asserts in the model) with the limb-form values pinned to the corners of their ranges
@@ -392,6 +590,7 @@ def main():
         g["sbox_limbs"], g["lazy_fold"] = corner_sbox, corner_lazy
         for _ in range(int(sys.argv[2])):
             permute_v6([0] * 12)
+            permute_q([0] * 12)
         print("FP64 bounds hold on", sys.argv[2], "corner walks")
         return
     path = os.path.join(here, "..", "city_rollup_b200", "csrc", "poseidon_rc_v6.inc")
@@ -407,6 +606,20 @@ def main():
                     f.write("  0x%016xull, 0x%016xull,%s" % (bits(a), bits(b), "\n" if n % 2 == 1 else ""))
                     n += 1
     print(n * 2, "entries ->", path)
+    path = os.path.join(here, "..", "city_rollup_b200", "csrc", "poseidon_rc_q.inc")
+    with open(path, "w") as f:
+        f.write("/* Generated by tools/gen_poseidon_v6_tables.py from poseidon_rc.inc: chain initialisers of the Q schedule (a\n"
+                " * partial-round pair as one application of M^2), per pair (r = 4, 6, .., 24) and limb set (lo, hi):\n"
+                " * P0x, M0x (row 0 of the first layer), sI[0..2], tI[0..2], M_init[0..5]; double bit patterns. */\n")
+        n = 0
+        for r in range(4, 26, 2):
+            x2, oi = Q_INITS[r]
+            for limb in range(2):
+                vals = [x2[limb][0], x2[limb][1]] + [oi[limb][rr][0] for rr in range(6)] + [oi[limb][rr][1] for rr in range(6)]
+                for v in vals:
+                    f.write("  0x%016xull,%s" % (bits(v), "\n" if n % 4 == 3 else ""))
+                    n += 1
+    print(n, "entries ->", path)
 
 
 if __name__ == "__main__":
