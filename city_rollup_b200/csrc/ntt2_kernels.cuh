@@ -203,7 +203,10 @@ __device__ __forceinline__ uint32_t pad16(uint32_t i) { return i + (i >> 4); }
 // MODE 2: MODE 1 + index reversal (n - r) mod n and scaling: plonky2's ifft.
 // grid = (rows per column, n_cols); 256 threads, 16 elements per thread.
 template <int MODE, bool PRESCALE>
-__global__ void __launch_bounds__(256, 3) k_row4096(RowParams P) {
+#ifndef P2B_ROW_MINB
+#define P2B_ROW_MINB 3
+#endif
+__global__ void __launch_bounds__(256, P2B_ROW_MINB) k_row4096(RowParams P) {
   __shared__ uint64_t sm[4096 + 256];
   const uint32_t tid = threadIdx.x;
   const uint32_t blk = tid >> 4, c = tid & 15;
