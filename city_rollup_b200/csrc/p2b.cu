@@ -1058,16 +1058,17 @@ static bool host_ptr_is_pinned(const void* p) {
 
 // Host columns [c0, c1) -> d_dst (column c at d_dst + c * n) on `stream`.  Pinned memory (p2b_host_alloc,
 // cudaHostRegister) goes by direct DMA, one copy per run of contiguous columns; pageable memory is staged through
-// the context's pinned double buffer — one memcpy + one DMA per 8 MiB instead of a synchronous, internally staged
-// cudaMemcpy per column (135 of them for a witness).
+// the context's pinned double buffer: consecutive pageable columns — plonky2's Vec<PolynomialValues>, one allocation per
+// column, wherever they lie — are packed into one half (their destinations are contiguous), one DMA per 8 MiB instead
+// of a synchronous, internally staged cudaMemcpy (or an event wait + DMA) per column.
 static int h2d_cols(p2b_ctx* ctx, cudaStream_t stream, const uint64_t* const* cols, size_t c0, size_t c1, size_t n,
                     uint64_t* d_dst) {
   size_t c = c0;
   while (c < c1) {
     if (!cols[c]) return fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c);
-    size_t e = c + 1;
-    while (e < c1 && cols[e] == cols[e - 1] + n) e++;
     if (host_ptr_is_pinned(cols[c])) {
+      size_t e = c + 1;
+      while (e < c1 && cols[e] == cols[e - 1] + n) e++;
       CU(ctx, cudaMemcpyAsync(d_dst + c * n, cols[c], (e - c) * n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
       // the DMA reads the caller's memory: remember where it ends (the host-input entry points wait for it)
       if (!ctx->ev_h2d) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
@@ -1076,9 +1077,10 @@ static int h2d_cols(p2b_ctx* ctx, cudaStream_t stream, const uint64_t* const* co
       c = e;
       continue;
     }
-    // pageable: pack as many whole columns (or pieces of a long one) as fit into the current half
+    // a run of pageable columns (it ends at the next pinned one): pack whole columns, or pieces of a long one, half by half
     size_t off = 0;  // words already sent of column c
-    while (c < e) {
+    bool run = true;
+    while (run && c < c1) {
       const int h = ctx->upload_half;
       if (!ctx->h_upload[h]) {
         CU(ctx, cudaMallocHost((void**)&ctx->h_upload[h], UPLOAD_HALF_WORDS * sizeof(uint64_t)));
@@ -1088,18 +1090,27 @@ static int h2d_cols(p2b_ctx* ctx, cudaStream_t stream, const uint64_t* const* co
       }
       size_t filled = 0;
       const size_t first_c = c, first_off = off;
-      while (c < e && filled < UPLOAD_HALF_WORDS) {
+      while (c < c1 && filled < UPLOAD_HALF_WORDS) {
+        if (off == 0 && c != first_c) {  // a column the run has not looked at yet
+          if (!cols[c]) return fail(ctx, P2B_ERR_INVALID, "cols[%zu] is null", c);
+          if (host_ptr_is_pinned(cols[c])) {
+            run = false;
+            break;
+          }
+        }
         const size_t take = (n - off) < (UPLOAD_HALF_WORDS - filled) ? (n - off) : (UPLOAD_HALF_WORDS - filled);
         memcpy(ctx->h_upload[h] + filled, cols[c] + off, take * sizeof(uint64_t));
         filled += take;
         off += take;
         if (off == n) c++, off = 0;
       }
-      // the packed words are contiguous in the destination too (column-major, consecutive columns)
-      CU(ctx, cudaMemcpyAsync(d_dst + first_c * n + first_off, ctx->h_upload[h], filled * sizeof(uint64_t),
-                              cudaMemcpyHostToDevice, stream));
-      CU(ctx, cudaEventRecord(ctx->upload_done[h], stream));
-      ctx->upload_half ^= 1;
+      if (filled) {
+        // the packed words are contiguous in the destination too (column-major, consecutive columns)
+        CU(ctx, cudaMemcpyAsync(d_dst + first_c * n + first_off, ctx->h_upload[h], filled * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, stream));
+        CU(ctx, cudaEventRecord(ctx->upload_done[h], stream));
+        ctx->upload_half ^= 1;
+      }
     }
   }
   return P2B_OK;

@@ -209,6 +209,29 @@ def test_pinned_and_pageable_inputs_agree(ctx, m):
     b.free()
 
 
+def test_separately_allocated_and_mixed_host_columns(ctx, m):
+    """plonky2's witness is one allocation per column: consecutive pageable columns are packed into the staging buffer
+    wherever they lie; pinned columns in between go by direct DMA.  Same batch as from one contiguous matrix."""
+    log_n, n_cols = 10, 37
+    base = rand_felts(77, (n_cols, 1 << log_n))
+    keep = [np.zeros(5 + 3 * c, np.uint64) for c in range(n_cols)]  # spread the allocations
+    separate = [base[c].copy() for c in range(n_cols)]
+    pinned = ctx.pinned_empty((4, 1 << log_n))
+    mixed = list(separate)
+    for k, c in enumerate((0, 9, 10, 36)):
+        pinned[k] = base[c]
+        mixed[c] = pinned[k]
+    ref = m.PolynomialBatch.from_values(ctx, base, 3, False, 4)
+    for cols in (separate, mixed):
+        b = m.PolynomialBatch.from_values(ctx, cols, 3, False, 4)
+        assert (b.cap == ref.cap).all()
+        for c in (0, 8, 9, 10, 11, 36):
+            assert (b.coeffs(c) == ref.coeffs(c)).all()
+        b.free()
+    ref.free()
+    del keep
+
+
 def test_batch_config1_shape_bit_exact(ctx, m):
     """BASELINE.json configs[1]: 2^16 rows x 135 wire columns, rate_bits 3, cap_height 4 — the full commit
     against the oracle (coefficients, sampled leaves, paths, cap)."""
