@@ -7,6 +7,7 @@
 //
 // Build: g++ -O2 -std=c++17 -I. tools/prove_bench.cpp -Lcity_rollup_b200 -lp2b -Wl,-rpath,'$ORIGIN/../city_rollup_b200' -lpthread -o tools/prove_bench_cpp
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,9 @@
 #include "tools/prove_case.hpp"
 
 int main(int argc, char** argv) {
+  // more hardware work queues than the default 8: with more worker streams than queues, streams that share a queue
+  // serialise behind each other (bench.py does the same; must be set before CUDA initialises)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   if (argc < 2) {
     fprintf(stderr, "usage: %s case.bin [threads=8] [proofs_per_thread=40] [device=0]\n", argv[0]);
     return 2;

@@ -25,6 +25,7 @@
 //
 // Build: g++ -O2 -std=c++17 -I. tools/qbench_replay.cpp -Lcity_rollup_b200 -lp2b -lpthread -o tools/qbench_replay
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -331,6 +332,9 @@ int plan_only(Block& blk, const char* source) {
 }
 
 int main(int argc, char** argv) {
+  // more hardware work queues than the default 8: with more worker streams than queues, streams that share a queue
+  // serialise behind each other (bench.py does the same; must be set before CUDA initialises)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   const char* case_path = nullptr;
   const char* out_path = nullptr;
   const char* dump_path = nullptr;
