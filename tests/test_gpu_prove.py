@@ -380,3 +380,17 @@ def test_qbench_replay_native_job_loop(ctx, m, tmp_path):
         ids = {b["job_id"] for b in bench}
         assert len(ids) == 2 * 43 and all(len(i) == 48 and i.startswith("00") for i in ids)
         assert all(isinstance(b["duration"], int) for b in bench)
+
+
+@pytest.mark.parametrize("env", [{"P2B_TREE_FUSE_LOG": "15"}, {"P2B_TREE_FUSE_LOG": "1"}, {"P2B_QUOT_EXT": "0"},
+                                 {"P2B_GRAPH": "0"}, {"P2B_HASH_BLOCK": "128", "P2B_POW_BLOCKS": "3"}])
+def test_tuning_knobs_do_not_change_results(env):
+    """the environment knobs of INTEGRATION.md select other launch structures (Merkle levels fused from 2^15 digests /
+    not at all, every gate at every point, no prove plans, other CTA sizes): smoke() — a commit and a complete proof,
+    both against the oracle, the proof through the restated verifier — must pass under each of them"""
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT,
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
