@@ -758,14 +758,16 @@ struct QuotientParams {
 // group 1 + g is gate g.  A point's work is a long dependent instruction stream (the PoseidonGate alone is a whole
 // permutation), and one thread per point leaves a 2^12-row proof with 7 warps per SM; splitting by term group puts
 // (1 + n_gates) times as many independent streams in flight.  Each group writes its alpha-weighted sum to
-// parts[group][challenge][point]; k_quotient_combine adds them (field addition is exact, so the order is irrelevant)
+// parts[group][challenge][leaf]; k_quotient_combine adds them (field addition is exact, so the order is irrelevant)
 // and divides by Z_H.
-// The groups are evaluated by THREE kernels, so that each gets the register budget its code needs (one kernel for
+// The groups are evaluated by separate kernels, so that each gets the register budget its code needs (one kernel for
 // everything had to live in 64 registers and spilled ~2 KB per thread in the widest gates):
-//   k_quotient_perm            grid (lde_size / 128, 1)          the permutation argument
-//   k_quotient_gates<false>    grid (lde_size / 128, n_light)    gates whose evaluators are short loops over wires
-//   k_quotient_gates<true>     grid (lde_size / 128, n_heavy)    Poseidon, PoseidonMds, RandomAccess, CosetInterpolation
-//                                                                (state arrays: 12-element permutation state, 64 items)
+//   k_quotient_perm                 grid (lde_size / 128, 1)          the permutation argument
+//   k_quotient_gates<false, false>  grid (lde_size / 128, n_light)    light gates evaluated at every point
+//   k_quotient_gates<true, false>   grid (lde_size / 128, n_heavy)    Poseidon, PoseidonMds, RandomAccess, CosetInterpolation
+//                                                                     (state arrays: 12-element permutation state, 64 items)
+//   k_quotient_gates<false, true>   grid (D n / 128, n_ext[D])        gates of constraint degree <= D in {2, 4}: the first D n
+//                                                                     leaves only, unfiltered, extended by NTT (see there)
 // gate_list[blockIdx.y] = index of the gate in P.gates.
 __device__ __forceinline__ bool gate_is_heavy(uint32_t kind) {
   return kind == GATE_POSEIDON || kind == GATE_POSEIDON_MDS || kind == GATE_RANDOM_ACCESS || kind == GATE_COSET_INTERPOLATION;
