@@ -1,1 +1,1 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python tools/_config3.py 2>&1 | tail -8
