@@ -246,10 +246,59 @@ struct ext2 {
 };
 __device__ __forceinline__ ext2 ext_add(ext2 a, ext2 b) { return {add(a.c0, b.c0), add(a.c1, b.c1)}; }
 __device__ __forceinline__ ext2 ext_sub(ext2 a, ext2 b) { return {sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+// a0 * b0 + a1 * b1 mod p with ONE reduction (any u64 inputs, canonical result): the two 128-bit products are summed as a
+// 129-bit integer x4:x3:x2:x1:x0 (2^128 = -2^32 mod p takes care of x4).  39 instructions instead of the 59 of
+// add(mul, mul); exact integer arithmetic, so the field element is the same.
+__device__ __forceinline__ uint64_t dot2(uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1) {
+  uint32_t r0, r1, x4;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,x2,x3,m,tl,th;\n\t"
+      "mul.lo.u32 x0, %3, %5;\n\t"
+      "mul.hi.u32 x1, %3, %5;\n\t"
+      "mul.lo.u32 x2, %4, %6;\n\t"
+      "mul.hi.u32 x3, %4, %6;\n\t"
+      "mad.lo.cc.u32 x1, %3, %6, x1;\n\t"
+      "madc.hi.cc.u32 x2, %3, %6, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      "mad.lo.cc.u32 x1, %4, %5, x1;\n\t"
+      "madc.hi.cc.u32 x2, %4, %5, x2;\n\t"
+      "addc.u32 x3, x3, 0;\n\t"
+      // + a1 * b1 (the accumulate pattern of plonk::Acc::add_product)
+      "mad.lo.cc.u32 x0, %7, %9, x0;\n\t"
+      "madc.hi.cc.u32 x1, %7, %9, x1;\n\t"
+      "madc.lo.cc.u32 x2, %8, %10, x2;\n\t"
+      "madc.hi.cc.u32 x3, %8, %10, x3;\n\t"
+      "addc.u32 %2, 0, 0;\n\t"
+      "mad.lo.cc.u32 x1, %7, %10, x1;\n\t"
+      "madc.hi.cc.u32 x2, %7, %10, x2;\n\t"
+      "addc.cc.u32 x3, x3, 0;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      "mad.lo.cc.u32 x1, %8, %9, x1;\n\t"
+      "madc.hi.cc.u32 x2, %8, %9, x2;\n\t"
+      "addc.cc.u32 x3, x3, 0;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      // low 128 bits: exactly mul_nc's reduction
+      "sub.cc.u32 tl, x0, x3;\n\t"
+      "subc.cc.u32 th, x1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 tl, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      "mad.lo.cc.u32 tl, x2, 0xFFFFFFFF, tl;\n\t"
+      "madc.hi.cc.u32 th, x2, 0xFFFFFFFF, th;\n\t"
+      "addc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, tl, m;\n\t"
+      "subc.u32 th, th, 0;\n\t"
+      "add.u32 %1, th, m;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1), "=&r"(x4)  // x4 is written while inputs are still to be read: early clobber
+      : "r"((uint32_t)a0), "r"((uint32_t)(a0 >> 32)), "r"((uint32_t)b0), "r"((uint32_t)(b0 >> 32)), "r"((uint32_t)a1),
+        "r"((uint32_t)(a1 >> 32)), "r"((uint32_t)b1), "r"((uint32_t)(b1 >> 32)));
+  // + x4 * 2^128 = - x4 * 2^32 (the sum of two products is below 2^129: x4 <= 1)
+  return sub(canon(pack(r0, r1)), pack(0u, x4));
+}
 __device__ __forceinline__ ext2 ext_mul(ext2 a, ext2 b) {
-  uint64_t c0 = add(mul(a.c0, b.c0), mul(7, mul(a.c1, b.c1)));
-  uint64_t c1 = add(mul(a.c0, b.c1), mul(a.c1, b.c0));
-  return {c0, c1};
+  // c0 = a0 b0 + 7 a1 b1, c1 = a0 b1 + a1 b0: two dot products with one reduction each
+  return {dot2(a.c0, b.c0, mul_nc(a.c1, b.c1), 7), dot2(a.c0, b.c1, a.c1, b.c0)};
 }
 __device__ __forceinline__ ext2 ext_scale(ext2 a, uint64_t s) { return {mul(a.c0, s), mul(a.c1, s)}; }
 

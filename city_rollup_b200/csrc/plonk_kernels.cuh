@@ -291,9 +291,8 @@ struct Vars {
 // prod_{x<4} (limb - x) = t (t + 2) with t = limb (limb - 3): two multiplications instead of three, the first a
 // square.  The result is congruent to the product but NOT canonical — it only ever goes to Acc::push.
 __device__ __forceinline__ uint64_t limb4_product(uint64_t limb) {
-  const uint64_t sq = gl::canon(gl::sqr_nc(limb));
-  const uint64_t t = fsub(sq, fadd(fadd(limb, limb), limb));
-  return gl::mul_nc(t, fadd(t, 2));
+  const uint64_t t = gl::mul_nc(limb, fsub(limb, 3));  // limb canonical; t any u64 congruent to limb (limb - 3)
+  return gl::mul_nc(t, gl::add_nc(t, 2));              // add_nc: one canonical operand is enough
 }
 
 // sum_j limb_j * 4^j (j < count <= 16) for canonical limbs, WITHOUT a reduction per term: the shifted limbs are added
