@@ -333,6 +333,62 @@ struct Base4Sum {
   }
 };
 
+// sum_j x_j * 2^(s_j) for any u64 x_j and 0 <= s_j < 64, WITHOUT a reduction per term: the shifted terms (< 2^127) are
+// added as a 160-bit integer (up to 2^32 terms fit) and reduced once, with Acc::value()'s reduction (2^128 = -2^32).
+// Replaces the Horner forms sum = 2 sum + b (14 instructions per term) and sum = sum + coeff * b (33) of the bit / limb
+// recombination constraints by 8 instructions per term; same field element (exact integer arithmetic).
+// HI = false: shifts 0..31 (the term starts in word 0); HI = true: shifts 32..63 (word 1); `sh` = shift mod 32.
+struct Sum160 {
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+  template <bool HI>
+  __device__ __forceinline__ void add(uint64_t x, uint32_t sh) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const uint32_t a0 = lo << sh, a1 = __funnelshift_l(lo, hi, sh), a2 = __funnelshift_l(hi, 0u, sh);
+    if (!HI)
+      asm("add.cc.u32 %0, %0, %5;\n\t"
+          "addc.cc.u32 %1, %1, %6;\n\t"
+          "addc.cc.u32 %2, %2, %7;\n\t"
+          "addc.cc.u32 %3, %3, 0;\n\t"
+          "addc.u32 %4, %4, 0;"
+          : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
+          : "r"(a0), "r"(a1), "r"(a2));
+    else
+      asm("add.cc.u32 %0, %0, %4;\n\t"
+          "addc.cc.u32 %1, %1, %5;\n\t"
+          "addc.cc.u32 %2, %2, %6;\n\t"
+          "addc.u32 %3, %3, 0;"
+          : "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
+          : "r"(a0), "r"(a1), "r"(a2));
+  }
+  // shift s in 0..63, known to lie on one side of 32 for the whole loop that calls it
+  __device__ __forceinline__ void add_shift(uint64_t x, uint32_t s) {
+    if (s < 32)
+      add<false>(x, s);
+    else
+      add<true>(x, s - 32);
+  }
+  __device__ __forceinline__ uint64_t value() const {
+    uint32_t r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m,tl,th;\n\t"
+        "sub.cc.u32 tl, %2, %5;\n\t"
+        "subc.cc.u32 th, %3, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 tl, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "mad.lo.cc.u32 tl, %4, 0xFFFFFFFF, tl;\n\t"
+        "madc.hi.cc.u32 th, %4, 0xFFFFFFFF, th;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "add.u32 %1, th, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+    return gl::sub(gl::canon(gl::pack(r0, r1)), gl::pack(0u, w4));  // + w4 * 2^128 = - w4 * 2^32
+  }
+};
+
 __device__ __forceinline__ void mds_plain(uint64_t (&s)[12]) {
   poseidon::mds_layer(s, poseidon::RCF + 24 * 29);  // round-30 "constants" are zero: pure MDS
 #pragma unroll
@@ -433,12 +489,20 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       break;
     }
     case GATE_BASE_SUM: {
-      uint64_t sum = 0;
-      for (uint32_t i = g.p0; i-- > 0;) sum = fadd(fadd(sum, sum), v.w(1 + i));
-      acc.push(fsub(sum, v.w(0)));
+      if (g.p0 <= 64) {  // sum_i limb_i 2^i, one reduction
+        Sum160 sum;
+        const uint32_t lo_n = g.p0 < 32 ? g.p0 : 32;
+        for (uint32_t i = 0; i < lo_n; i++) sum.add<false>(v.w(1 + i), i);
+        for (uint32_t i = 32; i < g.p0; i++) sum.add<true>(v.w(1 + i), i - 32);
+        acc.push(fsub(sum.value(), v.w(0)));
+      } else {
+        uint64_t sum = 0;
+        for (uint32_t i = g.p0; i-- > 0;) sum = fadd(fadd(sum, sum), v.w(1 + i));
+        acc.push(fsub(sum, v.w(0)));
+      }
       for (uint32_t i = 0; i < g.p0; i++) {
         uint64_t l = v.w(1 + i);
-        acc.push(fmul(l, fsub(l, 1)));
+        acc.push(gl::mul_nc(l, fsub(l, 1)));  // push takes any u64
       }
       break;
     }
@@ -525,19 +589,26 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       const uint32_t ops = g.p0;
 #pragma unroll 1
       for (uint32_t i = 0; i < ops; i++) {
-        uint64_t cx = 0, cxi = 0;
+        // big-endian bits: x = sum_j b_j 2^(31 - j), x_interleaved = sum_j b_j 4^(31 - j)
+        Sum160 cx, cxi;
 #pragma unroll 2
-        for (int j = 0; j < 32; j++) {
+        for (int j = 0; j < 16; j++) {
           const uint64_t b = v.w(2 * ops + 32 * i + j);
-          cx = fadd(fadd(cx, cx), b);
-          cxi = fadd(fmul(cxi, 4), b);
+          cx.add<false>(b, (uint32_t)(31 - j));
+          cxi.add<true>(b, (uint32_t)(30 - 2 * j));  // 2 (31 - j) - 32
         }
-        acc.push(fsub(cx, v.w(2 * i)));
-        acc.push(fsub(cxi, v.w(2 * i + 1)));
+#pragma unroll 2
+        for (int j = 16; j < 32; j++) {
+          const uint64_t b = v.w(2 * ops + 32 * i + j);
+          cx.add<false>(b, (uint32_t)(31 - j));
+          cxi.add<false>(b, (uint32_t)(62 - 2 * j));
+        }
+        acc.push(fsub(cx.value(), v.w(2 * i)));
+        acc.push(fsub(cxi.value(), v.w(2 * i + 1)));
 #pragma unroll 2
         for (int j = 0; j < 32; j++) {
           const uint64_t b = v.w(2 * ops + 32 * i + j);
-          acc.push(fmul(b, fsub(b, 1)));
+          acc.push(gl::mul_nc(b, fsub(b, 1)));
         }
       }
       break;
@@ -548,22 +619,37 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       const bool b32 = g.kind == GATE_UNINTERLEAVE_TO_B32;
 #pragma unroll 1
       for (uint32_t i = 0; i < ops; i++) {
-        uint64_t cx = 0, ce = 0, co = 0;
+        // x = sum_j b_j 2^(63 - j); evens / odds = sum_j b_{2j}, b_{2j+1} times 2^(31 - j) (U32) or 4^(31 - j) (B32)
+        Sum160 cx, ce, co;
 #pragma unroll 4
-        for (int j = 0; j < 64; j++) cx = fadd(fadd(cx, cx), v.w(3 * ops + 64 * i + j));
-        acc.push(fsub(cx, v.w(3 * i)));
+        for (int j = 0; j < 32; j++) cx.add<true>(v.w(3 * ops + 64 * i + j), (uint32_t)(31 - j));
+#pragma unroll 4
+        for (int j = 32; j < 64; j++) cx.add<false>(v.w(3 * ops + 64 * i + j), (uint32_t)(63 - j));
+        acc.push(fsub(cx.value(), v.w(3 * i)));
+        if (b32) {
 #pragma unroll 2
-        for (int j = 0; j < 32; j++) {
-          const uint64_t coeff = b32 ? (1ull << (2 * (31 - j))) : (1ull << (31 - j));
-          ce = fadd(ce, fmul(coeff, v.w(3 * ops + 64 * i + 2 * j)));
-          co = fadd(co, fmul(coeff, v.w(3 * ops + 64 * i + 2 * j + 1)));
+          for (int j = 0; j < 16; j++) {
+            ce.add<true>(v.w(3 * ops + 64 * i + 2 * j), (uint32_t)(30 - 2 * j));
+            co.add<true>(v.w(3 * ops + 64 * i + 2 * j + 1), (uint32_t)(30 - 2 * j));
+          }
+#pragma unroll 2
+          for (int j = 16; j < 32; j++) {
+            ce.add<false>(v.w(3 * ops + 64 * i + 2 * j), (uint32_t)(62 - 2 * j));
+            co.add<false>(v.w(3 * ops + 64 * i + 2 * j + 1), (uint32_t)(62 - 2 * j));
+          }
+        } else {
+#pragma unroll 2
+          for (int j = 0; j < 32; j++) {
+            ce.add<false>(v.w(3 * ops + 64 * i + 2 * j), (uint32_t)(31 - j));
+            co.add<false>(v.w(3 * ops + 64 * i + 2 * j + 1), (uint32_t)(31 - j));
+          }
         }
-        acc.push(fsub(ce, v.w(3 * i + 1)));
-        acc.push(fsub(co, v.w(3 * i + 2)));
+        acc.push(fsub(ce.value(), v.w(3 * i + 1)));
+        acc.push(fsub(co.value(), v.w(3 * i + 2)));
 #pragma unroll 2
         for (int j = 0; j < 64; j++) {
           const uint64_t b = v.w(3 * ops + 64 * i + j);
-          acc.push(fmul(b, fsub(b, 1)));
+          acc.push(gl::mul_nc(b, fsub(b, 1)));
         }
       }
       break;
@@ -580,17 +666,22 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       uint64_t msd = 0;
       for (uint32_t i = 0; i < nc; i++) {
         const uint64_t fc = v.w(4 + i), sc = v.w(4 + nc + i);
-        uint64_t fp = 1, sp = 1;
-        for (uint64_t x = 0; x < (1ull << cb); x++) {
-          fp = fmul(fp, fsub(fc, x));
-          sp = fmul(sp, fsub(sc, x));
+        if (cb == 2) {  // prod_{x<4} (chunk - x): the range-check product of the u32 gates
+          acc.push(limb4_product(fc));
+          acc.push(limb4_product(sc));
+        } else {
+          uint64_t fp = 1, sp = 1;
+          for (uint64_t x = 0; x < (1ull << cb); x++) {
+            fp = fmul(fp, fsub(fc, x));
+            sp = fmul(sp, fsub(sc, x));
+          }
+          acc.push(fp);
+          acc.push(sp);
         }
-        acc.push(fp);
-        acc.push(sp);
         const uint64_t diff = fsub(sc, fc);
         const uint64_t dummy = v.w(4 + 2 * nc + i), eq = v.w(4 + 3 * nc + i), inter = v.w(4 + 4 * nc + i);
         acc.push(fsub(fmul(diff, dummy), fsub(1, eq)));
-        acc.push(fmul(eq, diff));
+        acc.push(gl::mul_nc(eq, diff));
         acc.push(fsub(inter, fmul(eq, msd)));
         msd = fadd(inter, fmul(fsub(1, eq), diff));
       }
@@ -599,7 +690,7 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       uint64_t comb = 0;
       for (uint32_t b = 0; b <= cb; b++) {
         const uint64_t bit = v.w(4 + 5 * nc + b);
-        acc.push(fmul(bit, fsub(1, bit)));
+        acc.push(gl::mul_nc(bit, fsub(1, bit)));
       }
       for (uint32_t b = cb + 1; b-- > 0;) comb = fadd(fadd(comb, comb), v.w(4 + 5 * nc + b));
       acc.push(fsub(fadd(1ull << cb, msd_w), comb));
@@ -627,9 +718,10 @@ __device__ __forceinline__ void eval_gate_light(const Gate& g, const Vars& v, Ac
       const bool ext = g.kind == GATE_REDUCING_EXT;
       const uint32_t start_accs = 6 + (ext ? 2 * n : n);
       const gl::ext2 alpha{v.w(2), v.w(3)};
+      const uint64_t alpha1_7 = fmul(7, alpha.c1);  // acc * alpha with 7 alpha_1 formed once: two dot products per step
       gl::ext2 a{v.w(4), v.w(5)};
       for (uint32_t i = 0; i < n; i++) {
-        const gl::ext2 t = gl::ext_mul(a, alpha);
+        const gl::ext2 t{gl::dot2(a.c0, alpha.c0, a.c1, alpha1_7), gl::dot2(a.c0, alpha.c1, a.c1, alpha.c0)};
         const uint32_t nx = i == n - 1 ? 0 : start_accs + 2 * i;
         const gl::ext2 nxt{v.w(nx), v.w(nx + 1)};
         const uint64_t k0 = ext ? v.w(6 + 2 * i) : v.w(6 + i), k1 = ext ? v.w(7 + 2 * i) : 0;
