@@ -353,25 +353,13 @@ __global__ void __launch_bounds__(256) k_eval_polys_multi(EvalParams P) {
   const size_t n = P.n;
   const uint64_t* c = P.coeffs[r] + (size_t)idx * n;
   const uint64_t* zp = P.points + 2 * P.point[r];
-  const uint32_t tid = threadIdx.x;
-  const size_t per = (n + 255) / 256, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
+  __shared__ ext2 tab[48];
   const ext2 z{gl::canon(zp[0]), gl::canon(zp[1])};
-  ext2 acc{0, 0};
-  for (size_t k = hi; k-- > lo;) acc = provk::horner_step(acc, z, gl::canon(c[k]));
-  if (lo < n) acc = gl::ext_mul(acc, provk::ext_pow(z, lo));
-  s0[tid] = lo < n ? acc.c0 : 0;
-  s1[tid] = lo < n ? acc.c1 : 0;
-  __syncthreads();
-  for (uint32_t off = 128; off > 0; off >>= 1) {
-    if (tid < off) {
-      s0[tid] = gl::add(s0[tid], s0[tid + off]);
-      s1[tid] = gl::add(s1[tid], s1[tid + off]);
-    }
-    __syncthreads();
-  }
+  const ext2 val = provk::eval_poly_cta(c, n, z, s0, s1, tab);
+  const uint32_t tid = threadIdx.x;
   if (tid == 0) {
-    P.out[r][2 * idx] = s0[0];
-    P.out[r][2 * idx + 1] = s1[0];
+    P.out[r][2 * idx] = val.c0;
+    P.out[r][2 * idx + 1] = val.c1;
   }
 }
 

@@ -301,5 +301,51 @@ __device__ __forceinline__ ext2 ext_mul(ext2 a, ext2 b) {
   return {dot2(a.c0, b.c0, mul_nc(a.c1, b.c1), 7), dot2(a.c0, b.c1, a.c1, b.c0)};
 }
 __device__ __forceinline__ ext2 ext_scale(ext2 a, uint64_t s) { return {mul(a.c0, s), mul(a.c1, s)}; }
+// sum of products a_i * b_i (any u64 operands) as an unreduced 160-bit integer (up to 2^32 terms), reduced once by
+// value(): 2^128 = -2^32 (mod p).  13 instructions per term instead of the 33 of add(acc, mul(a, b)); exact.
+struct Dot160 {
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+  __device__ __forceinline__ void add_product(uint64_t c, uint64_t a) {
+    const uint32_t c0 = (uint32_t)c, c1 = (uint32_t)(c >> 32), a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %8, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3), "+r"(w4)
+        : "r"(c0), "r"(c1), "r"(a0), "r"(a1));
+  }
+  __device__ __forceinline__ uint64_t value() const {  // canonical
+    uint32_t r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m,tl,th;\n\t"
+        "sub.cc.u32 tl, %2, %5;\n\t"
+        "subc.cc.u32 th, %3, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 tl, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "mad.lo.cc.u32 tl, %4, 0xFFFFFFFF, tl;\n\t"
+        "madc.hi.cc.u32 th, %4, 0xFFFFFFFF, th;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, tl, m;\n\t"
+        "subc.u32 th, th, 0;\n\t"
+        "add.u32 %1, th, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+    return sub(canon(pack(r0, r1)), pack(0u, w4));
+  }
+};
+
 
 }  // namespace gl

@@ -33,19 +33,48 @@ __device__ __forceinline__ ext2 ext_pow(ext2 b, size_t e) {
   return r;
 }
 
-// out[p] = poly_p(point): one CTA per polynomial (column-major coefficients, n each)
-__global__ void __launch_bounds__(256) k_eval_polys_ext(const uint64_t* __restrict__ coeffs, size_t n,
-                                                         const uint64_t* __restrict__ zp, uint64_t* __restrict__ out) {
-  __shared__ uint64_t s0[256], s1[256];
-  const uint64_t* c = coeffs + (size_t)blockIdx.x * n;
+// poly(z) for a base-field polynomial of n coefficients (n a power of two) and an extension point z, by one CTA of 256
+// threads; every thread returns with the value only in thread 0 (the others get garbage).  Thread t owns the `per`
+// coefficients from t * per on.  Instead of a Horner chain of extension multiplications (100 instructions per
+// coefficient) plus z^(t * per) by square-and-multiply in every thread (~20 more extension multiplications), the powers
+// z^k, k < 16, and z^(t * per) = A[t >> 4] * B[t & 15] (A[a] = z^(16 per a), B[b] = z^(per b)) are built once per CTA by 48
+// threads, and a run of 16 coefficients is two dot products c_k * Re / Im (z^k) accumulated WITHOUT reduction
+// (gl::Dot160: 13 instructions per coefficient and component).  Field arithmetic is exact: same value as Horner's.
+__device__ __forceinline__ ext2 eval_poly_cta(const uint64_t* __restrict__ c, size_t n, ext2 z, uint64_t* s0, uint64_t* s1,
+                                              ext2* tab /* 48 entries of shared memory */) {
   const uint32_t tid = threadIdx.x;
   const size_t per = (n + 255) / 256, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
-  const ext2 z{gl::canon(zp[0]), gl::canon(zp[1])};
+  if (tid < 48) {
+    // group 0: z^b; group 1: (z^per)^b; group 2: (z^(16 per))^b   (per is a power of two: squarings)
+    ext2 base = z;
+    const uint32_t grp = tid >> 4, b = tid & 15;
+    if (grp >= 1)
+      for (size_t e = per; e > 1; e >>= 1) base = gl::ext_mul(base, base);
+    if (grp == 2)
+      for (int k = 0; k < 4; k++) base = gl::ext_mul(base, base);
+    tab[tid] = ext_pow(base, b);
+  }
+  __syncthreads();
   ext2 acc{0, 0};
-  for (size_t k = hi; k-- > lo;) acc = horner_step(acc, z, gl::canon(c[k]));
-  if (lo < n) acc = gl::ext_mul(acc, ext_pow(z, lo));
-  s0[tid] = lo < n ? acc.c0 : 0;
-  s1[tid] = lo < n ? acc.c1 : 0;
+  if (lo < n) {
+    const ext2 z16 = gl::ext_mul(tab[8], tab[8]);
+    // chunks of 16 coefficients from the top: acc = acc * z^16 + sum_k c[s + k] z^k
+    const size_t len = hi - lo, chunks = (len + 15) / 16;
+    for (size_t ch = chunks; ch-- > 0;) {
+      const size_t s = lo + 16 * ch, e = s + 16 < hi ? s + 16 : hi;
+      gl::Dot160 d0, d1;
+      for (size_t k = s; k < e; k++) {
+        const uint64_t ck = gl::canon(c[k]);  // coefficients of a from_coeffs batch are the caller's raw words
+        d0.add_product(ck, tab[k - s].c0);
+        d1.add_product(ck, tab[k - s].c1);
+      }
+      if (ch + 1 < chunks) acc = gl::ext_mul(acc, z16);
+      acc = gl::ext_add(acc, ext2{d0.value(), d1.value()});
+    }
+    acc = gl::ext_mul(acc, gl::ext_mul(tab[32 + (tid >> 4)], tab[16 + (tid & 15)]));  // * z^(tid * per)
+  }
+  s0[tid] = acc.c0;
+  s1[tid] = acc.c1;
   __syncthreads();
   for (uint32_t off = 128; off > 0; off >>= 1) {
     if (tid < off) {
@@ -54,9 +83,19 @@ __global__ void __launch_bounds__(256) k_eval_polys_ext(const uint64_t* __restri
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    out[2 * blockIdx.x] = s0[0];
-    out[2 * blockIdx.x + 1] = s1[0];
+  return ext2{s0[0], s1[0]};
+}
+
+// out[p] = poly_p(point): one CTA per polynomial (column-major coefficients, n each)
+__global__ void __launch_bounds__(256) k_eval_polys_ext(const uint64_t* __restrict__ coeffs, size_t n,
+                                                         const uint64_t* __restrict__ zp, uint64_t* __restrict__ out) {
+  __shared__ uint64_t s0[256], s1[256];
+  __shared__ ext2 tab[48];
+  const ext2 z{gl::canon(zp[0]), gl::canon(zp[1])};
+  const ext2 r = eval_poly_cta(coeffs + (size_t)blockIdx.x * n, n, z, s0, s1, tab);
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = r.c0;
+    out[2 * blockIdx.x + 1] = r.c1;
   }
 }
 
