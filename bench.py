@@ -53,6 +53,7 @@ WORKLOAD = ("City Rollup worker proof jobs: CircuitData::prove at 2^12 rows x 13
             "u32 gates), rate_bits=3, cap_height=4, pow 16 bits, 28 queries, arities [4,4], synthetic witness (BASELINE.json "
             "metric M1 / configs[3] job shape); M2 = standalone commit 2^20 rows x 135 cols")
 M2_LOG_N = 20
+FULL_LOG_N = 16  # roofline launch of the leaf-hash kernel with every SM occupied: 2^16 rows x 135 columns
 
 # Algorithmic int32-op model of one Poseidon permutation: a field multiplication = 4 32x32 multiplies
 # + 14 32-bit add/carry ops (18), a modular add = 5, the MDS layer on 32-bit halves = 2*144 multiply-adds + 12*6 folds:
@@ -443,23 +444,55 @@ def run_cuda(args):
         leaf_gops = pp["leaf"] * OPS_PER_PERM / (leaf_ms * 1e-3) / 1e9
         lde_bytes = 8 * (1 << DEGREE_BITS) * (1 << RATE_BITS) * sum(
             [N_WIRES, 20, 16]) + 32 * 3 * ((1 << DEGREE_BITS) << RATE_BITS)
+        # the same kernel with every SM occupied, as in the timed region (24 proofs in flight): one launch over the
+        # 2^19 leaves x 135 columns of a 2^16-row commit (BASELINE configs[1]; 2048 CTAs; 17 permutations per leaf,
+        # exactly the per-leaf work of a proof's wires commit), CUDA events around the launch on the context's stream
+        full = torch.empty((N_WIRES, 1 << FULL_LOG_N), dtype=torch.int64, device="cuda")
+        gfull = torch.Generator(device="cuda")
+        gfull.manual_seed(11)
+        full.random_(0, 2**62, generator=gfull)
+        torch.cuda.synchronize()
+        c.profile_enable(True)
+        for i in range(4):
+            b = m.PolynomialBatch.from_values_device(c, full.data_ptr(), N_WIRES, FULL_LOG_N, RATE_BITS, CAP_HEIGHT)
+            b.free()
+            if i == 0:
+                c.profile_read()  # drop the warm-up launch
+        st_full, cnt_full = c.profile_read()
+        c.profile_enable(False)
+        del full
+        full_ms = st_full["leaf_hash"] / max(1, cnt_full["leaf_hash"])
+        full_perms = -(-N_WIRES // 8) * ((1 << FULL_LOG_N) << RATE_BITS)
+        full_gops = full_perms * OPS_PER_PERM / (full_ms * 1e-3) / 1e9
+        full_bytes = 8 * N_WIRES * ((1 << FULL_LOG_N) << RATE_BITS) + 32 * ((1 << FULL_LOG_N) << RATE_BITS)
+        exec_instr = traffic.get("k_leaf_hash_colmajor_executed_instr_per_perm")
         roofline = {
-            "kernel": "k_leaf_hash_colmajor (Poseidon sponge over the LDE rows of the three commits of a proof: 17 + 3 + 2 "
-                      "permutations per leaf, 2^15 leaves), the largest kernel of the step",
-            "bound": "int32", "achieved": leaf_gops, "peak": int_peak, "unit": "Gop/s (int32)", "frac": leaf_gops / int_peak,
-            "traffic": traffic.get("k_leaf_hash_colmajor_m1"),
-            "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM, "permutations_per_proof_in_kernel": pp["leaf"],
-            "ms_per_proof_in_kernel": leaf_ms, "launches_per_proof": leaf_launches,
-            "timed": "CUDA events around the stage on the context's stream, one worker alone (in the timed region the kernels of all workers overlap)",
-            "share_of_single_worker_proof": leaf_ms / best,
+            "kernel": "k_leaf_hash_colmajor (Poseidon sponge over the LDE rows of a commit: ceil(C / 8) permutations per leaf), "
+                      "the largest kernel of the step (55 % of a proof's executed instructions)",
+            "bound": "int32", "achieved": full_gops, "peak": int_peak, "unit": "Gop/s (int32)", "frac": full_gops / int_peak,
+            "traffic": traffic.get("k_leaf_hash_colmajor_2p16x135"),
+            "peak_source": int_src, "ops_per_permutation": OPS_PER_PERM,
+            "permutations_per_launch": full_perms, "ms_per_launch": full_ms, "gperm_s": full_perms / (full_ms * 1e-3) / 1e9,
+            "algorithmic_bytes_per_launch": full_bytes,
+            "timed": "CUDA events around the launch on the context's stream; one launch over 2^19 leaves x 135 columns "
+                     "(2048 CTAs: every SM occupied, as in the timed region where the launches of 24 proofs overlap)",
+            "frac_executed_instructions": (full_perms * exec_instr / (full_ms * 1e-3) / 1e9 / int_peak) if exec_instr else None,
+            "executed_instructions_per_permutation": exec_instr,
+            "single_proof_launches": {
+                "achieved": leaf_gops, "frac": leaf_gops / int_peak, "permutations_per_proof_in_kernel": pp["leaf"],
+                "ms_per_proof_in_kernel": leaf_ms, "launches_per_proof": leaf_launches,
+                "share_of_single_worker_proof": leaf_ms / best,
+                "traffic": traffic.get("k_leaf_hash_colmajor_m1"),
+                "note": "the three launches of ONE proof running alone (17 + 3 + 2 permutations per leaf over 2^15 leaves = "
+                        "128 CTAs on 148 SMs, two warps per scheduler): latency, not throughput"},
             "whole_proof": {"permutations_per_proof": pp, "achieved_gperm_s": pp["total"] * value / world / 1e9,
                             "int32_frac_all_permutations": pp["total"] * value / world * OPS_PER_PERM / 1e9 / int_peak,
                             "note": "all Poseidon work of a proof at the measured proofs/s of one GPU against the INT32 issue peak"},
-            "hbm_view": {"bound": "hbm", "algorithmic_bytes_per_proof": lde_bytes,
-                         "achieved": lde_bytes / (leaf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": lde_bytes / (leaf_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
-            "note": "integer-issue bound (SURVEY.md §0.7); `frac` uses the fixed 19356-op scalar model of a permutation; the "
-                    "executed-instruction fraction of the same kernel is in profiles/ (ncu)",
+            "hbm_view": {"bound": "hbm", "algorithmic_bytes_per_launch": full_bytes,
+                         "achieved": full_bytes / (full_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": full_bytes / (full_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+            "note": "integer-issue bound (SURVEY.md §0.7); `frac` uses the fixed 19356-op scalar model of a permutation, "
+                    "`frac_executed_instructions` the instructions the kernel executes per permutation (ncu, profiles/)",
         }
     except Exception as e:  # noqa: BLE001
         single = {"error": str(e)[:200]}
