@@ -70,3 +70,17 @@ def test_truncated_dump_is_rejected(exe, tmp_path):
     bad.write_bytes(blob[: len(blob) // 2])
     res = subprocess.run([path, "--plan-only", "-d", str(bad)], env=env, capture_output=True, text=True, timeout=60)
     assert res.returncode != 0 and "dump" in res.stderr
+
+
+def test_worker_pool_keeps_the_workers_busy_on_the_dumped_dag(exe):
+    """the store protocol + ready queue + worker pool with a sleeping prover (--fake-ms): every job of 8 blocks in flight is
+    processed, every proving job recorded, and 8 workers are busy most of the time (the DAG itself allows 99 %: what is
+    measured on the GPU is then the prover, not the scheduler)"""
+    path, env = exe
+    res = subprocess.run([path, "--fake-ms", "4", "-d", os.path.join(ROOT, "tests", "golden", "example_dag.bin"), "-n", "8",
+                          "--contexts", "8"], env=env, capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr + res.stdout
+    d = json.loads(res.stdout.strip().splitlines()[-1])
+    assert d["jobs"] == 8 * 60 and d["proving_jobs"] == d["jobs_recorded"] == d["stored_proofs"] == 8 * 43 and d["proofs"] == 8 * 67
+    assert d["worker_busy_fraction"] > 0.8, d
+    assert d["wall_s"] <= d["wall_incl_teardown_s"]

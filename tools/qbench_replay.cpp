@@ -339,6 +339,7 @@ int main(int argc, char** argv) {
   const char* out_path = nullptr;
   const char* dump_path = nullptr;
   int n_gpus = 1, ctx_per_gpu = 8, n_blocks = 4, agg_tree = -1, async_depth = 0;
+  double fake_ms = 0.0;
   bool only_plan = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -352,11 +353,13 @@ int main(int argc, char** argv) {
     else if (a == "--agg-tree") agg_tree = atoi(val());
     else if (a == "--async") async_depth = atoi(val());
     else if (a == "--plan-only") only_plan = true;
+    else if (a == "--fake-ms") fake_ms = atof(val());
   }
-  if ((!case_path && !only_plan) || n_gpus < 1 || ctx_per_gpu < 1 || n_blocks < 1 || agg_tree == 0 || agg_tree > 20 || async_depth < 0) {
+  if ((!case_path && !only_plan && fake_ms <= 0.0) || n_gpus < 1 || ctx_per_gpu < 1 || n_blocks < 1 || agg_tree == 0 || agg_tree > 20 || async_depth < 0) {
     fprintf(stderr,
             "usage: %s -i case.bin [-d dump.bin] [-o bench.json] [-n blocks=4] [--gpus G=1] [--contexts W=8] [--agg-tree log2_leaves]\n"
             "          [--async K]   one host thread per GPU drives K contexts through p2b_prove_submit / collect\n"
+            "          [--fake-ms X] no GPU: every proof is a sleep of X ms (the store protocol, queue and worker pool alone)\n"
             "          [--plan-only] parse the dump (or the built-in plan), replay the DAG without a GPU, print its census\n"
             "  -d: a bincode BlockProofStoreDump (qbench_data/example.bin, or tests/golden/example_dag.bin = the same with\n"
             "      witness / proof payloads stripped): the job ids, counters, goals and next-job lists come from the file\n",
@@ -372,7 +375,7 @@ int main(int argc, char** argv) {
     }
     if (only_plan) return plan_only(blocks[0], dump_path ? dump_path : (agg_tree > 0 ? "built-in aggregation tree" : "built-in block plan"));
 
-    const Case cs = load_case(case_path);
+    const Case cs = fake_ms > 0.0 ? Case{} : load_case(case_path);
     p2b_proof_shape shape{};
     shape.degree_bits = cs.desc.degree_bits;
     shape.num_constants = cs.desc.num_constants;
@@ -394,6 +397,7 @@ int main(int argc, char** argv) {
     std::deque<std::pair<int, int>> ready;  // (block, job)
     std::map<std::string, std::vector<uint8_t>> store;
     std::atomic<size_t> jobs_done{0};
+    std::atomic<long long> t_done_ns{0};
     std::atomic<int> mismatches{0}, warm{0};
     std::atomic<bool> go{false};
     struct Bench { std::array<uint8_t, 24> id; uint64_t ms; };
@@ -422,8 +426,12 @@ int main(int argc, char** argv) {
       }
       if (job.id[0] != TOPIC_NOTIFY) after_job(blk, job, [&](int nx) { enqueue_job(b, nx); });
       if (jobs_done.fetch_add(1) + 1 == total_jobs) {
+        // NotifyOrchestratorComplete of the last block: the replay's clock stops HERE (qbench.rs:44-60 stops its timer when
+        // the job loop returns), not when the worker threads have torn their contexts down — freeing 24 contexts' pinned
+        // buffers, graphs and device memory takes seconds and was counted as proving time before
+        t_done_ns.store(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
         std::lock_guard<std::mutex> g(qm);
-        qcv.notify_all();  // NotifyOrchestratorComplete of the last block
+        qcv.notify_all();
       }
     };
     auto pop_job = [&](std::pair<int, int>& item, bool block) {
@@ -443,7 +451,24 @@ int main(int argc, char** argv) {
       jobs_done = total_jobs;
       qcv.notify_all();
     };
-    if (!async_depth) {
+    if (fake_ms > 0.0) {
+      // no GPU: a job costs fake_ms per proof of sleep.  What is left is the store protocol, the ready queue and the
+      // worker pool themselves — their overhead and the parallelism the DAG offers (CPU test of the scheduler)
+      for (int w = 0; w < n_workers; w++) {
+        pool.emplace_back([&, w] {
+          warm++;
+          while (!go.load()) std::this_thread::yield();
+          std::pair<int, int> item;
+          while (pop_job(item, true)) {
+            Job& job = blocks[item.first].jobs[item.second];
+            const auto t0 = std::chrono::steady_clock::now();
+            if (job.n_proofs) std::this_thread::sleep_for(std::chrono::duration<double, std::milli>(fake_ms * job.n_proofs));
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            finish_job(w, item.first, item.second, std::vector<uint8_t>(job.n_proofs ? 8 : 0), sec);
+          }
+        });
+      }
+    } else if (!async_depth) {
       // one OS thread and one context per worker (the reference's model: many l2-worker processes, one queue)
       for (int w = 0; w < n_workers; w++) {
         pool.emplace_back([&, w] {
@@ -566,7 +591,10 @@ int main(int argc, char** argv) {
       for (int j : blocks[b].entry_jobs) enqueue_job(b, j);
     go = true;
     for (auto& th : pool) th.join();
-    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double wall_join = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double wall = t_done_ns.load()
+        ? (double)(t_done_ns.load() - std::chrono::duration_cast<std::chrono::nanoseconds>(t0.time_since_epoch()).count()) * 1e-9
+        : wall_join;
     if (!first_error.empty()) throw std::runtime_error(first_error);
 
     size_t recorded = 0, stored_bytes = 0;
@@ -592,14 +620,15 @@ int main(int argc, char** argv) {
     const int slots_total = async_depth ? n_gpus * async_depth : n_workers;
     printf("{\"harness\": \"%s\", \"dag\": \"%s\", \"rows_log2\": %u, \"gpus\": %d, \"host_threads\": %d, "
            "\"contexts_per_gpu\": %d, \"mode\": \"%s\", \"blocks\": %d, \"jobs\": %zu, \"proving_jobs\": %zu, \"jobs_recorded\": %zu, "
-           "\"proofs\": %zu, \"wall_s\": %.4f, "
+           "\"proofs\": %zu, \"wall_s\": %.4f, \"wall_incl_teardown_s\": %.4f, "
            "\"proofs_per_s\": %.2f, \"jobs_per_s\": %.2f, \"sum_job_duration_ms\": %.0f, \"worker_busy_fraction\": %.3f, "
            "\"stored_proofs\": %zu, \"stored_bytes\": %zu, \"mismatching_proofs\": %d}\n",
            agg_tree > 0 ? "binary aggregation tree, level-synchronous (synthetic City-shaped circuit)"
                         : "qbench replay (synthetic City-shaped circuit)",
            dump_path ? dump_path : "built-in plan", cs.desc.degree_bits, n_gpus, n_workers, async_depth ? async_depth : ctx_per_gpu,
-           async_depth ? "one host thread per GPU, p2b_prove_submit / collect" : "one host thread per context, blocking p2b_prove",
-           n_blocks, total_jobs, proving_jobs, recorded, total_proofs, wall, total_proofs / wall, proving_jobs / wall, sum_ms,
+           fake_ms > 0.0 ? "no GPU: every proof is a sleep (--fake-ms), scheduler only"
+                       : async_depth ? "one host thread per GPU, p2b_prove_submit / collect" : "one host thread per context, blocking p2b_prove",
+           n_blocks, total_jobs, proving_jobs, recorded, total_proofs, wall, wall_join, total_proofs / wall, proving_jobs / wall, sum_ms,
            busy_sum / (wall * slots_total), store.size(), stored_bytes, mismatches.load());
     return (mismatches.load() || recorded != proving_jobs || store.size() != proving_jobs) ? 1 : 0;
   } catch (const std::exception& e) {
