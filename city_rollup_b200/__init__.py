@@ -6,4 +6,4 @@ from .plonky2 import (Challenger, CircuitData, Context, FriParams, MerkleTree, P
                       PolynomialBatch, all_wires_permutation_partial_products, compute_quotient_polys,
                       fri_committed_trees, fri_proof_of_work, proof_from_bincode, proof_shape, proof_to_bincode,
                       prove, prove_collect, prove_native, prove_native_device, prove_openings, prove_poll,
-                      prove_submit)
+                      prove_submit, prove_upload_poll)

@@ -85,6 +85,8 @@ SIGNATURES = {
     "p2b_prove_dev": (C.c_int, [vp, vp, vp, u64p, vp, u64p, sz, vp, u64p, sz]),
     "p2b_prove_submit": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp]),
     "p2b_prove_poll": (C.c_int, [vp]),
+    "p2b_prove_submit_nowait": (C.c_int, [vp, vp, vp, u64p, C.POINTER(u64p), u64p, sz, vp]),
+    "p2b_prove_upload_poll": (C.c_int, [vp]),
     "p2b_prove_collect": (C.c_int, [vp, u64p, sz]),
     "p2b_plan_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
     "p2b_proof_words": (sz, [vp, vp]),

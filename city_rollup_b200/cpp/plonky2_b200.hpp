@@ -322,6 +322,23 @@ inline size_t prove_submit(const Context& ctx, const CircuitData& circuit, const
                              public_inputs.data(), public_inputs.size(), &params));
   return len;
 }
+// p2b_prove_submit_nowait: no wait for the upload — the form for a thread that drives many contexts; pinned witness columns
+// stay untouched until prove_upload_poll(ctx) (or the proof has been collected)
+inline size_t prove_submit_nowait(const Context& ctx, const CircuitData& circuit, const PolynomialBatch& constants_sigmas,
+                                  const HashOut& circuit_digest, const std::vector<const F*>& wire_cols,
+                                  const std::vector<F>& public_inputs, const p2b_fri_params& params) {
+  const size_t len = p2b_proof_len(circuit.get(), constants_sigmas.get(), &params, public_inputs.size());
+  if (!len) throw Error(P2B_ERR_INVALID, "inconsistent FRI parameters");
+  if (wire_cols.size() != circuit.desc().num_wires) throw Error(P2B_ERR_INVALID, "witness column count does not match the circuit");
+  ctx.check(p2b_prove_submit_nowait(ctx.get(), circuit.get(), constants_sigmas.get(), circuit_digest.data(), wire_cols.data(),
+                                    public_inputs.data(), public_inputs.size(), &params));
+  return len;
+}
+inline bool prove_upload_poll(const Context& ctx) {
+  const int rc = p2b_prove_upload_poll(ctx.get());
+  if (rc < 0) ctx.check(rc);
+  return rc == 1;
+}
 inline bool prove_poll(const Context& ctx) {
   const int rc = p2b_prove_poll(ctx.get());
   if (rc < 0) ctx.check(rc);

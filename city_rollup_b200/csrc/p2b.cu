@@ -134,6 +134,7 @@ struct p2b_ctx {
   // returning, so the caller may refill its buffers)
   cudaEvent_t ev_h2d = nullptr;
   bool h2d_event_pending = false;
+  bool direct_src_pending = false;  // a replayed prove plan reads the caller's pinned witness (no separate upload event)
   nttk::Tables tables() const { return nttk::Tables{d_w12, d_rlo, d_rhi}; }
   ntt2::RootTables roots() const { return ntt2::RootTables{d_rlo, d_rhi}; }
 };
@@ -3303,6 +3304,7 @@ static int plan_launch(p2b_ctx* ctx, ProvePlan* pl, const p2b_circuit* c, const 
     // until the proof is collected (the blocking p2b_prove); everything else is packed into the plan's pinned matrix
     if (caller_keeps_buffers && cols_contiguous(wire_cols, c->d.num_wires, n) && host_ptr_is_pinned(wire_cols[0])) {
       src = wire_cols[0];
+      ctx->direct_src_pending = true;  // p2b_prove_upload_poll: the replayed graph reads the caller's memory
     } else {
       for (uint32_t w = 0; w < c->d.num_wires; w++) {
         if (!wire_cols[w]) return fail(ctx, P2B_ERR_INVALID, "cols[%u] is null", w);
@@ -3414,6 +3416,7 @@ static int prove_collect(p2b_ctx* ctx, uint64_t* proof_out, size_t proof_cap) {
   if (proof_cap < len) return fail(ctx, P2B_ERR_INVALID, "proof buffer too small: %zu < %zu words", proof_cap, len);
   ctx->pending_words = 0;
   ctx->h2d_event_pending = false;  // everything enqueued has finished once the stream is idle
+  ctx->direct_src_pending = false;
   CU(ctx, ctx_sync(ctx));
   memcpy(proof_out, ctx->pending_src, len * sizeof(uint64_t));
   if (ctx->pending_src[len] != 0) return fail(ctx, P2B_ERR_INVALID, "Opening point is in the subgroup.");  // plonky2's own failure
@@ -3454,6 +3457,32 @@ extern "C" int p2b_prove_submit(p2b_ctx* ctx, const p2b_circuit* c, const p2b_ba
     CU(ctx, cudaEventSynchronize(ctx->ev_h2d));
   }
   return rc;
+}
+// The driver-thread form: no wait for the upload.  With many proofs in flight an upload can sit behind another context's
+// kernels in a shared hardware queue for milliseconds; a thread that drives several contexts must not stall there.
+extern "C" int p2b_prove_submit_nowait(p2b_ctx* ctx, const p2b_circuit* c, const p2b_batch* cs, const uint64_t* circuit_digest,
+                                       const uint64_t* const* wire_cols, const uint64_t* public_inputs, size_t n_public_inputs,
+                                       const p2b_fri_params* fp) {
+  if (ctx && !wire_cols) return fail(ctx, P2B_ERR_INVALID, "null argument");
+  // the caller keeps its buffers untouched until p2b_prove_upload_poll says otherwise: a contiguous pinned matrix is read
+  // by DMA straight from the caller's memory (no 4.4 MB host copy into the plan's staging matrix inside submit)
+  return prove_submit(ctx, c, cs, circuit_digest, wire_cols, nullptr, public_inputs, n_public_inputs, fp, true);
+}
+extern "C" int p2b_prove_upload_poll(p2b_ctx* ctx) {
+  CHECK_CTX(ctx);
+  if (ctx->direct_src_pending) {
+    // the upload is a node of the replayed graph: no event of its own, the buffer is free when the proof has finished
+    cudaError_t q = cudaStreamQuery(ctx->stream);
+    if (q == cudaErrorNotReady) return 0;
+    if (q != cudaSuccess) return fail(ctx, P2B_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(q));
+    ctx->direct_src_pending = false;
+  }
+  if (!ctx->h2d_event_pending) return 1;  // pageable columns were staged inside submit; nothing else reads host memory
+  cudaError_t e = cudaEventQuery(ctx->ev_h2d);
+  if (e == cudaErrorNotReady) return 0;
+  if (e != cudaSuccess) return fail(ctx, P2B_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+  ctx->h2d_event_pending = false;
+  return 1;
 }
 extern "C" int p2b_prove_poll(p2b_ctx* ctx) {
   CHECK_CTX(ctx);

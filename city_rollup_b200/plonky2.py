@@ -622,9 +622,10 @@ def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
     return parse_proof_words(circuit.desc, cs, fri_params, buf, len(public_inputs))
 
 
-def prove_submit(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params):
+def prove_submit(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params, wait_upload=True):
     """p2b_prove_submit: enqueue the whole proof and return; `wire_values` may be reused at once.  -> number of proof
-    words to hand to prove_collect.  One proof may be pending per context."""
+    words to hand to prove_collect.  One proof may be pending per context.  wait_upload=False is
+    p2b_prove_submit_nowait: pinned `wire_values` must then stay untouched until prove_upload_poll(ctx) is True."""
     keep, ptrs, log_n, n_cols = PolynomialBatch._cols(wire_values)
     d = circuit.desc
     if n_cols != d["num_wires"] or log_n != d["degree_bits"]:
@@ -635,9 +636,19 @@ def prove_submit(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
     n_words = int(ctx.lib.p2b_proof_len(circuit.h, cs.h, C.byref(ps), len(public_inputs)))
     if n_words == 0:
         raise P2BError(-1, "inconsistent FRI parameters")
-    ctx.check(ctx.lib.p2b_prove_submit(ctx.h, circuit.h, cs.h, _ptr(_felts(circuit_digest)), ptrs, _ptr(pis),
-                                       len(public_inputs), C.byref(ps)))
+    fn = ctx.lib.p2b_prove_submit if wait_upload else ctx.lib.p2b_prove_submit_nowait
+    ctx.check(fn(ctx.h, circuit.h, cs.h, _ptr(_felts(circuit_digest)), ptrs, _ptr(pis), len(public_inputs), C.byref(ps)))
+    if not wait_upload:
+        ctx._upload_keep = keep  # the DMA still reads these
     return n_words
+
+
+def prove_upload_poll(ctx):
+    """True once the witness of the submitted proof has been read (p2b_prove_upload_poll)"""
+    rc = ctx.lib.p2b_prove_upload_poll(ctx.h)
+    if rc < 0:
+        ctx.check(rc)
+    return rc == 1
 
 
 def prove_poll(ctx):

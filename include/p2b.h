@@ -341,6 +341,17 @@ int p2b_prove_submit(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *
                      size_t n_public_inputs, const p2b_fri_params *params);
 int p2b_prove_poll(p2b_ctx *ctx);
 int p2b_prove_collect(p2b_ctx *ctx, uint64_t *proof_out, size_t proof_cap);
+/* p2b_prove_submit without the wait for the upload of pinned witness columns: they must stay untouched until
+ * p2b_prove_upload_poll returns 1 (or the proof has been collected).  For a thread that drives many contexts: with N
+ * proofs in flight an upload can wait milliseconds behind other contexts' kernels in a shared hardware queue, and a
+ * wait inside submit would stall every other context of that thread (measured with 24 contexts on one thread: 143
+ * proofs/s with the wait).  p2b_prove_upload_poll: 1 = the witness has been read, 0 = not yet; when a prove plan is
+ * replayed from a contiguous pinned matrix the upload is a node of the captured graph reading the caller's memory
+ * directly (no host copy inside submit), and the poll turns 1 when the proof has finished. */
+int p2b_prove_submit_nowait(p2b_ctx *ctx, const p2b_circuit *circuit, const p2b_batch *constants_sigmas,
+                            const uint64_t *circuit_digest, const uint64_t *const *wire_cols,
+                            const uint64_t *public_inputs, size_t n_public_inputs, const p2b_fri_params *params);
+int p2b_prove_upload_poll(p2b_ctx *ctx);
 /* Prove plans: from the second proof of a given (circuit, constants_sigmas, parameters) on, a context replays the proof
  * as ONE captured CUDA graph (P2B_GRAPH=0 turns this off).  Counts of this context's plans by state and the number of
  * kernels one replay launches; after a failed capture p2b_last_error tells why that shape stays on the eager path. */

@@ -124,6 +124,10 @@ extern "C" {
         circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
         params: *const p2b_fri_params) -> c_int;
     pub fn p2b_prove_poll(ctx: *mut p2b_ctx) -> c_int;
+    pub fn p2b_prove_submit_nowait(ctx: *mut p2b_ctx, circuit: *const p2b_circuit, constants_sigmas: *const p2b_batch,
+        circuit_digest: *const u64, wire_cols: *const *const u64, public_inputs: *const u64, n_public_inputs: usize,
+        params: *const p2b_fri_params) -> c_int;
+    pub fn p2b_prove_upload_poll(ctx: *mut p2b_ctx) -> c_int;
     pub fn p2b_prove_collect(ctx: *mut p2b_ctx, proof_out: *mut u64, proof_cap: usize) -> c_int;
     pub fn p2b_plan_info(ctx: *mut p2b_ctx, n_ready: *mut u32, n_seen: *mut u32, n_failed: *mut u32, kernels_per_launch: *mut u32) -> c_int;
     pub fn p2b_batch_attach(ctx: *mut p2b_ctx, src: *const p2b_batch, out: *mut *mut p2b_batch) -> c_int;
@@ -316,6 +320,34 @@ pub fn prove_submit<'a>(ctx: &'a Context, circuit: &Circuit, constants_sigmas: &
     };
     ctx.check(rc)?;
     Ok(PendingProof { ctx, len })
+}
+/// `p2b_prove_submit_nowait`: no wait for the upload of pinned witness columns — the form for ONE thread that keeps many
+/// contexts busy (an upload can wait milliseconds behind other contexts' kernels).  The returned proof borrows the
+/// witness until it is collected, so safe code cannot refill the columns while the DMA may still read them.
+pub struct PendingProofBorrowing<'a, 'w> { inner: PendingProof<'a>, _witness: core::marker::PhantomData<&'w [u64]> }
+pub fn prove_submit_nowait<'a, 'w>(ctx: &'a Context, circuit: &Circuit, constants_sigmas: &Batch, circuit_digest: &[u64; 4],
+                                   wire_values: &'w [&'w [u64]], public_inputs: &[u64], params: &p2b_fri_params)
+                                   -> Result<PendingProofBorrowing<'a, 'w>, P2bError> {
+    same_ctx(ctx, circuit, constants_sigmas)?;
+    let (ptrs, _) = column_ptrs(wire_values, Some(circuit.num_wires), Some(1usize << circuit.degree_bits))?;
+    let len = unsafe { p2b_proof_len(circuit.h, constants_sigmas.h, params, public_inputs.len()) };
+    if len == 0 { return Err(Context::invalid("inconsistent FRI parameters")); }
+    let rc = unsafe {
+        p2b_prove_submit_nowait(ctx.0, circuit.h, constants_sigmas.h, circuit_digest.as_ptr(), ptrs.as_ptr(),
+                                public_inputs.as_ptr(), public_inputs.len(), params)
+    };
+    ctx.check(rc)?;
+    Ok(PendingProofBorrowing { inner: PendingProof { ctx, len }, _witness: core::marker::PhantomData })
+}
+impl<'a, 'w> PendingProofBorrowing<'a, 'w> {
+    /// true once the witness has been read by the device
+    pub fn upload_finished(&self) -> Result<bool, P2bError> {
+        let rc = unsafe { p2b_prove_upload_poll(self.inner.ctx.0) };
+        if rc < 0 { self.inner.ctx.check(rc)?; }
+        Ok(rc == 1)
+    }
+    pub fn is_finished(&self) -> Result<bool, P2bError> { self.inner.is_finished() }
+    pub fn collect(self) -> Result<Vec<u64>, P2bError> { self.inner.collect() }
 }
 impl<'a> PendingProof<'a> {
     pub fn is_finished(&self) -> Result<bool, P2bError> {

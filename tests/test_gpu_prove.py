@@ -187,6 +187,42 @@ def test_one_thread_drives_several_contexts(m):
         c.close()
 
 
+def test_submit_nowait_with_pinned_witness(m):
+    """p2b_prove_submit_nowait / p2b_prove_upload_poll: the driver-thread form (no wait for the upload inside submit).  Two
+    contexts with pinned witness matrices; the upload poll turns true, the buffer is refilled only after that, and every
+    proof equals the oracle's."""
+    fp = dict(FP_SMALL, cap_height=3, proof_of_work_bits=8)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], fp["reduction_arity_bits"])
+    circ, digest, pis = make_case(9, CITY_GATES, CITY_GROUPS, 83)
+    ctxs = [m.Context(0) for _ in range(2)]
+    cds = [m.CircuitData(c, circ.desc()) for c in ctxs]
+    css = [m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"], keep_values=True)
+           for c in ctxs]
+    pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), fp)
+    shape = np.stack(circ.wire_values()).shape
+    bufs = [c.pinned_empty(shape) for c in ctxs]
+    assert m.prove_upload_poll(ctxs[0])  # nothing pending: nothing reads host memory
+    for rnd in range(3):
+        wvs = [circ.wire_values() if (rnd + i) % 2 == 0 else _random_witness(circ, 70 * rnd + i) for i in range(2)]
+        for b, w in zip(bufs, wvs):
+            b[:] = np.stack(w)
+        n_words = [m.prove_submit(c, cd, cs, digest, b, pis, params, wait_upload=False) for c, cd, cs, b in zip(ctxs, cds, css, bufs)]
+        for c in ctxs:
+            while not m.prove_upload_poll(c):
+                pass
+        for b in bufs:
+            b[:] = 0  # the witness has been read: the worker may build the next one in place
+        for c, nw, w in zip(ctxs, n_words, wvs):
+            assert (m.prove_collect(c, nw) == pd.prove(digest, w, pis)).all()
+    for cs in css:
+        cs.free()
+    for cd in cds:
+        cd.free()
+    pd.free()
+    for c in ctxs:
+        c.close()
+
+
 def test_constants_sigmas_export_import_round_trip(ctx, m):
     """p2b_batch_export / p2b_batch_import: the imported batch (coefficients + kept values + cap; LDE
     and tree recomputed on the device) proves the same proof; a flipped byte is rejected through the cap check."""

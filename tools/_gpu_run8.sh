@@ -1,15 +1,13 @@
+# one process, G GPUs: the qbench-shaped replay (dumped DAG) and the aggregation tree; usage: bash tools/_gpu_run8.sh G
 set -x
-mkdir -p gpurun_out
-N=${1:-8}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_v18_${N}gpu.json 2> gpurun_out/r2_bench_v18_${N}gpu.err; echo "bench$N rc=$?"
-tail -c 400 gpurun_out/r2_bench_v18_${N}gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/r2_bench_v18_${N}gpu_reference.json 2> gpurun_out/r2_bench_v18_${N}gpu_reference.err; echo "ref$N rc=$?"
+G=${1:-8}
+python tools/dump_prove_case.py gpurun_out/prove_case.bin 12 2>&1 | tail -1
+python tools/dump_prove_case.py gpurun_out/prove_case13.bin 13 2>&1 | tail -1
+g++ -O2 -std=c++17 -I. tools/qbench_replay.cpp -Lcity_rollup_b200 -lp2b -lpthread -Wl,-rpath,$PWD/city_rollup_b200 -o tools/qbench_replay
 nproc
-python - <<PY
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r2_bench_v18_${N}gpu*.json')):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, d['n_gpus'], round(d['value'],2), round(d['e2e']['value'],2), d['e2e'].get('pageable_value'), d.get('launches_per_proof'), d.get('cpu_baseline',{}).get('cores'))
-    except Exception as e: print(f, 'ERR', e)
-PY
+./tools/qbench_replay -i gpurun_out/prove_case.bin -d tests/golden/example_dag.bin -n $((24 * G)) --gpus $G --contexts 24 2>&1 | tee gpurun_out/qbench_replay_${G}gpu_v21.txt
+./tools/qbench_replay -i gpurun_out/prove_case.bin -d tests/golden/example_dag.bin -n $((24 * G)) --gpus $G --contexts 16 2>&1 | tee -a gpurun_out/qbench_replay_${G}gpu_v21.txt
+./tools/qbench_replay -i gpurun_out/prove_case.bin -d tests/golden/example_dag.bin -n $((24 * G)) --gpus $G --async 8 2>&1 | tee -a gpurun_out/qbench_replay_${G}gpu_v21.txt
+./tools/qbench_replay -i gpurun_out/prove_case13.bin -n 1 --agg-tree 10 --gpus $G --contexts 8 2>&1 | tee gpurun_out/agg_tree_${G}gpu_v21.txt
+./tools/qbench_replay -i gpurun_out/prove_case13.bin -n 1 --agg-tree 10 --gpus $G --contexts 16 2>&1 | tee -a gpurun_out/agg_tree_${G}gpu_v21.txt
+rm -f gpurun_out/prove_case.bin gpurun_out/prove_case13.bin

@@ -533,6 +533,9 @@ int main(int argc, char** argv) {
             warm++;
             while (!go.load()) std::this_thread::yield();
             struct Slot { bool busy = false; int b = 0, j = 0, left = 0; size_t len = 0; std::chrono::steady_clock::time_point t0; };
+            double t_submit = 0, t_collect = 0, t_finish = 0;  // where the driver thread's own time goes (stderr at the end)
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(now() - a).count(); };
             std::vector<Slot> slots(K);
             int in_flight = 0;
             for (;;) {
@@ -541,17 +544,23 @@ int main(int argc, char** argv) {
                 Slot& sl = slots[k];
                 if (sl.busy) {
                   if (!prove_poll(*ctxs[k])) continue;
+                  auto tc = now();
                   auto words = prove_collect(*ctxs[k], sl.len);
+                  t_collect += since(tc);
                   if (words != cs.expected) mismatches++;
                   progressed = true;
                   if (--sl.left > 0) {  // the job's next proof (minifier chain): dependent on this one in the reference
-                    sl.len = prove_submit(*ctxs[k], *circuits[k], cs_of(k), cs.digest, witnesses[k]->pointers(), cs.public_inputs, cs.params);
+                    auto ts = now();
+                    sl.len = prove_submit_nowait(*ctxs[k], *circuits[k], cs_of(k), cs.digest, witnesses[k]->pointers(), cs.public_inputs, cs.params);
+                    t_submit += since(ts);
                     continue;
                   }
                   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - sl.t0).count();
                   sl.busy = false;
                   in_flight--;
+                  auto tf = now();
                   finish_job(w, sl.b, sl.j, proof_to_bincode(shape, cs.params, words), sec);
+                  t_finish += since(tf);
                 }
                 if (!sl.busy) {
                   std::pair<int, int> item;
@@ -563,11 +572,16 @@ int main(int argc, char** argv) {
                     continue;
                   }
                   sl = Slot{true, item.first, item.second, job.n_proofs, 0, std::chrono::steady_clock::now()};
-                  sl.len = prove_submit(*ctxs[k], *circuits[k], cs_of(k), cs.digest, witnesses[k]->pointers(), cs.public_inputs, cs.params);
+                  auto ts = now();
+                  sl.len = prove_submit_nowait(*ctxs[k], *circuits[k], cs_of(k), cs.digest, witnesses[k]->pointers(), cs.public_inputs, cs.params);
+                  t_submit += since(ts);
                   in_flight++;
                 }
               }
-              if (in_flight == 0 && jobs_done.load() == total_jobs) break;
+              if (in_flight == 0 && jobs_done.load() == total_jobs) {
+                fprintf(stderr, "driver %d: submit %.3f s, collect %.3f s, store / queue %.3f s\n", w, t_submit, t_collect, t_finish);
+                break;
+              }
               if (!progressed) {
                 if (in_flight == 0) {
                   std::pair<int, int> item;
