@@ -204,6 +204,17 @@ inline std::pair<std::vector<MerkleTree>, std::vector<Ext>> fri_committed_trees(
 }
 
 // fri::prover::fri_proof_of_work(challenger, config) — returns the minimal witness
+// get_circuit_fingerprint_generic(verifier_data) = hash_no_pad(constants_sigmas_cap || circuit_digest)
+// (city_common_circuit/src/proof_minifier/pm_core.rs:18-42): the name City Rollup gives a circuit (whitelist leaves,
+// allowed_fingerprints of the aggregators)
+inline HashOut circuit_fingerprint(const Context& ctx, const PolynomialBatch& constants_sigmas, const HashOut& circuit_digest) {
+  std::vector<F> all;
+  for (const HashOut& h : constants_sigmas.merkle_tree().cap()) all.insert(all.end(), h.begin(), h.end());
+  all.insert(all.end(), circuit_digest.begin(), circuit_digest.end());
+  HashOut out{};
+  ctx.check(p2b_hash_no_pad(ctx.get(), all.data(), all.size(), out.data()));
+  return out;
+}
 inline F fri_proof_of_work(const Context& ctx, Challenger& challenger, uint32_t proof_of_work_bits) {
   F w = 0;
   ctx.check(p2b_fri_pow(ctx.get(), challenger.get(), proof_of_work_bits, &w));

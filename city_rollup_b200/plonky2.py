@@ -622,6 +622,15 @@ def prove_native(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire
     return parse_proof_words(circuit.desc, cs, fri_params, buf, len(public_inputs))
 
 
+def circuit_fingerprint(ctx, constants_sigmas_commitment, circuit_digest):
+    """get_circuit_fingerprint_generic(verifier_data) = hash_no_pad(constants_sigmas_cap ‖ circuit_digest)
+    (city_common_circuit/src/proof_minifier/pm_core.rs:18-42; the in-circuit twin: builder/verify.rs:41-53): how City
+    Rollup names a circuit — the leaves of the sighash whitelist tree and the `allowed_fingerprints` of the aggregators.
+    Computed on the device from the batch's cap."""
+    cap = np.asarray(constants_sigmas_commitment.cap, dtype=np.uint64).reshape(-1)
+    return ctx.hash_no_pad(np.concatenate([cap, _felts(circuit_digest)]))
+
+
 def prove_submit(ctx, circuit, constants_sigmas_commitment, circuit_digest, wire_values, public_inputs, fri_params, wait_upload=True):
     """p2b_prove_submit: enqueue the whole proof and return; `wire_values` may be reused at once.  -> number of proof
     words to hand to prove_collect.  One proof may be pending per context.  wait_upload=False is

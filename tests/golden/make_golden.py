@@ -4,7 +4,7 @@
 This script is the ONLY thing in the repo that reads /root/reference, and it is
 never run by tests, smoke() or bench.py (the GPU box has no /root/reference).
 It extracts, verbatim, the known-answer data the reference holds for the
-Plonky2 hot path (SURVEY.md §8(c), K1..K5):
+Plonky2 hot path (SURVEY.md §8(c), K1..K6):
 
   K1/K2  city_crypto/src/hash/cached_zero_hashes.rs:10-1036, :1039-2066
          -> zero_hashes.json  {"zero": [[4 u64] x128], "marked": [[4 u64] x128]}
@@ -12,6 +12,8 @@ Plonky2 hot path:
          -> example_proofs.bin (concatenated proof blobs) + example_proofs.json (index)
   K4/K5  city_common_circuit/src/circuits/zk_signature2/mod.rs:31-145
          -> circuit_params.json (FRI/Plonk parameters + the 80 k_is)
+  K6     city_rollup_common/src/config/sighash_wrapper_config.rs:16-23 (whitelist root), :24-1900 (1 875 circuit fingerprints)
+         -> sighash_whitelist.json {"root": [4 u64], "fingerprints": [[4 u64] x1875]}
   DAG    qbench_data/example.bin's job ids, level counters, goals and next-job lists
          -> example_dag.bin (the dump with witness / proof payloads stripped; read by tools/qbench_replay.cpp)
 
@@ -125,7 +127,28 @@ def circuit_params():
     }
 
 
+def sighash_whitelist():
+    """The root of the sighash-circuit whitelist tree and the 1 875 circuit fingerprints it is built from
+    (city_store/src/store/sighash/mod.rs:44-75: leaf i of a height-16 zero-hash Merkle tree = the fingerprint of the i-th
+    gadget id in SORTED order; the tests rebuild the order from the id generator,
+    city_rollup_common/src/introspection/rollup/introspection.rs:402-431, and derive(Ord) on the id's fields, :156-163)."""
+    src = open(os.path.join(REF, "city_rollup_common/src/config/sighash_wrapper_config.rs")).read()
+    a = src.index("SIGHASH_WHITELIST_TREE_ROOT")
+    b = src.index("SIGHASH_CIRCUIT_FINGERPRINTS")
+    e = src.index("];", b)
+    root = [int(x) for x in re.findall(r"GoldilocksField\((\d+)\)", src[a:b])]
+    nums = [int(x) for x in re.findall(r"GoldilocksField\((\d+)\)", src[b:e])]
+    assert len(root) == 4 and len(nums) == 4 * 1875, (len(root), len(nums))
+    height = int(re.search(r"SIGHASH_CIRCUIT_WHITELIST_TREE_HEIGHT: u8 = (\d+)", src).group(1))
+    md = int(re.search(r"^pub const SIGHASH_CIRCUIT_MAX_DEPOSITS: usize = (\d+)", src, re.M).group(1))
+    mw = int(re.search(r"^pub const SIGHASH_CIRCUIT_MAX_WITHDRAWALS: usize = (\d+)", src, re.M).group(1))
+    return {"source": "city_rollup_common/src/config/sighash_wrapper_config.rs:7,14-23,24-1900", "tree_height": height,
+            "max_deposits": md, "max_withdrawals": mw, "root": root,
+            "fingerprints": [nums[i : i + 4] for i in range(0, len(nums), 4)]}
+
+
 if __name__ == "__main__":
+    json.dump(sighash_whitelist(), open(os.path.join(OUT, "sighash_whitelist.json"), "w"))
     json.dump(zero_hash_tables(), open(os.path.join(OUT, "zero_hashes.json"), "w"))
     blob, idx = example_proofs()
     open(os.path.join(OUT, "example_proofs.bin"), "wb").write(blob)

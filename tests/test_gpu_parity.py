@@ -70,6 +70,33 @@ def test_k1_k2_zero_hash_chains_on_gpu(ctx, golden_dir):
         assert cur[0].tolist() == z["marked"][i], i
 
 
+def test_k6_sighash_whitelist_root_on_gpu(ctx, m, golden_dir):
+    """K6 on the GPU, against the constant the reference holds (not against the oracle): MerkleTree::new over the 2^16
+    leaves of the sighash-circuit whitelist (1 875 real fingerprints + zero hashes), cap_height 0 ->
+    SIGHASH_WHITELIST_TREE_ROOT (city_rollup_common/src/config/sighash_wrapper_config.rs:14-23); the inclusion proof of one
+    fingerprint climbs to it."""
+    from util import sighash_whitelist_leaves
+
+    wl = json.load(open(os.path.join(golden_dir, "sighash_whitelist.json")))
+    leaves = sighash_whitelist_leaves(wl)
+    t = m.MerkleTree.new(ctx, leaves, 0)
+    assert t.cap.shape == (1, 4) and t.cap[0].tolist() == wl["root"]
+    j = 777
+    assert O.merkle_verify(leaves[j], j, t.prove(j), np.array([wl["root"]], dtype=np.uint64))
+    t.free()
+
+
+def test_circuit_fingerprint(ctx, m):
+    """get_circuit_fingerprint_generic (pm_core.rs:18-42) = hash_no_pad(constants_sigmas_cap || circuit_digest)"""
+    cols = [rand_felts(0xF1F0 + c, 1 << 6) for c in range(9)]
+    b = m.PolynomialBatch.from_values(ctx, cols, 3, False, 4)
+    digest = [11, 12, 13, 14]
+    ref = O.batch_from_values(cols, 3, 4)
+    want = O.hash_no_pad(list(ref["cap"].reshape(-1)) + digest)
+    assert m.circuit_fingerprint(ctx, b, digest).tolist() == want.tolist()
+    b.free()
+
+
 def test_hash_no_pad_lengths(ctx):
     for n in (0, 1, 4, 5, 7, 8, 9, 16, 17, 135):
         x = rand_felts(n + 1, n, canonical=False)

@@ -45,6 +45,24 @@ def test_k2_marked_leaf_chain(zero_hashes):
         assert O.two_to_one(t[i - 1], t[i - 1]).tolist() == t[i], i
 
 
+def test_k6_sighash_whitelist_root(golden_dir):
+    """city_rollup_common/src/config/sighash_wrapper_config.rs:14-23: SIGHASH_WHITELIST_TREE_ROOT is the root of a height-16
+    zero-hash Merkle tree over the 1 875 circuit fingerprints of :24-1900 (city_store/src/store/sighash/mod.rs:44-75).  A
+    4-element leaf is its own digest (hash_or_noop) and an empty subtree is the K1 zero hash, so the root is the one-element
+    cap of MerkleTree::new over the 2^16 leaves: 65 535 two_to_one compressions over real data, against a root the reference
+    holds as a constant."""
+    from util import sighash_whitelist_leaves
+
+    wl = json.load(open(os.path.join(golden_dir, "sighash_whitelist.json")))
+    leaves = sighash_whitelist_leaves(wl)
+    digests, cap = O.merkle_tree_new(leaves, 0)
+    assert cap.shape == (1, 4) and cap[0].tolist() == wl["root"]
+    # a whitelist inclusion proof as the wrapper circuit checks it (sighash_wrapper.rs:73-80): 16 siblings up to the root
+    j = 1234
+    siblings = O.merkle_prove(digests, len(leaves), 0, j)
+    assert len(siblings) == wl["tree_height"] and O.merkle_verify(leaves[j], j, siblings, cap)
+
+
 def test_k4_generator_and_roots(params):
     """zk_signature2/mod.rs:58-138: k_is[i] = 7^i; and the derived 2-adic root"""
     for i, k in enumerate(params["k_is"]):

@@ -27,3 +27,23 @@ def bitrev(x, bits):
     for i in range(bits):
         r |= ((x >> i) & 1) << (bits - 1 - i)
     return r
+
+
+def sighash_whitelist_leaves(wl):
+    """The 2^tree_height leaves of the reference's sighash-circuit whitelist tree (tests/golden/sighash_whitelist.json):
+    the gadget ids in the order BlockSpendCoreConfig::generate_id_permutations emits them
+    (city_rollup_common/src/introspection/rollup/introspection.rs:402-431) index the fingerprint table; leaf i is the
+    fingerprint of the i-th id in SORTED order (derive(Ord) over num_deposits, num_withdrawals, last_block_num_deposits,
+    last_block_num_withdrawals, current_spend_index, :156-163; city_store/src/store/sighash/mod.rs:49-66); every other leaf is
+    the zero hash."""
+    import numpy as np
+
+    ni, no = wl["max_deposits"] + 1, wl["max_withdrawals"] + 1
+    ids = [(nd, nw, lbd, lbw, csi) for lbw in range(no) for lbd in range(ni) for nw in range(no) for nd in range(ni)
+           for csi in range(nd + 1)]
+    assert len(ids) == len(wl["fingerprints"])
+    order = sorted(range(len(ids)), key=lambda i: ids[i])
+    leaves = np.zeros((1 << wl["tree_height"], 4), dtype=np.uint64)
+    for i, k in enumerate(order):
+        leaves[i] = wl["fingerprints"][k]
+    return leaves
