@@ -551,6 +551,9 @@ def run_cuda(args):
                   "ntt_lde_ms": ntt2, "leaf_hash_ms": leaf2, "tree_levels_ms": st["tree_levels"] / 3,
                   "ntt_lde_hbm_frac": lde_b / (ntt2 * 1e-3) / 1e9 / hbm_peak,
                   "ntt_lde_dram_traffic": traffic.get("ntt_2p20"),
+                  # the transforms are bound by integer issue, not by HBM: executed instructions (ncu) / measured time / peak
+                  "ntt_lde_int32_frac_executed": ((traffic.get("ntt_2p20") or {}).get("executed_thread_instructions", 0.0)
+                                                  / (ntt2 * 1e-3) / 1e9 / int_peak) or None,
                   "whole_commit_hbm_frac": ab / (min(times[1:]) * 1e-3) / 1e9 / hbm_peak,
                   "poseidon_int32_frac": leaf_perms * OPS_PER_PERM / (leaf2 * 1e-3) / 1e9 / int_peak,
                   "leaf_hash_gperm_s": leaf_perms / (leaf2 * 1e-3) / 1e9,
