@@ -1,5 +1,5 @@
 """Pin the CPU oracle to every known answer the reference tree holds for the hot path
-(SURVEY.md §8(c) K1..K5).  CPU-only."""
+(SURVEY.md §8(c) K1..K6).  CPU-only."""
 import json
 import os
 
