@@ -23,6 +23,7 @@ SIGNATURES = {
     "p2b_last_error": (C.c_char_p, [vp]),
     "p2b_synchronize": (C.c_int, [vp]),
     "p2b_set_blocking_sync": (C.c_int, [vp, C.c_int]),
+    "p2b_set_latency_mode": (C.c_int, [vp, C.c_int]),
     "p2b_host_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
     "p2b_host_free": (C.c_int, [vp, vp]),
     "p2b_launch_count": (u64, [vp]),

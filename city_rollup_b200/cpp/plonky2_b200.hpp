@@ -39,6 +39,8 @@ class Context {
   p2b_ctx* get() const { return h_; }
   // sleep instead of spinning while waiting for the device (more proving threads than host cores)
   void set_blocking_sync(bool on) const { check(p2b_set_blocking_sync(h_, on ? 1 : 0)); }
+  // one proof at a time on this GPU: shorter launch chains for more work (p2b.h); the default is throughput mode
+  void set_latency_mode(bool on) const { check(p2b_set_latency_mode(h_, on ? 1 : 0)); }
 
  private:
   p2b_ctx* h_ = nullptr;

@@ -73,6 +73,9 @@ struct p2b_ctx {
   // host waits: spin (cudaStreamSynchronize, lowest latency, one busy core per waiting thread) or sleep on a
   // blocking-sync event (p2b_set_blocking_sync: many contexts per host core)
   bool blocking_sync = false;
+  // p2b_set_latency_mode: one proof at a time on this GPU — the Merkle trees fused from 2^15 digests (12 launches less per
+  // proof) and the proof-of-work search on every SM (one stride of candidates covers the mean); see the setter
+  bool latency_mode = false;
   cudaEvent_t ev_block = nullptr;
   bool poisoned = false;
   std::string err;
@@ -385,6 +388,7 @@ static int init_common(int device, void* stream, bool borrow, p2b_ctx** out) {
   if (!ctx) return fail(nullptr, P2B_ERR_OOM, "host allocation failed");
   ctx->device = device;
   if (const char* m = getenv("P2B_SYNC")) ctx->blocking_sync = m[0] == 'b' || m[0] == 'B';  // P2B_SYNC=block | spin
+  if (const char* m = getenv("P2B_MODE")) ctx->latency_mode = m[0] == 'l' || m[0] == 'L';    // P2B_MODE=latency | throughput
   if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0)
     ctx->sm_count = 148;
   if (borrow) {
@@ -458,6 +462,24 @@ extern "C" const char* p2b_last_error(const p2b_ctx* ctx) { return ctx ? ctx->er
 extern "C" int p2b_set_blocking_sync(p2b_ctx* ctx, int on) {
   CHECK_CTX(ctx);
   ctx->blocking_sync = on != 0;
+  return P2B_OK;
+}
+
+// Throughput mode (default) sizes every launch for many proofs in flight on the GPU: what counts is the instructions a
+// proof executes and the registers its CTAs hold.  Latency mode is for a worker that has the GPU to itself (the reference's
+// one-job-at-a-time worker with no sibling processes on the device): dependent launch chains are shortened at the price of
+// work — the Merkle trees are climbed by the fused subtree kernel from 2^15 digests up (12 launches less per 2^12-row
+// proof; with 24 proofs in flight that costs 9 % throughput, profiles/r02_tree_fuse_sweep.txt) and the proof-of-work
+// search runs one CTA per SM (one stride covers the mean of the 16-bit search; ~2x the necessary permutations).  Measured
+// on one context at the City shape: 3.71 -> 3.35 ms per proof (269 -> 298 proofs/s).  Results are identical in both modes.
+extern "C" int p2b_set_latency_mode(p2b_ctx* ctx, int on) {
+  CHECK_CTX(ctx);
+  if (ctx->pending_words) return fail(ctx, P2B_ERR_INVALID, "a submitted proof has not been collected yet");
+  if (ctx->latency_mode != (on != 0)) {
+    CU(ctx, ctx_sync(ctx));
+    plans_clear(ctx);  // captured prove plans hold the launch configuration of the other mode
+    ctx->latency_mode = on != 0;
+  }
   return P2B_OK;
 }
 
@@ -934,8 +956,9 @@ static int build_levels(p2b_ctx* ctx, p2b_tree* t) {
       const int v = e ? atoi(e) : 11;
       return (uint32_t)(v < 1 ? 1 : v > 24 ? 24 : v);
     }();
+    const uint32_t fuse_log_eff = ctx->latency_mode && fuse_log < 15 ? 15 : fuse_log;
     uint32_t i = 0;
-    while (i < L && (t->n_leaves >> i) > ((size_t)1 << fuse_log)) {
+    while (i < L && (t->n_leaves >> i) > ((size_t)1 << fuse_log_eff)) {
       const size_t n_par = t->n_leaves >> (i + 1);
       hashk::k_tree_level<<<cdiv(n_par, hash_block()), hash_block(), 0, ctx->stream>>>(t->d_levels + 4 * level_off(t->n_leaves, i),
                                                                       t->d_levels + 4 * level_off(t->n_leaves, i + 1), n_par);
@@ -2502,6 +2525,7 @@ static int fri_pow_dev(p2b_ctx* ctx, p2b_challenger* ch, uint32_t pow_bits, uint
   }();
   uint64_t blocks = (((uint64_t)1 << pow_bits) / 8 + 255) / 256;
   blocks = blocks < 16 ? 16 : blocks > sms ? sms : blocks;
+  if (ctx->latency_mode) blocks = sms;
   if (force_blocks > 0) blocks = (uint64_t)force_blocks;
   CU(ctx, cudaMemsetAsync(d_best, 0xFF, sizeof(uint64_t), ctx->stream));
   frik::k_pow_search<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ch->d_state, 0, GL_P, pow_bits, d_best);

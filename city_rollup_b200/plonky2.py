@@ -60,6 +60,11 @@ class Context:
         """sleep instead of spinning while waiting for the device (many proving threads per host core)"""
         self.check(self.lib.p2b_set_blocking_sync(self.h, 1 if on else 0))
 
+    def set_latency_mode(self, on=True):
+        """p2b_set_latency_mode: this worker has the GPU to itself (one proof at a time) — shorter launch chains for more
+        work; the default is throughput mode (many proofs in flight per GPU).  Same results."""
+        self.check(self.lib.p2b_set_latency_mode(self.h, 1 if on else 0))
+
     def synchronize(self):
         self.check(self.lib.p2b_synchronize(self.h))
 

@@ -65,6 +65,12 @@ int p2b_synchronize(p2b_ctx *ctx);
  * sleeps on a blocking-sync event, for hosts that run more proving threads than they have cores (several contexts
  * per GPU times several GPUs).  The environment variable P2B_SYNC=block|spin sets the default of new contexts. */
 int p2b_set_blocking_sync(p2b_ctx *ctx, int on);
+/* Latency mode: for a worker that has the GPU to itself (one job at a time, no sibling worker processes on the device —
+ * city_rollup_core_worker/src/actors/simple.rs:32-56 run as a single process per GPU).  Dependent launch chains are
+ * shortened at the price of extra work (Merkle trees fused from 2^15 digests, proof-of-work search on every SM): 3.71 ->
+ * 3.35 ms per 2^12-row proof on one context; with many proofs in flight the default (throughput mode) is ~10 % faster
+ * per GPU.  Same results in both modes.  Also P2B_MODE=latency in the environment.  Drops the context's prove plans. */
+int p2b_set_latency_mode(p2b_ctx *ctx, int on);
 /* Pinned host memory for inputs/outputs that should move by DMA without staging. */
 int p2b_host_alloc(p2b_ctx *ctx, size_t bytes, void **out);
 int p2b_host_free(p2b_ctx *ctx, void *p);

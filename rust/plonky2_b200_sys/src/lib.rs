@@ -37,6 +37,7 @@ extern "C" {
     pub fn p2b_version() -> c_int;
     pub fn p2b_init(device: c_int, out: *mut *mut p2b_ctx) -> c_int;
     pub fn p2b_set_blocking_sync(ctx: *mut p2b_ctx, on: c_int) -> c_int;
+    pub fn p2b_set_latency_mode(ctx: *mut p2b_ctx, on: c_int) -> c_int;
     pub fn p2b_init_on_stream(device: c_int, stream: *mut c_void, out: *mut *mut p2b_ctx) -> c_int;
     pub fn p2b_destroy(ctx: *mut p2b_ctx);
     pub fn p2b_last_error(ctx: *const p2b_ctx) -> *const c_char;
@@ -190,6 +191,11 @@ impl Context {
         Ok(Context(h))
     }
     pub fn raw(&self) -> *mut p2b_ctx { self.0 }
+    /// Waiting threads sleep instead of spinning (several proving threads per host core).
+    pub fn set_blocking_sync(&self, on: bool) -> Result<(), P2bError> { self.check(unsafe { p2b_set_blocking_sync(self.0, on as c_int) }) }
+    /// This worker has the GPU to itself (one job at a time, `simple.rs:32-56` as the only process on the device):
+    /// shorter launch chains for more work.  The default is throughput mode.
+    pub fn set_latency_mode(&self, on: bool) -> Result<(), P2bError> { self.check(unsafe { p2b_set_latency_mode(self.0, on as c_int) }) }
     pub fn check(&self, rc: c_int) -> Result<(), P2bError> {
         if rc == 0 { Ok(()) } else { Err(P2bError { code: rc, message: last_error(self.0) }) }
     }

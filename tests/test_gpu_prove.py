@@ -223,6 +223,32 @@ def test_submit_nowait_with_pinned_witness(m):
         c.close()
 
 
+def test_latency_mode_proofs_equal_throughput_mode(m):
+    """p2b_set_latency_mode: other launch configurations (trees fused from 2^15 digests, proof-of-work search on every SM),
+    the same proof words — eagerly, from a captured plan, and after switching back (the switch drops the plans)"""
+    fp = dict(FP_SMALL, cap_height=3, proof_of_work_bits=10)
+    params = m.FriParams(fp["rate_bits"], fp["cap_height"], fp["proof_of_work_bits"], fp["num_query_rounds"], fp["reduction_arity_bits"])
+    circ, digest, pis = make_case(10, CITY_GATES, CITY_GROUPS, 85)
+    c = m.Context(0)
+    cd = m.CircuitData(c, circ.desc())
+    cs = m.PolynomialBatch.from_values(c, circ.constants_sigmas_values(), fp["rate_bits"], False, fp["cap_height"], keep_values=True)
+    pd = O.ProverData(circ.desc(), circ.constants_sigmas_values(), fp)
+    want = pd.prove(digest, circ.wire_values(), pis)
+    for mode in (True, True, False, True):
+        c.set_latency_mode(mode)
+        for _ in range(3):  # eager, capture, replay
+            got = m.prove_native(c, cd, cs, digest, circ.wire_values(), pis, params, raw=True)
+            assert (got == want).all(), mode
+    n = m.prove_submit(c, cd, cs, digest, np.stack(circ.wire_values()), pis, params)
+    with pytest.raises(m.P2BError):
+        c.set_latency_mode(False)  # a proof is pending
+    assert (m.prove_collect(c, n) == want).all()
+    cs.free()
+    cd.free()
+    pd.free()
+    c.close()
+
+
 def test_constants_sigmas_export_import_round_trip(ctx, m):
     """p2b_batch_export / p2b_batch_import: the imported batch (coefficients + kept values + cap; LDE
     and tree recomputed on the device) proves the same proof; a flipped byte is rejected through the cap check."""
