@@ -436,20 +436,23 @@ def run_cuda(args):
         st_ms, st_cnt = c.profile_read()
         c.profile_enable(False)
         # the same worker in latency mode (p2b_set_latency_mode: it has the GPU to itself)
-        c.set_latency_mode(True)
-        for _ in range(3):
-            farm.prove_one(0, "dev")
-        best_lat = 1e30
-        for _ in range(3):
-            c.timer_start()
-            for _ in range(n1):
+        best_lat = None
+        try:
+            c.set_latency_mode(True)
+            for _ in range(3):
                 farm.prove_one(0, "dev")
-            best_lat = min(best_lat, c.timer_stop_ms() / n1)
-        c.set_latency_mode(False)
+            best_lat = 1e30
+            for _ in range(3):
+                c.timer_start()
+                for _ in range(n1):
+                    farm.prove_one(0, "dev")
+                best_lat = min(best_lat, c.timer_stop_ms() / n1)
+        finally:
+            c.set_latency_mode(False)
         c.set_blocking_sync(n_ctx > 1)
         single = {"proofs_per_s": 1e3 / best, "ms_per_proof": best, "note": "one context, one proof at a time (spin wait), best of 3 x 24",
                   "stage_ms_per_proof": {k: v / n1 for k, v in st_ms.items() if v},
-                  "latency_mode": {"proofs_per_s": 1e3 / best_lat, "ms_per_proof": best_lat,
+                  "latency_mode": {"proofs_per_s": 1e3 / best_lat if best_lat else None, "ms_per_proof": best_lat,
                                    "note": "p2b_set_latency_mode(ctx, 1): Merkle trees fused from 2^15 digests, proof-of-work "
                                            "search on every SM — for a worker that has the GPU to itself"}}
         pp = perms_per_proof(circ.desc())
